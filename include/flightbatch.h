@@ -1,0 +1,230 @@
+/* flightbatch.h — C ABI of the B200-native batched C172 flight-dynamics engine.
+ *
+ * Drop-in boundary for ONE path of e271828e/Flight.jl: N independent
+ * `Simulation(SimpleWorld(Cessna172...))` objects stepped in lock-step with the
+ * reference's fixed-step RK4 + discrete callbacks.  Each entry point names the
+ * reference interface it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every function returns int32: 0 = ok, <0 = API misuse or CUDA error
+ *     (text via fb_last_error(), thread-local, valid until the next call);
+ *   - per-member physics terminations are NOT API errors: they set status[i]
+ *     (FB_ST_*) and freeze that member (reference: SimulationTermination,
+ *     lib/FlightCore/src/sim.jl:32,561-570);
+ *   - host arrays are struct-of-arrays, member index fastest: a field with C
+ *     components is `double a[C][N]` (a Julia `Matrix{Float64}(undef, N, C)`);
+ *   - the caller owns every host pointer; the library owns all device memory;
+ *   - one handle = one owner thread at a time; there is NO CPU fallback: every
+ *     entry point that computes fails with FB_ERR_CUDA when no device exists.
+ */
+#ifndef FLIGHTBATCH_H
+#define FLIGHTBATCH_H
+#include <stdint.h>
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB_API_VERSION 1
+
+/* error codes */
+#define FB_OK 0
+#define FB_ERR_ARG (-1)
+#define FB_ERR_CUDA (-2)
+#define FB_ERR_STATE (-3)   /* call out of order (e.g. step before init) */
+#define FB_ERR_ALLOC (-4)
+
+/* aircraft variant: lib/FlightApps/src/c172/c172s/c172s0.jl:14-18, c172x/c172x{0,1,2}.jl */
+#define FB_C172S 0   /* Cessna172Sv0: mechanical actuation, NoAvionics          */
+#define FB_C172X0 1  /* Cessna172Xv0: fly-by-wire actuators, NoAvionics         */
+#define FB_C172X1 2  /* Cessna172Xv1: + C172XControl.ControlLaws                */
+#define FB_C172X2 3  /* Cessna172Xv2: + guidance (ModeGuidance.direct pass-through) */
+/* kinematic mechanisation: lib/FlightPhysics/src/kinematics.jl:150,250,329 */
+#define FB_WA 0
+#define FB_ECEF 1
+#define FB_NED 2
+
+/* per-member status */
+#define FB_ST_RUNNING 0
+#define FB_ST_DONE 1
+#define FB_ST_CRASH_ANGLE 2    /* landinggear.jl:336-339  strut/terrain angle > 60 deg   */
+#define FB_ST_CRASH_RATE 3     /* landinggear.jl:340-343  damper compression > 10 m/s     */
+#define FB_ST_BOUNDS 4         /* geodesy.jl:218-221, atmosphere.jl:133, geodesy.jl:83-86 */
+#define FB_ST_CONTACT_ASSERT 5 /* landinggear.jl:321                                      */
+#define FB_ST_TRIM_FAILED 6    /* c172.jl:934-940 (warning + success=false)               */
+
+/* engine discrete state, lib/FlightPhysics/src/piston.jl:199-203 */
+#define FB_ENG_OFF 0
+#define FB_ENG_STARTING 1
+#define FB_ENG_RUNNING 2
+
+/* ---- input fields (fb_set_input / fb_get_input / fb_schedule_inputs) --------------------
+ * Values are doubles; Bool/enum inputs use 0/1/2.  Ranged inputs saturate on assignment
+ * exactly like the reference's `Ranged` (lib/FlightPhysics/src/types.jl:15-20).            */
+enum fb_input {
+    /* C172S MechanicalActuation.u, c172s.jl:62-72 */
+    FB_U_AILERON = 0, FB_U_ELEVATOR, FB_U_RUDDER, FB_U_AILERON_OFFSET, FB_U_ELEVATOR_OFFSET, FB_U_RUDDER_OFFSET,
+    FB_U_FLAPS, FB_U_BRAKE_LEFT, FB_U_BRAKE_RIGHT,
+    /* PistonEngine.u, piston.jl:259-267 (throttle is an input only for C172S; C172X drives it through its actuator) */
+    FB_U_THROTTLE = 9, FB_U_MIXTURE, FB_U_ENG_START, FB_U_ENG_STOP, FB_U_MIXTURE_AUTO,
+    FB_U_STEERING_ENGAGED = 14, /* landinggear.jl:45-48 */
+    /* Payload.u, c172.jl:521-527 */
+    FB_U_M_PILOT = 15, FB_U_M_COPILOT, FB_U_M_LPASS, FB_U_M_RPASS, FB_U_M_BAGGAGE,
+    /* SimpleAtmosphere: TunableSeaLevel.u (atmosphere.jl:75-78), TunableWind.u (:165) */
+    FB_U_T_SL = 20, FB_U_P_SL, FB_U_WIND_N, FB_U_WIND_E, FB_U_WIND_D,
+    /* HorizontalTerrain: elevation (terrain.jl:34-36), surface type u[] (:38) 0 dry 1 wet 2 icy */
+    FB_U_TRN_ELEVATION = 25, FB_U_TRN_SURFACE,
+    /* C172X FlyByWireActuation commands, c172x.jl:112-120 (written by the control laws for X1/X2) */
+    FB_U_ACT_THROTTLE = 27, FB_U_ACT_AILERON, FB_U_ACT_ELEVATOR, FB_U_ACT_RUDDER, FB_U_ACT_FLAPS,
+    FB_U_ACT_BRAKE_LEFT, FB_U_ACT_BRAKE_RIGHT,
+    /* C172XControl.ControlLawsLon.u, c172x_ctl.jl:226-237 */
+    FB_U_LON_MODE_REQ = 40, FB_U_LON_THROTTLE_AXIS, FB_U_LON_THROTTLE_OFFSET, FB_U_LON_ELEVATOR_AXIS, FB_U_LON_ELEVATOR_OFFSET,
+    FB_U_LON_Q_REF, FB_U_LON_THETA_REF, FB_U_LON_EAS_REF, FB_U_LON_CLM_REF, FB_U_LON_H_REF,
+    /* C172XControl.ControlLawsLat.u, c172x_ctl.jl:826-836 */
+    FB_U_LAT_MODE_REQ = 60, FB_U_LAT_AILERON_AXIS, FB_U_LAT_AILERON_OFFSET, FB_U_LAT_RUDDER_AXIS, FB_U_LAT_RUDDER_OFFSET,
+    FB_U_LAT_P_REF, FB_U_LAT_BETA_REF, FB_U_LAT_PHI_REF, FB_U_LAT_CHI_REF,
+    /* remaining C172XControl.ControlLaws.u pass-throughs, c172x_ctl.jl:1190-1200 */
+    FB_U_CTL_FLAPS = 70, FB_U_CTL_BRAKE_LEFT, FB_U_CTL_BRAKE_RIGHT, FB_U_CTL_ENG_START, FB_U_CTL_ENG_STOP, FB_U_CTL_MIXTURE,
+    FB_U__COUNT = 80
+};
+
+/* ---- output fields (fb_get_output / fb_log_* / fb_stats) --------------------------------
+ * Scalars of the root `y` the reference saves each step (sim.jl:345-347); names follow the
+ * reference's dotted path under `y.aircraft.vehicle`.                                     */
+enum fb_output {
+    FB_Y_PSI = 0, FB_Y_THETA, FB_Y_PHI,            /* kinematics.e_nb                       */
+    FB_Y_LAT, FB_Y_LON, FB_Y_H_E, FB_Y_H_O,        /* kinematics.ϕ_λ, h_e, h_o              */
+    FB_Y_V_N, FB_Y_V_E, FB_Y_V_D,                  /* kinematics.v_eb_n                     */
+    FB_Y_V_GND, FB_Y_CHI_GND, FB_Y_GAMMA_GND,
+    FB_Y_P, FB_Y_Q, FB_Y_R,                        /* kinematics.ω_wb_b                     */
+    FB_Y_TAS, FB_Y_EAS, FB_Y_CAS, FB_Y_MACH, FB_Y_QBAR, /* airflow                          */
+    FB_Y_ALPHA, FB_Y_BETA, FB_Y_ALPHA_FILT, FB_Y_BETA_FILT, FB_Y_STALL, FB_Y_C_L, FB_Y_C_D, /* systems.aero */
+    FB_Y_WOW_LEFT, FB_Y_WOW_RIGHT, FB_Y_WOW_NOSE,  /* systems.ldg.*.strut.wow               */
+    FB_Y_XI_LEFT, FB_Y_XI_RIGHT, FB_Y_XI_NOSE,     /* systems.ldg.*.strut.ξ                 */
+    FB_Y_FDMP_LEFT, FB_Y_FDMP_RIGHT, FB_Y_FDMP_NOSE,
+    FB_Y_ENG_OMEGA, FB_Y_ENG_STATE, FB_Y_ENG_MAP, FB_Y_ENG_P_SHAFT, FB_Y_ENG_TAU_SHAFT, FB_Y_ENG_MDOT, /* systems.pwp.engine */
+    FB_Y_FUEL_M_TOTAL,                             /* systems.fuel.m_total                  */
+    FB_Y_PROP_THRUST, FB_Y_PROP_J,                 /* systems.pwp.propeller.wr_p.F[1], J    */
+    FB_Y_MASS,                                     /* dynamics.mp_Σ_b.m                     */
+    FB_Y_F_X, FB_Y_F_Y, FB_Y_F_Z,                  /* dynamics.f_c_c (specific force)       */
+    FB_Y_LON_MODE, FB_Y_LAT_MODE,                  /* avionics.ctl.lon.mode / lat.mode      */
+    FB_Y_THROTTLE_CMD, FB_Y_ELEVATOR_CMD, FB_Y_AILERON_CMD, FB_Y_RUDDER_CMD,
+    FB_Y__COUNT
+};
+
+typedef struct fb_sim* fb_handle;
+
+/* Simulation(mdl; dt, Δt, t_start, t_end, saveat) — lib/FlightCore/src/sim.jl:183-196 */
+typedef struct fb_config {
+    int32_t variant;        /* FB_C172*                                             */
+    int32_t kinematics;     /* FB_WA / FB_ECEF / FB_NED                             */
+    int64_t n_members;      /* members held by THIS handle (one handle per GPU)     */
+    int64_t member_offset;  /* global index of member 0 (sharding; used by RNG-free bookkeeping only) */
+    double dt;              /* RK4 step (reference default 0.02)                    */
+    double Dt;              /* periodic (avionics) interval; must be k*dt, k>=1     */
+    double t_start, t_end;
+    int32_t device;         /* CUDA device ordinal                                  */
+    int32_t log_every;      /* save outputs every `log_every` steps; 0 = no log (save_on=false) */
+    int32_t log_n_fields;   /* number of entries of log_fields                      */
+    int32_t log_fields[32]; /* fb_output ids to log                                 */
+    int32_t steps_per_launch; /* K: RK4 steps fused per kernel launch (0 = default) */
+} fb_config;
+
+/* C172.TrimParameters — lib/FlightApps/src/c172/c172.jl:806-818, struct-of-arrays; NULL = default */
+typedef struct fb_trim_params_soa {
+    const double* lat;        /* rad */
+    const double* lon;        /* rad */
+    const double* h_e;        /* ellipsoidal altitude, m (default 1050) */
+    const double* psi_nb;     /* heading */
+    const double* EAS;        /* default 50 */
+    const double* gamma_wb_n;
+    const double* psi_wb_dot;
+    const double* theta_wb_dot;
+    const double* beta_a;
+    const double* fuel_load;  /* default 0.5 */
+    const double* mixture;    /* default 0.5 */
+    const double* flaps;      /* default 0   */
+    const double* payload[5]; /* pilot, copilot, lpass, rpass, baggage: default 75,75,0,0,50 */
+} fb_trim_params_soa;
+
+/* C172.Init(KinInit(...), SystemsInitializer(...)) — c172.jl:773-794, kinematics.jl:21-40 */
+typedef struct fb_init_soa {
+    const double* q_nb[4];    /* attitude quaternion (real, i, j, k); NULL = identity */
+    const double* lat; const double* lon;
+    const double* h_e;        /* ellipsoidal altitude */
+    const double* w_wb_b[3];
+    const double* v_eb_n[3];
+    const double* n_eng;      /* normalised engine speed */
+    const double* engine_state; /* FB_ENG_* as double */
+    const double* throttle; const double* mixture; const double* elevator; const double* aileron; const double* rudder;
+    const double* flaps; const double* brake_left; const double* brake_right; const double* fuel_load;
+    const double* payload[5];
+    const double* stall; const double* alpha_filt; const double* beta_filt;
+} fb_init_soa;
+
+typedef struct fb_moments {  /* ensemble statistics over members with status RUNNING or DONE */
+    int64_t count; double sum, sum_sq, min, max;
+} fb_moments;
+
+/* ---- lifecycle ----------------------------------------------------------------------- */
+int32_t fb_api_version(void);
+const char* fb_last_error(void);
+/* Simulation(world; ...) : sim.jl:183-253 */
+int32_t fb_create(const fb_config* cfg, fb_handle* out);
+/* table blob produced by tools/build_tables.py (aero/engine/propeller/geoid/gain schedules) */
+int32_t fb_load_tables(fb_handle h, const void* blob, size_t nbytes);
+int32_t fb_destroy(fb_handle h);
+int32_t fb_sync(fb_handle h);
+
+/* ---- initialisation -------------------------------------------------------------------- */
+/* init!(sim, C172.TrimParameters(...)) : sim.jl:390-414 -> c172.jl:883-942. trim_state_out [7][N] and
+ * cost_out [N] may be NULL. Members whose trim does not reach cost <= 1e-16 get FB_ST_TRIM_FAILED. */
+int32_t fb_init_trim(fb_handle h, const fb_trim_params_soa* p, double* trim_state_out, double* cost_out);
+/* init!(sim, C172.Init(kin, sys)) : aircraftbase.jl:76-86 */
+int32_t fb_init(fb_handle h, const fb_init_soa* ic);
+/* raw state injection (mdl.x, aero.s.stall, engine.s[]) followed by the reinit! RHS evaluation */
+int32_t fb_init_state(fb_handle h, const double* x, const uint8_t* stall, const uint8_t* eng_state);
+
+/* ---- inputs ---------------------------------------------------------------------------- */
+/* mdl.<...>.u.<field> = value : stride 0 broadcasts values[0], stride 1 = one value per member */
+int32_t fb_set_input(fb_handle h, int32_t field, const double* values, int64_t stride);
+int32_t fb_get_input(fb_handle h, int32_t field, double* out);
+/* declarative replacement of user_callback! (sim.jl:331-341): event k sets `field[k]` of `member[k]` to
+ * `value[k]` in the user-callback slot at the end of the step that reaches step index `step[k]`
+ * (i.e. it is in force from t = t_start + step*dt). Replaces any previous schedule. */
+int32_t fb_schedule_inputs(fb_handle h, int64_t n_events, const int64_t* member, const int64_t* step,
+                           const int32_t* field, const double* value);
+
+/* ---- stepping ---------------------------------------------------------------------------- */
+/* step!(sim, Δt, true) : sim.jl:386 — advance every running member by round(t_advance/dt) steps */
+int32_t fb_step(fb_handle h, double t_advance);
+/* run!(sim) headless : sim.jl:611-638 — step until t_end */
+int32_t fb_run(fb_handle h);
+int32_t fb_time(fb_handle h, double* t, int64_t* n_steps);
+
+/* ---- read-back ------------------------------------------------------------------------- */
+int32_t fb_nx(fb_handle h, int32_t* nx);
+int32_t fb_get_state(fb_handle h, double* x);                       /* sim.x : [nx][N] */
+int32_t fb_get_discrete(fb_handle h, uint8_t* stall, uint8_t* eng_state);
+int32_t fb_get_output(fb_handle h, int32_t field, double* out);     /* sim.y.<field> : [N] */
+int32_t fb_status(fb_handle h, int32_t* status);
+/* TimeSeries(sim) : sim.jl:644-704 — decimated SoA log */
+int32_t fb_log_info(fb_handle h, int64_t* n_samples, int32_t* n_fields);
+int32_t fb_log_times(fb_handle h, double* t);                        /* [n_samples] */
+int32_t fb_log_fetch(fb_handle h, int32_t field, double* out);       /* [n_samples][N] */
+int32_t fb_stats(fb_handle h, int32_t field, fb_moments* out);
+
+/* ---- test hooks: the Modeling protocol pieces, for parity checks in isolation ---------- */
+/* f_ode!(world) at the current state: writes ẋ [nx][N] (modeling.jl:201-254, world.jl:26-32) */
+int32_t fb_rhs(fb_handle h, double* xdot);
+/* counters */
+int32_t fb_counters(fb_handle h, int64_t* kernel_launches, int64_t* rhs_evals_per_member);
+/* device pointers for zero-copy interop with torch / CUDA.jl (valid until fb_destroy) */
+int32_t fb_device_state(fb_handle h, void** d_x, int64_t* pitch_elems);
+/* launch stream handle (cudaStream_t) so that callers can time with events on the right stream */
+int32_t fb_stream(fb_handle h, void** stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLIGHTBATCH_H */

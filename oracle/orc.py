@@ -1,0 +1,214 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes binding of the CPU oracle (oracle/liborc*.so).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module; the product path (flight.jl_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_GEOID = os.path.join(_HERE, "..", "flight.jl_b200", "data", "egm96_ww15mgh_le.bin")
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+
+def _load(name):
+    path = os.path.join(_HERE, name)
+    if not os.path.exists(path):
+        build()
+    lib = C.CDLL(path)
+    vp, dp, i32, i64, dbl = C.c_void_p, C.POINTER(C.c_double), C.c_int, C.c_longlong, C.c_double
+    sig = {
+        "orc_load_geoid": (i32, [C.c_char_p]),
+        "orc_world_create": (vp, []),
+        "orc_world_destroy": (None, [vp]),
+        "orc_world_prop_table": (None, [vp, dp]),
+        "orc_world_engine_tables": (None, [vp, dp, dp, dp]),
+        "orc_sim_create": (vp, [vp, i32, i32, dbl, dbl]),
+        "orc_sim_destroy": (None, [vp]),
+        "orc_sim_nx": (i32, [vp]),
+        "orc_sim_status": (i32, [vp]),
+        "orc_sim_want_y_extra": (None, [vp, i32]),
+        "orc_sim_init_trim": (i32, [vp, dp, dp, dp]),
+        "orc_sim_trim_cost_at": (dbl, [vp, dp, dp]),
+        "orc_sim_init": (i32, [vp, dp]),
+        "orc_sim_init_state": (i32, [vp, dp, i32, i32]),
+        "orc_sim_get_state": (None, [vp, dp]),
+        "orc_sim_get_xdot": (None, [vp, dp]),
+        "orc_sim_get_discrete": (None, [vp, C.POINTER(i32), C.POINTER(i32)]),
+        "orc_sim_set_input": (i32, [vp, i32, dbl]),
+        "orc_sim_get_input": (dbl, [vp, i32]),
+        "orc_sim_get_output": (dbl, [vp, i32]),
+        "orc_sim_add_event": (None, [vp, i64, i32, dbl]),
+        "orc_sim_clear_events": (None, [vp]),
+        "orc_sim_rhs": (i32, [vp]),
+        "orc_sim_step": (i32, [vp, i64]),
+        "orc_sim_steps_taken": (i64, [vp]),
+        "orc_ops_reset": (None, []),
+        "orc_ops_get": (None, [C.POINTER(C.c_ulonglong)]),
+        "orc_is_counting": (i32, []),
+        "orc_batch_step": (i32, [C.POINTER(vp), i64, i64, i32]),
+    }
+    for k, (res, args) in sig.items():
+        f = getattr(lib, k)
+        f.restype = res
+        f.argtypes = args
+    rc = lib.orc_load_geoid(os.path.abspath(_GEOID).encode())
+    if rc != 0:
+        raise RuntimeError(f"oracle: cannot load geoid ({rc})")
+    return lib
+
+
+_libs = {}
+
+
+def lib(counting=False):
+    key = "liborc_count.so" if counting else "liborc.so"
+    if key not in _libs:
+        _libs[key] = _load(key)
+    return _libs[key]
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+TRIM_DEFAULT = dict(lat=0.0, lon=0.0, h_e=1050.0, psi_nb=0.0, EAS=50.0, gamma_wb_n=0.0, psi_wb_dot=0.0,
+                    theta_wb_dot=0.0, beta_a=0.0, fuel_load=0.5, mixture=0.5, flaps=0.0,
+                    m_pilot=75.0, m_copilot=75.0, m_lpass=0.0, m_rpass=0.0, m_baggage=50.0)
+TRIM_KEYS = list(TRIM_DEFAULT.keys())
+
+INIT_DEFAULT = dict(q0=1.0, q1=0.0, q2=0.0, q3=0.0, lat=0.0, lon=0.0, h_e=0.0, w0=0.0, w1=0.0, w2=0.0,
+                    vN=0.0, vE=0.0, vD=0.0, n_eng=0.0, engine_state=0.0, throttle=0.0, mixture=0.5, elevator=0.0,
+                    aileron=0.0, rudder=0.0, flaps=0.0, brake_left=0.0, brake_right=0.0, fuel_load=0.5,
+                    m_pilot=75.0, m_copilot=75.0, m_lpass=0.0, m_rpass=0.0, m_baggage=50.0, stall=0.0,
+                    alpha_filt=0.0, beta_filt=0.0)
+INIT_KEYS = list(INIT_DEFAULT.keys())
+
+
+class World:
+    def __init__(self, counting=False):
+        self.lib = lib(counting)
+        self.h = self.lib.orc_world_create()
+        assert self.h
+
+    def prop_table(self):
+        out = np.zeros((6, 21, 21))
+        self.lib.orc_world_prop_table(self.h, _dp(out))
+        return out
+
+    def engine_tables(self):
+        a, b, c = np.zeros((2, 9)), np.zeros((13, 3)), np.zeros((5, 3))
+        self.lib.orc_world_engine_tables(self.h, _dp(a), _dp(b), _dp(c))
+        return a, b, c
+
+
+_world = {}
+
+
+def world(counting=False):
+    if counting not in _world:
+        _world[counting] = World(counting)
+    return _world[counting]
+
+
+class Sim:
+    """One reference `Simulation(SimpleWorld(Cessna172...); dt, Δt)` on the CPU oracle."""
+
+    def __init__(self, variant=0, kin=0, dt=0.02, Dt=None, counting=False):
+        self.w = world(counting)
+        self.lib = self.w.lib
+        self.h = self.lib.orc_sim_create(self.w.h, variant, kin, dt, dt if Dt is None else Dt)
+        self.nx = self.lib.orc_sim_nx(self.h)
+        self.dt = dt
+
+    def __del__(self):
+        try:
+            self.lib.orc_sim_destroy(self.h)
+        except Exception:
+            pass
+
+    def init_trim(self, **kw):
+        p = dict(TRIM_DEFAULT); p.update(kw)
+        pv = np.array([p[k] for k in TRIM_KEYS], dtype=np.float64)
+        ts = np.zeros(7); cost = C.c_double(0)
+        rc = self.lib.orc_sim_init_trim(self.h, _dp(pv), _dp(ts), C.byref(cost))
+        return rc == 0, ts, cost.value
+
+    def trim_cost_at(self, trim_state, **kw):
+        p = dict(TRIM_DEFAULT); p.update(kw)
+        pv = np.array([p[k] for k in TRIM_KEYS], dtype=np.float64)
+        ts = np.ascontiguousarray(trim_state, dtype=np.float64)
+        return self.lib.orc_sim_trim_cost_at(self.h, _dp(pv), _dp(ts))
+
+    def init(self, **kw):
+        p = dict(INIT_DEFAULT); p.update(kw)
+        pv = np.array([p[k] for k in INIT_KEYS], dtype=np.float64)
+        return self.lib.orc_sim_init(self.h, _dp(pv))
+
+    def init_state(self, x, stall=0, eng_state=2):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        return self.lib.orc_sim_init_state(self.h, _dp(x), int(stall), int(eng_state))
+
+    @property
+    def x(self):
+        out = np.zeros(self.nx)
+        self.lib.orc_sim_get_state(self.h, _dp(out))
+        return out
+
+    @property
+    def xdot(self):
+        out = np.zeros(self.nx)
+        self.lib.orc_sim_get_xdot(self.h, _dp(out))
+        return out
+
+    @property
+    def discrete(self):
+        a, b = C.c_int(0), C.c_int(0)
+        self.lib.orc_sim_get_discrete(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    @property
+    def status(self):
+        return self.lib.orc_sim_status(self.h)
+
+    def set_input(self, field, v):
+        rc = self.lib.orc_sim_set_input(self.h, int(field), float(v))
+        assert rc == 0, f"unknown input field {field}"
+
+    def get_input(self, field):
+        return self.lib.orc_sim_get_input(self.h, int(field))
+
+    def y(self, field):
+        return self.lib.orc_sim_get_output(self.h, int(field))
+
+    def add_event(self, step, field, value):
+        self.lib.orc_sim_add_event(self.h, int(step), int(field), float(value))
+
+    def rhs(self):
+        return self.lib.orc_sim_rhs(self.h)
+
+    def step(self, n=1):
+        return self.lib.orc_sim_step(self.h, int(n))
+
+    def want_y_extra(self, on=True):
+        self.lib.orc_sim_want_y_extra(self.h, 1 if on else 0)
+
+
+def batch_step(sims, n_steps, threads):
+    arr = (C.c_void_p * len(sims))(*[s.h for s in sims])
+    sims[0].lib.orc_batch_step(arr, len(sims), int(n_steps), int(threads))
+
+
+def ops_reset(counting_lib):
+    counting_lib.orc_ops_reset()
+
+
+def ops_get(counting_lib):
+    out = (C.c_ulonglong * 4)()
+    counting_lib.orc_ops_get(out)
+    return dict(plain=out[0], div=out[1], sqrt=out[2], trans=out[3], total=sum(out))

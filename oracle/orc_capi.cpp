@@ -1,0 +1,275 @@
+// TEST INFRASTRUCTURE ONLY (see orc_real.hpp). extern "C" surface used by tests/, smoke() and
+// bench.py's cpu_baseline / --impl reference legs through ctypes.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <memory>
+#include <thread>
+#include <atomic>
+#include "../include/flightbatch.h"
+#include "orc_sim.hpp"
+
+#if ORC_COUNT
+thread_local OpCounts g_ops;
+#endif
+
+static std::vector<float> g_geoid_data;
+static Geoid g_geoid;
+
+static real clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+bool set_input_field(Member& m, int f, double v) {
+    Inputs& u = m.u;
+    switch (f) {
+        case FB_U_AILERON: u.aileron = clampd(v, -1, 1); break;
+        case FB_U_ELEVATOR: u.elevator = clampd(v, -1, 1); break;
+        case FB_U_RUDDER: u.rudder = clampd(v, -1, 1); break;
+        case FB_U_AILERON_OFFSET: u.aileron_offset = clampd(v, -1, 1); break;
+        case FB_U_ELEVATOR_OFFSET: u.elevator_offset = clampd(v, -1, 1); break;
+        case FB_U_RUDDER_OFFSET: u.rudder_offset = clampd(v, -1, 1); break;
+        case FB_U_FLAPS: u.flaps = clampd(v, 0, 1); break;
+        case FB_U_BRAKE_LEFT: u.brake_left = clampd(v, 0, 1); break;
+        case FB_U_BRAKE_RIGHT: u.brake_right = clampd(v, 0, 1); break;
+        case FB_U_THROTTLE: u.throttle = clampd(v, 0, 1); break;
+        case FB_U_MIXTURE: u.mixture = clampd(v, 0, 1); break;
+        case FB_U_ENG_START: u.eng_start = v != 0; break;
+        case FB_U_ENG_STOP: u.eng_stop = v != 0; break;
+        case FB_U_MIXTURE_AUTO: u.mixture_auto = v != 0; break;
+        case FB_U_STEERING_ENGAGED: u.steering_engaged = v != 0; break;
+        case FB_U_M_PILOT: u.m_pilot = clampd(v, 0, 100); break;
+        case FB_U_M_COPILOT: u.m_copilot = clampd(v, 0, 100); break;
+        case FB_U_M_LPASS: u.m_lpass = clampd(v, 0, 100); break;
+        case FB_U_M_RPASS: u.m_rpass = clampd(v, 0, 100); break;
+        case FB_U_M_BAGGAGE: u.m_baggage = clampd(v, 0, 100); break;
+        case FB_U_T_SL: u.T_sl = clampd(v, isa::T_std - 50, isa::T_std + 50); break;
+        case FB_U_P_SL: u.p_sl = clampd(v, isa::p_std - 10000, isa::p_std + 10000); break;
+        case FB_U_WIND_N: u.wind_n.x = v; break;
+        case FB_U_WIND_E: u.wind_n.y = v; break;
+        case FB_U_WIND_D: u.wind_n.z = v; break;
+        case FB_U_TRN_ELEVATION: u.trn_elev = v; break;
+        case FB_U_TRN_SURFACE: u.surface = (int)v; break;
+        default:
+            if (f >= FB_U_ACT_THROTTLE && f <= FB_U_ACT_BRAKE_RIGHT) { int i = f - FB_U_ACT_THROTTLE; u.act_cmd[i] = clampd(v, ACT_LO[i], ACT_HI[i]); break; }
+            return false;
+    }
+    return true;
+}
+double get_input_field(const Member& m, int f) {
+    const Inputs& u = m.u;
+    switch (f) {
+        case FB_U_AILERON: return val(u.aileron); case FB_U_ELEVATOR: return val(u.elevator); case FB_U_RUDDER: return val(u.rudder);
+        case FB_U_AILERON_OFFSET: return val(u.aileron_offset); case FB_U_ELEVATOR_OFFSET: return val(u.elevator_offset);
+        case FB_U_RUDDER_OFFSET: return val(u.rudder_offset); case FB_U_FLAPS: return val(u.flaps);
+        case FB_U_BRAKE_LEFT: return val(u.brake_left); case FB_U_BRAKE_RIGHT: return val(u.brake_right);
+        case FB_U_THROTTLE: return val(u.throttle); case FB_U_MIXTURE: return val(u.mixture);
+        case FB_U_ENG_START: return u.eng_start; case FB_U_ENG_STOP: return u.eng_stop; case FB_U_MIXTURE_AUTO: return u.mixture_auto;
+        case FB_U_STEERING_ENGAGED: return u.steering_engaged;
+        case FB_U_M_PILOT: return val(u.m_pilot); case FB_U_M_COPILOT: return val(u.m_copilot); case FB_U_M_LPASS: return val(u.m_lpass);
+        case FB_U_M_RPASS: return val(u.m_rpass); case FB_U_M_BAGGAGE: return val(u.m_baggage);
+        case FB_U_T_SL: return val(u.T_sl); case FB_U_P_SL: return val(u.p_sl);
+        case FB_U_WIND_N: return val(u.wind_n.x); case FB_U_WIND_E: return val(u.wind_n.y); case FB_U_WIND_D: return val(u.wind_n.z);
+        case FB_U_TRN_ELEVATION: return val(u.trn_elev); case FB_U_TRN_SURFACE: return u.surface;
+        default:
+            if (f >= FB_U_ACT_THROTTLE && f <= FB_U_ACT_BRAKE_RIGHT) return val(u.act_cmd[f - FB_U_ACT_THROTTLE]);
+    }
+    return 0.0 / 0.0;
+}
+
+static double get_output_field(const Sim& s, int f) {
+    const VehicleY& y = s.m.y;
+    switch (f) {
+        case FB_Y_PSI: return val(y.kin.e_nb.psi); case FB_Y_THETA: return val(y.kin.e_nb.theta); case FB_Y_PHI: return val(y.kin.e_nb.phi);
+        case FB_Y_LAT: return val(y.kin.ll.lat); case FB_Y_LON: return val(y.kin.ll.lon); case FB_Y_H_E: return val(y.kin.h_e); case FB_Y_H_O: return val(y.kin.h_o);
+        case FB_Y_V_N: return val(y.kin.v_eb_n.x); case FB_Y_V_E: return val(y.kin.v_eb_n.y); case FB_Y_V_D: return val(y.kin.v_eb_n.z);
+        case FB_Y_V_GND: return val(y.kin.v_gnd); case FB_Y_CHI_GND: return val(y.kin.chi_gnd); case FB_Y_GAMMA_GND: return val(y.kin.gamma_gnd);
+        case FB_Y_P: return val(y.kin.w_wb_b.x); case FB_Y_Q: return val(y.kin.w_wb_b.y); case FB_Y_R: return val(y.kin.w_wb_b.z);
+        case FB_Y_TAS: return val(y.air.TAS); case FB_Y_EAS: return val(y.air.EAS); case FB_Y_CAS: return val(y.air.CAS); case FB_Y_MACH: return val(y.air.M); case FB_Y_QBAR: return val(y.air.q);
+        case FB_Y_ALPHA: return val(y.aero.alpha); case FB_Y_BETA: return val(y.aero.beta); case FB_Y_ALPHA_FILT: return val(y.aero.alpha_filt); case FB_Y_BETA_FILT: return val(y.aero.beta_filt);
+        case FB_Y_STALL: return y.aero.stall; case FB_Y_C_L: return val(y.aero.C_L); case FB_Y_C_D: return val(y.aero.C_D);
+        case FB_Y_WOW_LEFT: return y.strut[0].wow; case FB_Y_WOW_RIGHT: return y.strut[1].wow; case FB_Y_WOW_NOSE: return y.strut[2].wow;
+        case FB_Y_XI_LEFT: return val(y.strut[0].xi); case FB_Y_XI_RIGHT: return val(y.strut[1].xi); case FB_Y_XI_NOSE: return val(y.strut[2].xi);
+        case FB_Y_FDMP_LEFT: return val(y.strut[0].F_dmp); case FB_Y_FDMP_RIGHT: return val(y.strut[1].F_dmp); case FB_Y_FDMP_NOSE: return val(y.strut[2].F_dmp);
+        case FB_Y_ENG_OMEGA: return val(y.eng.omega); case FB_Y_ENG_STATE: return y.eng.state; case FB_Y_ENG_MAP: return val(y.eng.MAP);
+        case FB_Y_ENG_P_SHAFT: return val(y.eng.P_shaft); case FB_Y_ENG_TAU_SHAFT: return val(y.eng.tau_shaft); case FB_Y_ENG_MDOT: return val(y.eng.mdot);
+        case FB_Y_FUEL_M_TOTAL: return val(y.fuel.m_total);
+        case FB_Y_PROP_THRUST: return val(y.prop.wr_p.F.x); case FB_Y_PROP_J: return val(y.prop.J);
+        case FB_Y_MASS: return val(y.dyn.mp_b.m);
+        case FB_Y_F_X: return val(y.dyn.f_c_c.x); case FB_Y_F_Y: return val(y.dyn.f_c_c.y); case FB_Y_F_Z: return val(y.dyn.f_c_c.z);
+        default: return s.av.output(s.m, f);
+    }
+}
+
+extern "C" {
+
+int orc_load_geoid(const char* path) {
+    FILE* fp = fopen(path, "rb");
+    if (!fp) return -1;
+    g_geoid_data.resize((size_t)Geoid::NLAT * Geoid::NLON);
+    size_t n = fread(g_geoid_data.data(), sizeof(float), g_geoid_data.size(), fp);
+    fclose(fp);
+    if (n != g_geoid_data.size()) return -2;
+    g_geoid.data = g_geoid_data.data();
+    return 0;
+}
+
+void* orc_world_create() { if (!g_geoid.data) return nullptr; return new World(&g_geoid); }
+void orc_world_destroy(void* w) { delete (World*)w; }
+// propeller table as generated by the oracle: out[6][21][21] in order C_Fx, C_Mx, C_Fz_a, C_Mz_a, C_P, eta_p
+void orc_world_prop_table(void* w, double* out) {
+    World* W = (World*)w;
+    const Interp2* all[6] = {&W->prop.C_Fx, &W->prop.C_Mx, &W->prop.C_Fz_a, &W->prop.C_Mz_a, &W->prop.C_P, &W->prop.eta_p};
+    for (int k = 0; k < 6; k++) for (int i = 0; i < 441; i++) out[k * 441 + i] = all[k]->y[i];
+}
+// engine tables: mu_wot[2][9], pi_std[13][3], pi_wot[5][3]
+void orc_world_engine_tables(void* w, double* mu_wot, double* pi_std, double* pi_wot) {
+    World* W = (World*)w;
+    for (int i = 0; i < 18; i++) mu_wot[i] = W->eng.mu_wot.y[i];
+    for (int i = 0; i < 39; i++) pi_std[i] = W->eng.pi_std.y[i];
+    for (int i = 0; i < 15; i++) pi_wot[i] = W->eng.pi_wot.y[i];
+}
+
+void* orc_sim_create(void* w, int variant, int kin, double dt, double Dt) {
+    Sim* s = new Sim();
+    s->W = (World*)w;
+    s->m.L = Layout(variant, kin);
+    s->av.variant = variant;
+    s->dt = dt; s->Dt = Dt;
+    s->periodic_every = (int)std::llround(Dt / dt);
+    if (s->periodic_every < 1) s->periodic_every = 1;
+    return s;
+}
+void orc_sim_destroy(void* s) { delete (Sim*)s; }
+int orc_sim_nx(void* s) { return ((Sim*)s)->m.L.nx; }
+int orc_sim_status(void* s) { return ((Sim*)s)->m.status; }
+void orc_sim_want_y_extra(void* s, int on) { ((Sim*)s)->m.want_y_extra = on != 0; }
+
+static void reinit(Sim* S) {
+    S->n_steps = 0; S->n_periodic = 0; S->sched_pos = 0; S->m.status = ST_RUNNING;
+}
+
+// p[17]: lat, lon, h_e, psi_nb, EAS, gamma_wb_n, psi_wb_dot, theta_wb_dot, beta_a, fuel_load, mixture, flaps, payload[5]
+int orc_sim_init_trim(void* s, const double* p, double* trim_state_out, double* cost_out) {
+    Sim* S = (Sim*)s;
+    TrimParams tp;
+    LatLon ll; ll.lat = p[0]; ll.lon = p[1];
+    tp.n_e = n_from_latlon(ll); tp.h_e = p[2]; tp.psi_nb = p[3]; tp.EAS = p[4]; tp.gamma_wb_n = p[5];
+    tp.psi_wb_dot = p[6]; tp.theta_wb_dot = p[7]; tp.beta_a = p[8];
+    tp.fuel_load = clampd(p[9], 0, 1); tp.mixture = clampd(p[10], 0, 1); tp.flaps = clampd(p[11], 0, 1);
+    for (int i = 0; i < 5; i++) tp.payload[i] = clampd(p[12 + i], 0, 100);
+    reinit(S);
+    TrimState ts; double cost = 0; int iters = 0;
+    bool ok = false;
+    try { ok = trim_solve(S->m, *S->W, tp, ts, &cost, &iters); } catch (OrcTermination& e) { S->m.status = e.code; return -1; }
+    if (trim_state_out) for (int i = 0; i < 7; i++) trim_state_out[i] = val(ts.v[i]);
+    if (cost_out) *cost_out = cost;
+    if (!ok) S->m.status = ST_TRIM_FAILED;
+    S->av.f_init(S->m, *S->W);
+    S->apply_events();
+    return ok ? 0 : 1;
+}
+// evaluate the trim cost at a given trim state (no optimisation): pins the stored reference trims
+double orc_sim_trim_cost_at(void* s, const double* p, const double* trim_state) {
+    Sim* S = (Sim*)s;
+    TrimParams tp;
+    LatLon ll; ll.lat = p[0]; ll.lon = p[1];
+    tp.n_e = n_from_latlon(ll); tp.h_e = p[2]; tp.psi_nb = p[3]; tp.EAS = p[4]; tp.gamma_wb_n = p[5];
+    tp.psi_wb_dot = p[6]; tp.theta_wb_dot = p[7]; tp.beta_a = p[8];
+    tp.fuel_load = clampd(p[9], 0, 1); tp.mixture = clampd(p[10], 0, 1); tp.flaps = clampd(p[11], 0, 1);
+    for (int i = 0; i < 5; i++) tp.payload[i] = clampd(p[12 + i], 0, 100);
+    TrimState ts; for (int i = 0; i < 7; i++) ts.v[i] = trim_state[i];
+    reinit(S);
+    try { trim_assign(S->m, *S->W, tp, ts); } catch (OrcTermination& e) { return 1e300; }
+    return val(trim_cost(S->m, *S->W));
+}
+// ic[40]: q_nb[4], lat, lon, h_e, w_wb_b[3], v_eb_n[3], n_eng, engine_state, throttle, mixture, elevator, aileron,
+//         rudder, flaps, brake_left, brake_right, fuel_load, payload[5], stall, alpha_filt, beta_filt
+int orc_sim_init(void* s, const double* ic) {
+    Sim* S = (Sim*)s;
+    KinInit ki; SysInit si;
+    ki.q_nb = qnormalize(Q4(ic[0], ic[1], ic[2], ic[3]));   // RQuat(v) normalises (attitude.jl:69-71)
+    LatLon ll; ll.lat = ic[4]; ll.lon = ic[5];
+    ki.n_e = n_from_latlon(ll); ki.h_e = ic[6];
+    ki.w_wb_b = V3(ic[7], ic[8], ic[9]); ki.v_eb_n = V3(ic[10], ic[11], ic[12]);
+    si.n_eng = ic[13]; si.engine_state = (int)ic[14]; si.throttle = ic[15]; si.mixture = ic[16]; si.elevator = ic[17];
+    si.aileron = ic[18]; si.rudder = ic[19]; si.flaps = ic[20]; si.brake_left = ic[21]; si.brake_right = ic[22]; si.fuel_load = ic[23];
+    for (int i = 0; i < 5; i++) si.payload[i] = ic[24 + i];
+    si.stall = ic[29] != 0; si.alpha_filt = ic[30]; si.beta_filt = ic[31];
+    reinit(S);
+    try { vehicle_init(S->m, *S->W, ki, si); } catch (OrcTermination& e) { S->m.status = e.code; return -1; }
+    S->av.f_init(S->m, *S->W);
+    S->apply_events();
+    return 0;
+}
+int orc_sim_init_state(void* s, const double* x, int stall, int eng_state) {
+    Sim* S = (Sim*)s;
+    for (int i = 0; i < S->m.L.nx; i++) S->m.x[i] = x[i];
+    S->m.s.stall = stall != 0; S->m.s.eng_state = eng_state;
+    reinit(S);
+    try { S->world_ode(); } catch (OrcTermination& e) { S->m.status = e.code; return -1; }
+    S->apply_events();
+    return 0;
+}
+void orc_sim_get_state(void* s, double* x) { Sim* S = (Sim*)s; for (int i = 0; i < S->m.L.nx; i++) x[i] = val(S->m.x[i]); }
+void orc_sim_get_xdot(void* s, double* xd) { Sim* S = (Sim*)s; for (int i = 0; i < S->m.L.nx; i++) xd[i] = val(S->m.xdot[i]); }
+void orc_sim_get_discrete(void* s, int* stall, int* eng_state) { Sim* S = (Sim*)s; *stall = S->m.s.stall; *eng_state = S->m.s.eng_state; }
+int orc_sim_set_input(void* s, int field, double v) { Sim* S = (Sim*)s; return (set_input_field(S->m, field, v) || S->av.set_input(field, v)) ? 0 : -1; }
+double orc_sim_get_input(void* s, int field) { Sim* S = (Sim*)s; double v = get_input_field(S->m, field); return v == v ? v : S->av.get_input(field); }
+double orc_sim_get_output(void* s, int field) { return get_output_field(*(Sim*)s, field); }
+void orc_sim_add_event(void* s, long long step, int field, double value) {
+    Sim* S = (Sim*)s;
+    S->schedule.push_back({step, field, value});
+    std::stable_sort(S->schedule.begin(), S->schedule.end(), [](const InputEvent& a, const InputEvent& b) { return a.step < b.step; });
+}
+void orc_sim_clear_events(void* s) { Sim* S = (Sim*)s; S->schedule.clear(); S->sched_pos = 0; }
+// f_ode!(world) at the current state
+int orc_sim_rhs(void* s) {
+    Sim* S = (Sim*)s;
+    try { S->world_ode(); } catch (OrcTermination& e) { return e.code; }
+    return 0;
+}
+int orc_sim_step(void* s, long long n) {
+    Sim* S = (Sim*)s;
+    for (long long i = 0; i < n; i++) S->step();
+    return S->m.status;
+}
+long long orc_sim_steps_taken(void* s) { return ((Sim*)s)->n_steps; }
+
+// op counters (only meaningful in the ORC_COUNT build)
+void orc_ops_reset() {
+#if ORC_COUNT
+    g_ops = OpCounts();
+#endif
+}
+void orc_ops_get(unsigned long long* out4) {
+#if ORC_COUNT
+    out4[0] = g_ops.plain; out4[1] = g_ops.div; out4[2] = g_ops.sqrt; out4[3] = g_ops.trans;
+#else
+    out4[0] = out4[1] = out4[2] = out4[3] = 0;
+#endif
+}
+int orc_is_counting() { return ORC_COUNT; }
+
+// ---- batch helper for the CPU baseline: step an array of sims on `threads` OpenMP threads
+int orc_batch_step(void** sims, long long n_sims, long long n_steps, int threads) {
+    if (threads < 1) threads = 1;
+    std::atomic<long long> next(0);
+    auto work = [&]() {
+        for (;;) {
+            long long i0 = next.fetch_add(8);
+            if (i0 >= n_sims) break;
+            long long i1 = std::min(n_sims, i0 + 8);
+            for (long long i = i0; i < i1; i++) {
+                Sim* S = (Sim*)sims[i];
+                for (long long k = 0; k < n_steps; k++) S->step();
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; t++) pool.emplace_back(work);
+    work();
+    for (auto& th : pool) th.join();
+    return 0;
+}
+
+}  // extern "C"
