@@ -1,0 +1,502 @@
+"""flightbatch — host-side mirror of the Flight.jl user API for the batched C172 RK4 path.
+
+Reference surface kept (paths relative to the reference root):
+  Simulation(mdl; dt, Δt, t_start, t_end, saveat)   lib/FlightCore/src/sim.jl:183-196  -> BatchSimulation
+  init!(sim, init)                                   sim.jl:390-414                      -> init_b / sim.init
+  step!(sim, Δt, true)                               sim.jl:386                          -> step_b / sim.step
+  run!(sim)                                          sim.jl:611-638                      -> run_b / sim.run
+  TimeSeries(sim)                                    sim.jl:644-704                      -> TimeSeries
+  C172.TrimParameters / C172.Init(KinInit, ...)      lib/FlightApps/src/c172/c172.jl:773-818
+  Cessna172Sv0 / Cessna172Xv0/v1/v2, WA / NED, SimpleWorld
+Everything numerical happens in libflightbatch.so (hand-written sm_100a CUDA behind the C ABI of
+include/flightbatch.h), loaded with ctypes. There is no CPU fallback: importing works without a GPU,
+but creating a BatchSimulation raises when the library or a CUDA device is missing.
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libflightbatch.so")
+TABLES_PATH = os.path.join(_HERE, "data", "c172_tables.bin")
+HEADER_PATH = os.path.join(_HERE, "..", "include", "flightbatch.h")
+
+
+class FlightBatchError(RuntimeError):
+    pass
+
+
+# ----------------------------------------------------------------------------- enums from the C header
+def _parse_header():
+    txt = open(HEADER_PATH).read()
+    defs = {k: int(v) for k, v in re.findall(r"#define\s+(FB_[A-Z0-9_]+)\s+\(?(-?\d+)\)?", txt)}
+    enums = {}
+    for name in ("fb_input", "fb_output"):
+        body = re.search(r"enum\s+%s\s*\{(.*?)\};" % name, txt, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        val = -1
+        out = {}
+        for item in body.split(","):
+            item = item.strip()
+            if not item:
+                continue
+            if "=" in item:
+                k, v = [t.strip() for t in item.split("=")]
+                val = int(v)
+            else:
+                k = item
+                val += 1
+            out[k] = val
+        enums[name] = out
+    return defs, enums
+
+
+DEFS, _ENUMS = _parse_header()
+U = _ENUMS["fb_input"]     # e.g. U["FB_U_ELEVATOR"]
+Y = _ENUMS["fb_output"]
+globals().update(DEFS)
+globals().update(U)
+globals().update(Y)
+
+INPUT_NAMES = {k[len("FB_U_"):].lower(): v for k, v in U.items() if not k.endswith("_COUNT")}
+OUTPUT_NAMES = {k[len("FB_Y_"):].lower(): v for k, v in Y.items() if not k.endswith("_COUNT")}
+
+
+# ----------------------------------------------------------------------------- ctypes structs
+class fb_config(C.Structure):
+    _fields_ = [("variant", C.c_int32), ("kinematics", C.c_int32), ("n_members", C.c_int64), ("member_offset", C.c_int64),
+                ("dt", C.c_double), ("Dt", C.c_double), ("t_start", C.c_double), ("t_end", C.c_double),
+                ("device", C.c_int32), ("log_every", C.c_int32), ("log_n_fields", C.c_int32), ("log_fields", C.c_int32 * 32),
+                ("steps_per_launch", C.c_int32)]
+
+
+_DP = C.POINTER(C.c_double)
+
+
+class fb_trim_params_soa(C.Structure):
+    _fields_ = [(k, _DP) for k in ("lat", "lon", "h_e", "psi_nb", "EAS", "gamma_wb_n", "psi_wb_dot", "theta_wb_dot",
+                                   "beta_a", "fuel_load", "mixture", "flaps")] + [("payload", _DP * 5)]
+
+
+class fb_init_soa(C.Structure):
+    _fields_ = ([("q_nb", _DP * 4), ("lat", _DP), ("lon", _DP), ("h_e", _DP), ("w_wb_b", _DP * 3), ("v_eb_n", _DP * 3)] +
+                [(k, _DP) for k in ("n_eng", "engine_state", "throttle", "mixture", "elevator", "aileron", "rudder", "flaps",
+                                    "brake_left", "brake_right", "fuel_load")] +
+                [("payload", _DP * 5), ("stall", _DP), ("alpha_filt", _DP), ("beta_filt", _DP)])
+
+
+class fb_moments(C.Structure):
+    _fields_ = [("count", C.c_int64), ("sum", C.c_double), ("sum_sq", C.c_double), ("min", C.c_double), ("max", C.c_double)]
+
+
+EXPORTS = ["fb_api_version", "fb_last_error", "fb_create", "fb_load_tables", "fb_destroy", "fb_sync", "fb_init_trim", "fb_init",
+           "fb_init_state", "fb_set_input", "fb_get_input", "fb_schedule_inputs", "fb_step", "fb_run", "fb_time", "fb_nx",
+           "fb_get_state", "fb_get_discrete", "fb_get_output", "fb_status", "fb_log_info", "fb_log_times", "fb_log_fetch",
+           "fb_stats", "fb_rhs", "fb_counters", "fb_device_state", "fb_stream"]
+
+_lib = None
+
+
+def load_library():
+    """Load libflightbatch.so (the CUDA engine). Raises when it has not been built: no fallback exists."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FlightBatchError(f"{LIB_PATH} not built; run __graft_entry__.build() (nvcc, sm_100a)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    u8p = C.POINTER(C.c_uint8)
+    sig = {
+        "fb_api_version": (i32, []), "fb_last_error": (C.c_char_p, []),
+        "fb_create": (i32, [C.POINTER(fb_config), C.POINTER(vp)]), "fb_load_tables": (i32, [vp, C.c_char_p, C.c_size_t]),
+        "fb_destroy": (i32, [vp]), "fb_sync": (i32, [vp]),
+        "fb_init_trim": (i32, [vp, C.POINTER(fb_trim_params_soa), _DP, _DP]), "fb_init": (i32, [vp, C.POINTER(fb_init_soa)]),
+        "fb_init_state": (i32, [vp, _DP, u8p, u8p]),
+        "fb_set_input": (i32, [vp, i32, _DP, i64]), "fb_get_input": (i32, [vp, i32, _DP]),
+        "fb_schedule_inputs": (i32, [vp, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32), _DP]),
+        "fb_step": (i32, [vp, dbl]), "fb_run": (i32, [vp]), "fb_time": (i32, [vp, _DP, C.POINTER(i64)]),
+        "fb_nx": (i32, [vp, C.POINTER(i32)]), "fb_get_state": (i32, [vp, _DP]), "fb_get_discrete": (i32, [vp, u8p, u8p]),
+        "fb_get_output": (i32, [vp, i32, _DP]), "fb_status": (i32, [vp, C.POINTER(i32)]),
+        "fb_log_info": (i32, [vp, C.POINTER(i64), C.POINTER(i32)]), "fb_log_times": (i32, [vp, _DP]),
+        "fb_log_fetch": (i32, [vp, i32, _DP]), "fb_stats": (i32, [vp, i32, C.POINTER(fb_moments)]),
+        "fb_rhs": (i32, [vp, _DP]), "fb_counters": (i32, [vp, C.POINTER(i64), C.POINTER(i64)]),
+        "fb_device_state": (i32, [vp, C.POINTER(vp), C.POINTER(i64)]), "fb_stream": (i32, [vp, C.POINTER(vp)]),
+    }
+    for name in EXPORTS:
+        f = getattr(lib, name)   # AttributeError if the library does not export a declared symbol
+        f.restype, f.argtypes = sig[name]
+    _lib = lib
+    return lib
+
+
+def _ck(rc, lib):
+    if rc != 0:
+        raise FlightBatchError(f"flightbatch error {rc}: {lib.fb_last_error().decode()}")
+
+
+def _dp(a):
+    return a.ctypes.data_as(_DP)
+
+
+# ----------------------------------------------------------------------------- model definitions
+class WA:
+    kin = DEFS["FB_WA"]
+
+
+class NED:
+    kin = DEFS["FB_NED"]
+
+
+class ECEF:
+    kin = DEFS["FB_ECEF"]
+
+
+class _Aircraft:
+    variant = None
+
+    def __init__(self, kinematics=None):
+        self.kinematics = kinematics if kinematics is not None else WA()
+
+
+class Cessna172Sv0(_Aircraft):
+    variant = DEFS["FB_C172S"]
+
+
+class Cessna172Xv0(_Aircraft):
+    variant = DEFS["FB_C172X0"]
+
+
+class Cessna172Xv1(_Aircraft):
+    variant = DEFS["FB_C172X1"]
+
+
+class Cessna172Xv2(_Aircraft):
+    variant = DEFS["FB_C172X2"]
+
+
+class SimpleWorld:
+    """SimpleWorld(aircraft, SimpleAtmosphere(), HorizontalTerrain()) — lib/FlightPhysics/src/world.jl:20-24"""
+
+    def __init__(self, aircraft=None):
+        self.aircraft = aircraft if aircraft is not None else Cessna172Sv0()
+
+
+class TrimParameters:
+    """C172.TrimParameters (c172.jl:806-818), one value or one array of N values per field."""
+    FIELDS = dict(lat=0.0, lon=0.0, h_e=1050.0, psi_nb=0.0, EAS=50.0, gamma_wb_n=0.0, psi_wb_dot=0.0, theta_wb_dot=0.0,
+                  beta_a=0.0, fuel_load=0.5, mixture=0.5, flaps=0.0,
+                  m_pilot=75.0, m_copilot=75.0, m_lpass=0.0, m_rpass=0.0, m_baggage=50.0)
+
+    def __init__(self, **kw):
+        for k in kw:
+            if k not in self.FIELDS:
+                raise TypeError(f"TrimParameters has no field {k}")
+        self.values = dict(kw)
+
+
+class Init:
+    """C172.Init(KinInit(q_nb, location, h, ω_wb_b, v_eb_n), SystemsInitializer(...)) — c172.jl:773-794"""
+    FIELDS = dict(q0=1.0, q1=0.0, q2=0.0, q3=0.0, lat=0.0, lon=0.0, h_e=0.0, w0=0.0, w1=0.0, w2=0.0, vN=0.0, vE=0.0, vD=0.0,
+                  n_eng=0.0, engine_state=0.0, throttle=0.0, mixture=0.5, elevator=0.0, aileron=0.0, rudder=0.0, flaps=0.0,
+                  brake_left=0.0, brake_right=0.0, fuel_load=0.5, m_pilot=75.0, m_copilot=75.0, m_lpass=0.0, m_rpass=0.0,
+                  m_baggage=50.0, stall=0.0, alpha_filt=0.0, beta_filt=0.0)
+
+    def __init__(self, **kw):
+        for k in kw:
+            if k not in self.FIELDS:
+                raise TypeError(f"Init has no field {k}")
+        self.values = dict(kw)
+
+
+class C172:
+    TrimParameters = TrimParameters
+    Init = Init
+
+
+class _InputProxy:
+    """sim.u.<field>: read returns an [N] array, assignment broadcasts a scalar or uploads an [N] array.
+    Mirrors direct mutation of nested inputs in the reference (README.md:166)."""
+
+    def __init__(self, sim):
+        object.__setattr__(self, "_sim", sim)
+
+    def __getattr__(self, name):
+        if name not in INPUT_NAMES:
+            raise AttributeError(name)
+        return self._sim.get_input(INPUT_NAMES[name])
+
+    def __setattr__(self, name, value):
+        if name not in INPUT_NAMES:
+            raise AttributeError(name)
+        self._sim.set_input(INPUT_NAMES[name], value)
+
+    __getitem__ = __getattr__
+    __setitem__ = __setattr__
+
+
+class _OutputProxy:
+    def __init__(self, sim):
+        self._sim = sim
+
+    def __getattr__(self, name):
+        if name not in OUTPUT_NAMES:
+            raise AttributeError(name)
+        return self._sim.get_output(OUTPUT_NAMES[name])
+
+    __getitem__ = __getattr__
+
+
+class BatchSimulation:
+    """N independent `Simulation(world; dt, Δt, t_start, t_end, saveat)` stepped in lock-step on one B200."""
+
+    def __init__(self, world=None, n=1, dt=0.02, Dt=None, t_start=0.0, t_end=10000.0, saveat=None, log_fields=(),
+                 device=0, member_offset=0, steps_per_launch=0, tables_path=None):
+        self._h = None
+        self._lib = load_library()
+        world = world if world is not None else SimpleWorld()
+        ac = world.aircraft
+        cfg = fb_config()
+        cfg.variant = ac.variant
+        cfg.kinematics = ac.kinematics.kin
+        cfg.n_members = int(n)
+        cfg.member_offset = int(member_offset)
+        cfg.dt = float(dt)
+        cfg.Dt = float(dt if Dt is None else Dt)
+        cfg.t_start = float(t_start)
+        cfg.t_end = float(t_end)
+        cfg.device = int(device)
+        fields = [OUTPUT_NAMES[f] if isinstance(f, str) else int(f) for f in log_fields]
+        cfg.log_every = 0 if (saveat is None or not fields) else max(1, int(round(saveat / dt)))
+        cfg.log_n_fields = len(fields)
+        for i, f in enumerate(fields):
+            cfg.log_fields[i] = f
+        cfg.steps_per_launch = int(steps_per_launch)
+        self.cfg = cfg
+        self.n = int(n)
+        self.dt = float(dt)
+        self.log_fields = fields
+        h = C.c_void_p()
+        _ck(self._lib.fb_create(C.byref(cfg), C.byref(h)), self._lib)
+        self._h = h
+        blob = open(tables_path or TABLES_PATH, "rb").read()
+        _ck(self._lib.fb_load_tables(self._h, blob, len(blob)), self._lib)
+        nx = C.c_int32()
+        _ck(self._lib.fb_nx(self._h, C.byref(nx)), self._lib)
+        self.nx = nx.value
+        self.u = _InputProxy(self)
+        self.y = _OutputProxy(self)
+
+    def close(self):
+        if self._h is not None:
+            self._lib.fb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers
+    def _col(self, v, keep):
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), (self.n,)))
+        keep.append(a)
+        return _dp(a)
+
+    # -- init!(sim, ...)
+    def init(self, init=None, **kw):
+        """init!(sim, C172.TrimParameters(...)) or init!(sim, C172.Init(...)); returns (success[N], trim_state[7,N], cost[N]) for trims."""
+        if init is None:
+            init = TrimParameters(**kw)
+        keep = []
+        if isinstance(init, TrimParameters):
+            p = fb_trim_params_soa()
+            v = init.values
+            for k in ("lat", "lon", "h_e", "psi_nb", "EAS", "gamma_wb_n", "psi_wb_dot", "theta_wb_dot", "beta_a", "fuel_load", "mixture", "flaps"):
+                if k in v:
+                    setattr(p, k, self._col(v[k], keep))
+            for j, k in enumerate(("m_pilot", "m_copilot", "m_lpass", "m_rpass", "m_baggage")):
+                if k in v:
+                    p.payload[j] = self._col(v[k], keep)
+            ts = np.zeros((7, self.n))
+            cost = np.zeros(self.n)
+            _ck(self._lib.fb_init_trim(self._h, C.byref(p), _dp(ts), _dp(cost)), self._lib)
+            return self.status() != DEFS["FB_ST_TRIM_FAILED"], ts, cost
+        if isinstance(init, Init):
+            ic = fb_init_soa()
+            v = init.values
+            for j in range(4):
+                if f"q{j}" in v:
+                    ic.q_nb[j] = self._col(v[f"q{j}"], keep)
+            for j in range(3):
+                if f"w{j}" in v:
+                    ic.w_wb_b[j] = self._col(v[f"w{j}"], keep)
+            for j, k in enumerate(("vN", "vE", "vD")):
+                if k in v:
+                    ic.v_eb_n[j] = self._col(v[k], keep)
+            for k in ("lat", "lon", "h_e", "n_eng", "engine_state", "throttle", "mixture", "elevator", "aileron", "rudder", "flaps",
+                      "brake_left", "brake_right", "fuel_load", "stall", "alpha_filt", "beta_filt"):
+                if k in v:
+                    setattr(ic, k, self._col(v[k], keep))
+            for j, k in enumerate(("m_pilot", "m_copilot", "m_lpass", "m_rpass", "m_baggage")):
+                if k in v:
+                    ic.payload[j] = self._col(v[k], keep)
+            _ck(self._lib.fb_init(self._h, C.byref(ic)), self._lib)
+            return None
+        raise TypeError("init! expects C172.TrimParameters or C172.Init")
+
+    def init_state(self, x, stall=None, eng_state=None):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert x.shape == (self.nx, self.n)
+        u8 = C.POINTER(C.c_uint8)
+        st = None if stall is None else np.ascontiguousarray(stall, dtype=np.uint8)
+        en = None if eng_state is None else np.ascontiguousarray(eng_state, dtype=np.uint8)
+        _ck(self._lib.fb_init_state(self._h, _dp(x), st.ctypes.data_as(u8) if st is not None else None,
+                                    en.ctypes.data_as(u8) if en is not None else None), self._lib)
+
+    # -- inputs
+    def set_input(self, field, value):
+        field = INPUT_NAMES[field] if isinstance(field, str) else int(field)
+        a = np.asarray(value, dtype=np.float64)
+        if a.ndim == 0:
+            a1 = np.array([float(a)])
+            _ck(self._lib.fb_set_input(self._h, field, _dp(a1), 0), self._lib)
+        else:
+            a = np.ascontiguousarray(a)
+            assert a.shape == (self.n,)
+            _ck(self._lib.fb_set_input(self._h, field, _dp(a), 1), self._lib)
+
+    def get_input(self, field):
+        field = INPUT_NAMES[field] if isinstance(field, str) else int(field)
+        out = np.zeros(self.n)
+        _ck(self._lib.fb_get_input(self._h, field, _dp(out)), self._lib)
+        return out
+
+    def schedule_inputs(self, member, step, field, value):
+        """Declarative user_callback! replacement: piecewise-constant inputs (see fb_schedule_inputs)."""
+        member = np.ascontiguousarray(member, dtype=np.int64)
+        step = np.ascontiguousarray(step, dtype=np.int64)
+        field = np.ascontiguousarray(field, dtype=np.int32)
+        value = np.ascontiguousarray(value, dtype=np.float64)
+        n = len(member)
+        assert len(step) == n and len(field) == n and len(value) == n
+        _ck(self._lib.fb_schedule_inputs(self._h, n, member.ctypes.data_as(C.POINTER(C.c_int64)), step.ctypes.data_as(C.POINTER(C.c_int64)),
+                                         field.ctypes.data_as(C.POINTER(C.c_int32)), _dp(value)), self._lib)
+
+    # -- step! / run!
+    def step(self, t_advance=None):
+        _ck(self._lib.fb_step(self._h, float(self.dt if t_advance is None else t_advance)), self._lib)
+
+    def run(self):
+        _ck(self._lib.fb_run(self._h), self._lib)
+
+    def sync(self):
+        _ck(self._lib.fb_sync(self._h), self._lib)
+
+    # -- read-back
+    @property
+    def t(self):
+        t = C.c_double()
+        ns = C.c_int64()
+        _ck(self._lib.fb_time(self._h, C.byref(t), C.byref(ns)), self._lib)
+        return t.value
+
+    @property
+    def n_steps(self):
+        t = C.c_double()
+        ns = C.c_int64()
+        _ck(self._lib.fb_time(self._h, C.byref(t), C.byref(ns)), self._lib)
+        return ns.value
+
+    @property
+    def x(self):
+        out = np.zeros((self.nx, self.n))
+        _ck(self._lib.fb_get_state(self._h, _dp(out)), self._lib)
+        return out
+
+    @property
+    def xdot(self):
+        out = np.zeros((self.nx, self.n))
+        _ck(self._lib.fb_rhs(self._h, _dp(out)), self._lib)
+        return out
+
+    def discrete(self):
+        st = np.zeros(self.n, dtype=np.uint8)
+        en = np.zeros(self.n, dtype=np.uint8)
+        u8 = C.POINTER(C.c_uint8)
+        _ck(self._lib.fb_get_discrete(self._h, st.ctypes.data_as(u8), en.ctypes.data_as(u8)), self._lib)
+        return st, en
+
+    def status(self):
+        out = np.zeros(self.n, dtype=np.int32)
+        _ck(self._lib.fb_status(self._h, out.ctypes.data_as(C.POINTER(C.c_int32))), self._lib)
+        return out
+
+    def get_output(self, field):
+        field = OUTPUT_NAMES[field] if isinstance(field, str) else int(field)
+        out = np.zeros(self.n)
+        _ck(self._lib.fb_get_output(self._h, field, _dp(out)), self._lib)
+        return out
+
+    def stats(self, field):
+        field = OUTPUT_NAMES[field] if isinstance(field, str) else int(field)
+        m = fb_moments()
+        _ck(self._lib.fb_stats(self._h, field, C.byref(m)), self._lib)
+        return dict(count=m.count, sum=m.sum, sum_sq=m.sum_sq, min=m.min, max=m.max)
+
+    def counters(self):
+        a, b = C.c_int64(), C.c_int64()
+        _ck(self._lib.fb_counters(self._h, C.byref(a), C.byref(b)), self._lib)
+        return dict(kernel_launches=a.value, rhs_evals=b.value)
+
+    def stream_handle(self):
+        p = C.c_void_p()
+        _ck(self._lib.fb_stream(self._h, C.byref(p)), self._lib)
+        return p.value
+
+    def device_state(self):
+        p = C.c_void_p()
+        pitch = C.c_int64()
+        _ck(self._lib.fb_device_state(self._h, C.byref(p), C.byref(pitch)), self._lib)
+        return p.value, pitch.value
+
+
+class TimeSeries:
+    """TimeSeries(sim) (sim.jl:644-704): columnar view over the decimated device log; `ts.theta` is [n_samples, N]."""
+
+    def __init__(self, sim):
+        self._sim = sim
+        ns, nf = C.c_int64(), C.c_int32()
+        _ck(sim._lib.fb_log_info(sim._h, C.byref(ns), C.byref(nf)), sim._lib)
+        self.n_samples = ns.value
+        self.t = np.zeros(self.n_samples)
+        if self.n_samples:
+            _ck(sim._lib.fb_log_times(sim._h, _dp(self.t)), sim._lib)
+        self._cache = {}
+
+    def __getattr__(self, name):
+        if name.startswith("_") or name not in OUTPUT_NAMES:
+            raise AttributeError(name)
+        if name not in self._cache:
+            out = np.zeros((self.n_samples, self._sim.n))
+            _ck(self._sim._lib.fb_log_fetch(self._sim._h, OUTPUT_NAMES[name], _dp(out)), self._sim._lib)
+            self._cache[name] = out
+        return self._cache[name]
+
+    __getitem__ = __getattr__
+
+
+# reference-style free functions (Julia's init!, step!, run!)
+def init_b(sim, *a, **kw):
+    return sim.init(*a, **kw)
+
+
+def step_b(sim, *a):
+    return sim.step(*a)
+
+
+def run_b(sim):
+    return sim.run()

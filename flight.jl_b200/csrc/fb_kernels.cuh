@@ -1,0 +1,219 @@
+// fb_kernels.cuh — ensemble kernels: fused K-step RK4 integrator, single RHS (test hook), initialisers.
+// One thread per aircraft; state is struct-of-arrays in HBM (component-major, member fastest) and lives in
+// registers / local scratch for the K fused steps of one launch.
+#pragma once
+#include "fb_physics.cuh"
+#include "fb_avionics.cuh"
+
+#define FB_BLOCK 128
+
+struct EnsembleDev {
+    double* x;            // [NX][pitch]
+    double* u;            // [FB_U__COUNT][pitch]
+    unsigned char* stall; // [pitch]
+    unsigned char* eng;   // [pitch]
+    int* status;          // [pitch]
+    double* ctl;          // [FB_CTL_STATE_COUNT][pitch] avionics discrete state (C172X1/X2)
+    long long pitch;
+    long long n;
+    // input schedule, CSR by member: events of member i are ev_*[ev_off[i] .. ev_off[i+1]) sorted by step
+    const long long* ev_off;
+    const long long* ev_step;
+    const int* ev_field;
+    const double* ev_value;
+    long long* ev_cursor; // [pitch]
+    // decimated log: log[(sample * n_fields + f) * pitch + i]
+    double* log;
+    const int* log_fields;
+    int log_n_fields;
+    int log_every;
+    long long log_capacity;
+    FbDeviceTables tables;
+};
+
+// Stage the lookup-table pack into shared memory with one bulk asynchronous copy (TMA unit,
+// cp.async.bulk + mbarrier complete_tx); every thread of the CTA then waits on the barrier phase.
+FB_DEV void stage_tables(double* smem_tb, const double* __restrict__ gsrc) {
+    __shared__ __align__(8) unsigned long long bar;
+    unsigned bar_a = (unsigned)__cvta_generic_to_shared(&bar);
+    unsigned dst_a = (unsigned)__cvta_generic_to_shared(smem_tb);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((unsigned)FB_TB_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst_a), "l"(gsrc), "r"((unsigned)FB_TB_BYTES), "r"(bar_a) : "memory");
+    }
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar_a) : "memory");
+    }
+}
+
+__host__ __device__ inline double saturate_input(int f, double v) {   // Ranged{T,Min,Max} assignment (types.jl:15-20)
+    if (f <= FB_U_RUDDER_OFFSET) return clampd(v, -1.0, 1.0);
+    if (f <= FB_U_MIXTURE) return clampd(v, 0.0, 1.0);
+    if (f >= FB_U_M_PILOT && f <= FB_U_M_BAGGAGE) return clampd(v, 0.0, 100.0);
+    if (f == FB_U_T_SL) return clampd(v, isa::T_std - 50.0, isa::T_std + 50.0);
+    if (f == FB_U_P_SL) return clampd(v, isa::p_std - 10000.0, isa::p_std + 10000.0);
+    if (f >= FB_U_ACT_THROTTLE && f <= FB_U_ACT_BRAKE_RIGHT) {
+        int i = f - FB_U_ACT_THROTTLE;
+        return clampd(v, (i == 0 || i >= 4) ? 0.0 : -1.0, 1.0);
+    }
+    return avionics_saturate_input(f, v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused integrator: K reference steps per launch. Per step:
+//   k1..k4 (inputs and discrete state frozen), x* = x + dt/6 (k1 + 2k2 + 2k3 + k4),
+//   y* = outputs of f(x*), f_step!, f_periodic! (every Dt), user-callback slot (scheduled inputs), save.
+// The derivative evaluated at x* doubles as the next step's k1 unless a callback changed something the
+// RHS reads, in which case it is evaluated again (as the reference always does). The loop below has ONE
+// call site of the RHS; each thread carries its own stage counter, so members that need the extra
+// evaluation simply run one iteration out of phase with their warp neighbours.
+template <int VAR, int KIN>
+__global__ void __launch_bounds__(FB_BLOCK, 2)
+step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic_every, double Dt,
+            unsigned long long* rhs_count) {
+    typedef Lay<VAR, KIN> L;
+    constexpr int NX = L::NX;
+    extern __shared__ __align__(16) double smem_tb[];
+    stage_tables(smem_tb, E.tables.pack);
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= E.n) return;
+    int status = E.status[i];
+    if (status != FB_ST_RUNNING) return;
+    MemberIn u; u.u = E.u + i; u.pitch = E.pitch;
+    double x[NX], xs[NX], acc[NX], k[NX];
+#pragma unroll
+    for (int c = 0; c < NX; c++) { x[c] = E.x[(long long)c * E.pitch + i]; xs[c] = x[c]; }
+    int stall = E.stall[i], eng = E.eng[i];
+    long long ev_cur = E.ev_off ? E.ev_off[i] + E.ev_cursor[i] : 0;
+    const long long ev_end = E.ev_off ? E.ev_off[i + 1] : 0;
+    CtlState cs;
+    if (VAR >= FB_C172X1) cs.load(E.ctl + i, E.pitch);
+    // inputs scheduled at or before the current step index are in force from the start of this launch
+    while (ev_cur < ev_end && E.ev_step[ev_cur] <= step0) {
+        int f = E.ev_field[ev_cur];
+        u.set(f, saturate_input(f, E.ev_value[ev_cur]));
+        ev_cur++;
+    }
+
+    int stage = 0, done = 0;
+    unsigned n_rhs = 0;
+    bool pending = false;
+    const double h2 = 0.5 * dt, h6 = dt * (1.0 / 6.0);
+    for (;;) {
+        RhsOut y;
+        rhs<VAR, KIN, false>(xs, k, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr);
+        n_rhs++;
+        if (stage == 0) {
+            if (pending) {   // xs == x == x*: this evaluation is the reference's FSAL-last one, y = y*
+                pending = false;
+                done++;
+                if (y.err) { status = y.err; break; }
+                const long long step_idx = step0 + done;
+                const bool ctl_due = (VAR >= FB_C172X1) && (step_idx % periodic_every) == 0;
+                const bool log_due = E.log_every > 0 && E.log_n_fields > 0 && (step_idx % E.log_every) == 0 &&
+                                     (step_idx / E.log_every) < E.log_capacity;
+                YFull yf;
+                const int stall_y = stall, eng_y = eng;
+                if (ctl_due || log_due) {   // the saved / fed-back y is the one left by f(x*), before any callback
+                    RhsOut y2; double kd[NX];
+                    rhs_with_outputs<VAR, KIN>(xs, kd, stall, eng, u, smem_tb, E.tables.geoid, &y2, &yf);
+                }
+                bool changed = f_step<VAR, KIN>(x, stall, eng, u, y, status);
+                if (status != FB_ST_RUNNING) break;
+                if (ctl_due) changed |= avionics_periodic<VAR, KIN>(yf, y, u, cs, E.tables, Dt);
+                while (ev_cur < ev_end && E.ev_step[ev_cur] <= step_idx) {
+                    int f = E.ev_field[ev_cur];
+                    u.set(f, saturate_input(f, E.ev_value[ev_cur]));
+                    ev_cur++;
+                    changed = true;
+                }
+                if (log_due) {
+                    const long long smp = step_idx / E.log_every;
+                    for (int f = 0; f < E.log_n_fields; f++)
+                        E.log[(smp * E.log_n_fields + f) * E.pitch + i] = pick_output(yf, stall_y, eng_y, cs, E.log_fields[f]);
+                }
+#pragma unroll
+                for (int c = 0; c < NX; c++) xs[c] = x[c];
+                if (done == n_steps) break;
+                if (changed) continue;            // re-evaluate k1 with the new x / s / u
+            } else if (y.err) { status = y.err; break; }
+#pragma unroll
+            for (int c = 0; c < NX; c++) { acc[c] = k[c]; xs[c] = fma(h2, k[c], x[c]); }
+            stage = 1;
+        } else {
+            if (y.err) { status = y.err; break; }
+            if (stage == 1) {
+#pragma unroll
+                for (int c = 0; c < NX; c++) { acc[c] = fma(2.0, k[c], acc[c]); xs[c] = fma(h2, k[c], x[c]); }
+                stage = 2;
+            } else if (stage == 2) {
+#pragma unroll
+                for (int c = 0; c < NX; c++) { acc[c] = fma(2.0, k[c], acc[c]); xs[c] = fma(dt, k[c], x[c]); }
+                stage = 3;
+            } else {
+#pragma unroll
+                for (int c = 0; c < NX; c++) { x[c] = fma(h6, acc[c] + k[c], x[c]); xs[c] = x[c]; }
+                stage = 0; pending = true;
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NX; c++) E.x[(long long)c * E.pitch + i] = x[c];
+    E.stall[i] = (unsigned char)stall; E.eng[i] = (unsigned char)eng; E.status[i] = status;
+    if (E.ev_off) E.ev_cursor[i] = ev_cur - E.ev_off[i];
+    if (VAR >= FB_C172X1) cs.store(E.ctl + i, E.pitch);
+    if (rhs_count) atomicAdd(rhs_count, (unsigned long long)n_rhs);
+}
+
+// f_ode!(world) at the current state: test hook + reinit! evaluation
+template <int VAR, int KIN>
+__global__ void __launch_bounds__(FB_BLOCK, 2)
+rhs_kernel(EnsembleDev E, double* xdot, double* alpha_out, int* wow_out, int* err_out) {
+    typedef Lay<VAR, KIN> L;
+    constexpr int NX = L::NX;
+    extern __shared__ __align__(16) double smem_tb[];
+    stage_tables(smem_tb, E.tables.pack);
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= E.n) return;
+    MemberIn u; u.u = E.u + i; u.pitch = E.pitch;
+    double x[NX], k[NX];
+#pragma unroll
+    for (int c = 0; c < NX; c++) x[c] = E.x[(long long)c * E.pitch + i];
+    RhsOut y;
+    rhs<VAR, KIN, false>(x, k, E.stall[i], E.eng[i], u, smem_tb, E.tables.geoid, y, nullptr);
+#pragma unroll
+    for (int c = 0; c < NX; c++) xdot[(long long)c * E.pitch + i] = k[c];
+    if (alpha_out) alpha_out[i] = y.alpha;
+    if (wow_out) wow_out[i] = y.wow;
+    if (err_out) err_out[i] = y.err;
+}
+
+// output pass: one fb_output field of every member from the current state (the y the reference would hold
+// after an f_ode! at this state)
+template <int VAR, int KIN>
+__global__ void __launch_bounds__(FB_BLOCK, 2)
+output_kernel(EnsembleDev E, int field, double* out) {
+    typedef Lay<VAR, KIN> L;
+    constexpr int NX = L::NX;
+    extern __shared__ __align__(16) double smem_tb[];
+    stage_tables(smem_tb, E.tables.pack);
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= E.n) return;
+    MemberIn u; u.u = E.u + i; u.pitch = E.pitch;
+    double x[NX];
+#pragma unroll
+    for (int c = 0; c < NX; c++) x[c] = E.x[(long long)c * E.pitch + i];
+    CtlState cs;
+    if (VAR >= FB_C172X1) cs.load(E.ctl + i, E.pitch);
+    YFull yf; RhsOut y; double k[NX];
+    rhs<VAR, KIN, true>(x, k, E.stall[i], E.eng[i], u, smem_tb, E.tables.geoid, y, &yf);
+    out[i] = pick_output(yf, E.stall[i], E.eng[i], cs, field);
+}

@@ -1,0 +1,55 @@
+// fb_math.cuh — FP64 vector/quaternion helpers for the batched C172 kernels (sm_100a).
+// Reference semantics: lib/FlightPhysics/src/quaternions.jl:109-115, attitude.jl:98-118.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#define FB_DEV __device__ __forceinline__
+#define FB_PI 3.14159265358979323846
+
+struct d3 { double x, y, z; };
+struct q4 { double w, x, y, z; };
+
+FB_DEV d3 mk3(double x, double y, double z) { d3 r; r.x = x; r.y = y; r.z = z; return r; }
+FB_DEV d3 operator+(d3 a, d3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+FB_DEV d3 operator-(d3 a, d3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+FB_DEV d3 operator-(d3 a) { return mk3(-a.x, -a.y, -a.z); }
+FB_DEV d3 operator*(double s, d3 a) { return mk3(s * a.x, s * a.y, s * a.z); }
+FB_DEV double dot(d3 a, d3 b) { return fma(a.x, b.x, fma(a.y, b.y, a.z * b.z)); }
+FB_DEV d3 cross(d3 a, d3 b) {
+    return mk3(fma(a.y, b.z, -a.z * b.y), fma(a.z, b.x, -a.x * b.z), fma(a.x, b.y, -a.y * b.x));
+}
+FB_DEV q4 mkq(double w, double x, double y, double z) { q4 r; r.w = w; r.x = x; r.y = y; r.z = z; return r; }
+FB_DEV q4 qconj(q4 a) { return mkq(a.w, -a.x, -a.y, -a.z); }
+// Hamilton product
+FB_DEV q4 qmul(q4 a, q4 b) {
+    return mkq(a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z,
+               a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+               a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x,
+               a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w);
+}
+// v_a = q_ab * v_b  (v + 2 q_im x (q_re v + q_im x v))
+FB_DEV d3 qrot(q4 q, d3 v) {
+    d3 qi = mk3(q.x, q.y, q.z);
+    d3 t = cross(qi, v);
+    t = mk3(fma(q.w, v.x, t.x), fma(q.w, v.y, t.y), fma(q.w, v.z, t.z));
+    d3 c = cross(qi, t);
+    return mk3(fma(2.0, c.x, v.x), fma(2.0, c.y, v.y), fma(2.0, c.z, v.z));
+}
+FB_DEV d3 qrot_inv(q4 q, d3 v) { return qrot(qconj(q), v); }
+// 0.5 * q * (0, w)
+FB_DEV q4 qdt(q4 q, d3 w) {
+    return mkq(-0.5 * (q.x * w.x + q.y * w.y + q.z * w.z),
+               0.5 * (q.w * w.x + q.y * w.z - q.z * w.y),
+               0.5 * (q.w * w.y - q.x * w.z + q.z * w.x),
+               0.5 * (q.w * w.z + q.x * w.y - q.y * w.x));
+}
+// cos(a/2), sin(a/2) of a = atan2(y, x) without evaluating the angle (|(x,y)| > 0)
+FB_DEV void half_angle(double y, double x, double& ch, double& sh) {
+    double r = sqrt(fma(x, x, y * y));
+    double c = x / r, s = y / r;
+    if (c >= 0.0) { ch = sqrt(0.5 * (1.0 + c)); sh = s / (2.0 * ch); }
+    else { double a = sqrt(0.5 * (1.0 - c)); sh = (s >= 0.0 ? a : -a); ch = s / (2.0 * sh); }
+}
+__host__ __device__ inline double clampd(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
+FB_DEV int isign(double a) { return (a > 0.0) - (a < 0.0); }

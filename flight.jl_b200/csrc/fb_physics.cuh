@@ -1,0 +1,797 @@
+// fb_physics.cuh — one-thread-per-aircraft FP64 physics of the Cessna 172 hot path (sm_100a).
+//
+// Continuous right-hand side f_ode!(world) and discrete f_step!(world) of
+//   Cessna172Sv0 / Cessna172Xv* on SimpleWorld(SimpleAtmosphere, HorizontalTerrain)
+// Behavioural spec (reference file:line, paths relative to the reference root):
+//   kinematics   lib/FlightPhysics/src/kinematics.jl:181-223 (WA), :363-409 (NED), :226-229 (renormalise)
+//   geodesy      lib/FlightPhysics/src/geodesy.jl:62-69,103-106,125-129,204-211,367-428,451-467
+//   atmosphere   lib/FlightPhysics/src/atmosphere.jl:116-135,220-242,269-283
+//   aero         lib/FlightApps/src/c172/c172.jl:226-245,307-384
+//   landing gear lib/FlightPhysics/src/landinggear.jl:228-347,411-483
+//   propeller    lib/FlightPhysics/src/propellers.jl:405-452
+//   engine       lib/FlightPhysics/src/piston.jl:314-477,575-603
+//   fuel/payload lib/FlightApps/src/c172/c172.jl:542-554,607-641
+//   dynamics     lib/FlightPhysics/src/dynamics.jl:443-499
+//   actuation    lib/FlightApps/src/c172/c172s/c172s.jl:92-120, c172x/c172x.jl:39-52,127-143
+//
+// This is a B200-first restatement, not a transcription: the dataflow is rearranged so that one RHS
+// needs 6 atan2 + 3 exp/log instead of the reference's 21 atan2 + 8 pow + 5 sincos (results agree to
+// rounding): frame rotations are built from direction cosines / half-angle identities instead of
+// angle -> sincos round trips, the local-vertical at the CoM is the n-vector itself, output-only
+// quantities (CAS, total pressure, Euler angles, accelerations) are left to the output pass, mass
+// properties are evaluated in their affine-in-mass form, and a conservative height gate skips the
+// three strut evaluations while the aircraft is well clear of the terrain.
+#pragma once
+#include "fb_math.cuh"
+#include "fb_tables.h"
+#include "../../include/flightbatch.h"
+
+// ------------------------------------------------------------------------------------------- layout
+template <int VAR, int KIN>
+struct Lay {
+    static constexpr int AERO = 0, LDG = 2, FUEL = 8, ENG = 9, ACT = 12;
+    static constexpr int NACT = (VAR == FB_C172S) ? 0 : 7;
+    static constexpr int KINX = 12 + NACT;
+    static constexpr int NKIN = (KIN == FB_WA) ? 9 : (KIN == FB_ECEF ? 8 : 6);
+    static constexpr int DYN = KINX + NKIN;
+    static constexpr int NX = DYN + 6;
+};
+
+namespace wgs {
+constexpr double a = 6378137.0;
+constexpr double f = 1.0 / 298.257223563;
+constexpr double w_ie = 7.292115e-05;
+constexpr double GM = 3.986005e+14;
+constexpr double b = a * (1 - f);
+constexpr double e2 = 2 * f - f * f;
+constexpr double m = w_ie * w_ie * a * a * b / GM;
+constexpr double g_a = 9.7803253359;
+constexpr double g_b = 9.8321849378;
+constexpr double k_g = b * g_b / (a * g_a) - 1;
+}
+namespace isa {
+constexpr double R = 287.05287, gamma = 1.40, T_std = 288.15, p_std = 101325.0, g_std = 9.80665;
+constexpr double rho_std = p_std / (R * T_std);
+}
+
+// flags a single RHS evaluation hands to f_step! and to the status logic
+struct RhsOut {
+    double alpha;       // unclamped aerodynamic AoA (aero.y.α, c172.jl:324,367)
+    int wow;            // bit i = strut i weight-on-wheels
+    int crash;          // 2 bits per strut: 0 none, 1 strut/terrain angle > 60 deg, 2 compression rate > 10 m/s (landinggear.jl:331-347)
+    int err;            // 0 none, FB_ST_BOUNDS / FB_ST_CONTACT_ASSERT (would have thrown inside f_ode!)
+};
+
+// everything the output pass / log / control laws may ask for (filled only by the WY=true instantiation)
+struct YFull {
+    double psi, theta, phi, lat, lon, h_e, h_o;
+    d3 v_eb_n, w_wb_b, w_eb_b;
+    double v_gnd, chi_gnd, gamma_gnd;
+    double TAS, EAS, CAS, M, q;
+    double alpha, beta, alpha_filt, beta_filt, C_L, C_D;
+    int wow;
+    double xi[3], F_dmp[3];
+    double eng_omega, eng_n, eng_MAP, eng_P_shaft, eng_tau_shaft, eng_mdot, fuel_m_total, prop_thrust, prop_J, mass;
+    d3 f_c_c;
+    double act_pos[7], act_cmd[7];
+};
+
+struct MemberIn {       // per-member input view: field f of this member is u[f * pitch]
+    double* u;          // plain (coherent) loads: the owning thread also writes inputs (events, control laws)
+    long long pitch;
+    FB_DEV double operator()(int f) const { return u[(long long)f * pitch]; }
+    FB_DEV void set(int f, double v) const { u[(long long)f * pitch] = v; }
+};
+
+// ------------------------------------------------------------------------------------ interpolation
+// cell index / weight on explicit knots (Gridded(Linear())), coordinate already clamped to the knot span
+FB_DEV void locate(const double* k, int n, double x, int& i, double& w) {
+    int lo = 0;
+#pragma unroll 1
+    for (int j = 1; j < n - 1; j++) lo = (x >= k[j]) ? j : lo;
+    i = lo;
+    w = (x - k[lo]) / (k[lo + 1] - k[lo]);
+}
+FB_DEV double lerp(double a, double b, double w) { return fma(w, b - a, a); }
+FB_DEV double interp1_flat(const double* k, const double* y, int n, double x) {
+    x = clampd(x, k[0], k[n - 1]);
+    int i; double w;
+    locate(k, n, x, i, w);
+    return lerp(y[i], y[i + 1], w);
+}
+// uniform axis k0 + i*dk, n knots; Flat
+FB_DEV void locate_uniform(double k0, double dk, int n, double x, int& i, double& w) {
+    double t = (x - k0) / dk;
+    t = clampd(t, 0.0, (double)(n - 1));
+    i = min((int)t, n - 2);
+    w = t - (double)i;
+}
+
+// geoid undulation, bilinear on the EGM96 15' grid (geodesy.jl:186-211); geoid[lon][lat] float32
+FB_DEV double geoid_height(const float* __restrict__ g, double lat, double lon) {
+    double l = lon + 2.0 * FB_PI;
+    l = l - 2.0 * FB_PI * floor(l / (2.0 * FB_PI));
+    double fi = (lat + 0.5 * FB_PI) / (FB_PI / 720.0);
+    double fj = l / (2.0 * FB_PI / 1440.0);
+    int i = min(max((int)floor(fi), 0), FB_GEOID_NLAT - 2);
+    int j = min(max((int)floor(fj), 0), FB_GEOID_NLON - 2);
+    double u = fi - (double)i, w = fj - (double)j;
+    const float* p = g + (size_t)j * FB_GEOID_NLAT + i;
+    double f00 = (double)__ldg(p), f10 = (double)__ldg(p + 1);
+    double f01 = (double)__ldg(p + FB_GEOID_NLAT), f11 = (double)__ldg(p + FB_GEOID_NLAT + 1);
+    return lerp(lerp(f00, f10, u), lerp(f01, f11, u), w);
+}
+FB_DEV double geoid_at_n(const float* __restrict__ g, d3 n) {
+    double lat = atan2(n.z, sqrt(fma(n.x, n.x, n.y * n.y)));
+    double lon = atan2(n.y, n.x);
+    return geoid_height(g, lat, lon);
+}
+
+// ------------------------------------------------------------------------------------------ geodesy
+FB_DEV void radii(double n3, double& M, double& N) {
+    double fd2 = fma(-wgs::e2 * n3, n3, 1.0);
+    double fd = sqrt(fd2);
+    N = wgs::a / fd;
+    M = N * (1 - wgs::e2) / fd2;
+}
+FB_DEV d3 cartesian_from_geo(d3 n, double h) {
+    double M, N;
+    radii(n.z, M, N);
+    return mk3((N + h) * n.x, (N + h) * n.y, fma(N, 1 - wgs::e2, h) * n.z);
+}
+// ECEF -> (n-vector, ellipsoidal altitude): Fukushima's one-step Halley method (geodesy.jl:367-412)
+FB_DEV void geo_from_cartesian(d3 r, d3& n, double& h) {
+    constexpr double c = wgs::a * wgs::e2;
+    constexpr double ec2 = 1 - wgs::e2;
+    const double ec = sqrt(ec2);
+    double p2 = fma(r.x, r.x, r.y * r.y);
+    double p = sqrt(p2);
+    double az = fabs(r.z);
+    double zc = ec * az, s0 = az, c0 = ec * p;
+    double a02 = fma(s0, s0, c0 * c0);
+    double a0 = sqrt(a02);
+    double a03 = a02 * a0;
+    double sc = s0 * c0;
+    double b0 = 1.5 * c * sc * (fma(p, s0, -zc * c0) * a0 - c * sc);
+    double s1 = fma(zc, a03, c * s0 * s0 * s0) * a03 - b0 * s0;
+    double c1 = fma(p, a03, -c * c0 * c0 * c0) * a03 - b0 * c0;
+    double cc = ec * c1;
+    double s12 = s1 * s1, cc2 = cc * cc;
+    double inv = rsqrt(s12 + cc2);
+    h = (fma(p, cc, s0 * s1) - wgs::a * sqrt(fma(ec2, s12, cc2))) * inv;
+    // cos(lat) = cc/sqrt(s1^2+cc^2), |sin(lat)| = s1/sqrt(s1^2+cc^2)
+    double cl = cc * inv, sl = s1 * inv;
+    sl = (r.z > 0.0) ? sl : ((r.z < 0.0) ? -sl : 0.0);
+    double ip = (p > 0.0) ? 1.0 / p : 0.0;
+    double clon = (p > 0.0) ? r.x * ip : 1.0, slon = r.y * ip;
+    d3 v = mk3(cl * clon, cl * slon, sl);
+    double nn = rsqrt(dot(v, v));
+    n = nn * v;
+}
+FB_DEV double gravity(double n3, double h) {  // Somigliana + 2nd-order altitude term (geodesy.jl:451-467)
+    double s2 = n3 * n3;
+    double g0 = wgs::g_a * fma(wgs::k_g, s2, 1.0) * rsqrt(fma(-wgs::e2, s2, 1.0));
+    return g0 * (1.0 - 2.0 / wgs::a * (1.0 + wgs::f + wgs::m - 2.0 * wgs::f * s2) * h + 3.0 / (wgs::a * wgs::a) * h * h);
+}
+
+// --------------------------------------------------------------------------------------- atmosphere
+struct Air { d3 v_wb_b; double T, p, rho, a, TAS, q, lnp; };  // lnp = log(p / p_std)
+
+__device__ __noinline__ void isa_upper(double hg, double T_sl, double p_sl, double& T, double& p, int& err) {
+    const double beta[7] = {-6.5e-3, 0, 1e-3, 2.8e-3, 0, -2.8e-3, -2e-3};
+    const double hc[7] = {11000, 20000, 32000, 47000, 51000, 71000, 84852};
+    double hb = 0, Tb = T_sl, pb = p_sl;
+    for (int i = 0; i < 7; i++) {
+        double hh = (hg < hc[i]) ? hg : hc[i];
+        double Tn = Tb + beta[i] * (hh - hb);
+        double pn = (beta[i] != 0.0) ? pb * pow(1.0 + beta[i] / Tb * (hh - hb), -isa::g_std / (beta[i] * isa::R))
+                                     : pb * exp(-isa::g_std / (isa::R * Tb) * (hh - hb));
+        if (hg < hc[i]) { T = Tn; p = pn; return; }
+        hb = hc[i]; Tb = Tn; pb = pn;
+    }
+    err = FB_ST_BOUNDS; T = Tb; p = pb;
+}
+FB_DEV void isa_data(double h_o, double T_sl, double p_sl, double& T, double& p, double& lnp, int& err) {
+    if (h_o < -1000.0) err = FB_ST_BOUNDS;
+    double hg = h_o * wgs::a / (wgs::a + h_o);
+    if (hg < 11000.0) {
+        constexpr double beta = -6.5e-3;
+        constexpr double k = -isa::g_std / (beta * isa::R);
+        T = fma(beta, hg, T_sl);
+        lnp = log(p_sl * (1.0 / isa::p_std)) + k * log(T / T_sl);
+        p = isa::p_std * exp(lnp);
+    } else {
+        isa_upper(hg, T_sl, p_sl, T, p, err);
+        lnp = log(p * (1.0 / isa::p_std));
+    }
+}
+
+// ------------------------------------------------------------------------------ PI lane (control.jl:52-81)
+FB_DEV double pi_lane(double input, double x_i, double k_p, double k_i, double k_l, double lo, double hi, double& xdot) {
+    double out_free = fma(k_p, input, x_i);
+    int sat = (out_free >= hi) - (out_free <= lo);
+    bool halted = isign(input * (double)sat) > 0;
+    xdot = (halted ? 0.0 : k_i * input) - k_l * x_i;
+    return clampd(out_free, lo, hi);
+}
+
+FB_DEV double get_mu(double mu_s, double mu_d, double v) {  // landinggear.jl:170-174, v_s 0.005, v_d 0.01
+    double k = clampd((fabs(v) - 0.005) / (0.01 - 0.005), 0.0, 1.0);
+    return k * mu_d + (1.0 - k) * mu_s;
+}
+
+// kinematic data shared by the subsystems of one RHS evaluation
+struct Kin { q4 q_nb, q_eb; d3 n_e, r_eb_e, w_wb_b, w_eb_b, v_eb_b, v_eb_n; double h_e, h_o, lat, lon; };
+
+// one landing-gear unit (strut + contact). Adds its wrench to (F, tau) in body axes.
+FB_DEV void ldg_unit(const Kin& k, const float* __restrict__ geoid, double elev, int surface,
+                     d3 r_bs_b, double k_s, double k_d_ext, double k_d_cmp,
+                     bool has_steering, bool steering_engaged, double steer_input, double brake,
+                     double x0, double x1, double& xd0, double& xd1, d3& F, d3& tau, int leg, RhsOut& out,
+                     double* xi_out, double* fdmp_out) {
+    const d3 e3 = mk3(0.0, 0.0, 1.0);
+    d3 ks_e = qrot(k.q_eb, e3);
+    d3 r_bs_e = qrot(k.q_eb, r_bs_b);
+    d3 r_es_e = k.r_eb_e + r_bs_e;
+    d3 n_t; double he_w;
+    geo_from_cartesian(r_es_e, n_t, he_w);
+    if (he_w < -1000.0) out.err = FB_ST_BOUNDS;
+    double he_t = elev + geoid_at_n(geoid, n_t);
+    if (he_t < -1000.0 || elev < -1000.0) out.err = FB_ST_BOUNDS;
+    double dh = he_w - he_t;
+    bool wow = dh <= 0.0;
+    double vx = 0.0, vy = 0.0;
+    double F_dmp = 0.0;
+    q4 q_bc = mkq(1, 0, 0, 0);
+    d3 r_bc_b = r_bs_b;
+    if (wow) {
+        out.wow |= (1 << leg);
+        d3 r_et_e = cartesian_from_geo(n_t, he_t);
+        d3 r_st_e = r_et_e - r_es_e;
+        q4 q_en = qmul(k.q_eb, qconj(k.q_nb));          // product first, then rotate: keeps the reference's norm defect
+        d3 ut_e = qrot(q_en, e3);                       // terrain normal (NED down) in ECEF: q_en(0,0,1)
+        double ut_ks = dot(ut_e, ks_e);
+        double l = dot(ut_e, r_st_e) / ut_ks;
+        double alpha_ts = acos(fmax(fmin(ut_ks, 1.0), -1.0));
+        bool crash_angle = alpha_ts * (180.0 / FB_PI) > 60.0;
+        if (crash_angle) out.crash |= (1 << (2 * leg));
+        double xi = fmin(0.0, l);
+        r_bc_b = mk3(r_bs_b.x, r_bs_b.y, r_bs_b.z + xi);
+        d3 v_b = k.v_eb_b + cross(k.w_eb_b, r_bc_b);
+        double cs = 1.0, sn = 0.0;  // wheel heading in strut axes
+        if (has_steering) {
+            if (steering_engaged) sincos(steer_input * (FB_PI / 6), &sn, &cs);
+            else { double r = sqrt(fma(v_b.x, v_b.x, v_b.y * v_b.y)); if (r > 0.0) { cs = v_b.x / r; sn = v_b.y / r; } }
+        }
+        // q_nw = q_nb o Rz(psi_sw) applied to e1 (landinggear.jl:291-296); Rz(psi) built from (cos, sin) by half angles
+        double chw, shw;
+        half_angle(sn, cs, chw, shw);
+        d3 iw_n = qrot(qmul(k.q_nb, mkq(chw, 0.0, 0.0, shw)), mk3(1.0, 0.0, 0.0));
+        double ch, sh;
+        half_angle(iw_n.y, iw_n.x, ch, sh);              // contact frame = NED rotated about down by azimuth(iw_n)
+        q4 q_nc = mkq(ch, 0.0, 0.0, sh);
+        q_bc = qmul(qconj(k.q_nb), q_nc);
+        d3 v_c_body = qrot_inv(q_bc, v_b);
+        d3 ks_c = qrot_inv(q_bc, e3);
+        double xi_dot = -v_c_body.z / ks_c.z;
+        if (-xi_dot > 10.0 && !crash_angle) out.crash |= (2 << (2 * leg));
+        double k_d = (xi_dot > 0.0) ? k_d_ext : k_d_cmp;
+        F_dmp = -(k_s * xi + k_d * xi_dot);
+        double vz = fma(ks_c.z, xi_dot, v_c_body.z);
+        if (!(fabs(vz) < 1e-8)) out.err = FB_ST_CONTACT_ASSERT;
+        vx = fma(ks_c.x, xi_dot, v_c_body.x);
+        vy = fma(ks_c.y, xi_dot, v_c_body.y);
+    }
+    if (xi_out) { *xi_out = wow ? (r_bc_b.z - r_bs_b.z) : 0.0; *fdmp_out = F_dmp; }
+    // friction regulator (landinggear.jl:401-409,417-419): k_p 5, k_i 400, k_l 0.2, bounds +-1
+    double o0 = pi_lane(-vx, x0, 5.0, 400.0, 0.2, -1.0, 1.0, xd0);
+    double o1 = pi_lane(-vy, x1, 5.0, 400.0, 0.2, -1.0, 1.0, xd1);
+    if (wow) {
+        double norm_v = sqrt(fma(vx, vx, vy * vy));
+        double mu_roll = get_mu(0.03, 0.02, norm_v);
+        double mu_skid = (surface == 0) ? get_mu(0.75, 0.25, norm_v) : ((surface == 1) ? get_mu(0.25, 0.15, norm_v) : get_mu(0.075, 0.025, norm_v));
+        double mu_x = fma(mu_skid - mu_roll, brake, mu_roll);
+        double psi_cv = (norm_v < 1e-3) ? (FB_PI / 2) : atan2(vy, vx);
+        const double psi_skid = 10 * FB_PI / 180.0;
+        double psi_abs = fabs(psi_cv);
+        double mu_y;
+        if (psi_abs < psi_skid) mu_y = mu_skid * psi_abs / psi_skid;
+        else if (psi_abs > FB_PI - psi_skid) mu_y = mu_skid * (1.0 - (psi_skid + psi_abs - FB_PI) / psi_skid);
+        else mu_y = mu_skid;
+        double sc = fmin(1.0, mu_skid / sqrt(fma(mu_x, mu_x, mu_y * mu_y)));
+        d3 f_c = mk3(o0 * mu_x * sc, o1 * mu_y * sc, -1.0);
+        d3 f_s = qrot(q_bc, f_c);
+        double Nf = fmax(0.0, -F_dmp / f_s.z);
+        d3 F_b = Nf * f_s;
+        F = F + F_b;
+        tau = tau + cross(r_bc_b, F_b);
+    }
+}
+
+// 2-D table on uniform ("scaled") axes with Line extrapolation (piston.jl:84-104): 2 x 9 tables
+FB_DEV double interp_2x9_line(const double* y, double n0, double n1, double x0, double x1, double n, double x) {
+    double ns = clampd(n, n0, n1), xs = clampd(x, x0, x1);
+    double u = (ns - n0) / (n1 - n0);
+    double t = (xs - x0) / ((x1 - x0) / 8.0);
+    int j = min((int)t, 7);
+    double w = t - (double)j;
+    double f00 = y[j], f01 = y[j + 1], f10 = y[9 + j], f11 = y[9 + j + 1];
+    double v = lerp(lerp(f00, f01, w), lerp(f10, f11, w), u);
+    double g0 = lerp(f10 - f00, f11 - f01, w) / (n1 - n0);
+    double g1 = lerp(f01 - f00, f11 - f10, u) / ((x1 - x0) / 8.0);
+    return fma(n - ns, g0, fma(x - xs, g1, v));
+}
+
+// ------------------------------------------------------------------------------------------- the RHS
+template <int VAR, int KIN, bool WY>
+FB_DEV void rhs(const double* x, double* xd, int stall, int eng_state, const MemberIn& u,
+                const double* __restrict__ tb, const float* __restrict__ geoid, RhsOut& out, YFull* yf) {
+    typedef Lay<VAR, KIN> L;
+    out.wow = 0; out.crash = 0; out.err = 0;
+    Kin k;
+    k.w_eb_b = mk3(x[L::DYN], x[L::DYN + 1], x[L::DYN + 2]);
+    k.v_eb_b = mk3(x[L::DYN + 3], x[L::DYN + 4], x[L::DYN + 5]);
+    // ------------------------------------------------------------------ kinematics
+    if (KIN == FB_WA) {
+        q4 q_wb = mkq(x[L::KINX], x[L::KINX + 1], x[L::KINX + 2], x[L::KINX + 3]);
+        q4 q_ew = mkq(x[L::KINX + 4], x[L::KINX + 5], x[L::KINX + 6], x[L::KINX + 7]);
+        k.h_e = x[L::KINX + 8];
+        double dq12 = 2.0 * q_ew.w * q_ew.x, dq13 = 2.0 * q_ew.w * q_ew.y;
+        double dq24 = 2.0 * q_ew.x * q_ew.z, dq34 = 2.0 * q_ew.y * q_ew.z;
+        // psi_nw = atan2(-(dq34+dq12), dq24-dq13); q_nw = Rz(psi_nw)
+        double yy = -(dq34 + dq12), xx = dq24 - dq13;
+        double rr = sqrt(fma(xx, xx, yy * yy));
+        double c = xx / rr, s = yy / rr;
+        double ch, sh;
+        if (c >= 0.0) { ch = sqrt(0.5 * (1.0 + c)); sh = s / (2.0 * ch); }
+        else { double a = sqrt(0.5 * (1.0 - c)); sh = (s >= 0.0 ? a : -a); ch = s / (2.0 * sh); }
+        q4 q_nw = mkq(ch, 0.0, 0.0, sh);
+        k.q_nb = qmul(q_nw, q_wb);
+        k.q_eb = qmul(q_ew, q_wb);
+        k.n_e = mk3(-(dq24 + dq13), -(dq34 - dq12), -(1.0 - 2.0 * (q_ew.x * q_ew.x + q_ew.y * q_ew.y)));
+        k.lat = atan2(k.n_e.z, sqrt(fma(k.n_e.x, k.n_e.x, k.n_e.y * k.n_e.y)));
+        k.lon = atan2(k.n_e.y, k.n_e.x);
+        k.v_eb_n = qrot(k.q_nb, k.v_eb_b);
+        double M, N;
+        radii(k.n_e.z, M, N);
+        k.r_eb_e = mk3((N + k.h_e) * k.n_e.x, (N + k.h_e) * k.n_e.y, fma(N, 1 - wgs::e2, k.h_e) * k.n_e.z);
+        double wn_x = k.v_eb_n.y / (N + k.h_e), wn_y = -k.v_eb_n.x / (M + k.h_e);
+        d3 w_ew_w = mk3(fma(c, wn_x, s * wn_y), fma(-s, wn_x, c * wn_y), 0.0);  // q_nw'(w_ew_n)
+        d3 w_ew_b = qrot_inv(q_wb, w_ew_w);
+        k.w_wb_b = k.w_eb_b - w_ew_b;
+        q4 d1 = qdt(q_wb, k.w_wb_b), d2 = qdt(q_ew, w_ew_w);
+        xd[L::KINX] = d1.w; xd[L::KINX + 1] = d1.x; xd[L::KINX + 2] = d1.y; xd[L::KINX + 3] = d1.z;
+        xd[L::KINX + 4] = d2.w; xd[L::KINX + 5] = d2.x; xd[L::KINX + 6] = d2.y; xd[L::KINX + 7] = d2.z;
+        xd[L::KINX + 8] = -k.v_eb_n.z;
+    } else if (KIN == FB_NED) {
+        double psi = x[L::KINX], th = x[L::KINX + 1], phi = x[L::KINX + 2];
+        k.lat = x[L::KINX + 3]; k.lon = x[L::KINX + 4]; k.h_e = x[L::KINX + 5];
+        if (fabs(k.lat) > 0.5 * FB_PI || fabs(k.lon) > FB_PI) out.err = FB_ST_BOUNDS;
+        double sps, cps, sth, cth, sph, cph;
+        sincos(0.5 * psi, &sps, &cps); sincos(0.5 * th, &sth, &cth); sincos(0.5 * phi, &sph, &cph);
+        k.q_nb = qmul(qmul(mkq(cps, 0, 0, sps), mkq(cth, 0, sth, 0)), mkq(cph, sph, 0, 0));
+        double sla, cla, slo, clo;
+        sincos(k.lat, &sla, &cla); sincos(k.lon, &slo, &clo);
+        k.n_e = mk3(cla * clo, cla * slo, sla);
+        // q_en = Rz(lon) o Ry(-(lat + pi/2))
+        double sl2, cl2, sa2, ca2;
+        sincos(0.5 * k.lon, &sl2, &cl2); sincos(-0.5 * (k.lat + 0.5 * FB_PI), &sa2, &ca2);
+        q4 q_en = qmul(mkq(cl2, 0, 0, sl2), mkq(ca2, 0, sa2, 0));
+        k.q_eb = qmul(q_en, k.q_nb);
+        k.v_eb_n = qrot(k.q_nb, k.v_eb_b);
+        double M, N;
+        radii(k.n_e.z, M, N);
+        k.r_eb_e = mk3((N + k.h_e) * k.n_e.x, (N + k.h_e) * k.n_e.y, fma(N, 1 - wgs::e2, k.h_e) * k.n_e.z);
+        double wx = k.v_eb_n.y / (N + k.h_e), wy = -k.v_eb_n.x / (M + k.h_e);
+        // latitude as LatLon(NVector(lat, lon)) sees it (kinematics.jl:417): identical to x.lat to rounding
+        d3 w_en_n = mk3(wx, wy, -k.v_eb_n.y * (sla / cla) / (N + k.h_e));
+        d3 w_nb_b = k.w_eb_b - qrot_inv(k.q_nb, w_en_n);
+        k.w_wb_b = k.w_eb_b - qrot_inv(k.q_nb, mk3(wx, wy, 0.0));
+        double sf, cf, st, ct;
+        sincos(phi, &sf, &cf); sincos(th, &st, &ct);
+        double sec = 1.0 / ct, tn = st / ct;
+        xd[L::KINX] = (sf * w_nb_b.y + cf * w_nb_b.z) * sec;
+        xd[L::KINX + 1] = cf * w_nb_b.y - sf * w_nb_b.z;
+        xd[L::KINX + 2] = w_nb_b.x + (sf * w_nb_b.y + cf * w_nb_b.z) * tn;
+        xd[L::KINX + 3] = -wy;
+        xd[L::KINX + 4] = wx / cla;
+        xd[L::KINX + 5] = -k.v_eb_n.z;
+    }
+    if (k.h_e < -1000.0) out.err = FB_ST_BOUNDS;
+    k.h_o = k.h_e - geoid_height(geoid, k.lat, k.lon);
+    if (WY) {
+        q4 q = k.q_nb;
+        if (KIN == FB_NED) { yf->psi = x[L::KINX]; yf->theta = x[L::KINX + 1]; yf->phi = x[L::KINX + 2]; }
+        else {   // REuler(q_nb), attitude.jl:382-390
+            yf->psi = atan2(2.0 * (q.w * q.z + q.x * q.y), 1.0 - 2.0 * (q.y * q.y + q.z * q.z));
+            yf->theta = asin(clampd(2.0 * (q.w * q.y - q.x * q.z), -1.0, 1.0));
+            yf->phi = atan2(2.0 * (q.w * q.x + q.y * q.z), 1.0 - 2.0 * (q.x * q.x + q.y * q.y));
+        }
+        yf->lat = k.lat; yf->lon = k.lon; yf->h_e = k.h_e; yf->h_o = k.h_o;
+        yf->v_eb_n = k.v_eb_n; yf->w_wb_b = k.w_wb_b; yf->w_eb_b = k.w_eb_b;
+        yf->v_gnd = sqrt(dot(k.v_eb_n, k.v_eb_n));
+        bool valid = (KIN == FB_NED) || (yf->v_gnd > 0.1);   // kinematics.jl:212-213 vs :393-394
+        yf->chi_gnd = valid ? atan2(k.v_eb_n.y, k.v_eb_n.x) : 0.0;
+        yf->gamma_gnd = valid ? atan2(-k.v_eb_n.z, sqrt(fma(k.v_eb_n.x, k.v_eb_n.x, k.v_eb_n.y * k.v_eb_n.y))) : 0.0;
+    }
+
+    // ------------------------------------------------------------------ atmosphere + air data
+    Air air;
+    isa_data(k.h_o, u(FB_U_T_SL), u(FB_U_P_SL), air.T, air.p, air.lnp, out.err);
+    air.rho = air.p / (isa::R * air.T);
+    air.a = sqrt(isa::gamma * isa::R * air.T);
+    {
+        d3 wind = mk3(u(FB_U_WIND_N), u(FB_U_WIND_E), u(FB_U_WIND_D));
+        air.v_wb_b = k.v_eb_b - qrot_inv(k.q_nb, wind);
+        double tas2 = dot(air.v_wb_b, air.v_wb_b);
+        air.TAS = sqrt(tas2);
+        air.q = 0.5 * air.rho * tas2;
+    }
+    if (WY) {   // atmosphere.jl:220-242
+        yf->TAS = air.TAS; yf->q = air.q;
+        yf->EAS = air.TAS * sqrt(air.rho / isa::rho_std);
+        yf->M = air.TAS / air.a;
+        double Tt = air.T * (1.0 + (isa::gamma - 1) / 2 * yf->M * yf->M);
+        double pt = air.p * pow(Tt / air.T, isa::gamma / (isa::gamma - 1));
+        yf->CAS = sqrt(2 * isa::gamma / (isa::gamma - 1) * isa::p_std / isa::rho_std * (pow(1.0 + (pt - air.p) / isa::p_std, (isa::gamma - 1) / isa::gamma) - 1.0));
+    }
+
+    // ------------------------------------------------------------------ actuation
+    double a_e, a_a, a_r, a_f, steer, br_l, br_r, throttle;
+    if (VAR == FB_C172S) {
+        double ru = clampd(u(FB_U_RUDDER_OFFSET) + u(FB_U_RUDDER), -1.0, 1.0);
+        steer = ru; a_r = -ru;
+        a_e = -clampd(u(FB_U_ELEVATOR_OFFSET) + u(FB_U_ELEVATOR), -1.0, 1.0);
+        a_a = clampd(u(FB_U_AILERON_OFFSET) + u(FB_U_AILERON), -1.0, 1.0);
+        a_f = u(FB_U_FLAPS); br_l = u(FB_U_BRAKE_LEFT); br_r = u(FB_U_BRAKE_RIGHT);
+        throttle = u(FB_U_THROTTLE);
+    } else {
+        double pos[7];
+#pragma unroll
+        for (int i = 0; i < 7; i++) {
+            double lo = (i == 0 || i >= 4) ? 0.0 : -1.0;
+            double xp = x[L::ACT + i];
+            double cmd = u(FB_U_ACT_THROTTLE + i);   // stored saturated (Ranged)
+            pos[i] = clampd(xp, lo, 1.0);
+            xd[L::ACT + i] = (1.0 / 0.05) * (cmd - xp);
+            if (WY) { yf->act_pos[i] = pos[i]; yf->act_cmd[i] = cmd; }
+        }
+        throttle = pos[0]; a_a = pos[1]; a_e = -pos[2]; a_r = -pos[3]; steer = pos[3]; a_f = pos[4]; br_l = pos[5]; br_r = pos[6];
+    }
+
+    d3 F = mk3(0, 0, 0), tau = mk3(0, 0, 0);
+    // ------------------------------------------------------------------ aerodynamics
+    {
+        constexpr double S = 16.165, b = 10.912, c = 1.494, tau_f = 0.02;
+        constexpr double d2r = FB_PI / 180.0;
+        double alpha_filt = x[L::AERO], beta_filt = x[L::AERO + 1];
+        d3 v = air.v_wb_b;
+        double alpha = 0.0, beta = 0.0, ca = 1.0, sa = 0.0;
+        double vxz2 = fma(v.x, v.x, v.z * v.z);
+        if (air.TAS > 0.1) {   // covers both TAS thresholds (c172.jl:324, atmosphere.jl:337)
+            double vxz = sqrt(vxz2);
+            alpha = atan2(v.z, v.x);
+            beta = atan2(v.y, vxz);
+            if (vxz > 0.0) { ca = v.x / vxz; sa = v.z / vxz; }
+        }
+        out.alpha = alpha;
+        double V = fmax(air.TAS, 1.0);
+        double i2V = 0.5 / V;
+        double afd = (1.0 / tau_f) * (alpha - alpha_filt), bfd = (1.0 / tau_f) * (beta - beta_filt);
+        xd[L::AERO] = afd; xd[L::AERO + 1] = bfd;
+        double p_nd = k.w_wb_b.x * b * i2V, q_nd = k.w_wb_b.y * c * i2V, r_nd = k.w_wb_b.z * b * i2V;
+        double adot_nd = clampd(afd * c * i2V, -0.04, 0.04);
+        double de = fma((23 + 28) * d2r * 0.5, a_e + 1.0, -28 * d2r);
+        double da = fma(40 * d2r * 0.5, a_a + 1.0, -20 * d2r);
+        double dr = fma(32 * d2r * 0.5, a_r + 1.0, -16 * d2r);
+        double df = 30 * d2r * a_f;
+        double dh_nd = (k.h_o - u(FB_U_TRN_ELEVATION)) * (1.0 / b);
+        double a_c = clampd(alpha, -0.1, 0.36), b_c = clampd(beta, -0.2, 0.2);
+        // flap axis (knots 0,10,20,30 deg) shared by five tables
+        int jf; double wf;
+        { double dfc = clampd(df, tb[TB_DF_X], tb[TB_DF_X + 3]); locate(tb + TB_DF_X, 4, dfc, jf, wf); }
+        double wf2 = clampd(df * (1.0 / (30 * d2r)), 0.0, 1.0);   // 2-knot flap axis (0, 30 deg)
+        int ig; double wg;
+        { double g = clampd(dh_nd, 0.0, 1.1); locate(tb + TB_GE_X, 13, g, ig, wg); }
+        double CD_ge = lerp(tb[TB_CD_GE + ig], tb[TB_CD_GE + ig + 1], wg);
+        double CL_ge = lerp(tb[TB_CL_GE + ig], tb[TB_CL_GE + ig + 1], wg);
+        double CD_df = lerp(tb[TB_CD_DF + jf], tb[TB_CD_DF + jf + 1], wf);
+        double CL_df = lerp(tb[TB_CL_DF + jf], tb[TB_CL_DF + jf + 1], wf);
+        double Cm_df = lerp(tb[TB_CM_DF + jf], tb[TB_CM_DF + jf + 1], wf);
+        int ia; double wa;
+        { double ac = clampd(a_c, tb[TB_CD_A_X], tb[TB_CD_A_X + 25]); locate(tb + TB_CD_A_X, 26, ac, ia, wa); }
+        const double* cd = tb + TB_CD_A_DF + ia * 4 + jf;
+        double CD_a_df = lerp(lerp(cd[0], cd[1], wf), lerp(cd[4], cd[5], wf), wa);
+        int il; double wl;
+        { double ac = clampd(a_c, tb[TB_CL_A_X], tb[TB_CL_A_X + 16]); locate(tb + TB_CL_A_X, 17, ac, il, wl); }
+        double CL_a = lerp(tb[TB_CL_A + il * 2 + stall], tb[TB_CL_A + il * 2 + 2 + stall], wl);
+        double CD_de = 0.06 * fabs(clampd(de, -1.0, 1.0));       // knots (-1,0,1) -> (0.06,0,0.06)
+        double CD_b = 0.17 * fabs(b_c);
+        // 2x2 tables over alpha in (0, 0.094) and flap (0, 30 deg)
+        double wa2 = clampd(a_c * (1.0 / 0.094), 0.0, 1.0);
+        auto t22 = [&](int o) { return lerp(lerp(tb[o], tb[o + 1], wf2), lerp(tb[o + 2], tb[o + 3], wf2), wa2); };
+        double CY_p = t22(TB_CY_P), CY_r = t22(TB_CY_R), Cl_r = t22(TB_CL_R);
+        // C_Y.beta_dflap: beta knots (-0.349, 0, 0.349); beta is clamped to +-0.2 so only the inner cells are used
+        double CY_b_df;
+        {
+            double bb = b_c * (1.0 / 0.3490);
+            int ib = (bb >= 0.0) ? 1 : 0;
+            double wb = bb + (double)(1 - ib);
+            const double* t = tb + TB_CY_B_DF + ib * 2;
+            CY_b_df = lerp(lerp(t[0], t[1], wf2), lerp(t[2], t[3], wf2), wb);
+        }
+        double C_D = 0.027 + CD_ge * (CD_a_df + CD_df) + CD_de + CD_b;
+        double C_Y = 0.1870 * dr + 0.0 * da + CY_b_df + CY_p * p_nd + CY_r * r_nd;
+        double C_L = CL_ge * (CL_a + CL_df) + 0.43 * de + 3.9 * q_nd + 1.7 * adot_nd;
+        double C_l = 0.229 * da + 0.0147 * dr + -0.09226 * b_c + -0.4840 * p_nd + Cl_r * r_nd;
+        double C_m = 0.1 + -1.1220 * de + Cm_df + -1.8 * a_c + -12.4 * q_nd + -7.27 * adot_nd;
+        double C_n = -0.0430 * dr + -0.0053 * da + 0.05874 * b_c + -0.0278 * p_nd + -0.0937 * r_nd;
+        double qS = air.q * S;
+        // stability -> body axes: Ry(-alpha) applied to (-C_D, C_Y, -C_L)
+        double fx = -C_D, fz = -C_L;
+        F = mk3(qS * (ca * fx - sa * fz), qS * C_Y, qS * (sa * fx + ca * fz));
+        tau = mk3(qS * C_l * b, qS * C_m * c, qS * C_n * b);
+        if (WY) { yf->alpha = alpha; yf->beta = beta; yf->alpha_filt = alpha_filt; yf->beta_filt = beta_filt; yf->C_L = C_L; yf->C_D = C_D; }
+    }
+
+    // ------------------------------------------------------------------ landing gear
+    {
+        double elev = u(FB_U_TRN_ELEVATION);
+        if (k.h_o - elev > 4.0) {
+            // every strut attachment is < 2.4 m from Ob: no wheel can reach the terrain; regulators just leak
+#pragma unroll
+            for (int i = 0; i < 6; i++) xd[L::LDG + i] = -0.2 * x[L::LDG + i];
+            if (WY) { for (int i = 0; i < 3; i++) { yf->xi[i] = 0.0; yf->F_dmp[i] = 0.0; } }
+        } else {
+            int surface = (int)u(FB_U_TRN_SURFACE);
+            bool eng = u(FB_U_STEERING_ENGAGED) != 0.0;
+            ldg_unit(k, geoid, elev, surface, mk3(-0.381, -1.092, 1.902), 39404, 9340, 9340, false, false, 0.0, br_l,
+                     x[L::LDG], x[L::LDG + 1], xd[L::LDG], xd[L::LDG + 1], F, tau, 0, out, WY ? &yf->xi[0] : nullptr, WY ? &yf->F_dmp[0] : nullptr);
+            ldg_unit(k, geoid, elev, surface, mk3(-0.381, 1.092, 1.902), 39404, 9340, 9340, false, false, 0.0, br_r,
+                     x[L::LDG + 2], x[L::LDG + 3], xd[L::LDG + 2], xd[L::LDG + 3], F, tau, 1, out, WY ? &yf->xi[1] : nullptr, WY ? &yf->F_dmp[1] : nullptr);
+            ldg_unit(k, geoid, elev, surface, mk3(1.27, 0.0, 1.9), 26269, 3503, 3503, true, eng, steer, 0.0,
+                     x[L::LDG + 4], x[L::LDG + 5], xd[L::LDG + 4], xd[L::LDG + 5], F, tau, 2, out, WY ? &yf->xi[2] : nullptr, WY ? &yf->F_dmp[2] : nullptr);
+        }
+    }
+
+    // ------------------------------------------------------------------ power plant
+    d3 h_rot;
+    double mdot;
+    {
+        constexpr double d = 2.0, J_xx = 0.3, J_eng = 0.05;
+        constexpr double w_rated = 2700 * FB_PI / 30, w_idle = 600 * FB_PI / 30, P_rated = 735.49875 * 200, tau_start = 40;
+        double w = x[L::ENG];
+        const d3 r_bp = mk3(2.055, 0.0, 0.833);
+        d3 v = air.v_wb_b + cross(k.w_eb_b, r_bp);
+        double v_J = sqrt(dot(v, v));
+        double aw = fabs(w);
+        double J = 2 * FB_PI * v_J / (fmax(aw, 1.0) * d);
+        double Mt = aw * (d / 2) / air.a;
+        int ij, im; double wj, wm;
+        locate_uniform(0.0, 1.5 / 20, 21, J, ij, wj);
+        locate_uniform(0.0, 1.5 / 20, 21, Mt, im, wm);
+        const double* p00 = tb + TB_PROP + (ij * 21 + im) * 6;
+        const double* p10 = p00 + 21 * 6;
+        double cf[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) cf[c] = lerp(lerp(p00[c], p00[6 + c], wm), lerp(p10[c], p10[6 + c], wm), wj);
+        double al_p = 0.0, be_p = 0.0;
+        if (v_J >= 0.1) { double vxz = sqrt(fma(v.x, v.x, v.z * v.z)); al_p = atan2(v.z, v.x); be_p = atan2(v.y, vxz); }
+        double f = w * (1.0 / (2 * FB_PI)), f2 = f * f;
+        constexpr double d4 = d * d * d * d, d5 = d4 * d;
+        double kF = air.rho * f2 * d4, kM = air.rho * f2 * d5;
+        d3 Fp = mk3(kF * cf[0], kF * cf[2] * be_p, kF * cf[2] * al_p);
+        d3 Mp = mk3(kM * cf[1], kM * cf[3] * be_p, kM * cf[3] * al_p);
+        F = F + Fp;
+        tau = tau + Mp + cross(r_bp, Fp);
+        h_rot = mk3(J_xx * w, 0.0, 0.0);
+        double tau_load = Mp.x;
+        // engine
+        double xd_frc, xd_idle;
+        double o_frc = pi_lane(-w, x[L::ENG + 2], 5.0, 200.0, 0.0, -1.0, 1.0, xd_frc);
+        double o_idle = pi_lane(1.0 - w / w_idle, x[L::ENG + 1], 4.0, 2.0, 0.0, -0.5, 0.5, xd_idle);
+        xd[L::ENG + 1] = xd_idle; xd[L::ENG + 2] = xd_frc;
+        double tau_shaft;
+        mdot = 0.0;
+        double MAP_y = air.p, P_y = 0.0;
+        if (eng_state == FB_ENG_OFF) {
+            tau_shaft = o_frc * (0.01 * P_rated / w_rated);
+        } else if (eng_state == FB_ENG_STARTING) {
+            tau_shaft = tau_start;
+            P_y = tau_shaft * w;
+            if (WY) {   // MAP = mu * p_std needs mu also in this state (piston.jl:378-384)
+                constexpr double kT = 6.5e-3 * isa::R / isa::g_std;
+                double tr = exp(kT * air.lnp);
+                double delta = (air.p * (1.0 / isa::p_std)) * rsqrt(tr);
+                double mri = 0.5 + o_idle;
+                MAP_y = interp_2x9_line(tb + TB_MU_WOT, 0.667, 1.0, 0.441, 1.0, w * (1.0 / w_rated), delta) * fma(throttle, 1.0 - mri, mri) * isa::p_std;
+            }
+        } else {
+            double n = w * (1.0 / w_rated);
+            // T_ISA(p)/T_std = (p/p_std)^(-beta R / g), delta = (p/p_std) (T_ISA/T_std)^-0.5 (piston.jl:38-39)
+            constexpr double kT = 6.5e-3 * isa::R / isa::g_std;
+            double tr = exp(kT * air.lnp);                 // T_ISA(p) / T_std
+            double delta = (air.p * (1.0 / isa::p_std)) * rsqrt(tr);
+            double mu_ratio_idle = 0.5 + o_idle;
+            double mu_wot = interp_2x9_line(tb + TB_MU_WOT, 0.667, 1.0, 0.441, 1.0, n, delta);
+            double mu = mu_wot * fma(throttle, 1.0 - mu_ratio_idle, mu_ratio_idle);
+            double sq_rr = sqrt(air.rho * (1.0 / isa::rho_std));   // 1/k_f
+            double mixture = u(FB_U_MIXTURE);
+            double mixture_pos = (u(FB_U_MIXTURE_AUTO) == 0.0) ? 0.5 * (mixture + 1.0)
+                                                               : fma(mixture, 0.0950 - 0.0625, 0.0625) * sq_rr * (1.0 / 0.0950);
+            double far = (0.0950 * mixture_pos) / sq_rr;
+            double d_wot = interp_2x9_line(tb + TB_D_WOT, 0.667, 1.0, 0.401, 0.936, n, mu);
+            // pi_std(n, mu): gridded 13 x 3, Flat
+            double pi_std, pi_wot;
+            {
+                double nc = clampd(n, tb[TB_N_STD], tb[TB_N_STD + 12]);
+                int i; double wn; locate(tb + TB_N_STD, 13, nc, i, wn);
+                double mc = clampd(mu, 0.0, 1.0);
+                int j = (mc >= 0.568) ? 1 : 0;
+                double wmu = (j == 0) ? mc * (1.0 / 0.568) : (mc - 0.568) * (1.0 / (1.0 - 0.568));
+                const double* t = tb + TB_PI_STD + i * 3 + j;
+                pi_std = lerp(lerp(t[0], t[1], wmu), lerp(t[3], t[4], wmu), wn);
+            }
+            {   // pi_wot(n, d_wot): gridded 5 x 3 (delta knots 0, 0.441, 1), Flat in n and below, Line above in delta
+                double nc = clampd(n, tb[TB_N_WOT], tb[TB_N_WOT + 4]);
+                int i; double wn; locate(tb + TB_N_WOT, 5, nc, i, wn);
+                double dc = clampd(d_wot, 0.0, 1.0);
+                int j = (dc >= 0.441) ? 1 : 0;
+                double wd = (j == 0) ? dc * (1.0 / 0.441) : (dc - 0.441) * (1.0 / (1.0 - 0.441));
+                const double* t = tb + TB_PI_WOT + i * 3 + j;
+                pi_wot = lerp(lerp(t[0], t[1], wd), lerp(t[3], t[4], wd), wn);
+                if (d_wot > 1.0) {
+                    double g = lerp(t[1] - t[0], t[4] - t[3], wn) * (1.0 / (1.0 - 0.441));
+                    pi_wot = fma(d_wot - 1.0, g, pi_wot);
+                }
+            }
+            double pi_ISA = (fabs(d_wot - 1.0) < 5e-3) ? pi_std : fma((pi_wot - pi_std) / (d_wot - 1.0), delta - 1.0, pi_std);
+            pi_ISA = fmax(pi_ISA, 0.0);
+            double pi_pow = pi_ISA * sqrt(tr * isa::T_std / air.T);
+            int jf; double wff;
+            { double fc = clampd(far, tb[TB_F_X], tb[TB_F_X + 10]); locate(tb + TB_F_X, 11, fc, jf, wff); }
+            double pi_actual = pi_pow * lerp(tb[TB_PI_RATIO + jf], tb[TB_PI_RATIO + jf + 1], wff);
+            double P_shaft = P_rated * pi_actual;
+            tau_shaft = (w > 0.0) ? P_shaft / w : 0.0;
+            MAP_y = mu * isa::p_std; P_y = P_shaft;
+            // sfc_pow(n, pi_actual): gridded 5 x 8, Line
+            double sfc;
+            {
+                double nc = clampd(n, tb[TB_N_SFC], tb[TB_N_SFC + 4]);
+                double pc = clampd(pi_actual, tb[TB_PI_SFC], tb[TB_PI_SFC + 7]);
+                int i, j; double wn, wp;
+                locate(tb + TB_N_SFC, 5, nc, i, wn);
+                locate(tb + TB_PI_SFC, 8, pc, j, wp);
+                const double* t = tb + TB_SFC_POW + i * 8 + j;
+                double f00 = t[0], f01 = t[1], f10 = t[8], f11 = t[9];
+                sfc = lerp(lerp(f00, f01, wp), lerp(f10, f11, wp), wn);
+                double g0 = lerp(f10 - f00, f11 - f01, wp) / (tb[TB_N_SFC + i + 1] - tb[TB_N_SFC + i]);
+                double g1 = lerp(f01 - f00, f11 - f10, wn) / (tb[TB_PI_SFC + j + 1] - tb[TB_PI_SFC + j]);
+                sfc = fma(n - nc, g0, fma(pi_actual - pc, g1, sfc));
+            }
+            double SFC = sfc * lerp(tb[TB_SFC_RATIO + jf], tb[TB_SFC_RATIO + jf + 1], wff);
+            mdot = SFC * P_shaft;
+        }
+        xd[L::ENG] = (tau_shaft + tau_load) * (1.0 / (J_eng + J_xx));
+        if (WY) {
+            yf->eng_omega = w; yf->eng_n = w * (1.0 / w_rated); yf->eng_MAP = MAP_y; yf->eng_P_shaft = P_y; yf->eng_tau_shaft = tau_shaft;
+            yf->eng_mdot = mdot; yf->prop_thrust = Fp.x; yf->prop_J = J;
+        }
+    }
+    // ------------------------------------------------------------------ fuel
+    constexpr double m_full = 114.4, m_res = 1.0;
+    xd[L::FUEL] = -mdot * (1.0 / (m_full - m_res));
+    double m_fuel = fmax(0.0, fma(x[L::FUEL], m_full - m_res, m_res));
+
+    // ------------------------------------------------------------------ mass properties (affine in the masses)
+    // airframe at Ob: m 767, J_G diag(820,1164,1702), r (0.056,0,0.582): J_O = J_G + m (|r|^2 I - r r^T)
+    double m, mrx, mry, mrz, Jxx, Jyy, Jzz, Jxy, Jxz, Jyz;
+    {
+        constexpr double ma = 767.0, ax = 0.056, az = 0.582;
+        m = ma; mrx = ma * ax; mry = 0.0; mrz = ma * az;
+        Jxx = 820.0 + ma * (az * az); Jyy = 1164.0 + ma * (ax * ax + az * az); Jzz = 1702.0 + ma * (ax * ax);
+        Jxy = 0.0; Jxz = -ma * ax * az; Jyz = 0.0;
+        auto add_pt = [&](double mp, double rx, double ry, double rz) {
+            m += mp; mrx = fma(mp, rx, mrx); mry = fma(mp, ry, mry); mrz = fma(mp, rz, mrz);
+            Jxx = fma(mp, ry * ry + rz * rz, Jxx); Jyy = fma(mp, rx * rx + rz * rz, Jyy); Jzz = fma(mp, rx * rx + ry * ry, Jzz);
+            Jxy = fma(mp, -rx * ry, Jxy); Jxz = fma(mp, -rx * rz, Jxz); Jyz = fma(mp, -ry * rz, Jyz);
+        };
+        add_pt(0.5 * m_fuel, 0.325, -2.845, 0.0);
+        add_pt(0.5 * m_fuel, 0.325, 2.845, 0.0);
+        add_pt(u(FB_U_M_PILOT), 0.183, -0.356, 0.899);
+        add_pt(u(FB_U_M_COPILOT), 0.183, 0.356, 0.899);
+        add_pt(u(FB_U_M_LPASS), -0.681, -0.356, 0.899);
+        add_pt(u(FB_U_M_RPASS), -0.681, 0.356, 0.899);
+        add_pt(u(FB_U_M_BAGGAGE), -1.316, 0.0, 0.899);
+    }
+    // ------------------------------------------------------------------ rigid-body dynamics (dynamics.jl:443-499)
+    {
+        double im = 1.0 / m;
+        d3 rc = mk3(mrx * im, mry * im, mrz * im);
+        // inertia about the CoM: J_c = J_O - m (|rc|^2 I - rc rc^T)
+        double a11 = Jxx - m * (rc.y * rc.y + rc.z * rc.z), a22 = Jyy - m * (rc.x * rc.x + rc.z * rc.z), a33 = Jzz - m * (rc.x * rc.x + rc.y * rc.y);
+        double a12 = Jxy + m * rc.x * rc.y, a13 = Jxz + m * rc.x * rc.z, a23 = Jyz + m * rc.y * rc.z;
+        d3 w = k.w_eb_b;
+        d3 tau_c = tau - cross(rc, F);
+        d3 v_c = k.v_eb_b + cross(w, rc);
+        d3 w_ie_b = qrot_inv(k.q_eb, mk3(0.0, 0.0, wgs::w_ie));
+        d3 w_ic = w_ie_b + w;
+        d3 r_ec_e = k.r_eb_e + qrot(k.q_eb, rc);
+        d3 n_c; double h_c;
+        geo_from_cartesian(r_ec_e, n_c, h_c);
+        if (h_c < -1000.0) out.err = FB_ST_BOUNDS;
+        double g = gravity(n_c.z, h_c);
+        // Gravity in body axes. The reference rotates (0,0,g) by q_cl = q_eb' o ltf(Oc) (dynamics.jl:481-488); its
+        // quaternion rotation v + 2 q_im x (q_re v + q_im x v) equals v + |q|^2 (R v - v), and the state quaternions
+        // are only renormalised when | |q| - 1 | > 1e-8 (kinematics.jl:114-118), so the norm defect is part of the
+        // reference's arithmetic. The local vertical at the CoM is -n_c, hence R (0,0,g) = R_be (-g n_c); the term
+        // (|q_eb|^2 - 1)(u - v) restores the reference's defect exactly without building ltf(Oc).
+        d3 u_dn = (-g) * n_c;
+        d3 g_c = qrot_inv(k.q_eb, u_dn);
+        {
+            double s1 = fma(k.q_eb.w, k.q_eb.w, fma(k.q_eb.x, k.q_eb.x, fma(k.q_eb.y, k.q_eb.y, k.q_eb.z * k.q_eb.z))) - 1.0;
+            g_c = mk3(fma(s1, u_dn.x, g_c.x), fma(s1, u_dn.y, g_c.y), fma(s1, u_dn.z - g, g_c.z));
+        }
+        auto Jmul = [&](d3 v) { return mk3(a11 * v.x + a12 * v.y + a13 * v.z, a12 * v.x + a22 * v.y + a23 * v.z, a13 * v.x + a23 * v.y + a33 * v.z); };
+        d3 hc = Jmul(w_ic) + h_rot;
+        d3 rhs3 = tau_c - Jmul(cross(w_ie_b, w)) - cross(w_ic, hc);
+        // symmetric 3x3 solve by cofactors
+        double c11 = a22 * a33 - a23 * a23, c12 = a13 * a23 - a12 * a33, c13 = a12 * a23 - a13 * a22;
+        double c22 = a11 * a33 - a13 * a13, c23 = a12 * a13 - a11 * a23, c33 = a11 * a22 - a12 * a12;
+        double idet = 1.0 / (a11 * c11 + a12 * c12 + a13 * c13);
+        d3 wd = mk3((c11 * rhs3.x + c12 * rhs3.y + c13 * rhs3.z) * idet,
+                    (c12 * rhs3.x + c22 * rhs3.y + c23 * rhs3.z) * idet,
+                    (c13 * rhs3.x + c23 * rhs3.y + c33 * rhs3.z) * idet);
+        d3 vd_c = im * F + g_c - cross(w + 2.0 * w_ie_b, v_c);
+        d3 vd_b = vd_c - cross(wd, rc);
+        xd[L::DYN] = wd.x; xd[L::DYN + 1] = wd.y; xd[L::DYN + 2] = wd.z;
+        xd[L::DYN + 3] = vd_b.x; xd[L::DYN + 4] = vd_b.y; xd[L::DYN + 5] = vd_b.z;
+        if (WY) {   // specific force at the CoM, dynamics.jl:503-508: f = a_ic - gamma = vd_c + (w + 2 w_ie) x v_c - g_c
+            yf->f_c_c = vd_c + cross(w + 2.0 * w_ie_b, v_c) - g_c;
+            yf->mass = m; yf->fuel_m_total = fma(x[L::FUEL], m_full - m_res, m_res); yf->wow = out.wow;
+        }
+    }
+}
+
+// f_step!(world) (world.jl:34-39 -> aircraftbase.jl:172-181 -> c172.jl:715-724). `y` is the RhsOut of the
+// evaluation at the post-step state. Returns true when something the RHS reads changed (so that the
+// first-same-as-last derivative must be re-evaluated).
+template <int VAR, int KIN>
+FB_DEV bool f_step(double* x, int& stall, int& eng_state, const MemberIn& u, const RhsOut& y, int& status) {
+    typedef Lay<VAR, KIN> L;
+    bool changed = false;
+    if (KIN == FB_WA) {   // kinematics.jl:114-118,226-229
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            double* q = x + L::KINX + 4 * b;
+            double nn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+            if (fabs(nn - 1.0) > 1e-8) { q[0] /= nn; q[1] /= nn; q[2] /= nn; q[3] /= nn; changed = true; }
+        }
+    }
+    int st0 = stall;
+    if (y.alpha > 0.36) stall = 1; else if (y.alpha < 0.09) stall = 0;   // c172.jl:375-384
+    changed |= (stall != st0);
+#pragma unroll
+    for (int leg = 0; leg < 3; leg++) {
+        int cr = (y.crash >> (2 * leg)) & 3;                             // landinggear.jl:331-347
+        if (cr) { status = (cr == 1) ? FB_ST_CRASH_ANGLE : FB_ST_CRASH_RATE; return changed; }
+        if (!(y.wow & (1 << leg))) {                                     // landinggear.jl:479-483
+            changed |= (x[L::LDG + 2 * leg] != 0.0) | (x[L::LDG + 2 * leg + 1] != 0.0);
+            x[L::LDG + 2 * leg] = 0.0; x[L::LDG + 2 * leg + 1] = 0.0;
+        }
+    }
+    constexpr double w_stall = 300 * FB_PI / 30, w_idle = 600 * FB_PI / 30;
+    int e0 = eng_state;                                                  // piston.jl:428-453
+    double w = x[L::ENG];
+    bool fuel_available = (x[L::FUEL] * (114.4 - 1.0)) > 0.0;
+    bool start = u(FB_U_ENG_START) != 0.0, stop = u(FB_U_ENG_STOP) != 0.0;
+    if (eng_state == FB_ENG_OFF) { if (start) eng_state = FB_ENG_STARTING; }
+    else if (eng_state == FB_ENG_STARTING) {
+        if (!start) eng_state = FB_ENG_OFF;
+        if (w > w_idle && fuel_available) eng_state = FB_ENG_RUNNING;
+    } else {
+        if (stop || w < w_stall || !fuel_available) eng_state = FB_ENG_OFF;
+    }
+    changed |= (eng_state != e0);
+    return changed;
+}

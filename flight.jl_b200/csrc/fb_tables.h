@@ -1,0 +1,55 @@
+// fb_tables.h — layout of the lookup-table pack staged into shared memory by every physics kernel
+// (one bulk async copy per CTA), plus the device-global tables that stay in L2 (geoid, gain schedules).
+// Table semantics: SURVEY.md App. C; data come from the blob written by tools/build_tables.py.
+#pragma once
+#include <stdint.h>
+
+// offsets in doubles inside the shared pack
+enum {
+    // ---- aero (lib/FlightApps/src/c172/c172.jl:51-159), gridded, Flat
+    TB_GE_X = 0,                    // 13
+    TB_CD_GE = TB_GE_X + 13,        // 13
+    TB_CL_GE = TB_CD_GE + 13,       // 13
+    TB_DF_X = TB_CL_GE + 13,        // 4
+    TB_CD_DF = TB_DF_X + 4,         // 4
+    TB_CL_DF = TB_CD_DF + 4,        // 4
+    TB_CM_DF = TB_CL_DF + 4,        // 4
+    TB_CD_A_X = TB_CM_DF + 4,       // 26
+    TB_CD_A_DF = TB_CD_A_X + 26,    // 26*4  [alpha][flap]
+    TB_CL_A_X = TB_CD_A_DF + 104,   // 17
+    TB_CL_A = TB_CL_A_X + 17,       // 17*2  [alpha][stall]
+    TB_CY_B_DF = TB_CL_A + 34,      // 3*2
+    TB_CY_P = TB_CY_B_DF + 6,       // 2*2
+    TB_CY_R = TB_CY_P + 4,          // 2*2
+    TB_CL_R = TB_CY_R + 4,          // 2*2  (C_l.r)
+    // ---- engine (lib/FlightPhysics/src/piston.jl:70-195)
+    TB_D_WOT = TB_CL_R + 4,         // 2*9  scaled, Line
+    TB_MU_WOT = TB_D_WOT + 18,      // 2*9  scaled, Line
+    TB_N_STD = TB_MU_WOT + 18,      // 13
+    TB_PI_STD = TB_N_STD + 13,      // 13*3 gridded, Flat (mu knots 0, 0.568, 1)
+    TB_N_WOT = TB_PI_STD + 39,      // 5
+    TB_PI_WOT = TB_N_WOT + 5,       // 5*3  gridded (delta knots 0, 0.441, 1), Flat / Line above in delta
+    TB_F_X = TB_PI_WOT + 15,        // 11
+    TB_PI_RATIO = TB_F_X + 11,      // 11
+    TB_SFC_RATIO = TB_PI_RATIO + 11,  // 11
+    TB_N_SFC = TB_SFC_RATIO + 11,   // 5
+    TB_PI_SFC = TB_N_SFC + 5,       // 8
+    TB_SFC_POW = TB_PI_SFC + 8,     // 5*8  gridded, Line
+    // ---- propeller (lib/FlightPhysics/src/propellers.jl:235-291): 21x21 over J, Mt in [0,1.5], scaled, Flat;
+    //      interleaved [iJ][iMt][6] = C_Fx, C_Mx, C_Fz_a, C_Mz_a, C_P, eta_p
+    TB_PROP = TB_SFC_POW + 40,
+    TB_COUNT = TB_PROP + 21 * 21 * 6
+};
+#define FB_TB_BYTES ((TB_COUNT * 8 + 15) / 16 * 16)
+
+#define FB_GEOID_NLAT 721
+#define FB_GEOID_NLON 1441
+
+// gain schedules (lib/FlightApps/src/c172/c172x/control/data/*.h5), [7 EAS][4 h][P] row-major, device-global
+enum { GS_TE2TE = 0, GS_TV2TE, GS_VH2TE, GS_AR2AR, GS_PHIBETA2AR, GS_Q2E, GS_C2THETA, GS_V2T, GS_P2PHI, GS_CHI2PHI, GS_COUNT };
+
+struct FbDeviceTables {
+    const double* pack;   // TB_COUNT doubles, 16-byte aligned (global source of the shared pack)
+    const float* geoid;   // [1441 lon][721 lat]
+    const double* gains[GS_COUNT];
+};

@@ -1,0 +1,588 @@
+// flightbatch.cu — C ABI (include/flightbatch.h) and host-side driver of the batched C172 engine.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+// There is no CPU fallback anywhere in this file: without a CUDA device every computing call fails.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <numeric>
+#include "fb_init.cuh"
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(FB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+struct fb_sim {
+    fb_config cfg;
+    int var_t = 0;   // template variant actually instantiated (X2 shares X1's kernels)
+    int nx = 0;
+    long long pitch = 0;
+    EnsembleDev E{};
+    cudaStream_t stream = nullptr;
+    double* d_pack = nullptr; float* d_geoid = nullptr; double* d_gains[GS_COUNT] = {};
+    bool tables_loaded = false, initialised = false;
+    long long n_steps = 0;
+    long long* d_ev_off = nullptr; long long* d_ev_step = nullptr; int* d_ev_field = nullptr; double* d_ev_value = nullptr;
+    long long* d_ev_cursor = nullptr;
+    int* d_log_fields = nullptr;
+    double* d_scratch = nullptr;      // [max(nx, 8)][pitch]
+    double* d_stats = nullptr;        // 5 doubles
+    unsigned long long* d_rhs_count = nullptr;
+    long long launches = 0;
+    int periodic_every = 1;
+    std::vector<double> h_row;
+};
+
+// ------------------------------------------------------------------------------------ kernel dispatch
+template <int VAR, int KIN> struct Ops {
+    static cudaError_t step(fb_sim* s, long long step0, int n) {
+        int grid = (int)((s->E.n + FB_BLOCK - 1) / FB_BLOCK);
+        step_kernel<VAR, KIN><<<grid, FB_BLOCK, FB_TB_BYTES, s->stream>>>(s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count);
+        return cudaGetLastError();
+    }
+    static cudaError_t rhs(fb_sim* s, double* xdot) {
+        int grid = (int)((s->E.n + FB_BLOCK - 1) / FB_BLOCK);
+        rhs_kernel<VAR, KIN><<<grid, FB_BLOCK, FB_TB_BYTES, s->stream>>>(s->E, xdot, nullptr, nullptr, nullptr);
+        return cudaGetLastError();
+    }
+    static cudaError_t output(fb_sim* s, int field, double* out) {
+        int grid = (int)((s->E.n + FB_BLOCK - 1) / FB_BLOCK);
+        output_kernel<VAR, KIN><<<grid, FB_BLOCK, FB_TB_BYTES, s->stream>>>(s->E, field, out);
+        return cudaGetLastError();
+    }
+    static cudaError_t init(fb_sim* s, const InitSoA& I) {
+        int grid = (int)((s->E.n + FB_BLOCK - 1) / FB_BLOCK);
+        init_kernel<VAR, KIN><<<grid, FB_BLOCK, 0, s->stream>>>(s->E, I);
+        return cudaGetLastError();
+    }
+    static cudaError_t trim(fb_sim* s, const TrimSoA& P, double* ts, double* cost) {
+        int grid = (int)((s->E.n + FB_BLOCK - 1) / FB_BLOCK);
+        trim_kernel<VAR, KIN><<<grid, FB_BLOCK, FB_TB_BYTES, s->stream>>>(s->E, P, ts, cost);
+        return cudaGetLastError();
+    }
+};
+#define FB_DISPATCH(s, CALL)                                                            \
+    ((s)->var_t == FB_C172S ? ((s)->cfg.kinematics == FB_WA ? Ops<FB_C172S, FB_WA>::CALL : Ops<FB_C172S, FB_NED>::CALL) \
+     : (s)->var_t == FB_C172X0 ? ((s)->cfg.kinematics == FB_WA ? Ops<FB_C172X0, FB_WA>::CALL : Ops<FB_C172X0, FB_NED>::CALL) \
+                               : ((s)->cfg.kinematics == FB_WA ? Ops<FB_C172X1, FB_WA>::CALL : Ops<FB_C172X1, FB_NED>::CALL))
+
+static int layout_nx(int variant, int kin) {
+    int nact = (variant == FB_C172S) ? 0 : 7;
+    int nkin = (kin == FB_WA) ? 9 : (kin == FB_ECEF ? 8 : 6);
+    return 12 + nact + nkin + 6;
+}
+
+// ------------------------------------------------------------------------------------ statistics kernel
+__global__ void stats_kernel(const double* v, const int* status, long long n, double* out /*count,sum,sumsq,min,max*/) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double c = 0.0, s = 0.0, s2 = 0.0, mn = INFINITY, mx = -INFINITY;
+    if (i < n && (status[i] == FB_ST_RUNNING || status[i] == FB_ST_DONE)) { double x = v[i]; c = 1.0; s = x; s2 = x * x; mn = x; mx = x; }
+    for (int o = 16; o > 0; o >>= 1) {   // warp-level shuffle reduction
+        c += __shfl_down_sync(0xffffffffu, c, o); s += __shfl_down_sync(0xffffffffu, s, o); s2 += __shfl_down_sync(0xffffffffu, s2, o);
+        mn = fmin(mn, __shfl_down_sync(0xffffffffu, mn, o)); mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0 && c > 0.0) {
+        atomicAdd(out, c); atomicAdd(out + 1, s); atomicAdd(out + 2, s2);
+        unsigned long long* pmn = (unsigned long long*)(out + 3); unsigned long long* pmx = (unsigned long long*)(out + 4);
+        unsigned long long old = *pmn, assumed;
+        do { assumed = old; if (__longlong_as_double(assumed) <= mn) break; old = atomicCAS(pmn, assumed, (unsigned long long)__double_as_longlong(mn)); } while (assumed != old);
+        old = *pmx;
+        do { assumed = old; if (__longlong_as_double(assumed) >= mx) break; old = atomicCAS(pmx, assumed, (unsigned long long)__double_as_longlong(mx)); } while (assumed != old);
+    }
+}
+__global__ void fill_kernel(double* p, long long n, double v) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------ table blob
+struct BlobSec { std::string name; uint32_t dtype, ndim, dims[4]; uint64_t off, nbytes; };
+static bool parse_blob(const uint8_t* b, size_t n, std::vector<BlobSec>& out) {
+    if (n < 16 || memcmp(b, "FBTABLE1", 8) != 0) return false;
+    uint32_t ns; memcpy(&ns, b + 8, 4);
+    if (16 + 64ull * ns > n) return false;
+    for (uint32_t i = 0; i < ns; i++) {
+        const uint8_t* r = b + 16 + 64ull * i;
+        BlobSec s; char nm[25]; memcpy(nm, r, 24); nm[24] = 0; s.name = nm;
+        memcpy(&s.dtype, r + 24, 4); memcpy(&s.ndim, r + 28, 4); memcpy(s.dims, r + 32, 16);
+        memcpy(&s.off, r + 48, 8); memcpy(&s.nbytes, r + 56, 8);
+        if (s.off + s.nbytes > n) return false;
+        out.push_back(s);
+    }
+    return true;
+}
+
+static double default_input(int f) {
+    switch (f) {
+        case FB_U_MIXTURE: return 0.5; case FB_U_MIXTURE_AUTO: return 1.0; case FB_U_STEERING_ENGAGED: return 1.0;
+        case FB_U_M_PILOT: case FB_U_M_COPILOT: return 75.0; case FB_U_M_BAGGAGE: return 50.0;
+        case FB_U_T_SL: return 288.15; case FB_U_P_SL: return 101325.0;
+        case FB_U_LON_EAS_REF: return 50.0;
+        default: return 0.0;
+    }
+}
+
+extern "C" {
+
+int32_t fb_api_version(void) { return FB_API_VERSION; }
+const char* fb_last_error(void) { return g_err.c_str(); }
+
+int32_t fb_create(const fb_config* cfg, fb_handle* out) {
+    if (!cfg || !out) return fail(FB_ERR_ARG, "fb_create: null argument");
+    if (cfg->variant < FB_C172S || cfg->variant > FB_C172X2) return fail(FB_ERR_ARG, "fb_create: unknown variant");
+    if (cfg->kinematics != FB_WA && cfg->kinematics != FB_NED) return fail(FB_ERR_ARG, "fb_create: kinematics must be FB_WA or FB_NED (ECEF not built yet)");
+    if (cfg->n_members <= 0) return fail(FB_ERR_ARG, "fb_create: n_members must be positive");
+    if (!(cfg->dt > 0.0)) return fail(FB_ERR_ARG, "fb_create: dt must be positive");
+    double Dt = cfg->Dt > 0.0 ? cfg->Dt : cfg->dt;
+    long long pe = llround(Dt / cfg->dt);
+    if (pe < 1 || fabs(pe * cfg->dt - Dt) > 1e-9 * Dt) return fail(FB_ERR_ARG, "fb_create: Dt must be a positive integer multiple of dt");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(FB_ERR_CUDA, "fb_create: no CUDA device available (this engine has no CPU path)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(FB_ERR_ARG, "fb_create: bad device ordinal");
+    CK(cudaSetDevice(cfg->device));
+    fb_sim* s = new fb_sim();
+    s->cfg = *cfg; s->cfg.Dt = Dt;
+    s->periodic_every = (int)pe;
+    s->var_t = cfg->variant >= FB_C172X1 ? FB_C172X1 : cfg->variant;
+    s->nx = layout_nx(cfg->variant, cfg->kinematics);
+    long long N = cfg->n_members;
+    s->pitch = (N + 31) / 32 * 32;
+    if (s->cfg.steps_per_launch <= 0) s->cfg.steps_per_launch = 250;
+    CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    EnsembleDev& E = s->E;
+    E.pitch = s->pitch; E.n = N;
+    CK(cudaMalloc(&E.x, sizeof(double) * s->nx * s->pitch));
+    CK(cudaMalloc(&E.u, sizeof(double) * FB_U__COUNT * s->pitch));
+    CK(cudaMalloc(&E.stall, s->pitch)); CK(cudaMalloc(&E.eng, s->pitch));
+    CK(cudaMalloc(&E.status, sizeof(int) * s->pitch));
+    CK(cudaMalloc(&E.ctl, sizeof(double) * FB_CTL_STATE_COUNT * s->pitch));
+    CK(cudaMalloc(&s->d_ev_cursor, sizeof(long long) * s->pitch));
+    CK(cudaMalloc(&s->d_scratch, sizeof(double) * std::max(s->nx, 8) * s->pitch));
+    CK(cudaMalloc(&s->d_stats, sizeof(double) * 8));
+    CK(cudaMalloc(&s->d_rhs_count, sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(s->d_rhs_count, 0, sizeof(unsigned long long), s->stream));
+    CK(cudaMemsetAsync(E.x, 0, sizeof(double) * s->nx * s->pitch, s->stream));
+    CK(cudaMemsetAsync(E.ctl, 0, sizeof(double) * FB_CTL_STATE_COUNT * s->pitch, s->stream));
+    CK(cudaMemsetAsync(E.stall, 0, s->pitch, s->stream)); CK(cudaMemsetAsync(E.eng, 0, s->pitch, s->stream));
+    CK(cudaMemsetAsync(E.status, 0, sizeof(int) * s->pitch, s->stream));
+    CK(cudaMemsetAsync(s->d_ev_cursor, 0, sizeof(long long) * s->pitch, s->stream));
+    for (int f = 0; f < FB_U__COUNT; f++) {
+        int grid = (int)((s->pitch + 255) / 256);
+        fill_kernel<<<grid, 256, 0, s->stream>>>(E.u + (long long)f * s->pitch, s->pitch, default_input(f));
+    }
+    E.ev_cursor = s->d_ev_cursor;
+    // decimated log
+    E.log_every = cfg->log_every > 0 ? cfg->log_every : 0;
+    E.log_n_fields = 0; E.log_capacity = 0;
+    if (E.log_every > 0 && cfg->log_n_fields > 0) {
+        if (cfg->log_n_fields > 32) return fail(FB_ERR_ARG, "fb_create: at most 32 log fields");
+        long long total = llround((cfg->t_end - cfg->t_start) / cfg->dt);
+        if (total < 0) return fail(FB_ERR_ARG, "fb_create: t_end < t_start");
+        E.log_n_fields = cfg->log_n_fields;
+        E.log_capacity = total / E.log_every + 1;
+        double bytes = (double)E.log_capacity * E.log_n_fields * s->pitch * 8.0;
+        if (bytes > 64e9) return fail(FB_ERR_ALLOC, "fb_create: log would exceed 64 GB; raise log_every or log fewer fields");
+        CK(cudaMalloc(&E.log, (size_t)bytes));
+        CK(cudaMalloc(&s->d_log_fields, sizeof(int) * 32));
+        CK(cudaMemcpyAsync(s->d_log_fields, cfg->log_fields, sizeof(int) * cfg->log_n_fields, cudaMemcpyHostToDevice, s->stream));
+        E.log_fields = s->d_log_fields;
+    }
+    // opt in to the shared-memory size of the table pack
+    CK(cudaFuncSetAttribute(step_kernel<FB_C172S, FB_WA>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES));
+    CK(cudaFuncSetAttribute(step_kernel<FB_C172S, FB_NED>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES));
+    CK(cudaFuncSetAttribute(step_kernel<FB_C172X0, FB_WA>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES));
+    CK(cudaFuncSetAttribute(step_kernel<FB_C172X0, FB_NED>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES));
+    CK(cudaFuncSetAttribute(step_kernel<FB_C172X1, FB_WA>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES));
+    CK(cudaFuncSetAttribute(step_kernel<FB_C172X1, FB_NED>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES));
+    CK(cudaStreamSynchronize(s->stream));
+    *out = s;
+    return FB_OK;
+}
+
+int32_t fb_destroy(fb_handle s) {
+    if (!s) return FB_OK;
+    cudaSetDevice(s->cfg.device);
+    cudaStreamSynchronize(s->stream);
+    EnsembleDev& E = s->E;
+    cudaFree(E.x); cudaFree(E.u); cudaFree(E.stall); cudaFree(E.eng); cudaFree(E.status); cudaFree(E.ctl); cudaFree(E.log);
+    cudaFree(s->d_pack); cudaFree(s->d_geoid);
+    for (int i = 0; i < GS_COUNT; i++) cudaFree(s->d_gains[i]);
+    cudaFree(s->d_ev_off); cudaFree(s->d_ev_step); cudaFree(s->d_ev_field); cudaFree(s->d_ev_value); cudaFree(s->d_ev_cursor);
+    cudaFree(s->d_log_fields); cudaFree(s->d_scratch); cudaFree(s->d_stats); cudaFree(s->d_rhs_count);
+    cudaStreamDestroy(s->stream);
+    delete s;
+    return FB_OK;
+}
+
+int32_t fb_sync(fb_handle s) {
+    if (!s) return fail(FB_ERR_ARG, "null handle");
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaStreamSynchronize(s->stream));
+    return FB_OK;
+}
+
+int32_t fb_load_tables(fb_handle s, const void* blob, size_t nbytes) {
+    if (!s || !blob) return fail(FB_ERR_ARG, "fb_load_tables: null argument");
+    CK(cudaSetDevice(s->cfg.device));
+    std::vector<BlobSec> secs;
+    const uint8_t* b = (const uint8_t*)blob;
+    if (!parse_blob(b, nbytes, secs)) return fail(FB_ERR_ARG, "fb_load_tables: not a table blob");
+    auto find = [&](const char* name) -> const BlobSec* { for (auto& x : secs) if (x.name == name) return &x; return nullptr; };
+    std::vector<double> pack(FB_TB_BYTES / 8, 0.0);
+    struct Map { const char* name; int off; int count; };
+    const Map maps[] = {
+        {"aero.ge_x", TB_GE_X, 13}, {"aero.CD_ge", TB_CD_GE, 13}, {"aero.CL_ge", TB_CL_GE, 13}, {"aero.df_x", TB_DF_X, 4},
+        {"aero.CD_df", TB_CD_DF, 4}, {"aero.CL_df", TB_CL_DF, 4}, {"aero.Cm_df", TB_CM_DF, 4}, {"aero.CD_a_x", TB_CD_A_X, 26},
+        {"aero.CD_a_df", TB_CD_A_DF, 104}, {"aero.CL_a_x", TB_CL_A_X, 17}, {"aero.CL_a", TB_CL_A, 34}, {"aero.CY_b_df", TB_CY_B_DF, 6},
+        {"aero.CY_p", TB_CY_P, 4}, {"aero.CY_r", TB_CY_R, 4}, {"aero.Cl_r", TB_CL_R, 4},
+        {"eng.d_wot", TB_D_WOT, 18}, {"eng.mu_wot", TB_MU_WOT, 18}, {"eng.n_std", TB_N_STD, 13}, {"eng.pi_std", TB_PI_STD, 39},
+        {"eng.n_wot", TB_N_WOT, 5}, {"eng.pi_wot", TB_PI_WOT, 15}, {"eng.f_x", TB_F_X, 11}, {"eng.pi_ratio", TB_PI_RATIO, 11},
+        {"eng.sfc_ratio", TB_SFC_RATIO, 11}, {"eng.n_sfc", TB_N_SFC, 5}, {"eng.pi_sfc", TB_PI_SFC, 8}, {"eng.sfc_pow", TB_SFC_POW, 40}};
+    for (const Map& m : maps) {
+        const BlobSec* sec = find(m.name);
+        if (!sec || sec->dtype != 0 || sec->nbytes != (uint64_t)m.count * 8) return fail(FB_ERR_ARG, std::string("fb_load_tables: bad or missing section ") + m.name);
+        memcpy(pack.data() + m.off, b + sec->off, sec->nbytes);
+    }
+    {
+        const BlobSec* sec = find("prop.tables");
+        if (!sec || sec->nbytes != 6ull * 441 * 8) return fail(FB_ERR_ARG, "fb_load_tables: bad or missing section prop.tables");
+        const double* p = (const double*)(b + sec->off);
+        for (int c = 0; c < 6; c++) for (int ij = 0; ij < 441; ij++) pack[TB_PROP + ij * 6 + c] = p[c * 441 + ij];
+    }
+    const BlobSec* g = find("geoid");
+    if (!g || g->dtype != 1 || g->nbytes != (uint64_t)FB_GEOID_NLAT * FB_GEOID_NLON * 4) return fail(FB_ERR_ARG, "fb_load_tables: bad or missing geoid section");
+    if (!s->d_pack) CK(cudaMalloc(&s->d_pack, FB_TB_BYTES));
+    if (!s->d_geoid) CK(cudaMalloc(&s->d_geoid, g->nbytes));
+    CK(cudaMemcpyAsync(s->d_pack, pack.data(), FB_TB_BYTES, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemcpyAsync(s->d_geoid, b + g->off, g->nbytes, cudaMemcpyHostToDevice, s->stream));
+    static const char* gnames[GS_COUNT] = {"gain.te2te", "gain.tv2te", "gain.vh2te", "gain.ar2ar", "gain.phibeta2ar",
+                                           "gain.q2e", "gain.c2theta", "gain.v2t", "gain.p2phi", "gain.chi2phi"};
+    for (int i = 0; i < GS_COUNT; i++) {
+        const BlobSec* sec = find(gnames[i]);
+        if (!sec) return fail(FB_ERR_ARG, std::string("fb_load_tables: missing section ") + gnames[i]);
+        if (!s->d_gains[i]) CK(cudaMalloc(&s->d_gains[i], sec->nbytes));
+        CK(cudaMemcpyAsync(s->d_gains[i], b + sec->off, sec->nbytes, cudaMemcpyHostToDevice, s->stream));
+        s->E.tables.gains[i] = s->d_gains[i];
+    }
+    CK(cudaStreamSynchronize(s->stream));
+    s->E.tables.pack = s->d_pack; s->E.tables.geoid = s->d_geoid;
+    s->tables_loaded = true;
+    return FB_OK;
+}
+
+// upload an optional host column [N] into a device row of the scratch arena; returns device pointer or nullptr
+struct Uploader {
+    fb_sim* s; std::vector<double*> bufs; cudaError_t err = cudaSuccess;
+    const double* up(const double* h) {
+        if (!h) return nullptr;
+        double* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, sizeof(double) * s->pitch);
+        if (e != cudaSuccess) { err = e; return nullptr; }
+        bufs.push_back(d);
+        e = cudaMemcpyAsync(d, h, sizeof(double) * s->E.n, cudaMemcpyHostToDevice, s->stream);
+        if (e != cudaSuccess) err = e;
+        return d;
+    }
+    ~Uploader() { cudaStreamSynchronize(s->stream); for (double* d : bufs) cudaFree(d); }
+};
+
+static int32_t after_init(fb_sim* s) {
+    s->n_steps = 0; s->initialised = true;
+    CK(cudaMemsetAsync(s->d_ev_cursor, 0, sizeof(long long) * s->pitch, s->stream));
+    // log sample 0 = y left by f_init! (sim.jl:405-408)
+    for (int f = 0; f < s->E.log_n_fields; f++) {
+        CK(FB_DISPATCH(s, output)(s, s->cfg.log_fields[f], s->E.log + (long long)f * s->pitch));
+    }
+    return FB_OK;
+}
+
+int32_t fb_init_trim(fb_handle s, const fb_trim_params_soa* p, double* trim_state_out, double* cost_out) {
+    if (!s) return fail(FB_ERR_ARG, "null handle");
+    if (!s->tables_loaded) return fail(FB_ERR_STATE, "fb_init_trim: call fb_load_tables first");
+    CK(cudaSetDevice(s->cfg.device));
+    fb_trim_params_soa z; memset(&z, 0, sizeof(z));
+    if (!p) p = &z;
+    double* d_ts = nullptr; double* d_cost = nullptr;
+    {
+        Uploader U{s};
+        TrimSoA P;
+        P.lat = U.up(p->lat); P.lon = U.up(p->lon); P.h_e = U.up(p->h_e); P.psi_nb = U.up(p->psi_nb); P.EAS = U.up(p->EAS);
+        P.gamma_wb_n = U.up(p->gamma_wb_n); P.psi_wb_dot = U.up(p->psi_wb_dot); P.theta_wb_dot = U.up(p->theta_wb_dot);
+        P.beta_a = U.up(p->beta_a); P.fuel_load = U.up(p->fuel_load); P.mixture = U.up(p->mixture); P.flaps = U.up(p->flaps);
+        for (int j = 0; j < 5; j++) P.payload[j] = U.up(p->payload[j]);
+        if (U.err != cudaSuccess) return fail(FB_ERR_CUDA, cudaGetErrorString(U.err));
+        CK(cudaMalloc(&d_ts, sizeof(double) * 7 * s->pitch));
+        CK(cudaMalloc(&d_cost, sizeof(double) * s->pitch));
+        CK(FB_DISPATCH(s, trim)(s, P, d_ts, d_cost));
+        if (trim_state_out) CK(cudaMemcpy2DAsync(trim_state_out, sizeof(double) * s->E.n, d_ts, sizeof(double) * s->pitch, sizeof(double) * s->E.n, 7, cudaMemcpyDeviceToHost, s->stream));
+        if (cost_out) CK(cudaMemcpyAsync(cost_out, d_cost, sizeof(double) * s->E.n, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+    }
+    cudaFree(d_ts); cudaFree(d_cost);
+    return after_init(s);
+}
+
+int32_t fb_init(fb_handle s, const fb_init_soa* ic) {
+    if (!s) return fail(FB_ERR_ARG, "null handle");
+    if (!s->tables_loaded) return fail(FB_ERR_STATE, "fb_init: call fb_load_tables first");
+    CK(cudaSetDevice(s->cfg.device));
+    fb_init_soa z; memset(&z, 0, sizeof(z));
+    if (!ic) ic = &z;
+    {
+        Uploader U{s};
+        InitSoA I;
+        for (int j = 0; j < 4; j++) I.q_nb[j] = U.up(ic->q_nb[j]);
+        I.lat = U.up(ic->lat); I.lon = U.up(ic->lon); I.h_e = U.up(ic->h_e);
+        for (int j = 0; j < 3; j++) { I.w_wb_b[j] = U.up(ic->w_wb_b[j]); I.v_eb_n[j] = U.up(ic->v_eb_n[j]); }
+        I.n_eng = U.up(ic->n_eng); I.engine_state = U.up(ic->engine_state); I.throttle = U.up(ic->throttle); I.mixture = U.up(ic->mixture);
+        I.elevator = U.up(ic->elevator); I.aileron = U.up(ic->aileron); I.rudder = U.up(ic->rudder); I.flaps = U.up(ic->flaps);
+        I.brake_left = U.up(ic->brake_left); I.brake_right = U.up(ic->brake_right); I.fuel_load = U.up(ic->fuel_load);
+        for (int j = 0; j < 5; j++) I.payload[j] = U.up(ic->payload[j]);
+        I.stall = U.up(ic->stall); I.alpha_filt = U.up(ic->alpha_filt); I.beta_filt = U.up(ic->beta_filt);
+        if (U.err != cudaSuccess) return fail(FB_ERR_CUDA, cudaGetErrorString(U.err));
+        CK(FB_DISPATCH(s, init)(s, I));
+        CK(cudaStreamSynchronize(s->stream));
+    }
+    return after_init(s);
+}
+
+int32_t fb_init_state(fb_handle s, const double* x, const uint8_t* stall, const uint8_t* eng_state) {
+    if (!s || !x) return fail(FB_ERR_ARG, "fb_init_state: null argument");
+    if (!s->tables_loaded) return fail(FB_ERR_STATE, "fb_init_state: call fb_load_tables first");
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaMemcpy2DAsync(s->E.x, sizeof(double) * s->pitch, x, sizeof(double) * s->E.n, sizeof(double) * s->E.n, s->nx, cudaMemcpyHostToDevice, s->stream));
+    if (stall) CK(cudaMemcpyAsync(s->E.stall, stall, s->E.n, cudaMemcpyHostToDevice, s->stream)); else CK(cudaMemsetAsync(s->E.stall, 0, s->pitch, s->stream));
+    if (eng_state) CK(cudaMemcpyAsync(s->E.eng, eng_state, s->E.n, cudaMemcpyHostToDevice, s->stream)); else CK(cudaMemsetAsync(s->E.eng, FB_ENG_RUNNING, s->pitch, s->stream));
+    CK(cudaMemsetAsync(s->E.status, 0, sizeof(int) * s->pitch, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return after_init(s);
+}
+
+int32_t fb_set_input(fb_handle s, int32_t field, const double* values, int64_t stride) {
+    if (!s || !values) return fail(FB_ERR_ARG, "fb_set_input: null argument");
+    if (field < 0 || field >= FB_U__COUNT) return fail(FB_ERR_ARG, "fb_set_input: unknown field");
+    if (stride != 0 && stride != 1) return fail(FB_ERR_ARG, "fb_set_input: stride must be 0 (broadcast) or 1");
+    CK(cudaSetDevice(s->cfg.device));
+    double* row = s->E.u + (long long)field * s->pitch;
+    if (stride == 0) {
+        int grid = (int)((s->pitch + 255) / 256);
+        fill_kernel<<<grid, 256, 0, s->stream>>>(row, s->pitch, saturate_input(field, values[0]));
+        CK(cudaGetLastError());
+    } else {
+        s->h_row.resize(s->E.n);
+        for (long long i = 0; i < s->E.n; i++) s->h_row[i] = saturate_input(field, values[i]);
+        CK(cudaMemcpyAsync(row, s->h_row.data(), sizeof(double) * s->E.n, cudaMemcpyHostToDevice, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+    }
+    return FB_OK;
+}
+
+int32_t fb_get_input(fb_handle s, int32_t field, double* out) {
+    if (!s || !out) return fail(FB_ERR_ARG, "fb_get_input: null argument");
+    if (field < 0 || field >= FB_U__COUNT) return fail(FB_ERR_ARG, "fb_get_input: unknown field");
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaMemcpyAsync(out, s->E.u + (long long)field * s->pitch, sizeof(double) * s->E.n, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return FB_OK;
+}
+
+int32_t fb_schedule_inputs(fb_handle s, int64_t n_events, const int64_t* member, const int64_t* step, const int32_t* field, const double* value) {
+    if (!s) return fail(FB_ERR_ARG, "null handle");
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaStreamSynchronize(s->stream));
+    cudaFree(s->d_ev_off); cudaFree(s->d_ev_step); cudaFree(s->d_ev_field); cudaFree(s->d_ev_value);
+    s->d_ev_off = nullptr; s->d_ev_step = nullptr; s->d_ev_field = nullptr; s->d_ev_value = nullptr;
+    s->E.ev_off = nullptr; s->E.ev_step = nullptr; s->E.ev_field = nullptr; s->E.ev_value = nullptr;
+    CK(cudaMemsetAsync(s->d_ev_cursor, 0, sizeof(long long) * s->pitch, s->stream));
+    if (n_events <= 0) return FB_OK;
+    if (!member || !step || !field || !value) return fail(FB_ERR_ARG, "fb_schedule_inputs: null array");
+    long long N = s->E.n;
+    std::vector<long long> order(n_events);
+    std::iota(order.begin(), order.end(), 0LL);
+    for (long long k = 0; k < n_events; k++) {
+        if (member[k] < 0 || member[k] >= N) return fail(FB_ERR_ARG, "fb_schedule_inputs: member out of range");
+        if (field[k] < 0 || field[k] >= FB_U__COUNT) return fail(FB_ERR_ARG, "fb_schedule_inputs: unknown field");
+    }
+    std::stable_sort(order.begin(), order.end(), [&](long long a, long long b) { return member[a] != member[b] ? member[a] < member[b] : step[a] < step[b]; });
+    std::vector<long long> off(N + 1, 0), st(n_events); std::vector<int> fl(n_events); std::vector<double> vl(n_events);
+    for (long long k = 0; k < n_events; k++) { long long o = order[k]; off[member[o] + 1]++; st[k] = step[o]; fl[k] = field[o]; vl[k] = value[o]; }
+    for (long long i = 0; i < N; i++) off[i + 1] += off[i];
+    CK(cudaMalloc(&s->d_ev_off, sizeof(long long) * (N + 1))); CK(cudaMalloc(&s->d_ev_step, sizeof(long long) * n_events));
+    CK(cudaMalloc(&s->d_ev_field, sizeof(int) * n_events)); CK(cudaMalloc(&s->d_ev_value, sizeof(double) * n_events));
+    CK(cudaMemcpy(s->d_ev_off, off.data(), sizeof(long long) * (N + 1), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->d_ev_step, st.data(), sizeof(long long) * n_events, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->d_ev_field, fl.data(), sizeof(int) * n_events, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->d_ev_value, vl.data(), sizeof(double) * n_events, cudaMemcpyHostToDevice));
+    s->E.ev_off = s->d_ev_off; s->E.ev_step = s->d_ev_step; s->E.ev_field = s->d_ev_field; s->E.ev_value = s->d_ev_value;
+    return FB_OK;
+}
+
+static int32_t advance(fb_sim* s, long long n) {
+    CK(cudaSetDevice(s->cfg.device));
+    while (n > 0) {
+        int k = (int)std::min<long long>(n, s->cfg.steps_per_launch);
+        CK(FB_DISPATCH(s, step)(s, s->n_steps, k));
+        s->launches++;
+        s->n_steps += k;
+        n -= k;
+    }
+    return FB_OK;
+}
+
+int32_t fb_step(fb_handle s, double t_advance) {
+    if (!s) return fail(FB_ERR_ARG, "null handle");
+    if (!s->initialised) return fail(FB_ERR_STATE, "fb_step: not initialised (call fb_init_trim / fb_init / fb_init_state)");
+    if (t_advance < 0) return fail(FB_ERR_ARG, "fb_step: negative advance");
+    return advance(s, llround(t_advance / s->cfg.dt));
+}
+
+int32_t fb_run(fb_handle s) {
+    if (!s) return fail(FB_ERR_ARG, "null handle");
+    if (!s->initialised) return fail(FB_ERR_STATE, "fb_run: not initialised");
+    long long total = llround((s->cfg.t_end - s->cfg.t_start) / s->cfg.dt);
+    return advance(s, std::max(0LL, total - s->n_steps));
+}
+
+int32_t fb_time(fb_handle s, double* t, int64_t* n_steps) {
+    if (!s) return fail(FB_ERR_ARG, "null handle");
+    if (t) *t = s->cfg.t_start + s->n_steps * s->cfg.dt;
+    if (n_steps) *n_steps = s->n_steps;
+    return FB_OK;
+}
+
+int32_t fb_nx(fb_handle s, int32_t* nx) { if (!s || !nx) return fail(FB_ERR_ARG, "null argument"); *nx = s->nx; return FB_OK; }
+
+int32_t fb_get_state(fb_handle s, double* x) {
+    if (!s || !x) return fail(FB_ERR_ARG, "fb_get_state: null argument");
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaMemcpy2DAsync(x, sizeof(double) * s->E.n, s->E.x, sizeof(double) * s->pitch, sizeof(double) * s->E.n, s->nx, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return FB_OK;
+}
+
+int32_t fb_get_discrete(fb_handle s, uint8_t* stall, uint8_t* eng_state) {
+    if (!s) return fail(FB_ERR_ARG, "null handle");
+    CK(cudaSetDevice(s->cfg.device));
+    if (stall) CK(cudaMemcpyAsync(stall, s->E.stall, s->E.n, cudaMemcpyDeviceToHost, s->stream));
+    if (eng_state) CK(cudaMemcpyAsync(eng_state, s->E.eng, s->E.n, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return FB_OK;
+}
+
+int32_t fb_get_output(fb_handle s, int32_t field, double* out) {
+    if (!s || !out) return fail(FB_ERR_ARG, "fb_get_output: null argument");
+    if (field < 0 || field >= FB_Y__COUNT) return fail(FB_ERR_ARG, "fb_get_output: unknown field");
+    if (!s->initialised) return fail(FB_ERR_STATE, "fb_get_output: not initialised");
+    CK(cudaSetDevice(s->cfg.device));
+    CK(FB_DISPATCH(s, output)(s, field, s->d_scratch));
+    CK(cudaMemcpyAsync(out, s->d_scratch, sizeof(double) * s->E.n, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return FB_OK;
+}
+
+int32_t fb_status(fb_handle s, int32_t* status) {
+    if (!s || !status) return fail(FB_ERR_ARG, "fb_status: null argument");
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaMemcpyAsync(status, s->E.status, sizeof(int) * s->E.n, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    long long total = llround((s->cfg.t_end - s->cfg.t_start) / s->cfg.dt);
+    if (s->n_steps >= total && total > 0)
+        for (long long i = 0; i < s->E.n; i++) if (status[i] == FB_ST_RUNNING) status[i] = FB_ST_DONE;
+    return FB_OK;
+}
+
+int32_t fb_log_info(fb_handle s, int64_t* n_samples, int32_t* n_fields) {
+    if (!s) return fail(FB_ERR_ARG, "null handle");
+    long long ns = 0;
+    if (s->E.log_every > 0 && s->E.log_n_fields > 0 && s->initialised) ns = std::min<long long>(s->E.log_capacity, s->n_steps / s->E.log_every + 1);
+    if (n_samples) *n_samples = ns;
+    if (n_fields) *n_fields = s->E.log_n_fields;
+    return FB_OK;
+}
+
+int32_t fb_log_times(fb_handle s, double* t) {
+    int64_t ns; int32_t nf;
+    fb_log_info(s, &ns, &nf);
+    if (!t) return fail(FB_ERR_ARG, "null argument");
+    for (int64_t k = 0; k < ns; k++) t[k] = s->cfg.t_start + (double)(k * s->E.log_every) * s->cfg.dt;
+    return FB_OK;
+}
+
+int32_t fb_log_fetch(fb_handle s, int32_t field, double* out) {
+    if (!s || !out) return fail(FB_ERR_ARG, "fb_log_fetch: null argument");
+    int64_t ns; int32_t nf;
+    fb_log_info(s, &ns, &nf);
+    int fi = -1;
+    for (int f = 0; f < nf; f++) if (s->cfg.log_fields[f] == field) fi = f;
+    if (fi < 0) return fail(FB_ERR_ARG, "fb_log_fetch: field is not logged");
+    CK(cudaSetDevice(s->cfg.device));
+    // sample k of field fi lives at log[(k * nf + fi) * pitch]
+    CK(cudaMemcpy2DAsync(out, sizeof(double) * s->E.n, s->E.log + (long long)fi * s->pitch, sizeof(double) * s->pitch * nf,
+                         sizeof(double) * s->E.n, ns, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return FB_OK;
+}
+
+int32_t fb_stats(fb_handle s, int32_t field, fb_moments* out) {
+    if (!s || !out) return fail(FB_ERR_ARG, "fb_stats: null argument");
+    if (field < 0 || field >= FB_Y__COUNT) return fail(FB_ERR_ARG, "fb_stats: unknown field");
+    if (!s->initialised) return fail(FB_ERR_STATE, "fb_stats: not initialised");
+    CK(cudaSetDevice(s->cfg.device));
+    CK(FB_DISPATCH(s, output)(s, field, s->d_scratch));
+    double init[5] = {0.0, 0.0, 0.0, INFINITY, -INFINITY};
+    CK(cudaMemcpyAsync(s->d_stats, init, sizeof(init), cudaMemcpyHostToDevice, s->stream));
+    int grid = (int)((s->E.n + 255) / 256);
+    stats_kernel<<<grid, 256, 0, s->stream>>>(s->d_scratch, s->E.status, s->E.n, s->d_stats);
+    CK(cudaGetLastError());
+    double r[5];
+    CK(cudaMemcpyAsync(r, s->d_stats, sizeof(r), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    out->count = (int64_t)r[0]; out->sum = r[1]; out->sum_sq = r[2]; out->min = r[3]; out->max = r[4];
+    return FB_OK;
+}
+
+int32_t fb_rhs(fb_handle s, double* xdot) {
+    if (!s || !xdot) return fail(FB_ERR_ARG, "fb_rhs: null argument");
+    if (!s->initialised) return fail(FB_ERR_STATE, "fb_rhs: not initialised");
+    CK(cudaSetDevice(s->cfg.device));
+    CK(FB_DISPATCH(s, rhs)(s, s->d_scratch));
+    CK(cudaMemcpy2DAsync(xdot, sizeof(double) * s->E.n, s->d_scratch, sizeof(double) * s->pitch, sizeof(double) * s->E.n, s->nx, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return FB_OK;
+}
+
+int32_t fb_counters(fb_handle s, int64_t* kernel_launches, int64_t* rhs_evals) {
+    if (!s) return fail(FB_ERR_ARG, "null handle");
+    if (kernel_launches) *kernel_launches = s->launches;
+    if (rhs_evals) {
+        CK(cudaSetDevice(s->cfg.device));
+        unsigned long long c = 0;
+        CK(cudaMemcpyAsync(&c, s->d_rhs_count, sizeof(c), cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        *rhs_evals = (int64_t)c;
+    }
+    return FB_OK;
+}
+
+int32_t fb_device_state(fb_handle s, void** d_x, int64_t* pitch_elems) {
+    if (!s) return fail(FB_ERR_ARG, "null handle");
+    if (d_x) *d_x = s->E.x;
+    if (pitch_elems) *pitch_elems = s->pitch;
+    return FB_OK;
+}
+
+int32_t fb_stream(fb_handle s, void** stream) {
+    if (!s || !stream) return fail(FB_ERR_ARG, "null argument");
+    *stream = (void*)s->stream;
+    return FB_OK;
+}
+
+}  // extern "C"

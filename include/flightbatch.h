@@ -83,8 +83,8 @@ enum fb_input {
     /* C172XControl.ControlLawsLat.u, c172x_ctl.jl:826-836 */
     FB_U_LAT_MODE_REQ = 60, FB_U_LAT_AILERON_AXIS, FB_U_LAT_AILERON_OFFSET, FB_U_LAT_RUDDER_AXIS, FB_U_LAT_RUDDER_OFFSET,
     FB_U_LAT_P_REF, FB_U_LAT_BETA_REF, FB_U_LAT_PHI_REF, FB_U_LAT_CHI_REF,
-    /* remaining C172XControl.ControlLaws.u pass-throughs, c172x_ctl.jl:1190-1200 */
-    FB_U_CTL_FLAPS = 70, FB_U_CTL_BRAKE_LEFT, FB_U_CTL_BRAKE_RIGHT, FB_U_CTL_ENG_START, FB_U_CTL_ENG_STOP, FB_U_CTL_MIXTURE,
+    /* C172XGuidance.GuidanceLaws.u.mode_req, c172x_gdc.jl:281-283 (0 = direct) */
+    FB_U_GDC_MODE_REQ = 70,
     FB_U__COUNT = 80
 };
 

@@ -9,7 +9,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_GEOID = os.path.join(_HERE, "..", "flight.jl_b200", "data", "egm96_ww15mgh_le.bin")
+_GEOID = os.path.join(_HERE, "..", "flight.jl_b200", "data", "c172_tables.bin")
 
 
 def build():

@@ -102,15 +102,31 @@ static double get_output_field(const Sim& s, int f) {
 
 extern "C" {
 
+// reads the "geoid" section (721x1441 float32, latitude fastest) of the table blob written by
+// tools/build_tables.py — data only; the blob format is documented there.
 int orc_load_geoid(const char* path) {
     FILE* fp = fopen(path, "rb");
     if (!fp) return -1;
-    g_geoid_data.resize((size_t)Geoid::NLAT * Geoid::NLON);
-    size_t n = fread(g_geoid_data.data(), sizeof(float), g_geoid_data.size(), fp);
+    char magic[8]; uint32_t n = 0, pad = 0;
+    if (fread(magic, 1, 8, fp) != 8 || memcmp(magic, "FBTABLE1", 8) != 0) { fclose(fp); return -2; }
+    if (fread(&n, 4, 1, fp) != 1 || fread(&pad, 4, 1, fp) != 1) { fclose(fp); return -2; }
+    for (uint32_t i = 0; i < n; i++) {
+        struct { char name[24]; uint32_t dtype, ndim, dims[4]; uint64_t off, nbytes; } rec;
+        fseek(fp, 16 + 64L * i, SEEK_SET);
+        if (fread(&rec, 64, 1, fp) != 1) break;
+        if (strncmp(rec.name, "geoid", 24) == 0) {
+            g_geoid_data.resize((size_t)Geoid::NLAT * Geoid::NLON);
+            if (rec.nbytes != g_geoid_data.size() * 4) { fclose(fp); return -3; }
+            fseek(fp, (long)rec.off, SEEK_SET);
+            size_t got = fread(g_geoid_data.data(), sizeof(float), g_geoid_data.size(), fp);
+            fclose(fp);
+            if (got != g_geoid_data.size()) return -4;
+            g_geoid.data = g_geoid_data.data();
+            return 0;
+        }
+    }
     fclose(fp);
-    if (n != g_geoid_data.size()) return -2;
-    g_geoid.data = g_geoid_data.data();
-    return 0;
+    return -5;
 }
 
 void* orc_world_create() { if (!g_geoid.data) return nullptr; return new World(&g_geoid); }

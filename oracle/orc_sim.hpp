@@ -242,6 +242,7 @@ struct Sim {
     // then callbacks in CallbackSet order (step, periodic, user).
     void step() {
         if (m.status != ST_RUNNING) return;
+        apply_events();   // inputs scheduled at or before the current step index are already in force
         const int nx = m.L.nx;
         real x0[ORC_NX_MAX], k1[ORC_NX_MAX], k2[ORC_NX_MAX], k3[ORC_NX_MAX], k4[ORC_NX_MAX];
         for (int i = 0; i < nx; i++) x0[i] = m.x[i];
@@ -255,14 +256,16 @@ struct Sim {
             world_ode(); for (int i = 0; i < nx; i++) k3[i] = m.xdot[i];
             for (int i = 0; i < nx; i++) m.x[i] = x0[i] + dt * k3[i];
             world_ode(); for (int i = 0; i < nx; i++) k4[i] = m.xdot[i];
-            for (int i = 0; i < nx; i++) m.x[i] = x0[i] + (dt / 6) * (2.0 * (k2[i] + k3[i]) + (k1[i] + k4[i]));
-            world_ode();  // fsallast: leaves y*
-        } catch (OrcTermination& e) {
+        } catch (OrcTermination& e) {   // thrown inside a stage evaluation: the member freezes at the step start
             for (int i = 0; i < nx; i++) m.x[i] = x0[i];
             m.s = s0; m.status = e.code;
             return;
         }
+        for (int i = 0; i < nx; i++) m.x[i] = x0[i] + (dt / 6) * (2.0 * (k2[i] + k3[i]) + (k1[i] + k4[i]));
         n_steps++;
+        try {
+            world_ode();  // fsallast: leaves y*
+        } catch (OrcTermination& e) { m.status = e.code; return; }   // freezes at x*
         try {
             av.f_step(m);
             av.assign(m);

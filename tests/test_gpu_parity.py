@@ -1,0 +1,164 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Bars: continuous state <= 1e-9 scaled error (see parity_util.state_floors); Bool/enum state bit-exact."""
+import numpy as np
+import pytest
+
+from parity_util import scaled_err, state_floors
+
+pytestmark = pytest.mark.gpu
+
+SEED = 20261018
+
+
+def cfg2_params(n, rng):
+    EAS = rng.uniform(30, 55, n)
+    flaps = rng.choice([0.0, 1 / 3, 2 / 3, 1.0], n)
+    flaps[EAS < 35] = 1.0
+    flaps[EAS > 42] = 0.0   # full flap at high speed cannot be trimmed level with the available power
+    return dict(EAS=EAS, h_e=rng.uniform(50, 3050, n), flaps=flaps, psi_nb=rng.uniform(-np.pi, np.pi, n),
+                lat=np.deg2rad(rng.uniform(-60, 60, n)), lon=rng.uniform(-np.pi, np.pi, n), fuel_load=rng.uniform(0.1, 1, n),
+                m_pilot=rng.uniform(0, 100, n), m_copilot=rng.uniform(0, 100, n), m_lpass=rng.uniform(0, 100, n),
+                m_rpass=rng.uniform(0, 100, n), m_baggage=rng.uniform(0, 100, n))
+
+
+COPY_FIELDS = ["aileron", "elevator", "rudder", "aileron_offset", "elevator_offset", "rudder_offset", "flaps", "brake_left",
+               "brake_right", "throttle", "mixture", "eng_start", "eng_stop", "mixture_auto", "steering_engaged", "m_pilot",
+               "m_copilot", "m_lpass", "m_rpass", "m_baggage", "t_sl", "p_sl", "wind_n", "wind_e", "wind_d", "trn_elevation",
+               "trn_surface", "act_throttle", "act_aileron", "act_elevator", "act_rudder", "act_flaps", "act_brake_left",
+               "act_brake_right"]
+
+
+def oracle_from_gpu(fb, orc, sim, variant, kin, dt, idx, Dt=None):
+    """Oracle members started from the GPU ensemble's CURRENT state and inputs (isolates the stepping path)."""
+    x = sim.x
+    st, en = sim.discrete()
+    inputs = {f: sim.get_input(f) for f in COPY_FIELDS}
+    out = []
+    for i in idx:
+        o = orc.Sim(variant=variant, kin=kin, dt=dt, Dt=Dt)
+        for f, v in inputs.items():
+            o.set_input(fb.INPUT_NAMES[f], v[i])
+        o.init_state(x[:, i], stall=int(st[i]), eng_state=int(en[i]))
+        out.append(o)
+    return out
+
+
+def oracle_members(orc, variant, kin, dt, params, idx, Dt=None):
+    sims = []
+    for i in idx:
+        o = orc.Sim(variant=variant, kin=kin, dt=dt, Dt=Dt)
+        ok, ts, cost = o.init_trim(**{k: float(np.asarray(v)[i]) if np.ndim(v) else float(v) for k, v in params.items()})
+        assert ok
+        sims.append(o)
+    return sims
+
+
+@pytest.mark.parametrize("variant,kin", [(0, 0), (0, 2), (1, 0), (1, 2)])
+def test_trim_and_rhs_parity(fb, orc, variant, kin):
+    n = 64
+    rng = np.random.default_rng(SEED)
+    p = cfg2_params(n, rng)
+    ac = [fb.Cessna172Sv0, fb.Cessna172Xv0][variant]([fb.WA, None, fb.NED][kin]())
+    sim = fb.BatchSimulation(fb.SimpleWorld(ac), n=n, dt=0.01, t_end=10.0)
+    ok, ts, cost = sim.init(fb.C172.TrimParameters(**p))
+    assert ok.all()
+    assert cost.max() <= 1e-16
+    xg, xdg = sim.x, sim.xdot
+    fl = state_floors(sim.nx, variant, kin)
+    for i in range(0, n, 4):
+        o = oracle_members(orc, variant, kin, 0.01, p, [i])[0]
+        # trim states agree (both converge far below the reference optimiser's 1e-16 stop value)
+        assert np.max(scaled_err(xg[:, i], o.x, fl)) < 1e-9
+        # RHS at the SAME state: feed the GPU state to the oracle
+        st, en = o.discrete
+        o.init_state(xg[:, i], stall=st, eng_state=en)
+        xdo = o.xdot
+        err = np.abs(xdg[:, i] - xdo) / np.maximum(np.abs(xdo), fl)
+        assert err.max() < 1e-9, (i, err.argmax(), err.max())
+    sim.close()
+
+
+@pytest.mark.parametrize("variant,kin,steps", [(0, 0, 1000), (0, 2, 1000), (1, 0, 400)])
+def test_step_parity_with_doublets(fb, orc, variant, kin, steps):
+    n = 96
+    dt = 0.01
+    rng = np.random.default_rng(SEED + 1)
+    p = cfg2_params(n, rng)
+    ac = [fb.Cessna172Sv0, fb.Cessna172Xv0][variant]([fb.WA, None, fb.NED][kin]())
+    sim = fb.BatchSimulation(fb.SimpleWorld(ac), n=n, dt=dt, t_end=100.0, steps_per_launch=64)
+    ok, ts, cost = sim.init(fb.C172.TrimParameters(**p))
+    assert ok.all()
+    ele_f = fb.U["FB_U_ELEVATOR"] if variant == 0 else fb.U["FB_U_ACT_ELEVATOR"]
+    ail_f = fb.U["FB_U_AILERON"] if variant == 0 else fb.U["FB_U_ACT_AILERON"]
+    ele0, ail0 = sim.get_input(ele_f), sim.get_input(ail_f)
+    # elevator doublet +-0.1 on [1,2) s and [2,3) s, aileron doublet on [4,5), [5,6)
+    ev = []
+    for i in range(n):
+        ev += [(i, 100, ele_f, ele0[i] + 0.1), (i, 200, ele_f, ele0[i] - 0.1), (i, 300, ele_f, ele0[i]),
+               (i, 400, ail_f, ail0[i] + 0.1), (i, 500, ail_f, ail0[i] - 0.1), (i, 600, ail_f, ail0[i])]
+    m, s, f, v = zip(*ev)
+    sim.schedule_inputs(m, s, f, v)
+    idx = list(range(0, n, 8))
+    oracles = oracle_from_gpu(fb, orc, sim, variant, kin, dt, idx)
+    sim.step(steps * dt)
+    xg = sim.x
+    stg, eng = sim.discrete()
+    assert (sim.status() == 0).all()
+    fl = state_floors(sim.nx, variant, kin)
+    worst = 0.0
+    for i, o in zip(idx, oracles):
+        for (mi, si, fi, vi) in ev:
+            if mi == i:
+                o.add_event(si, fi, vi)
+        o.step(steps)
+        assert o.status == 0
+        err = scaled_err(xg[:, i], o.x, fl)
+        worst = max(worst, err.max())
+        assert err.max() < 1e-9, (i, int(err.argmax()), float(err.max()))
+        st, en = o.discrete
+        assert (st, en) == (int(stg[i]), int(eng[i]))
+    print("worst scaled state error", worst)
+    sim.close()
+
+
+def test_infeasible_trim_is_flagged_like_the_oracle(fb, orc):
+    # full flaps at 55 m/s EAS needs more power than the engine has: init! reports failure (c172.jl:934-940)
+    n = 8
+    EAS = np.array([54.9, 50.0, 54.2, 45.0, 55.0, 40.0, 35.0, 30.0])
+    flaps = np.array([1.0, 0.0, 1.0, 0.0, 1.0, 0.0, 0.5, 1.0])
+    h = np.full(n, 2700.0)
+    sim = fb.BatchSimulation(fb.SimpleWorld(fb.Cessna172Sv0(fb.WA())), n=n, dt=0.01, t_end=1.0)
+    ok, ts, cost = sim.init(fb.C172.TrimParameters(EAS=EAS, flaps=flaps, h_e=h))
+    st = sim.status()
+    for i in range(n):
+        o = orc.Sim(0, 0, 0.01)
+        ok_o, _, _ = o.init_trim(EAS=EAS[i], flaps=flaps[i], h_e=h[i])
+        assert bool(ok[i]) == ok_o
+        assert (st[i] == fb.FB_ST_TRIM_FAILED) == (not ok_o)
+    assert not ok.all() and ok.any()
+    sim.close()
+
+
+def test_outputs_match_oracle(fb, orc):
+    n = 32
+    rng = np.random.default_rng(SEED + 2)
+    p = cfg2_params(n, rng)
+    sim = fb.BatchSimulation(fb.SimpleWorld(fb.Cessna172Sv0(fb.WA())), n=n, dt=0.01, t_end=10.0)
+    sim.init(fb.C172.TrimParameters(**p))
+    sim.step(0.5)
+    names = ["psi", "theta", "phi", "lat", "lon", "h_e", "h_o", "v_n", "v_e", "v_d", "v_gnd", "chi_gnd", "gamma_gnd", "p", "q", "r",
+             "tas", "eas", "cas", "mach", "qbar", "alpha", "beta", "alpha_filt", "beta_filt", "stall", "c_l", "c_d",
+             "wow_left", "wow_right", "wow_nose", "eng_omega", "eng_state", "eng_map", "eng_p_shaft", "eng_tau_shaft", "eng_mdot",
+             "fuel_m_total", "prop_thrust", "prop_j", "mass", "f_x", "f_y", "f_z"]
+    xg = sim.x
+    stg, eng = sim.discrete()
+    out = {k: sim.get_output(k) for k in names}
+    for i in range(0, n, 4):
+        o = orc.Sim(variant=0, kin=0, dt=0.01)
+        o.init_trim(**{k: float(v[i]) for k, v in p.items()})
+        o.want_y_extra(True)
+        o.init_state(xg[:, i], stall=int(stg[i]), eng_state=int(eng[i]))
+        for k in names:
+            a, b = out[k][i], o.y(fb.OUTPUT_NAMES[k])
+            assert abs(a - b) <= 1e-9 * max(abs(b), 1e-2), (k, a, b)
+    sim.close()
