@@ -94,7 +94,7 @@ class fb_moments(C.Structure):
 EXPORTS = ["fb_api_version", "fb_last_error", "fb_create", "fb_load_tables", "fb_destroy", "fb_sync", "fb_init_trim", "fb_init",
            "fb_init_state", "fb_set_input", "fb_get_input", "fb_schedule_inputs", "fb_step", "fb_run", "fb_time", "fb_nx",
            "fb_get_state", "fb_get_discrete", "fb_get_output", "fb_status", "fb_log_info", "fb_log_times", "fb_log_fetch",
-           "fb_stats", "fb_rhs", "fb_counters", "fb_device_state", "fb_stream"]
+           "fb_stats", "fb_rhs", "fb_counters", "fb_device_state", "fb_stream", "fb_measure_fp64_peak"]
 
 _lib = None
 
@@ -124,6 +124,7 @@ def load_library():
         "fb_log_fetch": (i32, [vp, i32, _DP]), "fb_stats": (i32, [vp, i32, C.POINTER(fb_moments)]),
         "fb_rhs": (i32, [vp, _DP]), "fb_counters": (i32, [vp, C.POINTER(i64), C.POINTER(i64)]),
         "fb_device_state": (i32, [vp, C.POINTER(vp), C.POINTER(i64)]), "fb_stream": (i32, [vp, C.POINTER(vp)]),
+        "fb_measure_fp64_peak": (i32, [i32, _DP]),
     }
     for name in EXPORTS:
         f = getattr(lib, name)   # AttributeError if the library does not export a declared symbol
@@ -487,6 +488,14 @@ class TimeSeries:
         return self._cache[name]
 
     __getitem__ = __getattr__
+
+
+def measure_fp64_peak(device=0):
+    """Measured FP64 FMA throughput (TFLOP/s) of `device`: the roofline denominator of this path."""
+    lib = load_library()
+    v = C.c_double()
+    _ck(lib.fb_measure_fp64_peak(int(device), C.byref(v)), lib)
+    return v.value
 
 
 # reference-style free functions (Julia's init!, step!, run!)

@@ -102,6 +102,18 @@ __global__ void fill_kernel(double* p, long long n, double v) {
     if (i < n) p[i] = v;
 }
 
+// FP64 FMA-pipe peak probe: 8 independent dependent-FMA chains per thread, all SMs, no memory traffic
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
+    double r0 = threadIdx.x * 1e-3, r1 = r0 + 1, r2 = r0 + 2, r3 = r0 + 3, r4 = r0 + 4, r5 = r0 + 5, r6 = r0 + 6, r7 = r0 + 7;
+#pragma unroll 4
+    for (int i = 0; i < iters; i++) {
+        r0 = fma(r0, a, b); r1 = fma(r1, a, b); r2 = fma(r2, a, b); r3 = fma(r3, a, b);
+        r4 = fma(r4, a, b); r5 = fma(r5, a, b); r6 = fma(r6, a, b); r7 = fma(r7, a, b);
+    }
+    double s = r0 + r1 + r2 + r3 + r4 + r5 + r6 + r7;
+    if (s == 123.456) out[0] = s;   // never true; keeps the chains alive
+}
+
 // ------------------------------------------------------------------------------------ table blob
 struct BlobSec { std::string name; uint32_t dtype, ndim, dims[4]; uint64_t off, nbytes; };
 static bool parse_blob(const uint8_t* b, size_t n, std::vector<BlobSec>& out) {
@@ -569,6 +581,35 @@ int32_t fb_counters(fb_handle s, int64_t* kernel_launches, int64_t* rhs_evals) {
         CK(cudaStreamSynchronize(s->stream));
         *rhs_evals = (int64_t)c;
     }
+    return FB_OK;
+}
+
+// measured FP64 FMA throughput of the device (TFLOP/s, FMA = 2 flop): the roofline denominator of this path
+int32_t fb_measure_fp64_peak(int32_t device, double* tflops) {
+    if (!tflops) return fail(FB_ERR_ARG, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(FB_ERR_CUDA, "no CUDA device");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    double* d = nullptr;
+    CK(cudaMalloc(&d, 64));
+    const int iters = 1 << 15, blocks = prop.multiProcessorCount * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; rep++) {
+        CK(cudaEventRecord(e0));
+        fp64_peak_kernel<<<blocks, threads>>>(d, iters, 1.0000001, 1e-9);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        double fl = 2.0 * 8.0 * iters * (double)blocks * threads;
+        if (rep > 0) best = std::max(best, fl / (ms * 1e-3) * 1e-12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *tflops = best;
     return FB_OK;
 }
 

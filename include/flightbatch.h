@@ -219,6 +219,8 @@ int32_t fb_stats(fb_handle h, int32_t field, fb_moments* out);
 int32_t fb_rhs(fb_handle h, double* xdot);
 /* counters */
 int32_t fb_counters(fb_handle h, int64_t* kernel_launches, int64_t* rhs_evals_per_member);
+/* utility: measured FP64 FMA throughput of `device` in TFLOP/s (the roofline denominator of this path) */
+int32_t fb_measure_fp64_peak(int32_t device, double* tflops);
 /* device pointers for zero-copy interop with torch / CUDA.jl (valid until fb_destroy) */
 int32_t fb_device_state(fb_handle h, void** d_x, int64_t* pitch_elems);
 /* launch stream handle (cudaStream_t) so that callers can time with events on the right stream */
