@@ -32,7 +32,8 @@ __host__ __device__ inline double avionics_saturate_input(int f, double v) {
 template <int VAR, int KIN>
 __device__ __noinline__ void rhs_with_outputs(const double* x, double* xd, int stall, int eng, MemberIn u,
                                               const double* tb, const float* geoid, RhsOut* out, YFull* yf) {
-    rhs<VAR, KIN, true>(x, xd, stall, eng, u, tb, geoid, *out, yf);
+    ArraySink sink; sink.xd = xd;
+    rhs<VAR, KIN, true>(x, sink, stall, eng, u, tb, geoid, *out, yf);
 }
 
 FB_DEV double pick_output(const YFull& y, int stall, int eng, const CtlState& cs, int field) {

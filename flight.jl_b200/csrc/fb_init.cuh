@@ -133,6 +133,10 @@ init_kernel(EnsembleDev E, InitSoA I) {
     E.stall[i] = (unsigned char)stall; E.eng[i] = (unsigned char)eng; E.status[i] = FB_ST_RUNNING;
 }
 
+// trim bounds, c172.jl:897-917 (alpha_a, phi_nb, n_eng, throttle, aileron, elevator, rudder)
+__constant__ double c_trim_lo[7] = {-FB_PI / 12, -FB_PI / 3, 0.4, 0, -1, -1, -1};
+__constant__ double c_trim_hi[7] = {0.36, FB_PI / 3, 1.1, 1, 1, 1, 1};
+
 struct TrimP { double lat, lon, h_e, psi_nb, EAS, gamma, psi_dot, theta_dot, beta_a, fuel_load, mixture, flaps, payload[5]; };
 
 // assign!(vehicle, trim_params, trim_state) up to (not including) the final f_ode!
@@ -195,8 +199,8 @@ trim_kernel(EnsembleDev E, TrimSoA P, double* trim_state_out, double* cost_out) 
     const double pd[5] = {75.0, 75.0, 0.0, 0.0, 50.0};
     for (int j = 0; j < 5; j++) p.payload[j] = clampd(opt(P.payload[j], i, pd[j]), 0.0, 100.0);
 
-    const double lo[7] = {-FB_PI / 12, -FB_PI / 3, 0.4, 0, -1, -1, -1};
-    const double hi[7] = {0.36, FB_PI / 3, 1.1, 1, 1, 1, 1};
+    const double* lo = c_trim_lo;
+    const double* hi = c_trim_hi;
     double ts[7] = {0.1, 0.0, 0.75, 0.47, 0.014, -0.0015, 0.02};   // TrimState() defaults, c172.jl:796-804
     double x[NX], xd[NX];
     int stall = 0, eng = FB_ENG_RUNNING;
@@ -205,7 +209,8 @@ trim_kernel(EnsembleDev E, TrimSoA P, double* trim_state_out, double* cost_out) 
         int err = 0;
         trim_assign<VAR, KIN>(x, u, stall, eng, p, t, E.tables.geoid, err);
         RhsOut y;
-        rhs<VAR, KIN, false>(x, xd, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr);
+        ArraySink sink; sink.xd = xd;
+        rhs<VAR, KIN, false>(x, sink, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr);
         if (err || y.err) { for (int j = 0; j < 7; j++) r[j] = 1e3; return 7e6; }
         double vn = rsqrt(x[L::DYN + 3] * x[L::DYN + 3] + x[L::DYN + 4] * x[L::DYN + 4] + x[L::DYN + 5] * x[L::DYN + 5]);
         for (int j = 0; j < 3; j++) r[j] = xd[L::DYN + 3 + j] * vn;       // cost(vehicle), c172.jl:857-867
@@ -250,16 +255,24 @@ trim_kernel(EnsembleDev E, TrimSoA P, double* trim_state_out, double* cost_out) 
             double tn[7], rn[7];
             for (int q = 0; q < 7; q++) tn[q] = clampd(fma(lam, dx[q], ts[q]), lo[q], hi[q]);
             double cn = eval(tn, rn);
+#ifdef FB_TRIM_DEBUG
+            if (i == 0 && it >= 5 && ls == 0) printf("  lo %.6e %.6e %.6e hi %.6e %.6e %.6e dx0 %.6e fma %.10e clamp %.10e\n", lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], dx[0], fma(lam, dx[0], ts[0]), clampd(fma(lam, dx[0], ts[0]), lo[0], hi[0]));
+            if (i == 0 && it >= 5) printf("  ls %d lam %.3e ts0 %.10e tn0 %.10e ts1 %.10e tn1 %.10e cn %.6e c0 %.6e\n", ls, lam, ts[0], tn[0], ts[1], tn[1], cn, c0);
+#endif
             if (cn < c0) { for (int q = 0; q < 7; q++) { ts[q] = tn[q]; r0[q] = rn[q]; } c0 = cn; improved = true; break; }
             lam *= 0.5;
         }
+#ifdef FB_TRIM_DEBUG
+        if (i == 0) printf("it %d c0 %.3e lam %.3e improved %d dx %.3e %.3e %.3e %.3e %.3e %.3e %.3e\n", it, c0, lam, (int)improved, dx[0], dx[1], dx[2], dx[3], dx[4], dx[5], dx[6]);
+#endif
         if (!improved) break;
     }
     int err = 0;
     trim_assign<VAR, KIN>(x, u, stall, eng, p, ts, E.tables.geoid, err);   // leave the vehicle at the optimum
     // the trimmed condition must be airborne with the engine above idle (asserts at c172s.jl:256-261)
     RhsOut y;
-    rhs<VAR, KIN, false>(x, xd, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr);
+    ArraySink sink; sink.xd = xd;
+    rhs<VAR, KIN, false>(x, sink, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr);
     bool ok = (c0 <= 1e-16) && !err && !y.err && y.wow == 0;
 #pragma unroll
     for (int c = 0; c < NX; c++) E.x[(long long)c * E.pitch + i] = x[c];

@@ -1,11 +1,14 @@
-// fb_kernels.cuh — ensemble kernels: fused K-step RK4 integrator, single RHS (test hook), initialisers.
-// One thread per aircraft; state is struct-of-arrays in HBM (component-major, member fastest) and lives in
-// registers / local scratch for the K fused steps of one launch.
+// fb_kernels.cuh — ensemble kernels: fused K-step RK4 integrator, single RHS (test hook), output pass.
+// One thread per aircraft. The integrator keeps the step-start state x and the Runge-Kutta accumulator in
+// shared memory ([component][thread], conflict-free 64-bit columns), the stage state in registers, and folds
+// every derivative into both as soon as the RHS produces it; ensemble state in HBM is struct-of-arrays
+// (component-major, member fastest) and is touched once per launch of K fused steps.
 #pragma once
 #include "fb_physics.cuh"
 #include "fb_avionics.cuh"
 
-#define FB_BLOCK 128
+#define FB_BLOCK 128          // block size of the light kernels (rhs / output / init / trim)
+#define FB_STEP_MAX_BLOCK 448 // register budget of the integrator: 65536 / 448 = 146 registers per thread
 
 struct EnsembleDev {
     double* x;            // [NX][pitch]
@@ -67,6 +70,35 @@ __host__ __device__ inline double saturate_input(int f, double v) {   // Ranged{
     return avionics_saturate_input(f, v);
 }
 
+// Runge-Kutta sink: folds derivative component c into the accumulators the moment the RHS produces it.
+//   stage 0: acc = k            xs = x + dt/2 k
+//   stage 1: acc += 2k          xs = x + dt/2 k
+//   stage 2: acc += 2k          xs = x + dt k
+//   stage 3: x += dt/6 (acc+k)  xs = x
+// written with per-thread coefficients (ca, cb, cx) so that one code path serves all four stages:
+//   acc' = cb*k + ca*acc ; xs = x + cx * (last ? acc' : k) ; x = xs if last
+struct RkSink {
+    double* xs;          // stage state, registers
+    double* sx;          // shared: step-start state column of this thread  (stride T doubles)
+    double* sacc;        // shared: accumulator column of this thread
+    int T;
+    double ca, cb, cx;
+    bool last;
+    FB_DEV void put(int c, double k) {
+        double a = sacc[c * T], xv = sx[c * T];
+        double an = fma(cb, k, ca * a);
+        double xn = fma(cx, last ? an : k, xv);
+        sacc[c * T] = an;
+        xs[c] = xn;
+        if (last) sx[c * T] = xn;
+    }
+};
+struct SmemState {       // f_step! view of the step-start state column
+    double* sx; int T;
+    FB_DEV double get(int c) const { return sx[c * T]; }
+    FB_DEV void set(int c, double v) { sx[c * T] = v; }
+};
+
 // ------------------------------------------------------------------------------------------------
 // Fused integrator: K reference steps per launch. Per step:
 //   k1..k4 (inputs and discrete state frozen), x* = x + dt/6 (k1 + 2k2 + 2k3 + k4),
@@ -75,22 +107,27 @@ __host__ __device__ inline double saturate_input(int f, double v) {   // Ranged{
 // RHS reads, in which case it is evaluated again (as the reference always does). The loop below has ONE
 // call site of the RHS; each thread carries its own stage counter, so members that need the extra
 // evaluation simply run one iteration out of phase with their warp neighbours.
+// Dynamic shared memory: [table pack | x columns NX*T | acc columns NX*T].
 template <int VAR, int KIN>
-__global__ void __launch_bounds__(FB_BLOCK, 2)
+__global__ void __launch_bounds__(FB_STEP_MAX_BLOCK, 1)
 step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic_every, double Dt,
             unsigned long long* rhs_count) {
     typedef Lay<VAR, KIN> L;
     constexpr int NX = L::NX;
-    extern __shared__ __align__(16) double smem_tb[];
+    extern __shared__ __align__(16) double smem[];
+    double* smem_tb = smem;
+    const int T = blockDim.x;
     stage_tables(smem_tb, E.tables.pack);
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long i = (long long)blockIdx.x * T + threadIdx.x;
     if (i >= E.n) return;
     int status = E.status[i];
     if (status != FB_ST_RUNNING) return;
     MemberIn u; u.u = E.u + i; u.pitch = E.pitch;
-    double x[NX], xs[NX], acc[NX], k[NX];
+    double* sx = smem + FB_TB_BYTES / 8 + threadIdx.x;
+    double* sacc = sx + NX * T;
+    double xs[NX];
 #pragma unroll
-    for (int c = 0; c < NX; c++) { x[c] = E.x[(long long)c * E.pitch + i]; xs[c] = x[c]; }
+    for (int c = 0; c < NX; c++) { double v = E.x[(long long)c * E.pitch + i]; xs[c] = v; sx[c * T] = v; sacc[c * T] = 0.0; }
     int stall = E.stall[i], eng = E.eng[i];
     long long ev_cur = E.ev_off ? E.ev_off[i] + E.ev_cursor[i] : 0;
     const long long ev_end = E.ev_off ? E.ev_off[i + 1] : 0;
@@ -107,66 +144,61 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
     unsigned n_rhs = 0;
     bool pending = false;
     const double h2 = 0.5 * dt, h6 = dt * (1.0 / 6.0);
+    RkSink sink; sink.xs = xs; sink.sx = sx; sink.sacc = sacc; sink.T = T;
+    SmemState xstate; xstate.sx = sx; xstate.T = T;
     for (;;) {
+        // coefficients of this thread's current stage
+        sink.ca = (stage == 0) ? 0.0 : 1.0;
+        sink.cb = (stage == 1 || stage == 2) ? 2.0 : 1.0;
+        sink.cx = (stage == 3) ? h6 : ((stage == 2) ? dt : h2);
+        sink.last = (stage == 3);
         RhsOut y;
-        rhs<VAR, KIN, false>(xs, k, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr);
+        rhs<VAR, KIN, false>(xs, sink, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr);
         n_rhs++;
-        if (stage == 0) {
-            if (pending) {   // xs == x == x*: this evaluation is the reference's FSAL-last one, y = y*
-                pending = false;
-                done++;
-                if (y.err) { status = y.err; break; }
-                const long long step_idx = step0 + done;
-                const bool ctl_due = (VAR >= FB_C172X1) && (step_idx % periodic_every) == 0;
-                const bool log_due = E.log_every > 0 && E.log_n_fields > 0 && (step_idx % E.log_every) == 0 &&
-                                     (step_idx / E.log_every) < E.log_capacity;
-                YFull yf;
-                const int stall_y = stall, eng_y = eng;
-                if (ctl_due || log_due) {   // the saved / fed-back y is the one left by f(x*), before any callback
-                    RhsOut y2; double kd[NX];
-                    rhs_with_outputs<VAR, KIN>(xs, kd, stall, eng, u, smem_tb, E.tables.geoid, &y2, &yf);
-                }
-                bool changed = f_step<VAR, KIN>(x, stall, eng, u, y, status);
-                if (status != FB_ST_RUNNING) break;
-                if (ctl_due) changed |= avionics_periodic<VAR, KIN>(yf, y, u, cs, E.tables, Dt);
-                while (ev_cur < ev_end && E.ev_step[ev_cur] <= step_idx) {
-                    int f = E.ev_field[ev_cur];
-                    u.set(f, saturate_input(f, E.ev_value[ev_cur]));
-                    ev_cur++;
-                    changed = true;
-                }
-                if (log_due) {
-                    const long long smp = step_idx / E.log_every;
-                    for (int f = 0; f < E.log_n_fields; f++)
-                        E.log[(smp * E.log_n_fields + f) * E.pitch + i] = pick_output(yf, stall_y, eng_y, cs, E.log_fields[f]);
-                }
+        if (y.err) { status = y.err; break; }
+        if (stage == 3) { stage = 0; pending = true; continue; }   // xs == x == x*: next evaluation is the FSAL-last one
+        if (stage != 0 || !pending) { stage++; continue; }
+        // ---- stage 0 with a pending step end: this evaluation was the reference's f(x*) and y = y*.
+        // (It also produced the tentative k1 / first stage state of the next step.)
+        pending = false;
+        done++;
+        const long long step_idx = step0 + done;
+        const bool ctl_due = (VAR >= FB_C172X1) && (step_idx % periodic_every) == 0;
+        const bool log_due = E.log_every > 0 && E.log_n_fields > 0 && (step_idx % E.log_every) == 0 &&
+                             (step_idx / E.log_every) < E.log_capacity;
+        YFull yf;
+        const int stall_y = stall, eng_y = eng;
+        if (ctl_due || log_due) {   // the saved / fed-back y is the one left by f(x*), before any callback
+            double xl[NX], kd[NX];
 #pragma unroll
-                for (int c = 0; c < NX; c++) xs[c] = x[c];
-                if (done == n_steps) break;
-                if (changed) continue;            // re-evaluate k1 with the new x / s / u
-            } else if (y.err) { status = y.err; break; }
-#pragma unroll
-            for (int c = 0; c < NX; c++) { acc[c] = k[c]; xs[c] = fma(h2, k[c], x[c]); }
-            stage = 1;
-        } else {
-            if (y.err) { status = y.err; break; }
-            if (stage == 1) {
-#pragma unroll
-                for (int c = 0; c < NX; c++) { acc[c] = fma(2.0, k[c], acc[c]); xs[c] = fma(h2, k[c], x[c]); }
-                stage = 2;
-            } else if (stage == 2) {
-#pragma unroll
-                for (int c = 0; c < NX; c++) { acc[c] = fma(2.0, k[c], acc[c]); xs[c] = fma(dt, k[c], x[c]); }
-                stage = 3;
-            } else {
-#pragma unroll
-                for (int c = 0; c < NX; c++) { x[c] = fma(h6, acc[c] + k[c], x[c]); xs[c] = x[c]; }
-                stage = 0; pending = true;
-            }
+            for (int c = 0; c < NX; c++) xl[c] = sx[c * T];
+            RhsOut y2;
+            rhs_with_outputs<VAR, KIN>(xl, kd, stall, eng, u, smem_tb, E.tables.geoid, &y2, &yf);
         }
+        bool changed = f_step<VAR, KIN>(xstate, stall, eng, u, y, status);
+        if (status != FB_ST_RUNNING) break;
+        if (ctl_due) changed |= avionics_periodic<VAR, KIN>(yf, y, u, cs, E.tables, Dt);
+        while (ev_cur < ev_end && E.ev_step[ev_cur] <= step_idx) {
+            int f = E.ev_field[ev_cur];
+            u.set(f, saturate_input(f, E.ev_value[ev_cur]));
+            ev_cur++;
+            changed = true;
+        }
+        if (log_due) {
+            const long long smp = step_idx / E.log_every;
+            for (int f = 0; f < E.log_n_fields; f++)
+                E.log[(smp * E.log_n_fields + f) * E.pitch + i] = pick_output(yf, stall_y, eng_y, cs, E.log_fields[f]);
+        }
+        if (done == n_steps) break;
+        if (changed) {            // re-evaluate k1 from the post-callback x / s / u
+#pragma unroll
+            for (int c = 0; c < NX; c++) xs[c] = sx[c * T];
+            continue;             // stage stays 0, pending is false
+        }
+        stage = 1;
     }
 #pragma unroll
-    for (int c = 0; c < NX; c++) E.x[(long long)c * E.pitch + i] = x[c];
+    for (int c = 0; c < NX; c++) E.x[(long long)c * E.pitch + i] = sx[c * T];
     E.stall[i] = (unsigned char)stall; E.eng[i] = (unsigned char)eng; E.status[i] = status;
     if (E.ev_off) E.ev_cursor[i] = ev_cur - E.ev_off[i];
     if (VAR >= FB_C172X1) cs.store(E.ctl + i, E.pitch);
@@ -188,7 +220,8 @@ rhs_kernel(EnsembleDev E, double* xdot, double* alpha_out, int* wow_out, int* er
 #pragma unroll
     for (int c = 0; c < NX; c++) x[c] = E.x[(long long)c * E.pitch + i];
     RhsOut y;
-    rhs<VAR, KIN, false>(x, k, E.stall[i], E.eng[i], u, smem_tb, E.tables.geoid, y, nullptr);
+    ArraySink sink; sink.xd = k;
+    rhs<VAR, KIN, false>(x, sink, E.stall[i], E.eng[i], u, smem_tb, E.tables.geoid, y, nullptr);
 #pragma unroll
     for (int c = 0; c < NX; c++) xdot[(long long)c * E.pitch + i] = k[c];
     if (alpha_out) alpha_out[i] = y.alpha;
@@ -214,6 +247,7 @@ output_kernel(EnsembleDev E, int field, double* out) {
     CtlState cs;
     if (VAR >= FB_C172X1) cs.load(E.ctl + i, E.pitch);
     YFull yf; RhsOut y; double k[NX];
-    rhs<VAR, KIN, true>(x, k, E.stall[i], E.eng[i], u, smem_tb, E.tables.geoid, y, &yf);
+    ArraySink sink; sink.xd = k;
+    rhs<VAR, KIN, true>(x, sink, E.stall[i], E.eng[i], u, smem_tb, E.tables.geoid, y, &yf);
     out[i] = pick_output(yf, E.stall[i], E.eng[i], cs, field);
 }

@@ -14,13 +14,16 @@
 //   dynamics     lib/FlightPhysics/src/dynamics.jl:443-499
 //   actuation    lib/FlightApps/src/c172/c172s/c172s.jl:92-120, c172x/c172x.jl:39-52,127-143
 //
-// This is a B200-first restatement, not a transcription: the dataflow is rearranged so that one RHS
-// needs 6 atan2 + 3 exp/log instead of the reference's 21 atan2 + 8 pow + 5 sincos (results agree to
-// rounding): frame rotations are built from direction cosines / half-angle identities instead of
-// angle -> sincos round trips, the local-vertical at the CoM is the n-vector itself, output-only
-// quantities (CAS, total pressure, Euler angles, accelerations) are left to the output pass, mass
-// properties are evaluated in their affine-in-mass form, and a conservative height gate skips the
-// three strut evaluations while the aircraft is well clear of the terrain.
+// This is a B200-first restatement, not a transcription. The dataflow is rearranged so that one RHS needs
+// 6 atan2 + 1 log + 1 exp instead of the reference's 21 atan2 + 8 pow + 5 sincos (results agree to rounding):
+// frame rotations are built from direction cosines / half-angle identities instead of angle -> sincos round
+// trips, the local vertical at the CoM is the n-vector itself, output-only quantities (CAS, total pressure,
+// Euler angles, accelerations) are left to the output pass, mass properties are evaluated in their
+// affine-in-mass form, divisions by table spacings and constants are multiplications by stored reciprocals,
+// the remaining divisions / square roots use MUFU-seeded Newton sequences without IEEE slow paths, and a
+// conservative height gate skips the three strut evaluations while the aircraft is well clear of the terrain.
+// Derivatives are handed to a `Sink` as they are produced so that the integrator can fold each one into
+// its Runge-Kutta accumulators (kept in shared memory) instead of holding a derivative vector in registers.
 #pragma once
 #include "fb_math.cuh"
 #include "fb_tables.h"
@@ -83,38 +86,42 @@ struct MemberIn {       // per-member input view: field f of this member is u[f 
     FB_DEV void set(int f, double v) const { u[(long long)f * pitch] = v; }
 };
 
+// derivative sink that simply stores into a local array (test hook, trim, output pass)
+struct ArraySink {
+    double* xd;
+    FB_DEV void put(int c, double v) { xd[c] = v; }
+};
+// state holder over a plain array (f_step! on register / local state)
+struct ArrayState {
+    double* x;
+    FB_DEV double get(int c) const { return x[c]; }
+    FB_DEV void set(int c, double v) { x[c] = v; }
+};
+
 // ------------------------------------------------------------------------------------ interpolation
-// cell index / weight on explicit knots (Gridded(Linear())), coordinate already clamped to the knot span
-FB_DEV void locate(const double* k, int n, double x, int& i, double& w) {
+// cell index / weight on explicit knots (Gridded(Linear())); x already clamped to the knot span; ik = 1/spacing
+FB_DEV void locate(const double* k, const double* ik, int n, double x, int& i, double& w) {
     int lo = 0;
 #pragma unroll 1
     for (int j = 1; j < n - 1; j++) lo = (x >= k[j]) ? j : lo;
     i = lo;
-    w = (x - k[lo]) / (k[lo + 1] - k[lo]);
+    w = (x - k[lo]) * ik[lo];
 }
 FB_DEV double lerp(double a, double b, double w) { return fma(w, b - a, a); }
-FB_DEV double interp1_flat(const double* k, const double* y, int n, double x) {
-    x = clampd(x, k[0], k[n - 1]);
-    int i; double w;
-    locate(k, n, x, i, w);
-    return lerp(y[i], y[i + 1], w);
-}
-// uniform axis k0 + i*dk, n knots; Flat
-FB_DEV void locate_uniform(double k0, double dk, int n, double x, int& i, double& w) {
-    double t = (x - k0) / dk;
-    t = clampd(t, 0.0, (double)(n - 1));
+// uniform axis k0 + i/idk, n knots; Flat
+FB_DEV void locate_uniform(double k0, double idk, int n, double x, int& i, double& w) {
+    double t = clampd((x - k0) * idk, 0.0, (double)(n - 1));
     i = min((int)t, n - 2);
     w = t - (double)i;
 }
 
 // geoid undulation, bilinear on the EGM96 15' grid (geodesy.jl:186-211); geoid[lon][lat] float32
 FB_DEV double geoid_height(const float* __restrict__ g, double lat, double lon) {
-    double l = lon + 2.0 * FB_PI;
-    l = l - 2.0 * FB_PI * floor(l / (2.0 * FB_PI));
-    double fi = (lat + 0.5 * FB_PI) / (FB_PI / 720.0);
-    double fj = l / (2.0 * FB_PI / 1440.0);
-    int i = min(max((int)floor(fi), 0), FB_GEOID_NLAT - 2);
-    int j = min(max((int)floor(fj), 0), FB_GEOID_NLON - 2);
+    double l = (lon < 0.0) ? lon + 2.0 * FB_PI : lon;               // mod(lon + 2pi, 2pi) for lon in [-pi, pi]
+    double fi = (lat + 0.5 * FB_PI) * (720.0 / FB_PI);
+    double fj = l * (1440.0 / (2.0 * FB_PI));
+    int i = min(max((int)fi, 0), FB_GEOID_NLAT - 2);
+    int j = min(max((int)fj, 0), FB_GEOID_NLON - 2);
     double u = fi - (double)i, w = fj - (double)j;
     const float* p = g + (size_t)j * FB_GEOID_NLAT + i;
     double f00 = (double)__ldg(p), f10 = (double)__ldg(p + 1);
@@ -122,17 +129,16 @@ FB_DEV double geoid_height(const float* __restrict__ g, double lat, double lon) 
     return lerp(lerp(f00, f10, u), lerp(f01, f11, u), w);
 }
 FB_DEV double geoid_at_n(const float* __restrict__ g, d3 n) {
-    double lat = atan2(n.z, sqrt(fma(n.x, n.x, n.y * n.y)));
+    double lat = atan2(n.z, fb_sqrt(fma(n.x, n.x, n.y * n.y)));
     double lon = atan2(n.y, n.x);
     return geoid_height(g, lat, lon);
 }
 
 // ------------------------------------------------------------------------------------------ geodesy
-FB_DEV void radii(double n3, double& M, double& N) {
-    double fd2 = fma(-wgs::e2 * n3, n3, 1.0);
-    double fd = sqrt(fd2);
-    N = wgs::a / fd;
-    M = N * (1 - wgs::e2) / fd2;
+FB_DEV void radii(double n3, double& M, double& N) {   // geodesy.jl:125-129
+    double ifd = fb_rsqrt(fma(-wgs::e2 * n3, n3, 1.0));
+    N = wgs::a * ifd;
+    M = N * (1 - wgs::e2) * ifd * ifd;
 }
 FB_DEV d3 cartesian_from_geo(d3 n, double h) {
     double M, N;
@@ -143,13 +149,14 @@ FB_DEV d3 cartesian_from_geo(d3 n, double h) {
 FB_DEV void geo_from_cartesian(d3 r, d3& n, double& h) {
     constexpr double c = wgs::a * wgs::e2;
     constexpr double ec2 = 1 - wgs::e2;
-    const double ec = sqrt(ec2);
+    constexpr double ec = 0.99664718933525254;   // sqrt(1 - e2)
     double p2 = fma(r.x, r.x, r.y * r.y);
-    double p = sqrt(p2);
+    double ip = (p2 > 0.0) ? fb_rsqrt(p2) : 0.0;
+    double p = p2 * ip;
     double az = fabs(r.z);
     double zc = ec * az, s0 = az, c0 = ec * p;
     double a02 = fma(s0, s0, c0 * c0);
-    double a0 = sqrt(a02);
+    double a0 = fb_sqrt(a02);
     double a03 = a02 * a0;
     double sc = s0 * c0;
     double b0 = 1.5 * c * sc * (fma(p, s0, -zc * c0) * a0 - c * sc);
@@ -157,25 +164,23 @@ FB_DEV void geo_from_cartesian(d3 r, d3& n, double& h) {
     double c1 = fma(p, a03, -c * c0 * c0 * c0) * a03 - b0 * c0;
     double cc = ec * c1;
     double s12 = s1 * s1, cc2 = cc * cc;
-    double inv = rsqrt(s12 + cc2);
-    h = (fma(p, cc, s0 * s1) - wgs::a * sqrt(fma(ec2, s12, cc2))) * inv;
-    // cos(lat) = cc/sqrt(s1^2+cc^2), |sin(lat)| = s1/sqrt(s1^2+cc^2)
-    double cl = cc * inv, sl = s1 * inv;
+    double inv = fb_rsqrt(s12 + cc2);
+    h = (fma(p, cc, s0 * s1) - wgs::a * fb_sqrt(fma(ec2, s12, cc2))) * inv;
+    double cl = cc * inv, sl = s1 * inv;            // cos(lat), |sin(lat)|
     sl = (r.z > 0.0) ? sl : ((r.z < 0.0) ? -sl : 0.0);
-    double ip = (p > 0.0) ? 1.0 / p : 0.0;
-    double clon = (p > 0.0) ? r.x * ip : 1.0, slon = r.y * ip;
+    double clon = (p2 > 0.0) ? r.x * ip : 1.0, slon = r.y * ip;
     d3 v = mk3(cl * clon, cl * slon, sl);
-    double nn = rsqrt(dot(v, v));
+    double nn = fb_rsqrt(dot(v, v));                  // NVector constructor normalises (geodesy.jl:49-52)
     n = nn * v;
 }
 FB_DEV double gravity(double n3, double h) {  // Somigliana + 2nd-order altitude term (geodesy.jl:451-467)
     double s2 = n3 * n3;
-    double g0 = wgs::g_a * fma(wgs::k_g, s2, 1.0) * rsqrt(fma(-wgs::e2, s2, 1.0));
+    double g0 = wgs::g_a * fma(wgs::k_g, s2, 1.0) * fb_rsqrt(fma(-wgs::e2, s2, 1.0));
     return g0 * (1.0 - 2.0 / wgs::a * (1.0 + wgs::f + wgs::m - 2.0 * wgs::f * s2) * h + 3.0 / (wgs::a * wgs::a) * h * h);
 }
 
 // --------------------------------------------------------------------------------------- atmosphere
-struct Air { d3 v_wb_b; double T, p, rho, a, TAS, q, lnp; };  // lnp = log(p / p_std)
+struct Air { d3 v_wb_b; double T, p, rho, a, TAS, q, tr; };  // tr = T_ISA(p) / T_std (piston.jl:38)
 
 __device__ __noinline__ void isa_upper(double hg, double T_sl, double p_sl, double& T, double& p, int& err) {
     const double beta[7] = {-6.5e-3, 0, 1e-3, 2.8e-3, 0, -2.8e-3, -2e-3};
@@ -191,18 +196,23 @@ __device__ __noinline__ void isa_upper(double hg, double T_sl, double p_sl, doub
     }
     err = FB_ST_BOUNDS; T = Tb; p = pb;
 }
-FB_DEV void isa_data(double h_o, double T_sl, double p_sl, double& T, double& p, double& lnp, int& err) {
+__device__ __noinline__ double pow_slow(double a, double b) { return pow(a, b); }
+// ISA temperature / pressure at orthometric altitude h_o, plus tr = (p/p_std)^(-beta R/g) for the engine
+FB_DEV void isa_data(double h_o, double T_sl, double p_sl, double& T, double& p, double& tr, int& err) {
+    constexpr double beta = -6.5e-3;
+    constexpr double k = -isa::g_std / (beta * isa::R);     // 5.2558...
+    constexpr double kT = -beta * isa::R / isa::g_std;      // 1 / k
     if (h_o < -1000.0) err = FB_ST_BOUNDS;
-    double hg = h_o * wgs::a / (wgs::a + h_o);
+    double hg = h_o * wgs::a * fb_rcp(wgs::a + h_o);
     if (hg < 11000.0) {
-        constexpr double beta = -6.5e-3;
-        constexpr double k = -isa::g_std / (beta * isa::R);
         T = fma(beta, hg, T_sl);
-        lnp = log(p_sl * (1.0 / isa::p_std)) + k * log(T / T_sl);
-        p = isa::p_std * exp(lnp);
+        double ratio = T * fb_rcp(T_sl);
+        p = p_sl * exp(k * log(ratio));
+        // (p/p_std)^kT = (p_sl/p_std)^kT * ratio, since k * kT == 1
+        tr = (p_sl == isa::p_std) ? ratio : ratio * pow_slow(p_sl * (1.0 / isa::p_std), kT);
     } else {
         isa_upper(hg, T_sl, p_sl, T, p, err);
-        lnp = log(p * (1.0 / isa::p_std));
+        tr = pow_slow(p * (1.0 / isa::p_std), kT);
     }
 }
 
@@ -216,19 +226,20 @@ FB_DEV double pi_lane(double input, double x_i, double k_p, double k_i, double k
 }
 
 FB_DEV double get_mu(double mu_s, double mu_d, double v) {  // landinggear.jl:170-174, v_s 0.005, v_d 0.01
-    double k = clampd((fabs(v) - 0.005) / (0.01 - 0.005), 0.0, 1.0);
+    double k = clampd((fabs(v) - 0.005) * (1.0 / (0.01 - 0.005)), 0.0, 1.0);
     return k * mu_d + (1.0 - k) * mu_s;
 }
 
 // kinematic data shared by the subsystems of one RHS evaluation
 struct Kin { q4 q_nb, q_eb; d3 n_e, r_eb_e, w_wb_b, w_eb_b, v_eb_b, v_eb_n; double h_e, h_o, lat, lon; };
 
-// one landing-gear unit (strut + contact). Adds its wrench to (F, tau) in body axes.
-FB_DEV void ldg_unit(const Kin& k, const float* __restrict__ geoid, double elev, int surface,
-                     d3 r_bs_b, double k_s, double k_d_ext, double k_d_cmp,
-                     bool has_steering, bool steering_engaged, double steer_input, double brake,
-                     double x0, double x1, double& xd0, double& xd1, d3& F, d3& tau, int leg, RhsOut& out,
-                     double* xi_out, double* fdmp_out) {
+// one landing-gear unit (strut + contact). Adds its wrench to (F, tau) in body axes. Off the airborne fast path,
+// so it keeps IEEE divisions: wheel speeds and damper rates pass through zero here.
+__device__ __noinline__ void ldg_unit(const Kin& k, const float* __restrict__ geoid, double elev, int surface,
+                                      d3 r_bs_b, double k_s, double k_d_ext, double k_d_cmp,
+                                      bool has_steering, bool steering_engaged, double steer_input, double brake,
+                                      double x0, double x1, double& xd0, double& xd1, d3& F, d3& tau, int leg, RhsOut& out,
+                                      double* xi_out, double* fdmp_out) {
     const d3 e3 = mk3(0.0, 0.0, 1.0);
     d3 ks_e = qrot(k.q_eb, e3);
     d3 r_bs_e = qrot(k.q_eb, r_bs_b);
@@ -265,7 +276,7 @@ FB_DEV void ldg_unit(const Kin& k, const float* __restrict__ geoid, double elev,
         }
         // q_nw = q_nb o Rz(psi_sw) applied to e1 (landinggear.jl:291-296); Rz(psi) built from (cos, sin) by half angles
         double chw, shw;
-        half_angle(sn, cs, chw, shw);
+        half_angle_cs(cs, sn, chw, shw);
         d3 iw_n = qrot(qmul(k.q_nb, mkq(chw, 0.0, 0.0, shw)), mk3(1.0, 0.0, 0.0));
         double ch, sh;
         half_angle(iw_n.y, iw_n.x, ch, sh);              // contact frame = NED rotated about down by azimuth(iw_n)
@@ -308,23 +319,25 @@ FB_DEV void ldg_unit(const Kin& k, const float* __restrict__ geoid, double elev,
     }
 }
 
-// 2-D table on uniform ("scaled") axes with Line extrapolation (piston.jl:84-104): 2 x 9 tables
+// 2 x 9 table on uniform ("scaled") axes with Line extrapolation (piston.jl:84-104)
 FB_DEV double interp_2x9_line(const double* y, double n0, double n1, double x0, double x1, double n, double x) {
+    const double idn = 1.0 / (n1 - n0), idx = 8.0 / (x1 - x0);
     double ns = clampd(n, n0, n1), xs = clampd(x, x0, x1);
-    double u = (ns - n0) / (n1 - n0);
-    double t = (xs - x0) / ((x1 - x0) / 8.0);
+    double u = (ns - n0) * idn;
+    double t = (xs - x0) * idx;
     int j = min((int)t, 7);
     double w = t - (double)j;
     double f00 = y[j], f01 = y[j + 1], f10 = y[9 + j], f11 = y[9 + j + 1];
     double v = lerp(lerp(f00, f01, w), lerp(f10, f11, w), u);
-    double g0 = lerp(f10 - f00, f11 - f01, w) / (n1 - n0);
-    double g1 = lerp(f01 - f00, f11 - f10, u) / ((x1 - x0) / 8.0);
+    double g0 = lerp(f10 - f00, f11 - f01, w) * idn;
+    double g1 = lerp(f01 - f00, f11 - f10, u) * idx;
     return fma(n - ns, g0, fma(x - xs, g1, v));
 }
 
 // ------------------------------------------------------------------------------------------- the RHS
-template <int VAR, int KIN, bool WY>
-FB_DEV void rhs(const double* x, double* xd, int stall, int eng_state, const MemberIn& u,
+// x: state (read-only; every component is read before its derivative is put into the sink).
+template <int VAR, int KIN, bool WY, class Sink>
+FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const MemberIn& u,
                 const double* __restrict__ tb, const float* __restrict__ geoid, RhsOut& out, YFull* yf) {
     typedef Lay<VAR, KIN> L;
     out.wow = 0; out.crash = 0; out.err = 0;
@@ -338,31 +351,30 @@ FB_DEV void rhs(const double* x, double* xd, int stall, int eng_state, const Mem
         k.h_e = x[L::KINX + 8];
         double dq12 = 2.0 * q_ew.w * q_ew.x, dq13 = 2.0 * q_ew.w * q_ew.y;
         double dq24 = 2.0 * q_ew.x * q_ew.z, dq34 = 2.0 * q_ew.y * q_ew.z;
-        // psi_nw = atan2(-(dq34+dq12), dq24-dq13); q_nw = Rz(psi_nw)
+        // psi_nw = atan2(-(dq34+dq12), dq24-dq13); q_nw = Rz(psi_nw), built from (cos, sin) by half-angle identities
         double yy = -(dq34 + dq12), xx = dq24 - dq13;
-        double rr = sqrt(fma(xx, xx, yy * yy));
-        double c = xx / rr, s = yy / rr;
+        double irr = fb_rsqrt(fma(xx, xx, yy * yy));
+        double c = xx * irr, s = yy * irr;
         double ch, sh;
-        if (c >= 0.0) { ch = sqrt(0.5 * (1.0 + c)); sh = s / (2.0 * ch); }
-        else { double a = sqrt(0.5 * (1.0 - c)); sh = (s >= 0.0 ? a : -a); ch = s / (2.0 * sh); }
+        half_angle_cs(c, s, ch, sh);
         q4 q_nw = mkq(ch, 0.0, 0.0, sh);
         k.q_nb = qmul(q_nw, q_wb);
         k.q_eb = qmul(q_ew, q_wb);
         k.n_e = mk3(-(dq24 + dq13), -(dq34 - dq12), -(1.0 - 2.0 * (q_ew.x * q_ew.x + q_ew.y * q_ew.y)));
-        k.lat = atan2(k.n_e.z, sqrt(fma(k.n_e.x, k.n_e.x, k.n_e.y * k.n_e.y)));
+        k.lat = atan2(k.n_e.z, fb_sqrt(fma(k.n_e.x, k.n_e.x, k.n_e.y * k.n_e.y)));
         k.lon = atan2(k.n_e.y, k.n_e.x);
         k.v_eb_n = qrot(k.q_nb, k.v_eb_b);
         double M, N;
         radii(k.n_e.z, M, N);
         k.r_eb_e = mk3((N + k.h_e) * k.n_e.x, (N + k.h_e) * k.n_e.y, fma(N, 1 - wgs::e2, k.h_e) * k.n_e.z);
-        double wn_x = k.v_eb_n.y / (N + k.h_e), wn_y = -k.v_eb_n.x / (M + k.h_e);
+        double wn_x = k.v_eb_n.y * fb_rcp(N + k.h_e), wn_y = -k.v_eb_n.x * fb_rcp(M + k.h_e);
         d3 w_ew_w = mk3(fma(c, wn_x, s * wn_y), fma(-s, wn_x, c * wn_y), 0.0);  // q_nw'(w_ew_n)
         d3 w_ew_b = qrot_inv(q_wb, w_ew_w);
         k.w_wb_b = k.w_eb_b - w_ew_b;
         q4 d1 = qdt(q_wb, k.w_wb_b), d2 = qdt(q_ew, w_ew_w);
-        xd[L::KINX] = d1.w; xd[L::KINX + 1] = d1.x; xd[L::KINX + 2] = d1.y; xd[L::KINX + 3] = d1.z;
-        xd[L::KINX + 4] = d2.w; xd[L::KINX + 5] = d2.x; xd[L::KINX + 6] = d2.y; xd[L::KINX + 7] = d2.z;
-        xd[L::KINX + 8] = -k.v_eb_n.z;
+        sink.put(L::KINX, d1.w); sink.put(L::KINX + 1, d1.x); sink.put(L::KINX + 2, d1.y); sink.put(L::KINX + 3, d1.z);
+        sink.put(L::KINX + 4, d2.w); sink.put(L::KINX + 5, d2.x); sink.put(L::KINX + 6, d2.y); sink.put(L::KINX + 7, d2.z);
+        sink.put(L::KINX + 8, -k.v_eb_n.z);
     } else if (KIN == FB_NED) {
         double psi = x[L::KINX], th = x[L::KINX + 1], phi = x[L::KINX + 2];
         k.lat = x[L::KINX + 3]; k.lon = x[L::KINX + 4]; k.h_e = x[L::KINX + 5];
@@ -382,20 +394,21 @@ FB_DEV void rhs(const double* x, double* xd, int stall, int eng_state, const Mem
         double M, N;
         radii(k.n_e.z, M, N);
         k.r_eb_e = mk3((N + k.h_e) * k.n_e.x, (N + k.h_e) * k.n_e.y, fma(N, 1 - wgs::e2, k.h_e) * k.n_e.z);
-        double wx = k.v_eb_n.y / (N + k.h_e), wy = -k.v_eb_n.x / (M + k.h_e);
-        // latitude as LatLon(NVector(lat, lon)) sees it (kinematics.jl:417): identical to x.lat to rounding
-        d3 w_en_n = mk3(wx, wy, -k.v_eb_n.y * (sla / cla) / (N + k.h_e));
+        double iN = fb_rcp(N + k.h_e);
+        double wx = k.v_eb_n.y * iN, wy = -k.v_eb_n.x * fb_rcp(M + k.h_e);
+        double icla = fb_rcp(cla);
+        d3 w_en_n = mk3(wx, wy, -k.v_eb_n.y * (sla * icla) * iN);
         d3 w_nb_b = k.w_eb_b - qrot_inv(k.q_nb, w_en_n);
         k.w_wb_b = k.w_eb_b - qrot_inv(k.q_nb, mk3(wx, wy, 0.0));
-        double sf, cf, st, ct;
-        sincos(phi, &sf, &cf); sincos(th, &st, &ct);
-        double sec = 1.0 / ct, tn = st / ct;
-        xd[L::KINX] = (sf * w_nb_b.y + cf * w_nb_b.z) * sec;
-        xd[L::KINX + 1] = cf * w_nb_b.y - sf * w_nb_b.z;
-        xd[L::KINX + 2] = w_nb_b.x + (sf * w_nb_b.y + cf * w_nb_b.z) * tn;
-        xd[L::KINX + 3] = -wy;
-        xd[L::KINX + 4] = wx / cla;
-        xd[L::KINX + 5] = -k.v_eb_n.z;
+        double sf = 2.0 * sph * cph, cf = fma(-2.0 * sph, sph, 1.0);   // sin / cos of phi and theta from the half angles
+        double st = 2.0 * sth * cth, ct = fma(-2.0 * sth, sth, 1.0);
+        double sec = fb_rcp(ct), tn = st * sec;
+        sink.put(L::KINX, (sf * w_nb_b.y + cf * w_nb_b.z) * sec);
+        sink.put(L::KINX + 1, cf * w_nb_b.y - sf * w_nb_b.z);
+        sink.put(L::KINX + 2, w_nb_b.x + (sf * w_nb_b.y + cf * w_nb_b.z) * tn);
+        sink.put(L::KINX + 3, -wy);
+        sink.put(L::KINX + 4, wx * icla);
+        sink.put(L::KINX + 5, -k.v_eb_n.z);
     }
     if (k.h_e < -1000.0) out.err = FB_ST_BOUNDS;
     k.h_o = k.h_e - geoid_height(geoid, k.lat, k.lon);
@@ -417,14 +430,15 @@ FB_DEV void rhs(const double* x, double* xd, int stall, int eng_state, const Mem
 
     // ------------------------------------------------------------------ atmosphere + air data
     Air air;
-    isa_data(k.h_o, u(FB_U_T_SL), u(FB_U_P_SL), air.T, air.p, air.lnp, out.err);
-    air.rho = air.p / (isa::R * air.T);
-    air.a = sqrt(isa::gamma * isa::R * air.T);
+    isa_data(k.h_o, u(FB_U_T_SL), u(FB_U_P_SL), air.T, air.p, air.tr, out.err);
     {
+        double iRT = fb_rcp(isa::R * air.T);
+        air.rho = air.p * iRT;
+        air.a = fb_sqrt(isa::gamma * isa::R * air.T);
         d3 wind = mk3(u(FB_U_WIND_N), u(FB_U_WIND_E), u(FB_U_WIND_D));
         air.v_wb_b = k.v_eb_b - qrot_inv(k.q_nb, wind);
         double tas2 = dot(air.v_wb_b, air.v_wb_b);
-        air.TAS = sqrt(tas2);
+        air.TAS = (tas2 > 0.0) ? fb_sqrt(tas2) : 0.0;
         air.q = 0.5 * air.rho * tas2;
     }
     if (WY) {   // atmosphere.jl:220-242
@@ -453,7 +467,7 @@ FB_DEV void rhs(const double* x, double* xd, int stall, int eng_state, const Mem
             double xp = x[L::ACT + i];
             double cmd = u(FB_U_ACT_THROTTLE + i);   // stored saturated (Ranged)
             pos[i] = clampd(xp, lo, 1.0);
-            xd[L::ACT + i] = (1.0 / 0.05) * (cmd - xp);
+            sink.put(L::ACT + i, (1.0 / 0.05) * (cmd - xp));
             if (WY) { yf->act_pos[i] = pos[i]; yf->act_cmd[i] = cmd; }
         }
         throttle = pos[0]; a_a = pos[1]; a_e = -pos[2]; a_r = -pos[3]; steer = pos[3]; a_f = pos[4]; br_l = pos[5]; br_r = pos[6];
@@ -467,18 +481,18 @@ FB_DEV void rhs(const double* x, double* xd, int stall, int eng_state, const Mem
         double alpha_filt = x[L::AERO], beta_filt = x[L::AERO + 1];
         d3 v = air.v_wb_b;
         double alpha = 0.0, beta = 0.0, ca = 1.0, sa = 0.0;
-        double vxz2 = fma(v.x, v.x, v.z * v.z);
         if (air.TAS > 0.1) {   // covers both TAS thresholds (c172.jl:324, atmosphere.jl:337)
-            double vxz = sqrt(vxz2);
+            double vxz2 = fma(v.x, v.x, v.z * v.z);
+            double ivxz = (vxz2 > 0.0) ? fb_rsqrt(vxz2) : 0.0;
             alpha = atan2(v.z, v.x);
-            beta = atan2(v.y, vxz);
-            if (vxz > 0.0) { ca = v.x / vxz; sa = v.z / vxz; }
+            beta = atan2(v.y, vxz2 * ivxz);
+            if (vxz2 > 0.0) { ca = v.x * ivxz; sa = v.z * ivxz; }
         }
         out.alpha = alpha;
         double V = fmax(air.TAS, 1.0);
-        double i2V = 0.5 / V;
+        double i2V = 0.5 * fb_rcp(V);
         double afd = (1.0 / tau_f) * (alpha - alpha_filt), bfd = (1.0 / tau_f) * (beta - beta_filt);
-        xd[L::AERO] = afd; xd[L::AERO + 1] = bfd;
+        sink.put(L::AERO, afd); sink.put(L::AERO + 1, bfd);
         double p_nd = k.w_wb_b.x * b * i2V, q_nd = k.w_wb_b.y * c * i2V, r_nd = k.w_wb_b.z * b * i2V;
         double adot_nd = clampd(afd * c * i2V, -0.04, 0.04);
         double de = fma((23 + 28) * d2r * 0.5, a_e + 1.0, -28 * d2r);
@@ -489,21 +503,21 @@ FB_DEV void rhs(const double* x, double* xd, int stall, int eng_state, const Mem
         double a_c = clampd(alpha, -0.1, 0.36), b_c = clampd(beta, -0.2, 0.2);
         // flap axis (knots 0,10,20,30 deg) shared by five tables
         int jf; double wf;
-        { double dfc = clampd(df, tb[TB_DF_X], tb[TB_DF_X + 3]); locate(tb + TB_DF_X, 4, dfc, jf, wf); }
+        { double dfc = clampd(df, tb[TB_DF_X], tb[TB_DF_X + 3]); locate(tb + TB_DF_X, tb + TB_I_DF, 4, dfc, jf, wf); }
         double wf2 = clampd(df * (1.0 / (30 * d2r)), 0.0, 1.0);   // 2-knot flap axis (0, 30 deg)
         int ig; double wg;
-        { double g = clampd(dh_nd, 0.0, 1.1); locate(tb + TB_GE_X, 13, g, ig, wg); }
+        { double g = clampd(dh_nd, 0.0, 1.1); locate(tb + TB_GE_X, tb + TB_I_GE, 13, g, ig, wg); }
         double CD_ge = lerp(tb[TB_CD_GE + ig], tb[TB_CD_GE + ig + 1], wg);
         double CL_ge = lerp(tb[TB_CL_GE + ig], tb[TB_CL_GE + ig + 1], wg);
         double CD_df = lerp(tb[TB_CD_DF + jf], tb[TB_CD_DF + jf + 1], wf);
         double CL_df = lerp(tb[TB_CL_DF + jf], tb[TB_CL_DF + jf + 1], wf);
         double Cm_df = lerp(tb[TB_CM_DF + jf], tb[TB_CM_DF + jf + 1], wf);
         int ia; double wa;
-        { double ac = clampd(a_c, tb[TB_CD_A_X], tb[TB_CD_A_X + 25]); locate(tb + TB_CD_A_X, 26, ac, ia, wa); }
+        { double ac = clampd(a_c, tb[TB_CD_A_X], tb[TB_CD_A_X + 25]); locate(tb + TB_CD_A_X, tb + TB_I_CD_A, 26, ac, ia, wa); }
         const double* cd = tb + TB_CD_A_DF + ia * 4 + jf;
         double CD_a_df = lerp(lerp(cd[0], cd[1], wf), lerp(cd[4], cd[5], wf), wa);
         int il; double wl;
-        { double ac = clampd(a_c, tb[TB_CL_A_X], tb[TB_CL_A_X + 16]); locate(tb + TB_CL_A_X, 17, ac, il, wl); }
+        { double ac = clampd(a_c, tb[TB_CL_A_X], tb[TB_CL_A_X + 16]); locate(tb + TB_CL_A_X, tb + TB_I_CL_A, 17, ac, il, wl); }
         double CL_a = lerp(tb[TB_CL_A + il * 2 + stall], tb[TB_CL_A + il * 2 + 2 + stall], wl);
         double CD_de = 0.06 * fabs(clampd(de, -1.0, 1.0));       // knots (-1,0,1) -> (0.06,0,0.06)
         double CD_b = 0.17 * fabs(b_c);
@@ -540,22 +554,25 @@ FB_DEV void rhs(const double* x, double* xd, int stall, int eng_state, const Mem
         if (k.h_o - elev > 4.0) {
             // every strut attachment is < 2.4 m from Ob: no wheel can reach the terrain; regulators just leak
 #pragma unroll
-            for (int i = 0; i < 6; i++) xd[L::LDG + i] = -0.2 * x[L::LDG + i];
+            for (int i = 0; i < 6; i++) sink.put(L::LDG + i, -0.2 * x[L::LDG + i]);
             if (WY) { for (int i = 0; i < 3; i++) { yf->xi[i] = 0.0; yf->F_dmp[i] = 0.0; } }
         } else {
             int surface = (int)u(FB_U_TRN_SURFACE);
             bool eng = u(FB_U_STEERING_ENGAGED) != 0.0;
+            double xd[6];
             ldg_unit(k, geoid, elev, surface, mk3(-0.381, -1.092, 1.902), 39404, 9340, 9340, false, false, 0.0, br_l,
-                     x[L::LDG], x[L::LDG + 1], xd[L::LDG], xd[L::LDG + 1], F, tau, 0, out, WY ? &yf->xi[0] : nullptr, WY ? &yf->F_dmp[0] : nullptr);
+                     x[L::LDG], x[L::LDG + 1], xd[0], xd[1], F, tau, 0, out, WY ? &yf->xi[0] : nullptr, WY ? &yf->F_dmp[0] : nullptr);
             ldg_unit(k, geoid, elev, surface, mk3(-0.381, 1.092, 1.902), 39404, 9340, 9340, false, false, 0.0, br_r,
-                     x[L::LDG + 2], x[L::LDG + 3], xd[L::LDG + 2], xd[L::LDG + 3], F, tau, 1, out, WY ? &yf->xi[1] : nullptr, WY ? &yf->F_dmp[1] : nullptr);
+                     x[L::LDG + 2], x[L::LDG + 3], xd[2], xd[3], F, tau, 1, out, WY ? &yf->xi[1] : nullptr, WY ? &yf->F_dmp[1] : nullptr);
             ldg_unit(k, geoid, elev, surface, mk3(1.27, 0.0, 1.9), 26269, 3503, 3503, true, eng, steer, 0.0,
-                     x[L::LDG + 4], x[L::LDG + 5], xd[L::LDG + 4], xd[L::LDG + 5], F, tau, 2, out, WY ? &yf->xi[2] : nullptr, WY ? &yf->F_dmp[2] : nullptr);
+                     x[L::LDG + 4], x[L::LDG + 5], xd[4], xd[5], F, tau, 2, out, WY ? &yf->xi[2] : nullptr, WY ? &yf->F_dmp[2] : nullptr);
+#pragma unroll
+            for (int i = 0; i < 6; i++) sink.put(L::LDG + i, xd[i]);
         }
     }
 
     // ------------------------------------------------------------------ power plant
-    d3 h_rot;
+    double h_rot_x;
     double mdot;
     {
         constexpr double d = 2.0, J_xx = 0.3, J_eng = 0.05;
@@ -563,20 +580,25 @@ FB_DEV void rhs(const double* x, double* xd, int stall, int eng_state, const Mem
         double w = x[L::ENG];
         const d3 r_bp = mk3(2.055, 0.0, 0.833);
         d3 v = air.v_wb_b + cross(k.w_eb_b, r_bp);
-        double v_J = sqrt(dot(v, v));
+        double vJ2 = dot(v, v);
+        double v_J = (vJ2 > 0.0) ? fb_sqrt(vJ2) : 0.0;
         double aw = fabs(w);
-        double J = 2 * FB_PI * v_J / (fmax(aw, 1.0) * d);
-        double Mt = aw * (d / 2) / air.a;
+        double J = (2 * FB_PI / d) * v_J * fb_rcp(fmax(aw, 1.0));
+        double Mt = aw * (d / 2) * fb_rcp(air.a);
         int ij, im; double wj, wm;
-        locate_uniform(0.0, 1.5 / 20, 21, J, ij, wj);
-        locate_uniform(0.0, 1.5 / 20, 21, Mt, im, wm);
-        const double* p00 = tb + TB_PROP + (ij * 21 + im) * 6;
-        const double* p10 = p00 + 21 * 6;
+        locate_uniform(0.0, 20 / 1.5, 21, J, ij, wj);
+        locate_uniform(0.0, 20 / 1.5, 21, Mt, im, wm);
+        const double* p00 = tb + TB_PROP + (ij * 21 + im) * 4;
+        const double* p10 = p00 + 21 * 4;
         double cf[4];
 #pragma unroll
-        for (int c = 0; c < 4; c++) cf[c] = lerp(lerp(p00[c], p00[6 + c], wm), lerp(p10[c], p10[6 + c], wm), wj);
+        for (int c = 0; c < 4; c++) cf[c] = lerp(lerp(p00[c], p00[4 + c], wm), lerp(p10[c], p10[4 + c], wm), wj);
         double al_p = 0.0, be_p = 0.0;
-        if (v_J >= 0.1) { double vxz = sqrt(fma(v.x, v.x, v.z * v.z)); al_p = atan2(v.z, v.x); be_p = atan2(v.y, vxz); }
+        if (v_J >= 0.1) {
+            double vxz2 = fma(v.x, v.x, v.z * v.z);
+            double vxz = (vxz2 > 0.0) ? fb_sqrt(vxz2) : 0.0;
+            al_p = atan2(v.z, v.x); be_p = atan2(v.y, vxz);
+        }
         double f = w * (1.0 / (2 * FB_PI)), f2 = f * f;
         constexpr double d4 = d * d * d * d, d5 = d4 * d;
         double kF = air.rho * f2 * d4, kM = air.rho * f2 * d5;
@@ -584,13 +606,13 @@ FB_DEV void rhs(const double* x, double* xd, int stall, int eng_state, const Mem
         d3 Mp = mk3(kM * cf[1], kM * cf[3] * be_p, kM * cf[3] * al_p);
         F = F + Fp;
         tau = tau + Mp + cross(r_bp, Fp);
-        h_rot = mk3(J_xx * w, 0.0, 0.0);
+        h_rot_x = J_xx * w;
         double tau_load = Mp.x;
         // engine
         double xd_frc, xd_idle;
         double o_frc = pi_lane(-w, x[L::ENG + 2], 5.0, 200.0, 0.0, -1.0, 1.0, xd_frc);
-        double o_idle = pi_lane(1.0 - w / w_idle, x[L::ENG + 1], 4.0, 2.0, 0.0, -0.5, 0.5, xd_idle);
-        xd[L::ENG + 1] = xd_idle; xd[L::ENG + 2] = xd_frc;
+        double o_idle = pi_lane(1.0 - w * (1.0 / w_idle), x[L::ENG + 1], 4.0, 2.0, 0.0, -0.5, 0.5, xd_idle);
+        sink.put(L::ENG + 1, xd_idle); sink.put(L::ENG + 2, xd_frc);
         double tau_shaft;
         mdot = 0.0;
         double MAP_y = air.p, P_y = 0.0;
@@ -600,32 +622,31 @@ FB_DEV void rhs(const double* x, double* xd, int stall, int eng_state, const Mem
             tau_shaft = tau_start;
             P_y = tau_shaft * w;
             if (WY) {   // MAP = mu * p_std needs mu also in this state (piston.jl:378-384)
-                constexpr double kT = 6.5e-3 * isa::R / isa::g_std;
-                double tr = exp(kT * air.lnp);
-                double delta = (air.p * (1.0 / isa::p_std)) * rsqrt(tr);
+                double delta = (air.p * (1.0 / isa::p_std)) * rsqrt(air.tr);
                 double mri = 0.5 + o_idle;
                 MAP_y = interp_2x9_line(tb + TB_MU_WOT, 0.667, 1.0, 0.441, 1.0, w * (1.0 / w_rated), delta) * fma(throttle, 1.0 - mri, mri) * isa::p_std;
             }
         } else {
             double n = w * (1.0 / w_rated);
-            // T_ISA(p)/T_std = (p/p_std)^(-beta R / g), delta = (p/p_std) (T_ISA/T_std)^-0.5 (piston.jl:38-39)
-            constexpr double kT = 6.5e-3 * isa::R / isa::g_std;
-            double tr = exp(kT * air.lnp);                 // T_ISA(p) / T_std
-            double delta = (air.p * (1.0 / isa::p_std)) * rsqrt(tr);
+            // delta = (p/p_std) (T_ISA(p)/T_std)^-0.5 (piston.jl:38-39)
+            double itr = fb_rsqrt(air.tr);
+            double delta = (air.p * (1.0 / isa::p_std)) * itr;
             double mu_ratio_idle = 0.5 + o_idle;
             double mu_wot = interp_2x9_line(tb + TB_MU_WOT, 0.667, 1.0, 0.441, 1.0, n, delta);
             double mu = mu_wot * fma(throttle, 1.0 - mu_ratio_idle, mu_ratio_idle);
-            double sq_rr = sqrt(air.rho * (1.0 / isa::rho_std));   // 1/k_f
+            double rr = air.rho * (1.0 / isa::rho_std);
+            double isq = fb_rsqrt(rr);          // k_f = 1 / sqrt(rho / rho_std)
+            double sq_rr = rr * isq;
             double mixture = u(FB_U_MIXTURE);
             double mixture_pos = (u(FB_U_MIXTURE_AUTO) == 0.0) ? 0.5 * (mixture + 1.0)
                                                                : fma(mixture, 0.0950 - 0.0625, 0.0625) * sq_rr * (1.0 / 0.0950);
-            double far = (0.0950 * mixture_pos) / sq_rr;
+            double far = (0.0950 * mixture_pos) * isq;
             double d_wot = interp_2x9_line(tb + TB_D_WOT, 0.667, 1.0, 0.401, 0.936, n, mu);
             // pi_std(n, mu): gridded 13 x 3, Flat
             double pi_std, pi_wot;
             {
                 double nc = clampd(n, tb[TB_N_STD], tb[TB_N_STD + 12]);
-                int i; double wn; locate(tb + TB_N_STD, 13, nc, i, wn);
+                int i; double wn; locate(tb + TB_N_STD, tb + TB_I_N_STD, 13, nc, i, wn);
                 double mc = clampd(mu, 0.0, 1.0);
                 int j = (mc >= 0.568) ? 1 : 0;
                 double wmu = (j == 0) ? mc * (1.0 / 0.568) : (mc - 0.568) * (1.0 / (1.0 - 0.568));
@@ -634,7 +655,7 @@ FB_DEV void rhs(const double* x, double* xd, int stall, int eng_state, const Mem
             }
             {   // pi_wot(n, d_wot): gridded 5 x 3 (delta knots 0, 0.441, 1), Flat in n and below, Line above in delta
                 double nc = clampd(n, tb[TB_N_WOT], tb[TB_N_WOT + 4]);
-                int i; double wn; locate(tb + TB_N_WOT, 5, nc, i, wn);
+                int i; double wn; locate(tb + TB_N_WOT, tb + TB_I_N_WOT, 5, nc, i, wn);
                 double dc = clampd(d_wot, 0.0, 1.0);
                 int j = (dc >= 0.441) ? 1 : 0;
                 double wd = (j == 0) ? dc * (1.0 / 0.441) : (dc - 0.441) * (1.0 / (1.0 - 0.441));
@@ -645,14 +666,14 @@ FB_DEV void rhs(const double* x, double* xd, int stall, int eng_state, const Mem
                     pi_wot = fma(d_wot - 1.0, g, pi_wot);
                 }
             }
-            double pi_ISA = (fabs(d_wot - 1.0) < 5e-3) ? pi_std : fma((pi_wot - pi_std) / (d_wot - 1.0), delta - 1.0, pi_std);
+            double pi_ISA = (fabs(d_wot - 1.0) < 5e-3) ? pi_std : fma(fb_div(pi_wot - pi_std, d_wot - 1.0), delta - 1.0, pi_std);
             pi_ISA = fmax(pi_ISA, 0.0);
-            double pi_pow = pi_ISA * sqrt(tr * isa::T_std / air.T);
+            double pi_pow = pi_ISA * fb_sqrt(air.tr * isa::T_std * fb_rcp(air.T));
             int jf; double wff;
-            { double fc = clampd(far, tb[TB_F_X], tb[TB_F_X + 10]); locate(tb + TB_F_X, 11, fc, jf, wff); }
+            { double fc = clampd(far, tb[TB_F_X], tb[TB_F_X + 10]); locate(tb + TB_F_X, tb + TB_I_F, 11, fc, jf, wff); }
             double pi_actual = pi_pow * lerp(tb[TB_PI_RATIO + jf], tb[TB_PI_RATIO + jf + 1], wff);
             double P_shaft = P_rated * pi_actual;
-            tau_shaft = (w > 0.0) ? P_shaft / w : 0.0;
+            tau_shaft = (w > 0.0) ? fb_div(P_shaft, w) : 0.0;
             MAP_y = mu * isa::p_std; P_y = P_shaft;
             // sfc_pow(n, pi_actual): gridded 5 x 8, Line
             double sfc;
@@ -660,19 +681,19 @@ FB_DEV void rhs(const double* x, double* xd, int stall, int eng_state, const Mem
                 double nc = clampd(n, tb[TB_N_SFC], tb[TB_N_SFC + 4]);
                 double pc = clampd(pi_actual, tb[TB_PI_SFC], tb[TB_PI_SFC + 7]);
                 int i, j; double wn, wp;
-                locate(tb + TB_N_SFC, 5, nc, i, wn);
-                locate(tb + TB_PI_SFC, 8, pc, j, wp);
+                locate(tb + TB_N_SFC, tb + TB_I_N_SFC, 5, nc, i, wn);
+                locate(tb + TB_PI_SFC, tb + TB_I_PI_SFC, 8, pc, j, wp);
                 const double* t = tb + TB_SFC_POW + i * 8 + j;
                 double f00 = t[0], f01 = t[1], f10 = t[8], f11 = t[9];
                 sfc = lerp(lerp(f00, f01, wp), lerp(f10, f11, wp), wn);
-                double g0 = lerp(f10 - f00, f11 - f01, wp) / (tb[TB_N_SFC + i + 1] - tb[TB_N_SFC + i]);
-                double g1 = lerp(f01 - f00, f11 - f10, wn) / (tb[TB_PI_SFC + j + 1] - tb[TB_PI_SFC + j]);
+                double g0 = lerp(f10 - f00, f11 - f01, wp) * tb[TB_I_N_SFC + i];
+                double g1 = lerp(f01 - f00, f11 - f10, wn) * tb[TB_I_PI_SFC + j];
                 sfc = fma(n - nc, g0, fma(pi_actual - pc, g1, sfc));
             }
             double SFC = sfc * lerp(tb[TB_SFC_RATIO + jf], tb[TB_SFC_RATIO + jf + 1], wff);
             mdot = SFC * P_shaft;
         }
-        xd[L::ENG] = (tau_shaft + tau_load) * (1.0 / (J_eng + J_xx));
+        sink.put(L::ENG, (tau_shaft + tau_load) * (1.0 / (J_eng + J_xx)));
         if (WY) {
             yf->eng_omega = w; yf->eng_n = w * (1.0 / w_rated); yf->eng_MAP = MAP_y; yf->eng_P_shaft = P_y; yf->eng_tau_shaft = tau_shaft;
             yf->eng_mdot = mdot; yf->prop_thrust = Fp.x; yf->prop_J = J;
@@ -680,8 +701,9 @@ FB_DEV void rhs(const double* x, double* xd, int stall, int eng_state, const Mem
     }
     // ------------------------------------------------------------------ fuel
     constexpr double m_full = 114.4, m_res = 1.0;
-    xd[L::FUEL] = -mdot * (1.0 / (m_full - m_res));
-    double m_fuel = fmax(0.0, fma(x[L::FUEL], m_full - m_res, m_res));
+    const double x_fuel = x[L::FUEL];
+    sink.put(L::FUEL, -mdot * (1.0 / (m_full - m_res)));
+    double m_fuel = fmax(0.0, fma(x_fuel, m_full - m_res, m_res));
 
     // ------------------------------------------------------------------ mass properties (affine in the masses)
     // airframe at Ob: m 767, J_G diag(820,1164,1702), r (0.056,0,0.582): J_O = J_G + m (|r|^2 I - r r^T)
@@ -706,7 +728,7 @@ FB_DEV void rhs(const double* x, double* xd, int stall, int eng_state, const Mem
     }
     // ------------------------------------------------------------------ rigid-body dynamics (dynamics.jl:443-499)
     {
-        double im = 1.0 / m;
+        double im = fb_rcp(m);
         d3 rc = mk3(mrx * im, mry * im, mrz * im);
         // inertia about the CoM: J_c = J_O - m (|rc|^2 I - rc rc^T)
         double a11 = Jxx - m * (rc.y * rc.y + rc.z * rc.z), a22 = Jyy - m * (rc.x * rc.x + rc.z * rc.z), a33 = Jzz - m * (rc.x * rc.x + rc.y * rc.y);
@@ -733,39 +755,42 @@ FB_DEV void rhs(const double* x, double* xd, int stall, int eng_state, const Mem
             g_c = mk3(fma(s1, u_dn.x, g_c.x), fma(s1, u_dn.y, g_c.y), fma(s1, u_dn.z - g, g_c.z));
         }
         auto Jmul = [&](d3 v) { return mk3(a11 * v.x + a12 * v.y + a13 * v.z, a12 * v.x + a22 * v.y + a23 * v.z, a13 * v.x + a23 * v.y + a33 * v.z); };
-        d3 hc = Jmul(w_ic) + h_rot;
+        d3 hc = Jmul(w_ic);
+        hc.x += h_rot_x;
         d3 rhs3 = tau_c - Jmul(cross(w_ie_b, w)) - cross(w_ic, hc);
         // symmetric 3x3 solve by cofactors
         double c11 = a22 * a33 - a23 * a23, c12 = a13 * a23 - a12 * a33, c13 = a12 * a23 - a13 * a22;
         double c22 = a11 * a33 - a13 * a13, c23 = a12 * a13 - a11 * a23, c33 = a11 * a22 - a12 * a12;
-        double idet = 1.0 / (a11 * c11 + a12 * c12 + a13 * c13);
+        double idet = fb_rcp(a11 * c11 + a12 * c12 + a13 * c13);
         d3 wd = mk3((c11 * rhs3.x + c12 * rhs3.y + c13 * rhs3.z) * idet,
                     (c12 * rhs3.x + c22 * rhs3.y + c23 * rhs3.z) * idet,
                     (c13 * rhs3.x + c23 * rhs3.y + c33 * rhs3.z) * idet);
         d3 vd_c = im * F + g_c - cross(w + 2.0 * w_ie_b, v_c);
         d3 vd_b = vd_c - cross(wd, rc);
-        xd[L::DYN] = wd.x; xd[L::DYN + 1] = wd.y; xd[L::DYN + 2] = wd.z;
-        xd[L::DYN + 3] = vd_b.x; xd[L::DYN + 4] = vd_b.y; xd[L::DYN + 5] = vd_b.z;
+        sink.put(L::DYN, wd.x); sink.put(L::DYN + 1, wd.y); sink.put(L::DYN + 2, wd.z);
+        sink.put(L::DYN + 3, vd_b.x); sink.put(L::DYN + 4, vd_b.y); sink.put(L::DYN + 5, vd_b.z);
         if (WY) {   // specific force at the CoM, dynamics.jl:503-508: f = a_ic - gamma = vd_c + (w + 2 w_ie) x v_c - g_c
             yf->f_c_c = vd_c + cross(w + 2.0 * w_ie_b, v_c) - g_c;
-            yf->mass = m; yf->fuel_m_total = fma(x[L::FUEL], m_full - m_res, m_res); yf->wow = out.wow;
+            yf->mass = m; yf->fuel_m_total = fma(x_fuel, m_full - m_res, m_res); yf->wow = out.wow;
         }
     }
 }
 
 // f_step!(world) (world.jl:34-39 -> aircraftbase.jl:172-181 -> c172.jl:715-724). `y` is the RhsOut of the
-// evaluation at the post-step state. Returns true when something the RHS reads changed (so that the
-// first-same-as-last derivative must be re-evaluated).
-template <int VAR, int KIN>
-FB_DEV bool f_step(double* x, int& stall, int& eng_state, const MemberIn& u, const RhsOut& y, int& status) {
+// evaluation at the post-step state. X is any indexable state holder (registers or a shared-memory column).
+// Returns true when something the RHS reads changed (so that the first-same-as-last derivative must be
+// re-evaluated).
+template <int VAR, int KIN, class X>
+FB_DEV bool f_step(X& x, int& stall, int& eng_state, const MemberIn& u, const RhsOut& y, int& status) {
     typedef Lay<VAR, KIN> L;
     bool changed = false;
     if (KIN == FB_WA) {   // kinematics.jl:114-118,226-229
 #pragma unroll
         for (int b = 0; b < 2; b++) {
-            double* q = x + L::KINX + 4 * b;
-            double nn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-            if (fabs(nn - 1.0) > 1e-8) { q[0] /= nn; q[1] /= nn; q[2] /= nn; q[3] /= nn; changed = true; }
+            const int o = L::KINX + 4 * b;
+            double q0 = x.get(o), q1 = x.get(o + 1), q2 = x.get(o + 2), q3 = x.get(o + 3);
+            double nn = sqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+            if (fabs(nn - 1.0) > 1e-8) { x.set(o, q0 / nn); x.set(o + 1, q1 / nn); x.set(o + 2, q2 / nn); x.set(o + 3, q3 / nn); changed = true; }
         }
     }
     int st0 = stall;
@@ -776,14 +801,14 @@ FB_DEV bool f_step(double* x, int& stall, int& eng_state, const MemberIn& u, con
         int cr = (y.crash >> (2 * leg)) & 3;                             // landinggear.jl:331-347
         if (cr) { status = (cr == 1) ? FB_ST_CRASH_ANGLE : FB_ST_CRASH_RATE; return changed; }
         if (!(y.wow & (1 << leg))) {                                     // landinggear.jl:479-483
-            changed |= (x[L::LDG + 2 * leg] != 0.0) | (x[L::LDG + 2 * leg + 1] != 0.0);
-            x[L::LDG + 2 * leg] = 0.0; x[L::LDG + 2 * leg + 1] = 0.0;
+            double a = x.get(L::LDG + 2 * leg), b = x.get(L::LDG + 2 * leg + 1);
+            if (a != 0.0 || b != 0.0) { changed = true; x.set(L::LDG + 2 * leg, 0.0); x.set(L::LDG + 2 * leg + 1, 0.0); }
         }
     }
     constexpr double w_stall = 300 * FB_PI / 30, w_idle = 600 * FB_PI / 30;
     int e0 = eng_state;                                                  // piston.jl:428-453
-    double w = x[L::ENG];
-    bool fuel_available = (x[L::FUEL] * (114.4 - 1.0)) > 0.0;
+    double w = x.get(L::ENG);
+    bool fuel_available = (x.get(L::FUEL) * (114.4 - 1.0)) > 0.0;
     bool start = u(FB_U_ENG_START) != 0.0, stop = u(FB_U_ENG_STOP) != 0.0;
     if (eng_state == FB_ENG_OFF) { if (start) eng_state = FB_ENG_STARTING; }
     else if (eng_state == FB_ENG_STARTING) {

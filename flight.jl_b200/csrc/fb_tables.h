@@ -4,20 +4,25 @@
 #pragma once
 #include <stdint.h>
 
-// offsets in doubles inside the shared pack
+// offsets in doubles inside the shared pack. Every explicit-knot axis carries a companion array of reciprocal
+// knot spacings (I_*), filled by the host when it builds the pack, so that cell weights are multiplications.
 enum {
     // ---- aero (lib/FlightApps/src/c172/c172.jl:51-159), gridded, Flat
     TB_GE_X = 0,                    // 13
-    TB_CD_GE = TB_GE_X + 13,        // 13
+    TB_I_GE = TB_GE_X + 13,         // 12
+    TB_CD_GE = TB_I_GE + 12,        // 13
     TB_CL_GE = TB_CD_GE + 13,       // 13
     TB_DF_X = TB_CL_GE + 13,        // 4
-    TB_CD_DF = TB_DF_X + 4,         // 4
+    TB_I_DF = TB_DF_X + 4,          // 3
+    TB_CD_DF = TB_I_DF + 3,         // 4
     TB_CL_DF = TB_CD_DF + 4,        // 4
     TB_CM_DF = TB_CL_DF + 4,        // 4
     TB_CD_A_X = TB_CM_DF + 4,       // 26
-    TB_CD_A_DF = TB_CD_A_X + 26,    // 26*4  [alpha][flap]
+    TB_I_CD_A = TB_CD_A_X + 26,     // 25
+    TB_CD_A_DF = TB_I_CD_A + 25,    // 26*4  [alpha][flap]
     TB_CL_A_X = TB_CD_A_DF + 104,   // 17
-    TB_CL_A = TB_CL_A_X + 17,       // 17*2  [alpha][stall]
+    TB_I_CL_A = TB_CL_A_X + 17,     // 16
+    TB_CL_A = TB_I_CL_A + 16,       // 17*2  [alpha][stall]
     TB_CY_B_DF = TB_CL_A + 34,      // 3*2
     TB_CY_P = TB_CY_B_DF + 6,       // 2*2
     TB_CY_R = TB_CY_P + 4,          // 2*2
@@ -26,19 +31,24 @@ enum {
     TB_D_WOT = TB_CL_R + 4,         // 2*9  scaled, Line
     TB_MU_WOT = TB_D_WOT + 18,      // 2*9  scaled, Line
     TB_N_STD = TB_MU_WOT + 18,      // 13
-    TB_PI_STD = TB_N_STD + 13,      // 13*3 gridded, Flat (mu knots 0, 0.568, 1)
+    TB_I_N_STD = TB_N_STD + 13,     // 12
+    TB_PI_STD = TB_I_N_STD + 12,    // 13*3 gridded, Flat (mu knots 0, 0.568, 1)
     TB_N_WOT = TB_PI_STD + 39,      // 5
-    TB_PI_WOT = TB_N_WOT + 5,       // 5*3  gridded (delta knots 0, 0.441, 1), Flat / Line above in delta
+    TB_I_N_WOT = TB_N_WOT + 5,      // 4
+    TB_PI_WOT = TB_I_N_WOT + 4,     // 5*3  gridded (delta knots 0, 0.441, 1), Flat / Line above in delta
     TB_F_X = TB_PI_WOT + 15,        // 11
-    TB_PI_RATIO = TB_F_X + 11,      // 11
+    TB_I_F = TB_F_X + 11,           // 10
+    TB_PI_RATIO = TB_I_F + 10,      // 11
     TB_SFC_RATIO = TB_PI_RATIO + 11,  // 11
     TB_N_SFC = TB_SFC_RATIO + 11,   // 5
-    TB_PI_SFC = TB_N_SFC + 5,       // 8
-    TB_SFC_POW = TB_PI_SFC + 8,     // 5*8  gridded, Line
+    TB_I_N_SFC = TB_N_SFC + 5,      // 4
+    TB_PI_SFC = TB_I_N_SFC + 4,     // 8
+    TB_I_PI_SFC = TB_PI_SFC + 8,    // 7
+    TB_SFC_POW = TB_I_PI_SFC + 7,   // 5*8  gridded, Line
     // ---- propeller (lib/FlightPhysics/src/propellers.jl:235-291): 21x21 over J, Mt in [0,1.5], scaled, Flat;
-    //      interleaved [iJ][iMt][6] = C_Fx, C_Mx, C_Fz_a, C_Mz_a, C_P, eta_p
+    //      interleaved [iJ][iMt][4] = C_Fx, C_Mx, C_Fz_a, C_Mz_a (C_P and eta_p are not on the path)
     TB_PROP = TB_SFC_POW + 40,
-    TB_COUNT = TB_PROP + 21 * 21 * 6
+    TB_COUNT = TB_PROP + 21 * 21 * 4
 };
 #define FB_TB_BYTES ((TB_COUNT * 8 + 15) / 16 * 16)
 

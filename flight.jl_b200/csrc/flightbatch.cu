@@ -37,15 +37,28 @@ struct fb_sim {
     unsigned long long* d_rhs_count = nullptr;
     long long launches = 0;
     int periodic_every = 1;
+    int step_block = 128;            // threads per CTA of the integrator (one CTA per SM)
     std::vector<double> h_row;
 };
 
 // ------------------------------------------------------------------------------------ kernel dispatch
 template <int VAR, int KIN> struct Ops {
     static cudaError_t step(fb_sim* s, long long step0, int n) {
-        int grid = (int)((s->E.n + FB_BLOCK - 1) / FB_BLOCK);
-        step_kernel<VAR, KIN><<<grid, FB_BLOCK, FB_TB_BYTES, s->stream>>>(s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count);
+        int T = s->step_block;
+        int grid = (int)((s->E.n + T - 1) / T);
+        size_t smem = FB_TB_BYTES + sizeof(double) * 2 * Lay<VAR, KIN>::NX * T;
+        step_kernel<VAR, KIN><<<grid, T, smem, s->stream>>>(s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count);
         return cudaGetLastError();
+    }
+    static cudaError_t prepare(fb_sim* s) {
+        size_t smem = FB_TB_BYTES + sizeof(double) * 2 * Lay<VAR, KIN>::NX * s->step_block;
+        cudaError_t e = cudaFuncSetAttribute(step_kernel<VAR, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(rhs_kernel<VAR, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(output_kernel<VAR, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES);
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(trim_kernel<VAR, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES);
     }
     static cudaError_t rhs(fb_sim* s, double* xdot) {
         int grid = (int)((s->E.n + FB_BLOCK - 1) / FB_BLOCK);
@@ -68,10 +81,14 @@ template <int VAR, int KIN> struct Ops {
         return cudaGetLastError();
     }
 };
+#ifdef FB_ONLY_S_WA   // development build: one instantiation only (fast compile)
+#define FB_DISPATCH(s, CALL) (Ops<FB_C172S, FB_WA>::CALL)
+#else
 #define FB_DISPATCH(s, CALL)                                                            \
     ((s)->var_t == FB_C172S ? ((s)->cfg.kinematics == FB_WA ? Ops<FB_C172S, FB_WA>::CALL : Ops<FB_C172S, FB_NED>::CALL) \
      : (s)->var_t == FB_C172X0 ? ((s)->cfg.kinematics == FB_WA ? Ops<FB_C172X0, FB_WA>::CALL : Ops<FB_C172X0, FB_NED>::CALL) \
                                : ((s)->cfg.kinematics == FB_WA ? Ops<FB_C172X1, FB_WA>::CALL : Ops<FB_C172X1, FB_NED>::CALL))
+#endif
 
 static int layout_nx(int variant, int kin) {
     int nact = (variant == FB_C172S) ? 0 : 7;
@@ -207,13 +224,22 @@ int32_t fb_create(const fb_config* cfg, fb_handle* out) {
         CK(cudaMemcpyAsync(s->d_log_fields, cfg->log_fields, sizeof(int) * cfg->log_n_fields, cudaMemcpyHostToDevice, s->stream));
         E.log_fields = s->d_log_fields;
     }
-    // opt in to the shared-memory size of the table pack
-    CK(cudaFuncSetAttribute(step_kernel<FB_C172S, FB_WA>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES));
-    CK(cudaFuncSetAttribute(step_kernel<FB_C172S, FB_NED>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES));
-    CK(cudaFuncSetAttribute(step_kernel<FB_C172X0, FB_WA>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES));
-    CK(cudaFuncSetAttribute(step_kernel<FB_C172X0, FB_NED>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES));
-    CK(cudaFuncSetAttribute(step_kernel<FB_C172X1, FB_WA>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES));
-    CK(cudaFuncSetAttribute(step_kernel<FB_C172X1, FB_NED>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES));
+    // Integrator launch shape: one CTA per SM holding the table pack plus two NX x T column blocks in shared
+    // memory. T is the largest multiple of 32 that fits 227 KB and the register budget, then shrunk while the
+    // number of waves over the SMs stays the same (balances the last wave).
+    {
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, cfg->device));
+        size_t smem_max = prop.sharedMemPerBlockOptin;
+        int tmax = (int)((smem_max - FB_TB_BYTES - 1024) / (sizeof(double) * 2 * s->nx)) / 32 * 32;
+        tmax = std::min(tmax, FB_STEP_MAX_BLOCK);
+        int sms = prop.multiProcessorCount;
+        int T = (int)std::min<long long>(tmax, (N + 31) / 32 * 32);
+        long long waves = ((N + T - 1) / T + sms - 1) / sms;
+        while (T > 32 && (((N + (T - 32) - 1) / (T - 32) + sms - 1) / sms) == waves) T -= 32;
+        s->step_block = T;
+    }
+    CK(FB_DISPATCH(s, prepare)(s));
     CK(cudaStreamSynchronize(s->stream));
     *out = s;
     return FB_OK;
@@ -267,7 +293,14 @@ int32_t fb_load_tables(fb_handle s, const void* blob, size_t nbytes) {
         const BlobSec* sec = find("prop.tables");
         if (!sec || sec->nbytes != 6ull * 441 * 8) return fail(FB_ERR_ARG, "fb_load_tables: bad or missing section prop.tables");
         const double* p = (const double*)(b + sec->off);
-        for (int c = 0; c < 6; c++) for (int ij = 0; ij < 441; ij++) pack[TB_PROP + ij * 6 + c] = p[c * 441 + ij];
+        for (int c = 0; c < 4; c++) for (int ij = 0; ij < 441; ij++) pack[TB_PROP + ij * 4 + c] = p[c * 441 + ij];
+    }
+    {   // reciprocal knot spacings
+        struct Inv { int knots, inv, n; };
+        const Inv invs[] = {{TB_GE_X, TB_I_GE, 13}, {TB_DF_X, TB_I_DF, 4}, {TB_CD_A_X, TB_I_CD_A, 26}, {TB_CL_A_X, TB_I_CL_A, 17},
+                            {TB_N_STD, TB_I_N_STD, 13}, {TB_N_WOT, TB_I_N_WOT, 5}, {TB_F_X, TB_I_F, 11}, {TB_N_SFC, TB_I_N_SFC, 5},
+                            {TB_PI_SFC, TB_I_PI_SFC, 8}};
+        for (const Inv& v : invs) for (int i = 0; i + 1 < v.n; i++) pack[v.inv + i] = 1.0 / (pack[v.knots + i + 1] - pack[v.knots + i]);
     }
     const BlobSec* g = find("geoid");
     if (!g || g->dtype != 1 || g->nbytes != (uint64_t)FB_GEOID_NLAT * FB_GEOID_NLON * 4) return fail(FB_ERR_ARG, "fb_load_tables: bad or missing geoid section");
