@@ -39,6 +39,29 @@ UNIT = "aircraft-steps/s"
 A_STEP_FLOP = 15695.0
 
 
+_GEOID = None
+
+
+def geoid_height(lat, lon):
+    """EGM96 undulation N(lat, lon) [m], bilinear on the 15' grid of the table blob (workload generation only):
+    the cfg-2 altitudes are heights above mean sea level, TrimParameters wants ellipsoidal altitude h_e = h_msl + N."""
+    global _GEOID
+    if _GEOID is None:
+        import struct
+        blob = open(os.path.join(ROOT, "flight.jl_b200", "data", "c172_tables.bin"), "rb").read()
+        ns = struct.unpack_from("<I", blob, 8)[0]
+        for k in range(ns):
+            nm, dt, nd, d0, d1, d2, d3, off, nb = struct.unpack_from("<24sII4IQQ", blob, 16 + 64 * k)
+            if nm.rstrip(b"\0") == b"geoid":
+                _GEOID = np.frombuffer(blob, dtype="<f4", count=nb // 4, offset=off).reshape(1441, 721).astype(np.float64)
+    fi = (np.asarray(lat) + np.pi / 2) / (np.pi / 720)
+    fj = np.mod(np.asarray(lon) + 2 * np.pi, 2 * np.pi) / (2 * np.pi / 1440)
+    i = np.clip(np.floor(fi).astype(int), 0, 719); j = np.clip(np.floor(fj).astype(int), 0, 1439)
+    u, w = fi - i, fj - j
+    g = _GEOID
+    return (1 - w) * ((1 - u) * g[j, i] + u * g[j, i + 1]) + w * ((1 - u) * g[j + 1, i] + u * g[j + 1, i + 1])
+
+
 def member_params(i0, n):
     """cfg-2 trim parameters for global members i0 .. i0+n-1; counter-based so sharding does not change values."""
     out = {k: np.empty(n) for k in ("EAS", "h_e", "flaps", "psi_nb", "lat", "lon", "fuel_load", "m_pilot", "m_copilot",
@@ -51,8 +74,10 @@ def member_params(i0, n):
         flaps = rng.choice([0.0, 1 / 3, 2 / 3, 1.0], m)
         flaps[EAS < 35] = 1.0
         flaps[EAS > 42] = 0.0     # level trim with flaps out is power-limited above ~45 m/s EAS
-        cols = dict(EAS=EAS, h_e=rng.uniform(50, 3050, m), flaps=flaps, psi_nb=rng.uniform(-np.pi, np.pi, m),
-                    lat=np.deg2rad(rng.uniform(-60, 60, m)), lon=rng.uniform(-np.pi, np.pi, m), fuel_load=rng.uniform(0.1, 1, m),
+        h_msl = rng.uniform(50, 3050, m)
+        lat = np.deg2rad(rng.uniform(-60, 60, m)); lon = rng.uniform(-np.pi, np.pi, m)
+        cols = dict(EAS=EAS, h_e=h_msl + geoid_height(lat, lon), flaps=flaps, psi_nb=rng.uniform(-np.pi, np.pi, m),
+                    lat=lat, lon=lon, fuel_load=rng.uniform(0.1, 1, m),
                     m_pilot=rng.uniform(0, 100, m), m_copilot=rng.uniform(0, 100, m), m_lpass=rng.uniform(0, 100, m),
                     m_rpass=rng.uniform(0, 100, m), m_baggage=rng.uniform(0, 100, m))
         lo, hi = max(b0, i0), min(b0 + blk, i0 + n)

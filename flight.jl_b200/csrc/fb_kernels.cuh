@@ -8,7 +8,9 @@
 #include "fb_avionics.cuh"
 
 #define FB_BLOCK 128          // block size of the light kernels (rhs / output / init / trim)
-#define FB_STEP_MAX_BLOCK 448 // register budget of the integrator: 65536 / 448 = 146 registers per thread
+#ifndef FB_STEP_MAX_BLOCK
+#define FB_STEP_MAX_BLOCK 448 // 14 warps per SM: 4 warps on an SM sub-partition -> 128 registers per thread
+#endif
 
 struct EnsembleDev {
     double* x;            // [NX][pitch]

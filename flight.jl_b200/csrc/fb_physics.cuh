@@ -99,11 +99,15 @@ struct ArrayState {
 };
 
 // ------------------------------------------------------------------------------------ interpolation
-// cell index / weight on explicit knots (Gridded(Linear())); x already clamped to the knot span; ik = 1/spacing
-FB_DEV void locate(const double* k, const double* ik, int n, double x, int& i, double& w) {
-    int lo = 0;
+// cell index / weight on explicit knots (Gridded(Linear())); x already clamped to the knot span; ik = 1/spacing.
+// `g` is a guess of the cell index (from the axis' nominal spacing); the two loops walk it to the right cell,
+// which costs zero or one iteration for the near-uniform axes of this model.
+FB_DEV void locate(const double* k, const double* ik, int n, double x, int g, int& i, double& w) {
+    int lo = min(max(g, 0), n - 2);
 #pragma unroll 1
-    for (int j = 1; j < n - 1; j++) lo = (x >= k[j]) ? j : lo;
+    while (lo > 0 && x < k[lo]) lo--;
+#pragma unroll 1
+    while (lo < n - 2 && x >= k[lo + 1]) lo++;
     i = lo;
     w = (x - k[lo]) * ik[lo];
 }
@@ -180,7 +184,7 @@ FB_DEV double gravity(double n3, double h) {  // Somigliana + 2nd-order altitude
 }
 
 // --------------------------------------------------------------------------------------- atmosphere
-struct Air { d3 v_wb_b; double T, p, rho, a, TAS, q, tr; };  // tr = T_ISA(p) / T_std (piston.jl:38)
+struct Air { d3 v_wb_b; double T, p, rho, ia, iRT, TAS, iTAS, q, tr; };  // tr = T_ISA(p) / T_std (piston.jl:38)
 
 __device__ __noinline__ void isa_upper(double hg, double T_sl, double p_sl, double& T, double& p, int& err) {
     const double beta[7] = {-6.5e-3, 0, 1e-3, 2.8e-3, 0, -2.8e-3, -2e-3};
@@ -210,9 +214,11 @@ FB_DEV void isa_data(double h_o, double T_sl, double p_sl, double& T, double& p,
         p = p_sl * exp(k * log(ratio));
         // (p/p_std)^kT = (p_sl/p_std)^kT * ratio, since k * kT == 1
         tr = (p_sl == isa::p_std) ? ratio : ratio * pow_slow(p_sl * (1.0 / isa::p_std), kT);
-    } else {
-        isa_upper(hg, T_sl, p_sl, T, p, err);
-        tr = pow_slow(p * (1.0 / isa::p_std), kT);
+    } else {   // rare: copies keep the callee's by-reference outputs from pinning the caller's values in local memory
+        double T2, p2; int e2 = 0;
+        isa_upper(hg, T_sl, p_sl, T2, p2, e2);
+        T = T2; p = p2; if (e2) err = e2;
+        tr = pow_slow(p2 * (1.0 / isa::p_std), kT);
     }
 }
 
@@ -361,8 +367,8 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const Mem
         k.q_nb = qmul(q_nw, q_wb);
         k.q_eb = qmul(q_ew, q_wb);
         k.n_e = mk3(-(dq24 + dq13), -(dq34 - dq12), -(1.0 - 2.0 * (q_ew.x * q_ew.x + q_ew.y * q_ew.y)));
-        k.lat = atan2(k.n_e.z, fb_sqrt(fma(k.n_e.x, k.n_e.x, k.n_e.y * k.n_e.y)));
-        k.lon = atan2(k.n_e.y, k.n_e.x);
+        k.lat = fb_atan2(k.n_e.z, fb_sqrt(fma(k.n_e.x, k.n_e.x, k.n_e.y * k.n_e.y)));
+        k.lon = fb_atan2(k.n_e.y, k.n_e.x);
         k.v_eb_n = qrot(k.q_nb, k.v_eb_b);
         double M, N;
         radii(k.n_e.z, M, N);
@@ -432,19 +438,20 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const Mem
     Air air;
     isa_data(k.h_o, u(FB_U_T_SL), u(FB_U_P_SL), air.T, air.p, air.tr, out.err);
     {
-        double iRT = fb_rcp(isa::R * air.T);
-        air.rho = air.p * iRT;
-        air.a = fb_sqrt(isa::gamma * isa::R * air.T);
+        air.iRT = fb_rcp(isa::R * air.T);
+        air.rho = air.p * air.iRT;
+        air.ia = fb_rsqrt(isa::gamma * isa::R * air.T);      // 1 / speed of sound
         d3 wind = mk3(u(FB_U_WIND_N), u(FB_U_WIND_E), u(FB_U_WIND_D));
         air.v_wb_b = k.v_eb_b - qrot_inv(k.q_nb, wind);
         double tas2 = dot(air.v_wb_b, air.v_wb_b);
-        air.TAS = (tas2 > 0.0) ? fb_sqrt(tas2) : 0.0;
+        air.iTAS = (tas2 > 0.0) ? fb_rsqrt(tas2) : 0.0;
+        air.TAS = tas2 * air.iTAS;
         air.q = 0.5 * air.rho * tas2;
     }
     if (WY) {   // atmosphere.jl:220-242
         yf->TAS = air.TAS; yf->q = air.q;
         yf->EAS = air.TAS * sqrt(air.rho / isa::rho_std);
-        yf->M = air.TAS / air.a;
+        yf->M = air.TAS * air.ia;
         double Tt = air.T * (1.0 + (isa::gamma - 1) / 2 * yf->M * yf->M);
         double pt = air.p * pow(Tt / air.T, isa::gamma / (isa::gamma - 1));
         yf->CAS = sqrt(2 * isa::gamma / (isa::gamma - 1) * isa::p_std / isa::rho_std * (pow(1.0 + (pt - air.p) / isa::p_std, (isa::gamma - 1) / isa::gamma) - 1.0));
@@ -484,13 +491,12 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const Mem
         if (air.TAS > 0.1) {   // covers both TAS thresholds (c172.jl:324, atmosphere.jl:337)
             double vxz2 = fma(v.x, v.x, v.z * v.z);
             double ivxz = (vxz2 > 0.0) ? fb_rsqrt(vxz2) : 0.0;
-            alpha = atan2(v.z, v.x);
-            beta = atan2(v.y, vxz2 * ivxz);
+            alpha = fb_atan2(v.z, v.x);
+            beta = fb_atan2(v.y, vxz2 * ivxz);
             if (vxz2 > 0.0) { ca = v.x * ivxz; sa = v.z * ivxz; }
         }
         out.alpha = alpha;
-        double V = fmax(air.TAS, 1.0);
-        double i2V = 0.5 * fb_rcp(V);
+        double i2V = (air.TAS > 1.0) ? 0.5 * air.iTAS : 0.5;   // 1 / (2 max(TAS, V_min)), V_min = 1
         double afd = (1.0 / tau_f) * (alpha - alpha_filt), bfd = (1.0 / tau_f) * (beta - beta_filt);
         sink.put(L::AERO, afd); sink.put(L::AERO + 1, bfd);
         double p_nd = k.w_wb_b.x * b * i2V, q_nd = k.w_wb_b.y * c * i2V, r_nd = k.w_wb_b.z * b * i2V;
@@ -503,21 +509,21 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const Mem
         double a_c = clampd(alpha, -0.1, 0.36), b_c = clampd(beta, -0.2, 0.2);
         // flap axis (knots 0,10,20,30 deg) shared by five tables
         int jf; double wf;
-        { double dfc = clampd(df, tb[TB_DF_X], tb[TB_DF_X + 3]); locate(tb + TB_DF_X, tb + TB_I_DF, 4, dfc, jf, wf); }
+        { double dfc = clampd(df, tb[TB_DF_X], tb[TB_DF_X + 3]); locate(tb + TB_DF_X, tb + TB_I_DF, 4, dfc, (int)(dfc * (18.0 / FB_PI)), jf, wf); }
         double wf2 = clampd(df * (1.0 / (30 * d2r)), 0.0, 1.0);   // 2-knot flap axis (0, 30 deg)
         int ig; double wg;
-        { double g = clampd(dh_nd, 0.0, 1.1); locate(tb + TB_GE_X, tb + TB_I_GE, 13, g, ig, wg); }
+        { double g = clampd(dh_nd, 0.0, 1.1); locate(tb + TB_GE_X, tb + TB_I_GE, 13, g, (g < 0.2) ? (int)(g * 20.0) - 1 : (int)(g * 10.0) + 1, ig, wg); }
         double CD_ge = lerp(tb[TB_CD_GE + ig], tb[TB_CD_GE + ig + 1], wg);
         double CL_ge = lerp(tb[TB_CL_GE + ig], tb[TB_CL_GE + ig + 1], wg);
         double CD_df = lerp(tb[TB_CD_DF + jf], tb[TB_CD_DF + jf + 1], wf);
         double CL_df = lerp(tb[TB_CL_DF + jf], tb[TB_CL_DF + jf + 1], wf);
         double Cm_df = lerp(tb[TB_CM_DF + jf], tb[TB_CM_DF + jf + 1], wf);
         int ia; double wa;
-        { double ac = clampd(a_c, tb[TB_CD_A_X], tb[TB_CD_A_X + 25]); locate(tb + TB_CD_A_X, tb + TB_I_CD_A, 26, ac, ia, wa); }
+        { double ac = clampd(a_c, tb[TB_CD_A_X], tb[TB_CD_A_X + 25]); locate(tb + TB_CD_A_X, tb + TB_I_CD_A, 26, ac, (int)((ac + 0.0873) * (25.0 / 0.4364)), ia, wa); }
         const double* cd = tb + TB_CD_A_DF + ia * 4 + jf;
         double CD_a_df = lerp(lerp(cd[0], cd[1], wf), lerp(cd[4], cd[5], wf), wa);
         int il; double wl;
-        { double ac = clampd(a_c, tb[TB_CL_A_X], tb[TB_CL_A_X + 16]); locate(tb + TB_CL_A_X, tb + TB_I_CL_A, 17, ac, il, wl); }
+        { double ac = clampd(a_c, tb[TB_CL_A_X], tb[TB_CL_A_X + 16]); locate(tb + TB_CL_A_X, tb + TB_I_CL_A, 17, ac, (ac < 0.1) ? (int)((ac + 0.09) * (1.0 / 0.09)) : 3 + (int)((ac - 0.1) * 50.0), il, wl); }
         double CL_a = lerp(tb[TB_CL_A + il * 2 + stall], tb[TB_CL_A + il * 2 + 2 + stall], wl);
         double CD_de = 0.06 * fabs(clampd(de, -1.0, 1.0));       // knots (-1,0,1) -> (0.06,0,0.06)
         double CD_b = 0.17 * fabs(b_c);
@@ -559,13 +565,18 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const Mem
         } else {
             int surface = (int)u(FB_U_TRN_SURFACE);
             bool eng = u(FB_U_STEERING_ENGAGED) != 0.0;
+            // the out-of-line strut code works on copies: taking addresses of k / F / tau / out themselves would pin
+            // them in local memory on the airborne fast path as well
+            Kin kk = k; d3 Fl = mk3(0, 0, 0), taul = mk3(0, 0, 0); RhsOut ol; ol.wow = 0; ol.crash = 0; ol.err = 0; ol.alpha = 0.0;
             double xd[6];
-            ldg_unit(k, geoid, elev, surface, mk3(-0.381, -1.092, 1.902), 39404, 9340, 9340, false, false, 0.0, br_l,
-                     x[L::LDG], x[L::LDG + 1], xd[0], xd[1], F, tau, 0, out, WY ? &yf->xi[0] : nullptr, WY ? &yf->F_dmp[0] : nullptr);
-            ldg_unit(k, geoid, elev, surface, mk3(-0.381, 1.092, 1.902), 39404, 9340, 9340, false, false, 0.0, br_r,
-                     x[L::LDG + 2], x[L::LDG + 3], xd[2], xd[3], F, tau, 1, out, WY ? &yf->xi[1] : nullptr, WY ? &yf->F_dmp[1] : nullptr);
-            ldg_unit(k, geoid, elev, surface, mk3(1.27, 0.0, 1.9), 26269, 3503, 3503, true, eng, steer, 0.0,
-                     x[L::LDG + 4], x[L::LDG + 5], xd[4], xd[5], F, tau, 2, out, WY ? &yf->xi[2] : nullptr, WY ? &yf->F_dmp[2] : nullptr);
+            ldg_unit(kk, geoid, elev, surface, mk3(-0.381, -1.092, 1.902), 39404, 9340, 9340, false, false, 0.0, br_l,
+                     x[L::LDG], x[L::LDG + 1], xd[0], xd[1], Fl, taul, 0, ol, WY ? &yf->xi[0] : nullptr, WY ? &yf->F_dmp[0] : nullptr);
+            ldg_unit(kk, geoid, elev, surface, mk3(-0.381, 1.092, 1.902), 39404, 9340, 9340, false, false, 0.0, br_r,
+                     x[L::LDG + 2], x[L::LDG + 3], xd[2], xd[3], Fl, taul, 1, ol, WY ? &yf->xi[1] : nullptr, WY ? &yf->F_dmp[1] : nullptr);
+            ldg_unit(kk, geoid, elev, surface, mk3(1.27, 0.0, 1.9), 26269, 3503, 3503, true, eng, steer, 0.0,
+                     x[L::LDG + 4], x[L::LDG + 5], xd[4], xd[5], Fl, taul, 2, ol, WY ? &yf->xi[2] : nullptr, WY ? &yf->F_dmp[2] : nullptr);
+            F = F + Fl; tau = tau + taul;
+            out.wow = ol.wow; out.crash = ol.crash; if (ol.err) out.err = ol.err;
 #pragma unroll
             for (int i = 0; i < 6; i++) sink.put(L::LDG + i, xd[i]);
         }
@@ -583,8 +594,8 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const Mem
         double vJ2 = dot(v, v);
         double v_J = (vJ2 > 0.0) ? fb_sqrt(vJ2) : 0.0;
         double aw = fabs(w);
-        double J = (2 * FB_PI / d) * v_J * fb_rcp(fmax(aw, 1.0));
-        double Mt = aw * (d / 2) * fb_rcp(air.a);
+        double J = (2 * FB_PI / d) * v_J * fb_rcp(fb_max(aw, 1.0));
+        double Mt = aw * (d / 2) * air.ia;
         int ij, im; double wj, wm;
         locate_uniform(0.0, 20 / 1.5, 21, J, ij, wj);
         locate_uniform(0.0, 20 / 1.5, 21, Mt, im, wm);
@@ -597,7 +608,7 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const Mem
         if (v_J >= 0.1) {
             double vxz2 = fma(v.x, v.x, v.z * v.z);
             double vxz = (vxz2 > 0.0) ? fb_sqrt(vxz2) : 0.0;
-            al_p = atan2(v.z, v.x); be_p = atan2(v.y, vxz);
+            al_p = fb_atan2(v.z, v.x); be_p = fb_atan2(v.y, vxz);
         }
         double f = w * (1.0 / (2 * FB_PI)), f2 = f * f;
         constexpr double d4 = d * d * d * d, d5 = d4 * d;
@@ -646,7 +657,7 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const Mem
             double pi_std, pi_wot;
             {
                 double nc = clampd(n, tb[TB_N_STD], tb[TB_N_STD + 12]);
-                int i; double wn; locate(tb + TB_N_STD, tb + TB_I_N_STD, 13, nc, i, wn);
+                int i; double wn; locate(tb + TB_N_STD, tb + TB_I_N_STD, 13, nc, (nc < 0.667) ? 0 : 1 + (int)((nc - 0.667) * (1.0 / 0.037)), i, wn);
                 double mc = clampd(mu, 0.0, 1.0);
                 int j = (mc >= 0.568) ? 1 : 0;
                 double wmu = (j == 0) ? mc * (1.0 / 0.568) : (mc - 0.568) * (1.0 / (1.0 - 0.568));
@@ -655,7 +666,7 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const Mem
             }
             {   // pi_wot(n, d_wot): gridded 5 x 3 (delta knots 0, 0.441, 1), Flat in n and below, Line above in delta
                 double nc = clampd(n, tb[TB_N_WOT], tb[TB_N_WOT + 4]);
-                int i; double wn; locate(tb + TB_N_WOT, tb + TB_I_N_WOT, 5, nc, i, wn);
+                int i; double wn; locate(tb + TB_N_WOT, tb + TB_I_N_WOT, 5, nc, (nc < 0.667) ? 0 : ((nc < 1.0) ? 1 : 2), i, wn);
                 double dc = clampd(d_wot, 0.0, 1.0);
                 int j = (dc >= 0.441) ? 1 : 0;
                 double wd = (j == 0) ? dc * (1.0 / 0.441) : (dc - 0.441) * (1.0 / (1.0 - 0.441));
@@ -667,10 +678,10 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const Mem
                 }
             }
             double pi_ISA = (fabs(d_wot - 1.0) < 5e-3) ? pi_std : fma(fb_div(pi_wot - pi_std, d_wot - 1.0), delta - 1.0, pi_std);
-            pi_ISA = fmax(pi_ISA, 0.0);
-            double pi_pow = pi_ISA * fb_sqrt(air.tr * isa::T_std * fb_rcp(air.T));
+            pi_ISA = fb_max(pi_ISA, 0.0);
+            double pi_pow = pi_ISA * fb_sqrt(air.tr * (isa::T_std * isa::R) * air.iRT);
             int jf; double wff;
-            { double fc = clampd(far, tb[TB_F_X], tb[TB_F_X + 10]); locate(tb + TB_F_X, tb + TB_I_F, 11, fc, jf, wff); }
+            { double fc = clampd(far, tb[TB_F_X], tb[TB_F_X + 10]); locate(tb + TB_F_X, tb + TB_I_F, 11, fc, (fc < 0.0625) ? 0 : 1 + (int)((fc - 0.0625) * (9.0 / 0.0325)), jf, wff); }
             double pi_actual = pi_pow * lerp(tb[TB_PI_RATIO + jf], tb[TB_PI_RATIO + jf + 1], wff);
             double P_shaft = P_rated * pi_actual;
             tau_shaft = (w > 0.0) ? fb_div(P_shaft, w) : 0.0;
@@ -681,8 +692,8 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const Mem
                 double nc = clampd(n, tb[TB_N_SFC], tb[TB_N_SFC + 4]);
                 double pc = clampd(pi_actual, tb[TB_PI_SFC], tb[TB_PI_SFC + 7]);
                 int i, j; double wn, wp;
-                locate(tb + TB_N_SFC, tb + TB_I_N_SFC, 5, nc, i, wn);
-                locate(tb + TB_PI_SFC, tb + TB_I_PI_SFC, 8, pc, j, wp);
+                locate(tb + TB_N_SFC, tb + TB_I_N_SFC, 5, nc, (int)((nc - 2000.0 / 2700.0) * 13.5), i, wn);
+                locate(tb + TB_PI_SFC, tb + TB_I_PI_SFC, 8, pc, (pc < 0.2683) ? ((pc < 0.1389) ? 0 : ((pc < 0.1931) ? 1 : 2)) : ((pc < 0.5179) ? ((pc < 0.3728) ? 3 : 4) : ((pc < 0.7197) ? 5 : 6)), j, wp);
                 const double* t = tb + TB_SFC_POW + i * 8 + j;
                 double f00 = t[0], f01 = t[1], f10 = t[8], f11 = t[9];
                 sfc = lerp(lerp(f00, f01, wp), lerp(f10, f11, wp), wn);
@@ -703,7 +714,7 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const Mem
     constexpr double m_full = 114.4, m_res = 1.0;
     const double x_fuel = x[L::FUEL];
     sink.put(L::FUEL, -mdot * (1.0 / (m_full - m_res)));
-    double m_fuel = fmax(0.0, fma(x_fuel, m_full - m_res, m_res));
+    double m_fuel = fb_max(0.0, fma(x_fuel, m_full - m_res, m_res));
 
     // ------------------------------------------------------------------ mass properties (affine in the masses)
     // airframe at Ob: m 767, J_G diag(820,1164,1702), r (0.056,0,0.582): J_O = J_G + m (|r|^2 I - r r^T)

@@ -11,12 +11,15 @@ SEED = 20261018
 
 
 def cfg2_params(n, rng):
+    import bench
     EAS = rng.uniform(30, 55, n)
+    lat = np.deg2rad(rng.uniform(-60, 60, n)); lon = rng.uniform(-np.pi, np.pi, n)
+    h_e = rng.uniform(50, 3050, n) + bench.geoid_height(lat, lon)   # 50..3050 m above mean sea level
     flaps = rng.choice([0.0, 1 / 3, 2 / 3, 1.0], n)
     flaps[EAS < 35] = 1.0
     flaps[EAS > 42] = 0.0   # full flap at high speed cannot be trimmed level with the available power
-    return dict(EAS=EAS, h_e=rng.uniform(50, 3050, n), flaps=flaps, psi_nb=rng.uniform(-np.pi, np.pi, n),
-                lat=np.deg2rad(rng.uniform(-60, 60, n)), lon=rng.uniform(-np.pi, np.pi, n), fuel_load=rng.uniform(0.1, 1, n),
+    return dict(EAS=EAS, h_e=h_e, flaps=flaps, psi_nb=rng.uniform(-np.pi, np.pi, n),
+                lat=lat, lon=lon, fuel_load=rng.uniform(0.1, 1, n),
                 m_pilot=rng.uniform(0, 100, n), m_copilot=rng.uniform(0, 100, n), m_lpass=rng.uniform(0, 100, n),
                 m_rpass=rng.uniform(0, 100, n), m_baggage=rng.uniform(0, 100, n))
 
