@@ -52,6 +52,13 @@ def _load(name):
         "orc_ops_get": (None, [C.POINTER(C.c_ulonglong)]),
         "orc_is_counting": (i32, []),
         "orc_batch_step": (i32, [C.POINTER(vp), i64, i64, i32]),
+        "orc_kin_sim": (i32, [vp, i32, dp, dbl, i64, dp]),
+        "orc_dyn_test": (i32, [vp, dp, dbl, dp, dp, dp, dp, dp]),
+        "orc_ldg_test": (i32, [vp, dp, dbl, dbl, i32, dbl, dbl, dbl, i32, dp]),
+        "orc_get_mu": (dbl, [i32, i32, dbl]),
+        "orc_engine_lookup": (dbl, [dbl, dbl, i32, dbl, dbl, dbl]),
+        "orc_h2delta": (dbl, [dbl]),
+        "orc_geo_roundtrip": (None, [dbl, dbl, dbl, dp]),
     }
     for k, (res, args) in sig.items():
         f = getattr(lib, k)
@@ -197,6 +204,47 @@ class Sim:
 
     def want_y_extra(self, on=True):
         self.lib.orc_sim_want_y_extra(self.h, 1 if on else 0)
+
+
+KIN_KEYS = ["q_nb", "n_e", "h_e", "v_eb_b", "w_eb_b", "v_eb_n", "q_en", "r_eb_e", "h_o"]
+
+
+def _kin_dict(a):
+    return dict(q_nb=a[0:4], n_e=a[4:7], h_e=a[7], v_eb_b=a[8:11], w_eb_b=a[11:14], v_eb_n=a[14:17], q_en=a[17:21], r_eb_e=a[21:24], h_o=a[24])
+
+
+def _ic(q_nb=(1, 0, 0, 0), lat=0.0, lon=0.0, h_orth=0.0, w_wb_b=(0, 0, 0), v_eb_n=(0, 0, 0)):
+    return np.array(list(q_nb) + [lat, lon, h_orth] + list(w_wb_b) + list(v_eb_n), dtype=np.float64)
+
+
+def kin_sim(kin, dt, nsteps, **ic):
+    """Kinematics model alone (reference test_kinematics.jl): returns the KinData fields after nsteps."""
+    w = world()
+    out = np.zeros(25)
+    rc = w.lib.orc_kin_sim(w.h, int(kin), _dp(_ic(**ic)), float(dt), int(nsteps), _dp(out))
+    assert rc == 0
+    return _kin_dict(out)
+
+
+def dyn_test(mass, Jdiag, r_bc, F, tau, **ic):
+    w = world()
+    out = np.zeros(38)
+    a = [np.ascontiguousarray(v, dtype=np.float64) for v in (Jdiag, r_bc, F, tau)]
+    rc = w.lib.orc_dyn_test(w.h, _dp(_ic(**ic)), float(mass), _dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(a[3]), _dp(out))
+    assert rc == 0
+    d = dict(wdot=out[0:3], vdot=out[3:6], a_eb_b=out[6:9], a_ib_b=out[9:12], gravity=out[12])
+    d.update(_kin_dict(out[13:]))
+    return d
+
+
+def ldg_test(steer_input=0.0, brake=0.0, engaged=True, psi_max=np.pi / 6, frc_x=(0.0, 0.0), surface=0, **ic):
+    w = world()
+    out = np.zeros(22)
+    rc = w.lib.orc_ldg_test(w.h, _dp(_ic(**ic)), float(steer_input), float(brake), int(engaged), float(psi_max),
+                            float(frc_x[0]), float(frc_x[1]), int(surface), _dp(out))
+    assert rc == 0, rc
+    return dict(wow=bool(out[0]), xi=out[1], xi_dot=out[2], F_dmp=out[3], v_xy=out[4:6], mu_roll=out[6], mu_skid=out[7], mu_max=out[8:10],
+                mu_eff=out[10:12], f_c=out[12:15], F_b=out[15:18], xdot=out[18:20], sat_out=out[20:22])
 
 
 def batch_step(sims, n_steps, threads):

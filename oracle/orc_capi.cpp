@@ -251,6 +251,138 @@ int orc_sim_step(void* s, long long n) {
 }
 long long orc_sim_steps_taken(void* s) { return ((Sim*)s)->n_steps; }
 
+// ---------------------------------------------------------------------------------------------------------
+// Component-level hooks used by tests/ to replay the reference's own unit tests against the oracle.
+static KinInit kin_init_from(const World* W, const double* ic) {   // ic: q_nb[4], lat, lon, h_orth, w_wb_b[3], v_eb_n[3]
+    KinInit ki;
+    ki.q_nb = qnormalize(Q4(ic[0], ic[1], ic[2], ic[3]));
+    LatLon ll; ll.lat = ic[4]; ll.lon = ic[5];
+    ki.n_e = n_from_latlon(ll);
+    ki.h_e = ic[6] + W->geoid->height(ki.n_e);    // KinInit(h = HOrth(..)) -> HEllip(h, n_e) (kinematics.jl:36-38)
+    ki.w_wb_b = V3(ic[7], ic[8], ic[9]); ki.v_eb_n = V3(ic[10], ic[11], ic[12]);
+    return ki;
+}
+static void put_kin(const KinData& k, double* out) {   // q_nb4, n_e3, h_e, v_eb_b3, w_eb_b3, v_eb_n3, q_en4, r_eb_e3, h_o  (25)
+    const real v[] = {k.q_nb.w, k.q_nb.x, k.q_nb.y, k.q_nb.z, k.n_e.x, k.n_e.y, k.n_e.z, k.h_e, k.v_eb_b.x, k.v_eb_b.y, k.v_eb_b.z,
+                      k.w_eb_b.x, k.w_eb_b.y, k.w_eb_b.z, k.v_eb_n.x, k.v_eb_n.y, k.v_eb_n.z, k.q_en.w, k.q_en.x, k.q_en.y, k.q_en.z,
+                      k.r_eb_e.x, k.r_eb_e.y, k.r_eb_e.z, k.h_o};
+    for (int i = 0; i < 25; i++) out[i] = val(v[i]);
+}
+// kinematics model alone, constant (w_eb_b, v_eb_b) input, fixed-step RK4 + f_step! renormalisation
+// (lib/FlightPhysics/test/test_kinematics.jl:37-41,75-93)
+int orc_kin_sim(void* w, int kin, const double* ic, double dt, long long nsteps, double* out25) {
+    World* W = (World*)w;
+    Member m; m.L = Layout(VAR_C172S, kin);
+    KinInit ki = kin_init_from(W, ic);
+    kin_init(m, ki);
+    const Layout& L = m.L;
+    try {
+        for (long long s = 0; s < nsteps; s++) {
+            real x0[12], k1[12], k2[12], k3[12], k4[12];
+            int n = L.nkin;
+            auto f = [&](real* kd) { m.kin_ode(*W); for (int i = 0; i < n; i++) kd[i] = m.xdot[L.kinx + i]; };
+            for (int i = 0; i < n; i++) x0[i] = m.x[L.kinx + i];
+            f(k1); for (int i = 0; i < n; i++) m.x[L.kinx + i] = x0[i] + dt / 2 * k1[i];
+            f(k2); for (int i = 0; i < n; i++) m.x[L.kinx + i] = x0[i] + dt / 2 * k2[i];
+            f(k3); for (int i = 0; i < n; i++) m.x[L.kinx + i] = x0[i] + dt * k3[i];
+            f(k4); for (int i = 0; i < n; i++) m.x[L.kinx + i] = x0[i] + (dt / 6) * (2.0 * (k2[i] + k3[i]) + (k1[i] + k4[i]));
+            if (kin != KIN_NED) {
+                int blocks[2][2] = {{L.kinx, 4}, {L.kinx + 4, kin == KIN_WA ? 4 : 3}};
+                for (auto& b : blocks) {
+                    real n2 = 0.0; for (int i = 0; i < b[1]; i++) n2 = n2 + m.x[b[0] + i] * m.x[b[0] + i];
+                    real nn = sqrt(n2);
+                    if (rabs(nn - 1.0) > 1e-8) for (int i = 0; i < b[1]; i++) m.x[b[0] + i] = m.x[b[0] + i] / nn;
+                }
+            }
+        }
+        m.kin_ode(*W);
+    } catch (OrcTermination& e) { return e.code; }
+    put_kin(m.y.kin, out25);
+    return 0;
+}
+// VehicleDynamics.f_ode! with a rigid body (mass m, inertia diag(J) at its CoM, CoM at r_bc_b) and a body wrench
+// (lib/FlightPhysics/test/test_dynamics.jl:21-66). out: wdot3, vdot3, a_eb_b3, a_ib_b3, gravity, kin(25)
+int orc_dyn_test(void* w, const double* ic, double mass, const double* Jd, const double* r_bc, const double* F, const double* tau, double* out) {
+    World* W = (World*)w;
+    Member m; m.L = Layout(VAR_C172S, KIN_WA); m.want_y_extra = true;
+    KinInit ki = kin_init_from(W, ic);
+    kin_init(m, ki);
+    try {
+        m.kin_ode(*W);
+        MassProps c; c.m = mass; c.J.m[0][0] = Jd[0]; c.J.m[1][1] = Jd[1]; c.J.m[2][2] = Jd[2];
+        MassProps b = mp_translate(V3(r_bc[0], r_bc[1], r_bc[2]), c);   // t_bc(mp_c), dynamics.jl:254-272
+        Wrench wr; wr.F = V3(F[0], F[1], F[2]); wr.tau = V3(tau[0], tau[1], tau[2]);
+        for (int i = 0; i < 6; i++) m.x[m.L.dyn + i] = 0.0;   // the reference test leaves dyn.x at zero (test_dynamics.jl:21)
+        m.dyn_ode(b, wr, V3());
+    } catch (OrcTermination& e) { return e.code; }
+    const Layout& L = m.L;
+    for (int i = 0; i < 6; i++) out[i] = val(m.xdot[L.dyn + i]);
+    const DynY& d = m.y.dyn;
+    out[6] = val(d.a_eb_b.x); out[7] = val(d.a_eb_b.y); out[8] = val(d.a_eb_b.z);
+    out[9] = val(d.a_ib_b.x); out[10] = val(d.a_ib_b.y); out[11] = val(d.a_ib_b.z);
+    out[12] = val(gravity(m.y.kin.n_e, m.y.kin.h_e));
+    put_kin(m.y.kin, out + 13);
+    return 0;
+}
+// LandingGearUnit{DirectSteering, DirectBraking, Strut(l_0 = 1, SimpleDamper(25000, 1000, 1000))}.f_ode! at the body
+// origin on HorizontalTerrain (lib/FlightPhysics/test/test_landing_gear.jl:104-209).
+// out: wow, xi, xi_dot, F_dmp, v_xy[2], mu_roll, mu_skid, mu_max[2], mu_eff[2], f_c[3], wr_b.F[3], xdot[2], sat_out[2]  (22)
+int orc_ldg_test(void* w, const double* ic, double steer_input, double brake, int engaged, double psi_max,
+                 double frc_x0, double frc_x1, int surface, double* out) {
+    World* W = (World*)w;
+    Member m; m.L = Layout(VAR_C172S, KIN_WA);
+    KinInit ki = kin_init_from(W, ic);
+    kin_init(m, ki);
+    m.u.steering_engaged = engaged != 0; m.u.surface = surface;
+    m.x[m.L.ldg] = frc_x0; m.x[m.L.ldg + 1] = frc_x1;
+    try {
+        m.kin_ode(*W);
+        m.ldg_unit(*W, 0, V3(0.0, 0.0, 0.0), 25000, 1000, 1000, true, clampd(steer_input, -1, 1), clampd(brake, 0, 1), 1.0, psi_max);
+    } catch (OrcTermination& e) { return e.code; }
+    const StrutY& s = m.y.strut[0]; const ContactY& c = m.y.contact[0];
+    const real v[] = {s.wow ? 1.0 : 0.0, s.xi, s.xi_dot, s.F_dmp, s.v_xy[0], s.v_xy[1], c.mu_roll, c.mu_skid, c.mu_max[0], c.mu_max[1],
+                      c.mu_eff[0], c.mu_eff[1], c.f_c.x, c.f_c.y, c.f_c.z, c.wr_b.F.x, c.wr_b.F.y, c.wr_b.F.z,
+                      m.xdot[m.L.ldg], m.xdot[m.L.ldg + 1], (double)c.frc.sat_out[0], (double)c.frc.sat_out[1]};
+    for (int i = 0; i < 22; i++) out[i] = val(v[i]);
+    return 0;
+}
+double orc_get_mu(int skidding, int surface, double v) {   // landinggear.jl:170-193
+    if (!skidding) return val(get_mu(0.03, 0.02, 0.005, 0.01, v));
+    if (surface == SURF_DRY) return val(get_mu(0.75, 0.25, 0.005, 0.01, v));
+    if (surface == SURF_WET) return val(get_mu(0.25, 0.15, 0.005, 0.01, v));
+    return val(get_mu(0.075, 0.025, 0.005, 0.01, v));
+}
+// PistonEngineLookup(n_stall, n_max) queries (lib/FlightPhysics/test/test_piston.jl:57-126).
+// which: 0 d_wot(n, mu), 1 pi_std(n, mu), 2 pi_wot(n, delta), 3 mu_wot(n, delta), 4 pi_ISA_pow(n, mu=a, delta=b)
+double orc_engine_lookup(double n_stall, double n_max, int which, double n, double a, double b) {
+    EngineTables E(n_stall, n_max);
+    switch (which) {
+        case 0: return val(E.d_wot(n, a));
+        case 1: return val(E.pi_std(n, a));
+        case 2: return val(E.pi_wot(n, a));
+        case 3: return val(E.mu_wot(n, a));
+        default: {
+            real d_wot = E.d_wot(n, a), pi_std = E.pi_std(n, a), pi_wot = E.pi_wot(n, d_wot), r;
+            if (rabs(d_wot - 1.0) < 5e-3) r = pi_std; else r = pi_std + (pi_wot - pi_std) / (d_wot - 1.0) * (b - 1.0);
+            return val(rmax(r, 0.0));
+        }
+    }
+}
+// h2delta(h) = p/p_std / sqrt(T/T_std) of the standard atmosphere (piston.jl:41-44)
+double orc_h2delta(double h_geop) {
+    real T, p; isa_data(h_geop, isa::T_std, isa::p_std, T, p);
+    return val(p / isa::p_std / sqrt(T / isa::T_std));
+}
+// geodesy round trip (lib/FlightPhysics/test/test_geodesy.jl:181-192): (lat, lon, h_e) -> ECEF -> (n, h_e)
+void orc_geo_roundtrip(double lat, double lon, double h_e, double* out7) {
+    LatLon ll; ll.lat = lat; ll.lon = lon;
+    V3 n = n_from_latlon(ll);
+    V3 r = cartesian_from_geo(n, h_e);
+    V3 n2; real h2;
+    geo_from_cartesian(r, n2, h2);
+    out7[0] = val(r.x); out7[1] = val(r.y); out7[2] = val(r.z); out7[3] = val(n2.x); out7[4] = val(n2.y); out7[5] = val(n2.z); out7[6] = val(h2);
+}
+
 // op counters (only meaningful in the ORC_COUNT build)
 void orc_ops_reset() {
 #if ORC_COUNT

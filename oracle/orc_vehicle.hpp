@@ -298,10 +298,9 @@ struct Member {
 
     // ------------------------------------------------------------------ landing gear unit, landinggear.jl:228-328, 411-476
     void ldg_unit(const World& W, int leg, V3 r_bs_b, double k_s, double k_d_ext, double k_d_cmp,
-                  bool has_steering, real steer_input, real brake_input) {
+                  bool has_steering, real steer_input, real brake_input, double l_0 = 0.0, double psi_max = ORC_PI / 6) {
         const KinData& kin = y.kin;
         StrutY st; ContactY ct;
-        const double l_0 = 0.0;
         Q4 q_bs;  // identity
         Q4 q_es = qmul(kin.q_eb, q_bs);
         V3 e3(0.0, 0.0, 1.0), e1(1.0, 0.0, 0.0);
@@ -334,7 +333,7 @@ struct Member {
             V3 v_s = qrot_inv(q_bs, v_b);
             real psi_v = atan2(v_s.y, v_s.x);
             real psi_sw = 0.0;
-            if (has_steering) psi_sw = u.steering_engaged ? steer_input * (ORC_PI / 6) : psi_v;  // landinggear.jl:68-72
+            if (has_steering) psi_sw = u.steering_engaged ? steer_input * psi_max : psi_v;  // landinggear.jl:68-72
             st.psi_sw = psi_sw;
             Q4 q_sw = Rz(psi_sw);
             Q4 q_ns = qmul(kin.q_nb, q_bs);

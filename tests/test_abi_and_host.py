@@ -1,0 +1,149 @@
+"""CPU tests of the boundary and the host logic: the C-ABI library loads and exports every symbol the header declares,
+computing calls fail loudly without a GPU (there is no CPU fallback), workload generation is sharding-invariant, and the
+N > 1 path (member sharding + statistics all-reduce) works on a world_size-2 gloo group."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "flightbatch.h")).read()
+    return sorted(set(re.findall(r"\b(fb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(fb):
+    lib = fb.load_library()
+    declared = _declared_symbols()
+    assert len(declared) >= 28
+    for name in declared:
+        assert hasattr(lib, name), f"libflightbatch.so does not export {name}"
+    assert sorted(fb.EXPORTS) == declared
+    assert lib.fb_api_version() == fb.DEFS["FB_API_VERSION"]
+
+
+def test_header_enums_are_consistent(fb):
+    assert fb.U["FB_U_AILERON"] == 0 and fb.U["FB_U_THROTTLE"] == 9 and fb.U["FB_U_ACT_THROTTLE"] == 27
+    assert len(set(fb.U.values())) == len(fb.U) and len(set(fb.Y.values())) == len(fb.Y)
+    assert max(v for k, v in fb.U.items() if not k.endswith("_COUNT")) < fb.U["FB_U__COUNT"]
+
+
+def test_no_gpu_means_loud_failure_not_a_fallback(fb):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(fb.FlightBatchError, match="no CUDA device"):
+        fb.BatchSimulation(n=4)
+    with pytest.raises(fb.FlightBatchError):
+        fb.measure_fp64_peak(0)
+
+
+def test_api_misuse_is_reported(fb):
+    lib = fb.load_library()
+    cfg = fb.fb_config()
+    cfg.variant = 99
+    h = C.c_void_p()
+    assert lib.fb_create(C.byref(cfg), C.byref(h)) == fb.DEFS["FB_ERR_ARG"]
+    assert b"variant" in lib.fb_last_error()
+    assert lib.fb_step(None, 1.0) == fb.DEFS["FB_ERR_ARG"]
+
+
+def test_table_blob_has_every_section():
+    import struct
+    blob = open(os.path.join(ROOT, "flight.jl_b200", "data", "c172_tables.bin"), "rb").read()
+    assert blob[:8] == b"FBTABLE1"
+    n = struct.unpack_from("<I", blob, 8)[0]
+    names = {struct.unpack_from("<24s", blob, 16 + 64 * i)[0].rstrip(b"\0").decode() for i in range(n)}
+    for need in ("aero.CD_a_df", "aero.CL_a", "eng.pi_std", "eng.sfc_pow", "prop.tables", "geoid", "gain.te2te", "gain.phibeta2ar", "gain.q2e", "gain.chi2phi"):
+        assert need in names
+
+
+def test_workload_is_sharding_invariant():
+    import bench
+    a = bench.member_params(0, 12288)
+    b = bench.member_params(4096, 8192)
+    c = bench.member_params(5000, 100)
+    for k in a:
+        assert np.array_equal(a[k][4096:], b[k])
+        assert np.array_equal(a[k][5000:5100], c[k])
+    assert a["EAS"].min() >= 30 and a["EAS"].max() <= 55
+    assert (a["flaps"][a["EAS"] < 35] == 1.0).all() and (a["flaps"][a["EAS"] > 42] == 0.0).all()
+
+
+def test_geoid_height_of_the_workload_generator_matches_the_oracle(orc, fb):
+    import bench
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        lat, lon = np.deg2rad(rng.uniform(-60, 60)), rng.uniform(-np.pi, np.pi)
+        o = orc.Sim(0, 0, 0.01)
+        o.init_trim(lat=lat, lon=lon, h_e=1000.0)
+        n_oracle = o.y(fb.Y["FB_Y_H_E"]) - o.y(fb.Y["FB_Y_H_O"])
+        assert abs(bench.geoid_height(lat, lon) - n_oracle) < 1e-9
+
+
+def test_doublet_schedule_shape():
+    import bench
+    n = 16
+    m, s, f, v = bench.doublet_events(n, np.zeros(n), np.ones(n), 1, 0)
+    assert len(m) == 6 * n and set(s) == {500, 700, 900, 2000, 2200, 2400}
+    assert np.allclose(sorted(set(v[f == 1])), [-0.1, 0.0, 0.1]) and np.allclose(sorted(set(v[f == 0])), [0.9, 1.0, 1.1])
+
+
+def test_shard_range_partitions_exactly():
+    import importlib
+    import flightbatch  # noqa: F401
+    dist = importlib.import_module("flightbatch.dist")
+    for n in (1, 7, 65536, 1_000_003):
+        for w in (1, 2, 4, 8):
+            pieces = [dist.shard_range(n, r, w) for r in range(w)]
+            assert pieces[0][0] == 0 and pieces[-1][1] == n
+            assert all(pieces[i][1] == pieces[i + 1][0] for i in range(w - 1))
+            assert max(hi - lo for lo, hi in pieces) - min(hi - lo for lo, hi in pieces) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import flightbatch  # noqa: F401
+    from flightbatch import dist as fbd
+    import bench
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    n_total = 10000
+    lo, hi = fbd.shard_range(n_total, rank, world)
+    p = bench.member_params(lo, hi - lo)                  # each rank generates only its shard
+    status = np.zeros(hi - lo, dtype=np.int32)
+    status[::97] = 6                                      # a few failed members are excluded, as fb_stats does
+    g = fbd.allreduce_moments(fbd.host_moments(p["EAS"], status), device="cpu")
+    q.put((rank, g))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_statistics_allreduce():
+    import torch.multiprocessing as mp
+    import bench
+    from flightbatch import dist as fbd
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full = bench.member_params(0, 10000)["EAS"]
+    keep = np.ones(10000, dtype=bool)
+    for r in range(2):
+        lo, hi = fbd.shard_range(10000, r, 2)
+        keep[lo:hi][::97] = False
+    ref = fbd.host_moments(full[keep])
+    for r in range(2):
+        g = res[r]
+        assert g["count"] == ref["count"] and g["min"] == ref["min"] and g["max"] == ref["max"]
+        assert abs(g["sum"] - ref["sum"]) < 1e-9 * abs(ref["sum"]) and abs(g["mean"] - full[keep].mean()) < 1e-12 * 50
