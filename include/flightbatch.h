@@ -109,6 +109,7 @@ enum fb_output {
     FB_Y_F_X, FB_Y_F_Y, FB_Y_F_Z,                  /* dynamics.f_c_c (specific force)       */
     FB_Y_LON_MODE, FB_Y_LAT_MODE,                  /* avionics.ctl.lon.mode / lat.mode      */
     FB_Y_THROTTLE_CMD, FB_Y_ELEVATOR_CMD, FB_Y_AILERON_CMD, FB_Y_RUDDER_CMD,
+    FB_Y_ALT_STATE,                                /* avionics.ctl.lon.s.h_state: 0 acquire, 1 hold (c172x_ctl.jl:44-47) */
     FB_Y__COUNT
 };
 

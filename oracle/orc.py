@@ -58,6 +58,7 @@ def _load(name):
         "orc_get_mu": (dbl, [i32, i32, dbl]),
         "orc_engine_lookup": (dbl, [dbl, dbl, i32, dbl, dbl, dbl]),
         "orc_h2delta": (dbl, [dbl]),
+        "orc_gain_lookup": (i32, [i32, dbl, dbl, dp]),
         "orc_geo_roundtrip": (None, [dbl, dbl, dbl, dp]),
     }
     for k, (res, args) in sig.items():
@@ -245,6 +246,12 @@ def ldg_test(steer_input=0.0, brake=0.0, engaged=True, psi_max=np.pi / 6, frc_x=
     assert rc == 0, rc
     return dict(wow=bool(out[0]), xi=out[1], xi_dot=out[2], F_dmp=out[3], v_xy=out[4:6], mu_roll=out[6], mu_skid=out[7], mu_max=out[8:10],
                 mu_eff=out[10:12], f_c=out[12:15], F_b=out[15:18], xdot=out[18:20], sat_out=out[20:22])
+
+
+def gain_lookup(which, EAS, h):
+    out = np.zeros(64)
+    n = lib().orc_gain_lookup(int(which), float(EAS), float(h), _dp(out))
+    return out[:n]
 
 
 def batch_step(sims, n_steps, threads):

@@ -16,6 +16,7 @@ thread_local OpCounts g_ops;
 
 static std::vector<float> g_geoid_data;
 static Geoid g_geoid;
+GainTables g_gains;
 
 static real clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
@@ -110,6 +111,20 @@ int orc_load_geoid(const char* path) {
     char magic[8]; uint32_t n = 0, pad = 0;
     if (fread(magic, 1, 8, fp) != 8 || memcmp(magic, "FBTABLE1", 8) != 0) { fclose(fp); return -2; }
     if (fread(&n, 4, 1, fp) != 1 || fread(&pad, 4, 1, fp) != 1) { fclose(fp); return -2; }
+    static const char* gnames[GainTables::COUNT] = {"gain.te2te", "gain.tv2te", "gain.vh2te", "gain.ar2ar", "gain.phibeta2ar",
+                                                    "gain.q2e", "gain.c2theta", "gain.v2t", "gain.p2phi", "gain.chi2phi"};
+    for (uint32_t i = 0; i < n; i++) {   // gain schedules first (data of control/data/*.h5, packed [7 EAS][4 h][P])
+        struct { char name[24]; uint32_t dtype, ndim, dims[4]; uint64_t off, nbytes; } rec;
+        fseek(fp, 16 + 64L * i, SEEK_SET);
+        if (fread(&rec, 64, 1, fp) != 1) break;
+        for (int k = 0; k < GainTables::COUNT; k++) if (strncmp(rec.name, gnames[k], 24) == 0) {
+            g_gains.t[k].resize(rec.nbytes / 8);
+            g_gains.P[k] = (int)rec.dims[2];
+            fseek(fp, (long)rec.off, SEEK_SET);
+            if (fread(g_gains.t[k].data(), 8, g_gains.t[k].size(), fp) != g_gains.t[k].size()) { fclose(fp); return -6; }
+            g_gains.loaded = true;
+        }
+    }
     for (uint32_t i = 0; i < n; i++) {
         struct { char name[24]; uint32_t dtype, ndim, dims[4]; uint64_t off, nbytes; } rec;
         fseek(fp, 16 + 64L * i, SEEK_SET);
@@ -180,7 +195,7 @@ int orc_sim_init_trim(void* s, const double* p, double* trim_state_out, double* 
     if (trim_state_out) for (int i = 0; i < 7; i++) trim_state_out[i] = val(ts.v[i]);
     if (cost_out) *cost_out = cost;
     if (!ok) S->m.status = ST_TRIM_FAILED;
-    S->av.f_init(S->m, *S->W);
+    S->av.f_init(S->m, *S->W, S->Dt);
     S->apply_events();
     return ok ? 0 : 1;
 }
@@ -213,7 +228,7 @@ int orc_sim_init(void* s, const double* ic) {
     si.stall = ic[29] != 0; si.alpha_filt = ic[30]; si.beta_filt = ic[31];
     reinit(S);
     try { vehicle_init(S->m, *S->W, ki, si); } catch (OrcTermination& e) { S->m.status = e.code; return -1; }
-    S->av.f_init(S->m, *S->W);
+    S->av.f_init(S->m, *S->W, S->Dt);
     S->apply_events();
     return 0;
 }
@@ -367,6 +382,13 @@ double orc_engine_lookup(double n_stall, double n_max, int which, double n, doub
             return val(rmax(r, 0.0));
         }
     }
+}
+// gain-schedule lookup (control.jl:975-994): which = GainTables index; returns the packed vector length
+int orc_gain_lookup(int which, double EAS, double h, double* out) {
+    real g[64];
+    g_gains.lookup(which, EAS, h, g);
+    for (int k = 0; k < g_gains.P[which]; k++) out[k] = val(g[k]);
+    return g_gains.P[which];
 }
 // h2delta(h) = p/p_std / sqrt(T/T_std) of the standard atmosphere (piston.jl:41-44)
 double orc_h2delta(double h_geop) {

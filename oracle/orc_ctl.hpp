@@ -1,14 +1,381 @@
 // TEST INFRASTRUCTURE ONLY (see orc_real.hpp).
-// Avionics of the C172X variants (control laws + direct guidance). Placeholder: NoAvionics only.
+// Avionics of the C172X variants: discrete PID / Integrator / LQR compensators and the gain-scheduled
+// longitudinal / lateral control laws, restating
+//   FP/control.jl:123-185 (Integrator), :370-471 (PID), :620-743 (LQR), :950-994 (gain lookups)
+//   FA/c172/c172x/control/c172x_ctl.jl:18-24,29-77,97-171 (modes, state / command vectors),
+//       :275-446 (ControlLawsLon), :449-519 (assign!, f_init!), :733-751,756-812 (lateral vectors),
+//       :858-1032 (ControlLawsLat), :1190-1250 (ControlLaws)
+//   FA/c172/c172x/c172x2.jl:18-37 + guidance/c172x_gdc.jl:297-329 (ModeGuidance.direct pass-through)
+// in the reference's operation order.
 #pragma once
+#include <limits>
 #include "orc_vehicle.hpp"
+
+// gain schedules: [7 EAS][4 h][P] row-major, from the table blob (data of control/data/*.h5)
+struct GainTables {
+    enum { TE2TE = 0, TV2TE, VH2TE, AR2AR, PHIBETA2AR, Q2E, C2THETA, V2T, P2PHI, CHI2PHI, COUNT };
+    std::vector<double> t[COUNT];
+    int P[COUNT] = {0};
+    bool loaded = false;
+    // extrapolate(scale(interpolate(A, BSpline(Linear())), range(25,55,7), range(50,3050,4)), Flat()) — control.jl:950-973
+    void lookup(int which, real EAS, real h, real* out) const {
+        real e = rclamp(EAS, 25.0, 55.0), hh = rclamp(h, 50.0, 3050.0);
+        real fe = (e - 25.0) / 5.0, fh = (hh - 50.0) / 1000.0;
+        int i = (int)std::floor(val(fe)), j = (int)std::floor(val(fh));
+        if (i > 5) i = 5; if (j > 2) j = 2; if (i < 0) i = 0; if (j < 0) j = 0;
+        real u = fe - (double)i, w = fh - (double)j;
+        const int p = P[which];
+        const double* a = t[which].data();
+        for (int k = 0; k < p; k++) {
+            double f00 = a[((i * 4) + j) * p + k], f01 = a[((i * 4) + j + 1) * p + k];
+            double f10 = a[(((i + 1) * 4) + j) * p + k], f11 = a[(((i + 1) * 4) + j + 1) * p + k];
+            out[k] = (1.0 - u) * ((1.0 - w) * f00 + w * f01) + u * ((1.0 - w) * f10 + w * f11);
+        }
+    }
+};
+extern GainTables g_gains;
+
+static const double ORC_INF = std::numeric_limits<double>::infinity();
+
+struct PIDc {   // control.jl:370-471
+    real k_p = 1.0, k_i = 0.0, k_d = 0.0, tau_f = 0.01, beta_p = 1.0, beta_d = 1.0;
+    double lo = -ORC_INF, hi = ORC_INF;
+    real input = 0.0; int sat_ext = 0;
+    real x_i0 = 0.0, x_d0 = 0.0; int sat_out_0 = 0;
+    real output = 0.0; int sat_out = 0;
+    void assign(const real* g) { k_p = g[0]; k_i = g[1]; k_d = g[2]; tau_f = g[3]; }
+    void periodic(double Dt) {
+        real alpha = 1.0 / (tau_f + Dt);
+        real u_p = beta_p * input, u_d = beta_d * input, u_i = input;
+        bool halted = (isign(u_i * (double)sat_out_0) > 0) || (isign(u_i * (double)sat_ext) > 0);
+        real x_i = x_i0 + Dt * k_i * u_i * (halted ? 0.0 : 1.0);
+        real x_d = alpha * tau_f * x_d0 + Dt * alpha * k_d * u_d;
+        real y_p = k_p * u_p, y_i = x_i, y_d = alpha * (-x_d0 + k_d * u_d);
+        real out_free = y_p + y_i + y_d;
+        sat_out = (out_free >= hi) - (out_free <= lo);
+        output = rclamp(out_free, lo, hi);
+        x_i0 = x_i; x_d0 = x_d; sat_out_0 = sat_out;
+    }
+    void init(double Dt) { input = 0.0; sat_ext = 0; x_i0 = 0.0; x_d0 = 0.0; sat_out_0 = 0; periodic(Dt); }
+};
+
+struct Integ {   // control.jl:123-185
+    double lo = -ORC_INF, hi = ORC_INF;
+    real input = 0.0; int sat_ext = 0;
+    real x0 = 0.0; int sat_out_0 = 0;
+    real output = 0.0;
+    void periodic(double Dt) {
+        bool halted = (isign(input * (double)sat_out_0) > 0) || (isign(input * (double)sat_ext) > 0);
+        real x1 = x0 + Dt * input * (halted ? 0.0 : 1.0);
+        output = rclamp(x1, lo, hi);
+        int sat_out = (x1 >= hi) - (x1 <= lo);
+        x0 = x1; sat_out_0 = sat_out;
+    }
+    void init(double Dt, real x_init = 0.0) { input = 0.0; sat_ext = 0; x0 = x_init; sat_out_0 = 0; periodic(Dt); }
+};
+
+template <int NX>
+struct LQRc {   // control.jl:620-743, NU = NZ = 2
+    real K_fbk[2][NX], K_fwd[2][2], K_int[2][2], x_trim[NX], u_trim[2], z_trim[2];
+    double lo[2] = {-ORC_INF, -ORC_INF}, hi[2] = {ORC_INF, ORC_INF};
+    int sat_ext[2] = {0, 0}; real z_ref[2], z[2], x[NX];
+    real int_out_0[2]; int out_sat_0[2] = {0, 0};
+    real output[2]; int out_sat[2] = {0, 0};
+    LQRc() {
+        for (int i = 0; i < 2; i++) { for (int j = 0; j < NX; j++) K_fbk[i][j] = 0.0; for (int j = 0; j < 2; j++) { K_fwd[i][j] = 0.0; K_int[i][j] = 0.0; }
+            u_trim[i] = 0.0; z_trim[i] = 0.0; z_ref[i] = 0.0; z[i] = 0.0; int_out_0[i] = 0.0; output[i] = 0.0; }
+        for (int j = 0; j < NX; j++) { x_trim[j] = 0.0; x[j] = 0.0; }
+    }
+    void assign(const real* g) {   // packed: K_fbk (2 x NX row-major), K_fwd 2x2, K_int 2x2, x_trim NX, u_trim 2, z_trim 2
+        int p = 0;
+        for (int i = 0; i < 2; i++) for (int j = 0; j < NX; j++) K_fbk[i][j] = g[p++];
+        for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) K_fwd[i][j] = g[p++];
+        for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) K_int[i][j] = g[p++];
+        for (int j = 0; j < NX; j++) x_trim[j] = g[p++];
+        for (int i = 0; i < 2; i++) u_trim[i] = g[p++];
+        for (int i = 0; i < 2; i++) z_trim[i] = g[p++];
+    }
+    void periodic(double Dt) {
+        for (int i = 0; i < 2; i++) {
+            real int_in = K_int[i][0] * (z_ref[0] - z[0]) + K_int[i][1] * (z_ref[1] - z[1]);
+            bool halted = (isign(int_in * (double)out_sat_0[i]) > 0) || (isign(int_in * (double)sat_ext[i]) > 0);
+            real int_out = int_out_0[i] + Dt * int_in * (halted ? 0.0 : 1.0);
+            real fwd = K_fwd[i][0] * (z_ref[0] - z_trim[0]) + K_fwd[i][1] * (z_ref[1] - z_trim[1]);
+            real fbk = 0.0;
+            for (int j = 0; j < NX; j++) fbk = fbk + K_fbk[i][j] * (x[j] - x_trim[j]);
+            real out_free = u_trim[i] + int_out + fwd - fbk;
+            out_sat[i] = (out_free >= hi[i]) - (out_free <= lo[i]);
+            output[i] = rclamp(out_free, lo[i], hi[i]);
+            int_out_0[i] = int_out;
+        }
+        out_sat_0[0] = out_sat[0]; out_sat_0[1] = out_sat[1];
+    }
+    void init(double Dt) {
+        for (int i = 0; i < 2; i++) { z_ref[i] = 0.0; z[i] = 0.0; sat_ext[i] = 0; int_out_0[i] = 0.0; out_sat_0[i] = 0; }
+        for (int j = 0; j < NX; j++) x[j] = 0.0;
+        periodic(Dt);
+    }
+};
+
+enum LonMode { LON_DIRECT = 0, LON_SAS, LON_THR_Q, LON_THR_THETA, LON_THR_EAS, LON_EAS_Q, LON_EAS_THETA, LON_EAS_CLM, LON_EAS_ALT };
+enum LatMode { LAT_DIRECT = 0, LAT_SAS, LAT_P_BETA, LAT_PHI_BETA, LAT_CHI_BETA };
+
 struct Avionics {
     int variant = VAR_C172S;
-    bool set_input(int, double) { return false; }
-    double get_input(int) const { return 0.0 / 0.0; }
-    double output(const Member&, int) const { return 0.0 / 0.0; }
-    void assign(Member&) {}
-    void f_step(Member&) {}
-    void f_periodic(Member&, const World&, double) {}
-    void f_init(Member&, const World&) {}
+    // ---- ControlLawsLon (c172x_ctl.jl:201-274)
+    struct { int mode_req = LON_DIRECT; real throttle_axis = 0.0, throttle_offset = 0.0, elevator_axis = 0.0, elevator_offset = 0.0,
+             q_ref = 0.0, theta_ref = 0.0, EAS_ref = 50.0, clm_ref = 0.0, h_ref = 0.0; } ulon;
+    struct { int mode = LON_DIRECT; real throttle_cmd = 0.0, elevator_cmd = 0.0; } ylon;
+    int h_state = 1;   // AltTrackingState.hold
+    LQRc<8> te2te, tv2te; LQRc<9> vh2te;
+    Integ q2e_int; PIDc q2e_pid, c2t_pid, v2t_pid;
+    // ---- ControlLawsLat (c172x_ctl.jl:813-857)
+    struct { int mode_req = LAT_DIRECT; real aileron_axis = 0.0, aileron_offset = 0.0, rudder_axis = 0.0, rudder_offset = 0.0,
+             p_ref = 0.0, beta_ref = 0.0, phi_ref = 0.0, chi_ref = 0.0; } ulat;
+    struct { int mode = LAT_DIRECT; real aileron_cmd = 0.0, rudder_cmd = 0.0; } ylat;
+    LQRc<8> ar2ar, pb2ar;
+    Integ p2phi_int; PIDc p2phi_pid, chi2phi_pid;
+    int gdc_mode_req = 0;
+
+    bool active() const { return variant >= VAR_C172X1; }
+
+    // assign!(vehicle, avionics): c172x_ctl.jl:449-458, 986-995 — commands are Ranged on assignment
+    void assign(Member& m) {
+        if (!active()) return;
+        m.u.act_cmd[0] = rclamp(ylon.throttle_cmd, 0.0, 1.0);
+        m.u.act_cmd[2] = rclamp(ylon.elevator_cmd, -1.0, 1.0);
+        m.u.act_cmd[1] = rclamp(ylat.aileron_cmd, -1.0, 1.0);
+        m.u.act_cmd[3] = rclamp(ylat.rudder_cmd, -1.0, 1.0);
+    }
+    void f_step(Member&) {}   // @no_step
+
+    static bool on_gnd(const Member& m) { return m.y.strut[0].wow || m.y.strut[1].wow || m.y.strut[2].wow; }   // c172.jl:998-1001
+
+    void lon_periodic(const Member& m, double Dt) {   // c172x_ctl.jl:286-446
+        const VehicleY& v = m.y;
+        real EAS = v.air.EAS, h_e = v.kin.h_e;
+        real q = v.kin.w_wb_b.y, r = v.kin.w_wb_b.z;
+        real theta = v.kin.e_nb.theta, phi = v.kin.e_nb.phi;
+        real clm = -v.kin.v_eb_n.z;
+        real h_err = ulon.h_ref - h_e;
+        int mode_prev = ylon.mode;
+        real throttle_ref = rclamp(ulon.throttle_axis + ulon.throttle_offset, 0.0, 1.0);
+        real elevator_ref = rclamp(ulon.elevator_axis + ulon.elevator_offset, -1.0, 1.0);
+        real throttle_cmd = throttle_ref, elevator_cmd = elevator_ref;
+        real q_ref = ulon.q_ref, theta_ref = ulon.theta_ref;
+        int mode;
+        const double h_thr = 10.0, h_hys = 1.0, k_p_theta = 1.0;
+        if (on_gnd(m)) mode = LON_DIRECT;
+        else if (ulon.mode_req == LON_EAS_ALT) {
+            if (h_state == 0) {   // acquire
+                mode = LON_THR_EAS;
+                throttle_ref = h_err > 0.0 ? 1.0 : 0.0;
+                if (rabs(h_err) < h_thr - h_hys) h_state = 1;
+            } else {
+                mode = LON_EAS_ALT;
+                if (rabs(h_err) > h_thr + h_hys) h_state = 0;
+            }
+        } else mode = ulon.mode_req;
+        auto te2te_en = [](int md) { return md == LON_SAS || md == LON_THR_Q || md == LON_THR_THETA || md == LON_EAS_Q || md == LON_EAS_THETA || md == LON_EAS_CLM; };
+        auto q2e_en = [](int md) { return md == LON_THR_Q || md == LON_THR_THETA || md == LON_EAS_Q || md == LON_EAS_THETA || md == LON_EAS_CLM; };
+        auto t2q_en = [](int md) { return md == LON_THR_THETA || md == LON_EAS_THETA || md == LON_EAS_CLM; };
+        auto v2t_en = [](int md) { return md == LON_EAS_Q || md == LON_EAS_THETA || md == LON_EAS_CLM; };
+        real xred[8] = {v.kin.w_eb_b.y, theta, EAS, v.aero.alpha, v.aero.alpha_filt, v.eng.n, v.act.pos[0], v.act.pos[2]};   // XLonRed :132-147
+        real g[64];
+        if (te2te_en(mode)) {
+            int sat_thr = te2te.out_sat[0], sat_ele = te2te.out_sat[1];
+            if (v2t_en(mode)) {
+                g_gains.lookup(GainTables::V2T, EAS, h_e, g); v2t_pid.assign(g);
+                if (mode != mode_prev) { v2t_pid.init(Dt); if (v2t_pid.k_i != 0.0) v2t_pid.x_i0 = rclamp(ylon.throttle_cmd, 0.0, 1.0); }
+                v2t_pid.input = ulon.EAS_ref - EAS; v2t_pid.sat_ext = sat_thr;
+                v2t_pid.periodic(Dt);
+                throttle_ref = v2t_pid.output;
+            }
+            if (q2e_en(mode)) {
+                g_gains.lookup(GainTables::Q2E, EAS, h_e, g); q2e_pid.assign(g);
+                if (mode != mode_prev) { q2e_int.init(Dt); q2e_pid.init(Dt); if (q2e_pid.k_i != 0.0) q2e_pid.x_i0 = te2te.z_ref[1]; }
+                if (t2q_en(mode)) {
+                    if (mode == LON_EAS_CLM) {
+                        g_gains.lookup(GainTables::C2THETA, EAS, h_e, g); c2t_pid.assign(g);
+                        if (mode != mode_prev) { c2t_pid.init(Dt); if (c2t_pid.k_i != 0.0) c2t_pid.x_i0 = theta; }
+                        c2t_pid.input = ulon.clm_ref - clm; c2t_pid.sat_ext = sat_ele;
+                        c2t_pid.periodic(Dt);
+                        theta_ref = c2t_pid.output;
+                    }
+                    real theta_dot_ref = k_p_theta * (theta_ref - theta);
+                    real phi_bnd = rclamp(phi, -ORC_PI / 3, ORC_PI / 3);
+                    q_ref = 1.0 / cos(phi_bnd) * theta_dot_ref + r * tan(phi_bnd);
+                }
+                q2e_int.input = q_ref - q; q2e_int.sat_ext = sat_ele;
+                q2e_int.periodic(Dt);
+                q2e_pid.input = q2e_int.output; q2e_pid.sat_ext = sat_ele;
+                q2e_pid.periodic(Dt);
+                elevator_ref = q2e_pid.output;
+            }
+            g_gains.lookup(GainTables::TE2TE, EAS, h_e, g); te2te.assign(g);
+            for (int i = 0; i < 8; i++) te2te.x[i] = xred[i];
+            te2te.z[0] = v.act.cmd[0]; te2te.z[1] = v.act.cmd[2];          // Zte(vehicle) :167-171
+            te2te.z_ref[0] = throttle_ref; te2te.z_ref[1] = elevator_ref;
+            te2te.periodic(Dt);
+            throttle_cmd = te2te.output[0]; elevator_cmd = te2te.output[1];
+        }
+        if (mode == LON_THR_EAS) {
+            g_gains.lookup(GainTables::TV2TE, EAS, h_e, g); tv2te.assign(g);
+            if (mode != mode_prev) tv2te.init(Dt);
+            for (int i = 0; i < 8; i++) tv2te.x[i] = xred[i];
+            tv2te.z[0] = v.act.cmd[0]; tv2te.z[1] = EAS;                    // Ztv :190-194
+            tv2te.z_ref[0] = throttle_ref; tv2te.z_ref[1] = ulon.EAS_ref;
+            tv2te.periodic(Dt);
+            throttle_cmd = tv2te.output[0]; elevator_cmd = tv2te.output[1];
+        }
+        if (mode == LON_EAS_ALT) {
+            g_gains.lookup(GainTables::VH2TE, EAS, h_e, g); vh2te.assign(g);
+            if (mode != mode_prev) vh2te.init(Dt);
+            real xfull[9] = {v.kin.w_eb_b.y, theta, EAS, v.aero.alpha, h_e, v.aero.alpha_filt, v.eng.n, v.act.pos[0], v.act.pos[2]};   // XLonFull :97-118
+            for (int i = 0; i < 9; i++) vh2te.x[i] = xfull[i];
+            vh2te.z[0] = EAS; vh2te.z[1] = h_e;                              // Zvh :178-182
+            vh2te.z_ref[0] = ulon.EAS_ref; vh2te.z_ref[1] = ulon.h_ref;
+            vh2te.periodic(Dt);
+            throttle_cmd = vh2te.output[0]; elevator_cmd = vh2te.output[1];
+        }
+        ylon.mode = mode;
+        ylon.throttle_cmd = rclamp(throttle_cmd, 0.0, 1.0);
+        ylon.elevator_cmd = rclamp(elevator_cmd, -1.0, 1.0);
+    }
+
+    void lat_periodic(const Member& m, double Dt) {   // c172x_ctl.jl:880-983
+        const VehicleY& v = m.y;
+        real EAS = v.air.EAS, h_e = v.kin.h_e;
+        real p = v.kin.w_wb_b.x;
+        int mode_prev = ylat.mode;
+        int mode = on_gnd(m) ? LAT_DIRECT : ulat.mode_req;
+        real aileron_ref = rclamp(ulat.aileron_axis + ulat.aileron_offset, -1.0, 1.0);
+        real rudder_ref = rclamp(ulat.rudder_axis + ulat.rudder_offset, -1.0, 1.0);
+        real aileron_cmd = aileron_ref, rudder_cmd = rudder_ref;
+        real phi_ref = ulat.phi_ref;
+        real xlat[8] = {v.kin.w_eb_b.x, v.kin.w_eb_b.z, v.kin.e_nb.phi, EAS, v.aero.beta, v.aero.beta_filt, v.act.pos[1], v.act.pos[3]};   // XLatRed :767-779
+        real g[64];
+        if (mode == LAT_SAS) {
+            g_gains.lookup(GainTables::AR2AR, EAS, h_e, g); ar2ar.assign(g);
+            for (int i = 0; i < 8; i++) ar2ar.x[i] = xlat[i];
+            ar2ar.z[0] = v.act.cmd[1]; ar2ar.z[1] = v.act.cmd[3];           // Zar :806-810
+            ar2ar.z_ref[0] = aileron_ref; ar2ar.z_ref[1] = rudder_ref;
+            ar2ar.periodic(Dt);
+            aileron_cmd = ar2ar.output[0]; rudder_cmd = ar2ar.output[1];
+        }
+        if (mode == LAT_P_BETA || mode == LAT_PHI_BETA || mode == LAT_CHI_BETA) {
+            int sat_ail = pb2ar.out_sat[0];
+            if (mode == LAT_P_BETA) {
+                g_gains.lookup(GainTables::P2PHI, EAS, h_e, g); p2phi_pid.assign(g);
+                if (mode != mode_prev) { p2phi_int.init(Dt); p2phi_pid.init(Dt); if (p2phi_pid.k_i != 0.0) p2phi_pid.x_i0 = pb2ar.z_ref[0]; }
+                p2phi_int.input = ulat.p_ref - p; p2phi_int.sat_ext = sat_ail;
+                p2phi_int.periodic(Dt);
+                p2phi_pid.input = p2phi_int.output; p2phi_pid.sat_ext = sat_ail;
+                p2phi_pid.periodic(Dt);
+                phi_ref = p2phi_pid.output;
+            } else if (mode == LAT_CHI_BETA) {
+                g_gains.lookup(GainTables::CHI2PHI, EAS, h_e, g); chi2phi_pid.assign(g);
+                if (mode != mode_prev) { chi2phi_pid.init(Dt); if (chi2phi_pid.k_i != 0.0) chi2phi_pid.x_i0 = pb2ar.z_ref[0]; }
+                chi2phi_pid.input = wrap_to_pi(ulat.chi_ref - v.kin.chi_gnd); chi2phi_pid.sat_ext = sat_ail;
+                chi2phi_pid.periodic(Dt);
+                phi_ref = chi2phi_pid.output;
+            }
+            g_gains.lookup(GainTables::PHIBETA2AR, EAS, h_e, g); pb2ar.assign(g);
+            if (mode != mode_prev) pb2ar.init(Dt);
+            for (int i = 0; i < 8; i++) pb2ar.x[i] = xlat[i];
+            pb2ar.z[0] = v.kin.e_nb.phi; pb2ar.z[1] = v.aero.beta;          // Zphibeta :789-793
+            pb2ar.z_ref[0] = phi_ref; pb2ar.z_ref[1] = ulat.beta_ref;
+            pb2ar.periodic(Dt);
+            aileron_cmd = pb2ar.output[0]; rudder_cmd = pb2ar.output[1];
+        }
+        ylat.mode = mode;
+        ylat.aileron_cmd = rclamp(aileron_cmd, -1.0, 1.0);
+        ylat.rudder_cmd = rclamp(rudder_cmd, -1.0, 1.0);
+    }
+
+    // f_periodic!(avionics, vehicle): c172x2.jl:28-37 (guidance in direct mode only forwards), then lon, lat (@sm_periodic)
+    void f_periodic(Member& m, const World&, double Dt) {
+        if (!active()) return;
+        lon_periodic(m, Dt);
+        lat_periodic(m, Dt);
+    }
+
+    // f_init!(avionics, vehicle): c172x_ctl.jl:1246-1250 -> :463-519 (lon), :998-1032 (lat)
+    void f_init(Member& m, const World& W, double Dt = 0.0) {
+        if (!active()) return;
+        const VehicleY& v = m.y;
+        // f_init!(lon): every submodel, then the LQR bounds (:275-284)
+        te2te.init(Dt); tv2te.init(Dt); vh2te.init(Dt); q2e_int.init(Dt); q2e_pid.init(Dt); c2t_pid.init(Dt); v2t_pid.init(Dt);
+        LQRc<8>* l8[2] = {&te2te, &tv2te};
+        for (auto* l : l8) { l->lo[0] = 0; l->lo[1] = -1; l->hi[0] = 1; l->hi[1] = 1; }
+        vh2te.lo[0] = 0; vh2te.lo[1] = -1; vh2te.hi[0] = 1; vh2te.hi[1] = 1;
+        ulon.throttle_axis = rclamp(v.act.pos[0], 0.0, 1.0); ulon.elevator_axis = rclamp(v.act.pos[2], -1.0, 1.0);
+        ulon.throttle_offset = 0.0; ulon.elevator_offset = 0.0;
+        ulon.q_ref = v.kin.w_wb_b.y; ulon.theta_ref = v.kin.e_nb.theta; ulon.EAS_ref = v.air.EAS; ulon.clm_ref = -v.kin.v_eb_n.z; ulon.h_ref = v.kin.h_e;
+        const int lon_seq[4] = {LON_SAS, LON_THR_EAS, LON_EAS_ALT, LON_DIRECT};
+        for (int md : lon_seq) { ulon.mode_req = md; lon_periodic(m, Dt); }
+        // f_init!(lat): :868-878
+        ar2ar.init(Dt); pb2ar.init(Dt); p2phi_int.init(Dt); p2phi_pid.init(Dt); chi2phi_pid.init(Dt);
+        LQRc<8>* la[2] = {&pb2ar, &ar2ar};
+        for (auto* l : la) { l->lo[0] = -1; l->lo[1] = -1; l->hi[0] = 1; l->hi[1] = 1; }
+        chi2phi_pid.lo = -ORC_PI / 4; chi2phi_pid.hi = ORC_PI / 4;
+        ulat.aileron_axis = rclamp(v.act.pos[1], -1.0, 1.0); ulat.rudder_axis = rclamp(v.act.pos[3], -1.0, 1.0);
+        ulat.aileron_offset = 0.0; ulat.rudder_offset = 0.0;
+        ulat.p_ref = v.kin.w_wb_b.x; ulat.phi_ref = v.kin.e_nb.phi; ulat.beta_ref = v.aero.beta; ulat.chi_ref = v.kin.chi_gnd;
+        const int lat_seq[3] = {LAT_SAS, LAT_PHI_BETA, LAT_DIRECT};
+        for (int md : lat_seq) { ulat.mode_req = md; lat_periodic(m, Dt); }
+        (void)W;
+    }
+
+    bool set_input(int f, double v) {
+        auto c01 = [](double x) { return x < 0 ? 0.0 : (x > 1 ? 1.0 : x); };
+        auto c11 = [](double x) { return x < -1 ? -1.0 : (x > 1 ? 1.0 : x); };
+        switch (f) {
+            case FB_U_LON_MODE_REQ: ulon.mode_req = (int)v; return true;
+            case FB_U_LON_THROTTLE_AXIS: ulon.throttle_axis = c01(v); return true;
+            case FB_U_LON_THROTTLE_OFFSET: ulon.throttle_offset = c01(v); return true;
+            case FB_U_LON_ELEVATOR_AXIS: ulon.elevator_axis = c11(v); return true;
+            case FB_U_LON_ELEVATOR_OFFSET: ulon.elevator_offset = c11(v); return true;
+            case FB_U_LON_Q_REF: ulon.q_ref = v; return true;
+            case FB_U_LON_THETA_REF: ulon.theta_ref = v; return true;
+            case FB_U_LON_EAS_REF: ulon.EAS_ref = v; return true;
+            case FB_U_LON_CLM_REF: ulon.clm_ref = v; return true;
+            case FB_U_LON_H_REF: ulon.h_ref = v; return true;
+            case FB_U_LAT_MODE_REQ: ulat.mode_req = (int)v; return true;
+            case FB_U_LAT_AILERON_AXIS: ulat.aileron_axis = c11(v); return true;
+            case FB_U_LAT_AILERON_OFFSET: ulat.aileron_offset = c11(v); return true;
+            case FB_U_LAT_RUDDER_AXIS: ulat.rudder_axis = c11(v); return true;
+            case FB_U_LAT_RUDDER_OFFSET: ulat.rudder_offset = c11(v); return true;
+            case FB_U_LAT_P_REF: ulat.p_ref = v; return true;
+            case FB_U_LAT_BETA_REF: ulat.beta_ref = v; return true;
+            case FB_U_LAT_PHI_REF: ulat.phi_ref = v; return true;
+            case FB_U_LAT_CHI_REF: ulat.chi_ref = v; return true;
+            case FB_U_GDC_MODE_REQ: gdc_mode_req = (int)v; return true;
+            default: return false;
+        }
+    }
+    double get_input(int f) const {
+        switch (f) {
+            case FB_U_LON_MODE_REQ: return ulon.mode_req; case FB_U_LON_THROTTLE_AXIS: return val(ulon.throttle_axis);
+            case FB_U_LON_THROTTLE_OFFSET: return val(ulon.throttle_offset); case FB_U_LON_ELEVATOR_AXIS: return val(ulon.elevator_axis);
+            case FB_U_LON_ELEVATOR_OFFSET: return val(ulon.elevator_offset); case FB_U_LON_Q_REF: return val(ulon.q_ref);
+            case FB_U_LON_THETA_REF: return val(ulon.theta_ref); case FB_U_LON_EAS_REF: return val(ulon.EAS_ref);
+            case FB_U_LON_CLM_REF: return val(ulon.clm_ref); case FB_U_LON_H_REF: return val(ulon.h_ref);
+            case FB_U_LAT_MODE_REQ: return ulat.mode_req; case FB_U_LAT_AILERON_AXIS: return val(ulat.aileron_axis);
+            case FB_U_LAT_AILERON_OFFSET: return val(ulat.aileron_offset); case FB_U_LAT_RUDDER_AXIS: return val(ulat.rudder_axis);
+            case FB_U_LAT_RUDDER_OFFSET: return val(ulat.rudder_offset); case FB_U_LAT_P_REF: return val(ulat.p_ref);
+            case FB_U_LAT_BETA_REF: return val(ulat.beta_ref); case FB_U_LAT_PHI_REF: return val(ulat.phi_ref);
+            case FB_U_LAT_CHI_REF: return val(ulat.chi_ref); case FB_U_GDC_MODE_REQ: return gdc_mode_req;
+            default: return 0.0 / 0.0;
+        }
+    }
+    double output(const Member&, int f) const {
+        switch (f) {
+            case FB_Y_LON_MODE: return ylon.mode; case FB_Y_LAT_MODE: return ylat.mode;
+            case FB_Y_THROTTLE_CMD: return val(ylon.throttle_cmd); case FB_Y_ELEVATOR_CMD: return val(ylon.elevator_cmd);
+            case FB_Y_AILERON_CMD: return val(ylat.aileron_cmd); case FB_Y_RUDDER_CMD: return val(ylat.rudder_cmd);
+            case FB_Y_ALT_STATE: return h_state;
+            default: return 0.0 / 0.0;
+        }
+    }
 };
