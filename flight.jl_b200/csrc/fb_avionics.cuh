@@ -1,21 +1,52 @@
 // fb_avionics.cuh — discrete-time side of the path: output extraction (the root `y` the reference saves),
-// the decimated log writer, and the C172X control laws (ControlLawsLon / ControlLawsLat,
-// lib/FlightApps/src/c172/c172x/control/c172x_ctl.jl:286-446, 880-983) run once per Δt.
+// and the C172X gain-scheduled control laws run once per Δt by the thread that owns the aircraft.
+// Behavioural spec (paths relative to the reference root):
+//   discrete compensators  lib/FlightPhysics/src/control.jl:123-185 (Integrator), :370-471 (PID), :620-743 (LQR)
+//   gain lookups           control.jl:950-994: scale(interpolate(A, BSpline(Linear())), 25:5:55, 50:1000:3050), Flat
+//   ControlLawsLon         lib/FlightApps/src/c172/c172x/control/c172x_ctl.jl:201-284 (model), :286-446 (f_periodic!),
+//                          :449-519 (assign!, f_init!)
+//   ControlLawsLat         c172x_ctl.jl:813-878 (model), :880-983 (f_periodic!), :986-1032 (assign!, f_init!)
+//   Cessna172Xv2           c172x/c172x2.jl:28-37 + guidance/c172x_gdc.jl:297-329 (ModeGuidance.direct forwards)
+// Layout: the per-member controller memory (integrator states, saturation flags, previous mode, last commands) is
+// one column of E.ctl ([FB_CTL_STATE_COUNT][pitch], member fastest); a thread loads its column once per launch,
+// keeps it in thread-local storage across the fused steps and writes it back at the end. Gain schedules stay in
+// global memory (45 KB, read-only path): only the compensators of the active mode are looked up.
 #pragma once
 #include "fb_physics.cuh"
 
 #define FB_CTL_STATE_COUNT 64
 
+enum { LON_DIRECT = 0, LON_SAS, LON_THR_Q, LON_THR_THETA, LON_THR_EAS, LON_EAS_Q, LON_EAS_THETA, LON_EAS_CLM, LON_EAS_ALT };  // c172x_ctl.jl:29-41
+enum { LAT_DIRECT = 0, LAT_SAS, LAT_P_BETA, LAT_PHI_BETA, LAT_CHI_BETA };                                                  // :733-741
+
+struct LqrS { double io[2]; int sat[2]; };          // LQR.s: int_out_0, out_sat_0 (control.jl:678-681)
+struct PidS { double xi, xd; int sat; };            // PID.s: x_i0, x_d0, sat_out_0 (control.jl:386-390)
+struct IntS { double x0; int sat; };                // Integrator.s (control.jl:133-136)
+
 struct CtlState {
-    // placeholder until the control laws land: modes and commands only
-    double lon_mode, lat_mode, thr_cmd, ele_cmd, ail_cmd, rud_cmd;
-    FB_DEV void load(const double* p, long long pitch) {
-        lon_mode = p[0]; lat_mode = p[pitch]; thr_cmd = p[2 * pitch]; ele_cmd = p[3 * pitch]; ail_cmd = p[4 * pitch]; rud_cmd = p[5 * pitch];
+    int lon_mode, lat_mode, h_state;                // y.lon.mode, y.lat.mode (previous mode for bumpless transfer), s.h_state
+    double thr_cmd, ele_cmd, ail_cmd, rud_cmd;      // y.*_cmd of the last update
+    LqrS te2te, tv2te, vh2te, ar2ar, pb2ar;
+    double te2te_zref1, pb2ar_zref0;                // te2te_lqr.u.z_ref.elevator_cmd, φβ2ar_lqr.u.z_ref.φ (read on resets)
+    IntS q2e_int, p2phi_int;
+    PidS q2e_pid, c2t_pid, v2t_pid, p2phi_pid, chi2phi_pid;
+
+    template <bool STORE>
+    FB_DEV void xfer(double* p, long long pitch) {
+        int k = 0;
+        auto D = [&](double& v) { if (STORE) p[k * pitch] = v; else v = p[k * pitch]; k++; };
+        auto I = [&](int& v) { if (STORE) p[k * pitch] = (double)v; else v = (int)p[k * pitch]; k++; };
+        auto L = [&](LqrS& s) { D(s.io[0]); D(s.io[1]); I(s.sat[0]); I(s.sat[1]); };
+        auto P = [&](PidS& s) { D(s.xi); D(s.xd); I(s.sat); };
+        auto N = [&](IntS& s) { D(s.x0); I(s.sat); };
+        I(lon_mode); I(lat_mode); I(h_state); D(thr_cmd); D(ele_cmd); D(ail_cmd); D(rud_cmd);
+        L(te2te); L(tv2te); L(vh2te); L(ar2ar); L(pb2ar); D(te2te_zref1); D(pb2ar_zref0);
+        N(q2e_int); N(p2phi_int); P(q2e_pid); P(c2t_pid); P(v2t_pid); P(p2phi_pid); P(chi2phi_pid);
     }
-    FB_DEV void store(double* p, long long pitch) const {
-        p[0] = lon_mode; p[pitch] = lat_mode; p[2 * pitch] = thr_cmd; p[3 * pitch] = ele_cmd; p[4 * pitch] = ail_cmd; p[5 * pitch] = rud_cmd;
-    }
+    FB_DEV void load(double* p, long long pitch) { xfer<false>(p, pitch); }
+    FB_DEV void store(double* p, long long pitch) { xfer<true>(p, pitch); }
 };
+#define FB_CTL_ROW_H_STATE 2   // row of h_state in the column (constructed-model default: hold = 1)
 
 __host__ __device__ inline double avionics_saturate_input(int f, double v) {
     switch (f) {
@@ -53,16 +84,260 @@ FB_DEV double pick_output(const YFull& y, int stall, int eng, const CtlState& cs
         case FB_Y_ENG_P_SHAFT: return y.eng_P_shaft; case FB_Y_ENG_TAU_SHAFT: return y.eng_tau_shaft; case FB_Y_ENG_MDOT: return y.eng_mdot;
         case FB_Y_FUEL_M_TOTAL: return y.fuel_m_total; case FB_Y_PROP_THRUST: return y.prop_thrust; case FB_Y_PROP_J: return y.prop_J;
         case FB_Y_MASS: return y.mass; case FB_Y_F_X: return y.f_c_c.x; case FB_Y_F_Y: return y.f_c_c.y; case FB_Y_F_Z: return y.f_c_c.z;
-        case FB_Y_LON_MODE: return cs.lon_mode; case FB_Y_LAT_MODE: return cs.lat_mode;
+        case FB_Y_LON_MODE: return (double)cs.lon_mode; case FB_Y_LAT_MODE: return (double)cs.lat_mode;
         case FB_Y_THROTTLE_CMD: return cs.thr_cmd; case FB_Y_ELEVATOR_CMD: return cs.ele_cmd;
         case FB_Y_AILERON_CMD: return cs.ail_cmd; case FB_Y_RUDDER_CMD: return cs.rud_cmd;
+        case FB_Y_ALT_STATE: return (double)cs.h_state;
         default: return nan("");
     }
 }
 
-// f_periodic!(avionics, vehicle) + assign!(vehicle, avionics): placeholder (NoAvionics behaviour)
+// ------------------------------------------------------------------------------------------ gain schedules
+// One bilinear cell of the (EAS, h_e) design grid, Flat outside (control.jl:965); value k of a schedule with P
+// values per design point is read on demand.
+struct GainCell {
+    int o;          // (i * 4 + j): design-point index of the cell's low corner
+    double u, w;    // weights along EAS and h
+    FB_DEV void locate(double EAS, double h) {
+        double fe = (clampd(EAS, 25.0, 55.0) - 25.0) * (1.0 / 5.0), fh = (clampd(h, 50.0, 3050.0) - 50.0) * (1.0 / 1000.0);
+        int i = min((int)fe, 5), j = min((int)fh, 2);
+        u = fe - (double)i; w = fh - (double)j; o = i * 4 + j;
+    }
+};
+struct Gain {
+    const double* p; int P; double u, w;
+    FB_DEV Gain(const double* tab, int P_, const GainCell& c) : p(tab + (long long)c.o * P_), P(P_), u(c.u), w(c.w) {}
+    FB_DEV double operator()(int k) const {
+        double f00 = __ldg(p + k), f01 = __ldg(p + P + k), f10 = __ldg(p + 4 * P + k), f11 = __ldg(p + 5 * P + k);
+        return (1.0 - u) * ((1.0 - w) * f00 + w * f01) + u * ((1.0 - w) * f10 + w * f11);
+    }
+};
+
+// ------------------------------------------------------------------------------------------ compensators
+// PID f_periodic! (control.jl:431-471), β_p = β_d = 1; gains g = (k_p, k_i, k_d, τ_f)
+FB_DEV double pid_update(PidS& s, double k_p, double k_i, double k_d, double tau_f, double lo, double hi,
+                         double input, int sat_ext, double Dt) {
+    double alpha = 1.0 / (tau_f + Dt);
+    bool halted = (isign(input * (double)s.sat) > 0) || (isign(input * (double)sat_ext) > 0);
+    double x_i = s.xi + Dt * k_i * input * (halted ? 0.0 : 1.0);
+    double x_d = alpha * tau_f * s.xd + Dt * alpha * k_d * input;
+    double out_free = k_p * input + x_i + alpha * (-s.xd + k_d * input);
+    s.sat = (out_free >= hi) - (out_free <= lo);
+    s.xi = x_i; s.xd = x_d;
+    return clampd(out_free, lo, hi);
+}
+FB_DEV void pid_reset(PidS& s) { s.xi = 0.0; s.xd = 0.0; s.sat = 0; }   // f_init!(pid): zero input leaves a zero state
+// Integrator f_periodic! (control.jl:164-185), unbounded
+FB_DEV double int_update(IntS& s, double input, int sat_ext, double Dt) {
+    bool halted = (isign(input * (double)s.sat) > 0) || (isign(input * (double)sat_ext) > 0);
+    double x1 = s.x0 + Dt * input * (halted ? 0.0 : 1.0);
+    s.x0 = x1; s.sat = 0;   // bounds are +-Inf: never saturated
+    return x1;
+}
+FB_DEV void int_reset(IntS& s) { s.x0 = 0.0; s.sat = 0; }
+
+// LQR f_periodic! (control.jl:708-743), NU = NZ = 2. Schedule record: K_fbk (2 x NX row-major), K_fwd 2x2, K_int 2x2,
+// x_trim NX, u_trim 2, z_trim 2 (packing of tools/build_tables.py).
+template <int NX>
+FB_DEV void lqr_update(LqrS& s, const Gain& g, const double* x, double z0, double z1, double zr0, double zr1,
+                       double lo0, double lo1, double Dt, double& out0, double& out1) {
+    double dx[NX];
+#pragma unroll
+    for (int j = 0; j < NX; j++) dx[j] = x[j] - g(2 * NX + 8 + j);
+    const double zt0 = g(3 * NX + 10), zt1 = g(3 * NX + 11);
+    double out[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        double int_in = g(2 * NX + 4 + 2 * i) * (zr0 - z0) + g(2 * NX + 5 + 2 * i) * (zr1 - z1);
+        bool halted = isign(int_in * (double)s.sat[i]) > 0;
+        double int_out = s.io[i] + Dt * int_in * (halted ? 0.0 : 1.0);
+        double fwd = g(2 * NX + 2 * i) * (zr0 - zt0) + g(2 * NX + 1 + 2 * i) * (zr1 - zt1);
+        double fbk = 0.0;
+#pragma unroll
+        for (int j = 0; j < NX; j++) fbk = fbk + g(i * NX + j) * dx[j];
+        double out_free = g(3 * NX + 8 + i) + int_out + fwd - fbk;
+        const double lo = i ? lo1 : lo0;
+        s.sat[i] = (out_free >= 1.0) - (out_free <= lo);
+        out[i] = clampd(out_free, lo, 1.0);
+        s.io[i] = int_out;
+    }
+    out0 = out[0]; out1 = out[1];
+}
+// f_init!(lqr) with the gains currently assigned: zero inputs, one update (leaves int_out_0 = 0 and the saturation
+// flags of the zero-input output)
+template <int NX>
+FB_DEV void lqr_reset(LqrS& s, const Gain& g, double lo0, double lo1, double Dt) {
+    s.io[0] = 0.0; s.io[1] = 0.0; s.sat[0] = 0; s.sat[1] = 0;
+    double x[NX];
+#pragma unroll
+    for (int j = 0; j < NX; j++) x[j] = 0.0;
+    double a, b;
+    lqr_update<NX>(s, g, x, 0.0, 0.0, 0.0, 0.0, lo0, lo1, Dt, a, b);
+}
+
+// ------------------------------------------------------------------------------------------ control laws
+// f_periodic!(ControlLawsLon) — c172x_ctl.jl:286-446
+__device__ __noinline__ void lon_periodic(CtlState& cs, const YFull& v, int wow, const MemberIn& u,
+                                          const FbDeviceTables& T, double Dt, int mode_req) {
+    const double EAS = v.EAS, h_e = v.h_e, q = v.w_wb_b.y, r = v.w_wb_b.z, theta = v.theta, phi = v.phi;
+    const double clm = -v.v_eb_n.z;
+    const double h_ref = u(FB_U_LON_H_REF), EAS_ref = u(FB_U_LON_EAS_REF);
+    const double h_err = h_ref - h_e;
+    const int mode_prev = cs.lon_mode;
+    double throttle_ref = clampd(u(FB_U_LON_THROTTLE_AXIS) + u(FB_U_LON_THROTTLE_OFFSET), 0.0, 1.0);
+    double elevator_ref = clampd(u(FB_U_LON_ELEVATOR_AXIS) + u(FB_U_LON_ELEVATOR_OFFSET), -1.0, 1.0);
+    double throttle_cmd = throttle_ref, elevator_cmd = elevator_ref;
+    double q_ref = u(FB_U_LON_Q_REF), theta_ref = u(FB_U_LON_THETA_REF);
+    int mode;
+    if (wow) mode = LON_DIRECT;
+    else if (mode_req == LON_EAS_ALT) {
+        if (cs.h_state == 0) {   // acquire
+            mode = LON_THR_EAS;
+            throttle_ref = h_err > 0.0 ? 1.0 : 0.0;
+            if (fabs(h_err) < 10.0 - 1.0) cs.h_state = 1;
+        } else {
+            mode = LON_EAS_ALT;
+            if (fabs(h_err) > 10.0 + 1.0) cs.h_state = 0;
+        }
+    } else mode = mode_req;
+    const bool te2te_en = (mode >= LON_SAS && mode <= LON_THR_THETA) || (mode >= LON_EAS_Q && mode <= LON_EAS_CLM);
+    const bool q2e_en = te2te_en && mode != LON_SAS;
+    const bool t2q_en = mode == LON_THR_THETA || mode == LON_EAS_THETA || mode == LON_EAS_CLM;
+    const bool v2t_en = mode >= LON_EAS_Q && mode <= LON_EAS_CLM;
+    GainCell c; c.locate(EAS, h_e);
+    const double xred[8] = {v.w_eb_b.y, theta, EAS, v.alpha, v.alpha_filt, v.eng_n, v.act_pos[0], v.act_pos[2]};   // XLonRed :132-147
+    if (te2te_en) {
+        const int sat_thr = cs.te2te.sat[0], sat_ele = cs.te2te.sat[1];
+        if (v2t_en) {
+            Gain g(T.gains[GS_V2T], 4, c);
+            const double k_i = g(1);
+            if (mode != mode_prev) { pid_reset(cs.v2t_pid); if (k_i != 0.0) cs.v2t_pid.xi = cs.thr_cmd; }
+            throttle_ref = pid_update(cs.v2t_pid, g(0), k_i, g(2), g(3), -INFINITY, INFINITY, EAS_ref - EAS, sat_thr, Dt);
+        }
+        if (q2e_en) {
+            Gain g(T.gains[GS_Q2E], 4, c);
+            const double k_i = g(1);
+            if (mode != mode_prev) { int_reset(cs.q2e_int); pid_reset(cs.q2e_pid); if (k_i != 0.0) cs.q2e_pid.xi = cs.te2te_zref1; }
+            if (t2q_en) {
+                if (mode == LON_EAS_CLM) {
+                    Gain gc(T.gains[GS_C2THETA], 4, c);
+                    const double k_ic = gc(1);
+                    if (mode != mode_prev) { pid_reset(cs.c2t_pid); if (k_ic != 0.0) cs.c2t_pid.xi = theta; }
+                    theta_ref = pid_update(cs.c2t_pid, gc(0), k_ic, gc(2), gc(3), -INFINITY, INFINITY, u(FB_U_LON_CLM_REF) - clm, sat_ele, Dt);
+                }
+                double theta_dot_ref = 1.0 * (theta_ref - theta);
+                double phi_bnd = clampd(phi, -FB_PI / 3, FB_PI / 3);
+                q_ref = 1.0 / cos(phi_bnd) * theta_dot_ref + r * tan(phi_bnd);
+            }
+            double io = int_update(cs.q2e_int, q_ref - q, sat_ele, Dt);
+            elevator_ref = pid_update(cs.q2e_pid, g(0), k_i, g(2), g(3), -INFINITY, INFINITY, io, sat_ele, Dt);
+        }
+        Gain g(T.gains[GS_TE2TE], 36, c);
+        cs.te2te_zref1 = elevator_ref;
+        lqr_update<8>(cs.te2te, g, xred, v.act_cmd[0], v.act_cmd[2], throttle_ref, elevator_ref, 0.0, -1.0, Dt, throttle_cmd, elevator_cmd);   // Zte :167-171
+    }
+    if (mode == LON_THR_EAS) {
+        Gain g(T.gains[GS_TV2TE], 36, c);
+        if (mode != mode_prev) lqr_reset<8>(cs.tv2te, g, 0.0, -1.0, Dt);
+        lqr_update<8>(cs.tv2te, g, xred, v.act_cmd[0], EAS, throttle_ref, EAS_ref, 0.0, -1.0, Dt, throttle_cmd, elevator_cmd);   // Ztv :190-194
+    }
+    if (mode == LON_EAS_ALT) {
+        Gain g(T.gains[GS_VH2TE], 39, c);
+        if (mode != mode_prev) lqr_reset<9>(cs.vh2te, g, 0.0, -1.0, Dt);
+        const double xfull[9] = {v.w_eb_b.y, theta, EAS, v.alpha, h_e, v.alpha_filt, v.eng_n, v.act_pos[0], v.act_pos[2]};   // XLonFull :97-118
+        lqr_update<9>(cs.vh2te, g, xfull, EAS, h_e, EAS_ref, h_ref, 0.0, -1.0, Dt, throttle_cmd, elevator_cmd);   // Zvh :178-182
+    }
+    cs.lon_mode = mode;
+    cs.thr_cmd = clampd(throttle_cmd, 0.0, 1.0);
+    cs.ele_cmd = clampd(elevator_cmd, -1.0, 1.0);
+}
+
+FB_DEV double wrap_to_pi(double x) { return x + 2.0 * FB_PI * floor((FB_PI - x) / (2.0 * FB_PI)); }   // attitude.jl wrap_to_π
+
+// f_periodic!(ControlLawsLat) — c172x_ctl.jl:880-983
+__device__ __noinline__ void lat_periodic(CtlState& cs, const YFull& v, int wow, const MemberIn& u,
+                                          const FbDeviceTables& T, double Dt, int mode_req) {
+    const double EAS = v.EAS, h_e = v.h_e, p = v.w_wb_b.x;
+    const int mode_prev = cs.lat_mode;
+    const int mode = wow ? LAT_DIRECT : mode_req;
+    double aileron_ref = clampd(u(FB_U_LAT_AILERON_AXIS) + u(FB_U_LAT_AILERON_OFFSET), -1.0, 1.0);
+    double rudder_ref = clampd(u(FB_U_LAT_RUDDER_AXIS) + u(FB_U_LAT_RUDDER_OFFSET), -1.0, 1.0);
+    double aileron_cmd = aileron_ref, rudder_cmd = rudder_ref;
+    double phi_ref = u(FB_U_LAT_PHI_REF);
+    const double xlat[8] = {v.w_eb_b.x, v.w_eb_b.z, v.phi, EAS, v.beta, v.beta_filt, v.act_pos[1], v.act_pos[3]};   // XLatRed :767-779
+    GainCell c; c.locate(EAS, h_e);
+    if (mode == LAT_SAS) {
+        Gain g(T.gains[GS_AR2AR], 36, c);
+        lqr_update<8>(cs.ar2ar, g, xlat, v.act_cmd[1], v.act_cmd[3], aileron_ref, rudder_ref, -1.0, -1.0, Dt, aileron_cmd, rudder_cmd);   // Zar :806-810
+    }
+    if (mode == LAT_P_BETA || mode == LAT_PHI_BETA || mode == LAT_CHI_BETA) {
+        const int sat_ail = cs.pb2ar.sat[0];
+        if (mode == LAT_P_BETA) {
+            Gain g(T.gains[GS_P2PHI], 4, c);
+            const double k_i = g(1);
+            if (mode != mode_prev) { int_reset(cs.p2phi_int); pid_reset(cs.p2phi_pid); if (k_i != 0.0) cs.p2phi_pid.xi = cs.pb2ar_zref0; }
+            double io = int_update(cs.p2phi_int, u(FB_U_LAT_P_REF) - p, sat_ail, Dt);
+            phi_ref = pid_update(cs.p2phi_pid, g(0), k_i, g(2), g(3), -INFINITY, INFINITY, io, sat_ail, Dt);
+        } else if (mode == LAT_CHI_BETA) {
+            Gain g(T.gains[GS_CHI2PHI], 4, c);
+            const double k_i = g(1);
+            if (mode != mode_prev) { pid_reset(cs.chi2phi_pid); if (k_i != 0.0) cs.chi2phi_pid.xi = cs.pb2ar_zref0; }
+            phi_ref = pid_update(cs.chi2phi_pid, g(0), k_i, g(2), g(3), -FB_PI / 4, FB_PI / 4, wrap_to_pi(u(FB_U_LAT_CHI_REF) - v.chi_gnd), sat_ail, Dt);
+        }
+        Gain g(T.gains[GS_PHIBETA2AR], 36, c);
+        if (mode != mode_prev) lqr_reset<8>(cs.pb2ar, g, -1.0, -1.0, Dt);
+        cs.pb2ar_zref0 = phi_ref;
+        lqr_update<8>(cs.pb2ar, g, xlat, v.phi, v.beta, phi_ref, u(FB_U_LAT_BETA_REF), -1.0, -1.0, Dt, aileron_cmd, rudder_cmd);   // Zφβ :789-793
+    }
+    cs.lat_mode = mode;
+    cs.ail_cmd = clampd(aileron_cmd, -1.0, 1.0);
+    cs.rud_cmd = clampd(rudder_cmd, -1.0, 1.0);
+}
+
+// assign!(vehicle, avionics): c172x_ctl.jl:449-458, 986-995 — the four fly-by-wire commands the control laws own
+FB_DEV bool avionics_assign(const CtlState& cs, const MemberIn& u) {
+    bool ch = false;
+    double v;
+    v = clampd(cs.thr_cmd, 0.0, 1.0);  if (u(FB_U_ACT_THROTTLE) != v) { u.set(FB_U_ACT_THROTTLE, v); ch = true; }
+    v = clampd(cs.ail_cmd, -1.0, 1.0); if (u(FB_U_ACT_AILERON) != v) { u.set(FB_U_ACT_AILERON, v); ch = true; }
+    v = clampd(cs.ele_cmd, -1.0, 1.0); if (u(FB_U_ACT_ELEVATOR) != v) { u.set(FB_U_ACT_ELEVATOR, v); ch = true; }
+    v = clampd(cs.rud_cmd, -1.0, 1.0); if (u(FB_U_ACT_RUDDER) != v) { u.set(FB_U_ACT_RUDDER, v); ch = true; }
+    return ch;
+}
+
+// f_periodic!(avionics, vehicle) (guidance in direct mode forwards, then lon, then lat) followed by assign!.
+// Returns true when an actuator command changed (only ẋ.act of the pending derivative depends on it).
 template <int VAR, int KIN>
 FB_DEV bool avionics_periodic(const YFull& yf, const RhsOut& y, const MemberIn& u,
                               CtlState& cs, const FbDeviceTables& T, double Dt) {
-    return false;
+    if (VAR < FB_C172X1) return false;
+    lon_periodic(cs, yf, y.wow, u, T, Dt, (int)u(FB_U_LON_MODE_REQ));
+    lat_periodic(cs, yf, y.wow, u, T, Dt, (int)u(FB_U_LAT_MODE_REQ));
+    return avionics_assign(cs, u);
+}
+
+// f_init!(avionics, vehicle): c172x_ctl.jl:1246-1250 -> :463-519 (lon), :998-1032 (lat). `yf` is the vehicle output
+// left by f_init!(vehicle, ...). A freshly constructed model is assumed (all compensator memory zero).
+FB_DEV void avionics_init(const YFull& v, int wow, const MemberIn& u, CtlState& cs, const FbDeviceTables& T, double Dt) {
+    LqrS z; z.io[0] = z.io[1] = 0.0; z.sat[0] = z.sat[1] = 0;
+    cs.te2te = z; cs.tv2te = z; cs.vh2te = z; cs.ar2ar = z; cs.pb2ar = z;
+    cs.te2te_zref1 = 0.0; cs.pb2ar_zref0 = 0.0;
+    int_reset(cs.q2e_int); int_reset(cs.p2phi_int);
+    pid_reset(cs.q2e_pid); pid_reset(cs.c2t_pid); pid_reset(cs.v2t_pid); pid_reset(cs.p2phi_pid); pid_reset(cs.chi2phi_pid);
+    u.set(FB_U_LON_THROTTLE_AXIS, clampd(v.act_pos[0], 0.0, 1.0)); u.set(FB_U_LON_ELEVATOR_AXIS, clampd(v.act_pos[2], -1.0, 1.0));
+    u.set(FB_U_LON_THROTTLE_OFFSET, 0.0); u.set(FB_U_LON_ELEVATOR_OFFSET, 0.0);
+    u.set(FB_U_LON_Q_REF, v.w_wb_b.y); u.set(FB_U_LON_THETA_REF, v.theta); u.set(FB_U_LON_EAS_REF, v.EAS);
+    u.set(FB_U_LON_CLM_REF, -v.v_eb_n.z); u.set(FB_U_LON_H_REF, v.h_e);
+    lon_periodic(cs, v, wow, u, T, Dt, LON_SAS);
+    lon_periodic(cs, v, wow, u, T, Dt, LON_THR_EAS);
+    lon_periodic(cs, v, wow, u, T, Dt, LON_EAS_ALT);
+    lon_periodic(cs, v, wow, u, T, Dt, LON_DIRECT);
+    u.set(FB_U_LON_MODE_REQ, (double)LON_DIRECT);
+    u.set(FB_U_LAT_AILERON_AXIS, clampd(v.act_pos[1], -1.0, 1.0)); u.set(FB_U_LAT_RUDDER_AXIS, clampd(v.act_pos[3], -1.0, 1.0));
+    u.set(FB_U_LAT_AILERON_OFFSET, 0.0); u.set(FB_U_LAT_RUDDER_OFFSET, 0.0);
+    u.set(FB_U_LAT_P_REF, v.w_wb_b.x); u.set(FB_U_LAT_PHI_REF, v.phi); u.set(FB_U_LAT_BETA_REF, v.beta); u.set(FB_U_LAT_CHI_REF, v.chi_gnd);
+    lat_periodic(cs, v, wow, u, T, Dt, LAT_SAS);
+    lat_periodic(cs, v, wow, u, T, Dt, LAT_PHI_BETA);
+    lat_periodic(cs, v, wow, u, T, Dt, LAT_DIRECT);
+    u.set(FB_U_LAT_MODE_REQ, (double)LAT_DIRECT);
 }

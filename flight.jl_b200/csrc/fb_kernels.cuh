@@ -141,6 +141,7 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
         u.set(f, saturate_input(f, E.ev_value[ev_cur]));
         ev_cur++;
     }
+    if (VAR >= FB_C172X1) avionics_assign(cs, u);   // assign!(vehicle, avionics) precedes every f_ode! (aircraftbase.jl:221-230)
 
     int stage = 0, done = 0;
     unsigned n_rhs = 0;
@@ -179,13 +180,15 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
         }
         bool changed = f_step<VAR, KIN>(xstate, stall, eng, u, y, status);
         if (status != FB_ST_RUNNING) break;
-        if (ctl_due) changed |= avionics_periodic<VAR, KIN>(yf, y, u, cs, E.tables, Dt);
+        bool cmd_changed = false;
+        if (ctl_due) cmd_changed = avionics_periodic<VAR, KIN>(yf, y, u, cs, E.tables, Dt);
         while (ev_cur < ev_end && E.ev_step[ev_cur] <= step_idx) {
             int f = E.ev_field[ev_cur];
             u.set(f, saturate_input(f, E.ev_value[ev_cur]));
             ev_cur++;
             changed = true;
         }
+        if (VAR >= FB_C172X1 && changed) avionics_assign(cs, u);   // an event cannot override a command the control laws own
         if (log_due) {
             const long long smp = step_idx / E.log_every;
             for (int f = 0; f < E.log_n_fields; f++)
@@ -196,6 +199,13 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
 #pragma unroll
             for (int c = 0; c < NX; c++) xs[c] = sx[c * T];
             continue;             // stage stays 0, pending is false
+        }
+        if (VAR != FB_C172S && cmd_changed) {
+            // New actuator commands alone: of the derivative just evaluated (the next step's k1) only
+            // x'.act = (cmd - x.act) / tau depends on them (c172x.jl:44-50), so those seven components are
+            // re-issued to the sink instead of re-evaluating the whole right-hand side.
+#pragma unroll
+            for (int a = 0; a < L::NACT; a++) sink.put(L::ACT + a, (1.0 / 0.05) * (u(FB_U_ACT_THROTTLE + a) - sx[(L::ACT + a) * T]));
         }
         stage = 1;
     }
@@ -221,6 +231,7 @@ rhs_kernel(EnsembleDev E, double* xdot, double* alpha_out, int* wow_out, int* er
     double x[NX], k[NX];
 #pragma unroll
     for (int c = 0; c < NX; c++) x[c] = E.x[(long long)c * E.pitch + i];
+    if (VAR >= FB_C172X1) { CtlState cs; cs.load(E.ctl + i, E.pitch); avionics_assign(cs, u); }
     RhsOut y;
     ArraySink sink; sink.xd = k;
     rhs<VAR, KIN, false>(x, sink, E.stall[i], E.eng[i], u, smem_tb, E.tables.geoid, y, nullptr);
@@ -247,9 +258,36 @@ output_kernel(EnsembleDev E, int field, double* out) {
 #pragma unroll
     for (int c = 0; c < NX; c++) x[c] = E.x[(long long)c * E.pitch + i];
     CtlState cs;
-    if (VAR >= FB_C172X1) cs.load(E.ctl + i, E.pitch);
+    if (VAR >= FB_C172X1) { cs.load(E.ctl + i, E.pitch); avionics_assign(cs, u); }
     YFull yf; RhsOut y; double k[NX];
     ArraySink sink; sink.xd = k;
     rhs<VAR, KIN, true>(x, sink, E.stall[i], E.eng[i], u, smem_tb, E.tables.geoid, y, &yf);
     out[i] = pick_output(yf, E.stall[i], E.eng[i], cs, field);
+}
+
+// f_init!(avionics, vehicle) for every member, from the vehicle outputs at the initial state
+// (c172x_ctl.jl:1246-1250); leaves the controller memory in E.ctl and the commands assigned.
+template <int VAR, int KIN>
+__global__ void __launch_bounds__(FB_BLOCK, 2)
+avionics_init_kernel(EnsembleDev E, double Dt) {
+    typedef Lay<VAR, KIN> L;
+    constexpr int NX = L::NX;
+    extern __shared__ __align__(16) double smem_tb[];
+    stage_tables(smem_tb, E.tables.pack);
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= E.n) return;
+    if (VAR < FB_C172X1) return;
+    MemberIn u; u.u = E.u + i; u.pitch = E.pitch;
+    double x[NX], k[NX];
+#pragma unroll
+    for (int c = 0; c < NX; c++) x[c] = E.x[(long long)c * E.pitch + i];
+    YFull yf; RhsOut y;
+    rhs_with_outputs<VAR, KIN>(x, k, E.stall[i], E.eng[i], u, smem_tb, E.tables.geoid, &y, &yf);
+    CtlState cs;
+    cs.load(E.ctl + i, E.pitch);
+    cs.lon_mode = LON_DIRECT; cs.lat_mode = LAT_DIRECT; cs.h_state = 1;
+    cs.thr_cmd = 0.0; cs.ele_cmd = 0.0; cs.ail_cmd = 0.0; cs.rud_cmd = 0.0;
+    avionics_init(yf, y.wow, u, cs, E.tables, Dt);
+    avionics_assign(cs, u);
+    cs.store(E.ctl + i, E.pitch);
 }

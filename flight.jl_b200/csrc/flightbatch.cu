@@ -58,6 +58,8 @@ template <int VAR, int KIN> struct Ops {
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(output_kernel<VAR, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(avionics_init_kernel<VAR, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES);
+        if (e != cudaSuccess) return e;
         return cudaFuncSetAttribute(trim_kernel<VAR, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES);
     }
     static cudaError_t rhs(fb_sim* s, double* xdot) {
@@ -73,6 +75,11 @@ template <int VAR, int KIN> struct Ops {
     static cudaError_t init(fb_sim* s, const InitSoA& I) {
         int grid = (int)((s->E.n + FB_BLOCK - 1) / FB_BLOCK);
         init_kernel<VAR, KIN><<<grid, FB_BLOCK, 0, s->stream>>>(s->E, I);
+        return cudaGetLastError();
+    }
+    static cudaError_t avionics_init(fb_sim* s) {
+        int grid = (int)((s->E.n + FB_BLOCK - 1) / FB_BLOCK);
+        avionics_init_kernel<VAR, KIN><<<grid, FB_BLOCK, FB_TB_BYTES, s->stream>>>(s->E, s->cfg.Dt);
         return cudaGetLastError();
     }
     static cudaError_t trim(fb_sim* s, const TrimSoA& P, double* ts, double* cost) {
@@ -200,6 +207,7 @@ int32_t fb_create(const fb_config* cfg, fb_handle* out) {
     CK(cudaMemsetAsync(s->d_rhs_count, 0, sizeof(unsigned long long), s->stream));
     CK(cudaMemsetAsync(E.x, 0, sizeof(double) * s->nx * s->pitch, s->stream));
     CK(cudaMemsetAsync(E.ctl, 0, sizeof(double) * FB_CTL_STATE_COUNT * s->pitch, s->stream));
+    fill_kernel<<<(int)((s->pitch + 255) / 256), 256, 0, s->stream>>>(E.ctl + (long long)FB_CTL_ROW_H_STATE * s->pitch, s->pitch, 1.0);   // AltTrackingState.hold
     CK(cudaMemsetAsync(E.stall, 0, s->pitch, s->stream)); CK(cudaMemsetAsync(E.eng, 0, s->pitch, s->stream));
     CK(cudaMemsetAsync(E.status, 0, sizeof(int) * s->pitch, s->stream));
     CK(cudaMemsetAsync(s->d_ev_cursor, 0, sizeof(long long) * s->pitch, s->stream));
@@ -339,8 +347,9 @@ struct Uploader {
     ~Uploader() { cudaStreamSynchronize(s->stream); for (double* d : bufs) cudaFree(d); }
 };
 
-static int32_t after_init(fb_sim* s) {
+static int32_t after_init(fb_sim* s, bool init_avionics) {
     s->n_steps = 0; s->initialised = true;
+    if (init_avionics && s->var_t >= FB_C172X1) CK(FB_DISPATCH(s, avionics_init)(s));   // f_init!(avionics, vehicle)
     CK(cudaMemsetAsync(s->d_ev_cursor, 0, sizeof(long long) * s->pitch, s->stream));
     // log sample 0 = y left by f_init! (sim.jl:405-408)
     for (int f = 0; f < s->E.log_n_fields; f++) {
@@ -372,7 +381,7 @@ int32_t fb_init_trim(fb_handle s, const fb_trim_params_soa* p, double* trim_stat
         CK(cudaStreamSynchronize(s->stream));
     }
     cudaFree(d_ts); cudaFree(d_cost);
-    return after_init(s);
+    return after_init(s, true);
 }
 
 int32_t fb_init(fb_handle s, const fb_init_soa* ic) {
@@ -396,7 +405,7 @@ int32_t fb_init(fb_handle s, const fb_init_soa* ic) {
         CK(FB_DISPATCH(s, init)(s, I));
         CK(cudaStreamSynchronize(s->stream));
     }
-    return after_init(s);
+    return after_init(s, true);
 }
 
 int32_t fb_init_state(fb_handle s, const double* x, const uint8_t* stall, const uint8_t* eng_state) {
@@ -408,7 +417,7 @@ int32_t fb_init_state(fb_handle s, const double* x, const uint8_t* stall, const 
     if (eng_state) CK(cudaMemcpyAsync(s->E.eng, eng_state, s->E.n, cudaMemcpyHostToDevice, s->stream)); else CK(cudaMemsetAsync(s->E.eng, FB_ENG_RUNNING, s->pitch, s->stream));
     CK(cudaMemsetAsync(s->E.status, 0, sizeof(int) * s->pitch, s->stream));
     CK(cudaStreamSynchronize(s->stream));
-    return after_init(s);
+    return after_init(s, false);   // raw state injection keeps the controller memory as it is
 }
 
 int32_t fb_set_input(fb_handle s, int32_t field, const double* values, int64_t stride) {

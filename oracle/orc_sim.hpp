@@ -230,7 +230,8 @@ struct Sim {
 
     void apply_events() {
         while (sched_pos < schedule.size() && schedule[sched_pos].step <= n_steps) {
-            set_input_field(m, schedule[sched_pos].field, schedule[sched_pos].value);
+            if (!set_input_field(m, schedule[sched_pos].field, schedule[sched_pos].value))
+                av.set_input(schedule[sched_pos].field, schedule[sched_pos].value);   // control-law inputs (c172x_ctl.jl:226-237,826-836)
             sched_pos++;
         }
     }
