@@ -94,7 +94,7 @@ class fb_moments(C.Structure):
 EXPORTS = ["fb_api_version", "fb_last_error", "fb_create", "fb_load_tables", "fb_destroy", "fb_sync", "fb_init_trim", "fb_init",
            "fb_init_state", "fb_set_input", "fb_get_input", "fb_schedule_inputs", "fb_step", "fb_run", "fb_time", "fb_nx",
            "fb_get_state", "fb_get_discrete", "fb_get_output", "fb_status", "fb_log_info", "fb_log_times", "fb_log_fetch",
-           "fb_stats", "fb_rhs", "fb_counters", "fb_device_state", "fb_stream", "fb_measure_fp64_peak"]
+           "fb_stats", "fb_rhs", "fb_counters", "fb_linearize", "fb_linearize_dims", "fb_device_state", "fb_stream", "fb_measure_fp64_peak"]
 
 _lib = None
 
@@ -125,6 +125,7 @@ def load_library():
         "fb_rhs": (i32, [vp, _DP]), "fb_counters": (i32, [vp, C.POINTER(i64), C.POINTER(i64)]),
         "fb_device_state": (i32, [vp, C.POINTER(vp), C.POINTER(i64)]), "fb_stream": (i32, [vp, C.POINTER(vp)]),
         "fb_measure_fp64_peak": (i32, [i32, _DP]),
+        "fb_linearize_dims": (i32, [vp, C.POINTER(i32)]), "fb_linearize": (i32, [vp] + [_DP] * 8),
     }
     for name in EXPORTS:
         f = getattr(lib, name)   # AttributeError if the library does not export a declared symbol
@@ -447,6 +448,19 @@ class BatchSimulation:
         m = fb_moments()
         _ck(self._lib.fb_stats(self._h, field, C.byref(m)), self._lib)
         return dict(count=m.count, sum=m.sum, sum_sq=m.sum_sq, min=m.min, max=m.max)
+
+    def linearize(self):
+        """linearize(aircraft, trim) for every member (NED kinematics, trimmed state): dict of A [N, nx, nx], B [N, nx, nu],
+        C [N, ny, nx], D [N, ny, nu] (row = output, column = perturbed variable) and x0, u0, y0, xdot0 [N, n]."""
+        d = (C.c_int32 * 3)()
+        _ck(self._lib.fb_linearize_dims(self._h, d), self._lib)
+        nx, nu, ny = d[0], d[1], d[2]
+        raw = dict(A=np.zeros((nx, nx, self.n)), B=np.zeros((nu, nx, self.n)), C=np.zeros((nx, ny, self.n)), D=np.zeros((nu, ny, self.n)),
+                   x0=np.zeros((nx, self.n)), u0=np.zeros((nu, self.n)), y0=np.zeros((ny, self.n)), xdot0=np.zeros((nx, self.n)))
+        _ck(self._lib.fb_linearize(self._h, *[_dp(raw[k]) for k in ("A", "B", "C", "D", "x0", "u0", "y0", "xdot0")]), self._lib)
+        out = {k: np.transpose(raw[k], (2, 1, 0)) for k in ("A", "B", "C", "D")}      # [col][row][N] -> [N][row][col]
+        out.update({k: raw[k].T for k in ("x0", "u0", "y0", "xdot0")})
+        return out
 
     def counters(self):
         a, b = C.c_int64(), C.c_int64()

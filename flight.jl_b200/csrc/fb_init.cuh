@@ -281,3 +281,105 @@ trim_kernel(EnsembleDev E, TrimSoA P, double* trim_state_out, double* cost_out) 
     if (trim_state_out) for (int j = 0; j < 7; j++) trim_state_out[(long long)j * E.pitch + i] = ts[j];
     if (cost_out) cost_out[i] = c0;
 }
+
+// ------------------------------------------------------------------------------------------ linearization
+// linearize(aircraft, trim_params) (lib/FlightPhysics/src/aircraftbase.jl:292-341 -> linearization.jl:55-111) for every
+// member about its current state and inputs, wind set to zero as the reference does (NoWind()). State / input /
+// output vectors: lib/FlightApps/src/c172/c172s/c172s.jl:269-412 (16 / 4 / 33), c172x/c172x.jl:332-498 (20 / 4 / 38);
+// NED kinematics only (the reference defines them for Vehicle{NED}). Jacobians follow FiniteDiff's default rule
+// (third-party, restated): forward differences, eps_j = max(sqrt(eps) |x_j|, sqrt(eps)).
+// Output layout (member fastest): A[(c * NXS + r) * pitch + i] = dxdot_r / dx_c, likewise B, C, D.
+template <int VAR> struct SS {
+    static constexpr int NX = (VAR == FB_C172S) ? 16 : 20;
+    static constexpr int NU = 4;
+    static constexpr int NY = (VAR == FB_C172S) ? 33 : 38;
+};
+template <int VAR, int KIN>
+FB_DEV void ss_get_x(const double* x, double* o) {
+    typedef Lay<VAR, KIN> L;
+    for (int i = 0; i < 3; i++) { o[i] = x[L::DYN + i]; o[3 + i] = x[L::KINX + i]; o[6 + i] = x[L::DYN + 3 + i]; o[9 + i] = x[L::KINX + 3 + i]; }
+    o[12] = x[L::AERO]; o[13] = x[L::AERO + 1]; o[14] = x[L::ENG]; o[15] = x[L::FUEL];
+    if (VAR != FB_C172S) for (int i = 0; i < 4; i++) o[16 + i] = x[L::ACT + i];
+}
+template <int VAR, int KIN>
+FB_DEV void ss_assign_x(double* x, const double* o) {
+    typedef Lay<VAR, KIN> L;
+    for (int i = 0; i < 3; i++) { x[L::DYN + i] = o[i]; x[L::KINX + i] = o[3 + i]; x[L::DYN + 3 + i] = o[6 + i]; x[L::KINX + 3 + i] = o[9 + i]; }
+    x[L::AERO] = o[12]; x[L::AERO + 1] = o[13]; x[L::ENG] = o[14]; x[L::FUEL] = o[15];
+    if (VAR != FB_C172S) for (int i = 0; i < 4; i++) x[L::ACT + i] = o[16 + i];
+}
+template <int VAR> FB_DEV int ss_u_field(int k) {
+    if (VAR == FB_C172S) return k == 0 ? FB_U_THROTTLE : (k == 1 ? FB_U_AILERON : (k == 2 ? FB_U_ELEVATOR : FB_U_RUDDER));
+    return FB_U_ACT_THROTTLE + k;
+}
+template <int VAR, int KIN>
+FB_DEV void ss_get_y(const double* x, const YFull& y, const MemberIn& u, double* o) {
+    typedef Lay<VAR, KIN> L;
+    int k = 0;
+    o[k++] = y.w_eb_b.x; o[k++] = y.w_eb_b.y; o[k++] = y.w_eb_b.z;
+    o[k++] = y.psi; o[k++] = y.theta; o[k++] = y.phi;
+    o[k++] = x[L::DYN + 3]; o[k++] = x[L::DYN + 4]; o[k++] = x[L::DYN + 5];
+    o[k++] = y.lat; o[k++] = y.lon; o[k++] = y.h_e;
+    o[k++] = y.alpha_filt; o[k++] = y.beta_filt; o[k++] = y.eng_omega;
+    if (VAR != FB_C172S) o[k++] = y.eng_n;
+    o[k++] = x[L::FUEL];
+    if (VAR != FB_C172S) for (int i = 0; i < 4; i++) o[k++] = y.act_pos[i];
+    o[k++] = y.f_c_c.x; o[k++] = y.f_c_c.y; o[k++] = y.f_c_c.z;
+    o[k++] = y.alpha; o[k++] = y.beta; o[k++] = y.EAS; o[k++] = y.TAS;
+    o[k++] = y.v_eb_n.x; o[k++] = y.v_eb_n.y; o[k++] = y.v_eb_n.z;
+    o[k++] = y.chi_gnd; o[k++] = y.gamma_gnd; o[k++] = -y.v_eb_n.z;
+    for (int i = 0; i < 4; i++) o[k++] = u(ss_u_field<VAR>(i));
+}
+
+template <int VAR, int KIN>
+__global__ void __launch_bounds__(FB_BLOCK, 2)
+linearize_kernel(EnsembleDev E, double* A, double* B, double* C, double* D, double* x0o, double* u0o, double* y0o, double* xd0o) {
+    typedef Lay<VAR, KIN> L;
+    constexpr int NX = L::NX, NXS = SS<VAR>::NX, NUS = SS<VAR>::NU, NYS = SS<VAR>::NY;
+    extern __shared__ __align__(16) double smem_tb[];
+    stage_tables(smem_tb, E.tables.pack);
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= E.n) return;
+    if (KIN != FB_NED) return;
+    const long long P = E.pitch;
+    double ul[FB_U__COUNT];                                   // private copy of the inputs: perturbations never reach HBM
+    for (int f = 0; f < FB_U__COUNT; f++) ul[f] = E.u[(long long)f * P + i];
+    ul[FB_U_WIND_N] = 0.0; ul[FB_U_WIND_E] = 0.0; ul[FB_U_WIND_D] = 0.0;
+    MemberIn u; u.u = ul; u.pitch = 1;
+    double x[NX], xd[NX];
+    for (int c = 0; c < NX; c++) x[c] = E.x[(long long)c * P + i];
+    const int stall = E.stall[i], eng = E.eng[i];
+    double x0[NXS], u0[NUS], f0[NXS], y0[NYS];
+    ss_get_x<VAR, KIN>(x, x0);
+    for (int k = 0; k < NUS; k++) u0[k] = ul[ss_u_field<VAR>(k)];
+    YFull yf; RhsOut ro;
+    rhs_with_outputs<VAR, KIN>(x, xd, stall, eng, u, smem_tb, E.tables.geoid, &ro, &yf);
+    ss_get_x<VAR, KIN>(xd, f0);
+    ss_get_y<VAR, KIN>(x, yf, u, y0);
+    for (int r = 0; r < NXS; r++) { if (x0o) x0o[r * P + i] = x0[r]; if (xd0o) xd0o[r * P + i] = f0[r]; }
+    for (int r = 0; r < NUS; r++) if (u0o) u0o[r * P + i] = u0[r];
+    for (int r = 0; r < NYS; r++) if (y0o) y0o[r * P + i] = y0[r];
+    const double rs = 1.4901161193847656e-08;   // sqrt(eps(Float64))
+#pragma unroll 1
+    for (int j = 0; j < NXS + NUS; j++) {
+        double xs[NXS], f[NXS], y[NYS];
+        for (int r = 0; r < NXS; r++) xs[r] = x0[r];
+        for (int k = 0; k < NUS; k++) ul[ss_u_field<VAR>(k)] = u0[k];
+        const bool is_x = j < NXS;
+        const double v0 = is_x ? x0[j] : u0[j - NXS];
+        const double eps = fmax(rs * fabs(v0), rs);
+        if (is_x) xs[j] += eps;
+        else { const int fld = ss_u_field<VAR>(j - NXS); ul[fld] = saturate_input(fld, u0[j - NXS] + eps); }   // Ranged assignment
+        ss_assign_x<VAR, KIN>(x, xs);
+        rhs_with_outputs<VAR, KIN>(x, xd, stall, eng, u, smem_tb, E.tables.geoid, &ro, &yf);
+        ss_get_x<VAR, KIN>(xd, f);
+        ss_get_y<VAR, KIN>(x, yf, u, y);
+        if (is_x) {
+            for (int r = 0; r < NXS; r++) A[((long long)j * NXS + r) * P + i] = (f[r] - f0[r]) / eps;
+            for (int r = 0; r < NYS; r++) C[((long long)j * NYS + r) * P + i] = (y[r] - y0[r]) / eps;
+        } else {
+            for (int r = 0; r < NXS; r++) B[((long long)(j - NXS) * NXS + r) * P + i] = (f[r] - f0[r]) / eps;
+            for (int r = 0; r < NYS; r++) D[((long long)(j - NXS) * NYS + r) * P + i] = (y[r] - y0[r]) / eps;
+        }
+    }
+}

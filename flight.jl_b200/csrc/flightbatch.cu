@@ -60,6 +60,8 @@ template <int VAR, int KIN> struct Ops {
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(avionics_init_kernel<VAR, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(linearize_kernel<VAR, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES);
+        if (e != cudaSuccess) return e;
         return cudaFuncSetAttribute(trim_kernel<VAR, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES);
     }
     static cudaError_t rhs(fb_sim* s, double* xdot) {
@@ -75,6 +77,11 @@ template <int VAR, int KIN> struct Ops {
     static cudaError_t init(fb_sim* s, const InitSoA& I) {
         int grid = (int)((s->E.n + FB_BLOCK - 1) / FB_BLOCK);
         init_kernel<VAR, KIN><<<grid, FB_BLOCK, 0, s->stream>>>(s->E, I);
+        return cudaGetLastError();
+    }
+    static cudaError_t linearize(fb_sim* s, double* A, double* B, double* C, double* D, double* x0, double* u0, double* y0, double* xd0) {
+        int grid = (int)((s->E.n + FB_BLOCK - 1) / FB_BLOCK);
+        linearize_kernel<VAR, KIN><<<grid, FB_BLOCK, FB_TB_BYTES, s->stream>>>(s->E, A, B, C, D, x0, u0, y0, xd0);
         return cudaGetLastError();
     }
     static cudaError_t avionics_init(fb_sim* s) {
@@ -623,6 +630,35 @@ int32_t fb_counters(fb_handle s, int64_t* kernel_launches, int64_t* rhs_evals) {
         CK(cudaStreamSynchronize(s->stream));
         *rhs_evals = (int64_t)c;
     }
+    return FB_OK;
+}
+
+int32_t fb_linearize_dims(fb_handle s, int32_t* dims) {
+    if (!s || !dims) return fail(FB_ERR_ARG, "fb_linearize_dims: null argument");
+    dims[0] = s->cfg.variant == FB_C172S ? 16 : 20; dims[1] = 4; dims[2] = s->cfg.variant == FB_C172S ? 33 : 38;
+    return FB_OK;
+}
+
+int32_t fb_linearize(fb_handle s, double* A, double* B, double* C, double* D, double* x0, double* u0, double* y0, double* xdot0) {
+    if (!s) return fail(FB_ERR_ARG, "null handle");
+    if (!s->initialised) return fail(FB_ERR_STATE, "fb_linearize: not initialised (trim first)");
+    if (s->cfg.kinematics != FB_NED) return fail(FB_ERR_ARG, "fb_linearize: needs NED kinematics (the reference defines XStateSpace for Vehicle{NED} only)");
+    CK(cudaSetDevice(s->cfg.device));
+    int32_t d[3]; fb_linearize_dims(s, d);
+    const long long nxs = d[0], nus = d[1], nys = d[2], P = s->pitch, N = s->E.n;
+    const long long counts[8] = {nxs * nxs, nxs * nus, nys * nxs, nys * nus, nxs, nus, nys, nxs};
+    double* host[8] = {A, B, C, D, x0, u0, y0, xdot0};
+    long long total = 0; for (int k = 0; k < 8; k++) total += counts[k];
+    double* dbuf = nullptr;
+    CK(cudaMalloc(&dbuf, sizeof(double) * total * P));
+    double* dp[8]; long long off = 0;
+    for (int k = 0; k < 8; k++) { dp[k] = dbuf + off * P; off += counts[k]; }
+    cudaError_t e = FB_DISPATCH(s, linearize)(s, dp[0], dp[1], dp[2], dp[3], dp[4], dp[5], dp[6], dp[7]);
+    for (int k = 0; k < 8 && e == cudaSuccess; k++)
+        if (host[k]) e = cudaMemcpy2DAsync(host[k], sizeof(double) * N, dp[k], sizeof(double) * P, sizeof(double) * N, counts[k], cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(dbuf);
+    if (e != cudaSuccess) return fail(FB_ERR_CUDA, std::string("fb_linearize: ") + cudaGetErrorString(e));
     return FB_OK;
 }
 

@@ -1,0 +1,193 @@
+# BatchSimulation.jl — Julia host side of the B200 batched C172 engine (thin `ccall` layer over
+# include/flightbatch.h). SOURCE ONLY in this repository: Julia is not installed in the build image, so this file has
+# not been executed here; the same C ABI is exercised by the Python mirror (flight.jl_b200/__init__.py) in tests/.
+#
+# It mirrors the user surface of Flight.jl for N members stepped in lock-step:
+#   Simulation(world; dt, Δt, t_start, t_end, saveat)  lib/FlightCore/src/sim.jl:183-196  -> BatchSimulation(world, N; ...)
+#   init!(sim, init)                                   sim.jl:390-414                      -> init!(bsim, C172.TrimParameters / C172.Init columns)
+#   step!(sim, Δt, true) / run!(sim)                   sim.jl:386,611                      -> step!(bsim, Δt) / run!(bsim)
+#   TimeSeries(sim)                                    sim.jl:644-704                      -> TimeSeries(bsim, :θ)
+#   sim.t / sim.x / sim.u / sim.y                      sim.jl:265-275                      -> bsim.t, bsim.x, getinput/setinput!, getoutput
+# There is no CPU fallback: every call goes to libflightbatch.so and throws FlightBatchError on a non-zero return.
+module BatchSimulations
+
+export BatchSimulation, FlightBatchError, init!, step!, run!, setinput!, getinput, getoutput, schedule_inputs!,
+       status, stats, linearize, TimeSeriesColumn
+
+const libflightbatch = get(ENV, "FLIGHTBATCH_LIB", joinpath(@__DIR__, "..", "libflightbatch.so"))
+const tables_path = get(ENV, "FLIGHTBATCH_TABLES", joinpath(@__DIR__, "..", "data", "c172_tables.bin"))
+
+struct FlightBatchError <: Exception
+    code::Int32
+    msg::String
+end
+Base.showerror(io::IO, e::FlightBatchError) = print(io, "flightbatch error ", e.code, ": ", e.msg)
+
+last_error() = unsafe_string(ccall((:fb_last_error, libflightbatch), Cstring, ()))
+check(rc::Int32) = rc == 0 ? nothing : throw(FlightBatchError(rc, last_error()))
+
+# enums of include/flightbatch.h (kept in the same order; FB_API_VERSION is checked at load)
+@enum Variant::Int32 C172S = 0 C172X0 = 1 C172X1 = 2 C172X2 = 3
+@enum KinematicsKind::Int32 WA = 0 ECEF = 1 NED = 2
+const FB_API_VERSION = 2
+
+# struct fb_config (must match the C layout field by field)
+struct FbConfig
+    variant::Int32
+    kinematics::Int32
+    n_members::Int64
+    member_offset::Int64
+    dt::Float64
+    Dt::Float64
+    t_start::Float64
+    t_end::Float64
+    device::Int32
+    log_every::Int32
+    log_n_fields::Int32
+    log_fields::NTuple{32,Int32}
+    steps_per_launch::Int32
+end
+
+mutable struct BatchSimulation
+    handle::Ptr{Cvoid}
+    n::Int
+    nx::Int
+    dt::Float64
+    log_fields::Vector{Int32}
+    function BatchSimulation(variant::Variant, kin::KinematicsKind, n::Integer;
+                             dt = 0.02, Δt = dt, t_start = 0.0, t_end = 10000.0, saveat = nothing,
+                             log_fields = Int32[], device = 0, member_offset = 0, steps_per_launch = 0)
+        @assert ccall((:fb_api_version, libflightbatch), Int32, ()) == FB_API_VERSION
+        lf = ntuple(i -> i <= length(log_fields) ? Int32(log_fields[i]) : Int32(0), 32)
+        log_every = (saveat === nothing || isempty(log_fields)) ? 0 : max(1, round(Int, saveat / dt))
+        cfg = Ref(FbConfig(Int32(variant), Int32(kin), n, member_offset, dt, Δt, t_start, t_end, device, log_every,
+                           length(log_fields), lf, steps_per_launch))
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:fb_create, libflightbatch), Int32, (Ref{FbConfig}, Ref{Ptr{Cvoid}}), cfg, h))
+        blob = read(tables_path)
+        GC.@preserve blob check(ccall((:fb_load_tables, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Csize_t), h[], blob, length(blob)))
+        nx = Ref{Int32}(0)
+        check(ccall((:fb_nx, libflightbatch), Int32, (Ptr{Cvoid}, Ref{Int32}), h[], nx))
+        sim = new(h[], n, nx[], dt, collect(Int32, log_fields))
+        finalizer(s -> (s.handle != C_NULL && ccall((:fb_destroy, libflightbatch), Int32, (Ptr{Cvoid},), s.handle); s.handle = C_NULL), sim)
+    end
+end
+
+# struct fb_trim_params_soa: 12 column pointers + payload[5]; C_NULL = the reference default of that field
+const TRIM_FIELDS = (:lat, :lon, :h_e, :psi_nb, :EAS, :gamma_wb_n, :psi_wb_dot, :theta_wb_dot, :beta_a, :fuel_load, :mixture, :flaps,
+                     :m_pilot, :m_copilot, :m_lpass, :m_rpass, :m_baggage)
+
+column(sim::BatchSimulation, v::Real) = fill(Float64(v), sim.n)
+column(sim::BatchSimulation, v::AbstractVector) = (length(v) == sim.n || throw(ArgumentError("column length != N")); Vector{Float64}(v))
+
+"""
+    init!(sim; EAS = ..., h_e = ..., flaps = ..., ...)   # init!(sim, C172.TrimParameters(...)) for every member
+
+Each keyword is a scalar (broadcast) or a length-N vector. Returns `(success::BitVector, trim_state::Matrix (N×7), cost)`.
+Members whose trim does not reach the reference's stop value (cost ≤ 1e-16, c172.jl:927) get status 6, like the
+reference's `success = false` + warning (c172.jl:934-940).
+"""
+function init!(sim::BatchSimulation; kw...)
+    cols = Dict{Symbol,Vector{Float64}}(k => column(sim, v) for (k, v) in kw)
+    all(k -> k in TRIM_FIELDS, keys(cols)) || throw(ArgumentError("unknown TrimParameters field"))
+    ptrs = [haskey(cols, f) ? pointer(cols[f]) : Ptr{Float64}(C_NULL) for f in TRIM_FIELDS]
+    ts = Matrix{Float64}(undef, sim.n, 7)
+    cost = Vector{Float64}(undef, sim.n)
+    GC.@preserve cols ptrs begin
+        check(ccall((:fb_init_trim, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{Ptr{Float64}}, Ptr{Float64}, Ptr{Float64}),
+                    sim.handle, ptrs, ts, cost))
+    end
+    (status(sim) .!= 6, ts, cost)
+end
+
+step!(sim::BatchSimulation, Δt::Real = sim.dt) = check(ccall((:fb_step, libflightbatch), Int32, (Ptr{Cvoid}, Float64), sim.handle, Δt))
+run!(sim::BatchSimulation) = check(ccall((:fb_run, libflightbatch), Int32, (Ptr{Cvoid},), sim.handle))
+Base.wait(sim::BatchSimulation) = check(ccall((:fb_sync, libflightbatch), Int32, (Ptr{Cvoid},), sim.handle))
+
+function Base.getproperty(sim::BatchSimulation, s::Symbol)
+    if s === :t
+        t = Ref(0.0); n = Ref{Int64}(0)
+        check(ccall((:fb_time, libflightbatch), Int32, (Ptr{Cvoid}, Ref{Float64}, Ref{Int64}), getfield(sim, :handle), t, n))
+        return t[]
+    elseif s === :x   # N × nx, column c = component c of `X(md)` (SURVEY.md App. A)
+        x = Matrix{Float64}(undef, getfield(sim, :n), getfield(sim, :nx))
+        check(ccall((:fb_get_state, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{Float64}), getfield(sim, :handle), x))
+        return x
+    else
+        return getfield(sim, s)
+    end
+end
+
+# mdl.<...>.u.<field> = value : `field` is an fb_input id (see include/flightbatch.h), value a scalar or an N-vector
+function setinput!(sim::BatchSimulation, field::Integer, v::Real)
+    r = Ref(Float64(v))
+    check(ccall((:fb_set_input, libflightbatch), Int32, (Ptr{Cvoid}, Int32, Ref{Float64}, Int64), sim.handle, field, r, 0))
+end
+function setinput!(sim::BatchSimulation, field::Integer, v::AbstractVector)
+    c = column(sim, v)
+    check(ccall((:fb_set_input, libflightbatch), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64), sim.handle, field, c, 1))
+end
+function getinput(sim::BatchSimulation, field::Integer)
+    out = Vector{Float64}(undef, sim.n)
+    check(ccall((:fb_get_input, libflightbatch), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}), sim.handle, field, out)); out
+end
+function getoutput(sim::BatchSimulation, field::Integer)
+    out = Vector{Float64}(undef, sim.n)
+    check(ccall((:fb_get_output, libflightbatch), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}), sim.handle, field, out)); out
+end
+
+"declarative replacement of `user_callback!` (sim.jl:331-341): piecewise-constant per-member inputs"
+function schedule_inputs!(sim::BatchSimulation, member::Vector{Int64}, step::Vector{Int64}, field::Vector{Int32}, value::Vector{Float64})
+    n = length(member)
+    @assert length(step) == n && length(field) == n && length(value) == n
+    check(ccall((:fb_schedule_inputs, libflightbatch), Int32, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int32}, Ptr{Float64}),
+                sim.handle, n, member, step, field, value))
+end
+
+function status(sim::BatchSimulation)
+    st = Vector{Int32}(undef, sim.n)
+    check(ccall((:fb_status, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{Int32}), sim.handle, st)); st
+end
+
+struct Moments
+    count::Int64
+    sum::Float64
+    sum_sq::Float64
+    min::Float64
+    max::Float64
+end
+function stats(sim::BatchSimulation, field::Integer)
+    m = Ref(Moments(0, 0.0, 0.0, 0.0, 0.0))
+    check(ccall((:fb_stats, libflightbatch), Int32, (Ptr{Cvoid}, Int32, Ref{Moments}), sim.handle, field, m)); m[]
+end
+
+"TimeSeries(sim) column: `(t, values)` with `values` of size N × n_samples for one logged `fb_output` field"
+function TimeSeriesColumn(sim::BatchSimulation, field::Integer)
+    ns = Ref{Int64}(0); nf = Ref{Int32}(0)
+    check(ccall((:fb_log_info, libflightbatch), Int32, (Ptr{Cvoid}, Ref{Int64}, Ref{Int32}), sim.handle, ns, nf))
+    t = Vector{Float64}(undef, ns[]); v = Matrix{Float64}(undef, sim.n, ns[])
+    check(ccall((:fb_log_times, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{Float64}), sim.handle, t))
+    check(ccall((:fb_log_fetch, libflightbatch), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}), sim.handle, field, v))
+    (t, v)
+end
+
+"""
+    linearize(sim)  ->  (A, B, C, D, x0, u0, y0)  # linearize(aircraft, trim_params), aircraftbase.jl:292-341
+
+Forward-difference Jacobians of every member about its current (trimmed) state; arrays are `N × rows × cols`
+(member fastest, exactly the layout `fb_linearize` writes). Needs NED kinematics, like the reference's
+`XStateSpace` (c172s.jl:269-412, c172x.jl:332-498).
+"""
+function linearize(sim::BatchSimulation)
+    d = zeros(Int32, 3)
+    check(ccall((:fb_linearize_dims, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{Int32}), sim.handle, d))
+    nxs, nus, nys = d
+    A = Array{Float64}(undef, sim.n, nxs, nxs); B = Array{Float64}(undef, sim.n, nxs, nus)
+    C = Array{Float64}(undef, sim.n, nys, nxs); D = Array{Float64}(undef, sim.n, nys, nus)
+    x0 = Matrix{Float64}(undef, sim.n, nxs); u0 = Matrix{Float64}(undef, sim.n, nus); y0 = Matrix{Float64}(undef, sim.n, nys)
+    check(ccall((:fb_linearize, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                sim.handle, A, B, C, D, x0, u0, y0))
+    (A, B, C, D, x0, u0, y0)
+end
+
+end # module

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FB_API_VERSION 1
+#define FB_API_VERSION 2
 
 /* error codes */
 #define FB_OK 0
@@ -214,6 +214,16 @@ int32_t fb_log_info(fb_handle h, int64_t* n_samples, int32_t* n_fields);
 int32_t fb_log_times(fb_handle h, double* t);                        /* [n_samples] */
 int32_t fb_log_fetch(fb_handle h, int32_t field, double* out);       /* [n_samples][N] */
 int32_t fb_stats(fb_handle h, int32_t field, fb_moments* out);
+
+/* ---- linearisation -------------------------------------------------------------------------
+ * linearize(aircraft, trim_params) : lib/FlightPhysics/src/aircraftbase.jl:292-341 -> linearization.jl:55-111, for every
+ * member about its current (trimmed) state and inputs with the wind set to zero (the reference linearises under NoWind()).
+ * NED kinematics only. dims = {nx, nu, ny} = {16, 4, 33} (C172S, c172s.jl:269-412) or {20, 4, 38} (C172X, c172x.jl:332-498).
+ * Forward-difference Jacobians with FiniteDiff's default step max(sqrt(eps)|x_j|, sqrt(eps)) (linearization.jl:4,104-107).
+ * Layout, member fastest: A is [nx cols][nx rows][N] (a Julia Array{Float64,3}(undef, N, nx, nx) indexed [i, row, col]),
+ * B [nu][nx][N], C [nx][ny][N], D [nu][ny][N]; x0 [nx][N], u0 [nu][N], y0 [ny][N], xdot0 [nx][N]. Any pointer may be NULL. */
+int32_t fb_linearize_dims(fb_handle h, int32_t dims[3]);
+int32_t fb_linearize(fb_handle h, double* A, double* B, double* C, double* D, double* x0, double* u0, double* y0, double* xdot0);
 
 /* ---- test hooks: the Modeling protocol pieces, for parity checks in isolation ---------- */
 /* f_ode!(world) at the current state: writes ẋ [nx][N] (modeling.jl:201-254, world.jl:26-32) */

@@ -48,6 +48,8 @@ def _load(name):
         "orc_sim_rhs": (i32, [vp]),
         "orc_sim_step": (i32, [vp, i64]),
         "orc_sim_steps_taken": (i64, [vp]),
+        "orc_sim_linearize_dims": (None, [vp, C.POINTER(i32)]),
+        "orc_sim_linearize": (i32, [vp, dp, dp, dp, dp, dp, dp, dp, dp]),
         "orc_ops_reset": (None, []),
         "orc_ops_get": (None, [C.POINTER(C.c_ulonglong)]),
         "orc_is_counting": (i32, []),
@@ -202,6 +204,17 @@ class Sim:
 
     def step(self, n=1):
         return self.lib.orc_sim_step(self.h, int(n))
+
+    def linearize(self):
+        """linearize(aircraft, trim) about the current state (NED kinematics): dict of A, B, C, D (row-major), x0, u0, y0, xdot0."""
+        d = (C.c_int * 3)()
+        self.lib.orc_sim_linearize_dims(self.h, d)
+        nx, nu, ny = d[0], d[1], d[2]
+        r = dict(A=np.zeros((nx, nx)), B=np.zeros((nx, nu)), C=np.zeros((ny, nx)), D=np.zeros((ny, nu)),
+                 x0=np.zeros(nx), u0=np.zeros(nu), y0=np.zeros(ny), xdot0=np.zeros(nx))
+        rc = self.lib.orc_sim_linearize(self.h, *[_dp(r[k]) for k in ("A", "B", "C", "D", "x0", "u0", "y0", "xdot0")])
+        assert rc == 0, rc
+        return r
 
     def want_y_extra(self, on=True):
         self.lib.orc_sim_want_y_extra(self.h, 1 if on else 0)

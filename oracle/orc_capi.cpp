@@ -265,6 +265,12 @@ int orc_sim_step(void* s, long long n) {
     return S->m.status;
 }
 long long orc_sim_steps_taken(void* s) { return ((Sim*)s)->n_steps; }
+// linearize(aircraft, trim) about the current state: dims[3] = nx, nu, ny; matrices row-major
+void orc_sim_linearize_dims(void* s, int* dims) { SSDims d = ss_dims(((Sim*)s)->m.L.variant); dims[0] = d.nx; dims[1] = d.nu; dims[2] = d.ny; }
+int orc_sim_linearize(void* s, double* A, double* B, double* C, double* D, double* x0, double* u0, double* y0, double* xd0) {
+    Sim* S = (Sim*)s;
+    try { S->av.assign(S->m); return linearize_member(S->m, *S->W, A, B, C, D, x0, u0, y0, xd0) ? 0 : -1; } catch (OrcTermination& e) { return e.code; }
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // Component-level hooks used by tests/ to replay the reference's own unit tests against the oracle.

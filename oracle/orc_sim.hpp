@@ -280,3 +280,98 @@ struct Sim {
         apply_events();                        // user callback slot
     }
 };
+
+// ---------------------------------------------------------------------------------- linearization
+// linearize(vehicle, trim_params): FP/aircraftbase.jl:292-341 -> FP/linearization.jl:55-111, with the state / input /
+// output vectors of FA/c172/c172s/c172s.jl:269-412 (16 / 4 / 33) and FA/c172/c172x/c172x.jl:332-498 (20 / 4 / 38); NED
+// kinematics only. Jacobians by FiniteDiff.finite_difference_jacobian! defaults (third-party, compat "2.28.1", source
+// not under /root/reference; published rule restated): forward differences, column j uses
+// eps_j = max(sqrt(eps(Float64)) * |x_j|, sqrt(eps(Float64))) and J[:, j] = (f(x + eps_j e_j) - f(x)) / eps_j.
+struct SSDims { int nx, nu, ny; };
+inline SSDims ss_dims(int variant) { SSDims d; if (variant == VAR_C172S) { d.nx = 16; d.nu = 4; d.ny = 33; } else { d.nx = 20; d.nu = 4; d.ny = 38; } return d; }
+
+inline void ss_get_x(const Layout& L, const real* x, real* o) {   // XStateSpace(x_vehicle)
+    for (int i = 0; i < 3; i++) o[i] = x[L.dyn + i];                 // p q r
+    for (int i = 0; i < 3; i++) o[3 + i] = x[L.kinx + i];            // psi theta phi
+    for (int i = 0; i < 3; i++) o[6 + i] = x[L.dyn + 3 + i];         // v_x v_y v_z
+    for (int i = 0; i < 3; i++) o[9 + i] = x[L.kinx + 3 + i];        // lat lon h
+    o[12] = x[L.aero]; o[13] = x[L.aero + 1]; o[14] = x[L.eng]; o[15] = x[L.fuel];
+    if (L.variant != VAR_C172S) for (int i = 0; i < 4; i++) o[16 + i] = x[L.act + i];   // thr ail ele rud
+}
+inline void ss_assign_x(const Layout& L, real* x, const real* o) {   // assign_x_ss!
+    for (int i = 0; i < 3; i++) x[L.dyn + i] = o[i];
+    for (int i = 0; i < 3; i++) x[L.kinx + i] = o[3 + i];
+    for (int i = 0; i < 3; i++) x[L.dyn + 3 + i] = o[6 + i];
+    for (int i = 0; i < 3; i++) x[L.kinx + 3 + i] = o[9 + i];
+    x[L.aero] = o[12]; x[L.aero + 1] = o[13]; x[L.eng] = o[14]; x[L.fuel] = o[15];
+    if (L.variant != VAR_C172S) for (int i = 0; i < 4; i++) x[L.act + i] = o[16 + i];
+}
+inline void ss_get_u(const Member& m, real* o) {   // UStateSpace(vehicle): throttle, aileron, elevator, rudder
+    if (m.L.variant == VAR_C172S) { o[0] = m.u.throttle; o[1] = m.u.aileron; o[2] = m.u.elevator; o[3] = m.u.rudder; }
+    else for (int i = 0; i < 4; i++) o[i] = m.u.act_cmd[i];
+}
+inline void ss_assign_u(Member& m, const real* o) {   // assign_u_ss!: Ranged fields saturate on assignment
+    if (m.L.variant == VAR_C172S) {
+        m.u.throttle = rclamp(o[0], 0.0, 1.0); m.u.aileron = rclamp(o[1], -1.0, 1.0);
+        m.u.elevator = rclamp(o[2], -1.0, 1.0); m.u.rudder = rclamp(o[3], -1.0, 1.0);
+    } else for (int i = 0; i < 4; i++) m.u.act_cmd[i] = rclamp(o[i], ACT_LO[i], ACT_HI[i]);
+}
+inline void ss_get_y(const Member& m, real* o) {   // YStateSpace(vehicle)
+    const VehicleY& y = m.y;
+    int k = 0;
+    o[k++] = y.kin.w_eb_b.x; o[k++] = y.kin.w_eb_b.y; o[k++] = y.kin.w_eb_b.z;
+    o[k++] = y.kin.e_nb.psi; o[k++] = y.kin.e_nb.theta; o[k++] = y.kin.e_nb.phi;
+    o[k++] = y.kin.v_eb_b.x; o[k++] = y.kin.v_eb_b.y; o[k++] = y.kin.v_eb_b.z;
+    o[k++] = y.kin.ll.lat; o[k++] = y.kin.ll.lon; o[k++] = y.kin.h_e;
+    o[k++] = y.aero.alpha_filt; o[k++] = y.aero.beta_filt; o[k++] = y.eng.omega;
+    if (m.L.variant != VAR_C172S) o[k++] = y.eng.n;
+    o[k++] = y.fuel.x_avail;
+    if (m.L.variant != VAR_C172S) for (int i = 0; i < 4; i++) o[k++] = y.act.pos[i];
+    o[k++] = y.dyn.f_c_c.x; o[k++] = y.dyn.f_c_c.y; o[k++] = y.dyn.f_c_c.z;
+    o[k++] = y.aero.alpha; o[k++] = y.aero.beta; o[k++] = y.air.EAS; o[k++] = y.air.TAS;
+    o[k++] = y.kin.v_eb_n.x; o[k++] = y.kin.v_eb_n.y; o[k++] = y.kin.v_eb_n.z;
+    o[k++] = y.kin.chi_gnd; o[k++] = y.kin.gamma_gnd; o[k++] = -y.kin.v_eb_n.z;
+    real u[4]; ss_get_u(m, u);
+    for (int i = 0; i < 4; i++) o[k++] = u[i];
+}
+
+// A [nx][nx], B [nx][nu], C [ny][nx], D [ny][nu] row-major; x0, u0, y0, xdot0 as named. Evaluated about the member's
+// current state and inputs with the wind set to zero (the reference linearizes under NoWind()); the member is restored.
+inline bool linearize_member(Member& m, const World& W, double* A, double* B, double* C, double* D,
+                             double* x0o, double* u0o, double* y0o, double* xd0o) {
+    if (m.L.kin != KIN_NED) return false;
+    const SSDims d = ss_dims(m.L.variant);
+    const int nx = m.L.nx;
+    real xsave[ORC_NX_MAX]; for (int i = 0; i < nx; i++) xsave[i] = m.x[i];
+    const Inputs usave = m.u; const bool wy = m.want_y_extra;
+    m.want_y_extra = true;
+    m.u.wind_n = V3(0.0, 0.0, 0.0);
+    real x0[20], u0[4], f0[20], y0[38];
+    ss_get_x(m.L, m.x, x0); ss_get_u(m, u0);
+    auto eval = [&](const real* xs, const real* us, real* f, real* y) {
+        ss_assign_x(m.L, m.x, xs); ss_assign_u(m, us);
+        m.f_ode(W);
+        ss_get_x(m.L, m.xdot, f); ss_get_y(m, y);
+    };
+    eval(x0, u0, f0, y0);
+    const double rs = std::sqrt(std::numeric_limits<double>::epsilon());
+    for (int j = 0; j < d.nx + d.nu; j++) {
+        real xs[20], us[4], f[20], y[38];
+        for (int i = 0; i < d.nx; i++) xs[i] = x0[i];
+        for (int i = 0; i < d.nu; i++) us[i] = u0[i];
+        const bool is_x = j < d.nx;
+        const double v0 = val(is_x ? x0[j] : u0[j - d.nx]);
+        const double eps = std::max(rs * std::fabs(v0), rs);
+        if (is_x) xs[j] = xs[j] + eps; else us[j - d.nx] = us[j - d.nx] + eps;
+        eval(xs, us, f, y);
+        for (int r = 0; r < d.nx; r++) { double v = (val(f[r]) - val(f0[r])) / eps; if (is_x) A[r * d.nx + j] = v; else B[r * d.nu + (j - d.nx)] = v; }
+        for (int r = 0; r < d.ny; r++) { double v = (val(y[r]) - val(y0[r])) / eps; if (is_x) C[r * d.nx + j] = v; else D[r * d.nu + (j - d.nx)] = v; }
+    }
+    for (int i = 0; i < d.nx; i++) { if (x0o) x0o[i] = val(x0[i]); if (xd0o) xd0o[i] = val(f0[i]); }
+    for (int i = 0; i < d.nu; i++) if (u0o) u0o[i] = val(u0[i]);
+    for (int i = 0; i < d.ny; i++) if (y0o) y0o[i] = val(y0[i]);
+    for (int i = 0; i < nx; i++) m.x[i] = xsave[i];
+    m.u = usave; m.want_y_extra = wy;
+    m.f_ode(W);
+    return true;
+}
