@@ -19,7 +19,7 @@ import re
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libflightbatch.so")
+LIB_PATH = os.environ.get("FLIGHTBATCH_LIB") or os.path.join(_HERE, "libflightbatch.so")   # override: development builds only
 TABLES_PATH = os.path.join(_HERE, "data", "c172_tables.bin")
 HEADER_PATH = os.path.join(_HERE, "..", "include", "flightbatch.h")
 

@@ -79,11 +79,11 @@ __host__ __device__ inline double saturate_input(int f, double v) {   // Ranged{
 //   stage 3: x += dt/6 (acc+k)  xs = x
 // written with per-thread coefficients (ca, cb, cx) so that one code path serves all four stages:
 //   acc' = cb*k + ca*acc ; xs = x + cx * (last ? acc' : k) ; x = xs if last
+template <int T>        // T: column stride in doubles (compile-time -> immediate shared-memory offsets)
 struct RkSink {
     double* xs;          // stage state, registers
     double* sx;          // shared: step-start state column of this thread  (stride T doubles)
     double* sacc;        // shared: accumulator column of this thread
-    int T;
     double ca, cb, cx;
     bool last;
     FB_DEV void put(int c, double k) {
@@ -95,8 +95,9 @@ struct RkSink {
         if (last) sx[c * T] = xn;
     }
 };
+template <int T>
 struct SmemState {       // f_step! view of the step-start state column
-    double* sx; int T;
+    double* sx;
     FB_DEV double get(int c) const { return sx[c * T]; }
     FB_DEV void set(int c, double v) { sx[c * T] = v; }
 };
@@ -109,7 +110,15 @@ struct SmemState {       // f_step! view of the step-start state column
 // RHS reads, in which case it is evaluated again (as the reference always does). The loop below has ONE
 // call site of the RHS; each thread carries its own stage counter, so members that need the extra
 // evaluation simply run one iteration out of phase with their warp neighbours.
-// Dynamic shared memory: [table pack | x columns NX*T | acc columns NX*T].
+// Dynamic shared memory: [table pack | x columns NX*T | acc columns NX*T], T = StepShape::T (a compile-time column
+// stride, so every column access is base + immediate); the CTA may be launched with fewer than T threads.
+template <int VAR, int KIN>
+struct StepShape {
+    static constexpr int NX = Lay<VAR, KIN>::NX;
+    static constexpr int FIT = (int)((232448 - FB_TB_BYTES - 1024) / (sizeof(double) * 2 * NX)) / 32 * 32;   // 227 KB per CTA
+    static constexpr int T = FIT < FB_STEP_MAX_BLOCK ? FIT : FB_STEP_MAX_BLOCK;
+    static constexpr size_t SMEM = FB_TB_BYTES + sizeof(double) * 2 * NX * T;
+};
 template <int VAR, int KIN>
 __global__ void __launch_bounds__(FB_STEP_MAX_BLOCK, 1)
 step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic_every, double Dt,
@@ -118,9 +127,9 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
     constexpr int NX = L::NX;
     extern __shared__ __align__(16) double smem[];
     double* smem_tb = smem;
-    const int T = blockDim.x;
+    constexpr int T = StepShape<VAR, KIN>::T;
     stage_tables(smem_tb, E.tables.pack);
-    long long i = (long long)blockIdx.x * T + threadIdx.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= E.n) return;
     int status = E.status[i];
     if (status != FB_ST_RUNNING) return;
@@ -147,8 +156,8 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
     unsigned n_rhs = 0;
     bool pending = false;
     const double h2 = 0.5 * dt, h6 = dt * (1.0 / 6.0);
-    RkSink sink; sink.xs = xs; sink.sx = sx; sink.sacc = sacc; sink.T = T;
-    SmemState xstate; xstate.sx = sx; xstate.T = T;
+    RkSink<T> sink; sink.xs = xs; sink.sx = sx; sink.sacc = sacc;
+    SmemState<T> xstate; xstate.sx = sx;
     for (;;) {
         // coefficients of this thread's current stage
         sink.ca = (stage == 0) ? 0.0 : 1.0;

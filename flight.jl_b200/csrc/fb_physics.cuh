@@ -30,11 +30,16 @@
 #include "../../include/flightbatch.h"
 
 // ------------------------------------------------------------------------------------------- layout
-template <int VAR, int KIN>
+// AIR = true is the integrator's compact layout for members clear of the terrain: the six friction-regulator states
+// of the landing gear are identically zero there (landinggear.jl:479-483 resets them while a strut is unloaded), so
+// they get no column; ROW maps a compact component to its row of the ensemble state in HBM.
+template <int VAR, int KIN, bool AIR = false>
 struct Lay {
-    static constexpr int AERO = 0, LDG = 2, FUEL = 8, ENG = 9, ACT = 12;
+    static constexpr int NLDG = AIR ? 0 : 6;
+    static constexpr int AERO = 0, LDG = 2, FUEL = 2 + NLDG, ENG = FUEL + 1, ACT = ENG + 3;
     static constexpr int NACT = (VAR == FB_C172S) ? 0 : 7;
-    static constexpr int KINX = 12 + NACT;
+    static constexpr int KINX = ACT + NACT;
+    static constexpr int row(int c) { return (AIR && c >= 2) ? c + 6 : c; }
     static constexpr int NKIN = (KIN == FB_WA) ? 9 : (KIN == FB_ECEF ? 8 : 6);
     static constexpr int DYN = KINX + NKIN;
     static constexpr int NX = DYN + 6;
@@ -62,8 +67,10 @@ struct RhsOut {
     double alpha;       // unclamped aerodynamic AoA (aero.y.α, c172.jl:324,367)
     int wow;            // bit i = strut i weight-on-wheels
     int crash;          // 2 bits per strut: 0 none, 1 strut/terrain angle > 60 deg, 2 compression rate > 10 m/s (landinggear.jl:331-347)
-    int err;            // 0 none, FB_ST_BOUNDS / FB_ST_CONTACT_ASSERT (would have thrown inside f_ode!)
+    int err;            // 0 none, FB_ST_BOUNDS / FB_ST_CONTACT_ASSERT (would have thrown inside f_ode!), FB_NEED_GROUND
+    int gnd;            // a strut was evaluated (the aircraft is within the height gate of the terrain)
 };
+#define FB_NEED_GROUND 64   // internal: an AIR-layout evaluation came within the height gate; the member goes to the full kernel
 
 // everything the output pass / log / control laws may ask for (filled only by the WY=true instantiation)
 struct YFull {
@@ -342,11 +349,11 @@ FB_DEV double interp_2x9_line(const double* y, double n0, double n1, double x0, 
 
 // ------------------------------------------------------------------------------------------- the RHS
 // x: state (read-only; every component is read before its derivative is put into the sink).
-template <int VAR, int KIN, bool WY, class Sink>
+template <int VAR, int KIN, bool WY, bool AIR = false, class Sink>
 FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const MemberIn& u,
                 const double* __restrict__ tb, const float* __restrict__ geoid, RhsOut& out, YFull* yf) {
-    typedef Lay<VAR, KIN> L;
-    out.wow = 0; out.crash = 0; out.err = 0;
+    typedef Lay<VAR, KIN, AIR> L;
+    out.wow = 0; out.crash = 0; out.err = 0; out.gnd = 0;
     Kin k;
     k.w_eb_b = mk3(x[L::DYN], x[L::DYN + 1], x[L::DYN + 2]);
     k.v_eb_b = mk3(x[L::DYN + 3], x[L::DYN + 4], x[L::DYN + 5]);
@@ -557,17 +564,21 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const Mem
     // ------------------------------------------------------------------ landing gear
     {
         double elev = u(FB_U_TRN_ELEVATION);
-        if (k.h_o - elev > 4.0) {
+        if (AIR) {
+            // compact layout: regulator states are zero and stay zero while the gate holds; otherwise hand the member over
+            if (!(k.h_o - elev > 4.0)) out.err = FB_NEED_GROUND;
+        } else if (k.h_o - elev > 4.0) {
             // every strut attachment is < 2.4 m from Ob: no wheel can reach the terrain; regulators just leak
 #pragma unroll
             for (int i = 0; i < 6; i++) sink.put(L::LDG + i, -0.2 * x[L::LDG + i]);
             if (WY) { for (int i = 0; i < 3; i++) { yf->xi[i] = 0.0; yf->F_dmp[i] = 0.0; } }
         } else {
+            out.gnd = 1;
             int surface = (int)u(FB_U_TRN_SURFACE);
             bool eng = u(FB_U_STEERING_ENGAGED) != 0.0;
             // the out-of-line strut code works on copies: taking addresses of k / F / tau / out themselves would pin
             // them in local memory on the airborne fast path as well
-            Kin kk = k; d3 Fl = mk3(0, 0, 0), taul = mk3(0, 0, 0); RhsOut ol; ol.wow = 0; ol.crash = 0; ol.err = 0; ol.alpha = 0.0;
+            Kin kk = k; d3 Fl = mk3(0, 0, 0), taul = mk3(0, 0, 0); RhsOut ol; ol.wow = 0; ol.crash = 0; ol.err = 0; ol.alpha = 0.0; ol.gnd = 1;
             double xd[6];
             ldg_unit(kk, geoid, elev, surface, mk3(-0.381, -1.092, 1.902), 39404, 9340, 9340, false, false, 0.0, br_l,
                      x[L::LDG], x[L::LDG + 1], xd[0], xd[1], Fl, taul, 0, ol, WY ? &yf->xi[0] : nullptr, WY ? &yf->F_dmp[0] : nullptr);
@@ -791,9 +802,9 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const Mem
 // evaluation at the post-step state. X is any indexable state holder (registers or a shared-memory column).
 // Returns true when something the RHS reads changed (so that the first-same-as-last derivative must be
 // re-evaluated).
-template <int VAR, int KIN, class X>
+template <int VAR, int KIN, bool AIR = false, class X>
 FB_DEV bool f_step(X& x, int& stall, int& eng_state, const MemberIn& u, const RhsOut& y, int& status) {
-    typedef Lay<VAR, KIN> L;
+    typedef Lay<VAR, KIN, AIR> L;
     bool changed = false;
     if (KIN == FB_WA) {   // kinematics.jl:114-118,226-229
 #pragma unroll
@@ -808,7 +819,7 @@ FB_DEV bool f_step(X& x, int& stall, int& eng_state, const MemberIn& u, const Rh
     if (y.alpha > 0.36) stall = 1; else if (y.alpha < 0.09) stall = 0;   // c172.jl:375-384
     changed |= (stall != st0);
 #pragma unroll
-    for (int leg = 0; leg < 3; leg++) {
+    for (int leg = 0; leg < (AIR ? 0 : 3); leg++) {
         int cr = (y.crash >> (2 * leg)) & 3;                             // landinggear.jl:331-347
         if (cr) { status = (cr == 1) ? FB_ST_CRASH_ANGLE : FB_ST_CRASH_RATE; return changed; }
         if (!(y.wow & (1 << leg))) {                                     // landinggear.jl:479-483

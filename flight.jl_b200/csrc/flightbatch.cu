@@ -46,12 +46,13 @@ template <int VAR, int KIN> struct Ops {
     static cudaError_t step(fb_sim* s, long long step0, int n) {
         int T = s->step_block;
         int grid = (int)((s->E.n + T - 1) / T);
-        size_t smem = FB_TB_BYTES + sizeof(double) * 2 * Lay<VAR, KIN>::NX * T;
+        size_t smem = StepShape<VAR, KIN>::SMEM;
         step_kernel<VAR, KIN><<<grid, T, smem, s->stream>>>(s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count);
         return cudaGetLastError();
     }
+    static int step_tmax() { return StepShape<VAR, KIN>::T; }
     static cudaError_t prepare(fb_sim* s) {
-        size_t smem = FB_TB_BYTES + sizeof(double) * 2 * Lay<VAR, KIN>::NX * s->step_block;
+        size_t smem = StepShape<VAR, KIN>::SMEM;
         cudaError_t e = cudaFuncSetAttribute(step_kernel<VAR, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(rhs_kernel<VAR, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES);
@@ -245,9 +246,7 @@ int32_t fb_create(const fb_config* cfg, fb_handle* out) {
     {
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, cfg->device));
-        size_t smem_max = prop.sharedMemPerBlockOptin;
-        int tmax = (int)((smem_max - FB_TB_BYTES - 1024) / (sizeof(double) * 2 * s->nx)) / 32 * 32;
-        tmax = std::min(tmax, FB_STEP_MAX_BLOCK);
+        int tmax = FB_DISPATCH(s, step_tmax)();   // compile-time column stride of the instantiation (fits 227 KB)
         int sms = prop.multiProcessorCount;
         int T = (int)std::min<long long>(tmax, (N + 31) / 32 * 32);
         long long waves = ((N + T - 1) / T + sms - 1) / sms;
