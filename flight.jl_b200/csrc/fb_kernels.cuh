@@ -4,12 +4,16 @@
 // every derivative into both as soon as the RHS produces it; ensemble state in HBM is struct-of-arrays
 // (component-major, member fastest) and is touched once per launch of K fused steps.
 #pragma once
+#include <climits>
 #include "fb_physics.cuh"
 #include "fb_avionics.cuh"
 
 #define FB_BLOCK 128          // block size of the light kernels (rhs / output / init / trim)
 #ifndef FB_STEP_MAX_BLOCK
 #define FB_STEP_MAX_BLOCK 448 // 14 warps per SM: 4 warps on an SM sub-partition -> 128 registers per thread
+#endif
+#ifndef FB_STEP_MAX_BLOCK_AIR
+#define FB_STEP_MAX_BLOCK_AIR 448
 #endif
 
 struct EnsembleDev {
@@ -76,28 +80,34 @@ __host__ __device__ inline double saturate_input(int f, double v) {   // Ranged{
 //   stage 0: acc = k            xs = x + dt/2 k
 //   stage 1: acc += 2k          xs = x + dt/2 k
 //   stage 2: acc += 2k          xs = x + dt k
-//   stage 3: x += dt/6 (acc+k)  xs = x
+//   stage 3: x* = x + dt/6 (acc+k), written over acc;  xs = x*
 // written with per-thread coefficients (ca, cb, cx) so that one code path serves all four stages:
-//   acc' = cb*k + ca*acc ; xs = x + cx * (last ? acc' : k) ; x = xs if last
+//   acc' = cb*k + ca*acc ; xn = x + cx * (last ? acc' : k) ; acc column <- last ? xn : acc' ; xs = xn
+// The step-start column is never written by a stage: after a successful stage-3 evaluation the two column pointers
+// are exchanged (commit), so an evaluation that has to be abandoned half-way leaves the step-start state intact.
 template <int T>        // T: column stride in doubles (compile-time -> immediate shared-memory offsets)
 struct RkSink {
     double* xs;          // stage state, registers
     double* sx;          // shared: step-start state column of this thread  (stride T doubles)
     double* sacc;        // shared: accumulator column of this thread
-    double ca, cb, cx;
-    bool last;
+    double cb, cx;
+    int stage;           // 0..3; 4 = stage 0 of the next step with this step's callbacks still pending
     FB_DEV void put(int c, double k) {
-        double a = sacc[c * T], xv = sx[c * T];
-        double an = fma(cb, k, ca * a);
+        const bool last = (stage == 3);
+        double a = 0.0;
+        if (stage & 3) a = sacc[c * T];          // stage 0: acc = k, whatever the column holds
+        double xv = sx[c * T];
+        double an = fma(cb, k, a);
         double xn = fma(cx, last ? an : k, xv);
-        sacc[c * T] = an;
+        sacc[c * T] = last ? xn : an;
         xs[c] = xn;
-        if (last) sx[c * T] = xn;
     }
+    FB_DEV void commit() { double* t = sx; sx = sacc; sacc = t; }
 };
 template <int T>
 struct SmemState {       // f_step! view of the step-start state column
-    double* sx;
+    double* const& sx;
+    FB_DEV SmemState(double* const& p) : sx(p) {}
     FB_DEV double get(int c) const { return sx[c * T]; }
     FB_DEV void set(int c, double v) { sx[c * T] = v; }
 };
@@ -112,33 +122,64 @@ struct SmemState {       // f_step! view of the step-start state column
 // evaluation simply run one iteration out of phase with their warp neighbours.
 // Dynamic shared memory: [table pack | x columns NX*T | acc columns NX*T], T = StepShape::T (a compile-time column
 // stride, so every column access is base + immediate); the CTA may be launched with fewer than T threads.
-template <int VAR, int KIN>
+//
+// Two instantiations per model. AIR = true is the fast path for members clear of the terrain: compact layout without
+// the six gear-regulator states (fewer columns -> more resident members per SM), no strut code. A member that comes
+// within the height gate of the terrain (or starts there) is handed over: its state is written back at the last
+// consistent point and `resume[i]` records how many steps it completed (bit 30: the step's callbacks are still
+// pending, i.e. the state is x*). AIR = false is the complete kernel; with `resume_mode` it finishes exactly those
+// members, from that point, so that a launch pair advances every member by the same n_steps.
+template <int VAR, int KIN, bool AIR>
 struct StepShape {
-    static constexpr int NX = Lay<VAR, KIN>::NX;
-    static constexpr int FIT = (int)((232448 - FB_TB_BYTES - 1024) / (sizeof(double) * 2 * NX)) / 32 * 32;   // 227 KB per CTA
-    static constexpr int T = FIT < FB_STEP_MAX_BLOCK ? FIT : FB_STEP_MAX_BLOCK;
-    static constexpr size_t SMEM = FB_TB_BYTES + sizeof(double) * 2 * NX * T;
+    static constexpr int NX = Lay<VAR, KIN, AIR>::NX;
+    static constexpr int BUDGET = 232448 - FB_TB_BYTES - 1024;                                 // 227 KB per CTA
+    static constexpr int FIT = (int)(BUDGET / (sizeof(double) * 2 * NX)) / 32 * 32;
+    static constexpr int CAP = AIR ? FB_STEP_MAX_BLOCK_AIR : FB_STEP_MAX_BLOCK;
+    static constexpr int T = FIT < CAP ? FIT : CAP;
+    static constexpr int SPARE = (int)(BUDGET / (sizeof(double) * T)) - 2 * NX;                // columns left for the input cache
+    static constexpr int NSLOT = SPARE < 16 ? SPARE : 16;
+    static constexpr size_t SMEM = FB_TB_BYTES + sizeof(double) * (2 * NX + NSLOT) * T;
 };
-template <int VAR, int KIN>
-__global__ void __launch_bounds__(FB_STEP_MAX_BLOCK, 1)
+#define FB_RESUME_PENDING (1 << 30)
+template <int VAR, int KIN, bool AIR>
+__global__ void __launch_bounds__((StepShape<VAR, KIN, AIR>::T), 1)
 step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic_every, double Dt,
-            unsigned long long* rhs_count) {
-    typedef Lay<VAR, KIN> L;
+            unsigned long long* rhs_count, int* resume, int resume_mode, unsigned* ground_count) {
+    typedef Lay<VAR, KIN, AIR> L;
+    typedef Lay<VAR, KIN, false> LF;
     constexpr int NX = L::NX;
     extern __shared__ __align__(16) double smem[];
     double* smem_tb = smem;
-    constexpr int T = StepShape<VAR, KIN>::T;
+    constexpr int T = StepShape<VAR, KIN, AIR>::T;
+    if (resume_mode && *ground_count == 0) return;        // nobody was handed over by the AIR launch (CTA-uniform)
     stage_tables(smem_tb, E.tables.pack);
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= E.n) return;
     int status = E.status[i];
-    if (status != FB_ST_RUNNING) return;
-    MemberIn u; u.u = E.u + i; u.pitch = E.pitch;
+    bool pending = false;
+    if (resume_mode) {
+        int r = resume[i];
+        if (r < 0) return;
+        pending = (r & FB_RESUME_PENDING) != 0;
+        int d0 = r & (FB_RESUME_PENDING - 1);
+        step0 += d0; n_steps -= d0;
+    } else if (status != FB_ST_RUNNING) {
+        if (AIR) resume[i] = -1;
+        return;
+    }
+    MemberIn ug; ug.u = E.u + i; ug.pitch = E.pitch;
     double* sx = smem + FB_TB_BYTES / 8 + threadIdx.x;
     double* sacc = sx + NX * T;
+    CachedIn<VAR, T, StepShape<VAR, KIN, AIR>::NSLOT> u; u.g = ug; u.sc = sx + 2 * NX * T;
     double xs[NX];
 #pragma unroll
-    for (int c = 0; c < NX; c++) { double v = E.x[(long long)c * E.pitch + i]; xs[c] = v; sx[c * T] = v; sacc[c * T] = 0.0; }
+    for (int c = 0; c < NX; c++) { double v = E.x[(long long)L::row(c) * E.pitch + i]; xs[c] = v; sx[c * T] = v; }
+    if (AIR) {   // regulator states must be zero to be left out
+        double nz = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; c++) nz += fabs(E.x[(long long)(LF::LDG + c) * E.pitch + i]);
+        if (nz != 0.0) { resume[i] = 0; atomicAdd(ground_count, 1u); return; }
+    }
     int stall = E.stall[i], eng = E.eng[i];
     long long ev_cur = E.ev_off ? E.ev_off[i] + E.ev_cursor[i] : 0;
     const long long ev_end = E.ev_off ? E.ev_off[i + 1] : 0;
@@ -147,32 +188,39 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
     // inputs scheduled at or before the current step index are in force from the start of this launch
     while (ev_cur < ev_end && E.ev_step[ev_cur] <= step0) {
         int f = E.ev_field[ev_cur];
-        u.set(f, saturate_input(f, E.ev_value[ev_cur]));
+        ug.set(f, saturate_input(f, E.ev_value[ev_cur]));
         ev_cur++;
     }
-    if (VAR >= FB_C172X1) avionics_assign(cs, u);   // assign!(vehicle, avionics) precedes every f_ode! (aircraftbase.jl:221-230)
+    // launch-relative step count at which the next scheduled input fires (checked once per step with one compare)
+    int next_ev = (ev_cur < ev_end) ? (int)min(E.ev_step[ev_cur] - step0, (long long)INT_MAX) : INT_MAX;
+    if (VAR >= FB_C172X1) avionics_assign(cs, ug);   // assign!(vehicle, avionics) precedes every f_ode! (aircraftbase.jl:221-230)
+    u.refresh();
 
-    int stage = 0, done = 0;
-    unsigned n_rhs = 0;
-    bool pending = false;
+    int done = 0, n_reeval = 0;
+    int gnd_seen = 0, handover = -1;
     const double h2 = 0.5 * dt, h6 = dt * (1.0 / 6.0);
     RkSink<T> sink; sink.xs = xs; sink.sx = sx; sink.sacc = sacc;
-    SmemState<T> xstate; xstate.sx = sx;
-    for (;;) {
+    sink.stage = pending ? 4 : 0;
+    SmemState<T> xstate(sink.sx);
+    if (n_steps > 0) for (;;) {
         // coefficients of this thread's current stage
-        sink.ca = (stage == 0) ? 0.0 : 1.0;
-        sink.cb = (stage == 1 || stage == 2) ? 2.0 : 1.0;
-        sink.cx = (stage == 3) ? h6 : ((stage == 2) ? dt : h2);
-        sink.last = (stage == 3);
+        const int st = sink.stage;
+        sink.cb = (st == 1 || st == 2) ? 2.0 : 1.0;
+        sink.cx = (st == 3) ? h6 : ((st == 2) ? dt : h2);
         RhsOut y;
-        rhs<VAR, KIN, false>(xs, sink, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr);
-        n_rhs++;
-        if (y.err) { status = y.err; break; }
-        if (stage == 3) { stage = 0; pending = true; continue; }   // xs == x == x*: next evaluation is the FSAL-last one
-        if (stage != 0 || !pending) { stage++; continue; }
+        rhs<VAR, KIN, false, AIR>(xs, sink, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr);
+        if (!AIR) gnd_seen |= y.gnd;
+        if (y.err) {
+            if (AIR && y.err == FB_NEED_GROUND) {
+                // sx is the step-start state (stages 1..3 and re-evaluations) or x* with this step's callbacks pending
+                handover = done | ((sink.stage == 4) ? FB_RESUME_PENDING : 0);
+            } else status = y.err;
+            break;
+        }
+        if (sink.stage == 3) { sink.commit(); sink.stage = 4; continue; }   // xs == x == x*: next evaluation is the FSAL-last one
+        if (sink.stage != 4) { sink.stage++; continue; }
         // ---- stage 0 with a pending step end: this evaluation was the reference's f(x*) and y = y*.
         // (It also produced the tentative k1 / first stage state of the next step.)
-        pending = false;
         done++;
         const long long step_idx = step0 + done;
         const bool ctl_due = (VAR >= FB_C172X1) && (step_idx % periodic_every) == 0;
@@ -181,23 +229,29 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
         YFull yf;
         const int stall_y = stall, eng_y = eng;
         if (ctl_due || log_due) {   // the saved / fed-back y is the one left by f(x*), before any callback
-            double xl[NX], kd[NX];
+            double xl[LF::NX], kd[LF::NX];
 #pragma unroll
-            for (int c = 0; c < NX; c++) xl[c] = sx[c * T];
+            for (int c = 0; c < LF::NX; c++) xl[c] = 0.0;
+#pragma unroll
+            for (int c = 0; c < NX; c++) xl[L::row(c)] = sink.sx[c * T];
             RhsOut y2;
-            rhs_with_outputs<VAR, KIN>(xl, kd, stall, eng, u, smem_tb, E.tables.geoid, &y2, &yf);
+            rhs_with_outputs<VAR, KIN>(xl, kd, stall, eng, ug, smem_tb, E.tables.geoid, &y2, &yf);
         }
-        bool changed = f_step<VAR, KIN>(xstate, stall, eng, u, y, status);
+        bool changed = f_step<VAR, KIN, AIR>(xstate, stall, eng, u, y, status);
         if (status != FB_ST_RUNNING) break;
         bool cmd_changed = false;
-        if (ctl_due) cmd_changed = avionics_periodic<VAR, KIN>(yf, y, u, cs, E.tables, Dt);
-        while (ev_cur < ev_end && E.ev_step[ev_cur] <= step_idx) {
-            int f = E.ev_field[ev_cur];
-            u.set(f, saturate_input(f, E.ev_value[ev_cur]));
-            ev_cur++;
+        if (ctl_due) cmd_changed = avionics_periodic<VAR, KIN>(yf, y, ug, cs, E.tables, Dt);
+        if (done >= next_ev) {
+            while (ev_cur < ev_end && E.ev_step[ev_cur] <= step_idx) {
+                int f = E.ev_field[ev_cur];
+                ug.set(f, saturate_input(f, E.ev_value[ev_cur]));
+                ev_cur++;
+            }
+            next_ev = (ev_cur < ev_end) ? (int)min(E.ev_step[ev_cur] - step0, (long long)INT_MAX) : INT_MAX;
             changed = true;
-        }
-        if (VAR >= FB_C172X1 && changed) avionics_assign(cs, u);   // an event cannot override a command the control laws own
+            if (VAR >= FB_C172X1) avionics_assign(cs, ug);   // an event cannot override a command the control laws own
+        } else if (VAR >= FB_C172X1 && changed) avionics_assign(cs, ug);
+        if (changed || cmd_changed) u.refresh();
         if (log_due) {
             const long long smp = step_idx / E.log_every;
             for (int f = 0; f < E.log_n_fields; f++)
@@ -206,24 +260,30 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
         if (done == n_steps) break;
         if (changed) {            // re-evaluate k1 from the post-callback x / s / u
 #pragma unroll
-            for (int c = 0; c < NX; c++) xs[c] = sx[c * T];
-            continue;             // stage stays 0, pending is false
+            for (int c = 0; c < NX; c++) xs[c] = sink.sx[c * T];
+            sink.stage = 0;       // not pending
+            n_reeval++;
+            continue;
         }
+        sink.stage = 0;
         if (VAR != FB_C172S && cmd_changed) {
             // New actuator commands alone: of the derivative just evaluated (the next step's k1) only
             // x'.act = (cmd - x.act) / tau depends on them (c172x.jl:44-50), so those seven components are
-            // re-issued to the sink instead of re-evaluating the whole right-hand side.
+            // re-issued to the sink (as stage 0) instead of re-evaluating the whole right-hand side.
 #pragma unroll
-            for (int a = 0; a < L::NACT; a++) sink.put(L::ACT + a, (1.0 / 0.05) * (u(FB_U_ACT_THROTTLE + a) - sx[(L::ACT + a) * T]));
+            for (int a = 0; a < L::NACT; a++) sink.put(L::ACT + a, (1.0 / 0.05) * (u(FB_U_ACT_THROTTLE + a) - sink.sx[(L::ACT + a) * T]));
         }
-        stage = 1;
+        sink.stage = 1;
     }
 #pragma unroll
-    for (int c = 0; c < NX; c++) E.x[(long long)c * E.pitch + i] = sx[c * T];
+    for (int c = 0; c < NX; c++) E.x[(long long)L::row(c) * E.pitch + i] = sink.sx[c * T];
     E.stall[i] = (unsigned char)stall; E.eng[i] = (unsigned char)eng; E.status[i] = status;
     if (E.ev_off) E.ev_cursor[i] = ev_cur - E.ev_off[i];
     if (VAR >= FB_C172X1) cs.store(E.ctl + i, E.pitch);
-    if (rhs_count) atomicAdd(rhs_count, (unsigned long long)n_rhs);
+    if (AIR) { resume[i] = handover; if (handover >= 0) atomicAdd(ground_count, 1u); }
+    else if (!resume_mode && gnd_seen) atomicAdd(ground_count, 1u);
+    // RHS evaluations of this launch: k1 of the first step, then k2..k4 and f(x*) per step, plus re-evaluations
+    if (rhs_count) atomicAdd(rhs_count, (unsigned long long)max(0, 4 * done + n_reeval + (pending ? -3 : 1) + (handover >= 0 ? (sink.stage & 3) : 0)));
 }
 
 // f_ode!(world) at the current state: test hook + reinit! evaluation

@@ -39,7 +39,7 @@ struct Lay {
     static constexpr int AERO = 0, LDG = 2, FUEL = 2 + NLDG, ENG = FUEL + 1, ACT = ENG + 3;
     static constexpr int NACT = (VAR == FB_C172S) ? 0 : 7;
     static constexpr int KINX = ACT + NACT;
-    static constexpr int row(int c) { return (AIR && c >= 2) ? c + 6 : c; }
+    __host__ __device__ static constexpr int row(int c) { return (AIR && c >= 2) ? c + 6 : c; }
     static constexpr int NKIN = (KIN == FB_WA) ? 9 : (KIN == FB_ECEF ? 8 : 6);
     static constexpr int DYN = KINX + NKIN;
     static constexpr int NX = DYN + 6;
@@ -86,11 +86,68 @@ struct YFull {
     double act_pos[7], act_cmd[7];
 };
 
+// pseudo input fields: combinations the RHS uses as one value (so that an input cache can hold them ready-made)
+enum { FB_UX_AE = 100,   // -clamp(elevator_offset + elevator)   C172S MechanicalActuation, c172s.jl:92-120
+       FB_UX_AA,         //  clamp(aileron_offset + aileron)
+       FB_UX_RU };       //  clamp(rudder_offset + rudder)
 struct MemberIn {       // per-member input view: field f of this member is u[f * pitch]
     double* u;          // plain (coherent) loads: the owning thread also writes inputs (events, control laws)
     long long pitch;
-    FB_DEV double operator()(int f) const { return u[(long long)f * pitch]; }
+    FB_DEV double raw(int f) const { return u[(long long)f * pitch]; }
+    FB_DEV double operator()(int f) const {
+        if (f == FB_UX_AE) return -clampd(raw(FB_U_ELEVATOR_OFFSET) + raw(FB_U_ELEVATOR), -1.0, 1.0);
+        if (f == FB_UX_AA) return clampd(raw(FB_U_AILERON_OFFSET) + raw(FB_U_AILERON), -1.0, 1.0);
+        if (f == FB_UX_RU) return clampd(raw(FB_U_RUDDER_OFFSET) + raw(FB_U_RUDDER), -1.0, 1.0);
+        return raw(f);
+    }
     FB_DEV void set(int f, double v) const { u[(long long)f * pitch] = v; }
+};
+
+// Input view of the integrator: the values every RHS evaluation reads are kept in spare shared-memory columns
+// (NSLOT of them, filled in priority order), Bool inputs in a flag word; everything else falls through to HBM/L2.
+// The owning thread calls refresh() after anything wrote inputs (events, control laws).
+template <int VAR, int T, int NSLOT>
+struct CachedIn {
+    MemberIn g;
+    double* sc;         // shared: column 0 of this thread's slots
+    int flags;          // bit 0 mixture_auto, 1 eng_start, 2 eng_stop, 3 any wind component non-zero
+    __host__ __device__ static constexpr int field_of(int s) {
+        if (VAR == FB_C172S) {
+            switch (s) {
+                case 0: return FB_U_T_SL; case 1: return FB_U_P_SL; case 2: return FB_U_TRN_ELEVATION; case 3: return FB_UX_AE;
+                case 4: return FB_UX_AA; case 5: return FB_UX_RU; case 6: return FB_U_FLAPS; case 7: return FB_U_THROTTLE;
+                case 8: return FB_U_MIXTURE; case 9: return FB_U_M_PILOT; case 10: return FB_U_M_COPILOT; case 11: return FB_U_M_LPASS;
+                case 12: return FB_U_M_RPASS; case 13: return FB_U_M_BAGGAGE; default: return -1;
+            }
+        } else {
+            switch (s) {
+                case 0: return FB_U_T_SL; case 1: return FB_U_P_SL; case 2: return FB_U_TRN_ELEVATION; case 3: return FB_U_ACT_THROTTLE;
+                case 4: return FB_U_ACT_AILERON; case 5: return FB_U_ACT_ELEVATOR; case 6: return FB_U_ACT_RUDDER; case 7: return FB_U_ACT_FLAPS;
+                case 8: return FB_U_MIXTURE; case 9: return FB_U_M_PILOT; case 10: return FB_U_M_COPILOT; case 11: return FB_U_M_LPASS;
+                case 12: return FB_U_M_RPASS; case 13: return FB_U_M_BAGGAGE; case 14: return FB_U_ACT_BRAKE_LEFT; case 15: return FB_U_ACT_BRAKE_RIGHT;
+                default: return -1;
+            }
+        }
+    }
+    __host__ __device__ static constexpr int slot(int f) {
+        for (int s = 0; s < NSLOT; s++) if (field_of(s) == f) return s;
+        return -1;
+    }
+    FB_DEV double operator()(int f) const {
+        const int s = slot(f);
+        if (s >= 0) return sc[s * T];
+        if (f == FB_U_MIXTURE_AUTO) return (flags & 1) ? 1.0 : 0.0;
+        if (f == FB_U_ENG_START) return (flags & 2) ? 1.0 : 0.0;
+        if (f == FB_U_ENG_STOP) return (flags & 4) ? 1.0 : 0.0;
+        if (f >= FB_U_WIND_N && f <= FB_U_WIND_D) return (flags & 8) ? g(f) : 0.0;
+        return g(f);
+    }
+    FB_DEV void refresh() {
+#pragma unroll
+        for (int s = 0; s < NSLOT; s++) if (field_of(s) >= 0) sc[s * T] = g(field_of(s));
+        flags = (g(FB_U_MIXTURE_AUTO) != 0.0 ? 1 : 0) | (g(FB_U_ENG_START) != 0.0 ? 2 : 0) | (g(FB_U_ENG_STOP) != 0.0 ? 4 : 0) |
+                ((g(FB_U_WIND_N) != 0.0 || g(FB_U_WIND_E) != 0.0 || g(FB_U_WIND_D) != 0.0) ? 8 : 0);
+    }
 };
 
 // derivative sink that simply stores into a local array (test hook, trim, output pass)
@@ -349,8 +406,8 @@ FB_DEV double interp_2x9_line(const double* y, double n0, double n1, double x0, 
 
 // ------------------------------------------------------------------------------------------- the RHS
 // x: state (read-only; every component is read before its derivative is put into the sink).
-template <int VAR, int KIN, bool WY, bool AIR = false, class Sink>
-FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const MemberIn& u,
+template <int VAR, int KIN, bool WY, bool AIR = false, class Sink, class U>
+FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& u,
                 const double* __restrict__ tb, const float* __restrict__ geoid, RhsOut& out, YFull* yf) {
     typedef Lay<VAR, KIN, AIR> L;
     out.wow = 0; out.crash = 0; out.err = 0; out.gnd = 0;
@@ -467,10 +524,10 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const Mem
     // ------------------------------------------------------------------ actuation
     double a_e, a_a, a_r, a_f, steer, br_l, br_r, throttle;
     if (VAR == FB_C172S) {
-        double ru = clampd(u(FB_U_RUDDER_OFFSET) + u(FB_U_RUDDER), -1.0, 1.0);
+        double ru = u(FB_UX_RU);
         steer = ru; a_r = -ru;
-        a_e = -clampd(u(FB_U_ELEVATOR_OFFSET) + u(FB_U_ELEVATOR), -1.0, 1.0);
-        a_a = clampd(u(FB_U_AILERON_OFFSET) + u(FB_U_AILERON), -1.0, 1.0);
+        a_e = u(FB_UX_AE);
+        a_a = u(FB_UX_AA);
         a_f = u(FB_U_FLAPS); br_l = u(FB_U_BRAKE_LEFT); br_r = u(FB_U_BRAKE_RIGHT);
         throttle = u(FB_U_THROTTLE);
     } else {
@@ -802,8 +859,8 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const Mem
 // evaluation at the post-step state. X is any indexable state holder (registers or a shared-memory column).
 // Returns true when something the RHS reads changed (so that the first-same-as-last derivative must be
 // re-evaluated).
-template <int VAR, int KIN, bool AIR = false, class X>
-FB_DEV bool f_step(X& x, int& stall, int& eng_state, const MemberIn& u, const RhsOut& y, int& status) {
+template <int VAR, int KIN, bool AIR = false, class X, class U>
+FB_DEV bool f_step(X& x, int& stall, int& eng_state, const U& u, const RhsOut& y, int& status) {
     typedef Lay<VAR, KIN, AIR> L;
     bool changed = false;
     if (KIN == FB_WA) {   // kinematics.jl:114-118,226-229

@@ -37,23 +37,49 @@ struct fb_sim {
     unsigned long long* d_rhs_count = nullptr;
     long long launches = 0;
     int periodic_every = 1;
-    int step_block = 128;            // threads per CTA of the integrator (one CTA per SM)
+    int step_block = 128;            // threads per CTA of the complete integrator kernel (one CTA per SM)
+    int step_block_air = 128;        // ... of the AIR (clear-of-terrain) instantiation
+    // hand-over between the two instantiations (fb_kernels.cuh): per-member resume record, device counter of members that
+    // were (AIR launch) or would have been (complete launch) handed over, and its pinned host copy read one launch late
+    int* d_resume = nullptr;
+    unsigned* d_ground = nullptr;
+    unsigned* h_ground = nullptr;
+    cudaEvent_t ground_ev = nullptr;
+    bool ground_ev_pending = false;
+    bool air_mode = true;
     std::vector<double> h_row;
 };
 
 // ------------------------------------------------------------------------------------ kernel dispatch
 template <int VAR, int KIN> struct Ops {
-    static cudaError_t step(fb_sim* s, long long step0, int n) {
+    // One advance of n steps: the AIR instantiation for everybody followed by the complete kernel for the members it
+    // handed over (it returns at once when there are none), or — while a large share of the ensemble is near the
+    // terrain — the complete kernel alone. Returns the number of kernels launched through *launched.
+    static cudaError_t step(fb_sim* s, long long step0, int n, int* launched) {
+        cudaError_t e = cudaMemsetAsync(s->d_ground, 0, sizeof(unsigned), s->stream);
+        if (e != cudaSuccess) return e;
         int T = s->step_block;
         int grid = (int)((s->E.n + T - 1) / T);
-        size_t smem = StepShape<VAR, KIN>::SMEM;
-        step_kernel<VAR, KIN><<<grid, T, smem, s->stream>>>(s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count);
+        if (s->air_mode) {
+            int Ta = s->step_block_air;
+            int grid_a = (int)((s->E.n + Ta - 1) / Ta);
+            step_kernel<VAR, KIN, true><<<grid_a, Ta, StepShape<VAR, KIN, true>::SMEM, s->stream>>>(
+                s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_resume, 0, s->d_ground);
+            step_kernel<VAR, KIN, false><<<grid, T, StepShape<VAR, KIN, false>::SMEM, s->stream>>>(
+                s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_resume, 1, s->d_ground);
+            *launched = 2;
+        } else {
+            step_kernel<VAR, KIN, false><<<grid, T, StepShape<VAR, KIN, false>::SMEM, s->stream>>>(
+                s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, nullptr, 0, s->d_ground);
+            *launched = 1;
+        }
         return cudaGetLastError();
     }
-    static int step_tmax() { return StepShape<VAR, KIN>::T; }
+    static int step_tmax(bool air) { return air ? StepShape<VAR, KIN, true>::T : StepShape<VAR, KIN, false>::T; }
     static cudaError_t prepare(fb_sim* s) {
-        size_t smem = StepShape<VAR, KIN>::SMEM;
-        cudaError_t e = cudaFuncSetAttribute(step_kernel<VAR, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(step_kernel<VAR, KIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StepShape<VAR, KIN, false>::SMEM);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(step_kernel<VAR, KIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StepShape<VAR, KIN, true>::SMEM);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(rhs_kernel<VAR, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES);
         if (e != cudaSuccess) return e;
@@ -246,13 +272,20 @@ int32_t fb_create(const fb_config* cfg, fb_handle* out) {
     {
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, cfg->device));
-        int tmax = FB_DISPATCH(s, step_tmax)();   // compile-time column stride of the instantiation (fits 227 KB)
         int sms = prop.multiProcessorCount;
-        int T = (int)std::min<long long>(tmax, (N + 31) / 32 * 32);
-        long long waves = ((N + T - 1) / T + sms - 1) / sms;
-        while (T > 32 && (((N + (T - 32) - 1) / (T - 32) + sms - 1) / sms) == waves) T -= 32;
-        s->step_block = T;
+        for (int air = 0; air < 2; air++) {
+            int tmax = FB_DISPATCH(s, step_tmax)(air != 0);   // compile-time column stride of the instantiation (fits 227 KB)
+            int T = (int)std::min<long long>(tmax, (N + 31) / 32 * 32);
+            long long waves = ((N + T - 1) / T + sms - 1) / sms;
+            while (T > 32 && (((N + (T - 32) - 1) / (T - 32) + sms - 1) / sms) == waves) T -= 32;
+            (air ? s->step_block_air : s->step_block) = T;
+        }
     }
+    CK(cudaMalloc(&s->d_resume, sizeof(int) * s->pitch));
+    CK(cudaMalloc(&s->d_ground, sizeof(unsigned)));
+    CK(cudaMallocHost(&s->h_ground, sizeof(unsigned)));
+    *s->h_ground = 0;
+    CK(cudaEventCreateWithFlags(&s->ground_ev, cudaEventDisableTiming));
     CK(FB_DISPATCH(s, prepare)(s));
     CK(cudaStreamSynchronize(s->stream));
     *out = s;
@@ -269,6 +302,7 @@ int32_t fb_destroy(fb_handle s) {
     for (int i = 0; i < GS_COUNT; i++) cudaFree(s->d_gains[i]);
     cudaFree(s->d_ev_off); cudaFree(s->d_ev_step); cudaFree(s->d_ev_field); cudaFree(s->d_ev_value); cudaFree(s->d_ev_cursor);
     cudaFree(s->d_log_fields); cudaFree(s->d_scratch); cudaFree(s->d_stats); cudaFree(s->d_rhs_count);
+    cudaFree(s->d_resume); cudaFree(s->d_ground); if (s->h_ground) cudaFreeHost(s->h_ground); if (s->ground_ev) cudaEventDestroy(s->ground_ev);
     cudaStreamDestroy(s->stream);
     delete s;
     return FB_OK;
@@ -489,8 +523,20 @@ static int32_t advance(fb_sim* s, long long n) {
     CK(cudaSetDevice(s->cfg.device));
     while (n > 0) {
         int k = (int)std::min<long long>(n, s->cfg.steps_per_launch);
-        CK(FB_DISPATCH(s, step)(s, s->n_steps, k));
-        s->launches++;
+        // Pick the launch shape from the most recent count of members near the terrain that has already arrived on
+        // the host (never waits for the GPU): mostly airborne -> AIR kernel + hand-over pass, otherwise complete kernel.
+        if (s->ground_ev_pending && cudaEventQuery(s->ground_ev) == cudaSuccess) {
+            s->ground_ev_pending = false;
+            s->air_mode = (long long)*s->h_ground * 8 <= s->E.n;
+        }
+        int launched = 0;
+        CK(FB_DISPATCH(s, step)(s, s->n_steps, k, &launched));
+        if (!s->ground_ev_pending) {
+            CK(cudaMemcpyAsync(s->h_ground, s->d_ground, sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
+            CK(cudaEventRecord(s->ground_ev, s->stream));
+            s->ground_ev_pending = true;
+        }
+        s->launches += launched;
         s->n_steps += k;
         n -= k;
     }
