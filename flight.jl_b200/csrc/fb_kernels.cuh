@@ -80,11 +80,10 @@ __host__ __device__ inline double saturate_input(int f, double v) {   // Ranged{
 //   stage 0: acc = k            xs = x + dt/2 k
 //   stage 1: acc += 2k          xs = x + dt/2 k
 //   stage 2: acc += 2k          xs = x + dt k
-//   stage 3: x* = x + dt/6 (acc+k), written over acc;  xs = x*
-// written with per-thread coefficients (ca, cb, cx) so that one code path serves all four stages:
-//   acc' = cb*k + ca*acc ; xn = x + cx * (last ? acc' : k) ; acc column <- last ? xn : acc' ; xs = xn
-// The step-start column is never written by a stage: after a successful stage-3 evaluation the two column pointers
-// are exchanged (commit), so an evaluation that has to be abandoned half-way leaves the step-start state intact.
+//   stage 3: acc += k           (xs is rebuilt by the combine pass: x* = x + dt/6 acc)
+// with per-thread coefficients (cb, cx) so that one code path serves all four stages. The step-start column is
+// never written by a stage, so an evaluation that has to be abandoned half-way leaves the step-start state intact;
+// the combine pass runs only after a complete, error-free stage-3 evaluation.
 template <int T>        // T: column stride in doubles (compile-time -> immediate shared-memory offsets)
 struct RkSink {
     double* xs;          // stage state, registers
@@ -93,21 +92,22 @@ struct RkSink {
     double cb, cx;
     int stage;           // 0..3; 4 = stage 0 of the next step with this step's callbacks still pending
     FB_DEV void put(int c, double k) {
-        const bool last = (stage == 3);
         double a = 0.0;
         if (stage & 3) a = sacc[c * T];          // stage 0: acc = k, whatever the column holds
         double xv = sx[c * T];
-        double an = fma(cb, k, a);
-        double xn = fma(cx, last ? an : k, xv);
-        sacc[c * T] = last ? xn : an;
-        xs[c] = xn;
+        sacc[c * T] = fma(cb, k, a);
+        xs[c] = fma(cx, k, xv);
     }
-    FB_DEV void commit() { double* t = sx; sx = sacc; sacc = t; }
+    template <int NX>
+    FB_DEV void combine(double h6) {             // x* = x + dt/6 (k1 + 2 k2 + 2 k3 + k4); xs = x*
+#pragma unroll
+        for (int c = 0; c < NX; c++) { double xn = fma(h6, sacc[c * T], sx[c * T]); sx[c * T] = xn; xs[c] = xn; }
+    }
 };
 template <int T>
 struct SmemState {       // f_step! view of the step-start state column
-    double* const& sx;
-    FB_DEV SmemState(double* const& p) : sx(p) {}
+    double* sx;
+    FB_DEV SmemState(double* p) : sx(p) {}
     FB_DEV double get(int c) const { return sx[c * T]; }
     FB_DEV void set(int c, double v) { sx[c * T] = v; }
 };
@@ -206,7 +206,7 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
         // coefficients of this thread's current stage
         const int st = sink.stage;
         sink.cb = (st == 1 || st == 2) ? 2.0 : 1.0;
-        sink.cx = (st == 3) ? h6 : ((st == 2) ? dt : h2);
+        sink.cx = (st == 2) ? dt : h2;
         RhsOut y;
         rhs<VAR, KIN, false, AIR>(xs, sink, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr);
         if (!AIR) gnd_seen |= y.gnd;
@@ -217,7 +217,7 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
             } else status = y.err;
             break;
         }
-        if (sink.stage == 3) { sink.commit(); sink.stage = 4; continue; }   // xs == x == x*: next evaluation is the FSAL-last one
+        if (sink.stage == 3) { sink.template combine<NX>(h6); sink.stage = 4; continue; }   // xs == x == x*: next evaluation is the FSAL-last one
         if (sink.stage != 4) { sink.stage++; continue; }
         // ---- stage 0 with a pending step end: this evaluation was the reference's f(x*) and y = y*.
         // (It also produced the tentative k1 / first stage state of the next step.)

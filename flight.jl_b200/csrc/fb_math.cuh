@@ -51,12 +51,12 @@ FB_DEV double fb_sqrt(double a) {   // a > 0
 // series to z^13 leaves a truncation error below 1e-18. Absolute error ~1 ulp of the result's quadrant offset.
 __constant__ double c_atan_tab[9] = {0.0, 0.12435499454676144, 0.24497866312686414, 0.35877067027057225, 0.46364760900080609,
                                      0.55859931534356244, 0.64350110879328437, 0.71882999962162453, 0.78539816339744831};
-FB_DEV double fb_atan2(double y, double x) {
+FB_DEV double fb_atan2(double y, double x) {   // branch-free; atan2(+-0, +-0) gives +-0 like an isolated zero vector should
     double ax = fabs(x), ay = fabs(y);
     double mx = fb_max(ax, ay), mn = fb_min(ax, ay);
+    mx = (mx > 0.0) ? mx : 1.0;
     float r = __fdividef((float)mn, (float)mx);
-    int idx = min(max(__float2int_rn(r * 8.0f), 0), 8);   // also absorbs the NaN of atan2(0, 0)
-    if (!(mx > 0.0)) return 0.0;
+    int idx = min(max(__float2int_rn(r * 8.0f), 0), 8);
     double c = (double)idx * 0.125;
     double z = fb_div(fma(-c, mx, mn), fma(c, mn, mx));
     double z2 = z * z;
@@ -111,8 +111,10 @@ FB_DEV void half_angle_cs(double c, double s, double& ch, double& sh) {   // (c,
     double it = fb_rsqrt(t);
     double big = t * it;                 // sqrt((1+|c|)/2)
     double small_ = 0.5 * s * it;        // s / (2 sqrt((1+|c|)/2))
-    if (c >= 0.0) { ch = big; sh = small_; }
-    else { sh = (s >= 0.0 ? big : -big); ch = fabs(small_); }
+    const bool pos = (c >= 0.0);
+    double sbig = (s >= 0.0) ? big : -big;
+    ch = pos ? big : fabs(small_);
+    sh = pos ? small_ : sbig;
 }
 FB_DEV void half_angle(double y, double x, double& ch, double& sh) {
     double ir = fb_rsqrt(fma(x, x, y * y));

@@ -163,17 +163,18 @@ struct ArrayState {
 };
 
 // ------------------------------------------------------------------------------------ interpolation
-// cell index / weight on explicit knots (Gridded(Linear())); x already clamped to the knot span; ik = 1/spacing.
-// `g` is a guess of the cell index (from the axis' nominal spacing); the two loops walk it to the right cell,
-// which costs zero or one iteration for the near-uniform axes of this model.
-FB_DEV void locate(const double* k, const double* ik, int n, double x, int g, int& i, double& w) {
-    int lo = min(max(g, 0), n - 2);
-#pragma unroll 1
-    while (lo > 0 && x < k[lo]) lo--;
-#pragma unroll 1
-    while (lo < n - 2 && x >= k[lo + 1]) lo++;
-    i = lo;
-    w = (x - k[lo]) * ik[lo];
+// cell index / weight on explicit knots (Gridded(Linear())); x already clamped to the knot span; IK = 1/spacing.
+// Branch-free: the span is cut into FB_BK uniform buckets with at most one interior knot each (fb_tables.h: TB_BK),
+// so the cell is the one at the bucket's left edge, plus one if x is at or beyond the knot inside the bucket.
+template <int AXIS>
+FB_DEV void locate(const double* tb, int KN, int IK, double x, int& i, double& w) {
+    double t = (x - tb[KN]) * tb[TB_BK_IH + AXIS];
+    int b = min(max((int)t, 0), FB_BK - 1);
+    const int4 r = *reinterpret_cast<const int4*>(tb + TB_BK + (AXIS * FB_BK + b) * 2);
+    double kb = __hiloint2double(r.y, r.x);
+    int c = r.z + ((x >= kb) ? 1 : 0);
+    i = c;
+    w = (x - tb[KN + c]) * tb[IK + c];
 }
 FB_DEV double lerp(double a, double b, double w) { return fma(w, b - a, a); }
 // uniform axis k0 + i/idk, n knots; Flat
@@ -219,7 +220,7 @@ FB_DEV void geo_from_cartesian(d3 r, d3& n, double& h) {
     constexpr double ec2 = 1 - wgs::e2;
     constexpr double ec = 0.99664718933525254;   // sqrt(1 - e2)
     double p2 = fma(r.x, r.x, r.y * r.y);
-    double ip = (p2 > 0.0) ? fb_rsqrt(p2) : 0.0;
+    double ip = fb_rsqrt(fb_max(p2, 1e-280));     // on the polar axis p = 0 and the longitude is taken as 0
     double p = p2 * ip;
     double az = fabs(r.z);
     double zc = ec * az, s0 = az, c0 = ec * p;
@@ -508,7 +509,7 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
         d3 wind = mk3(u(FB_U_WIND_N), u(FB_U_WIND_E), u(FB_U_WIND_D));
         air.v_wb_b = k.v_eb_b - qrot_inv(k.q_nb, wind);
         double tas2 = dot(air.v_wb_b, air.v_wb_b);
-        air.iTAS = (tas2 > 0.0) ? fb_rsqrt(tas2) : 0.0;
+        air.iTAS = fb_rsqrt(fb_max(tas2, 1e-280));
         air.TAS = tas2 * air.iTAS;
         air.q = 0.5 * air.rho * tas2;
     }
@@ -551,13 +552,16 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
         constexpr double d2r = FB_PI / 180.0;
         double alpha_filt = x[L::AERO], beta_filt = x[L::AERO + 1];
         d3 v = air.v_wb_b;
-        double alpha = 0.0, beta = 0.0, ca = 1.0, sa = 0.0;
-        if (air.TAS > 0.1) {   // covers both TAS thresholds (c172.jl:324, atmosphere.jl:337)
+        double alpha, beta, ca, sa;
+        {   // alpha = beta = 0 below TAS 0.1 (covers both thresholds: c172.jl:324, atmosphere.jl:337); evaluated branch-free
+            const bool moving = air.TAS > 0.1;
             double vxz2 = fma(v.x, v.x, v.z * v.z);
-            double ivxz = (vxz2 > 0.0) ? fb_rsqrt(vxz2) : 0.0;
-            alpha = fb_atan2(v.z, v.x);
-            beta = fb_atan2(v.y, vxz2 * ivxz);
-            if (vxz2 > 0.0) { ca = v.x * ivxz; sa = v.z * ivxz; }
+            const bool planar = vxz2 > 0.0;
+            double ivxz = fb_rsqrt(fb_max(vxz2, 1e-280));
+            double al = fb_atan2(v.z, v.x);
+            double be = fb_atan2(v.y, vxz2 * ivxz);
+            alpha = moving ? al : 0.0; beta = moving ? be : 0.0;
+            ca = (moving && planar) ? v.x * ivxz : 1.0; sa = (moving && planar) ? v.z * ivxz : 0.0;
         }
         out.alpha = alpha;
         double i2V = (air.TAS > 1.0) ? 0.5 * air.iTAS : 0.5;   // 1 / (2 max(TAS, V_min)), V_min = 1
@@ -573,21 +577,21 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
         double a_c = clampd(alpha, -0.1, 0.36), b_c = clampd(beta, -0.2, 0.2);
         // flap axis (knots 0,10,20,30 deg) shared by five tables
         int jf; double wf;
-        { double dfc = clampd(df, tb[TB_DF_X], tb[TB_DF_X + 3]); locate(tb + TB_DF_X, tb + TB_I_DF, 4, dfc, (int)(dfc * (18.0 / FB_PI)), jf, wf); }
+        { double dfc = clampd(df, tb[TB_DF_X], tb[TB_DF_X + 3]); locate<FB_AX_DF>(tb, TB_DF_X, TB_I_DF, dfc, jf, wf); }
         double wf2 = clampd(df * (1.0 / (30 * d2r)), 0.0, 1.0);   // 2-knot flap axis (0, 30 deg)
         int ig; double wg;
-        { double g = clampd(dh_nd, 0.0, 1.1); locate(tb + TB_GE_X, tb + TB_I_GE, 13, g, (g < 0.2) ? (int)(g * 20.0) - 1 : (int)(g * 10.0) + 1, ig, wg); }
+        { double g = clampd(dh_nd, 0.0, 1.1); locate<FB_AX_GE>(tb, TB_GE_X, TB_I_GE, g, ig, wg); }
         double CD_ge = lerp(tb[TB_CD_GE + ig], tb[TB_CD_GE + ig + 1], wg);
         double CL_ge = lerp(tb[TB_CL_GE + ig], tb[TB_CL_GE + ig + 1], wg);
         double CD_df = lerp(tb[TB_CD_DF + jf], tb[TB_CD_DF + jf + 1], wf);
         double CL_df = lerp(tb[TB_CL_DF + jf], tb[TB_CL_DF + jf + 1], wf);
         double Cm_df = lerp(tb[TB_CM_DF + jf], tb[TB_CM_DF + jf + 1], wf);
         int ia; double wa;
-        { double ac = clampd(a_c, tb[TB_CD_A_X], tb[TB_CD_A_X + 25]); locate(tb + TB_CD_A_X, tb + TB_I_CD_A, 26, ac, (int)((ac + 0.0873) * (25.0 / 0.4364)), ia, wa); }
+        { double ac = clampd(a_c, tb[TB_CD_A_X], tb[TB_CD_A_X + 25]); locate<FB_AX_CD_A>(tb, TB_CD_A_X, TB_I_CD_A, ac, ia, wa); }
         const double* cd = tb + TB_CD_A_DF + ia * 4 + jf;
         double CD_a_df = lerp(lerp(cd[0], cd[1], wf), lerp(cd[4], cd[5], wf), wa);
         int il; double wl;
-        { double ac = clampd(a_c, tb[TB_CL_A_X], tb[TB_CL_A_X + 16]); locate(tb + TB_CL_A_X, tb + TB_I_CL_A, 17, ac, (ac < 0.1) ? (int)((ac + 0.09) * (1.0 / 0.09)) : 3 + (int)((ac - 0.1) * 50.0), il, wl); }
+        { double ac = clampd(a_c, tb[TB_CL_A_X], tb[TB_CL_A_X + 16]); locate<FB_AX_CL_A>(tb, TB_CL_A_X, TB_I_CL_A, ac, il, wl); }
         double CL_a = lerp(tb[TB_CL_A + il * 2 + stall], tb[TB_CL_A + il * 2 + 2 + stall], wl);
         double CD_de = 0.06 * fabs(clampd(de, -1.0, 1.0));       // knots (-1,0,1) -> (0.06,0,0.06)
         double CD_b = 0.17 * fabs(b_c);
@@ -660,7 +664,7 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
         const d3 r_bp = mk3(2.055, 0.0, 0.833);
         d3 v = air.v_wb_b + cross(k.w_eb_b, r_bp);
         double vJ2 = dot(v, v);
-        double v_J = (vJ2 > 0.0) ? fb_sqrt(vJ2) : 0.0;
+        double v_J = fb_sqrt(fb_max(vJ2, 1e-280));          // (1e-140 instead of 0 for a propeller at rest in still air)
         double aw = fabs(w);
         double J = (2 * FB_PI / d) * v_J * fb_rcp(fb_max(aw, 1.0));
         double Mt = aw * (d / 2) * air.ia;
@@ -672,11 +676,12 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
         double cf[4];
 #pragma unroll
         for (int c = 0; c < 4; c++) cf[c] = lerp(lerp(p00[c], p00[4 + c], wm), lerp(p10[c], p10[4 + c], wm), wj);
-        double al_p = 0.0, be_p = 0.0;
-        if (v_J >= 0.1) {
+        double al_p, be_p;
+        {
             double vxz2 = fma(v.x, v.x, v.z * v.z);
-            double vxz = (vxz2 > 0.0) ? fb_sqrt(vxz2) : 0.0;
-            al_p = fb_atan2(v.z, v.x); be_p = fb_atan2(v.y, vxz);
+            double vxz = fb_sqrt(fb_max(vxz2, 1e-280));
+            double al = fb_atan2(v.z, v.x), be = fb_atan2(v.y, vxz);
+            al_p = (v_J >= 0.1) ? al : 0.0; be_p = (v_J >= 0.1) ? be : 0.0;
         }
         double f = w * (1.0 / (2 * FB_PI)), f2 = f * f;
         constexpr double d4 = d * d * d * d, d5 = d4 * d;
@@ -725,7 +730,7 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
             double pi_std, pi_wot;
             {
                 double nc = clampd(n, tb[TB_N_STD], tb[TB_N_STD + 12]);
-                int i; double wn; locate(tb + TB_N_STD, tb + TB_I_N_STD, 13, nc, (nc < 0.667) ? 0 : 1 + (int)((nc - 0.667) * (1.0 / 0.037)), i, wn);
+                int i; double wn; locate<FB_AX_N_STD>(tb, TB_N_STD, TB_I_N_STD, nc, i, wn);
                 double mc = clampd(mu, 0.0, 1.0);
                 int j = (mc >= 0.568) ? 1 : 0;
                 double wmu = (j == 0) ? mc * (1.0 / 0.568) : (mc - 0.568) * (1.0 / (1.0 - 0.568));
@@ -734,25 +739,26 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
             }
             {   // pi_wot(n, d_wot): gridded 5 x 3 (delta knots 0, 0.441, 1), Flat in n and below, Line above in delta
                 double nc = clampd(n, tb[TB_N_WOT], tb[TB_N_WOT + 4]);
-                int i; double wn; locate(tb + TB_N_WOT, tb + TB_I_N_WOT, 5, nc, (nc < 0.667) ? 0 : ((nc < 1.0) ? 1 : 2), i, wn);
+                int i; double wn; locate<FB_AX_N_WOT>(tb, TB_N_WOT, TB_I_N_WOT, nc, i, wn);
                 double dc = clampd(d_wot, 0.0, 1.0);
                 int j = (dc >= 0.441) ? 1 : 0;
                 double wd = (j == 0) ? dc * (1.0 / 0.441) : (dc - 0.441) * (1.0 / (1.0 - 0.441));
                 const double* t = tb + TB_PI_WOT + i * 3 + j;
                 pi_wot = lerp(lerp(t[0], t[1], wd), lerp(t[3], t[4], wd), wn);
-                if (d_wot > 1.0) {
-                    double g = lerp(t[1] - t[0], t[4] - t[3], wn) * (1.0 / (1.0 - 0.441));
-                    pi_wot = fma(d_wot - 1.0, g, pi_wot);
-                }
+                double g = lerp(t[1] - t[0], t[4] - t[3], wn) * (1.0 / (1.0 - 0.441));      // upper cell's slope (j = 1 whenever it is used)
+                pi_wot = fma(fb_max(d_wot - 1.0, 0.0), g, pi_wot);                        // Line extrapolation above delta = 1
             }
-            double pi_ISA = (fabs(d_wot - 1.0) < 5e-3) ? pi_std : fma(fb_div(pi_wot - pi_std, d_wot - 1.0), delta - 1.0, pi_std);
+            const bool at_std = fabs(d_wot - 1.0) < 5e-3;
+            double pi_ISA = fma(fb_div(pi_wot - pi_std, at_std ? 1.0 : d_wot - 1.0), delta - 1.0, pi_std);
+            pi_ISA = at_std ? pi_std : pi_ISA;
             pi_ISA = fb_max(pi_ISA, 0.0);
             double pi_pow = pi_ISA * fb_sqrt(air.tr * (isa::T_std * isa::R) * air.iRT);
             int jf; double wff;
-            { double fc = clampd(far, tb[TB_F_X], tb[TB_F_X + 10]); locate(tb + TB_F_X, tb + TB_I_F, 11, fc, (fc < 0.0625) ? 0 : 1 + (int)((fc - 0.0625) * (9.0 / 0.0325)), jf, wff); }
+            { double fc = clampd(far, tb[TB_F_X], tb[TB_F_X + 10]); locate<FB_AX_F>(tb, TB_F_X, TB_I_F, fc, jf, wff); }
             double pi_actual = pi_pow * lerp(tb[TB_PI_RATIO + jf], tb[TB_PI_RATIO + jf + 1], wff);
             double P_shaft = P_rated * pi_actual;
-            tau_shaft = (w > 0.0) ? fb_div(P_shaft, w) : 0.0;
+            tau_shaft = fb_div(P_shaft, (w > 0.0) ? w : 1.0);
+            tau_shaft = (w > 0.0) ? tau_shaft : 0.0;
             MAP_y = mu * isa::p_std; P_y = P_shaft;
             // sfc_pow(n, pi_actual): gridded 5 x 8, Line
             double sfc;
@@ -760,8 +766,8 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
                 double nc = clampd(n, tb[TB_N_SFC], tb[TB_N_SFC + 4]);
                 double pc = clampd(pi_actual, tb[TB_PI_SFC], tb[TB_PI_SFC + 7]);
                 int i, j; double wn, wp;
-                locate(tb + TB_N_SFC, tb + TB_I_N_SFC, 5, nc, (int)((nc - 2000.0 / 2700.0) * 13.5), i, wn);
-                locate(tb + TB_PI_SFC, tb + TB_I_PI_SFC, 8, pc, (pc < 0.2683) ? ((pc < 0.1389) ? 0 : ((pc < 0.1931) ? 1 : 2)) : ((pc < 0.5179) ? ((pc < 0.3728) ? 3 : 4) : ((pc < 0.7197) ? 5 : 6)), j, wp);
+                locate<FB_AX_N_SFC>(tb, TB_N_SFC, TB_I_N_SFC, nc, i, wn);
+                locate<FB_AX_PI_SFC>(tb, TB_PI_SFC, TB_I_PI_SFC, pc, j, wp);
                 const double* t = tb + TB_SFC_POW + i * 8 + j;
                 double f00 = t[0], f01 = t[1], f10 = t[8], f11 = t[9];
                 sfc = lerp(lerp(f00, f01, wp), lerp(f10, f11, wp), wn);

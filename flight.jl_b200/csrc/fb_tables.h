@@ -48,8 +48,15 @@ enum {
     // ---- propeller (lib/FlightPhysics/src/propellers.jl:235-291): 21x21 over J, Mt in [0,1.5], scaled, Flat;
     //      interleaved [iJ][iMt][4] = C_Fx, C_Mx, C_Fz_a, C_Mz_a (C_P and eta_p are not on the path)
     TB_PROP = TB_SFC_POW + 40,
-    TB_COUNT = TB_PROP + 21 * 21 * 4
+    // ---- cell finders of the nine explicit-knot axes (built by the host, fb_load_tables): the knot span of axis a is cut
+    //      into FB_BK uniform buckets, none holding more than one interior knot; record b = {the knot inside bucket b
+    //      (or +huge), cell index at the bucket's left edge (int32 in the low word of the second double)}, 16-byte aligned
+    TB_BK_IH = TB_PROP + 21 * 21 * 4,                 // FB_AX_COUNT reciprocal bucket widths (+1 pad)
+    TB_BK = (TB_BK_IH + 10 + 1) / 2 * 2,              // [FB_AX_COUNT][FB_BK][2]
+    TB_COUNT = TB_BK + 9 * 32 * 2
 };
+#define FB_BK 32
+enum { FB_AX_GE = 0, FB_AX_DF, FB_AX_CD_A, FB_AX_CL_A, FB_AX_N_STD, FB_AX_N_WOT, FB_AX_F, FB_AX_N_SFC, FB_AX_PI_SFC, FB_AX_COUNT };
 #define FB_TB_BYTES ((TB_COUNT * 8 + 15) / 16 * 16)
 
 #define FB_GEOID_NLAT 721

@@ -349,6 +349,37 @@ int32_t fb_load_tables(fb_handle s, const void* blob, size_t nbytes) {
                             {TB_N_STD, TB_I_N_STD, 13}, {TB_N_WOT, TB_I_N_WOT, 5}, {TB_F_X, TB_I_F, 11}, {TB_N_SFC, TB_I_N_SFC, 5},
                             {TB_PI_SFC, TB_I_PI_SFC, 8}};
         for (const Inv& v : invs) for (int i = 0; i + 1 < v.n; i++) pack[v.inv + i] = 1.0 / (pack[v.knots + i + 1] - pack[v.knots + i]);
+        // bucketed cell finders (fb_tables.h: TB_BK), in the order of the FB_AX_* ids
+        const int axes[FB_AX_COUNT] = {0, 1, 2, 3, 4, 5, 6, 7, 8};
+        for (int a = 0; a < FB_AX_COUNT; a++) {
+            const Inv& v = invs[axes[a]];
+            const double* k = pack.data() + v.knots;
+            const double k0 = k[0], h = (k[v.n - 1] - k0) / FB_BK;
+            pack[TB_BK_IH + a] = 1.0 / h;
+            for (int bkt = 0; bkt < FB_BK; bkt++) {
+                double left = k0 + bkt * h, right = k0 + (bkt + 1) * h;
+                int c0 = 0;
+                while (c0 < v.n - 2 && k[c0 + 1] <= left) c0++;
+                double kb = 1e300; int inside = 0;
+                for (int j = 1; j <= v.n - 2; j++) if (k[j] > left && k[j] < right) { kb = k[j]; inside++; }
+                if (inside > 1) return fail(FB_ERR_ARG, "fb_load_tables: an interpolation axis has two knots in one cell-finder bucket");
+                double* rec = pack.data() + TB_BK + (a * FB_BK + bkt) * 2;
+                rec[0] = kb;
+                int64_t word = (int64_t)c0;
+                memcpy(&rec[1], &word, 8);
+            }
+            // check the finder against a plain search: any disagreement must sit on a knot (weight 0 or 1 up to rounding)
+            for (int q = 0; q <= 8192; q++) {
+                double x = k0 + (k[v.n - 1] - k0) * q / 8192.0;
+                if (q % 3 == 1) x = k[(q / 3) % v.n];
+                int bkt = std::min(std::max((int)((x - k0) * pack[TB_BK_IH + a]), 0), FB_BK - 1);
+                const double* rec = pack.data() + TB_BK + (a * FB_BK + bkt) * 2;
+                int64_t word; memcpy(&word, &rec[1], 8);
+                int c = (int)word + (x >= rec[0] ? 1 : 0);
+                double w = (x - k[c]) / (k[c + 1] - k[c]);
+                if (c < 0 || c > v.n - 2 || w < -1e-9 || w > 1.0 + 1e-9) return fail(FB_ERR_ARG, "fb_load_tables: cell finder self-check failed");
+            }
+        }
     }
     const BlobSec* g = find("geoid");
     if (!g || g->dtype != 1 || g->nbytes != (uint64_t)FB_GEOID_NLAT * FB_GEOID_NLON * 4) return fail(FB_ERR_ARG, "fb_load_tables: bad or missing geoid section");
