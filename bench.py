@@ -275,17 +275,28 @@ def main():
     rhs_per_member_step = (c1["rhs_evals"] - c0["rhs_evals"]) / max(1.0, alive * RK_PER_STEP * K)
 
     # ---------------------------------------------------------------- end to end through the public API, host buffers
+    # A second handle with the same members, trims and doublet schedule, so that this leg covers the same simulated
+    # interval as the device-resident leg (W warm-up seconds, then Ke timed seconds) instead of continuing after it.
     Ke = min(K, 20)
+    sim.close()
+    sim = fb.BatchSimulation(fb.SimpleWorld(fb.Cessna172Sv0(fb.WA())), n=n, dt=DT, t_end=t_end, device=local,
+                             member_offset=rank * n, steps_per_launch=RK_PER_STEP)
+    sim.init(fb.C172.TrimParameters(**p))
+    sim.schedule_inputs(*ev)
     ele_h = torch.from_numpy(sim.get_input(ele_f).copy()).pin_memory()
     ail_h = torch.from_numpy(sim.get_input(ail_f).copy()).pin_memory()
-    x_h = np.zeros((sim.nx, n))
+    x_pin = torch.empty((sim.nx, n), dtype=torch.float64).pin_memory()   # the caller-owned host buffer the state lands in
+    x_h = x_pin.numpy()
+    for _ in range(W):
+        sim.step(RK_PER_STEP * DT)
+    sim.sync()
     barrier()
     e0 = time.perf_counter()
     for k in range(Ke):
         sim.set_input(ele_f, ele_h.numpy())         # H2D: this second's control inputs, one value per member
         sim.set_input(ail_f, ail_h.numpy())
         sim.step(RK_PER_STEP * DT)
-        x_h = sim.x                                 # D2H: the full ensemble state (the step's result)
+        sim.get_state(out=x_h)                      # D2H: the full ensemble state (the step's result)
     barrier()
     e1 = time.perf_counter()
     te = torch.tensor([e1 - e0], dtype=torch.float64, device="cuda")
@@ -320,13 +331,15 @@ def main():
                        "members_per_gpu": n, "members_alive": total_members, "trim_ok": float(tot_alive[1].item()), "rk4_steps_per_bench_step": RK_PER_STEP,
                        "rhs_evals_per_member_step": rhs_per_member_step,
                        "l2": "flushed between timed steps (256 MiB write outside the event pair); state+inputs (56 MB) < L2, kernel is FP64-bound",
-                       "timing": "CUDA events on the library's launch stream, sum over steps, max over ranks", "wall_s": wall1 - wall0},
+                       "timing": "CUDA events on the library's launch stream, sum over steps, max over ranks", "wall_s": wall1 - wall0,
+                       "ms_per_step_min_max": [min(ms), max(ms)],
+                       "launches_per_step": "2: airborne-layout kernel + hand-over pass of the complete kernel (returns at once when no member is near the terrain)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                    "what": "fb_set_input(elevator, aileron) from pinned host arrays + fb_step(1 s) + fb_get_state to host, wall clock"},
+                    "what": "fb_set_input(elevator, aileron) from pinned host arrays + fb_step(1 s) + fb_get_state into a pinned host array, wall clock"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None,
-                         "traffic": traffic, "kernel": "step_kernel<C172S,WA>",
+                         "traffic": traffic, "kernel": "step_kernel<C172S,WA,AIR>",
                          "note": "path is FP64-FMA-pipe bound, not HBM/tensor (SURVEY.md §8d); peak = FP64 FMA probe measured in this run "
                                  "(MEASURED_PEAKS.json carries no FP64 figure); achieved = 15,695 unit-FLOP/aircraft-step x steps/s per GPU",
                          "hbm": {"achieved_gbs": state_bytes / (dev_s / K) * 1e-9, "peak_gbs": peaks.get("hbm_gbs"), "algorithmic_bytes_per_launch": state_bytes}},

@@ -415,7 +415,15 @@ class BatchSimulation:
 
     @property
     def x(self):
-        out = np.zeros((self.nx, self.n))
+        return self.get_state()
+
+    def get_state(self, out=None):
+        """sim.x as an [nx][N] array. `out` may be a preallocated C-contiguous float64 array (e.g. the numpy view of a
+        pinned host buffer, which makes the device-to-host copy run at PCIe speed); it is filled and returned."""
+        if out is None:
+            out = np.empty((self.nx, self.n))
+        if out.dtype != np.float64 or not out.flags.c_contiguous or out.shape != (self.nx, self.n):
+            raise FlightBatchError(f"get_state: out must be a C-contiguous float64 array of shape {(self.nx, self.n)}")
         _ck(self._lib.fb_get_state(self._h, _dp(out)), self._lib)
         return out
 

@@ -26,6 +26,10 @@ struct fb_sim {
     long long pitch = 0;
     EnsembleDev E{};
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;                // host-to-device staging of per-member inputs (fb_set_input)
+    double* d_stage[FB_U__COUNT] = {};                 // lazily allocated staging rows
+    cudaEvent_t stage_consumed[FB_U__COUNT] = {};
+    cudaEvent_t copy_done = nullptr;
     double* d_pack = nullptr; float* d_geoid = nullptr; double* d_gains[GS_COUNT] = {};
     bool tables_loaded = false, initialised = false;
     long long n_steps = 0;
@@ -47,7 +51,6 @@ struct fb_sim {
     cudaEvent_t ground_ev = nullptr;
     bool ground_ev_pending = false;
     bool air_mode = true;
-    std::vector<double> h_row;
 };
 
 // ------------------------------------------------------------------------------------ kernel dispatch
@@ -155,6 +158,11 @@ __global__ void stats_kernel(const double* v, const int* status, long long n, do
         do { assumed = old; if (__longlong_as_double(assumed) >= mx) break; old = atomicCAS(pmx, assumed, (unsigned long long)__double_as_longlong(mx)); } while (assumed != old);
     }
 }
+// row[i] = Ranged-saturated staged value (types.jl:15-20), the device half of fb_set_input
+__global__ void saturate_row_kernel(double* row, const double* staged, long long n, int field) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) row[i] = saturate_input(field, staged[i]);
+}
 __global__ void fill_kernel(double* p, long long n, double v) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -227,6 +235,9 @@ int32_t fb_create(const fb_config* cfg, fb_handle* out) {
     s->pitch = (N + 31) / 32 * 32;
     if (s->cfg.steps_per_launch <= 0) s->cfg.steps_per_launch = 250;
     CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&s->copy_done, cudaEventDisableTiming));
+    for (int f = 0; f < FB_U__COUNT; f++) CK(cudaEventCreateWithFlags(&s->stage_consumed[f], cudaEventDisableTiming));
     EnsembleDev& E = s->E;
     E.pitch = s->pitch; E.n = N;
     CK(cudaMalloc(&E.x, sizeof(double) * s->nx * s->pitch));
@@ -303,6 +314,9 @@ int32_t fb_destroy(fb_handle s) {
     cudaFree(s->d_ev_off); cudaFree(s->d_ev_step); cudaFree(s->d_ev_field); cudaFree(s->d_ev_value); cudaFree(s->d_ev_cursor);
     cudaFree(s->d_log_fields); cudaFree(s->d_scratch); cudaFree(s->d_stats); cudaFree(s->d_rhs_count);
     cudaFree(s->d_resume); cudaFree(s->d_ground); if (s->h_ground) cudaFreeHost(s->h_ground); if (s->ground_ev) cudaEventDestroy(s->ground_ev);
+    for (int f = 0; f < FB_U__COUNT; f++) { cudaFree(s->d_stage[f]); if (s->stage_consumed[f]) cudaEventDestroy(s->stage_consumed[f]); }
+    if (s->copy_done) cudaEventDestroy(s->copy_done);
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     cudaStreamDestroy(s->stream);
     delete s;
     return FB_OK;
@@ -502,10 +516,18 @@ int32_t fb_set_input(fb_handle s, int32_t field, const double* values, int64_t s
         fill_kernel<<<grid, 256, 0, s->stream>>>(row, s->pitch, saturate_input(field, values[0]));
         CK(cudaGetLastError());
     } else {
-        s->h_row.resize(s->E.n);
-        for (long long i = 0; i < s->E.n; i++) s->h_row[i] = saturate_input(field, values[i]);
-        CK(cudaMemcpyAsync(row, s->h_row.data(), sizeof(double) * s->E.n, cudaMemcpyHostToDevice, s->stream));
-        CK(cudaStreamSynchronize(s->stream));
+        // The caller's array goes straight to a per-field staging row on the copy stream (a DMA at PCIe speed when the
+        // array is pinned), which is all this call waits for: the caller may reuse the array on return. Saturation and
+        // the write into the ensemble happen on the launch stream, ordered after whatever is still stepping there.
+        if (!s->d_stage[field]) CK(cudaMalloc(&s->d_stage[field], sizeof(double) * s->pitch));
+        CK(cudaStreamWaitEvent(s->copy_stream, s->stage_consumed[field], 0));      // previous value of this field consumed
+        CK(cudaMemcpyAsync(s->d_stage[field], values, sizeof(double) * s->E.n, cudaMemcpyHostToDevice, s->copy_stream));
+        CK(cudaEventRecord(s->copy_done, s->copy_stream));
+        CK(cudaEventSynchronize(s->copy_done));
+        int grid = (int)((s->E.n + 255) / 256);
+        saturate_row_kernel<<<grid, 256, 0, s->stream>>>(row, s->d_stage[field], s->E.n, field);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(s->stage_consumed[field], s->stream));
     }
     return FB_OK;
 }
