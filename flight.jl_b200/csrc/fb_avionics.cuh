@@ -47,6 +47,7 @@ struct CtlState {
     FB_DEV void store(double* p, long long pitch) { xfer<true>(p, pitch); }
 };
 #define FB_CTL_ROW_H_STATE 2   // row of h_state in the column (constructed-model default: hold = 1)
+#define FB_CTL_TAP_ROW 48      // rows 48..61 of the column: output tap of the integrator (TAP_COUNT values, fb_physics.cuh)
 
 __host__ __device__ inline double avionics_saturate_input(int f, double v) {
     switch (f) {

@@ -9,11 +9,15 @@
 #include "fb_avionics.cuh"
 
 #define FB_BLOCK 128          // block size of the light kernels (rhs / output / init / trim)
-#ifndef FB_STEP_MAX_BLOCK
-#define FB_STEP_MAX_BLOCK 448 // 14 warps per SM: 4 warps on an SM sub-partition -> 128 registers per thread
+// Threads per CTA of the integrator (one CTA per SM). The register file gives 168 registers per thread to 12 warps and
+// 128 to 13..16 warps (a sub-partition then holds 4 warps); measured on B200, a 100-step launch of the airborne C172S
+// kernel takes 2.9 ms at 384 threads and 4.3 ms at 448, so 384 wins whenever the ensemble spans several waves of CTAs
+// and 448 only when it lets the whole ensemble fit ONE wave (cfg 2: 65,536 members = 443 per SM). The host picks.
+#ifndef FB_STEP_BLOCK
+#define FB_STEP_BLOCK 384       // complete kernel, and the default airborne shape
 #endif
-#ifndef FB_STEP_MAX_BLOCK_AIR
-#define FB_STEP_MAX_BLOCK_AIR 448
+#ifndef FB_STEP_BLOCK_WIDE
+#define FB_STEP_BLOCK_WIDE 448  // second airborne shape
 #endif
 
 struct EnsembleDev {
@@ -129,20 +133,19 @@ struct SmemState {       // f_step! view of the step-start state column
 // consistent point and `resume[i]` records how many steps it completed (bit 30: the step's callbacks are still
 // pending, i.e. the state is x*). AIR = false is the complete kernel; with `resume_mode` it finishes exactly those
 // members, from that point, so that a launch pair advances every member by the same n_steps.
-template <int VAR, int KIN, bool AIR>
+template <int VAR, int KIN, bool AIR, int CAP = FB_STEP_BLOCK>
 struct StepShape {
     static constexpr int NX = Lay<VAR, KIN, AIR>::NX;
     static constexpr int BUDGET = 232448 - FB_TB_BYTES - 1024;                                 // 227 KB per CTA
     static constexpr int FIT = (int)(BUDGET / (sizeof(double) * 2 * NX)) / 32 * 32;
-    static constexpr int CAP = AIR ? FB_STEP_MAX_BLOCK_AIR : FB_STEP_MAX_BLOCK;
     static constexpr int T = FIT < CAP ? FIT : CAP;
     static constexpr int SPARE = (int)(BUDGET / (sizeof(double) * T)) - 2 * NX;                // columns left for the input cache
     static constexpr int NSLOT = SPARE < 16 ? SPARE : 16;
     static constexpr size_t SMEM = FB_TB_BYTES + sizeof(double) * (2 * NX + NSLOT) * T;
 };
 #define FB_RESUME_PENDING (1 << 30)
-template <int VAR, int KIN, bool AIR>
-__global__ void __launch_bounds__((StepShape<VAR, KIN, AIR>::T), 1)
+template <int VAR, int KIN, bool AIR, int CAP = FB_STEP_BLOCK>
+__global__ void __launch_bounds__((StepShape<VAR, KIN, AIR, CAP>::T), 1)
 step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic_every, double Dt,
             unsigned long long* rhs_count, int* resume, int resume_mode, unsigned* ground_count) {
     typedef Lay<VAR, KIN, AIR> L;
@@ -150,7 +153,8 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
     constexpr int NX = L::NX;
     extern __shared__ __align__(16) double smem[];
     double* smem_tb = smem;
-    constexpr int T = StepShape<VAR, KIN, AIR>::T;
+    constexpr int T = StepShape<VAR, KIN, AIR, CAP>::T;
+    constexpr int T_ = T;
     if (resume_mode && *ground_count == 0) return;        // nobody was handed over by the AIR launch (CTA-uniform)
     stage_tables(smem_tb, E.tables.pack);
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -170,7 +174,7 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
     MemberIn ug; ug.u = E.u + i; ug.pitch = E.pitch;
     double* sx = smem + FB_TB_BYTES / 8 + threadIdx.x;
     double* sacc = sx + NX * T;
-    CachedIn<VAR, T, StepShape<VAR, KIN, AIR>::NSLOT> u; u.g = ug; u.sc = sx + 2 * NX * T;
+    CachedIn<VAR, T, StepShape<VAR, KIN, AIR, CAP>::NSLOT> u; u.g = ug; u.sc = sx + 2 * NX * T;
     double xs[NX];
 #pragma unroll
     for (int c = 0; c < NX; c++) { double v = E.x[(long long)L::row(c) * E.pitch + i]; xs[c] = v; sx[c * T] = v; }
@@ -208,7 +212,10 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
         sink.cb = (st == 1 || st == 2) ? 2.0 : 1.0;
         sink.cx = (st == 2) ? dt : h2;
         RhsOut y;
-        rhs<VAR, KIN, false, AIR>(xs, sink, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr);
+        if (VAR >= FB_C172X1) {
+            ColumnTap tap; tap.p = E.ctl + (long long)FB_CTL_TAP_ROW * E.pitch + i; tap.pitch = E.pitch; tap.on = (st == 4);
+            rhs<VAR, KIN, false, AIR>(xs, sink, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr, tap);
+        } else rhs<VAR, KIN, false, AIR>(xs, sink, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr);
         if (!AIR) gnd_seen |= y.gnd;
         if (y.err) {
             if (AIR && y.err == FB_NEED_GROUND) {
@@ -228,7 +235,33 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
                              (step_idx / E.log_every) < E.log_capacity;
         YFull yf;
         const int stall_y = stall, eng_y = eng;
-        if (ctl_due || log_due) {   // the saved / fed-back y is the one left by f(x*), before any callback
+        if (ctl_due && !log_due) {
+            // control-law inputs from the tapped intermediates of the f(x*) evaluation just made and from x* itself
+            const double* tp = E.ctl + (long long)FB_CTL_TAP_ROW * E.pitch + i;
+            auto tapv = [&](int k) { return tp[(long long)k * E.pitch]; };
+            q4 q = mkq(tapv(TAP_Q_NB), tapv(TAP_Q_NB + 1), tapv(TAP_Q_NB + 2), tapv(TAP_Q_NB + 3));
+            if (KIN == FB_NED) { yf.theta = sink.sx[(L::KINX + 1) * T_]; yf.phi = sink.sx[(L::KINX + 2) * T_]; }
+            else {   // REuler(q_nb), attitude.jl:382-390
+                yf.theta = asin(clampd(2.0 * (q.w * q.y - q.x * q.z), -1.0, 1.0));
+                yf.phi = atan2(2.0 * (q.w * q.x + q.y * q.z), 1.0 - 2.0 * (q.x * q.x + q.y * q.y));
+            }
+            yf.v_eb_n = mk3(tapv(TAP_V_EB_N), tapv(TAP_V_EB_N + 1), tapv(TAP_V_EB_N + 2));
+            yf.w_wb_b = mk3(tapv(TAP_W_WB_B), tapv(TAP_W_WB_B + 1), tapv(TAP_W_WB_B + 2));
+            yf.w_eb_b = mk3(sink.sx[L::DYN * T_], sink.sx[(L::DYN + 1) * T_], sink.sx[(L::DYN + 2) * T_]);
+            yf.v_gnd = sqrt(dot(yf.v_eb_n, yf.v_eb_n));
+            const bool valid = (KIN == FB_NED) || (yf.v_gnd > 0.1);   // kinematics.jl:212-213 vs :393-394
+            yf.chi_gnd = valid ? atan2(yf.v_eb_n.y, yf.v_eb_n.x) : 0.0;
+            yf.EAS = tapv(TAP_TAS) * sqrt(tapv(TAP_RHO) / isa::rho_std);
+            yf.alpha = tapv(TAP_ALPHA); yf.beta = tapv(TAP_BETA);
+            yf.alpha_filt = sink.sx[L::AERO * T_]; yf.beta_filt = sink.sx[(L::AERO + 1) * T_];
+            yf.eng_n = sink.sx[L::ENG * T_] * (1.0 / (2700 * FB_PI / 30));
+            yf.h_e = sink.sx[(L::KINX + (KIN == FB_WA ? 8 : 5)) * T_];
+#pragma unroll
+            for (int a = 0; a < L::NACT; a++) {
+                yf.act_pos[a] = clampd(sink.sx[(L::ACT + a) * T_], (a == 0 || a >= 4) ? 0.0 : -1.0, 1.0);
+                yf.act_cmd[a] = ug(FB_U_ACT_THROTTLE + a);
+            }
+        } else if (ctl_due || log_due) {   // the saved / fed-back y is the one left by f(x*), before any callback
             double xl[LF::NX], kd[LF::NX];
 #pragma unroll
             for (int c = 0; c < LF::NX; c++) xl[c] = 0.0;

@@ -150,6 +150,16 @@ struct CachedIn {
     }
 };
 
+// Output tap of the lean RHS: the handful of intermediate values the control laws feed back (attitude quaternion, NED
+// velocity, wander-frame body rates, TAS, density, alpha, beta). The integrator stores them when the evaluation is the
+// one at x* (whose outputs the reference's f_periodic! sees), which saves a second, output-producing evaluation.
+enum { TAP_Q_NB = 0, TAP_V_EB_N = 4, TAP_W_WB_B = 7, TAP_TAS = 10, TAP_RHO = 11, TAP_ALPHA = 12, TAP_BETA = 13, TAP_COUNT = 14 };
+struct NoTap { FB_DEV void operator()(int, double) const {} };
+struct ColumnTap {        // column of a [TAP_COUNT][pitch] array, written only while `on`
+    double* p; long long pitch; bool on;
+    FB_DEV void operator()(int k, double v) const { if (on) p[(long long)k * pitch] = v; }
+};
+
 // derivative sink that simply stores into a local array (test hook, trim, output pass)
 struct ArraySink {
     double* xd;
@@ -407,9 +417,9 @@ FB_DEV double interp_2x9_line(const double* y, double n0, double n1, double x0, 
 
 // ------------------------------------------------------------------------------------------- the RHS
 // x: state (read-only; every component is read before its derivative is put into the sink).
-template <int VAR, int KIN, bool WY, bool AIR = false, class Sink, class U>
+template <int VAR, int KIN, bool WY, bool AIR = false, class Sink, class U, class Tap = NoTap>
 FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& u,
-                const double* __restrict__ tb, const float* __restrict__ geoid, RhsOut& out, YFull* yf) {
+                const double* __restrict__ tb, const float* __restrict__ geoid, RhsOut& out, YFull* yf, const Tap tap = Tap()) {
     typedef Lay<VAR, KIN, AIR> L;
     out.wow = 0; out.crash = 0; out.err = 0; out.gnd = 0;
     Kin k;
@@ -483,6 +493,9 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
     }
     if (k.h_e < -1000.0) out.err = FB_ST_BOUNDS;
     k.h_o = k.h_e - geoid_height(geoid, k.lat, k.lon);
+    tap(TAP_Q_NB, k.q_nb.w); tap(TAP_Q_NB + 1, k.q_nb.x); tap(TAP_Q_NB + 2, k.q_nb.y); tap(TAP_Q_NB + 3, k.q_nb.z);
+    tap(TAP_V_EB_N, k.v_eb_n.x); tap(TAP_V_EB_N + 1, k.v_eb_n.y); tap(TAP_V_EB_N + 2, k.v_eb_n.z);
+    tap(TAP_W_WB_B, k.w_wb_b.x); tap(TAP_W_WB_B + 1, k.w_wb_b.y); tap(TAP_W_WB_B + 2, k.w_wb_b.z);
     if (WY) {
         q4 q = k.q_nb;
         if (KIN == FB_NED) { yf->psi = x[L::KINX]; yf->theta = x[L::KINX + 1]; yf->phi = x[L::KINX + 2]; }
@@ -512,6 +525,7 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
         air.iTAS = fb_rsqrt(fb_max(tas2, 1e-280));
         air.TAS = tas2 * air.iTAS;
         air.q = 0.5 * air.rho * tas2;
+        tap(TAP_TAS, air.TAS); tap(TAP_RHO, air.rho);
     }
     if (WY) {   // atmosphere.jl:220-242
         yf->TAS = air.TAS; yf->q = air.q;
@@ -564,6 +578,7 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
             ca = (moving && planar) ? v.x * ivxz : 1.0; sa = (moving && planar) ? v.z * ivxz : 0.0;
         }
         out.alpha = alpha;
+        tap(TAP_ALPHA, alpha); tap(TAP_BETA, beta);
         double i2V = (air.TAS > 1.0) ? 0.5 * air.iTAS : 0.5;   // 1 / (2 max(TAS, V_min)), V_min = 1
         double afd = (1.0 / tau_f) * (alpha - alpha_filt), bfd = (1.0 / tau_f) * (beta - beta_filt);
         sink.put(L::AERO, afd); sink.put(L::AERO + 1, bfd);

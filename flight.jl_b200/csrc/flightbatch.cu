@@ -51,6 +51,7 @@ struct fb_sim {
     cudaEvent_t ground_ev = nullptr;
     bool ground_ev_pending = false;
     bool air_mode = true;
+    bool air_wide = false;           // airborne kernel shape: FB_STEP_BLOCK_WIDE threads (one-wave ensembles) or FB_STEP_BLOCK
 };
 
 // ------------------------------------------------------------------------------------ kernel dispatch
@@ -66,8 +67,12 @@ template <int VAR, int KIN> struct Ops {
         if (s->air_mode) {
             int Ta = s->step_block_air;
             int grid_a = (int)((s->E.n + Ta - 1) / Ta);
-            step_kernel<VAR, KIN, true><<<grid_a, Ta, StepShape<VAR, KIN, true>::SMEM, s->stream>>>(
-                s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_resume, 0, s->d_ground);
+            if (s->air_wide)
+                step_kernel<VAR, KIN, true, FB_STEP_BLOCK_WIDE><<<grid_a, Ta, StepShape<VAR, KIN, true, FB_STEP_BLOCK_WIDE>::SMEM, s->stream>>>(
+                    s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_resume, 0, s->d_ground);
+            else
+                step_kernel<VAR, KIN, true><<<grid_a, Ta, StepShape<VAR, KIN, true>::SMEM, s->stream>>>(
+                    s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_resume, 0, s->d_ground);
             step_kernel<VAR, KIN, false><<<grid, T, StepShape<VAR, KIN, false>::SMEM, s->stream>>>(
                 s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_resume, 1, s->d_ground);
             *launched = 2;
@@ -78,11 +83,17 @@ template <int VAR, int KIN> struct Ops {
         }
         return cudaGetLastError();
     }
-    static int step_tmax(bool air) { return air ? StepShape<VAR, KIN, true>::T : StepShape<VAR, KIN, false>::T; }
+    // shape 0: complete kernel, 1: airborne, 2: airborne wide
+    static int step_tmax(int shape) {
+        return shape == 0 ? StepShape<VAR, KIN, false>::T : (shape == 1 ? StepShape<VAR, KIN, true>::T : StepShape<VAR, KIN, true, FB_STEP_BLOCK_WIDE>::T);
+    }
     static cudaError_t prepare(fb_sim* s) {
         cudaError_t e = cudaFuncSetAttribute(step_kernel<VAR, KIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StepShape<VAR, KIN, false>::SMEM);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(step_kernel<VAR, KIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StepShape<VAR, KIN, true>::SMEM);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(step_kernel<VAR, KIN, true, FB_STEP_BLOCK_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)StepShape<VAR, KIN, true, FB_STEP_BLOCK_WIDE>::SMEM);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(rhs_kernel<VAR, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES);
         if (e != cudaSuccess) return e;
@@ -125,8 +136,10 @@ template <int VAR, int KIN> struct Ops {
         return cudaGetLastError();
     }
 };
-#ifdef FB_ONLY_S_WA   // development build: one instantiation only (fast compile)
+#if defined(FB_ONLY_S_WA)   // development builds: one instantiation only (fast compile)
 #define FB_DISPATCH(s, CALL) (Ops<FB_C172S, FB_WA>::CALL)
+#elif defined(FB_ONLY_X1_WA)
+#define FB_DISPATCH(s, CALL) (Ops<FB_C172X1, FB_WA>::CALL)
 #else
 #define FB_DISPATCH(s, CALL)                                                            \
     ((s)->var_t == FB_C172S ? ((s)->cfg.kinematics == FB_WA ? Ops<FB_C172S, FB_WA>::CALL : Ops<FB_C172S, FB_NED>::CALL) \
@@ -284,13 +297,19 @@ int32_t fb_create(const fb_config* cfg, fb_handle* out) {
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, cfg->device));
         int sms = prop.multiProcessorCount;
-        for (int air = 0; air < 2; air++) {
-            int tmax = FB_DISPATCH(s, step_tmax)(air != 0);   // compile-time column stride of the instantiation (fits 227 KB)
-            int T = (int)std::min<long long>(tmax, (N + 31) / 32 * 32);
+        // largest block <= tmax that keeps the number of CTA waves (balances the last wave); returns the wave count
+        auto shape = [&](int tmax, int& T) {
+            T = (int)std::min<long long>(tmax, (N + 31) / 32 * 32);
             long long waves = ((N + T - 1) / T + sms - 1) / sms;
             while (T > 32 && (((N + (T - 32) - 1) / (T - 32) + sms - 1) / sms) == waves) T -= 32;
-            (air ? s->step_block_air : s->step_block) = T;
-        }
+            return waves;
+        };
+        shape(FB_DISPATCH(s, step_tmax)(0), s->step_block);
+        int Tn, Tw;
+        long long waves_n = shape(FB_DISPATCH(s, step_tmax)(1), Tn), waves_w = shape(FB_DISPATCH(s, step_tmax)(2), Tw);
+        // cost model: a launch of the wide (128-register) shape takes ~1.45x as long as one of the 168-register shape
+        s->air_wide = (double)waves_w * 1.45 < (double)waves_n;
+        s->step_block_air = s->air_wide ? Tw : Tn;
     }
     CK(cudaMalloc(&s->d_resume, sizeof(int) * s->pitch));
     CK(cudaMalloc(&s->d_ground, sizeof(unsigned)));
