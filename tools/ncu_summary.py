@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Summarise an Nsight Compute report (read here on the CPU box) into the text kept under profiles/.
-usage: ncu_summary.py <report.ncu-rep> [--json out.json]
+usage: ncu_summary.py <report.ncu-rep | raw_page.csv> [--json out.json]
 Prints, per captured launch: duration, DRAM bytes, registers, shared memory, achieved occupancy, pipe utilisation
 (FP64 / FMA / ALU / LSU), issue-slot utilisation, L1/L2 traffic, local-memory traffic and the top stall reasons."""
 import csv
@@ -31,7 +31,10 @@ KEYS = [
 
 def main():
     rep = sys.argv[1]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):      # `ncu -i report --page raw --csv` already run where the report was taken
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     out = []
