@@ -199,6 +199,74 @@ class TrimParameters:
         self.values = dict(kw)
 
 
+# WGS84 (lib/FlightPhysics/src/geodesy.jl:23-38)
+_WGS_A, _WGS_F = 6378137.0, 1.0 / 298.257223563
+_WGS_E2 = 2 * _WGS_F - _WGS_F * _WGS_F
+
+
+def _cartesian(lat, lon, h):
+    """Cartesian(Geographic{LatLon,Ellipsoidal}) (geodesy.jl:418-428): ECEF position [3, ...]."""
+    sl, cl = np.sin(lat), np.cos(lat)
+    N = _WGS_A / np.sqrt(1.0 - _WGS_E2 * sl * sl)
+    return np.stack([(N + h) * cl * np.cos(lon), (N + h) * cl * np.sin(lon), (N * (1 - _WGS_E2) + h) * sl])
+
+
+def _ned_axes(lat, lon):
+    """Unit vectors of the local tangent frame NED(lat, lon) in ECEF axes (the rotation ltf() encodes, geodesy.jl:132-135)."""
+    sl, cl, so, co = np.sin(lat), np.cos(lat), np.sin(lon), np.cos(lon)
+    north = np.stack([-sl * co, -sl * so, cl])
+    east = np.stack([-so, co, np.zeros_like(sl)])
+    return north, east
+
+
+def _latlon_from_cartesian(r):
+    """LatLon(Cartesian) (geodesy.jl:367-412: Fukushima's method, one Halley iteration)."""
+    x, y, z = r
+    p = np.sqrt(x * x + y * y)
+    c, ec2 = _WGS_A * _WGS_E2, 1.0 - _WGS_E2
+    ec = np.sqrt(ec2)
+    zc, s0, c0 = ec * np.abs(z), np.abs(z), ec * p
+    a0 = np.sqrt(s0 * s0 + c0 * c0)
+    a03 = a0 ** 3
+    b0 = 1.5 * c * s0 * c0 * ((p * s0 - zc * c0) * a0 - c * s0 * c0)
+    s1 = (zc * a03 + c * s0 ** 3) * a03 - b0 * s0
+    cc = ec * ((p * a03 - c * c0 ** 3) * a03 - b0 * c0)
+    lat = np.sign(z) * np.arctan2(s1, cc)
+    return lat, np.arctan2(y, x)
+
+
+class Segment:
+    """C172XGuidance.Segment (c172x_gdc.jl:38-98): a straight target segment p1 -> p2, each point (lat, lon, h_e) as
+    Geographic{LatLon,Ellipsoidal}; scalars or arrays of N values. Vertical or degenerate segments are refused as the
+    reference does (horizontal length seen from p1 below 1e-6 m -> ValueError, the reference's ArgumentError)."""
+
+    def __init__(self, p1, p2):
+        self.p1 = tuple(np.asarray(v, dtype=np.float64) for v in p1)
+        self.p2 = tuple(np.asarray(v, dtype=np.float64) for v in p2)
+        r12 = _cartesian(*self.p2) - _cartesian(*self.p1)
+        north, east = _ned_axes(self.p1[0], self.p1[1])
+        s12 = np.hypot((north * r12).sum(axis=0), (east * r12).sum(axis=0))
+        if np.any(s12 < 1e-6):
+            raise ValueError("Segment is vertical or degenerate")
+
+    @classmethod
+    def from_origin(cls, p1, s, chi, gamma=None, dh=None):
+        """Segment(p1; s, χ, γ | Δh) (c172x_gdc.jl:64-88): horizontal length s along azimuth χ from p1."""
+        if (gamma is None) == (dh is None):
+            raise TypeError("provide either gamma (flight path angle) or dh (altitude increment)")
+        lat1, lon1, h1 = (np.asarray(v, dtype=np.float64) for v in p1)
+        s, chi = np.asarray(s, dtype=np.float64), np.asarray(chi, dtype=np.float64)
+        if dh is None:
+            dh = s * np.tan(gamma)
+        north, east = _ned_axes(lat1, lon1)
+        r2 = _cartesian(lat1, lon1, h1) + north * (s * np.cos(chi)) + east * (s * np.sin(chi))
+        lat2, lon2 = _latlon_from_cartesian(r2)
+        return cls((lat1, lon1, h1), (lat2, lon2, h1 + dh))
+
+    def __neg__(self):
+        return Segment(self.p2, self.p1)
+
+
 class Init:
     """C172.Init(KinInit(q_nb, location, h, ω_wb_b, v_eb_n), SystemsInitializer(...)) — c172.jl:773-794"""
     FIELDS = dict(q0=1.0, q1=0.0, q2=0.0, q3=0.0, lat=0.0, lon=0.0, h_e=0.0, w0=0.0, w1=0.0, w2=0.0, vN=0.0, vE=0.0, vD=0.0,
@@ -370,6 +438,11 @@ class BatchSimulation:
             a = np.ascontiguousarray(a)
             assert a.shape == (self.n,)
             _ck(self._lib.fb_set_input(self._h, field, _dp(a), 1), self._lib)
+
+    def set_segment(self, seg):
+        """avionics.gdc.seg.u.target = seg (Cessna172Xv2): one Segment for all members or one per member."""
+        for k, v in zip(("lat1", "lon1", "h1", "lat2", "lon2", "h2"), seg.p1 + seg.p2):
+            self.set_input("gdc_" + k, v if np.ndim(v) else float(v))
 
     def get_input(self, field):
         field = INPUT_NAMES[field] if isinstance(field, str) else int(field)

@@ -14,7 +14,10 @@
 #pragma once
 #include "fb_physics.cuh"
 
-#define FB_CTL_STATE_COUNT 64
+#define FB_CTL_STATE_COUNT 80
+#define FB_CTL_TAP_ROW 48      // rows 48..63 of the column: output tap of the integrator (TAP_COUNT values, fb_physics.cuh)
+#define FB_CTL_GDC_ROW 64      // rows 64..75: outputs of the last guidance update (GDC_* below), written in place
+enum { GDC_MODE = 0, GDC_HOR, GDC_VRT, GDC_DCHI, GDC_CHI_REF, GDC_H_REF, GDC_CHI_12, GDC_GAMMA_12, GDC_S_12, GDC_S_1B, GDC_E_SB, GDC_V_SB, GDC_COUNT };
 
 enum { LON_DIRECT = 0, LON_SAS, LON_THR_Q, LON_THR_THETA, LON_THR_EAS, LON_EAS_Q, LON_EAS_THETA, LON_EAS_CLM, LON_EAS_ALT };  // c172x_ctl.jl:29-41
 enum { LAT_DIRECT = 0, LAT_SAS, LAT_P_BETA, LAT_PHI_BETA, LAT_CHI_BETA };                                                  // :733-741
@@ -30,6 +33,7 @@ struct CtlState {
     double te2te_zref1, pb2ar_zref0;                // te2te_lqr.u.z_ref.elevator_cmd, φβ2ar_lqr.u.z_ref.φ (read on resets)
     IntS q2e_int, p2phi_int;
     PidS q2e_pid, c2t_pid, v2t_pid, p2phi_pid, chi2phi_pid;
+    double* gdc = nullptr; long long gdc_pitch = 0;   // this member's guidance outputs (rows FB_CTL_GDC_ROW.. of its column)
 
     template <bool STORE>
     FB_DEV void xfer(double* p, long long pitch) {
@@ -43,11 +47,10 @@ struct CtlState {
         L(te2te); L(tv2te); L(vh2te); L(ar2ar); L(pb2ar); D(te2te_zref1); D(pb2ar_zref0);
         N(q2e_int); N(p2phi_int); P(q2e_pid); P(c2t_pid); P(v2t_pid); P(p2phi_pid); P(chi2phi_pid);
     }
-    FB_DEV void load(double* p, long long pitch) { xfer<false>(p, pitch); }
+    FB_DEV void load(double* p, long long pitch) { xfer<false>(p, pitch); gdc = p + (long long)FB_CTL_GDC_ROW * pitch; gdc_pitch = pitch; }
     FB_DEV void store(double* p, long long pitch) { xfer<true>(p, pitch); }
 };
 #define FB_CTL_ROW_H_STATE 2   // row of h_state in the column (constructed-model default: hold = 1)
-#define FB_CTL_TAP_ROW 48      // rows 48..61 of the column: output tap of the integrator (TAP_COUNT values, fb_physics.cuh)
 
 __host__ __device__ inline double avionics_saturate_input(int f, double v) {
     switch (f) {
@@ -89,7 +92,9 @@ FB_DEV double pick_output(const YFull& y, int stall, int eng, const CtlState& cs
         case FB_Y_THROTTLE_CMD: return cs.thr_cmd; case FB_Y_ELEVATOR_CMD: return cs.ele_cmd;
         case FB_Y_AILERON_CMD: return cs.ail_cmd; case FB_Y_RUDDER_CMD: return cs.rud_cmd;
         case FB_Y_ALT_STATE: return (double)cs.h_state;
-        default: return nan("");
+        default:
+            if (field >= FB_Y_GDC_MODE && field <= FB_Y_GDC_V_SB && cs.gdc) return cs.gdc[(long long)(field - FB_Y_GDC_MODE) * cs.gdc_pitch];
+            return nan("");
     }
 }
 
@@ -295,6 +300,46 @@ __device__ __noinline__ void lat_periodic(CtlState& cs, const YFull& v, int wow,
     cs.rud_cmd = clampd(rudder_cmd, -1.0, 1.0);
 }
 
+// ------------------------------------------------------------------------------------------ guidance (Cessna172Xv2)
+// f_periodic!(GuidanceLaws, ctl, vehicle): c172x_gdc.jl:297-329 -> SegmentGuidance :228-252 -> SegmentGuidanceData :113-148
+// (dchi_inf = pi/2, e_sf = 250 m, e_thr = 1000 m, :203-207). On a Cessna172Xv1 the mode request stays `direct` (the host
+// refuses guidance inputs there), which makes this a no-op. Cold code: runs once per control period, IEEE arithmetic.
+__device__ __noinline__ void gdc_periodic(const CtlState& cs, double lat, double lon, double h_e, int wow, const MemberIn& u) {
+    const int mode = wow ? 0 : (int)u(FB_U_GDC_MODE_REQ);
+    auto out = [&](int k, double v) { cs.gdc[(long long)k * cs.gdc_pitch] = v; };
+    if (mode == 1) {
+        auto cart = [](double la, double lo, double h) {   // Cartesian(Geographic{LatLon}), geodesy.jl:418-428
+            double sl, cl, so, co;
+            sincos(la, &sl, &cl); sincos(lo, &so, &co);
+            double N = wgs::a / sqrt(1.0 - wgs::e2 * sl * sl);
+            return mk3((N + h) * cl * co, (N + h) * cl * so, (N * (1 - wgs::e2) + h) * sl);
+        };
+        const double h1 = u(FB_U_GDC_H1), h2 = u(FB_U_GDC_H2);
+        d3 r1 = cart(u(FB_U_GDC_LAT1), u(FB_U_GDC_LON1), h1), r2 = cart(u(FB_U_GDC_LAT2), u(FB_U_GDC_LON2), h2), rb = cart(lat, lon, h_e);
+        double sl2, cl2, sa2, ca2;   // ltf(Ob) = Rz(lon) o Ry(-(lat + pi/2)), geodesy.jl:132-135
+        sincos(0.5 * lon, &sl2, &cl2); sincos(-0.5 * (lat + 0.5 * FB_PI), &sa2, &ca2);
+        q4 q_en = qmul(mkq(cl2, 0, 0, sl2), mkq(ca2, 0, sa2, 0));
+        d3 r_1b = qrot_inv(q_en, rb - r1), r_12 = qrot_inv(q_en, r2 - r1);
+        double s_12 = sqrt(r_12.x * r_12.x + r_12.y * r_12.y);
+        double ux = r_12.x / s_12, uy = r_12.y / s_12;
+        double s_1b = ux * r_1b.x + uy * r_1b.y;
+        double e_sb = ux * r_1b.y - uy * r_1b.x;
+        double h_s = h1 + (h2 - h1) * s_1b / s_12;
+        double chi_12 = atan2(uy, ux);
+        double dchi = -(0.5 * FB_PI) / (0.5 * FB_PI) * atan(e_sb / 250.0);
+        double xw = chi_12 + dchi;
+        double chi_ref = xw + 2.0 * FB_PI * floor((FB_PI - xw) / (2.0 * FB_PI));   // wrap_to_pi, attitude.jl:478
+        const bool hor = u(FB_U_GDC_HOR_REQ) != 0.0;
+        const bool vrt = (fabs(e_sb) < 1000.0) ? (u(FB_U_GDC_VRT_REQ) != 0.0) : false;
+        out(GDC_HOR, hor ? 1.0 : 0.0); out(GDC_VRT, vrt ? 1.0 : 0.0); out(GDC_DCHI, dchi); out(GDC_CHI_REF, chi_ref); out(GDC_H_REF, h_s);
+        out(GDC_CHI_12, chi_12); out(GDC_GAMMA_12, atan2(h2 - h1, s_12)); out(GDC_S_12, s_12); out(GDC_S_1B, s_1b); out(GDC_E_SB, e_sb);
+        out(GDC_V_SB, h_e - h_s);
+        if (hor) { u.set(FB_U_LAT_CHI_REF, chi_ref); u.set(FB_U_LAT_MODE_REQ, (double)LAT_CHI_BETA); }
+        if (vrt) { u.set(FB_U_LON_H_REF, h_s); u.set(FB_U_LON_MODE_REQ, (double)LON_EAS_ALT); }
+    }
+    out(GDC_MODE, (double)mode);
+}
+
 // assign!(vehicle, avionics): c172x_ctl.jl:449-458, 986-995 — the four fly-by-wire commands the control laws own
 FB_DEV bool avionics_assign(const CtlState& cs, const MemberIn& u) {
     bool ch = false;
@@ -312,6 +357,7 @@ template <int VAR, int KIN>
 FB_DEV bool avionics_periodic(const YFull& yf, const RhsOut& y, const MemberIn& u,
                               CtlState& cs, const FbDeviceTables& T, double Dt) {
     if (VAR < FB_C172X1) return false;
+    gdc_periodic(cs, yf.lat, yf.lon, yf.h_e, y.wow, u);
     lon_periodic(cs, yf, y.wow, u, T, Dt, (int)u(FB_U_LON_MODE_REQ));
     lat_periodic(cs, yf, y.wow, u, T, Dt, (int)u(FB_U_LAT_MODE_REQ));
     return avionics_assign(cs, u);

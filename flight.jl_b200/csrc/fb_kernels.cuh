@@ -253,6 +253,7 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
             yf.chi_gnd = valid ? atan2(yf.v_eb_n.y, yf.v_eb_n.x) : 0.0;
             yf.EAS = tapv(TAP_TAS) * sqrt(tapv(TAP_RHO) / isa::rho_std);
             yf.alpha = tapv(TAP_ALPHA); yf.beta = tapv(TAP_BETA);
+            yf.lat = tapv(TAP_LAT); yf.lon = tapv(TAP_LON);
             yf.alpha_filt = sink.sx[L::AERO * T_]; yf.beta_filt = sink.sx[(L::AERO + 1) * T_];
             yf.eng_n = sink.sx[L::ENG * T_] * (1.0 / (2700 * FB_PI / 30));
             yf.h_e = sink.sx[(L::KINX + (KIN == FB_WA ? 8 : 5)) * T_];

@@ -150,10 +150,10 @@ struct CachedIn {
     }
 };
 
-// Output tap of the lean RHS: the handful of intermediate values the control laws feed back (attitude quaternion, NED
-// velocity, wander-frame body rates, TAS, density, alpha, beta). The integrator stores them when the evaluation is the
+// Output tap of the lean RHS: the handful of intermediate values the control and guidance laws feed back (attitude
+// quaternion, NED velocity, wander-frame body rates, TAS, density, alpha, beta, latitude, longitude). The integrator stores them when the evaluation is the
 // one at x* (whose outputs the reference's f_periodic! sees), which saves a second, output-producing evaluation.
-enum { TAP_Q_NB = 0, TAP_V_EB_N = 4, TAP_W_WB_B = 7, TAP_TAS = 10, TAP_RHO = 11, TAP_ALPHA = 12, TAP_BETA = 13, TAP_COUNT = 14 };
+enum { TAP_Q_NB = 0, TAP_V_EB_N = 4, TAP_W_WB_B = 7, TAP_TAS = 10, TAP_RHO = 11, TAP_ALPHA = 12, TAP_BETA = 13, TAP_LAT = 14, TAP_LON = 15, TAP_COUNT = 16 };
 struct NoTap { FB_DEV void operator()(int, double) const {} };
 struct ColumnTap {        // column of a [TAP_COUNT][pitch] array, written only while `on`
     double* p; long long pitch; bool on;
@@ -493,6 +493,7 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
     }
     if (k.h_e < -1000.0) out.err = FB_ST_BOUNDS;
     k.h_o = k.h_e - geoid_height(geoid, k.lat, k.lon);
+    tap(TAP_LAT, k.lat); tap(TAP_LON, k.lon);
     tap(TAP_Q_NB, k.q_nb.w); tap(TAP_Q_NB + 1, k.q_nb.x); tap(TAP_Q_NB + 2, k.q_nb.y); tap(TAP_Q_NB + 3, k.q_nb.z);
     tap(TAP_V_EB_N, k.v_eb_n.x); tap(TAP_V_EB_N + 1, k.v_eb_n.y); tap(TAP_V_EB_N + 2, k.v_eb_n.z);
     tap(TAP_W_WB_B, k.w_wb_b.x); tap(TAP_W_WB_B + 1, k.w_wb_b.y); tap(TAP_W_WB_B + 2, k.w_wb_b.z);

@@ -216,6 +216,7 @@ static double default_input(int f) {
         case FB_U_M_PILOT: case FB_U_M_COPILOT: return 75.0; case FB_U_M_BAGGAGE: return 50.0;
         case FB_U_T_SL: return 288.15; case FB_U_P_SL: return 101325.0;
         case FB_U_LON_EAS_REF: return 50.0;
+        case FB_U_GDC_LAT2: return 1e-3;   // Segment() default target, c172x_gdc.jl:90
         default: return 0.0;
     }
 }
@@ -528,6 +529,8 @@ int32_t fb_set_input(fb_handle s, int32_t field, const double* values, int64_t s
     if (!s || !values) return fail(FB_ERR_ARG, "fb_set_input: null argument");
     if (field < 0 || field >= FB_U__COUNT) return fail(FB_ERR_ARG, "fb_set_input: unknown field");
     if (stride != 0 && stride != 1) return fail(FB_ERR_ARG, "fb_set_input: stride must be 0 (broadcast) or 1");
+    if (field >= FB_U_GDC_MODE_REQ && field <= FB_U_GDC_H2 && s->cfg.variant != FB_C172X2)
+        return fail(FB_ERR_ARG, "fb_set_input: guidance inputs exist only on Cessna172Xv2");
     CK(cudaSetDevice(s->cfg.device));
     double* row = s->E.u + (long long)field * s->pitch;
     if (stride == 0) {

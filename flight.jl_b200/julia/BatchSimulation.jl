@@ -11,7 +11,7 @@
 # There is no CPU fallback: every call goes to libflightbatch.so and throws FlightBatchError on a non-zero return.
 module BatchSimulations
 
-export BatchSimulation, FlightBatchError, init!, step!, run!, setinput!, getinput, getoutput, schedule_inputs!,
+export BatchSimulation, FlightBatchError, init!, step!, run!, setinput!, getinput, getoutput, schedule_inputs!, set_segment!,
        status, stats, linearize, TimeSeriesColumn
 
 const libflightbatch = get(ENV, "FLIGHTBATCH_LIB", joinpath(@__DIR__, "..", "libflightbatch.so"))
@@ -29,7 +29,7 @@ check(rc::Int32) = rc == 0 ? nothing : throw(FlightBatchError(rc, last_error()))
 # enums of include/flightbatch.h (kept in the same order; FB_API_VERSION is checked at load)
 @enum Variant::Int32 C172S = 0 C172X0 = 1 C172X1 = 2 C172X2 = 3
 @enum KinematicsKind::Int32 WA = 0 ECEF = 1 NED = 2
-const FB_API_VERSION = 2
+const FB_API_VERSION = 3
 
 # struct fb_config (must match the C layout field by field)
 struct FbConfig
@@ -134,6 +134,24 @@ end
 function getoutput(sim::BatchSimulation, field::Integer)
     out = Vector{Float64}(undef, sim.n)
     check(ccall((:fb_get_output, libflightbatch), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}), sim.handle, field, out)); out
+end
+
+# Cessna172Xv2 guidance (c172x_gdc.jl): fb_input ids of GuidanceLaws.u / SegmentGuidance.u
+const FB_U_GDC_MODE_REQ, FB_U_GDC_HOR_REQ, FB_U_GDC_VRT_REQ = Int32(70), Int32(71), Int32(72)
+const FB_U_GDC_LAT1 = Int32(73)   # then LON1, H1, LAT2, LON2, H2
+
+"""
+    set_segment!(sim, p1, p2)
+
+`avionics.gdc.seg.u.target = Segment(p1, p2)` for every member: `p1`, `p2` are `(lat, lon, h_e)` tuples of scalars or
+N-vectors, i.e. the fields of the reference's `Geographic{LatLon,Ellipsoidal}` end points. With Flight.jl loaded, pass
+`(seg.p1.loc.ϕ, seg.p1.loc.λ, Float64(seg.p1.h))` of a `C172XGuidance.Segment`, whose constructor has already refused
+vertical or degenerate segments (c172x_gdc.jl:44-58).
+"""
+function set_segment!(sim::BatchSimulation, p1, p2)
+    for (k, v) in enumerate((p1..., p2...))
+        setinput!(sim, FB_U_GDC_LAT1 + Int32(k - 1), v)
+    end
 end
 
 "declarative replacement of `user_callback!` (sim.jl:331-341): piecewise-constant per-member inputs"

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FB_API_VERSION 2
+#define FB_API_VERSION 3
 
 /* error codes */
 #define FB_OK 0
@@ -38,7 +38,7 @@ extern "C" {
 #define FB_C172S 0   /* Cessna172Sv0: mechanical actuation, NoAvionics          */
 #define FB_C172X0 1  /* Cessna172Xv0: fly-by-wire actuators, NoAvionics         */
 #define FB_C172X1 2  /* Cessna172Xv1: + C172XControl.ControlLaws                */
-#define FB_C172X2 3  /* Cessna172Xv2: + guidance (ModeGuidance.direct pass-through) */
+#define FB_C172X2 3  /* Cessna172Xv2: + C172XGuidance.GuidanceLaws (direct and segment modes) */
 /* kinematic mechanisation: lib/FlightPhysics/src/kinematics.jl:150,250,329 */
 #define FB_WA 0
 #define FB_ECEF 1
@@ -83,8 +83,11 @@ enum fb_input {
     /* C172XControl.ControlLawsLat.u, c172x_ctl.jl:826-836 */
     FB_U_LAT_MODE_REQ = 60, FB_U_LAT_AILERON_AXIS, FB_U_LAT_AILERON_OFFSET, FB_U_LAT_RUDDER_AXIS, FB_U_LAT_RUDDER_OFFSET,
     FB_U_LAT_P_REF, FB_U_LAT_BETA_REF, FB_U_LAT_PHI_REF, FB_U_LAT_CHI_REF,
-    /* C172XGuidance.GuidanceLaws.u.mode_req, c172x_gdc.jl:281-283 (0 = direct) */
-    FB_U_GDC_MODE_REQ = 70,
+    /* C172XGuidance.GuidanceLaws.u.mode_req, c172x_gdc.jl:281-283 (0 = direct, 1 = segment), and SegmentGuidance.u
+     * (c172x_gdc.jl:209-213): the two guidance requests and the target Segment's end points p1, p2 as
+     * Geographic{LatLon,Ellipsoidal} (:38-41); default target Segment() = (0, 0, 0) -> (lat 1e-3, 0, 0) (:90) */
+    FB_U_GDC_MODE_REQ = 70, FB_U_GDC_HOR_REQ, FB_U_GDC_VRT_REQ,
+    FB_U_GDC_LAT1, FB_U_GDC_LON1, FB_U_GDC_H1, FB_U_GDC_LAT2, FB_U_GDC_LON2, FB_U_GDC_H2,
     FB_U__COUNT = 80
 };
 
@@ -110,6 +113,10 @@ enum fb_output {
     FB_Y_LON_MODE, FB_Y_LAT_MODE,                  /* avionics.ctl.lon.mode / lat.mode      */
     FB_Y_THROTTLE_CMD, FB_Y_ELEVATOR_CMD, FB_Y_AILERON_CMD, FB_Y_RUDDER_CMD,
     FB_Y_ALT_STATE,                                /* avionics.ctl.lon.s.h_state: 0 acquire, 1 hold (c172x_ctl.jl:44-47) */
+    /* avionics.gdc (Cessna172Xv2): GuidanceLawsY.mode and SegmentGuidanceY / SegmentGuidanceData of the last guidance
+     * update (c172x_gdc.jl:101-111,215-223,285-289) */
+    FB_Y_GDC_MODE, FB_Y_GDC_HOR, FB_Y_GDC_VRT, FB_Y_GDC_DCHI, FB_Y_GDC_CHI_REF, FB_Y_GDC_H_REF,
+    FB_Y_GDC_CHI_12, FB_Y_GDC_GAMMA_12, FB_Y_GDC_S_12, FB_Y_GDC_S_1B, FB_Y_GDC_E_SB, FB_Y_GDC_V_SB,
     FB_Y__COUNT
 };
 

@@ -62,6 +62,9 @@ def _load(name):
         "orc_h2delta": (dbl, [dbl]),
         "orc_gain_lookup": (i32, [i32, dbl, dbl, dp]),
         "orc_geo_roundtrip": (None, [dbl, dbl, dbl, dp]),
+        "orc_segment_end": (None, [dbl, dbl, dbl, dbl, dbl, dbl, dp]),
+        "orc_segment_data": (None, [dp, dp, dp, dp]),
+        "orc_segment_valid": (i32, [dp, dp]),
     }
     for k, (res, args) in sig.items():
         f = getattr(lib, k)
@@ -265,6 +268,31 @@ def gain_lookup(which, EAS, h):
     out = np.zeros(64)
     n = lib().orc_gain_lookup(int(which), float(EAS), float(h), _dp(out))
     return out[:n]
+
+
+def segment_end(p1, s, chi, dh=None, gamma=None):
+    """Segment(p1; s, chi, gamma | dh).p2 with p1 = (lat, lon, h_e) (c172x_gdc.jl:64-88)."""
+    assert (dh is None) != (gamma is None)
+    if dh is None:
+        dh = s * np.tan(gamma)
+    out = np.zeros(3)
+    lib().orc_segment_end(float(p1[0]), float(p1[1]), float(p1[2]), float(s), float(chi), float(dh), _dp(out))
+    return tuple(out)
+
+
+SEG_FIELDS = ("chi_12", "gamma_12", "s_12", "s_1b", "s_2b", "e_sb", "v_sb", "h_s")
+
+
+def segment_data(p1, p2, ob):
+    """SegmentGuidanceData(Segment(p1, p2), Ob) as a dict (c172x_gdc.jl:113-148)."""
+    a, b, o, out = (np.array(v, dtype=np.float64) for v in (p1, p2, ob, np.zeros(8)))
+    lib().orc_segment_data(_dp(a), _dp(b), _dp(o), _dp(out))
+    return dict(zip(SEG_FIELDS, out))
+
+
+def segment_valid(p1, p2):
+    a, b = np.array(p1, dtype=np.float64), np.array(p2, dtype=np.float64)
+    return bool(lib().orc_segment_valid(_dp(a), _dp(b)))
 
 
 def batch_step(sims, n_steps, threads):

@@ -412,6 +412,26 @@ void orc_geo_roundtrip(double lat, double lon, double h_e, double* out7) {
 }
 
 // op counters (only meaningful in the ORC_COUNT build)
+// Segment(p1; s, chi, dh) -> p2 = out3 {lat, lon, h}; SegmentGuidanceData(seg, Ob) -> out8 {chi_12, gamma_12, s_12, s_1b,
+// s_2b, e_sb, v_sb, h_s}; validity of Segment(p1, p2) (c172x_gdc.jl:38-148)
+void orc_segment_end(double lat1, double lon1, double h1, double s, double chi, double dh, double* out3) {
+    GeoLLH p1; p1.ll.lat = lat1; p1.ll.lon = lon1; p1.h = h1;
+    GeoLLH p2 = segment_end(p1, s, chi, dh);
+    out3[0] = val(p2.ll.lat); out3[1] = val(p2.ll.lon); out3[2] = val(p2.h);
+}
+void orc_segment_data(const double* p1, const double* p2, const double* ob, double* out8) {
+    GeoLLH a, b, o;
+    a.ll.lat = p1[0]; a.ll.lon = p1[1]; a.h = p1[2]; b.ll.lat = p2[0]; b.ll.lon = p2[1]; b.h = p2[2]; o.ll.lat = ob[0]; o.ll.lon = ob[1]; o.h = ob[2];
+    SegmentData d = segment_data(a, b, o);
+    out8[0] = val(d.chi_12); out8[1] = val(d.gamma_12); out8[2] = val(d.s_12); out8[3] = val(d.s_1b); out8[4] = val(d.s_2b);
+    out8[5] = val(d.e_sb); out8[6] = val(d.v_sb); out8[7] = val(d.h_s);
+}
+int orc_segment_valid(const double* p1, const double* p2) {
+    GeoLLH a, b;
+    a.ll.lat = p1[0]; a.ll.lon = p1[1]; a.h = p1[2]; b.ll.lat = p2[0]; b.ll.lon = p2[1]; b.h = p2[2];
+    return segment_valid(a, b) ? 1 : 0;
+}
+
 void orc_ops_reset() {
 #if ORC_COUNT
     g_ops = OpCounts();

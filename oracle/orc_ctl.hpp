@@ -117,6 +117,48 @@ struct LQRc {   // control.jl:620-743, NU = NZ = 2
     }
 };
 
+// ------------------------------------------------------------------------------------------------ guidance
+// Segment / SegmentGuidanceData: lib/FlightApps/src/c172/c172x/guidance/c172x_gdc.jl:38-148
+struct GeoLLH { LatLon ll; real h; };
+struct SegmentData { real chi_12 = 0.0, gamma_12 = 0.0, s_12 = 0.0, s_1b = 0.0, s_2b = 0.0, e_sb = 0.0, v_sb = 0.0, h_s = 0.0; };
+inline SegmentData segment_data(GeoLLH p1, GeoLLH p2, GeoLLH ob) {   // c172x_gdc.jl:113-148
+    V3 r_e1_e = cartesian_from_geo(n_from_latlon(p1.ll), p1.h);
+    V3 r_e2_e = cartesian_from_geo(n_from_latlon(p2.ll), p2.h);
+    V3 r_eb_e = cartesian_from_geo(n_from_latlon(ob.ll), ob.h);
+    Q4 q_en = ltf(n_from_latlon(ob.ll));
+    V3 r_1b_n = qrot_inv(q_en, r_eb_e - r_e1_e);
+    V3 r_1b_h(r_1b_n.x, r_1b_n.y, 0.0);
+    V3 r_12_n = qrot_inv(q_en, r_e2_e - r_e1_e);
+    V3 r_12_h(r_12_n.x, r_12_n.y, 0.0);
+    SegmentData d;
+    d.s_12 = norm(r_12_h);
+    V3 u_12 = r_12_h / d.s_12;
+    d.s_1b = dot(u_12, r_1b_h);
+    d.s_2b = d.s_1b - d.s_12;
+    d.e_sb = cross(u_12, r_1b_h).z;
+    d.h_s = p1.h + (p2.h - p1.h) * d.s_1b / d.s_12;
+    d.v_sb = ob.h - d.h_s;
+    d.chi_12 = azimuth(u_12);
+    d.gamma_12 = atan2(p2.h - p1.h, d.s_12);
+    return d;
+}
+// Segment(p1; s, chi, dh): c172x_gdc.jl:64-88 (gamma is turned into dh = s tan(gamma) by the caller)
+inline GeoLLH segment_end(GeoLLH p1, real s, real chi, real dh) {
+    Q4 q_en1 = ltf(n_from_latlon(p1.ll));
+    V3 r_12_e = qrot(q_en1, V3(s * cos(chi), s * sin(chi), 0.0));
+    V3 r_e2_e = cartesian_from_geo(n_from_latlon(p1.ll), p1.h) + r_12_e;
+    V3 n2; real h2;
+    geo_from_cartesian(r_e2_e, n2, h2);
+    GeoLLH p2; p2.ll = latlon_from_n(n2); p2.h = p1.h + dh;
+    return p2;
+}
+// the Segment constructor's validity check (:44-58): horizontal length, seen from p1, of at least 1e-6 m
+inline bool segment_valid(GeoLLH p1, GeoLLH p2) {
+    V3 r_12_e = cartesian_from_geo(n_from_latlon(p2.ll), p2.h) - cartesian_from_geo(n_from_latlon(p1.ll), p1.h);
+    V3 r_12_n = qrot_inv(ltf(n_from_latlon(p1.ll)), r_12_e);
+    return val(sqrt(r_12_n.x * r_12_n.x + r_12_n.y * r_12_n.y)) >= 1e-6;
+}
+
 enum LonMode { LON_DIRECT = 0, LON_SAS, LON_THR_Q, LON_THR_THETA, LON_THR_EAS, LON_EAS_Q, LON_EAS_THETA, LON_EAS_CLM, LON_EAS_ALT };
 enum LatMode { LAT_DIRECT = 0, LAT_SAS, LAT_P_BETA, LAT_PHI_BETA, LAT_CHI_BETA };
 
@@ -135,7 +177,10 @@ struct Avionics {
     struct { int mode = LAT_DIRECT; real aileron_cmd = 0.0, rudder_cmd = 0.0; } ylat;
     LQRc<8> ar2ar, pb2ar;
     Integ p2phi_int; PIDc p2phi_pid, chi2phi_pid;
-    int gdc_mode_req = 0;
+    // ---- GuidanceLaws (Cessna172Xv2 only): c172x_gdc.jl:201-223,264-289
+    struct { int mode_req = 0; bool hor_req = false, vrt_req = false;
+             GeoLLH p1{{0.0, 0.0}, 0.0}, p2{{1e-3, 0.0}, 0.0}; } ugdc;
+    struct { int mode = 0; SegmentData data; real dchi = 0.0, chi_ref = 0.0, h_ref = 0.0; bool hor = false, vrt = false; } ygdc;
 
     bool active() const { return variant >= VAR_C172X1; }
 
@@ -293,9 +338,30 @@ struct Avionics {
         ylat.rudder_cmd = rclamp(rudder_cmd, -1.0, 1.0);
     }
 
-    // f_periodic!(avionics, vehicle): c172x2.jl:28-37 (guidance in direct mode only forwards), then lon, lat (@sm_periodic)
+    // f_periodic!(GuidanceLaws, ctl, vehicle): c172x_gdc.jl:297-329 -> SegmentGuidance :228-252 (dchi_inf = pi/2,
+    // e_sf = 250 m, e_thr = 1000 m, :203-207). Writes the control laws' inputs when a guidance channel is active.
+    void gdc_periodic(const Member& m) {
+        const int mode = on_gnd(m) ? 0 : ugdc.mode_req;
+        if (mode == 1) {
+            GeoLLH ob; ob.ll = m.y.kin.ll; ob.h = m.y.kin.h_e;
+            SegmentData d = segment_data(ugdc.p1, ugdc.p2, ob);
+            const real dchi_inf = 0.5 * ORC_PI;
+            real dchi = -dchi_inf / (0.5 * ORC_PI) * atan(d.e_sb / 250.0);
+            ygdc.data = d; ygdc.dchi = dchi;
+            ygdc.chi_ref = wrap_to_pi(d.chi_12 + dchi);
+            ygdc.h_ref = d.h_s;
+            ygdc.hor = ugdc.hor_req;
+            ygdc.vrt = (rabs(d.e_sb) < 1000.0) ? ugdc.vrt_req : false;
+            if (ygdc.hor) { ulat.chi_ref = ygdc.chi_ref; ulat.mode_req = LAT_CHI_BETA; }
+            if (ygdc.vrt) { ulon.h_ref = ygdc.h_ref; ulon.mode_req = LON_EAS_ALT; }
+        }
+        ygdc.mode = mode;   // circular guidance is a stub in the reference (:257-262)
+    }
+
+    // f_periodic!(avionics, vehicle): c172x2.jl:28-37 (guidance, then the control laws), lon then lat (@sm_periodic)
     void f_periodic(Member& m, const World&, double Dt) {
         if (!active()) return;
+        if (variant == VAR_C172X2) gdc_periodic(m);
         lon_periodic(m, Dt);
         lat_periodic(m, Dt);
     }
@@ -350,7 +416,11 @@ struct Avionics {
             case FB_U_LAT_BETA_REF: ulat.beta_ref = v; return true;
             case FB_U_LAT_PHI_REF: ulat.phi_ref = v; return true;
             case FB_U_LAT_CHI_REF: ulat.chi_ref = v; return true;
-            case FB_U_GDC_MODE_REQ: gdc_mode_req = (int)v; return true;
+            case FB_U_GDC_MODE_REQ: ugdc.mode_req = (int)v; return true;
+            case FB_U_GDC_HOR_REQ: ugdc.hor_req = v != 0.0; return true;
+            case FB_U_GDC_VRT_REQ: ugdc.vrt_req = v != 0.0; return true;
+            case FB_U_GDC_LAT1: ugdc.p1.ll.lat = v; return true; case FB_U_GDC_LON1: ugdc.p1.ll.lon = v; return true; case FB_U_GDC_H1: ugdc.p1.h = v; return true;
+            case FB_U_GDC_LAT2: ugdc.p2.ll.lat = v; return true; case FB_U_GDC_LON2: ugdc.p2.ll.lon = v; return true; case FB_U_GDC_H2: ugdc.p2.h = v; return true;
             default: return false;
         }
     }
@@ -365,7 +435,10 @@ struct Avionics {
             case FB_U_LAT_AILERON_OFFSET: return val(ulat.aileron_offset); case FB_U_LAT_RUDDER_AXIS: return val(ulat.rudder_axis);
             case FB_U_LAT_RUDDER_OFFSET: return val(ulat.rudder_offset); case FB_U_LAT_P_REF: return val(ulat.p_ref);
             case FB_U_LAT_BETA_REF: return val(ulat.beta_ref); case FB_U_LAT_PHI_REF: return val(ulat.phi_ref);
-            case FB_U_LAT_CHI_REF: return val(ulat.chi_ref); case FB_U_GDC_MODE_REQ: return gdc_mode_req;
+            case FB_U_LAT_CHI_REF: return val(ulat.chi_ref); case FB_U_GDC_MODE_REQ: return ugdc.mode_req;
+            case FB_U_GDC_HOR_REQ: return ugdc.hor_req; case FB_U_GDC_VRT_REQ: return ugdc.vrt_req;
+            case FB_U_GDC_LAT1: return val(ugdc.p1.ll.lat); case FB_U_GDC_LON1: return val(ugdc.p1.ll.lon); case FB_U_GDC_H1: return val(ugdc.p1.h);
+            case FB_U_GDC_LAT2: return val(ugdc.p2.ll.lat); case FB_U_GDC_LON2: return val(ugdc.p2.ll.lon); case FB_U_GDC_H2: return val(ugdc.p2.h);
             default: return 0.0 / 0.0;
         }
     }
@@ -375,6 +448,10 @@ struct Avionics {
             case FB_Y_THROTTLE_CMD: return val(ylon.throttle_cmd); case FB_Y_ELEVATOR_CMD: return val(ylon.elevator_cmd);
             case FB_Y_AILERON_CMD: return val(ylat.aileron_cmd); case FB_Y_RUDDER_CMD: return val(ylat.rudder_cmd);
             case FB_Y_ALT_STATE: return h_state;
+            case FB_Y_GDC_MODE: return ygdc.mode; case FB_Y_GDC_HOR: return ygdc.hor; case FB_Y_GDC_VRT: return ygdc.vrt;
+            case FB_Y_GDC_DCHI: return val(ygdc.dchi); case FB_Y_GDC_CHI_REF: return val(ygdc.chi_ref); case FB_Y_GDC_H_REF: return val(ygdc.h_ref);
+            case FB_Y_GDC_CHI_12: return val(ygdc.data.chi_12); case FB_Y_GDC_GAMMA_12: return val(ygdc.data.gamma_12); case FB_Y_GDC_S_12: return val(ygdc.data.s_12);
+            case FB_Y_GDC_S_1B: return val(ygdc.data.s_1b); case FB_Y_GDC_E_SB: return val(ygdc.data.e_sb); case FB_Y_GDC_V_SB: return val(ygdc.data.v_sb);
             default: return 0.0 / 0.0;
         }
     }
