@@ -94,7 +94,7 @@ class fb_moments(C.Structure):
 EXPORTS = ["fb_api_version", "fb_last_error", "fb_create", "fb_load_tables", "fb_destroy", "fb_sync", "fb_init_trim", "fb_init",
            "fb_init_state", "fb_set_input", "fb_get_input", "fb_schedule_inputs", "fb_step", "fb_run", "fb_time", "fb_nx",
            "fb_get_state", "fb_get_discrete", "fb_get_output", "fb_status", "fb_log_info", "fb_log_times", "fb_log_fetch",
-           "fb_stats", "fb_rhs", "fb_counters", "fb_linearize", "fb_linearize_dims", "fb_device_state", "fb_stream", "fb_measure_fp64_peak"]
+           "fb_stats", "fb_rhs", "fb_fstep", "fb_fperiodic", "fb_counters", "fb_linearize", "fb_linearize_dims", "fb_device_state", "fb_stream", "fb_measure_fp64_peak"]
 
 _lib = None
 
@@ -122,7 +122,7 @@ def load_library():
         "fb_get_output": (i32, [vp, i32, _DP]), "fb_status": (i32, [vp, C.POINTER(i32)]),
         "fb_log_info": (i32, [vp, C.POINTER(i64), C.POINTER(i32)]), "fb_log_times": (i32, [vp, _DP]),
         "fb_log_fetch": (i32, [vp, i32, _DP]), "fb_stats": (i32, [vp, i32, C.POINTER(fb_moments)]),
-        "fb_rhs": (i32, [vp, _DP]), "fb_counters": (i32, [vp, C.POINTER(i64), C.POINTER(i64)]),
+        "fb_rhs": (i32, [vp, _DP]), "fb_fstep": (i32, [vp, C.POINTER(i32)]), "fb_fperiodic": (i32, [vp]), "fb_counters": (i32, [vp, C.POINTER(i64), C.POINTER(i64)]),
         "fb_device_state": (i32, [vp, C.POINTER(vp), C.POINTER(i64)]), "fb_stream": (i32, [vp, C.POINTER(vp)]),
         "fb_measure_fp64_peak": (i32, [i32, _DP]),
         "fb_linearize_dims": (i32, [vp, C.POINTER(i32)]), "fb_linearize": (i32, [vp] + [_DP] * 8),
@@ -542,6 +542,16 @@ class BatchSimulation:
         out = {k: np.transpose(raw[k], (2, 1, 0)) for k in ("A", "B", "C", "D")}      # [col][row][N] -> [N][row][col]
         out.update({k: raw[k].T for k in ("x0", "u0", "y0", "xdot0")})
         return out
+
+    def f_step(self):
+        """f_step!(world) at the current state (test hook); returns the per-member `changed` flags."""
+        out = np.zeros(self.n, dtype=np.int32)
+        _ck(self._lib.fb_fstep(self._h, out.ctypes.data_as(C.POINTER(C.c_int32))), self._lib)
+        return out
+
+    def f_periodic(self):
+        """f_periodic!(avionics, vehicle) + assign! at the current state (test hook)."""
+        _ck(self._lib.fb_fperiodic(self._h), self._lib)
 
     def counters(self):
         a, b = C.c_int64(), C.c_int64()

@@ -368,6 +368,63 @@ output_kernel(EnsembleDev E, int field, double* out) {
     out[i] = pick_output(yf, E.stall[i], E.eng[i], cs, field);
 }
 
+// f_step!(world) at the current state (test hook): y of an f_ode! at x, then the discrete updates of world.jl:34-39
+// (quaternion renormalisation, stall hysteresis, crash checks, contact reset, engine state machine)
+template <int VAR, int KIN>
+__global__ void __launch_bounds__(FB_BLOCK, 2)
+fstep_kernel(EnsembleDev E, int* changed_out) {
+    typedef Lay<VAR, KIN> L;
+    constexpr int NX = L::NX;
+    extern __shared__ __align__(16) double smem_tb[];
+    stage_tables(smem_tb, E.tables.pack);
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= E.n) return;
+    int status = E.status[i];
+    if (status != FB_ST_RUNNING) { if (changed_out) changed_out[i] = 0; return; }
+    MemberIn u; u.u = E.u + i; u.pitch = E.pitch;
+    double x[NX], k[NX];
+#pragma unroll
+    for (int c = 0; c < NX; c++) x[c] = E.x[(long long)c * E.pitch + i];
+    if (VAR >= FB_C172X1) { CtlState cs; cs.load(E.ctl + i, E.pitch); avionics_assign(cs, u); }
+    int stall = E.stall[i], eng = E.eng[i];
+    RhsOut y;
+    ArraySink sink; sink.xd = k;
+    rhs<VAR, KIN, false>(x, sink, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr);
+    bool changed = false;
+    if (y.err) status = y.err;
+    else { ArrayState xs; xs.x = x; changed = f_step<VAR, KIN>(xs, stall, eng, u, y, status); }
+#pragma unroll
+    for (int c = 0; c < NX; c++) E.x[(long long)c * E.pitch + i] = x[c];
+    E.stall[i] = (unsigned char)stall; E.eng[i] = (unsigned char)eng; E.status[i] = status;
+    if (changed_out) changed_out[i] = changed ? 1 : 0;
+}
+
+// f_periodic!(avionics, vehicle) followed by assign! at the current state (test hook): guidance, ControlLawsLon,
+// ControlLawsLat from the outputs of an f_ode! at x (c172x2.jl:28-37, c172x_ctl.jl:286-446,880-983)
+template <int VAR, int KIN>
+__global__ void __launch_bounds__(FB_BLOCK, 2)
+fperiodic_kernel(EnsembleDev E, double Dt) {
+    typedef Lay<VAR, KIN> L;
+    constexpr int NX = L::NX;
+    extern __shared__ __align__(16) double smem_tb[];
+    stage_tables(smem_tb, E.tables.pack);
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= E.n) return;
+    if (VAR < FB_C172X1) return;
+    if (E.status[i] != FB_ST_RUNNING) return;
+    MemberIn u; u.u = E.u + i; u.pitch = E.pitch;
+    double x[NX], k[NX];
+#pragma unroll
+    for (int c = 0; c < NX; c++) x[c] = E.x[(long long)c * E.pitch + i];
+    CtlState cs;
+    cs.load(E.ctl + i, E.pitch);
+    avionics_assign(cs, u);
+    YFull yf; RhsOut y;
+    rhs_with_outputs<VAR, KIN>(x, k, E.stall[i], E.eng[i], u, smem_tb, E.tables.geoid, &y, &yf);
+    avionics_periodic<VAR, KIN>(yf, y, u, cs, E.tables, Dt);
+    cs.store(E.ctl + i, E.pitch);
+}
+
 // f_init!(avionics, vehicle) for every member, from the vehicle outputs at the initial state
 // (c172x_ctl.jl:1246-1250); leaves the controller memory in E.ctl and the commands assigned.
 template <int VAR, int KIN>

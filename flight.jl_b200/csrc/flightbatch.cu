@@ -101,6 +101,10 @@ template <int VAR, int KIN> struct Ops {
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(avionics_init_kernel<VAR, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(fstep_kernel<VAR, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(fperiodic_kernel<VAR, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES);
+        if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(linearize_kernel<VAR, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES);
         if (e != cudaSuccess) return e;
         return cudaFuncSetAttribute(trim_kernel<VAR, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES);
@@ -113,6 +117,16 @@ template <int VAR, int KIN> struct Ops {
     static cudaError_t output(fb_sim* s, int field, double* out) {
         int grid = (int)((s->E.n + FB_BLOCK - 1) / FB_BLOCK);
         output_kernel<VAR, KIN><<<grid, FB_BLOCK, FB_TB_BYTES, s->stream>>>(s->E, field, out);
+        return cudaGetLastError();
+    }
+    static cudaError_t fstep(fb_sim* s, int* changed) {
+        int grid = (int)((s->E.n + FB_BLOCK - 1) / FB_BLOCK);
+        fstep_kernel<VAR, KIN><<<grid, FB_BLOCK, FB_TB_BYTES, s->stream>>>(s->E, changed);
+        return cudaGetLastError();
+    }
+    static cudaError_t fperiodic(fb_sim* s) {
+        int grid = (int)((s->E.n + FB_BLOCK - 1) / FB_BLOCK);
+        fperiodic_kernel<VAR, KIN><<<grid, FB_BLOCK, FB_TB_BYTES, s->stream>>>(s->E, s->cfg.Dt);
         return cudaGetLastError();
     }
     static cudaError_t init(fb_sim* s, const InitSoA& I) {
@@ -736,6 +750,26 @@ int32_t fb_rhs(fb_handle s, double* xdot) {
     CK(cudaSetDevice(s->cfg.device));
     CK(FB_DISPATCH(s, rhs)(s, s->d_scratch));
     CK(cudaMemcpy2DAsync(xdot, sizeof(double) * s->E.n, s->d_scratch, sizeof(double) * s->pitch, sizeof(double) * s->E.n, s->nx, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return FB_OK;
+}
+
+int32_t fb_fstep(fb_handle s, int32_t* changed) {
+    if (!s) return fail(FB_ERR_ARG, "null handle");
+    if (!s->initialised) return fail(FB_ERR_STATE, "fb_fstep: not initialised");
+    CK(cudaSetDevice(s->cfg.device));
+    int* d_changed = (int*)s->d_scratch;   // [pitch] ints fit in the scratch rows
+    CK(FB_DISPATCH(s, fstep)(s, changed ? d_changed : nullptr));
+    if (changed) CK(cudaMemcpyAsync(changed, d_changed, sizeof(int) * s->E.n, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return FB_OK;
+}
+
+int32_t fb_fperiodic(fb_handle s) {
+    if (!s) return fail(FB_ERR_ARG, "null handle");
+    if (!s->initialised) return fail(FB_ERR_STATE, "fb_fperiodic: not initialised");
+    CK(cudaSetDevice(s->cfg.device));
+    CK(FB_DISPATCH(s, fperiodic)(s));
     CK(cudaStreamSynchronize(s->stream));
     return FB_OK;
 }

@@ -235,6 +235,12 @@ int32_t fb_linearize(fb_handle h, double* A, double* B, double* C, double* D, do
 /* ---- test hooks: the Modeling protocol pieces, for parity checks in isolation ---------- */
 /* f_ode!(world) at the current state: writes ẋ [nx][N] (modeling.jl:201-254, world.jl:26-32) */
 int32_t fb_rhs(fb_handle h, double* xdot);
+/* f_step!(world) at the current state (world.jl:34-39): the y of an f_ode! there, then quaternion renormalisation, stall
+ * hysteresis, crash checks, contact reset and the engine state machine. changed [N] (may be NULL): 1 where x or s changed. */
+int32_t fb_fstep(fb_handle h, int32_t* changed);
+/* f_periodic!(avionics, vehicle) + assign! at the current state (c172x2.jl:28-37): guidance, ControlLawsLon, ControlLawsLat
+ * from the outputs of an f_ode! there; no-op for variants without avionics. */
+int32_t fb_fperiodic(fb_handle h);
 /* counters */
 int32_t fb_counters(fb_handle h, int64_t* kernel_launches, int64_t* rhs_evals_per_member);
 /* utility: measured FP64 FMA throughput of `device` in TFLOP/s (the roofline denominator of this path) */

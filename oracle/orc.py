@@ -48,6 +48,7 @@ def _load(name):
         "orc_sim_rhs": (i32, [vp]),
         "orc_sim_step": (i32, [vp, i64]),
         "orc_sim_steps_taken": (i64, [vp]),
+        "orc_sim_fstep": (i32, [vp]), "orc_sim_fperiodic": (i32, [vp]),
         "orc_sim_linearize_dims": (None, [vp, C.POINTER(i32)]),
         "orc_sim_linearize": (i32, [vp, dp, dp, dp, dp, dp, dp, dp, dp]),
         "orc_ops_reset": (None, []),
@@ -207,6 +208,12 @@ class Sim:
 
     def step(self, n=1):
         return self.lib.orc_sim_step(self.h, int(n))
+
+    def f_step(self):
+        return self.lib.orc_sim_fstep(self.h)
+
+    def f_periodic(self):
+        return self.lib.orc_sim_fperiodic(self.h)
 
     def linearize(self):
         """linearize(aircraft, trim) about the current state (NED kinematics): dict of A, B, C, D (row-major), x0, u0, y0, xdot0."""

@@ -264,6 +264,20 @@ int orc_sim_step(void* s, long long n) {
     for (long long i = 0; i < n; i++) S->step();
     return S->m.status;
 }
+// Modeling-protocol pieces in isolation (parity hooks): f_ode! at the current state for y, then f_step!(world) /
+// f_periodic!(avionics) + assign!, exactly the callback bodies of Sim::step()
+int orc_sim_fstep(void* s) {
+    Sim* S = (Sim*)s;
+    if (S->m.status != ST_RUNNING) return S->m.status;
+    try { S->world_ode(); S->av.f_step(S->m); S->av.assign(S->m); S->m.f_step(*S->W); } catch (OrcTermination& e) { S->m.status = e.code; }
+    return S->m.status;
+}
+int orc_sim_fperiodic(void* s) {
+    Sim* S = (Sim*)s;
+    if (S->m.status != ST_RUNNING) return S->m.status;
+    try { S->world_ode(); S->av.f_periodic(S->m, *S->W, S->Dt); S->av.assign(S->m); } catch (OrcTermination& e) { S->m.status = e.code; }
+    return S->m.status;
+}
 long long orc_sim_steps_taken(void* s) { return ((Sim*)s)->n_steps; }
 // linearize(aircraft, trim) about the current state: dims[3] = nx, nu, ny; matrices row-major
 void orc_sim_linearize_dims(void* s, int* dims) { SSDims d = ss_dims(((Sim*)s)->m.L.variant); dims[0] = d.nx; dims[1] = d.nu; dims[2] = d.ny; }

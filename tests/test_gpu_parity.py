@@ -165,3 +165,69 @@ def test_outputs_match_oracle(fb, orc):
             a, b = out[k][i], o.y(fb.OUTPUT_NAMES[k])
             assert abs(a - b) <= 1e-9 * max(abs(b), 1e-2), (k, a, b)
     sim.close()
+
+
+def test_fstep_and_fperiodic_hooks_match_oracle(fb, orc):
+    """The Modeling-protocol pieces in isolation: f_step!(world) on states that trip its branches
+    (denormalised quaternions, stall hysteresis, engine start/stop) and f_periodic!(avionics) + assign! on a trimmed
+    Cessna172Xv1, each against the oracle's callback bodies."""
+    n = 64
+    rng = np.random.default_rng(SEED + 90)
+    sim = fb.BatchSimulation(fb.SimpleWorld(fb.Cessna172Sv0(fb.WA())), n=n, dt=0.01, t_end=10.0)
+    EAS = rng.uniform(35, 55, n)
+    ok, _, _ = sim.init(fb.C172.TrimParameters(EAS=EAS, h_e=rng.uniform(500, 2500, n)))
+    assert ok.all()
+    x = sim.x.copy()
+    L = sim.nx
+    kinx, dyn = 12, L - 6
+    x[kinx:kinx + 4] *= 1.0 + rng.choice([0.0, 3e-8, 1e-9], n)          # q_wb: some beyond the 1e-8 renormalisation threshold
+    x[kinx + 4:kinx + 8] *= 1.0 - rng.choice([0.0, 5e-8], n)            # q_ew
+    pitch_up = rng.uniform(0, 1, n) < 0.3                               # alpha > 0.36 -> stall sets
+    x[dyn + 5] = np.where(pitch_up, x[dyn + 3] * 0.5, x[dyn + 5])
+    x[9] = np.where(rng.uniform(0, 1, n) < 0.2, 20.0, x[9])             # engine below the stall speed -> off
+    stall0 = (rng.uniform(0, 1, n) < 0.3).astype(np.uint8)
+    eng0 = rng.choice([0, 1, 2], n).astype(np.uint8)
+    start = (rng.uniform(0, 1, n) < 0.5).astype(float)
+    sim.set_input("eng_start", start)
+    sim.init_state(x, stall=stall0, eng_state=eng0)
+    changed = sim.f_step()
+    xg = sim.x; stg, eng = sim.discrete(); st = sim.status()
+    inputs = {f: sim.get_input(f) for f in ("throttle", "elevator", "aileron", "rudder", "flaps", "mixture", "m_pilot", "m_copilot", "m_lpass", "m_rpass", "m_baggage")}
+    n_changed = 0
+    for i in range(0, n, 2):
+        o = orc.Sim(variant=0, kin=0, dt=0.01)
+        for f, v in inputs.items():
+            o.set_input(fb.INPUT_NAMES[f], v[i])
+        o.set_input(fb.U["FB_U_ENG_START"], start[i])
+        o.init_state(x[:, i], stall=int(stall0[i]), eng_state=int(eng0[i]))
+        assert o.f_step() == st[i]
+        assert o.discrete == (int(stg[i]), int(eng[i])), i
+        assert np.max(np.abs(xg[:, i] - o.x) / np.maximum(np.abs(o.x), 1e-3)) < 1e-12, i
+        n_changed += int(changed[i])
+    assert 0 < n_changed < n // 2 + 1 and set(eng.tolist()) == {0, 1, 2}
+    sim.close()
+    # ---- f_periodic!(avionics) + assign! in isolation, right after the trim (controller memory = f_init!)
+    sim = fb.BatchSimulation(fb.SimpleWorld(fb.Cessna172Xv1(fb.WA())), n=n, dt=0.01, Dt=0.01, t_end=10.0)
+    h_e = rng.uniform(500, 2500, n)
+    ok, _, _ = sim.init(fb.C172.TrimParameters(EAS=EAS, h_e=h_e))
+    assert ok.all()
+    lon_req = rng.choice([1, 4, 6, 7, 8], n).astype(float); lat_req = rng.choice([1, 2, 3, 4], n).astype(float)
+    clm = rng.uniform(-2, 2, n); phi = rng.uniform(-0.4, 0.4, n)
+    sim.set_input("lon_mode_req", lon_req); sim.set_input("lat_mode_req", lat_req)
+    sim.set_input("lon_clm_ref", clm); sim.set_input("lat_phi_ref", phi)
+    sim.f_periodic()
+    names = ("act_throttle", "act_aileron", "act_elevator", "act_rudder")
+    cmds = {k: sim.get_input(k) for k in names}
+    lon_mode, lat_mode = sim.get_output("lon_mode"), sim.get_output("lat_mode")
+    for i in range(0, n, 2):
+        o = orc.Sim(variant=2, kin=0, dt=0.01, Dt=0.01)
+        ok_o, _, _ = o.init_trim(EAS=float(EAS[i]), h_e=float(h_e[i]))
+        assert ok_o
+        for f, v in (("lon_mode_req", lon_req[i]), ("lat_mode_req", lat_req[i]), ("lon_clm_ref", clm[i]), ("lat_phi_ref", phi[i])):
+            o.set_input(fb.INPUT_NAMES[f], float(v))
+        assert o.f_periodic() == 0
+        assert lon_mode[i] == o.y(fb.Y["FB_Y_LON_MODE"]) and lat_mode[i] == o.y(fb.Y["FB_Y_LAT_MODE"]), i
+        for k in names:
+            a, b = cmds[k][i], o.get_input(fb.INPUT_NAMES[k])
+            assert abs(a - b) <= 1e-9 * max(abs(b), 1e-2), (k, i, a, b)
+    sim.close()
