@@ -46,6 +46,14 @@ FB_DEV void kin_init(double* x, const KinIC& ic) {
         x[L::KINX] = ic.q_nb.w; x[L::KINX + 1] = ic.q_nb.x; x[L::KINX + 2] = ic.q_nb.y; x[L::KINX + 3] = ic.q_nb.z;
         x[L::KINX + 4] = q_ew.w; x[L::KINX + 5] = q_ew.x; x[L::KINX + 6] = q_ew.y; x[L::KINX + 7] = q_ew.z;
         x[L::KINX + 8] = ic.h_e;
+    } else if (KIN == FB_ECEF) {   // kinematics.jl:256-279: q_eb = ltf(n_e) o q_nb, n_e, h_e
+        double sl2, cl2, sa2, ca2;
+        sincos(0.5 * ic.lon, &sl2, &cl2); sincos(-0.5 * (ic.lat + 0.5 * FB_PI), &sa2, &ca2);
+        q4 q_en = qmul(mkq(cl2, 0, 0, sl2), mkq(ca2, 0, sa2, 0));
+        q4 q_eb = qmul(q_en, ic.q_nb);
+        x[L::KINX] = q_eb.w; x[L::KINX + 1] = q_eb.x; x[L::KINX + 2] = q_eb.y; x[L::KINX + 3] = q_eb.z;
+        x[L::KINX + 4] = cla * clo; x[L::KINX + 5] = cla * slo; x[L::KINX + 6] = sla;
+        x[L::KINX + 7] = ic.h_e;
     } else if (KIN == FB_NED) {
         q4 q = ic.q_nb;
         x[L::KINX] = atan2(2.0 * (q.w * q.z + q.x * q.y), 1.0 - 2.0 * (q.y * q.y + q.z * q.z));

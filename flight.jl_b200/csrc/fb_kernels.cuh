@@ -256,7 +256,7 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
             yf.lat = tapv(TAP_LAT); yf.lon = tapv(TAP_LON);
             yf.alpha_filt = sink.sx[L::AERO * T_]; yf.beta_filt = sink.sx[(L::AERO + 1) * T_];
             yf.eng_n = sink.sx[L::ENG * T_] * (1.0 / (2700 * FB_PI / 30));
-            yf.h_e = sink.sx[(L::KINX + (KIN == FB_WA ? 8 : 5)) * T_];
+            yf.h_e = sink.sx[(L::KINX + (KIN == FB_WA ? 8 : (KIN == FB_ECEF ? 7 : 5))) * T_];
 #pragma unroll
             for (int a = 0; a < L::NACT; a++) {
                 yf.act_pos[a] = clampd(sink.sx[(L::ACT + a) * T_], (a == 0 || a >= 4) ? 0.0 : -1.0, 1.0);

@@ -456,6 +456,35 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
         sink.put(L::KINX, d1.w); sink.put(L::KINX + 1, d1.x); sink.put(L::KINX + 2, d1.y); sink.put(L::KINX + 3, d1.z);
         sink.put(L::KINX + 4, d2.w); sink.put(L::KINX + 5, d2.x); sink.put(L::KINX + 6, d2.y); sink.put(L::KINX + 7, d2.z);
         sink.put(L::KINX + 8, -k.v_eb_n.z);
+    } else if (KIN == FB_ECEF) {   // kinematics.jl:281-315: x = (q_eb, n_e, h_e), neither block normalised on the fly
+        k.q_eb = mkq(x[L::KINX], x[L::KINX + 1], x[L::KINX + 2], x[L::KINX + 3]);
+        k.n_e = mk3(x[L::KINX + 4], x[L::KINX + 5], x[L::KINX + 6]);
+        k.h_e = x[L::KINX + 7];
+        // q_en = ltf(n_e) = Rz(lon) o Ry(-(lat + pi/2)) with (lat, lon) = LatLon(n_e): built from direction cosines by
+        // half-angle identities. cos/sin of -(lat + pi/2) are (-sin lat, -cos lat).
+        double p2 = fma(k.n_e.x, k.n_e.x, k.n_e.y * k.n_e.y);
+        double ip = fb_rsqrt(fb_max(p2, 1e-280));
+        double p = p2 * ip;
+        double inn = fb_rsqrt(fma(k.n_e.z, k.n_e.z, p2));
+        double clo = (p2 > 0.0) ? k.n_e.x * ip : 1.0, slo = k.n_e.y * ip;
+        double chl, shl, cha, sha;
+        half_angle_cs(clo, slo, chl, shl);
+        half_angle_cs(-k.n_e.z * inn, -p * inn, cha, sha);
+        q4 q_en = qmul(mkq(chl, 0.0, 0.0, shl), mkq(cha, 0.0, sha, 0.0));
+        k.q_nb = qmul(qconj(q_en), k.q_eb);
+        k.lat = fb_atan2(k.n_e.z, p);
+        k.lon = fb_atan2(k.n_e.y, k.n_e.x);
+        k.v_eb_n = qrot(k.q_nb, k.v_eb_b);
+        double M, N;
+        radii(k.n_e.z, M, N);
+        k.r_eb_e = mk3((N + k.h_e) * k.n_e.x, (N + k.h_e) * k.n_e.y, fma(N, 1 - wgs::e2, k.h_e) * k.n_e.z);
+        double wx = k.v_eb_n.y * fb_rcp(N + k.h_e), wy = -k.v_eb_n.x * fb_rcp(M + k.h_e);
+        k.w_wb_b = k.w_eb_b - qrot_inv(k.q_nb, mk3(wx, wy, 0.0));
+        q4 d1 = qdt(k.q_eb, k.w_eb_b);
+        d3 nd = qrot(q_en, mk3(-wy, wx, 0.0));                 // w_ew_n x (0, 0, -1)
+        sink.put(L::KINX, d1.w); sink.put(L::KINX + 1, d1.x); sink.put(L::KINX + 2, d1.y); sink.put(L::KINX + 3, d1.z);
+        sink.put(L::KINX + 4, nd.x); sink.put(L::KINX + 5, nd.y); sink.put(L::KINX + 6, nd.z);
+        sink.put(L::KINX + 7, -k.v_eb_n.z);
     } else if (KIN == FB_NED) {
         double psi = x[L::KINX], th = x[L::KINX + 1], phi = x[L::KINX + 2];
         k.lat = x[L::KINX + 3]; k.lon = x[L::KINX + 4]; k.h_e = x[L::KINX + 5];
@@ -892,6 +921,19 @@ FB_DEV bool f_step(X& x, int& stall, int& eng_state, const U& u, const RhsOut& y
             double q0 = x.get(o), q1 = x.get(o + 1), q2 = x.get(o + 2), q3 = x.get(o + 3);
             double nn = sqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
             if (fabs(nn - 1.0) > 1e-8) { x.set(o, q0 / nn); x.set(o + 1, q1 / nn); x.set(o + 2, q2 / nn); x.set(o + 3, q3 / nn); changed = true; }
+        }
+    } else if (KIN == FB_ECEF) {   // kinematics.jl:317-320: q_eb and n_e blocks
+        {
+            const int o = L::KINX;
+            double q0 = x.get(o), q1 = x.get(o + 1), q2 = x.get(o + 2), q3 = x.get(o + 3);
+            double nn = sqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+            if (fabs(nn - 1.0) > 1e-8) { x.set(o, q0 / nn); x.set(o + 1, q1 / nn); x.set(o + 2, q2 / nn); x.set(o + 3, q3 / nn); changed = true; }
+        }
+        {
+            const int o = L::KINX + 4;
+            double n0 = x.get(o), n1 = x.get(o + 1), n2 = x.get(o + 2);
+            double nn = sqrt(n0 * n0 + n1 * n1 + n2 * n2);
+            if (fabs(nn - 1.0) > 1e-8) { x.set(o, n0 / nn); x.set(o + 1, n1 / nn); x.set(o + 2, n2 / nn); changed = true; }
         }
     }
     int st0 = stall;

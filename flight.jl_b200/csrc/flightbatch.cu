@@ -155,10 +155,10 @@ template <int VAR, int KIN> struct Ops {
 #elif defined(FB_ONLY_X1_WA)
 #define FB_DISPATCH(s, CALL) (Ops<FB_C172X1, FB_WA>::CALL)
 #else
-#define FB_DISPATCH(s, CALL)                                                            \
-    ((s)->var_t == FB_C172S ? ((s)->cfg.kinematics == FB_WA ? Ops<FB_C172S, FB_WA>::CALL : Ops<FB_C172S, FB_NED>::CALL) \
-     : (s)->var_t == FB_C172X0 ? ((s)->cfg.kinematics == FB_WA ? Ops<FB_C172X0, FB_WA>::CALL : Ops<FB_C172X0, FB_NED>::CALL) \
-                               : ((s)->cfg.kinematics == FB_WA ? Ops<FB_C172X1, FB_WA>::CALL : Ops<FB_C172X1, FB_NED>::CALL))
+#define FB_KIN_DISPATCH(s, V, CALL) \
+    ((s)->cfg.kinematics == FB_WA ? Ops<V, FB_WA>::CALL : ((s)->cfg.kinematics == FB_NED ? Ops<V, FB_NED>::CALL : Ops<V, FB_ECEF>::CALL))
+#define FB_DISPATCH(s, CALL) \
+    ((s)->var_t == FB_C172S ? FB_KIN_DISPATCH(s, FB_C172S, CALL) : ((s)->var_t == FB_C172X0 ? FB_KIN_DISPATCH(s, FB_C172X0, CALL) : FB_KIN_DISPATCH(s, FB_C172X1, CALL)))
 #endif
 
 static int layout_nx(int variant, int kin) {
@@ -243,7 +243,7 @@ const char* fb_last_error(void) { return g_err.c_str(); }
 int32_t fb_create(const fb_config* cfg, fb_handle* out) {
     if (!cfg || !out) return fail(FB_ERR_ARG, "fb_create: null argument");
     if (cfg->variant < FB_C172S || cfg->variant > FB_C172X2) return fail(FB_ERR_ARG, "fb_create: unknown variant");
-    if (cfg->kinematics != FB_WA && cfg->kinematics != FB_NED) return fail(FB_ERR_ARG, "fb_create: kinematics must be FB_WA or FB_NED (ECEF not built yet)");
+    if (cfg->kinematics != FB_WA && cfg->kinematics != FB_NED && cfg->kinematics != FB_ECEF) return fail(FB_ERR_ARG, "fb_create: kinematics must be FB_WA, FB_ECEF or FB_NED");
     if (cfg->n_members <= 0) return fail(FB_ERR_ARG, "fb_create: n_members must be positive");
     if (!(cfg->dt > 0.0)) return fail(FB_ERR_ARG, "fb_create: dt must be positive");
     double Dt = cfg->Dt > 0.0 ? cfg->Dt : cfg->dt;

@@ -18,6 +18,9 @@ def state_floors(nx, variant, kin):
     if kin == 0:
         f[k0:k0 + 8] = 1e-2   # unit quaternions
         f[k0 + 8] = 1.0       # h_e [m]
+    elif kin == 1:
+        f[k0:k0 + 7] = 1e-2   # unit quaternion q_eb, n-vector
+        f[k0 + 7] = 1.0       # h_e [m]
     elif kin == 2:
         f[k0:k0 + 5] = 1e-2   # Euler angles, lat, lon [rad]
         f[k0 + 5] = 1.0

@@ -28,7 +28,7 @@ def cfg3_params(n, rng):
 
 
 def make_pair(fb, orc, variant, kin, n, p, idx, dt, Dt, wind=None, **simkw):
-    ac = {2: fb.Cessna172Xv1, 3: fb.Cessna172Xv2}[variant]([fb.WA, None, fb.NED][kin]())
+    ac = {2: fb.Cessna172Xv1, 3: fb.Cessna172Xv2}[variant]([fb.WA, fb.ECEF, fb.NED][kin]())
     sim = fb.BatchSimulation(fb.SimpleWorld(ac), n=n, dt=dt, Dt=Dt, t_end=1000.0, **simkw)
     oracles = []
     for i in idx:

@@ -56,12 +56,12 @@ def oracle_members(orc, variant, kin, dt, params, idx, Dt=None):
     return sims
 
 
-@pytest.mark.parametrize("variant,kin", [(0, 0), (0, 2), (1, 0), (1, 2)])
+@pytest.mark.parametrize("variant,kin", [(0, 0), (0, 2), (1, 0), (1, 2), (0, 1), (1, 1)])
 def test_trim_and_rhs_parity(fb, orc, variant, kin):
     n = 64
     rng = np.random.default_rng(SEED)
     p = cfg2_params(n, rng)
-    ac = [fb.Cessna172Sv0, fb.Cessna172Xv0][variant]([fb.WA, None, fb.NED][kin]())
+    ac = [fb.Cessna172Sv0, fb.Cessna172Xv0][variant]([fb.WA, fb.ECEF, fb.NED][kin]())
     sim = fb.BatchSimulation(fb.SimpleWorld(ac), n=n, dt=0.01, t_end=10.0)
     ok, ts, cost = sim.init(fb.C172.TrimParameters(**p))
     assert ok.all()
@@ -81,13 +81,13 @@ def test_trim_and_rhs_parity(fb, orc, variant, kin):
     sim.close()
 
 
-@pytest.mark.parametrize("variant,kin,steps", [(0, 0, 1000), (0, 2, 1000), (1, 0, 400)])
+@pytest.mark.parametrize("variant,kin,steps", [(0, 0, 1000), (0, 2, 1000), (1, 0, 400), (0, 1, 1000)])
 def test_step_parity_with_doublets(fb, orc, variant, kin, steps):
     n = 96
     dt = 0.01
     rng = np.random.default_rng(SEED + 1)
     p = cfg2_params(n, rng)
-    ac = [fb.Cessna172Sv0, fb.Cessna172Xv0][variant]([fb.WA, None, fb.NED][kin]())
+    ac = [fb.Cessna172Sv0, fb.Cessna172Xv0][variant]([fb.WA, fb.ECEF, fb.NED][kin]())
     sim = fb.BatchSimulation(fb.SimpleWorld(ac), n=n, dt=dt, t_end=100.0, steps_per_launch=64)
     ok, ts, cost = sim.init(fb.C172.TrimParameters(**p))
     assert ok.all()
