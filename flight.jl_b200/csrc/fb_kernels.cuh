@@ -218,7 +218,7 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
         } else rhs<VAR, KIN, false, AIR>(xs, sink, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr);
         if (!AIR) gnd_seen |= y.gnd;
         if (y.err) {
-            if (AIR && y.err == FB_NEED_GROUND) {
+            if (AIR && y.err == FB_NEED_COMPLETE) {
                 // sx is the step-start state (stages 1..3 and re-evaluations) or x* with this step's callbacks pending
                 handover = done | ((sink.stage == 4) ? FB_RESUME_PENDING : 0);
             } else status = y.err;

@@ -67,10 +67,10 @@ struct RhsOut {
     double alpha;       // unclamped aerodynamic AoA (aero.y.α, c172.jl:324,367)
     int wow;            // bit i = strut i weight-on-wheels
     int crash;          // 2 bits per strut: 0 none, 1 strut/terrain angle > 60 deg, 2 compression rate > 10 m/s (landinggear.jl:331-347)
-    int err;            // 0 none, FB_ST_BOUNDS / FB_ST_CONTACT_ASSERT (would have thrown inside f_ode!), FB_NEED_GROUND
+    int err;            // 0 none, FB_ST_BOUNDS / FB_ST_CONTACT_ASSERT (would have thrown inside f_ode!), FB_NEED_COMPLETE
     int gnd;            // a strut was evaluated (the aircraft is within the height gate of the terrain)
 };
-#define FB_NEED_GROUND 64   // internal: an AIR-layout evaluation came within the height gate; the member goes to the full kernel
+#define FB_NEED_COMPLETE 64   // internal: an AIR-layout evaluation came within the height gate (or left the troposphere); the member goes to the complete kernel
 
 // everything the output pass / log / control laws may ask for (filled only by the WY=true instantiation)
 struct YFull {
@@ -86,10 +86,12 @@ struct YFull {
     double act_pos[7], act_cmd[7];
 };
 
+__device__ __noinline__ double pow_slow(double a, double b) { return pow(a, b); }
 // pseudo input fields: combinations the RHS uses as one value (so that an input cache can hold them ready-made)
 enum { FB_UX_AE = 100,   // -clamp(elevator_offset + elevator)   C172S MechanicalActuation, c172s.jl:92-120
        FB_UX_AA,         //  clamp(aileron_offset + aileron)
-       FB_UX_RU };       //  clamp(rudder_offset + rudder)
+       FB_UX_RU,         //  clamp(rudder_offset + rudder)
+       FB_UX_TRF };      //  (p_sl / p_std)^(-beta R / g): sea-level factor of T_ISA(p)/T_std (piston.jl:38), 1 for the standard day
 struct MemberIn {       // per-member input view: field f of this member is u[f * pitch]
     double* u;          // plain (coherent) loads: the owning thread also writes inputs (events, control laws)
     long long pitch;
@@ -98,6 +100,7 @@ struct MemberIn {       // per-member input view: field f of this member is u[f 
         if (f == FB_UX_AE) return -clampd(raw(FB_U_ELEVATOR_OFFSET) + raw(FB_U_ELEVATOR), -1.0, 1.0);
         if (f == FB_UX_AA) return clampd(raw(FB_U_AILERON_OFFSET) + raw(FB_U_AILERON), -1.0, 1.0);
         if (f == FB_UX_RU) return clampd(raw(FB_U_RUDDER_OFFSET) + raw(FB_U_RUDDER), -1.0, 1.0);
+        if (f == FB_UX_TRF) { double p_sl = raw(FB_U_P_SL); return (p_sl == 101325.0) ? 1.0 : pow_slow(p_sl * (1.0 / 101325.0), 6.5e-3 * 287.05287 / 9.80665); }
         return raw(f);
     }
     FB_DEV void set(int f, double v) const { u[(long long)f * pitch] = v; }
@@ -116,15 +119,15 @@ struct CachedIn {
             switch (s) {
                 case 0: return FB_U_T_SL; case 1: return FB_U_P_SL; case 2: return FB_U_TRN_ELEVATION; case 3: return FB_UX_AE;
                 case 4: return FB_UX_AA; case 5: return FB_UX_RU; case 6: return FB_U_FLAPS; case 7: return FB_U_THROTTLE;
-                case 8: return FB_U_MIXTURE; case 9: return FB_U_M_PILOT; case 10: return FB_U_M_COPILOT; case 11: return FB_U_M_LPASS;
-                case 12: return FB_U_M_RPASS; case 13: return FB_U_M_BAGGAGE; default: return -1;
+                case 8: return FB_U_MIXTURE; case 9: return FB_UX_TRF; case 10: return FB_U_M_PILOT; case 11: return FB_U_M_COPILOT;
+                case 12: return FB_U_M_LPASS; case 13: return FB_U_M_RPASS; case 14: return FB_U_M_BAGGAGE; default: return -1;
             }
         } else {
             switch (s) {
                 case 0: return FB_U_T_SL; case 1: return FB_U_P_SL; case 2: return FB_U_TRN_ELEVATION; case 3: return FB_U_ACT_THROTTLE;
                 case 4: return FB_U_ACT_AILERON; case 5: return FB_U_ACT_ELEVATOR; case 6: return FB_U_ACT_RUDDER; case 7: return FB_U_ACT_FLAPS;
-                case 8: return FB_U_MIXTURE; case 9: return FB_U_M_PILOT; case 10: return FB_U_M_COPILOT; case 11: return FB_U_M_LPASS;
-                case 12: return FB_U_M_RPASS; case 13: return FB_U_M_BAGGAGE; case 14: return FB_U_ACT_BRAKE_LEFT; case 15: return FB_U_ACT_BRAKE_RIGHT;
+                case 8: return FB_U_MIXTURE; case 9: return FB_UX_TRF; case 10: return FB_U_M_PILOT; case 11: return FB_U_M_COPILOT;
+                case 12: return FB_U_M_LPASS; case 13: return FB_U_M_RPASS; case 14: return FB_U_M_BAGGAGE; case 15: return FB_U_ACT_BRAKE_LEFT;
                 default: return -1;
             }
         }
@@ -275,20 +278,22 @@ __device__ __noinline__ void isa_upper(double hg, double T_sl, double p_sl, doub
     }
     err = FB_ST_BOUNDS; T = Tb; p = pb;
 }
-__device__ __noinline__ double pow_slow(double a, double b) { return pow(a, b); }
 // ISA temperature / pressure at orthometric altitude h_o, plus tr = (p/p_std)^(-beta R/g) for the engine
-FB_DEV void isa_data(double h_o, double T_sl, double p_sl, double& T, double& p, double& tr, int& err) {
+// trf = (p_sl / p_std)^kT (input-derived, see FB_UX_TRF). TROPO_ONLY (the airborne integrator layout): above 11 km the
+// member is handed to the complete kernel instead of carrying the upper-layer code.
+template <bool TROPO_ONLY = false>
+FB_DEV void isa_data(double h_o, double T_sl, double p_sl, double trf, double& T, double& p, double& tr, int& err) {
     constexpr double beta = -6.5e-3;
     constexpr double k = -isa::g_std / (beta * isa::R);     // 5.2558...
     constexpr double kT = -beta * isa::R / isa::g_std;      // 1 / k
     if (h_o < -1000.0) err = FB_ST_BOUNDS;
     double hg = h_o * wgs::a * fb_rcp(wgs::a + h_o);
-    if (hg < 11000.0) {
+    if (TROPO_ONLY || hg < 11000.0) {
         T = fma(beta, hg, T_sl);
         double ratio = T * fb_rcp(T_sl);
         p = p_sl * exp(k * log(ratio));
-        // (p/p_std)^kT = (p_sl/p_std)^kT * ratio, since k * kT == 1
-        tr = (p_sl == isa::p_std) ? ratio : ratio * pow_slow(p_sl * (1.0 / isa::p_std), kT);
+        tr = ratio * trf;                                   // (p/p_std)^kT = (p_sl/p_std)^kT * ratio, since k * kT == 1
+        if (TROPO_ONLY && !(hg < 11000.0)) err = FB_NEED_COMPLETE;
     } else {   // rare: copies keep the callee's by-reference outputs from pinning the caller's values in local memory
         double T2, p2; int e2 = 0;
         isa_upper(hg, T_sl, p_sl, T2, p2, e2);
@@ -544,7 +549,7 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
 
     // ------------------------------------------------------------------ atmosphere + air data
     Air air;
-    isa_data(k.h_o, u(FB_U_T_SL), u(FB_U_P_SL), air.T, air.p, air.tr, out.err);
+    isa_data<AIR>(k.h_o, u(FB_U_T_SL), u(FB_U_P_SL), u(FB_UX_TRF), air.T, air.p, air.tr, out.err);
     {
         air.iRT = fb_rcp(isa::R * air.T);
         air.rho = air.p * air.iRT;
@@ -672,7 +677,7 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
         double elev = u(FB_U_TRN_ELEVATION);
         if (AIR) {
             // compact layout: regulator states are zero and stay zero while the gate holds; otherwise hand the member over
-            if (!(k.h_o - elev > 4.0)) out.err = FB_NEED_GROUND;
+            if (!(k.h_o - elev > 4.0)) out.err = FB_NEED_COMPLETE;
         } else if (k.h_o - elev > 4.0) {
             // every strut attachment is < 2.4 m from Ob: no wheel can reach the terrain; regulators just leak
 #pragma unroll
