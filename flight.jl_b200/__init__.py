@@ -570,29 +570,109 @@ class BatchSimulation:
         return p.value, pitch.value
 
 
-class TimeSeries:
-    """TimeSeries(sim) (sim.jl:644-704): columnar view over the decimated device log; `ts.theta` is [n_samples, N]."""
+# The reference's dotted path under the root `y` (what `TimeSeries(sim)` drills into, sim.jl:666-676) of every fb_output
+# field; vector components carry the reference's 1-based index. Same table as BatchSimulation.jl.
+Y_PATHS = {
+    "aircraft.vehicle.kinematics.e_nb.ψ": "psi", "aircraft.vehicle.kinematics.e_nb.θ": "theta", "aircraft.vehicle.kinematics.e_nb.φ": "phi",
+    "aircraft.vehicle.kinematics.ϕ_λ.ϕ": "lat", "aircraft.vehicle.kinematics.ϕ_λ.λ": "lon",
+    "aircraft.vehicle.kinematics.h_e": "h_e", "aircraft.vehicle.kinematics.h_o": "h_o",
+    "aircraft.vehicle.kinematics.v_eb_n[1]": "v_n", "aircraft.vehicle.kinematics.v_eb_n[2]": "v_e", "aircraft.vehicle.kinematics.v_eb_n[3]": "v_d",
+    "aircraft.vehicle.kinematics.v_gnd": "v_gnd", "aircraft.vehicle.kinematics.χ_gnd": "chi_gnd", "aircraft.vehicle.kinematics.γ_gnd": "gamma_gnd",
+    "aircraft.vehicle.kinematics.ω_wb_b[1]": "p", "aircraft.vehicle.kinematics.ω_wb_b[2]": "q", "aircraft.vehicle.kinematics.ω_wb_b[3]": "r",
+    "aircraft.vehicle.airflow.TAS": "tas", "aircraft.vehicle.airflow.EAS": "eas", "aircraft.vehicle.airflow.CAS": "cas",
+    "aircraft.vehicle.airflow.M": "mach", "aircraft.vehicle.airflow.q": "qbar",
+    "aircraft.vehicle.systems.aero.α": "alpha", "aircraft.vehicle.systems.aero.β": "beta", "aircraft.vehicle.systems.aero.α_filt": "alpha_filt",
+    "aircraft.vehicle.systems.aero.β_filt": "beta_filt", "aircraft.vehicle.systems.aero.stall": "stall",
+    "aircraft.vehicle.systems.aero.coeffs.C_L": "c_l", "aircraft.vehicle.systems.aero.coeffs.C_D": "c_d",
+    "aircraft.vehicle.systems.ldg.left.strut.wow": "wow_left", "aircraft.vehicle.systems.ldg.right.strut.wow": "wow_right",
+    "aircraft.vehicle.systems.ldg.nose.strut.wow": "wow_nose", "aircraft.vehicle.systems.ldg.left.strut.ξ": "xi_left",
+    "aircraft.vehicle.systems.ldg.right.strut.ξ": "xi_right", "aircraft.vehicle.systems.ldg.nose.strut.ξ": "xi_nose",
+    "aircraft.vehicle.systems.ldg.left.strut.F_dmp_zs": "fdmp_left", "aircraft.vehicle.systems.ldg.right.strut.F_dmp_zs": "fdmp_right",
+    "aircraft.vehicle.systems.ldg.nose.strut.F_dmp_zs": "fdmp_nose",
+    "aircraft.vehicle.systems.pwp.engine.ω": "eng_omega", "aircraft.vehicle.systems.pwp.engine.state": "eng_state",
+    "aircraft.vehicle.systems.pwp.engine.MAP": "eng_map", "aircraft.vehicle.systems.pwp.engine.P_shaft": "eng_p_shaft",
+    "aircraft.vehicle.systems.pwp.engine.τ_shaft": "eng_tau_shaft", "aircraft.vehicle.systems.pwp.engine.ṁ": "eng_mdot",
+    "aircraft.vehicle.systems.fuel.m_total": "fuel_m_total",
+    "aircraft.vehicle.systems.pwp.propeller.wr_p.F[1]": "prop_thrust", "aircraft.vehicle.systems.pwp.propeller.J": "prop_j",
+    "aircraft.vehicle.dynamics.mp_Σ_b.m": "mass",
+    "aircraft.vehicle.dynamics.f_c_c[1]": "f_x", "aircraft.vehicle.dynamics.f_c_c[2]": "f_y", "aircraft.vehicle.dynamics.f_c_c[3]": "f_z",
+    "aircraft.avionics.ctl.lon.mode": "lon_mode", "aircraft.avionics.ctl.lat.mode": "lat_mode",
+    "aircraft.avionics.ctl.lon.throttle_cmd": "throttle_cmd", "aircraft.avionics.ctl.lon.elevator_cmd": "elevator_cmd",
+    "aircraft.avionics.ctl.lat.aileron_cmd": "aileron_cmd", "aircraft.avionics.ctl.lat.rudder_cmd": "rudder_cmd",
+    "aircraft.avionics.ctl.lon.h_state": "alt_state",
+    "aircraft.avionics.gdc.mode": "gdc_mode", "aircraft.avionics.gdc.seg.hor_gdc": "gdc_hor", "aircraft.avionics.gdc.seg.vrt_gdc": "gdc_vrt",
+    "aircraft.avionics.gdc.seg.Δχ": "gdc_dchi", "aircraft.avionics.gdc.seg.χ_ref": "gdc_chi_ref", "aircraft.avionics.gdc.seg.h_ref": "gdc_h_ref",
+    "aircraft.avionics.gdc.seg.data.χ_12": "gdc_chi_12", "aircraft.avionics.gdc.seg.data.γ_12": "gdc_gamma_12",
+    "aircraft.avionics.gdc.seg.data.s_12": "gdc_s_12", "aircraft.avionics.gdc.seg.data.s_1b": "gdc_s_1b",
+    "aircraft.avionics.gdc.seg.data.e_sb": "gdc_e_sb", "aircraft.avionics.gdc.seg.data.v_sb": "gdc_v_sb",
+}
 
-    def __init__(self, sim):
+
+class _YNode:
+    """Lazy drill-down node of a TimeSeries: `ts.aircraft.vehicle.kinematics.e_nb.θ`, `...v_eb_n[0]` (0-based here)."""
+
+    def __init__(self, ts, prefix):
+        object.__setattr__(self, "_ts", ts)
+        object.__setattr__(self, "_prefix", prefix)
+
+    def _resolve(self, path):
+        if path in Y_PATHS:
+            return self._ts._column(Y_PATHS[path])
+        if any(k.startswith(path + ".") or k.startswith(path + "[") for k in Y_PATHS):
+            return _YNode(self._ts, path)
+        raise AttributeError(f"TimeSeries has no logged path {path}")
+
+    def __getattr__(self, name):
+        return self._resolve(f"{self._prefix}.{name}" if self._prefix else name)
+
+    def __getitem__(self, i):
+        return self._resolve(f"{self._prefix}[{int(i) + 1}]")
+
+    def __dir__(self):
+        n = len(self._prefix) + 1 if self._prefix else 0
+        return sorted({k[n:].split(".")[0].split("[")[0] for k in Y_PATHS if k.startswith(self._prefix)})
+
+
+class TimeSeries:
+    """TimeSeries(sim) (sim.jl:644-704): columnar view over the decimated device log. A column is [n_samples, N]; it is
+    fetched from the device on first use, by flat name (`ts.theta`, `ts["theta"]`) or by the reference's path under the
+    root `y` (`ts.aircraft.vehicle.kinematics.e_nb.θ`, lazily drilled like the reference's getproperty, sim.jl:666-676).
+    `ts[k]` with an integer or slice restricts the time axis of every column (sim.jl:683-699)."""
+
+    def __init__(self, sim, _sel=None):
         self._sim = sim
         ns, nf = C.c_int64(), C.c_int32()
         _ck(sim._lib.fb_log_info(sim._h, C.byref(ns), C.byref(nf)), sim._lib)
-        self.n_samples = ns.value
-        self.t = np.zeros(self.n_samples)
-        if self.n_samples:
-            _ck(sim._lib.fb_log_times(sim._h, _dp(self.t)), sim._lib)
+        self._sel = slice(None) if _sel is None else _sel
+        t = np.zeros(ns.value)
+        if ns.value:
+            _ck(sim._lib.fb_log_times(sim._h, _dp(t)), sim._lib)
+        self.t = t[self._sel]
+        self.n_samples = int(np.size(self.t))
+        self._n_all = ns.value
         self._cache = {}
 
-    def __getattr__(self, name):
-        if name.startswith("_") or name not in OUTPUT_NAMES:
-            raise AttributeError(name)
+    def _column(self, name):
         if name not in self._cache:
-            out = np.zeros((self.n_samples, self._sim.n))
+            out = np.zeros((self._n_all, self._sim.n))
             _ck(self._sim._lib.fb_log_fetch(self._sim._h, OUTPUT_NAMES[name], _dp(out)), self._sim._lib)
-            self._cache[name] = out
+            self._cache[name] = out[self._sel]
         return self._cache[name]
 
-    __getitem__ = __getattr__
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        if name in OUTPUT_NAMES:
+            return self._column(name)
+        return _YNode(self, "")._resolve(name)
+
+    def __getitem__(self, key):
+        if isinstance(key, str):
+            return self.__getattr__(key)
+        return TimeSeries(self._sim, _sel=key)
+
+    def __len__(self):
+        return self.n_samples
 
 
 def measure_fp64_peak(device=0):

@@ -11,7 +11,7 @@
 # There is no CPU fallback: every call goes to libflightbatch.so and throws FlightBatchError on a non-zero return.
 module BatchSimulations
 
-export BatchSimulation, FlightBatchError, init!, step!, run!, setinput!, getinput, getoutput, schedule_inputs!, set_segment!,
+export BatchSimulation, FlightBatchError, init!, step!, run!, setinput!, getinput, getoutput, schedule_inputs!, set_segment!, BatchTimeSeries,
        status, stats, linearize, TimeSeriesColumn
 
 const libflightbatch = get(ENV, "FLIGHTBATCH_LIB", joinpath(@__DIR__, "..", "libflightbatch.so"))
@@ -187,6 +187,56 @@ function TimeSeriesColumn(sim::BatchSimulation, field::Integer)
     check(ccall((:fb_log_times, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{Float64}), sim.handle, t))
     check(ccall((:fb_log_fetch, libflightbatch), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}), sim.handle, field, v))
     (t, v)
+end
+
+# ---- TimeSeries(sim) with the reference's lazy drilling (sim.jl:666-676): `ts.aircraft.vehicle.kinematics.e_nb.θ`
+# Path under the root `y` of every fb_output id (same table as Y_PATHS in flight.jl_b200/__init__.py).
+const Y_PATHS = Dict{String,Int32}(
+    "aircraft.vehicle.kinematics.e_nb.ψ" => 0, "aircraft.vehicle.kinematics.e_nb.θ" => 1, "aircraft.vehicle.kinematics.e_nb.φ" => 2,
+    "aircraft.vehicle.kinematics.ϕ_λ.ϕ" => 3, "aircraft.vehicle.kinematics.ϕ_λ.λ" => 4, "aircraft.vehicle.kinematics.h_e" => 5,
+    "aircraft.vehicle.kinematics.h_o" => 6, "aircraft.vehicle.kinematics.v_eb_n[1]" => 7, "aircraft.vehicle.kinematics.v_eb_n[2]" => 8,
+    "aircraft.vehicle.kinematics.v_eb_n[3]" => 9, "aircraft.vehicle.kinematics.v_gnd" => 10, "aircraft.vehicle.kinematics.χ_gnd" => 11,
+    "aircraft.vehicle.kinematics.γ_gnd" => 12, "aircraft.vehicle.kinematics.ω_wb_b[1]" => 13, "aircraft.vehicle.kinematics.ω_wb_b[2]" => 14,
+    "aircraft.vehicle.kinematics.ω_wb_b[3]" => 15, "aircraft.vehicle.airflow.TAS" => 16, "aircraft.vehicle.airflow.EAS" => 17,
+    "aircraft.vehicle.airflow.CAS" => 18, "aircraft.vehicle.airflow.M" => 19, "aircraft.vehicle.airflow.q" => 20,
+    "aircraft.vehicle.systems.aero.α" => 21, "aircraft.vehicle.systems.aero.β" => 22, "aircraft.vehicle.systems.aero.α_filt" => 23,
+    "aircraft.vehicle.systems.aero.β_filt" => 24, "aircraft.vehicle.systems.aero.stall" => 25, "aircraft.vehicle.systems.aero.coeffs.C_L" => 26,
+    "aircraft.vehicle.systems.aero.coeffs.C_D" => 27, "aircraft.vehicle.systems.ldg.left.strut.wow" => 28,
+    "aircraft.vehicle.systems.ldg.right.strut.wow" => 29, "aircraft.vehicle.systems.ldg.nose.strut.wow" => 30,
+    "aircraft.vehicle.systems.ldg.left.strut.ξ" => 31, "aircraft.vehicle.systems.ldg.right.strut.ξ" => 32, "aircraft.vehicle.systems.ldg.nose.strut.ξ" => 33,
+    "aircraft.vehicle.systems.ldg.left.strut.F_dmp_zs" => 34, "aircraft.vehicle.systems.ldg.right.strut.F_dmp_zs" => 35,
+    "aircraft.vehicle.systems.ldg.nose.strut.F_dmp_zs" => 36, "aircraft.vehicle.systems.pwp.engine.ω" => 37,
+    "aircraft.vehicle.systems.pwp.engine.state" => 38, "aircraft.vehicle.systems.pwp.engine.MAP" => 39, "aircraft.vehicle.systems.pwp.engine.P_shaft" => 40,
+    "aircraft.vehicle.systems.pwp.engine.τ_shaft" => 41, "aircraft.vehicle.systems.pwp.engine.ṁ" => 42, "aircraft.vehicle.systems.fuel.m_total" => 43,
+    "aircraft.vehicle.systems.pwp.propeller.wr_p.F[1]" => 44, "aircraft.vehicle.systems.pwp.propeller.J" => 45, "aircraft.vehicle.dynamics.mp_Σ_b.m" => 46,
+    "aircraft.vehicle.dynamics.f_c_c[1]" => 47, "aircraft.vehicle.dynamics.f_c_c[2]" => 48, "aircraft.vehicle.dynamics.f_c_c[3]" => 49,
+    "aircraft.avionics.ctl.lon.mode" => 50, "aircraft.avionics.ctl.lat.mode" => 51, "aircraft.avionics.ctl.lon.throttle_cmd" => 52,
+    "aircraft.avionics.ctl.lon.elevator_cmd" => 53, "aircraft.avionics.ctl.lat.aileron_cmd" => 54, "aircraft.avionics.ctl.lat.rudder_cmd" => 55,
+    "aircraft.avionics.ctl.lon.h_state" => 56, "aircraft.avionics.gdc.mode" => 57, "aircraft.avionics.gdc.seg.hor_gdc" => 58,
+    "aircraft.avionics.gdc.seg.vrt_gdc" => 59, "aircraft.avionics.gdc.seg.Δχ" => 60, "aircraft.avionics.gdc.seg.χ_ref" => 61,
+    "aircraft.avionics.gdc.seg.h_ref" => 62, "aircraft.avionics.gdc.seg.data.χ_12" => 63, "aircraft.avionics.gdc.seg.data.γ_12" => 64,
+    "aircraft.avionics.gdc.seg.data.s_12" => 65, "aircraft.avionics.gdc.seg.data.s_1b" => 66, "aircraft.avionics.gdc.seg.data.e_sb" => 67,
+    "aircraft.avionics.gdc.seg.data.v_sb" => 68)
+
+"`BatchTimeSeries(sim)`: lazy view over the device log; a leaf is `(t, values)` with `values` of size N × n_samples"
+struct BatchTimeSeries
+    sim::BatchSimulation
+    path::String
+end
+BatchTimeSeries(sim::BatchSimulation) = BatchTimeSeries(sim, "")
+function _resolve(ts::BatchTimeSeries, path::String)
+    haskey(Y_PATHS, path) && return TimeSeriesColumn(getfield(ts, :sim), Y_PATHS[path])
+    any(k -> startswith(k, path * ".") || startswith(k, path * "["), keys(Y_PATHS)) && return BatchTimeSeries(getfield(ts, :sim), path)
+    error("TimeSeries has no path $path")
+end
+function Base.getproperty(ts::BatchTimeSeries, s::Symbol)
+    p = getfield(ts, :path)
+    _resolve(ts, isempty(p) ? String(s) : p * "." * String(s))
+end
+Base.getindex(ts::BatchTimeSeries, i::Integer) = _resolve(ts, getfield(ts, :path) * "[$i]")
+Base.propertynames(ts::BatchTimeSeries) = begin
+    p = getfield(ts, :path); n = isempty(p) ? 0 : length(p) + 1
+    unique(Symbol(first(split(first(split(chop(k, head = n, tail = 0), ".")), "["))) for k in keys(Y_PATHS) if startswith(k, p))
 end
 
 """
