@@ -140,7 +140,10 @@ struct StepShape {
     static constexpr int FIT = (int)(BUDGET / (sizeof(double) * 2 * NX)) / 32 * 32;
     static constexpr int T = FIT < CAP ? FIT : CAP;
     static constexpr int SPARE = (int)(BUDGET / (sizeof(double) * T)) - 2 * NX;                // columns left for the input cache
-    static constexpr int NSLOT = SPARE < 16 ? SPARE : 16;
+#ifndef FB_NSLOT_MAX
+#define FB_NSLOT_MAX 16
+#endif
+    static constexpr int NSLOT = SPARE < FB_NSLOT_MAX ? SPARE : FB_NSLOT_MAX;
     static constexpr size_t SMEM = FB_TB_BYTES + sizeof(double) * (2 * NX + NSLOT) * T;
 };
 #define FB_RESUME_PENDING (1 << 30)
