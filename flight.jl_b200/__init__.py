@@ -94,7 +94,9 @@ class fb_moments(C.Structure):
 EXPORTS = ["fb_api_version", "fb_last_error", "fb_create", "fb_load_tables", "fb_destroy", "fb_sync", "fb_init_trim", "fb_init",
            "fb_init_state", "fb_set_input", "fb_get_input", "fb_schedule_inputs", "fb_step", "fb_run", "fb_time", "fb_nx",
            "fb_get_state", "fb_get_discrete", "fb_get_output", "fb_status", "fb_log_info", "fb_log_times", "fb_log_fetch",
-           "fb_stats", "fb_rhs", "fb_fstep", "fb_fperiodic", "fb_counters", "fb_linearize", "fb_linearize_dims", "fb_device_state", "fb_stream", "fb_measure_fp64_peak"]
+           "fb_stats", "fb_rhs", "fb_fstep", "fb_fperiodic", "fb_counters", "fb_linearize", "fb_linearize_dims", "fb_device_state", "fb_stream", "fb_measure_fp64_peak",
+           "fb_lss_create", "fb_lss_destroy", "fb_lss_set_model", "fb_lss_from_linearize", "fb_lss_set_state", "fb_lss_get_state",
+           "fb_lss_set_input", "fb_lss_get_input", "fb_lss_get_output", "fb_lss_step", "fb_lss_sync", "fb_lss_stream"]
 
 _lib = None
 
@@ -126,6 +128,11 @@ def load_library():
         "fb_device_state": (i32, [vp, C.POINTER(vp), C.POINTER(i64)]), "fb_stream": (i32, [vp, C.POINTER(vp)]),
         "fb_measure_fp64_peak": (i32, [i32, _DP]),
         "fb_linearize_dims": (i32, [vp, C.POINTER(i32)]), "fb_linearize": (i32, [vp] + [_DP] * 8),
+        "fb_lss_create": (i32, [i32, i64, i32, i32, i32, dbl, C.POINTER(vp)]), "fb_lss_destroy": (i32, [vp]),
+        "fb_lss_set_model": (i32, [vp] + [_DP] * 8), "fb_lss_from_linearize": (i32, [vp, vp]),
+        "fb_lss_set_state": (i32, [vp, _DP]), "fb_lss_get_state": (i32, [vp, _DP]), "fb_lss_set_input": (i32, [vp, _DP]),
+        "fb_lss_get_input": (i32, [vp, _DP]), "fb_lss_get_output": (i32, [vp, _DP]), "fb_lss_step": (i32, [vp, dbl]),
+        "fb_lss_sync": (i32, [vp]), "fb_lss_stream": (i32, [vp, C.POINTER(vp)]),
     }
     for name in EXPORTS:
         f = getattr(lib, name)   # AttributeError if the library does not export a declared symbol
@@ -673,6 +680,73 @@ class TimeSeries:
 
     def __len__(self):
         return self.n_samples
+
+
+class LinearizedSS:
+    """N LinearizedSS models (linearization.jl:24-111) stepped in lock-step: `Simulation(Model(linearize(aircraft, trim)))`
+    of the reference's README example 3 for every member. Build it from a trimmed NED BatchSimulation (`LinearizedSS(sim)`,
+    Jacobians stay on the device) or from arrays in the layout `BatchSimulation.linearize()` returns. State, input and
+    output vectors are the reference's XStateSpace / UStateSpace / YStateSpace (c172s.jl:269-412, c172x.jl:332-498)."""
+
+    def __init__(self, sim=None, model=None, n=None, dt=0.01, device=0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        if sim is not None:
+            d = (C.c_int32 * 3)()
+            _ck(self._lib.fb_linearize_dims(sim._h, d), self._lib)
+            self.nx, self.nu, self.ny, self.n, dt, device = d[0], d[1], d[2], sim.n, sim.dt, sim.cfg.device
+        else:
+            self.nx, self.nu, self.ny = model["A"].shape[1], model["B"].shape[2], model["C"].shape[1]
+            self.n = model["A"].shape[0] if n is None else n
+        self.dt = dt
+        _ck(self._lib.fb_lss_create(int(device), self.n, self.nx, self.nu, self.ny, float(dt), C.byref(self._h)), self._lib)
+        if sim is not None:
+            _ck(self._lib.fb_lss_from_linearize(self._h, sim._h), self._lib)
+        else:
+            raw = [np.ascontiguousarray(np.transpose(model[k], (2, 1, 0))) for k in ("A", "B", "C", "D")]   # [N][row][col] -> [col][row][N]
+            raw += [np.ascontiguousarray(np.asarray(model[k]).T) for k in ("x0", "u0", "y0", "xdot0")]
+            _ck(self._lib.fb_lss_set_model(self._h, *[_dp(a) for a in raw]), self._lib)
+
+    def _get(self, fn, rows):
+        out = np.empty((rows, self.n))
+        _ck(fn(self._h, _dp(out)), self._lib)
+        return out
+
+    @property
+    def x(self):
+        return self._get(self._lib.fb_lss_get_state, self.nx)
+
+    @x.setter
+    def x(self, v):
+        _ck(self._lib.fb_lss_set_state(self._h, _dp(np.ascontiguousarray(v, dtype=np.float64))), self._lib)
+
+    @property
+    def u(self):
+        return self._get(self._lib.fb_lss_get_input, self.nu)
+
+    @u.setter
+    def u(self, v):
+        _ck(self._lib.fb_lss_set_input(self._h, _dp(np.ascontiguousarray(v, dtype=np.float64))), self._lib)
+
+    @property
+    def y(self):
+        return self._get(self._lib.fb_lss_get_output, self.ny)
+
+    def step(self, t_advance=None):
+        _ck(self._lib.fb_lss_step(self._h, float(self.dt if t_advance is None else t_advance)), self._lib)
+
+    def sync(self):
+        _ck(self._lib.fb_lss_sync(self._h), self._lib)
+
+    def stream_handle(self):
+        p = C.c_void_p()
+        _ck(self._lib.fb_lss_stream(self._h, C.byref(p)), self._lib)
+        return p.value
+
+    def close(self):
+        if self._h:
+            self._lib.fb_lss_destroy(self._h)
+            self._h = C.c_void_p()
 
 
 def measure_fp64_peak(device=0):

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <numeric>
 #include "fb_init.cuh"
+#include "fb_lss.cuh"
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -813,6 +814,159 @@ int32_t fb_linearize(fb_handle s, double* A, double* B, double* C, double* D, do
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
     cudaFree(dbuf);
     if (e != cudaSuccess) return fail(FB_ERR_CUDA, std::string("fb_linearize: ") + cudaGetErrorString(e));
+    return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ LinearizedSS
+struct fb_lss {
+    int device = 0, nx = 0, nu = 0, ny = 0;
+    long long n = 0, pitch = 0, n_steps = 0;
+    double dt = 0.0;
+    double* buf = nullptr;     // one allocation: A B C D x0 u0 y0 xd0 x u y
+    double* y = nullptr;
+    LssDev L{};
+    cudaStream_t stream = nullptr;
+    bool has_model = false;
+};
+
+int32_t fb_lss_create(int32_t device, int64_t n, int32_t nx, int32_t nu, int32_t ny, double dt, fb_lss_handle* out) {
+    if (!out) return fail(FB_ERR_ARG, "fb_lss_create: null argument");
+    if (n <= 0 || !(dt > 0.0)) return fail(FB_ERR_ARG, "fb_lss_create: n and dt must be positive");
+    if (!((nx == 16 && ny == 33) || (nx == 20 && ny == 38)) || nu != 4)
+        return fail(FB_ERR_ARG, "fb_lss_create: (nx, nu, ny) must be (16, 4, 33) [C172S] or (20, 4, 38) [C172X], the XStateSpace / UStateSpace / YStateSpace sizes");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(FB_ERR_CUDA, "fb_lss_create: no CUDA device (there is no CPU fallback)");
+    CK(cudaSetDevice(device));
+    fb_lss* l = new fb_lss();
+    l->device = device; l->nx = nx; l->nu = nu; l->ny = ny; l->n = n; l->pitch = (n + 31) / 32 * 32; l->dt = dt;
+    const long long P = l->pitch;
+    const long long counts[11] = {(long long)nx * nx, (long long)nx * nu, (long long)ny * nx, (long long)ny * nu, nx, nu, ny, nx, nx, nu, ny};
+    long long total = 0; for (long long c : counts) total += c;
+    if (cudaMalloc(&l->buf, sizeof(double) * total * P) != cudaSuccess) { delete l; return fail(FB_ERR_ALLOC, "fb_lss_create: out of device memory"); }
+    CK(cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking));
+    CK(cudaMemsetAsync(l->buf, 0, sizeof(double) * total * P, l->stream));
+    double* p[11]; long long off = 0;
+    for (int k = 0; k < 11; k++) { p[k] = l->buf + off * P; off += counts[k]; }
+    l->L.A = p[0]; l->L.B = p[1]; l->L.C = p[2]; l->L.D = p[3]; l->L.x0 = p[4]; l->L.u0 = p[5]; l->L.y0 = p[6]; l->L.xd0 = p[7];
+    l->L.x = p[8]; l->L.u = p[9]; l->y = p[10]; l->L.pitch = P; l->L.n = n;
+    *out = l;
+    return FB_OK;
+}
+
+int32_t fb_lss_destroy(fb_lss_handle l) {
+    if (!l) return FB_OK;
+    cudaSetDevice(l->device);
+    cudaStreamSynchronize(l->stream);
+    cudaFree(l->buf); cudaStreamDestroy(l->stream);
+    delete l;
+    return FB_OK;
+}
+
+static cudaError_t lss_rows_h2d(fb_lss* l, double* dst, const double* src, long long rows) {
+    return cudaMemcpy2DAsync(dst, sizeof(double) * l->pitch, src, sizeof(double) * l->n, sizeof(double) * l->n, rows, cudaMemcpyHostToDevice, l->stream);
+}
+static void lss_reset_to_operating_point(fb_lss* l) {   // X(lss) = copy(x0), U(lss) = copy(u0), linearization.jl:152-153
+    cudaMemcpyAsync(l->L.x, l->L.x0, sizeof(double) * l->nx * l->pitch, cudaMemcpyDeviceToDevice, l->stream);
+    cudaMemcpyAsync(l->L.u, l->L.u0, sizeof(double) * l->nu * l->pitch, cudaMemcpyDeviceToDevice, l->stream);
+    l->n_steps = 0;
+}
+
+int32_t fb_lss_set_model(fb_lss_handle l, const double* A, const double* B, const double* C, const double* D,
+                         const double* x0, const double* u0, const double* y0, const double* xdot0) {
+    if (!l || !A || !B || !C || !D || !x0 || !u0 || !y0 || !xdot0) return fail(FB_ERR_ARG, "fb_lss_set_model: null argument");
+    CK(cudaSetDevice(l->device));
+    const long long nx = l->nx, nu = l->nu, ny = l->ny;
+    CK(lss_rows_h2d(l, l->L.A, A, nx * nx)); CK(lss_rows_h2d(l, l->L.B, B, nx * nu)); CK(lss_rows_h2d(l, l->L.C, C, ny * nx));
+    CK(lss_rows_h2d(l, l->L.D, D, ny * nu)); CK(lss_rows_h2d(l, l->L.x0, x0, nx)); CK(lss_rows_h2d(l, l->L.u0, u0, nu));
+    CK(lss_rows_h2d(l, l->L.y0, y0, ny)); CK(lss_rows_h2d(l, l->L.xd0, xdot0, nx));
+    lss_reset_to_operating_point(l);
+    CK(cudaStreamSynchronize(l->stream));
+    l->has_model = true;
+    return FB_OK;
+}
+
+int32_t fb_lss_from_linearize(fb_lss_handle l, fb_handle s) {
+    if (!l || !s) return fail(FB_ERR_ARG, "fb_lss_from_linearize: null argument");
+    if (!s->initialised) return fail(FB_ERR_STATE, "fb_lss_from_linearize: the simulation is not initialised (trim first)");
+    if (s->cfg.kinematics != FB_NED) return fail(FB_ERR_ARG, "fb_lss_from_linearize: needs NED kinematics");
+    int32_t d[3]; fb_linearize_dims(s, d);
+    if (d[0] != l->nx || d[1] != l->nu || d[2] != l->ny || s->E.n != l->n || s->cfg.device != l->device)
+        return fail(FB_ERR_ARG, "fb_lss_from_linearize: sizes / device of the two handles differ");
+    CK(cudaSetDevice(l->device));
+    CK(cudaStreamSynchronize(l->stream));
+    CK(FB_DISPATCH(s, linearize)(s, l->L.A, l->L.B, l->L.C, l->L.D, l->L.x0, l->L.u0, l->L.y0, l->L.xd0));   // device to device
+    CK(cudaStreamSynchronize(s->stream));
+    lss_reset_to_operating_point(l);
+    CK(cudaStreamSynchronize(l->stream));
+    l->has_model = true;
+    return FB_OK;
+}
+
+int32_t fb_lss_set_state(fb_lss_handle l, const double* x) {
+    if (!l || !x) return fail(FB_ERR_ARG, "fb_lss_set_state: null argument");
+    CK(cudaSetDevice(l->device));
+    CK(lss_rows_h2d(l, l->L.x, x, l->nx));
+    CK(cudaStreamSynchronize(l->stream));
+    return FB_OK;
+}
+int32_t fb_lss_set_input(fb_lss_handle l, const double* u) {
+    if (!l || !u) return fail(FB_ERR_ARG, "fb_lss_set_input: null argument");
+    CK(cudaSetDevice(l->device));
+    CK(lss_rows_h2d(l, l->L.u, u, l->nu));
+    CK(cudaStreamSynchronize(l->stream));
+    return FB_OK;
+}
+int32_t fb_lss_get_state(fb_lss_handle l, double* x) {
+    if (!l || !x) return fail(FB_ERR_ARG, "fb_lss_get_state: null argument");
+    CK(cudaSetDevice(l->device));
+    CK(cudaMemcpy2DAsync(x, sizeof(double) * l->n, l->L.x, sizeof(double) * l->pitch, sizeof(double) * l->n, l->nx, cudaMemcpyDeviceToHost, l->stream));
+    CK(cudaStreamSynchronize(l->stream));
+    return FB_OK;
+}
+int32_t fb_lss_get_input(fb_lss_handle l, double* u) {
+    if (!l || !u) return fail(FB_ERR_ARG, "fb_lss_get_input: null argument");
+    CK(cudaSetDevice(l->device));
+    CK(cudaMemcpy2DAsync(u, sizeof(double) * l->n, l->L.u, sizeof(double) * l->pitch, sizeof(double) * l->n, l->nu, cudaMemcpyDeviceToHost, l->stream));
+    CK(cudaStreamSynchronize(l->stream));
+    return FB_OK;
+}
+int32_t fb_lss_get_output(fb_lss_handle l, double* y) {
+    if (!l || !y) return fail(FB_ERR_ARG, "fb_lss_get_output: null argument");
+    if (!l->has_model) return fail(FB_ERR_STATE, "fb_lss_get_output: no model (fb_lss_set_model / fb_lss_from_linearize)");
+    CK(cudaSetDevice(l->device));
+    lss_output_kernel<<<(int)((l->n + 127) / 128), 128, 0, l->stream>>>(l->L, l->nx, l->nu, l->ny, l->y);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy2DAsync(y, sizeof(double) * l->n, l->y, sizeof(double) * l->pitch, sizeof(double) * l->n, l->ny, cudaMemcpyDeviceToHost, l->stream));
+    CK(cudaStreamSynchronize(l->stream));
+    return FB_OK;
+}
+int32_t fb_lss_step(fb_lss_handle l, double t_advance) {
+    if (!l) return fail(FB_ERR_ARG, "null handle");
+    if (!l->has_model) return fail(FB_ERR_STATE, "fb_lss_step: no model (fb_lss_set_model / fb_lss_from_linearize)");
+    if (t_advance < 0) return fail(FB_ERR_ARG, "fb_lss_step: negative advance");
+    CK(cudaSetDevice(l->device));
+    long long n = llround(t_advance / l->dt);
+    const int wpb = 8;                                            // warps per CTA; a warp holds two 16-state members or one 20-state member
+    const long long mpb = (l->nx == 16) ? 2 * wpb : wpb;
+    int grid = (int)((l->n + mpb - 1) / mpb);
+    while (n > 0) {
+        int k = (int)std::min<long long>(n, 1 << 20);
+        if (l->nx == 16) lss_step_kernel<16, 4><<<grid, wpb * 32, 0, l->stream>>>(l->L, k, l->dt);
+        else lss_step_kernel<20, 4><<<grid, wpb * 32, 0, l->stream>>>(l->L, k, l->dt);
+        CK(cudaGetLastError());
+        l->n_steps += k; n -= k;
+    }
+    return FB_OK;
+}
+int32_t fb_lss_sync(fb_lss_handle l) {
+    if (!l) return fail(FB_ERR_ARG, "null handle");
+    CK(cudaSetDevice(l->device));
+    CK(cudaStreamSynchronize(l->stream));
+    return FB_OK;
+}
+int32_t fb_lss_stream(fb_lss_handle l, void** stream) {
+    if (!l || !stream) return fail(FB_ERR_ARG, "fb_lss_stream: null argument");
+    *stream = (void*)l->stream;
     return FB_OK;
 }
 

@@ -11,7 +11,7 @@
 # There is no CPU fallback: every call goes to libflightbatch.so and throws FlightBatchError on a non-zero return.
 module BatchSimulations
 
-export BatchSimulation, FlightBatchError, init!, step!, run!, setinput!, getinput, getoutput, schedule_inputs!, set_segment!, BatchTimeSeries,
+export BatchSimulation, FlightBatchError, init!, step!, run!, setinput!, getinput, getoutput, schedule_inputs!, set_segment!, BatchTimeSeries, BatchLinearizedSS, getstate, getinputs, getoutputs, setinputs!, setstate!,
        status, stats, linearize, TimeSeriesColumn
 
 const libflightbatch = get(ENV, "FLIGHTBATCH_LIB", joinpath(@__DIR__, "..", "libflightbatch.so"))
@@ -257,5 +257,32 @@ function linearize(sim::BatchSimulation)
                 sim.handle, A, B, C, D, x0, u0, y0))
     (A, B, C, D, x0, u0, y0)
 end
+
+# ---- LinearizedSS ensembles (linearization.jl:24-111,157-192; README example 3 per member) ----------------------
+"N `LinearizedSS` models stepped in lock-step on the GPU; built device-to-device from a trimmed NED `BatchSimulation`"
+mutable struct BatchLinearizedSS
+    handle::Ptr{Cvoid}
+    n::Int64; nx::Int32; nu::Int32; ny::Int32; dt::Float64
+end
+function BatchLinearizedSS(sim::BatchSimulation)
+    d = zeros(Int32, 3)
+    check(ccall((:fb_linearize_dims, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{Int32}), sim.handle, d))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:fb_lss_create, libflightbatch), Int32, (Int32, Int64, Int32, Int32, Int32, Float64, Ref{Ptr{Cvoid}}),
+                sim.device, sim.n, d[1], d[2], d[3], sim.dt, h))
+    check(ccall((:fb_lss_from_linearize, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), h[], sim.handle))
+    lss = BatchLinearizedSS(h[], sim.n, d[1], d[2], d[3], sim.dt)
+    finalizer(l -> ccall((:fb_lss_destroy, libflightbatch), Int32, (Ptr{Cvoid},), l.handle), lss)
+end
+step!(lss::BatchLinearizedSS, Δt::Real = lss.dt) = check(ccall((:fb_lss_step, libflightbatch), Int32, (Ptr{Cvoid}, Float64), lss.handle, Δt))
+function _lss_get(lss::BatchLinearizedSS, f::Symbol, rows::Integer)
+    out = Matrix{Float64}(undef, lss.n, rows)      # N × rows: the C layout [rows][N]
+    check(ccall((f, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{Float64}), lss.handle, out)); out
+end
+getstate(lss::BatchLinearizedSS) = _lss_get(lss, :fb_lss_get_state, lss.nx)
+getinputs(lss::BatchLinearizedSS) = _lss_get(lss, :fb_lss_get_input, lss.nu)
+getoutputs(lss::BatchLinearizedSS) = _lss_get(lss, :fb_lss_get_output, lss.ny)
+setinputs!(lss::BatchLinearizedSS, u::Matrix{Float64}) = check(ccall((:fb_lss_set_input, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{Float64}), lss.handle, u))
+setstate!(lss::BatchLinearizedSS, x::Matrix{Float64}) = check(ccall((:fb_lss_set_state, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{Float64}), lss.handle, x))
 
 end # module

@@ -232,6 +232,28 @@ int32_t fb_stats(fb_handle h, int32_t field, fb_moments* out);
 int32_t fb_linearize_dims(fb_handle h, int32_t dims[3]);
 int32_t fb_linearize(fb_handle h, double* A, double* B, double* C, double* D, double* x0, double* u0, double* y0, double* xdot0);
 
+/* ---- LinearizedSS ensembles ------------------------------------------------------------------
+ * N linear state-space models xdot = xdot0 + A (x - x0) + B (u - u0), y = y0 + C (x - x0) + D (u - u0)
+ * (lib/FlightPhysics/src/linearization.jl:24-111,157-192) stepped in lock-step by the same fixed-step RK4: the
+ * `Simulation(Model(linearize(aircraft, trim)))` of the reference's README example 3 (README.md:142-204), per member.
+ * Array layouts are exactly those fb_linearize writes. The state starts at x0 and the input at u0 (X(lss) = copy(x0),
+ * U(lss) = copy(u0), linearization.jl:152-153). */
+typedef struct fb_lss* fb_lss_handle;
+int32_t fb_lss_create(int32_t device, int64_t n_members, int32_t nx, int32_t nu, int32_t ny, double dt, fb_lss_handle* out);
+int32_t fb_lss_destroy(fb_lss_handle l);
+int32_t fb_lss_set_model(fb_lss_handle l, const double* A, const double* B, const double* C, const double* D,
+                         const double* x0, const double* u0, const double* y0, const double* xdot0);
+/* LinearizedSS(linearize(aircraft, trim)) of every member of `sim`, device to device (same N, same device) */
+int32_t fb_lss_from_linearize(fb_lss_handle l, fb_handle sim);
+int32_t fb_lss_set_state(fb_lss_handle l, const double* x);   /* [nx][N] */
+int32_t fb_lss_get_state(fb_lss_handle l, double* x);
+int32_t fb_lss_set_input(fb_lss_handle l, const double* u);   /* [nu][N]: throttle, aileron, elevator, rudder commands */
+int32_t fb_lss_get_input(fb_lss_handle l, double* u);
+int32_t fb_lss_get_output(fb_lss_handle l, double* y);        /* [ny][N] */
+int32_t fb_lss_step(fb_lss_handle l, double t_advance);       /* step!(sim, t_advance, true); asynchronous */
+int32_t fb_lss_sync(fb_lss_handle l);
+int32_t fb_lss_stream(fb_lss_handle l, void** stream);
+
 /* ---- test hooks: the Modeling protocol pieces, for parity checks in isolation ---------- */
 /* f_ode!(world) at the current state: writes ẋ [nx][N] (modeling.jl:201-254, world.jl:26-32) */
 int32_t fb_rhs(fb_handle h, double* xdot);

@@ -63,6 +63,7 @@ def _load(name):
         "orc_h2delta": (dbl, [dbl]),
         "orc_gain_lookup": (i32, [i32, dbl, dbl, dp]),
         "orc_geo_roundtrip": (None, [dbl, dbl, dbl, dp]),
+        "orc_lss_step": (None, [i32, i32, dp, dp, dp, dp, dp, dp, dp, dbl, i64]),
         "orc_segment_end": (None, [dbl, dbl, dbl, dbl, dbl, dbl, dp]),
         "orc_segment_data": (None, [dp, dp, dp, dp]),
         "orc_segment_valid": (i32, [dp, dp]),
@@ -275,6 +276,14 @@ def gain_lookup(which, EAS, h):
     out = np.zeros(64)
     n = lib().orc_gain_lookup(int(which), float(EAS), float(h), _dp(out))
     return out[:n]
+
+
+def lss_step(A, B, x0, u0, xdot0, x, u, dt, n_steps):
+    """LinearizedSS (linearization.jl:157-192) under the path's fixed-step RK4; A [nx, nx], B [nx, nu] row-major. Returns x."""
+    A, B, x0, u0, xdot0, u = (np.ascontiguousarray(v, dtype=np.float64) for v in (A, B, x0, u0, xdot0, u))
+    x = np.array(x, dtype=np.float64)
+    lib().orc_lss_step(A.shape[0], B.shape[1], _dp(A), _dp(B), _dp(x0), _dp(u0), _dp(xdot0), _dp(x), _dp(u), float(dt), int(n_steps))
+    return x
 
 
 def segment_end(p1, s, chi, dh=None, gamma=None):

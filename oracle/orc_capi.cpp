@@ -446,6 +446,32 @@ int orc_segment_valid(const double* p1, const double* p2) {
     return segment_valid(a, b) ? 1 : 0;
 }
 
+// LinearizedSS f_ode! (linearization.jl:157-192) under the fixed-step RK4 of Sim::step(): row-major A [nx][nx], B [nx][nu];
+// x is advanced in place by n_steps steps with the input held at u
+void orc_lss_step(int nx, int nu, const double* A, const double* B, const double* x0, const double* u0, const double* xd0,
+                  double* x, const double* u, double dt, long long n_steps) {
+    std::vector<double> k1(nx), k2(nx), k3(nx), k4(nx), xs(nx), dx(nx), du(nu), c(nx);
+    auto f = [&](const double* xv, double* out) {
+        for (int i = 0; i < nx; i++) dx[i] = xv[i] - x0[i];
+        for (int i = 0; i < nu; i++) du[i] = u[i] - u0[i];
+        for (int i = 0; i < nx; i++) out[i] = xd0[i];
+        for (int i = 0; i < nx; i++) { double a = 0.0; for (int j = 0; j < nx; j++) a += A[i * nx + j] * dx[j]; c[i] = a; }
+        for (int i = 0; i < nx; i++) out[i] += c[i];
+        for (int i = 0; i < nx; i++) { double a = 0.0; for (int j = 0; j < nu; j++) a += B[i * nu + j] * du[j]; c[i] = a; }
+        for (int i = 0; i < nx; i++) out[i] += c[i];
+    };
+    for (long long s = 0; s < n_steps; s++) {
+        f(x, k1.data());
+        for (int i = 0; i < nx; i++) xs[i] = x[i] + (dt / 2) * k1[i];
+        f(xs.data(), k2.data());
+        for (int i = 0; i < nx; i++) xs[i] = x[i] + (dt / 2) * k2[i];
+        f(xs.data(), k3.data());
+        for (int i = 0; i < nx; i++) xs[i] = x[i] + dt * k3[i];
+        f(xs.data(), k4.data());
+        for (int i = 0; i < nx; i++) x[i] = x[i] + (dt / 6) * (2.0 * (k2[i] + k3[i]) + (k1[i] + k4[i]));
+    }
+}
+
 void orc_ops_reset() {
 #if ORC_COUNT
     g_ops = OpCounts();

@@ -6,6 +6,7 @@ warm-up first, one JSON line per configuration).
     python tools/bench_configs.py cfg3 [--members N] [--seconds S]     Cessna172Xv2 autopilot ensemble (EAS_clm / phi_beta, wind)
     python tools/bench_configs.py cfg4 [--members N] [--seconds S]     takeoff / landing ensemble (gear contact, engine start)
     python tools/bench_configs.py cfg5 [--members N]                   envelope sweep: batched trim + linearize
+    python tools/bench_configs.py lss  [--members N] [--seconds S]     LinearizedSS ensemble (warp-per-member linear RK4)
 """
 import argparse
 import json
@@ -127,15 +128,42 @@ def cfg5(fb, n, seconds):
             "A_shape": list(np.shape(lin["A"]))}
 
 
+def lss(fb, n, seconds):
+    """LinearizedSS ensemble (README example 3 per member): linearize a trimmed C172S/NED ensemble on the device, step the
+    N linear models with the warp-per-member RK4 kernel."""
+    import torch
+    rng = np.random.default_rng(SEED + 5)
+    sim = fb.BatchSimulation(fb.SimpleWorld(fb.Cessna172Sv0(fb.NED())), n=n, dt=DT, t_end=10.0)
+    ok, _, _ = sim.init(fb.C172.TrimParameters(EAS=rng.uniform(30, 55, n), h_e=rng.uniform(50, 3050, n)))
+    m = fb.LinearizedSS(sim)
+    u = m.u; u[2] += 0.1; m.u = u
+    stream = torch.cuda.ExternalStream(m.stream_handle())
+    m.step(1.0); m.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k = int(round(seconds))
+    e0.record(stream)
+    for _ in range(k):
+        m.step(1.0)
+    e1.record(stream)
+    m.sync()
+    ms = e0.elapsed_time(e1)
+    steps = k * 100
+    out = {"config": "LinearizedSS ensemble: N 16-state linear models from linearize() of a trimmed Cessna172Sv0/NED ensemble, elevator step, RK4 dt = 0.01",
+           "members": n, "rk4_steps": steps, "ms": ms, "model_steps_per_s": n * steps / (ms * 1e-3),
+           "fma_tflops": n * steps / (ms * 1e-3) * 4 * (16 * 16 + 16) * 2e-12}
+    m.close(); sim.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("which", choices=["cfg3", "cfg4", "cfg5"])
+    ap.add_argument("which", choices=["cfg3", "cfg4", "cfg5", "lss"])
     ap.add_argument("--members", type=int, default=0)
     ap.add_argument("--seconds", type=float, default=10.0)
     args = ap.parse_args()
     import flightbatch as fb
-    n = args.members or {"cfg3": 1 << 20, "cfg4": 1 << 18, "cfg5": 100000}[args.which]
-    out = {"cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5}[args.which](fb, n, args.seconds)
+    n = args.members or {"cfg3": 1 << 20, "cfg4": 1 << 18, "cfg5": 100000, "lss": 65536}[args.which]
+    out = {"cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "lss": lss}[args.which](fb, n, args.seconds)
     print(json.dumps(out))
 
 
