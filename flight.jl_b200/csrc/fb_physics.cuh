@@ -320,8 +320,10 @@ FB_DEV double get_mu(double mu_s, double mu_d, double v) {  // landinggear.jl:17
 struct Kin { q4 q_nb, q_eb; d3 n_e, r_eb_e, w_wb_b, w_eb_b, v_eb_b, v_eb_n; double h_e, h_o, lat, lon; };
 
 // one landing-gear unit (strut + contact). Adds its wrench to (F, tau) in body axes. Off the airborne fast path,
-// so it keeps IEEE divisions: wheel speeds and damper rates pass through zero here.
-__device__ __noinline__ void ldg_unit(const Kin& k, const float* __restrict__ geoid, double elev, int surface,
+// so it keeps IEEE divisions: wheel speeds and damper rates pass through zero here. Inlined ONCE, inside the
+// non-unrolled loop over the three legs of the RHS: an out-of-line copy would receive the kinematic data through
+// local memory (~25 L2 round trips per leg), three inlined copies would triple the code the I-cache has to hold.
+FB_DEV void ldg_unit(const Kin& k, const float* __restrict__ geoid, double elev, int surface,
                                       d3 r_bs_b, double k_s, double k_d_ext, double k_d_cmp,
                                       bool has_steering, bool steering_engaged, double steer_input, double brake,
                                       double x0, double x1, double& xd0, double& xd1, d3& F, d3& tau, int leg, RhsOut& out,
@@ -687,16 +689,24 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
             out.gnd = 1;
             int surface = (int)u(FB_U_TRN_SURFACE);
             bool eng = u(FB_U_STEERING_ENGAGED) != 0.0;
-            // the out-of-line strut code works on copies: taking addresses of k / F / tau / out themselves would pin
-            // them in local memory on the airborne fast path as well
-            Kin kk = k; d3 Fl = mk3(0, 0, 0), taul = mk3(0, 0, 0); RhsOut ol; ol.wow = 0; ol.crash = 0; ol.err = 0; ol.alpha = 0.0; ol.gnd = 1;
+            d3 Fl = mk3(0, 0, 0), taul = mk3(0, 0, 0); RhsOut ol; ol.wow = 0; ol.crash = 0; ol.err = 0; ol.alpha = 0.0; ol.gnd = 1;
             double xd[6];
-            ldg_unit(kk, geoid, elev, surface, mk3(-0.381, -1.092, 1.902), 39404, 9340, 9340, false, false, 0.0, br_l,
-                     x[L::LDG], x[L::LDG + 1], xd[0], xd[1], Fl, taul, 0, ol, WY ? &yf->xi[0] : nullptr, WY ? &yf->F_dmp[0] : nullptr);
-            ldg_unit(kk, geoid, elev, surface, mk3(-0.381, 1.092, 1.902), 39404, 9340, 9340, false, false, 0.0, br_r,
-                     x[L::LDG + 2], x[L::LDG + 3], xd[2], xd[3], Fl, taul, 1, ol, WY ? &yf->xi[1] : nullptr, WY ? &yf->F_dmp[1] : nullptr);
-            ldg_unit(kk, geoid, elev, surface, mk3(1.27, 0.0, 1.9), 26269, 3503, 3503, true, eng, steer, 0.0,
-                     x[L::LDG + 4], x[L::LDG + 5], xd[4], xd[5], Fl, taul, 2, ol, WY ? &yf->xi[2] : nullptr, WY ? &yf->F_dmp[2] : nullptr);
+            double xd_a = 0.0, xd_b = 0.0, xd_c = 0.0, xd_d = 0.0, xd_e = 0.0, xd_f = 0.0;
+#pragma unroll 1
+            for (int leg = 0; leg < 3; leg++) {   // left main, right main, nose (c172.jl:466-500): geometry and rates by select
+                const bool nose = (leg == 2);
+                const d3 r_bs_b = mk3(nose ? 1.27 : -0.381, nose ? 0.0 : (leg == 0 ? -1.092 : 1.092), nose ? 1.9 : 1.902);
+                const double k_s = nose ? 26269.0 : 39404.0, k_d = nose ? 3503.0 : 9340.0;
+                const double brake = nose ? 0.0 : (leg == 0 ? br_l : br_r);
+                const double x0 = (leg == 0) ? x[L::LDG] : ((leg == 1) ? x[L::LDG + 2] : x[L::LDG + 4]);
+                const double x1 = (leg == 0) ? x[L::LDG + 1] : ((leg == 1) ? x[L::LDG + 3] : x[L::LDG + 5]);
+                double a0, a1, xi_o = 0.0, fd_o = 0.0;
+                ldg_unit(k, geoid, elev, surface, r_bs_b, k_s, k_d, k_d, nose, nose && eng, steer, brake, x0, x1, a0, a1, Fl, taul, leg, ol,
+                         WY ? &xi_o : nullptr, WY ? &fd_o : nullptr);
+                if (leg == 0) { xd_a = a0; xd_b = a1; } else if (leg == 1) { xd_c = a0; xd_d = a1; } else { xd_e = a0; xd_f = a1; }
+                if (WY) { yf->xi[leg] = xi_o; yf->F_dmp[leg] = fd_o; }
+            }
+            xd[0] = xd_a; xd[1] = xd_b; xd[2] = xd_c; xd[3] = xd_d; xd[4] = xd_e; xd[5] = xd_f;
             F = F + Fl; tau = tau + taul;
             out.wow = ol.wow; out.crash = ol.crash; if (ol.err) out.err = ol.err;
 #pragma unroll
