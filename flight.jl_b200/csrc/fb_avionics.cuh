@@ -14,6 +14,11 @@
 #pragma once
 #include "fb_physics.cuh"
 
+// The control and guidance laws are inlined into the integrator (one call site each): out of line they would take the
+// controller memory and the vehicle outputs through local memory (measured: +8 % on cfg 3). f_init!, which runs each
+// law several times, goes through the out-of-line wrappers below.
+#define FB_GDC_FN FB_DEV
+#define FB_CTL_FN FB_DEV
 #define FB_CTL_STATE_COUNT 80
 #define FB_CTL_TAP_ROW 48      // rows 48..63 of the column: output tap of the integrator (TAP_COUNT values, fb_physics.cuh)
 #define FB_CTL_GDC_ROW 64      // rows 64..75: outputs of the last guidance update (GDC_* below), written in place
@@ -183,7 +188,7 @@ FB_DEV void lqr_reset(LqrS& s, const Gain& g, double lo0, double lo1, double Dt)
 
 // ------------------------------------------------------------------------------------------ control laws
 // f_periodic!(ControlLawsLon) — c172x_ctl.jl:286-446
-__device__ __noinline__ void lon_periodic(CtlState& cs, const YFull& v, int wow, const MemberIn& u,
+FB_CTL_FN void lon_periodic(CtlState& cs, const YFull& v, int wow, const MemberIn& u,
                                           const FbDeviceTables& T, double Dt, int mode_req) {
     const double EAS = v.EAS, h_e = v.h_e, q = v.w_wb_b.y, r = v.w_wb_b.z, theta = v.theta, phi = v.phi;
     const double clm = -v.v_eb_n.z;
@@ -261,7 +266,7 @@ __device__ __noinline__ void lon_periodic(CtlState& cs, const YFull& v, int wow,
 FB_DEV double wrap_to_pi(double x) { return x + 2.0 * FB_PI * floor((FB_PI - x) / (2.0 * FB_PI)); }   // attitude.jl wrap_to_π
 
 // f_periodic!(ControlLawsLat) — c172x_ctl.jl:880-983
-__device__ __noinline__ void lat_periodic(CtlState& cs, const YFull& v, int wow, const MemberIn& u,
+FB_CTL_FN void lat_periodic(CtlState& cs, const YFull& v, int wow, const MemberIn& u,
                                           const FbDeviceTables& T, double Dt, int mode_req) {
     const double EAS = v.EAS, h_e = v.h_e, p = v.w_wb_b.x;
     const int mode_prev = cs.lat_mode;
@@ -304,7 +309,7 @@ __device__ __noinline__ void lat_periodic(CtlState& cs, const YFull& v, int wow,
 // f_periodic!(GuidanceLaws, ctl, vehicle): c172x_gdc.jl:297-329 -> SegmentGuidance :228-252 -> SegmentGuidanceData :113-148
 // (dchi_inf = pi/2, e_sf = 250 m, e_thr = 1000 m, :203-207). On a Cessna172Xv1 the mode request stays `direct` (the host
 // refuses guidance inputs there), which makes this a no-op. Cold code: runs once per control period, IEEE arithmetic.
-__device__ __noinline__ void gdc_periodic(const CtlState& cs, double lat, double lon, double h_e, int wow, const MemberIn& u) {
+FB_GDC_FN void gdc_periodic(const CtlState& cs, double lat, double lon, double h_e, int wow, const MemberIn& u) {
     const int mode = wow ? 0 : (int)u(FB_U_GDC_MODE_REQ);
     auto out = [&](int k, double v) { cs.gdc[(long long)k * cs.gdc_pitch] = v; };
     if (mode == 1) {
@@ -338,6 +343,13 @@ __device__ __noinline__ void gdc_periodic(const CtlState& cs, double lat, double
         if (vrt) { u.set(FB_U_LON_H_REF, h_s); u.set(FB_U_LON_MODE_REQ, (double)LON_EAS_ALT); }
     }
     out(GDC_MODE, (double)mode);
+}
+
+__device__ __noinline__ void lon_periodic_ool(CtlState& cs, const YFull& v, int wow, const MemberIn& u, const FbDeviceTables& T, double Dt, int mode_req) {
+    lon_periodic(cs, v, wow, u, T, Dt, mode_req);
+}
+__device__ __noinline__ void lat_periodic_ool(CtlState& cs, const YFull& v, int wow, const MemberIn& u, const FbDeviceTables& T, double Dt, int mode_req) {
+    lat_periodic(cs, v, wow, u, T, Dt, mode_req);
 }
 
 // assign!(vehicle, avionics): c172x_ctl.jl:449-458, 986-995 — the four fly-by-wire commands the control laws own
@@ -375,16 +387,16 @@ FB_DEV void avionics_init(const YFull& v, int wow, const MemberIn& u, CtlState& 
     u.set(FB_U_LON_THROTTLE_OFFSET, 0.0); u.set(FB_U_LON_ELEVATOR_OFFSET, 0.0);
     u.set(FB_U_LON_Q_REF, v.w_wb_b.y); u.set(FB_U_LON_THETA_REF, v.theta); u.set(FB_U_LON_EAS_REF, v.EAS);
     u.set(FB_U_LON_CLM_REF, -v.v_eb_n.z); u.set(FB_U_LON_H_REF, v.h_e);
-    lon_periodic(cs, v, wow, u, T, Dt, LON_SAS);
-    lon_periodic(cs, v, wow, u, T, Dt, LON_THR_EAS);
-    lon_periodic(cs, v, wow, u, T, Dt, LON_EAS_ALT);
-    lon_periodic(cs, v, wow, u, T, Dt, LON_DIRECT);
+    lon_periodic_ool(cs, v, wow, u, T, Dt, LON_SAS);
+    lon_periodic_ool(cs, v, wow, u, T, Dt, LON_THR_EAS);
+    lon_periodic_ool(cs, v, wow, u, T, Dt, LON_EAS_ALT);
+    lon_periodic_ool(cs, v, wow, u, T, Dt, LON_DIRECT);
     u.set(FB_U_LON_MODE_REQ, (double)LON_DIRECT);
     u.set(FB_U_LAT_AILERON_AXIS, clampd(v.act_pos[1], -1.0, 1.0)); u.set(FB_U_LAT_RUDDER_AXIS, clampd(v.act_pos[3], -1.0, 1.0));
     u.set(FB_U_LAT_AILERON_OFFSET, 0.0); u.set(FB_U_LAT_RUDDER_OFFSET, 0.0);
     u.set(FB_U_LAT_P_REF, v.w_wb_b.x); u.set(FB_U_LAT_PHI_REF, v.phi); u.set(FB_U_LAT_BETA_REF, v.beta); u.set(FB_U_LAT_CHI_REF, v.chi_gnd);
-    lat_periodic(cs, v, wow, u, T, Dt, LAT_SAS);
-    lat_periodic(cs, v, wow, u, T, Dt, LAT_PHI_BETA);
-    lat_periodic(cs, v, wow, u, T, Dt, LAT_DIRECT);
+    lat_periodic_ool(cs, v, wow, u, T, Dt, LAT_SAS);
+    lat_periodic_ool(cs, v, wow, u, T, Dt, LAT_PHI_BETA);
+    lat_periodic_ool(cs, v, wow, u, T, Dt, LAT_DIRECT);
     u.set(FB_U_LAT_MODE_REQ, (double)LAT_DIRECT);
 }
