@@ -52,6 +52,7 @@ struct fb_sim {
     cudaEvent_t ground_ev = nullptr;
     bool ground_ev_pending = false;
     bool air_mode = true;
+    bool force_complete = false;
     bool air_wide = false;           // airborne kernel shape: FB_STEP_BLOCK_WIDE threads (one-wave ensembles) or FB_STEP_BLOCK
 };
 
@@ -327,6 +328,10 @@ int32_t fb_create(const fb_config* cfg, fb_handle* out) {
         s->air_wide = (double)waves_w * 1.45 < (double)waves_n;
         s->step_block_air = s->air_wide ? Tw : Tn;
     }
+    // FLIGHTBATCH_KERNEL=complete pins the complete kernel (no airborne instantiation, no hand-over): a diagnostic switch used
+    // by the tests to check that the two launch paths produce the same trajectories
+    if (const char* k = getenv("FLIGHTBATCH_KERNEL")) s->force_complete = (strcmp(k, "complete") == 0);
+    if (s->force_complete) s->air_mode = false;
     CK(cudaMalloc(&s->d_resume, sizeof(int) * s->pitch));
     CK(cudaMalloc(&s->d_ground, sizeof(unsigned)));
     CK(cudaMallocHost(&s->h_ground, sizeof(unsigned)));
@@ -617,7 +622,7 @@ static int32_t advance(fb_sim* s, long long n) {
         // the host (never waits for the GPU): mostly airborne -> AIR kernel + hand-over pass, otherwise complete kernel.
         if (s->ground_ev_pending && cudaEventQuery(s->ground_ev) == cudaSuccess) {
             s->ground_ev_pending = false;
-            s->air_mode = (long long)*s->h_ground * 8 <= s->E.n;
+            s->air_mode = !s->force_complete && (long long)*s->h_ground * 8 <= s->E.n;
         }
         int launched = 0;
         CK(FB_DISPATCH(s, step)(s, s->n_steps, k, &launched));

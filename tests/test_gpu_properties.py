@@ -1,0 +1,72 @@
+"""GPU property tests at BASELINE.json's full cfg-2 size (65,536 members), where the oracle is too slow to follow:
+size-independent properties of the integrator."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(fb, n, i0, seconds, mixed=False):
+    import bench
+    p = bench.member_params(i0, n)
+    sim = fb.BatchSimulation(fb.SimpleWorld(fb.Cessna172Sv0(fb.WA())), n=n, dt=0.01, t_end=1e4, steps_per_launch=100)
+    if mixed:   # put every 16th member low over raised terrain so that it lands / crashes during the run
+        elev = np.zeros(n); low = np.arange(n) % 16 == 0
+        elev[low] = p["h_e"][low] - bench.geoid_height(p["lat"][low], p["lon"][low]) - np.where(np.arange(n)[low] % 32 == 0, 3.0, 5.0)
+        sim.set_input("trn_elevation", elev)
+    ok, _, _ = sim.init(fb.C172.TrimParameters(**p))
+    ele_f, ail_f = fb.U["FB_U_ELEVATOR"], fb.U["FB_U_AILERON"]
+    sim.schedule_inputs(*bench.doublet_events(n, sim.get_input(ele_f), sim.get_input(ail_f), ele_f, ail_f))
+    sim.step(seconds)
+    out = dict(x=sim.x, status=sim.status(), disc=sim.discrete(), wow=np.maximum.reduce([sim.get_output(k) for k in ("wow_left", "wow_right", "wow_nose")]))
+    sim.close()
+    return out
+
+
+def test_sharding_and_launch_shape_do_not_change_trajectories(fb):
+    """65,536 members in one handle (one wave of the 448-thread airborne shape) against the same members in two handles of
+    32,768 (384-thread shape): the per-member result must not depend on the ensemble it is computed in. Different template
+    instantiations may round differently (FMA contraction), so the bound is the parity tolerance, not bit equality."""
+    n = 65536
+    a = _run(fb, n, 0, 10.0)
+    b0, b1 = _run(fb, n // 2, 0, 10.0), _run(fb, n // 2, n // 2, 10.0)
+    xb = np.concatenate([b0["x"], b1["x"]], axis=1)
+    assert np.array_equal(a["status"], np.concatenate([b0["status"], b1["status"]]))
+    run = a["status"] == 0
+    err = np.abs(a["x"] - xb)[:, run] / np.maximum(np.abs(xb[:, run]), 1e-2)
+    print("sharding: max scaled difference", err.max(), "bit-identical members", int((err.max(axis=0) == 0).sum()), "of", int(run.sum()))
+    assert err.max() < 1e-9
+    # quaternion blocks stay normalised to the reference's renormalisation threshold (kinematics.jl:114-118)
+    q_wb, q_ew = a["x"][12:16, run], a["x"][16:20, run]
+    assert np.abs(np.sqrt((q_wb ** 2).sum(axis=0)) - 1).max() < 2e-8 and np.abs(np.sqrt((q_ew ** 2).sum(axis=0)) - 1).max() < 2e-8
+
+
+def test_handover_path_equals_complete_kernel(fb):
+    """A mixed ensemble (1/16 of the members 3 or 5 m above raised terrain: inside or just outside the 4 m height gate, they
+    touch down or crash within the run)
+    through the airborne kernel + hand-over, against the same ensemble through the complete kernel alone
+    (FLIGHTBATCH_KERNEL=complete in a child process): statuses, stall / engine states identical, states to parity tolerance."""
+    n = 8192
+    a = _run(fb, n, 0, 12.0, mixed=True)
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r); import flightbatch as fb; "
+            "from test_gpu_properties import _run; r = _run(fb, %d, 0, 12.0, mixed=True); "
+            "np.savez('/tmp/fb_complete.npz', x=r['x'], status=r['status'], stall=r['disc'][0], eng=r['disc'][1])") % (ROOT, os.path.join(ROOT, "tests"), n)
+    subprocess.check_call([sys.executable, "-c", code], env=dict(os.environ, FLIGHTBATCH_KERNEL="complete"))
+    b = np.load("/tmp/fb_complete.npz")
+    low = np.arange(n) % 16 == 0
+    touched = (a["wow"][low] > 0).sum() + np.isin(a["status"][low], (2, 3)).sum()
+    assert touched > 20, touched                      # the hand-over path really ran: members on their wheels or crashed
+    assert np.array_equal(a["status"], b["status"])
+    assert np.array_equal(a["disc"][0], b["stall"]) and np.array_equal(a["disc"][1], b["eng"])
+    run = a["status"] == 0
+    err = np.abs(a["x"] - b["x"]) / np.maximum(np.abs(b["x"]), 1.0)
+    air = run & ~low
+    print("hand-over: max diff airborne", err[:, air].max(), "near-ground", err[:, run & low].max() if (run & low).any() else None,
+          "statuses", np.bincount(a["status"], minlength=7).tolist())
+    assert err[:, air].max() < 1e-9
+    assert err[:, run & low].max() < 1e-5      # ground-contact conditioning
