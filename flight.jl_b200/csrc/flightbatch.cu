@@ -620,9 +620,11 @@ static int32_t advance(fb_sim* s, long long n) {
         int k = (int)std::min<long long>(n, s->cfg.steps_per_launch);
         // Pick the launch shape from the most recent count of members near the terrain that has already arrived on
         // the host (never waits for the GPU): mostly airborne -> AIR kernel + hand-over pass, otherwise complete kernel.
-        if (s->ground_ev_pending && cudaEventQuery(s->ground_ev) == cudaSuccess) {
-            s->ground_ev_pending = false;
-            s->air_mode = !s->force_complete && (long long)*s->h_ground * 8 <= s->E.n;
+        if (s->ground_ev_pending) {
+            if (cudaEventQuery(s->ground_ev) == cudaSuccess) {
+                s->ground_ev_pending = false;
+                s->air_mode = !s->force_complete && (long long)*s->h_ground * 8 <= s->E.n;
+            } else (void)cudaGetLastError();   // cudaErrorNotReady is not an error: keep it out of the next launch check
         }
         int launched = 0;
         CK(FB_DISPATCH(s, step)(s, s->n_steps, k, &launched));
