@@ -345,10 +345,10 @@ FB_GDC_FN void gdc_periodic(const CtlState& cs, double lat, double lon, double h
     out(GDC_MODE, (double)mode);
 }
 
-__device__ __noinline__ void lon_periodic_ool(CtlState& cs, const YFull& v, int wow, const MemberIn& u, const FbDeviceTables& T, double Dt, int mode_req) {
+static __device__ __noinline__ void lon_periodic_ool(CtlState& cs, const YFull& v, int wow, const MemberIn& u, const FbDeviceTables& T, double Dt, int mode_req) {
     lon_periodic(cs, v, wow, u, T, Dt, mode_req);
 }
-__device__ __noinline__ void lat_periodic_ool(CtlState& cs, const YFull& v, int wow, const MemberIn& u, const FbDeviceTables& T, double Dt, int mode_req) {
+static __device__ __noinline__ void lat_periodic_ool(CtlState& cs, const YFull& v, int wow, const MemberIn& u, const FbDeviceTables& T, double Dt, int mode_req) {
     lat_periodic(cs, v, wow, u, T, Dt, mode_req);
 }
 

@@ -49,7 +49,7 @@ FB_DEV double fb_sqrt(double a) {   // a > 0
 // atan2 for finite, not-both-zero arguments. One division: with t = min/max in [0,1] and c the nearest
 // multiple of 1/8, atan(t) = atan(c) + atan(z), z = (min - c max) / (max + c min), |z| <= 1/16, and the odd
 // series to z^13 leaves a truncation error below 1e-18. Absolute error ~1 ulp of the result's quadrant offset.
-__constant__ double c_atan_tab[9] = {0.0, 0.12435499454676144, 0.24497866312686414, 0.35877067027057225, 0.46364760900080609,
+static __constant__ double c_atan_tab[9] = {0.0, 0.12435499454676144, 0.24497866312686414, 0.35877067027057225, 0.46364760900080609,
                                      0.55859931534356244, 0.64350110879328437, 0.71882999962162453, 0.78539816339744831};
 FB_DEV double fb_atan2(double y, double x) {   // branch-free; atan2(+-0, +-0) gives +-0 like an isolated zero vector should
     double ax = fabs(x), ay = fabs(y);

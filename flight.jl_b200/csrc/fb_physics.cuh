@@ -25,6 +25,13 @@
 // Derivatives are handed to a `Sink` as they are produced so that the integrator can fold each one into
 // its Runge-Kutta accumulators (kept in shared memory) instead of holding a derivative vector in registers.
 #pragma once
+// FB_LDG_INLINE: 1 in the translation unit of the complete integrator kernels (flightbatch_complete.cu), where the strut
+// code is inlined once inside the leg loop (cfg 4: +30 %); 0 elsewhere, where the legs call the out-of-line copy. The
+// split exists because the mere presence of the inlined copy in a module changes ptxas' register allocation of the
+// airborne kernels compiled beside it (measured: 52.6 -> 56.4 ms on the 1M-member cfg-2 launch).
+#ifndef FB_LDG_INLINE
+#define FB_LDG_INLINE 0
+#endif
 #include "fb_math.cuh"
 #include "fb_tables.h"
 #include "../../include/flightbatch.h"
@@ -86,7 +93,7 @@ struct YFull {
     double act_pos[7], act_cmd[7];
 };
 
-__device__ __noinline__ double pow_slow(double a, double b) { return pow(a, b); }
+static __device__ __noinline__ double pow_slow(double a, double b) { return pow(a, b); }
 // pseudo input fields: combinations the RHS uses as one value (so that an input cache can hold them ready-made)
 enum { FB_UX_AE = 100,   // -clamp(elevator_offset + elevator)   C172S MechanicalActuation, c172s.jl:92-120
        FB_UX_AA,         //  clamp(aileron_offset + aileron)
@@ -264,7 +271,7 @@ FB_DEV double gravity(double n3, double h) {  // Somigliana + 2nd-order altitude
 // --------------------------------------------------------------------------------------- atmosphere
 struct Air { d3 v_wb_b; double T, p, rho, ia, iRT, TAS, iTAS, q, tr; };  // tr = T_ISA(p) / T_std (piston.jl:38)
 
-__device__ __noinline__ void isa_upper(double hg, double T_sl, double p_sl, double& T, double& p, int& err) {
+static __device__ __noinline__ void isa_upper(double hg, double T_sl, double p_sl, double& T, double& p, int& err) {
     const double beta[7] = {-6.5e-3, 0, 1e-3, 2.8e-3, 0, -2.8e-3, -2e-3};
     const double hc[7] = {11000, 20000, 32000, 47000, 51000, 71000, 84852};
     double hb = 0, Tb = T_sl, pb = p_sl;
@@ -405,6 +412,17 @@ FB_DEV void ldg_unit(const Kin& k, const float* __restrict__ geoid, double elev,
         F = F + F_b;
         tau = tau + cross(r_bc_b, F_b);
     }
+}
+
+// Out-of-line copy for the output-producing RHS (log samples, test hooks): that function is called from inside the
+// integrator kernels, and keeping it small keeps its register demand from leaking into their allocation.
+static __device__ __noinline__ void ldg_unit_ool(const Kin& k, const float* __restrict__ geoid, double elev, int surface,
+                                          d3 r_bs_b, double k_s, double k_d_ext, double k_d_cmp,
+                                          bool has_steering, bool steering_engaged, double steer_input, double brake,
+                                          double x0, double x1, double& xd0, double& xd1, d3& F, d3& tau, int leg, RhsOut& out,
+                                          double* xi_out, double* fdmp_out) {
+    ldg_unit(k, geoid, elev, surface, r_bs_b, k_s, k_d_ext, k_d_cmp, has_steering, steering_engaged, steer_input, brake, x0, x1, xd0, xd1,
+             F, tau, leg, out, xi_out, fdmp_out);
 }
 
 // 2 x 9 table on uniform ("scaled") axes with Line extrapolation (piston.jl:84-104)
@@ -691,22 +709,37 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
             bool eng = u(FB_U_STEERING_ENGAGED) != 0.0;
             d3 Fl = mk3(0, 0, 0), taul = mk3(0, 0, 0); RhsOut ol; ol.wow = 0; ol.crash = 0; ol.err = 0; ol.alpha = 0.0; ol.gnd = 1;
             double xd[6];
-            double xd_a = 0.0, xd_b = 0.0, xd_c = 0.0, xd_d = 0.0, xd_e = 0.0, xd_f = 0.0;
+            if (WY) {
+                // output-producing RHS (log samples, test hooks; an out-of-line function called from inside the integrator
+                // kernels): three out-of-line strut evaluations on a copy of the kinematic data. Kept in exactly this shape:
+                // the register allocation of the calling kernels depends on it (ptxas allocates across the call).
+                Kin kk = k;
+                ldg_unit_ool(kk, geoid, elev, surface, mk3(-0.381, -1.092, 1.902), 39404, 9340, 9340, false, false, 0.0, br_l,
+                             x[L::LDG], x[L::LDG + 1], xd[0], xd[1], Fl, taul, 0, ol, &yf->xi[0], &yf->F_dmp[0]);
+                ldg_unit_ool(kk, geoid, elev, surface, mk3(-0.381, 1.092, 1.902), 39404, 9340, 9340, false, false, 0.0, br_r,
+                             x[L::LDG + 2], x[L::LDG + 3], xd[2], xd[3], Fl, taul, 1, ol, &yf->xi[1], &yf->F_dmp[1]);
+                ldg_unit_ool(kk, geoid, elev, surface, mk3(1.27, 0.0, 1.9), 26269, 3503, 3503, true, eng, steer, 0.0,
+                             x[L::LDG + 4], x[L::LDG + 5], xd[4], xd[5], Fl, taul, 2, ol, &yf->xi[2], &yf->F_dmp[2]);
+            } else {
+                double xd_a = 0.0, xd_b = 0.0, xd_c = 0.0, xd_d = 0.0, xd_e = 0.0, xd_f = 0.0;
 #pragma unroll 1
-            for (int leg = 0; leg < 3; leg++) {   // left main, right main, nose (c172.jl:466-500): geometry and rates by select
-                const bool nose = (leg == 2);
-                const d3 r_bs_b = mk3(nose ? 1.27 : -0.381, nose ? 0.0 : (leg == 0 ? -1.092 : 1.092), nose ? 1.9 : 1.902);
-                const double k_s = nose ? 26269.0 : 39404.0, k_d = nose ? 3503.0 : 9340.0;
-                const double brake = nose ? 0.0 : (leg == 0 ? br_l : br_r);
-                const double x0 = (leg == 0) ? x[L::LDG] : ((leg == 1) ? x[L::LDG + 2] : x[L::LDG + 4]);
-                const double x1 = (leg == 0) ? x[L::LDG + 1] : ((leg == 1) ? x[L::LDG + 3] : x[L::LDG + 5]);
-                double a0, a1, xi_o = 0.0, fd_o = 0.0;
-                ldg_unit(k, geoid, elev, surface, r_bs_b, k_s, k_d, k_d, nose, nose && eng, steer, brake, x0, x1, a0, a1, Fl, taul, leg, ol,
-                         WY ? &xi_o : nullptr, WY ? &fd_o : nullptr);
-                if (leg == 0) { xd_a = a0; xd_b = a1; } else if (leg == 1) { xd_c = a0; xd_d = a1; } else { xd_e = a0; xd_f = a1; }
-                if (WY) { yf->xi[leg] = xi_o; yf->F_dmp[leg] = fd_o; }
+                for (int leg = 0; leg < 3; leg++) {   // left main, right main, nose (c172.jl:466-500): geometry and rates by select
+                    const bool nose = (leg == 2);
+                    const d3 r_bs_b = mk3(nose ? 1.27 : -0.381, nose ? 0.0 : (leg == 0 ? -1.092 : 1.092), nose ? 1.9 : 1.902);
+                    const double k_s = nose ? 26269.0 : 39404.0, k_d = nose ? 3503.0 : 9340.0;
+                    const double brake = nose ? 0.0 : (leg == 0 ? br_l : br_r);
+                    const double x0 = (leg == 0) ? x[L::LDG] : ((leg == 1) ? x[L::LDG + 2] : x[L::LDG + 4]);
+                    const double x1 = (leg == 0) ? x[L::LDG + 1] : ((leg == 1) ? x[L::LDG + 3] : x[L::LDG + 5]);
+                    double a0, a1;
+#if !FB_LDG_INLINE
+                    ldg_unit_ool(k, geoid, elev, surface, r_bs_b, k_s, k_d, k_d, nose, nose && eng, steer, brake, x0, x1, a0, a1, Fl, taul, leg, ol, nullptr, nullptr);
+#else
+                    ldg_unit(k, geoid, elev, surface, r_bs_b, k_s, k_d, k_d, nose, nose && eng, steer, brake, x0, x1, a0, a1, Fl, taul, leg, ol, nullptr, nullptr);
+#endif
+                    if (leg == 0) { xd_a = a0; xd_b = a1; } else if (leg == 1) { xd_c = a0; xd_d = a1; } else { xd_e = a0; xd_f = a1; }
+                }
+                xd[0] = xd_a; xd[1] = xd_b; xd[2] = xd_c; xd[3] = xd_d; xd[4] = xd_e; xd[5] = xd_f;
             }
-            xd[0] = xd_a; xd[1] = xd_b; xd[2] = xd_c; xd[3] = xd_d; xd[4] = xd_e; xd[5] = xd_f;
             F = F + Fl; tau = tau + taul;
             out.wow = ol.wow; out.crash = ol.crash; if (ol.err) out.err = ol.err;
 #pragma unroll

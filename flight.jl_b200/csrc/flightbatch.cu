@@ -11,6 +11,7 @@
 #include <numeric>
 #include "fb_init.cuh"
 #include "fb_lss.cuh"
+#include "fb_complete.h"
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -75,22 +76,22 @@ template <int VAR, int KIN> struct Ops {
             else
                 step_kernel<VAR, KIN, true><<<grid_a, Ta, StepShape<VAR, KIN, true>::SMEM, s->stream>>>(
                     s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_resume, 0, s->d_ground);
-            step_kernel<VAR, KIN, false><<<grid, T, StepShape<VAR, KIN, false>::SMEM, s->stream>>>(
-                s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_resume, 1, s->d_ground);
+            { CompleteLaunch a{grid, T, s->stream, s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_resume, 1, s->d_ground};
+              e = fb_complete_launch(VAR, s->cfg.kinematics, a); if (e != cudaSuccess) return e; }
             *launched = 2;
         } else {
-            step_kernel<VAR, KIN, false><<<grid, T, StepShape<VAR, KIN, false>::SMEM, s->stream>>>(
-                s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, nullptr, 0, s->d_ground);
+            CompleteLaunch a{grid, T, s->stream, s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, nullptr, 0, s->d_ground};
+            e = fb_complete_launch(VAR, s->cfg.kinematics, a); if (e != cudaSuccess) return e;
             *launched = 1;
         }
         return cudaGetLastError();
     }
     // shape 0: complete kernel, 1: airborne, 2: airborne wide
     static int step_tmax(int shape) {
-        return shape == 0 ? StepShape<VAR, KIN, false>::T : (shape == 1 ? StepShape<VAR, KIN, true>::T : StepShape<VAR, KIN, true, FB_STEP_BLOCK_WIDE>::T);
+        return shape == 0 ? fb_complete_tmax(VAR, KIN) : (shape == 1 ? StepShape<VAR, KIN, true>::T : StepShape<VAR, KIN, true, FB_STEP_BLOCK_WIDE>::T);
     }
     static cudaError_t prepare(fb_sim* s) {
-        cudaError_t e = cudaFuncSetAttribute(step_kernel<VAR, KIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StepShape<VAR, KIN, false>::SMEM);
+        cudaError_t e = fb_complete_prepare(VAR, KIN);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(step_kernel<VAR, KIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StepShape<VAR, KIN, true>::SMEM);
         if (e != cudaSuccess) return e;
