@@ -107,21 +107,36 @@ FB_DEV double pick_output(const YFull& y, int stall, int eng, const CtlState& cs
 // One bilinear cell of the (EAS, h_e) design grid, Flat outside (control.jl:965); value k of a schedule with P
 // values per design point is read on demand.
 struct GainCell {
-    int o;          // (i * 4 + j): design-point index of the cell's low corner
+    int o;          // (i * 3 + j): index of the bilinear cell (device layout of fb_load_tables: [cell][k][4 corners])
     double u, w;    // weights along EAS and h
     FB_DEV void locate(double EAS, double h) {
         double fe = (clampd(EAS, 25.0, 55.0) - 25.0) * (1.0 / 5.0), fh = (clampd(h, 50.0, 3050.0) - 50.0) * (1.0 / 1000.0);
         int i = min((int)fe, 5), j = min((int)fh, 2);
-        u = fe - (double)i; w = fh - (double)j; o = i * 4 + j;
+        u = fe - (double)i; w = fh - (double)j; o = i * 3 + j;
     }
 };
+// Values of one schedule at the member's cell. The table lives in L2 (uncoalesced: every member has its own cell), so
+// what matters is how many reads are in flight at once: batch<N> issues N 256-bit reads back to back and interpolates
+// afterwards — one L2 round trip per batch instead of one per value.
 struct Gain {
-    const double* p; int P; double u, w;
-    FB_DEV Gain(const double* tab, int P_, const GainCell& c) : p(tab + (long long)c.o * P_), P(P_), u(c.u), w(c.w) {}
-    FB_DEV double operator()(int k) const {
-        double f00 = __ldg(p + k), f01 = __ldg(p + P + k), f10 = __ldg(p + 4 * P + k), f11 = __ldg(p + 5 * P + k);
+    const double* p; double u, w;
+    FB_DEV Gain(const double* tab, int P, const GainCell& c) : p(tab + (long long)c.o * P * 4), u(c.u), w(c.w) {}
+    FB_DEV double mix(double f00, double f01, double f10, double f11) const {
         return (1.0 - u) * ((1.0 - w) * f00 + w * f01) + u * ((1.0 - w) * f10 + w * f11);
     }
+    template <int N>
+    FB_DEV void batch(int k0, double* out) const {
+        double r[N][4];   // the four corners of value k: one 32-byte sector, one LDG.256
+#pragma unroll
+        for (int n = 0; n < N; n++)
+            asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r[n][0]), "=d"(r[n][1]), "=d"(r[n][2]), "=d"(r[n][3]) : "l"(p + 4 * (k0 + n)));
+#pragma unroll
+        for (int n = 0; n < N; n++) out[n] = mix(r[n][0], r[n][1], r[n][2], r[n][3]);
+    }
+};
+struct PidGains {      // (k_p, k_i, k_d, tau_f) of a scheduled PID
+    double k_p, k_i, k_d, tau_f;
+    FB_DEV PidGains(const double* tab, const GainCell& c) { double g[4]; Gain(tab, 4, c).batch<4>(0, g); k_p = g[0]; k_i = g[1]; k_d = g[2]; tau_f = g[3]; }
 };
 
 // ------------------------------------------------------------------------------------------ compensators
@@ -152,21 +167,25 @@ FB_DEV void int_reset(IntS& s) { s.x0 = 0.0; s.sat = 0; }
 template <int NX>
 FB_DEV void lqr_update(LqrS& s, const Gain& g, const double* x, double z0, double z1, double zr0, double zr1,
                        double lo0, double lo1, double Dt, double& out0, double& out1) {
-    double dx[NX];
+    double dx[NX], t[NX], c[8], uz[4];
+    g.batch<NX>(2 * NX + 8, t);            // x_trim
 #pragma unroll
-    for (int j = 0; j < NX; j++) dx[j] = x[j] - g(2 * NX + 8 + j);
-    const double zt0 = g(3 * NX + 10), zt1 = g(3 * NX + 11);
+    for (int j = 0; j < NX; j++) dx[j] = x[j] - t[j];
+    g.batch<8>(2 * NX, c);                 // K_fwd (2x2), K_int (2x2)
+    g.batch<4>(3 * NX + 8, uz);            // u_trim, z_trim
+    const double zt0 = uz[2], zt1 = uz[3];
     double out[2];
 #pragma unroll
     for (int i = 0; i < 2; i++) {
-        double int_in = g(2 * NX + 4 + 2 * i) * (zr0 - z0) + g(2 * NX + 5 + 2 * i) * (zr1 - z1);
+        double int_in = c[4 + 2 * i] * (zr0 - z0) + c[5 + 2 * i] * (zr1 - z1);
         bool halted = isign(int_in * (double)s.sat[i]) > 0;
         double int_out = s.io[i] + Dt * int_in * (halted ? 0.0 : 1.0);
-        double fwd = g(2 * NX + 2 * i) * (zr0 - zt0) + g(2 * NX + 1 + 2 * i) * (zr1 - zt1);
+        double fwd = c[2 * i] * (zr0 - zt0) + c[1 + 2 * i] * (zr1 - zt1);
+        g.batch<NX>(i * NX, t);            // row i of K_fbk
         double fbk = 0.0;
 #pragma unroll
-        for (int j = 0; j < NX; j++) fbk = fbk + g(i * NX + j) * dx[j];
-        double out_free = g(3 * NX + 8 + i) + int_out + fwd - fbk;
+        for (int j = 0; j < NX; j++) fbk = fbk + t[j] * dx[j];
+        double out_free = uz[i] + int_out + fwd - fbk;
         const double lo = i ? lo1 : lo0;
         s.sat[i] = (out_free >= 1.0) - (out_free <= lo);
         out[i] = clampd(out_free, lo, 1.0);
@@ -220,28 +239,25 @@ FB_CTL_FN void lon_periodic(CtlState& cs, const YFull& v, int wow, const MemberI
     if (te2te_en) {
         const int sat_thr = cs.te2te.sat[0], sat_ele = cs.te2te.sat[1];
         if (v2t_en) {
-            Gain g(T.gains[GS_V2T], 4, c);
-            const double k_i = g(1);
-            if (mode != mode_prev) { pid_reset(cs.v2t_pid); if (k_i != 0.0) cs.v2t_pid.xi = cs.thr_cmd; }
-            throttle_ref = pid_update(cs.v2t_pid, g(0), k_i, g(2), g(3), -INFINITY, INFINITY, EAS_ref - EAS, sat_thr, Dt);
+            const PidGains g(T.gains[GS_V2T], c);
+            if (mode != mode_prev) { pid_reset(cs.v2t_pid); if (g.k_i != 0.0) cs.v2t_pid.xi = cs.thr_cmd; }
+            throttle_ref = pid_update(cs.v2t_pid, g.k_p, g.k_i, g.k_d, g.tau_f, -INFINITY, INFINITY, EAS_ref - EAS, sat_thr, Dt);
         }
         if (q2e_en) {
-            Gain g(T.gains[GS_Q2E], 4, c);
-            const double k_i = g(1);
-            if (mode != mode_prev) { int_reset(cs.q2e_int); pid_reset(cs.q2e_pid); if (k_i != 0.0) cs.q2e_pid.xi = cs.te2te_zref1; }
+            const PidGains g(T.gains[GS_Q2E], c);
+            if (mode != mode_prev) { int_reset(cs.q2e_int); pid_reset(cs.q2e_pid); if (g.k_i != 0.0) cs.q2e_pid.xi = cs.te2te_zref1; }
             if (t2q_en) {
                 if (mode == LON_EAS_CLM) {
-                    Gain gc(T.gains[GS_C2THETA], 4, c);
-                    const double k_ic = gc(1);
-                    if (mode != mode_prev) { pid_reset(cs.c2t_pid); if (k_ic != 0.0) cs.c2t_pid.xi = theta; }
-                    theta_ref = pid_update(cs.c2t_pid, gc(0), k_ic, gc(2), gc(3), -INFINITY, INFINITY, u(FB_U_LON_CLM_REF) - clm, sat_ele, Dt);
+                    const PidGains gc(T.gains[GS_C2THETA], c);
+                    if (mode != mode_prev) { pid_reset(cs.c2t_pid); if (gc.k_i != 0.0) cs.c2t_pid.xi = theta; }
+                    theta_ref = pid_update(cs.c2t_pid, gc.k_p, gc.k_i, gc.k_d, gc.tau_f, -INFINITY, INFINITY, u(FB_U_LON_CLM_REF) - clm, sat_ele, Dt);
                 }
                 double theta_dot_ref = 1.0 * (theta_ref - theta);
                 double phi_bnd = clampd(phi, -FB_PI / 3, FB_PI / 3);
                 q_ref = 1.0 / cos(phi_bnd) * theta_dot_ref + r * tan(phi_bnd);
             }
             double io = int_update(cs.q2e_int, q_ref - q, sat_ele, Dt);
-            elevator_ref = pid_update(cs.q2e_pid, g(0), k_i, g(2), g(3), -INFINITY, INFINITY, io, sat_ele, Dt);
+            elevator_ref = pid_update(cs.q2e_pid, g.k_p, g.k_i, g.k_d, g.tau_f, -INFINITY, INFINITY, io, sat_ele, Dt);
         }
         Gain g(T.gains[GS_TE2TE], 36, c);
         cs.te2te_zref1 = elevator_ref;
@@ -284,16 +300,14 @@ FB_CTL_FN void lat_periodic(CtlState& cs, const YFull& v, int wow, const MemberI
     if (mode == LAT_P_BETA || mode == LAT_PHI_BETA || mode == LAT_CHI_BETA) {
         const int sat_ail = cs.pb2ar.sat[0];
         if (mode == LAT_P_BETA) {
-            Gain g(T.gains[GS_P2PHI], 4, c);
-            const double k_i = g(1);
-            if (mode != mode_prev) { int_reset(cs.p2phi_int); pid_reset(cs.p2phi_pid); if (k_i != 0.0) cs.p2phi_pid.xi = cs.pb2ar_zref0; }
+            const PidGains g(T.gains[GS_P2PHI], c);
+            if (mode != mode_prev) { int_reset(cs.p2phi_int); pid_reset(cs.p2phi_pid); if (g.k_i != 0.0) cs.p2phi_pid.xi = cs.pb2ar_zref0; }
             double io = int_update(cs.p2phi_int, u(FB_U_LAT_P_REF) - p, sat_ail, Dt);
-            phi_ref = pid_update(cs.p2phi_pid, g(0), k_i, g(2), g(3), -INFINITY, INFINITY, io, sat_ail, Dt);
+            phi_ref = pid_update(cs.p2phi_pid, g.k_p, g.k_i, g.k_d, g.tau_f, -INFINITY, INFINITY, io, sat_ail, Dt);
         } else if (mode == LAT_CHI_BETA) {
-            Gain g(T.gains[GS_CHI2PHI], 4, c);
-            const double k_i = g(1);
-            if (mode != mode_prev) { pid_reset(cs.chi2phi_pid); if (k_i != 0.0) cs.chi2phi_pid.xi = cs.pb2ar_zref0; }
-            phi_ref = pid_update(cs.chi2phi_pid, g(0), k_i, g(2), g(3), -FB_PI / 4, FB_PI / 4, wrap_to_pi(u(FB_U_LAT_CHI_REF) - v.chi_gnd), sat_ail, Dt);
+            const PidGains g(T.gains[GS_CHI2PHI], c);
+            if (mode != mode_prev) { pid_reset(cs.chi2phi_pid); if (g.k_i != 0.0) cs.chi2phi_pid.xi = cs.pb2ar_zref0; }
+            phi_ref = pid_update(cs.chi2phi_pid, g.k_p, g.k_i, g.k_d, g.tau_f, -FB_PI / 4, FB_PI / 4, wrap_to_pi(u(FB_U_LAT_CHI_REF) - v.chi_gnd), sat_ail, Dt);
         }
         Gain g(T.gains[GS_PHIBETA2AR], 36, c);
         if (mode != mode_prev) lqr_reset<8>(cs.pb2ar, g, -1.0, -1.0, Dt);

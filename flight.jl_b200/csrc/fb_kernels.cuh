@@ -88,24 +88,37 @@ __host__ __device__ inline double saturate_input(int f, double v) {   // Ranged{
 // with per-thread coefficients (cb, cx) so that one code path serves all four stages. The step-start column is
 // never written by a stage, so an evaluation that has to be abandoned half-way leaves the step-start state intact;
 // the combine pass runs only after a complete, error-free stage-3 evaluation.
-template <int T>        // T: column stride in doubles (compile-time -> immediate shared-memory offsets)
+//
+// Actuator states (C172X: rows ACT .. ACT+NACT-1) get neither a stage register nor an accumulator column. Each is a
+// first-order lag x' = (cmd - x) / tau (c172x.jl:39-52) that nothing feeds back into, with cmd frozen over the step, so
+// its Runge-Kutta stage states and step result are closed-form in the step-start value: with e = x - cmd, z = dt / tau,
+//   stage 0: e   1: e (1 - z/2)   2: e (1 - z/2 + z^2/4)   3: e (1 - z + z^2/2 - z^3/4)
+//   x* = cmd + e (1 - z + z^2/2 - z^3/6 + z^4/24)
+// which is what the tableau produces on that equation (agreement to rounding). The stage factor is the per-thread `pa`.
+template <int T, int ACT = 0, int NACT = 0>   // T: column stride in doubles (compile-time -> immediate shared-memory offsets)
 struct RkSink {
-    double* xs;          // stage state, registers
+    double* xs;          // stage state, registers (actuator entries unused)
     double* sx;          // shared: step-start state column of this thread  (stride T doubles)
-    double* sacc;        // shared: accumulator column of this thread
-    double cb, cx;
+    double* sacc;        // shared: accumulator column of this thread (actuator rows squeezed out)
+    double cb, cx, pa;
     int stage;           // 0..3; 4 = stage 0 of the next step with this step's callbacks still pending
+    __host__ __device__ static constexpr int acol(int c) { return c >= ACT + NACT ? c - NACT : c; }
     FB_DEV void put(int c, double k) {
         double a = 0.0;
-        if (stage & 3) a = sacc[c * T];          // stage 0: acc = k, whatever the column holds
+        if (stage & 3) a = sacc[acol(c) * T];    // stage 0: acc = k, whatever the column holds
         double xv = sx[c * T];
-        sacc[c * T] = fma(cb, k, a);
+        sacc[acol(c) * T] = fma(cb, k, a);
         xs[c] = fma(cx, k, xv);
     }
-    template <int NX>
-    FB_DEV void combine(double h6) {             // x* = x + dt/6 (k1 + 2 k2 + 2 k3 + k4); xs = x*
+    FB_DEV double act(int, int c, const double*, double cmd) const { return fma(pa, sx[c * T] - cmd, cmd); }
+    FB_DEV void put_act(int, double, double) {}
+    template <int NX, class Cmd>
+    FB_DEV void combine(double h6, double act_r, const Cmd& cmd) {   // x* = x + dt/6 (k1 + 2 k2 + 2 k3 + k4); xs = x*
 #pragma unroll
-        for (int c = 0; c < NX; c++) { double xn = fma(h6, sacc[c * T], sx[c * T]); sx[c * T] = xn; xs[c] = xn; }
+        for (int c = 0; c < NX; c++) {
+            if (c >= ACT && c < ACT + NACT) { const double u = cmd(c - ACT); sx[c * T] = fma(act_r, sx[c * T] - u, u); }
+            else { double xn = fma(h6, sacc[acol(c) * T], sx[c * T]); sx[c * T] = xn; xs[c] = xn; }
+        }
     }
 };
 template <int T>
@@ -137,14 +150,16 @@ template <int VAR, int KIN, bool AIR, int CAP = FB_STEP_BLOCK>
 struct StepShape {
     static constexpr int NX = Lay<VAR, KIN, AIR>::NX;
     static constexpr int BUDGET = 232448 - FB_TB_BYTES - 1024;                                 // 227 KB per CTA
-    static constexpr int FIT = (int)(BUDGET / (sizeof(double) * 2 * NX)) / 32 * 32;
+    static constexpr int NCOL = 2 * NX - Lay<VAR, KIN, AIR>::NACT;                              // state columns + accumulator columns (none for actuators)
+    static constexpr int FIT = (int)(BUDGET / (sizeof(double) * NCOL)) / 32 * 32;
     static constexpr int T = FIT < CAP ? FIT : CAP;
-    static constexpr int SPARE = (int)(BUDGET / (sizeof(double) * T)) - 2 * NX;                // columns left for the input cache
+    static constexpr int SPARE = (int)(BUDGET / (sizeof(double) * T)) - NCOL;                  // columns left for the input cache
 #ifndef FB_NSLOT_MAX
 #define FB_NSLOT_MAX 16
 #endif
-    static constexpr int NSLOT = SPARE < FB_NSLOT_MAX ? SPARE : FB_NSLOT_MAX;
-    static constexpr size_t SMEM = FB_TB_BYTES + sizeof(double) * (2 * NX + NSLOT) * T;
+    static constexpr int NSLOT_MAX = (VAR == FB_C172S) ? FB_NSLOT_MAX : FB_NSLOT_MAX + 3;   // C172X also caches the wind
+    static constexpr int NSLOT = SPARE < NSLOT_MAX ? SPARE : NSLOT_MAX;
+    static constexpr size_t SMEM = FB_TB_BYTES + sizeof(double) * (NCOL + NSLOT) * T;
 };
 #define FB_RESUME_PENDING (1 << 30)
 template <int VAR, int KIN, bool AIR, int CAP = FB_STEP_BLOCK>
@@ -177,7 +192,7 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
     MemberIn ug; ug.u = E.u + i; ug.pitch = E.pitch;
     double* sx = smem + FB_TB_BYTES / 8 + threadIdx.x;
     double* sacc = sx + NX * T;
-    CachedIn<VAR, T, StepShape<VAR, KIN, AIR, CAP>::NSLOT> u; u.g = ug; u.sc = sx + 2 * NX * T;
+    CachedIn<VAR, T, StepShape<VAR, KIN, AIR, CAP>::NSLOT> u; u.g = ug; u.sc = sx + StepShape<VAR, KIN, AIR, CAP>::NCOL * T;
     double xs[NX];
 #pragma unroll
     for (int c = 0; c < NX; c++) { double v = E.x[(long long)L::row(c) * E.pitch + i]; xs[c] = v; sx[c * T] = v; }
@@ -206,7 +221,11 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
     int done = 0, n_reeval = 0;
     int gnd_seen = 0, handover = -1;
     const double h2 = 0.5 * dt, h6 = dt * (1.0 / 6.0);
-    RkSink<T> sink; sink.xs = xs; sink.sx = sx; sink.sacc = sacc;
+    RkSink<T, L::ACT, L::NACT> sink; sink.xs = xs; sink.sx = sx; sink.sacc = sacc;
+    // stage factors and step factor of the closed-form actuator propagation (RkSink)
+    const double az = dt * (1.0 / 0.05);
+    const double ap1 = 1.0 - 0.5 * az, ap2 = 1.0 - 0.5 * az * ap1, ap3 = 1.0 - az * ap2;
+    const double act_r = 1.0 - az * (1.0 / 6.0) * (1.0 + 2.0 * ap1 + 2.0 * ap2 + ap3);
     sink.stage = pending ? 4 : 0;
     SmemState<T> xstate(sink.sx);
     if (n_steps > 0) for (;;) {
@@ -214,6 +233,7 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
         const int st = sink.stage;
         sink.cb = (st == 1 || st == 2) ? 2.0 : 1.0;
         sink.cx = (st == 2) ? dt : h2;
+        sink.pa = (st == 1) ? ap1 : ((st == 2) ? ap2 : ((st == 3) ? ap3 : 1.0));
         RhsOut y;
         if (VAR >= FB_C172X1) {
             ColumnTap tap; tap.p = E.ctl + (long long)FB_CTL_TAP_ROW * E.pitch + i; tap.pitch = E.pitch; tap.on = (st == 4);
@@ -227,7 +247,7 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
             } else status = y.err;
             break;
         }
-        if (sink.stage == 3) { sink.template combine<NX>(h6); sink.stage = 4; continue; }   // xs == x == x*: next evaluation is the FSAL-last one
+        if (sink.stage == 3) { sink.template combine<NX>(h6, act_r, [&](int a) { return u(FB_U_ACT_THROTTLE + a); }); sink.stage = 4; continue; }   // xs == x == x*: next evaluation is the FSAL-last one
         if (sink.stage != 4) { sink.stage++; continue; }
         // ---- stage 0 with a pending step end: this evaluation was the reference's f(x*) and y = y*.
         // (It also produced the tentative k1 / first stage state of the next step.)
@@ -302,14 +322,13 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
             n_reeval++;
             continue;
         }
-        sink.stage = 0;
-        if (VAR != FB_C172S && cmd_changed) {
-            // New actuator commands alone: of the derivative just evaluated (the next step's k1) only
-            // x'.act = (cmd - x.act) / tau depends on them (c172x.jl:44-50), so those seven components are
-            // re-issued to the sink (as stage 0) instead of re-evaluating the whole right-hand side.
+        // New actuator commands alone need no re-evaluation: of the derivative just evaluated (the next step's k1) only
+        // x'.act depends on them (c172x.jl:44-50), and the actuator states are propagated in closed form (RkSink).
+        // The first stage state of the next step is rebuilt from the two shared-memory columns (this evaluation ran as
+        // stage 0: acc = k1, xs = x + dt/2 k1) rather than carried in registers across the callbacks above.
 #pragma unroll
-            for (int a = 0; a < L::NACT; a++) sink.put(L::ACT + a, (1.0 / 0.05) * (u(FB_U_ACT_THROTTLE + a) - sink.sx[(L::ACT + a) * T]));
-        }
+        for (int c = 0; c < NX; c++)
+            if (c < L::ACT || c >= L::ACT + L::NACT) xs[c] = fma(h2, sink.sacc[sink.acol(c) * T], sink.sx[c * T]);
         sink.stage = 1;
     }
 #pragma unroll

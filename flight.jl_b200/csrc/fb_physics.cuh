@@ -134,7 +134,8 @@ struct CachedIn {
                 case 0: return FB_U_T_SL; case 1: return FB_U_P_SL; case 2: return FB_U_TRN_ELEVATION; case 3: return FB_U_ACT_THROTTLE;
                 case 4: return FB_U_ACT_AILERON; case 5: return FB_U_ACT_ELEVATOR; case 6: return FB_U_ACT_RUDDER; case 7: return FB_U_ACT_FLAPS;
                 case 8: return FB_U_MIXTURE; case 9: return FB_UX_TRF; case 10: return FB_U_M_PILOT; case 11: return FB_U_M_COPILOT;
-                case 12: return FB_U_M_LPASS; case 13: return FB_U_M_RPASS; case 14: return FB_U_M_BAGGAGE; case 15: return FB_U_ACT_BRAKE_LEFT;
+                case 12: return FB_U_M_LPASS; case 13: return FB_U_M_RPASS; case 14: return FB_U_M_BAGGAGE; case 15: return FB_U_WIND_N;
+                case 16: return FB_U_WIND_E; case 17: return FB_U_WIND_D; case 18: return FB_U_ACT_BRAKE_LEFT;
                 default: return -1;
             }
         }
@@ -174,6 +175,9 @@ struct ColumnTap {        // column of a [TAP_COUNT][pitch] array, written only 
 struct ArraySink {
     double* xd;
     FB_DEV void put(int c, double v) { xd[c] = v; }
+    // first-order actuator i at row c (c172x.jl:39-52): state as stored, derivative (cmd - x) / tau
+    FB_DEV double act(int, int c, const double* x, double) const { return x[c]; }
+    FB_DEV void put_act(int c, double cmd, double xp) { xd[c] = (1.0 / 0.05) * (cmd - xp); }
 };
 // state holder over a plain array (f_step! on register / local state)
 struct ArrayState {
@@ -605,10 +609,10 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
 #pragma unroll
         for (int i = 0; i < 7; i++) {
             double lo = (i == 0 || i >= 4) ? 0.0 : -1.0;
-            double xp = x[L::ACT + i];
             double cmd = u(FB_U_ACT_THROTTLE + i);   // stored saturated (Ranged)
+            double xp = sink.act(i, L::ACT + i, x, cmd);
             pos[i] = clampd(xp, lo, 1.0);
-            sink.put(L::ACT + i, (1.0 / 0.05) * (cmd - xp));
+            sink.put_act(L::ACT + i, cmd, xp);
             if (WY) { yf->act_pos[i] = pos[i]; yf->act_cmd[i] = cmd; }
         }
         throttle = pos[0]; a_a = pos[1]; a_e = -pos[2]; a_r = -pos[3]; steer = pos[3]; a_f = pos[4]; br_l = pos[5]; br_r = pos[6];

@@ -62,7 +62,8 @@ enum { FB_AX_GE = 0, FB_AX_DF, FB_AX_CD_A, FB_AX_CL_A, FB_AX_N_STD, FB_AX_N_WOT,
 #define FB_GEOID_NLAT 721
 #define FB_GEOID_NLON 1441
 
-// gain schedules (lib/FlightApps/src/c172/c172x/control/data/*.h5), [7 EAS][4 h][P] row-major, device-global
+// gain schedules (lib/FlightApps/src/c172/c172x/control/data/*.h5): blob sections [7 EAS][4 h][P] row-major;
+// on the device one record per bilinear cell, [6 x 3 cells][P][4 corners] (fb_load_tables)
 enum { GS_TE2TE = 0, GS_TV2TE, GS_VH2TE, GS_AR2AR, GS_PHIBETA2AR, GS_Q2E, GS_C2THETA, GS_V2T, GS_P2PHI, GS_CHI2PHI, GS_COUNT };
 
 struct FbDeviceTables {

@@ -444,11 +444,24 @@ int32_t fb_load_tables(fb_handle s, const void* blob, size_t nbytes) {
     CK(cudaMemcpyAsync(s->d_geoid, b + g->off, g->nbytes, cudaMemcpyHostToDevice, s->stream));
     static const char* gnames[GS_COUNT] = {"gain.te2te", "gain.tv2te", "gain.vh2te", "gain.ar2ar", "gain.phibeta2ar",
                                            "gain.q2e", "gain.c2theta", "gain.v2t", "gain.p2phi", "gain.chi2phi"};
+    std::vector<double> gcell[GS_COUNT];   // staging must outlive the asynchronous copies
     for (int i = 0; i < GS_COUNT; i++) {
         const BlobSec* sec = find(gnames[i]);
         if (!sec) return fail(FB_ERR_ARG, std::string("fb_load_tables: missing section ") + gnames[i]);
-        if (!s->d_gains[i]) CK(cudaMalloc(&s->d_gains[i], sec->nbytes));
-        CK(cudaMemcpyAsync(s->d_gains[i], b + sec->off, sec->nbytes, cudaMemcpyHostToDevice, s->stream));
+        // Device layout: one record per bilinear CELL of the 7 x 4 design grid, [6 x 3 cells][P][4 corners
+        // {f00, f01, f10, f11}], so that value k of a member's cell is one aligned 32-byte sector (one 256-bit load)
+        // instead of four scattered 8-byte reads.
+        if (sec->nbytes % (28 * 8) != 0) return fail(FB_ERR_ARG, std::string("fb_load_tables: bad section ") + gnames[i]);
+        const int P = (int)(sec->nbytes / (28 * 8));
+        const double* src = (const double*)(b + sec->off);
+        gcell[i].assign((size_t)18 * P * 4, 0.0);
+        for (int ci = 0; ci < 6; ci++) for (int cj = 0; cj < 3; cj++) for (int k = 0; k < P; k++) {
+            double* r = gcell[i].data() + ((size_t)(ci * 3 + cj) * P + k) * 4;
+            const double* q = src + (size_t)(ci * 4 + cj) * P + k;
+            r[0] = q[0]; r[1] = q[P]; r[2] = q[4 * P]; r[3] = q[5 * P];
+        }
+        if (!s->d_gains[i]) CK(cudaMalloc(&s->d_gains[i], gcell[i].size() * 8));
+        CK(cudaMemcpyAsync(s->d_gains[i], gcell[i].data(), gcell[i].size() * 8, cudaMemcpyHostToDevice, s->stream));
         s->E.tables.gains[i] = s->d_gains[i];
     }
     CK(cudaStreamSynchronize(s->stream));
