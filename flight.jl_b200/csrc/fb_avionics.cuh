@@ -107,36 +107,51 @@ FB_DEV double pick_output(const YFull& y, int stall, int eng, const CtlState& cs
 // One bilinear cell of the (EAS, h_e) design grid, Flat outside (control.jl:965); value k of a schedule with P
 // values per design point is read on demand.
 struct GainCell {
-    int o;          // (i * 3 + j): index of the bilinear cell (device layout of fb_load_tables: [cell][k][4 corners])
+    int o;          // (i * 4 + j): design-point index of the cell's low corner
     double u, w;    // weights along EAS and h
     FB_DEV void locate(double EAS, double h) {
         double fe = (clampd(EAS, 25.0, 55.0) - 25.0) * (1.0 / 5.0), fh = (clampd(h, 50.0, 3050.0) - 50.0) * (1.0 / 1000.0);
         int i = min((int)fe, 5), j = min((int)fh, 2);
-        u = fe - (double)i; w = fh - (double)j; o = i * 3 + j;
+        u = fe - (double)i; w = fh - (double)j; o = i * 4 + j;
     }
 };
-// Values of one schedule at the member's cell. The table lives in L2 (uncoalesced: every member has its own cell), so
-// what matters is how many reads are in flight at once: batch<N> issues N 256-bit reads back to back and interpolates
-// afterwards — one L2 round trip per batch instead of one per value.
-struct Gain {
-    const double* p; double u, w;
-    FB_DEV Gain(const double* tab, int P, const GainCell& c) : p(tab + (long long)c.o * P * 4), u(c.u), w(c.w) {}
-    FB_DEV double mix(double f00, double f01, double f10, double f11) const {
+// Values of one schedule at the member's cell. SH: the schedules sit in the CTA's shared memory (the integrator stages
+// them with the table pack: every member has its own cell, so from L2 each value was four uncoalesced round trips —
+// the dominant stall of the fly-by-wire kernels); otherwise they are read from the device buffer.
+template <bool SH>
+struct GainT {
+    const double* p; unsigned a; double u, w;   // low corner's record: generic pointer, or shared-window address when SH
+    int P;
+    FB_DEV double ld(int idx) const {
+        if (SH) { double v; asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a + 8u * (unsigned)idx)); return v; }
+        return __ldg(p + idx);
+    }
+    FB_DEV double operator()(int k) const {
+        double f00 = ld(k), f01 = ld(P + k), f10 = ld(4 * P + k), f11 = ld(5 * P + k);
         return (1.0 - u) * ((1.0 - w) * f00 + w * f01) + u * ((1.0 - w) * f10 + w * f11);
     }
     template <int N>
     FB_DEV void batch(int k0, double* out) const {
-        double r[N][4];   // the four corners of value k: one 32-byte sector, one LDG.256
 #pragma unroll
-        for (int n = 0; n < N; n++)
-            asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r[n][0]), "=d"(r[n][1]), "=d"(r[n][2]), "=d"(r[n][3]) : "l"(p + 4 * (k0 + n)));
-#pragma unroll
-        for (int n = 0; n < N; n++) out[n] = mix(r[n][0], r[n][1], r[n][2], r[n][3]);
+        for (int n = 0; n < N; n++) out[n] = (*this)(k0 + n);
     }
 };
+template <bool SH>
+struct GainTables {       // the ten schedules, [7 EAS][4 h][P] each, concatenated (fb_tables.h)
+    const double* base; unsigned sbase;
+    FB_DEV GainT<SH> gain(int s, const GainCell& c) const {
+        GainT<SH> g; g.P = gs_P(s); g.u = c.u; g.w = c.w;
+        g.p = base + gs_off(s) + c.o * gs_P(s);
+        g.a = sbase + 8u * (unsigned)(gs_off(s) + c.o * gs_P(s));
+        return g;
+    }
+};
+typedef GainTables<false> GainsGlobal;
+typedef GainTables<true> GainsShared;
+FB_DEV GainsGlobal gains_global(const FbDeviceTables& T) { GainsGlobal g; g.base = T.gains; g.sbase = 0; return g; }
 struct PidGains {      // (k_p, k_i, k_d, tau_f) of a scheduled PID
     double k_p, k_i, k_d, tau_f;
-    FB_DEV PidGains(const double* tab, const GainCell& c) { double g[4]; Gain(tab, 4, c).batch<4>(0, g); k_p = g[0]; k_i = g[1]; k_d = g[2]; tau_f = g[3]; }
+    template <class GT> FB_DEV PidGains(const GT& T, int s, const GainCell& c) { double g[4]; T.gain(s, c).template batch<4>(0, g); k_p = g[0]; k_i = g[1]; k_d = g[2]; tau_f = g[3]; }
 };
 
 // ------------------------------------------------------------------------------------------ compensators
@@ -164,15 +179,15 @@ FB_DEV void int_reset(IntS& s) { s.x0 = 0.0; s.sat = 0; }
 
 // LQR f_periodic! (control.jl:708-743), NU = NZ = 2. Schedule record: K_fbk (2 x NX row-major), K_fwd 2x2, K_int 2x2,
 // x_trim NX, u_trim 2, z_trim 2 (packing of tools/build_tables.py).
-template <int NX>
-FB_DEV void lqr_update(LqrS& s, const Gain& g, const double* x, double z0, double z1, double zr0, double zr1,
+template <int NX, class G>
+FB_DEV void lqr_update(LqrS& s, const G& g, const double* x, double z0, double z1, double zr0, double zr1,
                        double lo0, double lo1, double Dt, double& out0, double& out1) {
     double dx[NX], t[NX], c[8], uz[4];
-    g.batch<NX>(2 * NX + 8, t);            // x_trim
+    g.template batch<NX>(2 * NX + 8, t);            // x_trim
 #pragma unroll
     for (int j = 0; j < NX; j++) dx[j] = x[j] - t[j];
-    g.batch<8>(2 * NX, c);                 // K_fwd (2x2), K_int (2x2)
-    g.batch<4>(3 * NX + 8, uz);            // u_trim, z_trim
+    g.template batch<8>(2 * NX, c);                 // K_fwd (2x2), K_int (2x2)
+    g.template batch<4>(3 * NX + 8, uz);            // u_trim, z_trim
     const double zt0 = uz[2], zt1 = uz[3];
     double out[2];
 #pragma unroll
@@ -181,7 +196,7 @@ FB_DEV void lqr_update(LqrS& s, const Gain& g, const double* x, double z0, doubl
         bool halted = isign(int_in * (double)s.sat[i]) > 0;
         double int_out = s.io[i] + Dt * int_in * (halted ? 0.0 : 1.0);
         double fwd = c[2 * i] * (zr0 - zt0) + c[1 + 2 * i] * (zr1 - zt1);
-        g.batch<NX>(i * NX, t);            // row i of K_fbk
+        g.template batch<NX>(i * NX, t);            // row i of K_fbk
         double fbk = 0.0;
 #pragma unroll
         for (int j = 0; j < NX; j++) fbk = fbk + t[j] * dx[j];
@@ -195,8 +210,8 @@ FB_DEV void lqr_update(LqrS& s, const Gain& g, const double* x, double z0, doubl
 }
 // f_init!(lqr) with the gains currently assigned: zero inputs, one update (leaves int_out_0 = 0 and the saturation
 // flags of the zero-input output)
-template <int NX>
-FB_DEV void lqr_reset(LqrS& s, const Gain& g, double lo0, double lo1, double Dt) {
+template <int NX, class G>
+FB_DEV void lqr_reset(LqrS& s, const G& g, double lo0, double lo1, double Dt) {
     s.io[0] = 0.0; s.io[1] = 0.0; s.sat[0] = 0; s.sat[1] = 0;
     double x[NX];
 #pragma unroll
@@ -207,8 +222,9 @@ FB_DEV void lqr_reset(LqrS& s, const Gain& g, double lo0, double lo1, double Dt)
 
 // ------------------------------------------------------------------------------------------ control laws
 // f_periodic!(ControlLawsLon) — c172x_ctl.jl:286-446
-FB_CTL_FN void lon_periodic(CtlState& cs, const YFull& v, int wow, const MemberIn& u,
-                                          const FbDeviceTables& T, double Dt, int mode_req) {
+template <class U, class GT>
+FB_CTL_FN void lon_periodic(CtlState& cs, const YFull& v, int wow, const U& u,
+                                          const GT& T, double Dt, int mode_req) {
     const double EAS = v.EAS, h_e = v.h_e, q = v.w_wb_b.y, r = v.w_wb_b.z, theta = v.theta, phi = v.phi;
     const double clm = -v.v_eb_n.z;
     const double h_ref = u(FB_U_LON_H_REF), EAS_ref = u(FB_U_LON_EAS_REF);
@@ -239,16 +255,16 @@ FB_CTL_FN void lon_periodic(CtlState& cs, const YFull& v, int wow, const MemberI
     if (te2te_en) {
         const int sat_thr = cs.te2te.sat[0], sat_ele = cs.te2te.sat[1];
         if (v2t_en) {
-            const PidGains g(T.gains[GS_V2T], c);
+            const PidGains g(T, GS_V2T, c);
             if (mode != mode_prev) { pid_reset(cs.v2t_pid); if (g.k_i != 0.0) cs.v2t_pid.xi = cs.thr_cmd; }
             throttle_ref = pid_update(cs.v2t_pid, g.k_p, g.k_i, g.k_d, g.tau_f, -INFINITY, INFINITY, EAS_ref - EAS, sat_thr, Dt);
         }
         if (q2e_en) {
-            const PidGains g(T.gains[GS_Q2E], c);
+            const PidGains g(T, GS_Q2E, c);
             if (mode != mode_prev) { int_reset(cs.q2e_int); pid_reset(cs.q2e_pid); if (g.k_i != 0.0) cs.q2e_pid.xi = cs.te2te_zref1; }
             if (t2q_en) {
                 if (mode == LON_EAS_CLM) {
-                    const PidGains gc(T.gains[GS_C2THETA], c);
+                    const PidGains gc(T, GS_C2THETA, c);
                     if (mode != mode_prev) { pid_reset(cs.c2t_pid); if (gc.k_i != 0.0) cs.c2t_pid.xi = theta; }
                     theta_ref = pid_update(cs.c2t_pid, gc.k_p, gc.k_i, gc.k_d, gc.tau_f, -INFINITY, INFINITY, u(FB_U_LON_CLM_REF) - clm, sat_ele, Dt);
                 }
@@ -259,17 +275,17 @@ FB_CTL_FN void lon_periodic(CtlState& cs, const YFull& v, int wow, const MemberI
             double io = int_update(cs.q2e_int, q_ref - q, sat_ele, Dt);
             elevator_ref = pid_update(cs.q2e_pid, g.k_p, g.k_i, g.k_d, g.tau_f, -INFINITY, INFINITY, io, sat_ele, Dt);
         }
-        Gain g(T.gains[GS_TE2TE], 36, c);
+        const auto g = T.gain(GS_TE2TE, c);
         cs.te2te_zref1 = elevator_ref;
         lqr_update<8>(cs.te2te, g, xred, v.act_cmd[0], v.act_cmd[2], throttle_ref, elevator_ref, 0.0, -1.0, Dt, throttle_cmd, elevator_cmd);   // Zte :167-171
     }
     if (mode == LON_THR_EAS) {
-        Gain g(T.gains[GS_TV2TE], 36, c);
+        const auto g = T.gain(GS_TV2TE, c);
         if (mode != mode_prev) lqr_reset<8>(cs.tv2te, g, 0.0, -1.0, Dt);
         lqr_update<8>(cs.tv2te, g, xred, v.act_cmd[0], EAS, throttle_ref, EAS_ref, 0.0, -1.0, Dt, throttle_cmd, elevator_cmd);   // Ztv :190-194
     }
     if (mode == LON_EAS_ALT) {
-        Gain g(T.gains[GS_VH2TE], 39, c);
+        const auto g = T.gain(GS_VH2TE, c);
         if (mode != mode_prev) lqr_reset<9>(cs.vh2te, g, 0.0, -1.0, Dt);
         const double xfull[9] = {v.w_eb_b.y, theta, EAS, v.alpha, h_e, v.alpha_filt, v.eng_n, v.act_pos[0], v.act_pos[2]};   // XLonFull :97-118
         lqr_update<9>(cs.vh2te, g, xfull, EAS, h_e, EAS_ref, h_ref, 0.0, -1.0, Dt, throttle_cmd, elevator_cmd);   // Zvh :178-182
@@ -282,8 +298,9 @@ FB_CTL_FN void lon_periodic(CtlState& cs, const YFull& v, int wow, const MemberI
 FB_DEV double wrap_to_pi(double x) { return x + 2.0 * FB_PI * floor((FB_PI - x) / (2.0 * FB_PI)); }   // attitude.jl wrap_to_π
 
 // f_periodic!(ControlLawsLat) — c172x_ctl.jl:880-983
-FB_CTL_FN void lat_periodic(CtlState& cs, const YFull& v, int wow, const MemberIn& u,
-                                          const FbDeviceTables& T, double Dt, int mode_req) {
+template <class U, class GT>
+FB_CTL_FN void lat_periodic(CtlState& cs, const YFull& v, int wow, const U& u,
+                                          const GT& T, double Dt, int mode_req) {
     const double EAS = v.EAS, h_e = v.h_e, p = v.w_wb_b.x;
     const int mode_prev = cs.lat_mode;
     const int mode = wow ? LAT_DIRECT : mode_req;
@@ -294,22 +311,22 @@ FB_CTL_FN void lat_periodic(CtlState& cs, const YFull& v, int wow, const MemberI
     const double xlat[8] = {v.w_eb_b.x, v.w_eb_b.z, v.phi, EAS, v.beta, v.beta_filt, v.act_pos[1], v.act_pos[3]};   // XLatRed :767-779
     GainCell c; c.locate(EAS, h_e);
     if (mode == LAT_SAS) {
-        Gain g(T.gains[GS_AR2AR], 36, c);
+        const auto g = T.gain(GS_AR2AR, c);
         lqr_update<8>(cs.ar2ar, g, xlat, v.act_cmd[1], v.act_cmd[3], aileron_ref, rudder_ref, -1.0, -1.0, Dt, aileron_cmd, rudder_cmd);   // Zar :806-810
     }
     if (mode == LAT_P_BETA || mode == LAT_PHI_BETA || mode == LAT_CHI_BETA) {
         const int sat_ail = cs.pb2ar.sat[0];
         if (mode == LAT_P_BETA) {
-            const PidGains g(T.gains[GS_P2PHI], c);
+            const PidGains g(T, GS_P2PHI, c);
             if (mode != mode_prev) { int_reset(cs.p2phi_int); pid_reset(cs.p2phi_pid); if (g.k_i != 0.0) cs.p2phi_pid.xi = cs.pb2ar_zref0; }
             double io = int_update(cs.p2phi_int, u(FB_U_LAT_P_REF) - p, sat_ail, Dt);
             phi_ref = pid_update(cs.p2phi_pid, g.k_p, g.k_i, g.k_d, g.tau_f, -INFINITY, INFINITY, io, sat_ail, Dt);
         } else if (mode == LAT_CHI_BETA) {
-            const PidGains g(T.gains[GS_CHI2PHI], c);
+            const PidGains g(T, GS_CHI2PHI, c);
             if (mode != mode_prev) { pid_reset(cs.chi2phi_pid); if (g.k_i != 0.0) cs.chi2phi_pid.xi = cs.pb2ar_zref0; }
             phi_ref = pid_update(cs.chi2phi_pid, g.k_p, g.k_i, g.k_d, g.tau_f, -FB_PI / 4, FB_PI / 4, wrap_to_pi(u(FB_U_LAT_CHI_REF) - v.chi_gnd), sat_ail, Dt);
         }
-        Gain g(T.gains[GS_PHIBETA2AR], 36, c);
+        const auto g = T.gain(GS_PHIBETA2AR, c);
         if (mode != mode_prev) lqr_reset<8>(cs.pb2ar, g, -1.0, -1.0, Dt);
         cs.pb2ar_zref0 = phi_ref;
         lqr_update<8>(cs.pb2ar, g, xlat, v.phi, v.beta, phi_ref, u(FB_U_LAT_BETA_REF), -1.0, -1.0, Dt, aileron_cmd, rudder_cmd);   // Zφβ :789-793
@@ -323,7 +340,8 @@ FB_CTL_FN void lat_periodic(CtlState& cs, const YFull& v, int wow, const MemberI
 // f_periodic!(GuidanceLaws, ctl, vehicle): c172x_gdc.jl:297-329 -> SegmentGuidance :228-252 -> SegmentGuidanceData :113-148
 // (dchi_inf = pi/2, e_sf = 250 m, e_thr = 1000 m, :203-207). On a Cessna172Xv1 the mode request stays `direct` (the host
 // refuses guidance inputs there), which makes this a no-op. Cold code: runs once per control period, IEEE arithmetic.
-FB_GDC_FN void gdc_periodic(const CtlState& cs, double lat, double lon, double h_e, int wow, const MemberIn& u) {
+template <class U>
+FB_GDC_FN void gdc_periodic(const CtlState& cs, double lat, double lon, double h_e, int wow, U& u) {
     const int mode = wow ? 0 : (int)u(FB_U_GDC_MODE_REQ);
     auto out = [&](int k, double v) { cs.gdc[(long long)k * cs.gdc_pitch] = v; };
     if (mode == 1) {
@@ -360,14 +378,42 @@ FB_GDC_FN void gdc_periodic(const CtlState& cs, double lat, double lon, double h
 }
 
 static __device__ __noinline__ void lon_periodic_ool(CtlState& cs, const YFull& v, int wow, const MemberIn& u, const FbDeviceTables& T, double Dt, int mode_req) {
-    lon_periodic(cs, v, wow, u, T, Dt, mode_req);
+    lon_periodic(cs, v, wow, u, gains_global(T), Dt, mode_req);
 }
 static __device__ __noinline__ void lat_periodic_ool(CtlState& cs, const YFull& v, int wow, const MemberIn& u, const FbDeviceTables& T, double Dt, int mode_req) {
-    lat_periodic(cs, v, wow, u, T, Dt, mode_req);
+    lat_periodic(cs, v, wow, u, gains_global(T), Dt, mode_req);
 }
 
-// assign!(vehicle, avionics): c172x_ctl.jl:449-458, 986-995 — the four fly-by-wire commands the control laws own
-FB_DEV bool avionics_assign(const CtlState& cs, const MemberIn& u) {
+// The control- and guidance-law inputs of one member (fb_input 40..49, 60..68, 70) read in ONE batch of independent
+// loads; the laws then index the copy with compile-time field ids. set() keeps the copy and the ensemble in step (the
+// segment guidance hands references to the control laws that way, c172x_gdc.jl:316-326).
+struct CtlIn {
+    MemberIn g;
+    double lon[10], lat[9], gdc_mode;
+    FB_DEV void load() {
+#pragma unroll
+        for (int k = 0; k < 10; k++) lon[k] = g.raw(FB_U_LON_MODE_REQ + k);
+#pragma unroll
+        for (int k = 0; k < 9; k++) lat[k] = g.raw(FB_U_LAT_MODE_REQ + k);
+        gdc_mode = g.raw(FB_U_GDC_MODE_REQ);
+    }
+    FB_DEV double operator()(int f) const {
+        if (f >= FB_U_LON_MODE_REQ && f < FB_U_LON_MODE_REQ + 10) return lon[f - FB_U_LON_MODE_REQ];
+        if (f >= FB_U_LAT_MODE_REQ && f < FB_U_LAT_MODE_REQ + 9) return lat[f - FB_U_LAT_MODE_REQ];
+        if (f == FB_U_GDC_MODE_REQ) return gdc_mode;
+        return g(f);
+    }
+    FB_DEV void set(int f, double v) {
+        g.set(f, v);
+        if (f >= FB_U_LON_MODE_REQ && f < FB_U_LON_MODE_REQ + 10) lon[f - FB_U_LON_MODE_REQ] = v;
+        if (f >= FB_U_LAT_MODE_REQ && f < FB_U_LAT_MODE_REQ + 9) lat[f - FB_U_LAT_MODE_REQ] = v;
+    }
+};
+
+// assign!(vehicle, avionics): c172x_ctl.jl:449-458, 986-995 — the four fly-by-wire commands the control laws own.
+// U: MemberIn (ensemble) or the integrator's CachedIn (compares against, and updates, its shared-memory copy).
+template <class U>
+FB_DEV bool avionics_assign(const CtlState& cs, U& u) {
     bool ch = false;
     double v;
     v = clampd(cs.thr_cmd, 0.0, 1.0);  if (u(FB_U_ACT_THROTTLE) != v) { u.set(FB_U_ACT_THROTTLE, v); ch = true; }
@@ -379,14 +425,14 @@ FB_DEV bool avionics_assign(const CtlState& cs, const MemberIn& u) {
 
 // f_periodic!(avionics, vehicle) (guidance in direct mode forwards, then lon, then lat) followed by assign!.
 // Returns true when an actuator command changed (only ẋ.act of the pending derivative depends on it).
-template <int VAR, int KIN>
-FB_DEV bool avionics_periodic(const YFull& yf, const RhsOut& y, const MemberIn& u,
-                              CtlState& cs, const FbDeviceTables& T, double Dt) {
+template <int VAR, int KIN, class UA, class GT>
+FB_DEV bool avionics_periodic(const YFull& yf, const RhsOut& y, CtlIn& u, UA& ua,
+                              CtlState& cs, const GT& T, double Dt) {
     if (VAR < FB_C172X1) return false;
     gdc_periodic(cs, yf.lat, yf.lon, yf.h_e, y.wow, u);
     lon_periodic(cs, yf, y.wow, u, T, Dt, (int)u(FB_U_LON_MODE_REQ));
     lat_periodic(cs, yf, y.wow, u, T, Dt, (int)u(FB_U_LAT_MODE_REQ));
-    return avionics_assign(cs, u);
+    return avionics_assign(cs, ua);
 }
 
 // f_init!(avionics, vehicle): c172x_ctl.jl:1246-1250 -> :463-519 (lon), :998-1032 (lat). `yf` is the vehicle output

@@ -46,7 +46,7 @@ struct EnsembleDev {
 
 // Stage the lookup-table pack into shared memory with one bulk asynchronous copy (TMA unit,
 // cp.async.bulk + mbarrier complete_tx); every thread of the CTA then waits on the barrier phase.
-FB_DEV void stage_tables(double* smem_tb, const double* __restrict__ gsrc) {
+FB_DEV void stage_tables(double* smem_tb, const double* __restrict__ gsrc, unsigned nbytes = FB_TB_BYTES) {
     __shared__ __align__(8) unsigned long long bar;
     unsigned bar_a = (unsigned)__cvta_generic_to_shared(&bar);
     unsigned dst_a = (unsigned)__cvta_generic_to_shared(smem_tb);
@@ -56,9 +56,9 @@ FB_DEV void stage_tables(double* smem_tb, const double* __restrict__ gsrc) {
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((unsigned)FB_TB_BYTES) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(nbytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(dst_a), "l"(gsrc), "r"((unsigned)FB_TB_BYTES), "r"(bar_a) : "memory");
+                     ::"r"(dst_a), "l"(gsrc), "r"(nbytes), "r"(bar_a) : "memory");
     }
     unsigned done = 0;
     while (!done) {
@@ -149,7 +149,9 @@ struct SmemState {       // f_step! view of the step-start state column
 template <int VAR, int KIN, bool AIR, int CAP = FB_STEP_BLOCK>
 struct StepShape {
     static constexpr int NX = Lay<VAR, KIN, AIR>::NX;
-    static constexpr int BUDGET = 232448 - FB_TB_BYTES - 1024;                                 // 227 KB per CTA
+    // shared-memory tables: the lookup pack, plus the gain schedules for the variants that run control laws
+    static constexpr int TBL = FB_TB_BYTES + (VAR >= FB_C172X1 ? FB_GS_BYTES : 0);
+    static constexpr int BUDGET = 232448 - TBL - 1024;                                         // 227 KB per CTA
     static constexpr int NCOL = 2 * NX - Lay<VAR, KIN, AIR>::NACT;                              // state columns + accumulator columns (none for actuators)
     static constexpr int FIT = (int)(BUDGET / (sizeof(double) * NCOL)) / 32 * 32;
     static constexpr int T = FIT < CAP ? FIT : CAP;
@@ -159,7 +161,7 @@ struct StepShape {
 #endif
     static constexpr int NSLOT_MAX = (VAR == FB_C172S) ? FB_NSLOT_MAX : FB_NSLOT_MAX + 3;   // C172X also caches the wind
     static constexpr int NSLOT = SPARE < NSLOT_MAX ? SPARE : NSLOT_MAX;
-    static constexpr size_t SMEM = FB_TB_BYTES + sizeof(double) * (NCOL + NSLOT) * T;
+    static constexpr size_t SMEM = TBL + sizeof(double) * (NCOL + NSLOT) * T;
 };
 #define FB_RESUME_PENDING (1 << 30)
 template <int VAR, int KIN, bool AIR, int CAP = FB_STEP_BLOCK>
@@ -174,7 +176,9 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
     constexpr int T = StepShape<VAR, KIN, AIR, CAP>::T;
     constexpr int T_ = T;
     if (resume_mode && *ground_count == 0) return;        // nobody was handed over by the AIR launch (CTA-uniform)
-    stage_tables(smem_tb, E.tables.pack);
+    constexpr int TBL = StepShape<VAR, KIN, AIR, CAP>::TBL;
+    stage_tables(smem_tb, E.tables.pack, TBL);
+    GainsShared gains; gains.base = nullptr; gains.sbase = (unsigned)__cvta_generic_to_shared(smem) + FB_TB_BYTES;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= E.n) return;
     int status = E.status[i];
@@ -190,7 +194,7 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
         return;
     }
     MemberIn ug; ug.u = E.u + i; ug.pitch = E.pitch;
-    double* sx = smem + FB_TB_BYTES / 8 + threadIdx.x;
+    double* sx = smem + TBL / 8 + threadIdx.x;
     double* sacc = sx + NX * T;
     CachedIn<VAR, T, StepShape<VAR, KIN, AIR, CAP>::NSLOT> u; u.g = ug; u.sc = sx + StepShape<VAR, KIN, AIR, CAP>::NCOL * T;
     double xs[NX];
@@ -296,8 +300,11 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
         }
         bool changed = f_step<VAR, KIN, AIR>(xstate, stall, eng, u, y, status);
         if (status != FB_ST_RUNNING) break;
-        bool cmd_changed = false;
-        if (ctl_due) cmd_changed = avionics_periodic<VAR, KIN>(yf, y, ug, cs, E.tables, Dt);
+        // the new commands go to the ensemble and straight into their input-cache slots (no refresh)
+        if (ctl_due) {
+            CtlIn ci; ci.g = ug; ci.load();   // one L2 round trip for all control-law inputs
+            avionics_periodic<VAR, KIN>(yf, y, ci, u, cs, gains, Dt);
+        }
         if (done >= next_ev) {
             while (ev_cur < ev_end && E.ev_step[ev_cur] <= step_idx) {
                 int f = E.ev_field[ev_cur];
@@ -308,7 +315,7 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
             changed = true;
             if (VAR >= FB_C172X1) avionics_assign(cs, ug);   // an event cannot override a command the control laws own
         } else if (VAR >= FB_C172X1 && changed) avionics_assign(cs, ug);
-        if (changed || cmd_changed) u.refresh();
+        if (changed) u.refresh();
         if (log_due) {
             const long long smp = step_idx / E.log_every;
             for (int f = 0; f < E.log_n_fields; f++)
@@ -443,7 +450,8 @@ fperiodic_kernel(EnsembleDev E, double Dt) {
     avionics_assign(cs, u);
     YFull yf; RhsOut y;
     rhs_with_outputs<VAR, KIN>(x, k, E.stall[i], E.eng[i], u, smem_tb, E.tables.geoid, &y, &yf);
-    avionics_periodic<VAR, KIN>(yf, y, u, cs, E.tables, Dt);
+    CtlIn ci; ci.g = u; ci.load();
+    avionics_periodic<VAR, KIN>(yf, y, ci, u, cs, gains_global(E.tables), Dt);
     cs.store(E.ctl + i, E.pitch);
 }
 

@@ -153,6 +153,11 @@ struct CachedIn {
         if (f >= FB_U_WIND_N && f <= FB_U_WIND_D) return (flags & 8) ? g(f) : 0.0;
         return g(f);
     }
+    FB_DEV void set(int f, double v) {       // one plain field (not a flag, not a derived slot): ensemble + cached copy
+        g.set(f, v);
+        const int s = slot(f);
+        if (s >= 0) sc[s * T] = v;
+    }
     FB_DEV void refresh() {
 #pragma unroll
         for (int s = 0; s < NSLOT; s++) if (field_of(s) >= 0) sc[s * T] = g(field_of(s));

@@ -32,7 +32,7 @@ struct fb_sim {
     double* d_stage[FB_U__COUNT] = {};                 // lazily allocated staging rows
     cudaEvent_t stage_consumed[FB_U__COUNT] = {};
     cudaEvent_t copy_done = nullptr;
-    double* d_pack = nullptr; float* d_geoid = nullptr; double* d_gains[GS_COUNT] = {};
+    double* d_pack = nullptr; float* d_geoid = nullptr;
     bool tables_loaded = false, initialised = false;
     long long n_steps = 0;
     long long* d_ev_off = nullptr; long long* d_ev_step = nullptr; int* d_ev_field = nullptr; double* d_ev_value = nullptr;
@@ -351,7 +351,6 @@ int32_t fb_destroy(fb_handle s) {
     EnsembleDev& E = s->E;
     cudaFree(E.x); cudaFree(E.u); cudaFree(E.stall); cudaFree(E.eng); cudaFree(E.status); cudaFree(E.ctl); cudaFree(E.log);
     cudaFree(s->d_pack); cudaFree(s->d_geoid);
-    for (int i = 0; i < GS_COUNT; i++) cudaFree(s->d_gains[i]);
     cudaFree(s->d_ev_off); cudaFree(s->d_ev_step); cudaFree(s->d_ev_field); cudaFree(s->d_ev_value); cudaFree(s->d_ev_cursor);
     cudaFree(s->d_log_fields); cudaFree(s->d_scratch); cudaFree(s->d_stats); cudaFree(s->d_rhs_count);
     cudaFree(s->d_resume); cudaFree(s->d_ground); if (s->h_ground) cudaFreeHost(s->h_ground); if (s->ground_ev) cudaEventDestroy(s->ground_ev);
@@ -438,34 +437,21 @@ int32_t fb_load_tables(fb_handle s, const void* blob, size_t nbytes) {
     }
     const BlobSec* g = find("geoid");
     if (!g || g->dtype != 1 || g->nbytes != (uint64_t)FB_GEOID_NLAT * FB_GEOID_NLON * 4) return fail(FB_ERR_ARG, "fb_load_tables: bad or missing geoid section");
-    if (!s->d_pack) CK(cudaMalloc(&s->d_pack, FB_TB_BYTES));
+    if (!s->d_pack) CK(cudaMalloc(&s->d_pack, FB_TB_BYTES + FB_GS_BYTES));
     if (!s->d_geoid) CK(cudaMalloc(&s->d_geoid, g->nbytes));
     CK(cudaMemcpyAsync(s->d_pack, pack.data(), FB_TB_BYTES, cudaMemcpyHostToDevice, s->stream));
     CK(cudaMemcpyAsync(s->d_geoid, b + g->off, g->nbytes, cudaMemcpyHostToDevice, s->stream));
     static const char* gnames[GS_COUNT] = {"gain.te2te", "gain.tv2te", "gain.vh2te", "gain.ar2ar", "gain.phibeta2ar",
                                            "gain.q2e", "gain.c2theta", "gain.v2t", "gain.p2phi", "gain.chi2phi"};
-    std::vector<double> gcell[GS_COUNT];   // staging must outlive the asynchronous copies
+    std::vector<double> gpack(FB_GS_BYTES / 8, 0.0);   // staging must outlive the asynchronous copy
     for (int i = 0; i < GS_COUNT; i++) {
         const BlobSec* sec = find(gnames[i]);
-        if (!sec) return fail(FB_ERR_ARG, std::string("fb_load_tables: missing section ") + gnames[i]);
-        // Device layout: one record per bilinear CELL of the 7 x 4 design grid, [6 x 3 cells][P][4 corners
-        // {f00, f01, f10, f11}], so that value k of a member's cell is one aligned 32-byte sector (one 256-bit load)
-        // instead of four scattered 8-byte reads.
-        if (sec->nbytes % (28 * 8) != 0) return fail(FB_ERR_ARG, std::string("fb_load_tables: bad section ") + gnames[i]);
-        const int P = (int)(sec->nbytes / (28 * 8));
-        const double* src = (const double*)(b + sec->off);
-        gcell[i].assign((size_t)18 * P * 4, 0.0);
-        for (int ci = 0; ci < 6; ci++) for (int cj = 0; cj < 3; cj++) for (int k = 0; k < P; k++) {
-            double* r = gcell[i].data() + ((size_t)(ci * 3 + cj) * P + k) * 4;
-            const double* q = src + (size_t)(ci * 4 + cj) * P + k;
-            r[0] = q[0]; r[1] = q[P]; r[2] = q[4 * P]; r[3] = q[5 * P];
-        }
-        if (!s->d_gains[i]) CK(cudaMalloc(&s->d_gains[i], gcell[i].size() * 8));
-        CK(cudaMemcpyAsync(s->d_gains[i], gcell[i].data(), gcell[i].size() * 8, cudaMemcpyHostToDevice, s->stream));
-        s->E.tables.gains[i] = s->d_gains[i];
+        if (!sec || sec->dtype != 0 || sec->nbytes != (uint64_t)28 * gs_P(i) * 8) return fail(FB_ERR_ARG, std::string("fb_load_tables: bad or missing section ") + gnames[i]);
+        memcpy(gpack.data() + gs_off(i), b + sec->off, sec->nbytes);
     }
+    CK(cudaMemcpyAsync((char*)s->d_pack + FB_TB_BYTES, gpack.data(), FB_GS_BYTES, cudaMemcpyHostToDevice, s->stream));
     CK(cudaStreamSynchronize(s->stream));
-    s->E.tables.pack = s->d_pack; s->E.tables.geoid = s->d_geoid;
+    s->E.tables.pack = s->d_pack; s->E.tables.gains = s->d_pack + FB_TB_BYTES / 8; s->E.tables.geoid = s->d_geoid;
     s->tables_loaded = true;
     return FB_OK;
 }
