@@ -331,11 +331,14 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
         }
         // New actuator commands alone need no re-evaluation: of the derivative just evaluated (the next step's k1) only
         // x'.act depends on them (c172x.jl:44-50), and the actuator states are propagated in closed form (RkSink).
-        // The first stage state of the next step is rebuilt from the two shared-memory columns (this evaluation ran as
-        // stage 0: acc = k1, xs = x + dt/2 k1) rather than carried in registers across the callbacks above.
+        // Variants with control laws: the first stage state of the next step is rebuilt from the two shared-memory columns
+        // (this evaluation ran as stage 0: acc = k1, xs = x + dt/2 k1) rather than carried in registers across the
+        // callbacks above. (Without control laws carrying it is cheaper: measured on cfg 4.)
+        if (VAR >= FB_C172X1) {
 #pragma unroll
-        for (int c = 0; c < NX; c++)
-            if (c < L::ACT || c >= L::ACT + L::NACT) xs[c] = fma(h2, sink.sacc[sink.acol(c) * T], sink.sx[c * T]);
+            for (int c = 0; c < NX; c++)
+                if (c < L::ACT || c >= L::ACT + L::NACT) xs[c] = fma(h2, sink.sacc[sink.acol(c) * T], sink.sx[c * T]);
+        }
         sink.stage = 1;
     }
 #pragma unroll
