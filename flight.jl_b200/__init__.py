@@ -93,7 +93,7 @@ class fb_moments(C.Structure):
 
 EXPORTS = ["fb_api_version", "fb_last_error", "fb_create", "fb_load_tables", "fb_destroy", "fb_sync", "fb_init_trim", "fb_init",
            "fb_init_state", "fb_set_input", "fb_get_input", "fb_schedule_inputs", "fb_step", "fb_run", "fb_time", "fb_nx",
-           "fb_get_state", "fb_get_discrete", "fb_get_output", "fb_status", "fb_log_info", "fb_log_times", "fb_log_fetch",
+           "fb_get_state", "fb_get_state_async", "fb_wait_state", "fb_get_discrete", "fb_get_output", "fb_status", "fb_log_info", "fb_log_times", "fb_log_fetch",
            "fb_stats", "fb_rhs", "fb_fstep", "fb_fperiodic", "fb_counters", "fb_linearize", "fb_linearize_dims", "fb_device_state", "fb_stream", "fb_measure_fp64_peak",
            "fb_lss_create", "fb_lss_destroy", "fb_lss_set_model", "fb_lss_from_linearize", "fb_lss_set_state", "fb_lss_get_state",
            "fb_lss_set_input", "fb_lss_get_input", "fb_lss_get_output", "fb_lss_step", "fb_lss_sync", "fb_lss_stream"]
@@ -120,7 +120,7 @@ def load_library():
         "fb_set_input": (i32, [vp, i32, _DP, i64]), "fb_get_input": (i32, [vp, i32, _DP]),
         "fb_schedule_inputs": (i32, [vp, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32), _DP]),
         "fb_step": (i32, [vp, dbl]), "fb_run": (i32, [vp]), "fb_time": (i32, [vp, _DP, C.POINTER(i64)]),
-        "fb_nx": (i32, [vp, C.POINTER(i32)]), "fb_get_state": (i32, [vp, _DP]), "fb_get_discrete": (i32, [vp, u8p, u8p]),
+        "fb_nx": (i32, [vp, C.POINTER(i32)]), "fb_get_state": (i32, [vp, _DP]), "fb_get_state_async": (i32, [vp, _DP]), "fb_wait_state": (i32, [vp]), "fb_get_discrete": (i32, [vp, u8p, u8p]),
         "fb_get_output": (i32, [vp, i32, _DP]), "fb_status": (i32, [vp, C.POINTER(i32)]),
         "fb_log_info": (i32, [vp, C.POINTER(i64), C.POINTER(i32)]), "fb_log_times": (i32, [vp, _DP]),
         "fb_log_fetch": (i32, [vp, i32, _DP]), "fb_stats": (i32, [vp, i32, C.POINTER(fb_moments)]),
@@ -506,6 +506,19 @@ class BatchSimulation:
             raise FlightBatchError(f"get_state: out must be a C-contiguous float64 array of shape {(self.nx, self.n)}")
         _ck(self._lib.fb_get_state(self._h, _dp(out)), self._lib)
         return out
+
+    def get_state_async(self, out):
+        """Pipelined sim.x: snapshot the state as of the work submitted so far and copy it into `out` (an [nx][N] float64
+        array over PINNED host memory) while later step() calls already run. `out` is valid after wait_state()."""
+        if out.dtype != np.float64 or not out.flags.c_contiguous or out.shape != (self.nx, self.n):
+            raise FlightBatchError(f"get_state_async: out must be a C-contiguous float64 array of shape {(self.nx, self.n)}")
+        self._snap_out = out   # keep the buffer alive while the copy is in flight
+        _ck(self._lib.fb_get_state_async(self._h, _dp(out)), self._lib)
+        return out
+
+    def wait_state(self):
+        _ck(self._lib.fb_wait_state(self._h), self._lib)
+        self._snap_out = None
 
     @property
     def xdot(self):

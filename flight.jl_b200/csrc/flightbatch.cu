@@ -28,6 +28,10 @@ struct fb_sim {
     long long pitch = 0;
     EnsembleDev E{};
     cudaStream_t stream = nullptr;
+    double* d_snap = nullptr;                          // device snapshot of x for fb_get_state_async
+    cudaEvent_t snap_ready = nullptr, snap_done = nullptr;
+    cudaStream_t snap_stream = nullptr;                // its own stream: the input copy stream must not queue behind a read-back
+    bool snap_pending = false;
     cudaStream_t copy_stream = nullptr;                // host-to-device staging of per-member inputs (fb_set_input)
     double* d_stage[FB_U__COUNT] = {};                 // lazily allocated staging rows
     cudaEvent_t stage_consumed[FB_U__COUNT] = {};
@@ -348,6 +352,9 @@ int32_t fb_destroy(fb_handle s) {
     if (!s) return FB_OK;
     cudaSetDevice(s->cfg.device);
     cudaStreamSynchronize(s->stream);
+    if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
+    if (s->snap_stream) { cudaStreamSynchronize(s->snap_stream); cudaStreamDestroy(s->snap_stream); }
+    cudaFree(s->d_snap); if (s->snap_ready) cudaEventDestroy(s->snap_ready); if (s->snap_done) cudaEventDestroy(s->snap_done);
     EnsembleDev& E = s->E;
     cudaFree(E.x); cudaFree(E.u); cudaFree(E.stall); cudaFree(E.eng); cudaFree(E.status); cudaFree(E.ctl); cudaFree(E.log);
     cudaFree(s->d_pack); cudaFree(s->d_geoid);
@@ -362,11 +369,12 @@ int32_t fb_destroy(fb_handle s) {
     return FB_OK;
 }
 
+int32_t fb_wait_state(fb_handle s);
 int32_t fb_sync(fb_handle s) {
     if (!s) return fail(FB_ERR_ARG, "null handle");
     CK(cudaSetDevice(s->cfg.device));
     CK(cudaStreamSynchronize(s->stream));
-    return FB_OK;
+    return fb_wait_state(s);
 }
 
 int32_t fb_load_tables(fb_handle s, const void* blob, size_t nbytes) {
@@ -668,6 +676,32 @@ int32_t fb_get_state(fb_handle s, double* x) {
     CK(cudaSetDevice(s->cfg.device));
     CK(cudaMemcpy2DAsync(x, sizeof(double) * s->E.n, s->E.x, sizeof(double) * s->pitch, sizeof(double) * s->E.n, s->nx, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
+    return FB_OK;
+}
+
+int32_t fb_wait_state(fb_handle s) {
+    if (!s) return fail(FB_ERR_ARG, "null handle");
+    if (s->snap_pending) { CK(cudaEventSynchronize(s->snap_done)); s->snap_pending = false; }
+    return FB_OK;
+}
+
+int32_t fb_get_state_async(fb_handle s, double* x) {
+    if (!s || !x) return fail(FB_ERR_ARG, "fb_get_state_async: null argument");
+    CK(cudaSetDevice(s->cfg.device));
+    int32_t rc = fb_wait_state(s);   // the snapshot buffer is free again once the previous copy has landed
+    if (rc != FB_OK) return rc;
+    if (!s->d_snap) {
+        CK(cudaMalloc(&s->d_snap, sizeof(double) * s->pitch * s->nx));
+        CK(cudaEventCreateWithFlags(&s->snap_ready, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s->snap_done, cudaEventDisableTiming));
+        CK(cudaStreamCreateWithFlags(&s->snap_stream, cudaStreamNonBlocking));
+    }
+    CK(cudaMemcpyAsync(s->d_snap, s->E.x, sizeof(double) * s->pitch * s->nx, cudaMemcpyDeviceToDevice, s->stream));
+    CK(cudaEventRecord(s->snap_ready, s->stream));
+    CK(cudaStreamWaitEvent(s->snap_stream, s->snap_ready, 0));
+    CK(cudaMemcpy2DAsync(x, sizeof(double) * s->E.n, s->d_snap, sizeof(double) * s->pitch, sizeof(double) * s->E.n, s->nx, cudaMemcpyDeviceToHost, s->snap_stream));
+    CK(cudaEventRecord(s->snap_done, s->snap_stream));
+    s->snap_pending = true;
     return FB_OK;
 }
 

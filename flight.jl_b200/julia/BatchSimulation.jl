@@ -11,7 +11,7 @@
 # There is no CPU fallback: every call goes to libflightbatch.so and throws FlightBatchError on a non-zero return.
 module BatchSimulations
 
-export BatchSimulation, FlightBatchError, init!, step!, run!, setinput!, getinput, getoutput, schedule_inputs!, set_segment!, BatchTimeSeries, BatchLinearizedSS, getstate, getinputs, getoutputs, setinputs!, setstate!,
+export BatchSimulation, state_async!, wait_state, FlightBatchError, init!, step!, run!, setinput!, getinput, getoutput, schedule_inputs!, set_segment!, BatchTimeSeries, BatchLinearizedSS, getstate, getinputs, getoutputs, setinputs!, setstate!,
        status, stats, linearize, TimeSeriesColumn
 
 const libflightbatch = get(ENV, "FLIGHTBATCH_LIB", joinpath(@__DIR__, "..", "libflightbatch.so"))
@@ -103,6 +103,17 @@ end
 step!(sim::BatchSimulation, Δt::Real = sim.dt) = check(ccall((:fb_step, libflightbatch), Int32, (Ptr{Cvoid}, Float64), sim.handle, Δt))
 run!(sim::BatchSimulation) = check(ccall((:fb_run, libflightbatch), Int32, (Ptr{Cvoid},), sim.handle))
 Base.wait(sim::BatchSimulation) = check(ccall((:fb_sync, libflightbatch), Int32, (Ptr{Cvoid},), sim.handle))
+
+"""
+    state_async!(x, sim); ...; wait_state(sim)
+
+Pipelined read of `sim.x` into the caller's `N x nx` matrix `x` (page-locked memory for a truly asynchronous copy):
+the state as of the work submitted so far is snapshotted on the device and copied while later `step!` calls run.
+The caller keeps `x` alive (`GC.@preserve`) until `wait_state` returns.
+"""
+state_async!(x::Matrix{Float64}, sim::BatchSimulation) =
+    check(ccall((:fb_get_state_async, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{Float64}), getfield(sim, :handle), x))
+wait_state(sim::BatchSimulation) = check(ccall((:fb_wait_state, libflightbatch), Int32, (Ptr{Cvoid},), getfield(sim, :handle)))
 
 function Base.getproperty(sim::BatchSimulation, s::Symbol)
     if s === :t

@@ -213,6 +213,13 @@ int32_t fb_time(fb_handle h, double* t, int64_t* n_steps);
 /* ---- read-back ------------------------------------------------------------------------- */
 int32_t fb_nx(fb_handle h, int32_t* nx);
 int32_t fb_get_state(fb_handle h, double* x);                       /* sim.x : [nx][N] */
+/* Pipelined read of sim.x (no reference counterpart: the reference reads its own memory). The state as of the work
+ * submitted so far is snapshotted on the device and copied to `x` (pinned host memory, or the copy is not
+ * asynchronous) on a stream of its own while later fb_step calls already run; `x` is valid after fb_wait_state (or any
+ * later fb_get_state_async / fb_sync / fb_destroy on the handle). One read may be in flight per handle: a second
+ * call first waits for the previous one. */
+int32_t fb_get_state_async(fb_handle h, double* x);
+int32_t fb_wait_state(fb_handle h);
 int32_t fb_get_discrete(fb_handle h, uint8_t* stall, uint8_t* eng_state);
 int32_t fb_get_output(fb_handle h, int32_t field, double* out);     /* sim.y.<field> : [N] */
 int32_t fb_status(fb_handle h, int32_t* status);

@@ -70,3 +70,33 @@ def test_handover_path_equals_complete_kernel(fb):
           "statuses", np.bincount(a["status"], minlength=7).tolist())
     assert err[:, air].max() < 1e-9
     assert err[:, run & low].max() < 1e-5      # ground-contact conditioning
+
+
+def test_pipelined_state_read_matches_blocking_read(fb):
+    """fb_get_state_async snapshots the state as of the work submitted so far: a read issued after step k and collected
+    after step k+1 has been launched must equal the blocking read taken after step k (bit for bit), not the later state."""
+    import torch
+    import bench
+    n = 4096
+    p = bench.member_params(0, n)
+
+    def make():
+        sim = fb.BatchSimulation(fb.SimpleWorld(fb.Cessna172Sv0(fb.WA())), n=n, dt=0.01, t_end=1e4, steps_per_launch=50)
+        sim.init(fb.C172.TrimParameters(**p))
+        sim.set_input("elevator", sim.get_input("elevator") + 0.05)
+        return sim
+    a, b = make(), make()
+    bufs = [torch.empty((a.nx, n), dtype=torch.float64).pin_memory().numpy() for _ in range(2)]
+    ref = []
+    for k in range(4):
+        a.step(0.5); ref.append(a.x.copy())
+    got = []
+    for k in range(4):
+        b.step(0.5)
+        b.get_state_async(bufs[k % 2])      # waits for read k-1 first, so bufs[(k-1) % 2] is complete here
+        if k > 0:
+            got.append(bufs[(k - 1) % 2].copy())
+    b.wait_state(); got.append(bufs[3 % 2].copy())
+    for k in range(4):
+        assert np.array_equal(ref[k], got[k]), k
+    a.close(); b.close()
