@@ -164,10 +164,11 @@ struct StepShape {
     static constexpr size_t SMEM = TBL + sizeof(double) * (NCOL + NSLOT) * T;
 };
 #define FB_RESUME_PENDING (1 << 30)
+#define FB_MW_MAX 32            // member-warps a CTA can time-slice over its hardware warps (step_kernel)
 template <int VAR, int KIN, bool AIR, int CAP = FB_STEP_BLOCK>
 __global__ void __launch_bounds__((StepShape<VAR, KIN, AIR, CAP>::T), 1)
-step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic_every, double Dt,
-            unsigned long long* rhs_count, int* resume, int resume_mode, unsigned* ground_count) {
+step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt, int periodic_every, double Dt,
+            unsigned long long* rhs_count, int* resume, int resume_mode, unsigned* ground_count, int mpc, int chunk) {
     typedef Lay<VAR, KIN, AIR> L;
     typedef Lay<VAR, KIN, false> LF;
     constexpr int NX = L::NX;
@@ -177,22 +178,45 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
     constexpr int T_ = T;
     if (resume_mode && *ground_count == 0) return;        // nobody was handed over by the AIR launch (CTA-uniform)
     constexpr int TBL = StepShape<VAR, KIN, AIR, CAP>::TBL;
+    __shared__ int chunk_done_s[FB_MW_MAX];
+    if (threadIdx.x < FB_MW_MAX) chunk_done_s[threadIdx.x] = 0;
     stage_tables(smem_tb, E.tables.pack, TBL);
     GainsShared gains; gains.base = nullptr; gains.sbase = (unsigned)__cvta_generic_to_shared(smem) + FB_TB_BYTES;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= E.n) return;
+    // Work distribution: the CTA owns `mpc` consecutive members = MW member-warps, and the launch is cut into C chunks
+    // of `chunk` steps. Task j = (member-warp j % MW, chunk j / MW); hardware warp w runs tasks w, w + HW, ... Each task
+    // is the whole body below on its members (state from HBM, `chunk` steps, state back to HBM). With mpc = blockDim
+    // and chunk = n_steps this is the plain one-thread-per-member launch. With MW > HW it time-slices the member-warps
+    // over the 12 warps the register file holds, so an ensemble of e.g. 443 members per SM takes 14/12 of a wave
+    // instead of two waves (or a 14-warp shape at 128 registers). A task's predecessor (same members, previous chunk)
+    // sits MW tasks earlier in the sequence, i.e. always in an earlier round of some warp: the wait below cannot deadlock.
+    const int lane = threadIdx.x & 31, HW = blockDim.x >> 5;
+    const long long cta_base = (long long)blockIdx.x * mpc;
+    const int MW = (int)((min((long long)mpc, E.n - cta_base) + 31) / 32);
+    const int C = (n_steps_launch + chunk - 1) / chunk;
+    volatile int* chunk_done = chunk_done_s;
+    for (int task = threadIdx.x >> 5; task < MW * C; task += HW) {
+    const int mw = task % MW, ck = task / MW;
+    if (C > 1) {
+        while (chunk_done[mw] < ck) __nanosleep(64);
+        __threadfence_block(); __syncwarp();
+    }
+    do {   // one task; `break` leaves it
+    long long step0 = step0_launch + (long long)ck * chunk;
+    int n_steps = min(chunk, n_steps_launch - ck * chunk);
+    const long long i = cta_base + (long long)mw * 32 + lane;
+    if (i >= E.n) break;
     int status = E.status[i];
     bool pending = false;
     if (resume_mode) {
         int r = resume[i];
-        if (r < 0) return;
+        if (r < 0) break;
         pending = (r & FB_RESUME_PENDING) != 0;
         int d0 = r & (FB_RESUME_PENDING - 1);
         step0 += d0; n_steps -= d0;
     } else if (status != FB_ST_RUNNING) {
         if (AIR) resume[i] = -1;
-        return;
-    }
+        break;
+    } else if (AIR && ck > 0 && resume[i] >= 0) break;   // handed over in an earlier chunk of this launch
     MemberIn ug; ug.u = E.u + i; ug.pitch = E.pitch;
     double* sx = smem + TBL / 8 + threadIdx.x;
     double* sacc = sx + NX * T;
@@ -204,7 +228,7 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
         double nz = 0.0;
 #pragma unroll
         for (int c = 0; c < 6; c++) nz += fabs(E.x[(long long)(LF::LDG + c) * E.pitch + i]);
-        if (nz != 0.0) { resume[i] = 0; atomicAdd(ground_count, 1u); return; }
+        if (nz != 0.0) { resume[i] = ck * chunk; atomicAdd(ground_count, 1u); break; }
     }
     int stall = E.stall[i], eng = E.eng[i];
     long long ev_cur = E.ev_off ? E.ev_off[i] + E.ev_cursor[i] : 0;
@@ -247,7 +271,7 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
         if (y.err) {
             if (AIR && y.err == FB_NEED_COMPLETE) {
                 // sx is the step-start state (stages 1..3 and re-evaluations) or x* with this step's callbacks pending
-                handover = done | ((sink.stage == 4) ? FB_RESUME_PENDING : 0);
+                handover = (ck * chunk + done) | ((sink.stage == 4) ? FB_RESUME_PENDING : 0);
             } else status = y.err;
             break;
         }
@@ -350,6 +374,12 @@ step_kernel(EnsembleDev E, long long step0, int n_steps, double dt, int periodic
     else if (!resume_mode && gnd_seen) atomicAdd(ground_count, 1u);
     // RHS evaluations of this launch: k1 of the first step, then k2..k4 and f(x*) per step, plus re-evaluations
     if (rhs_count) atomicAdd(rhs_count, (unsigned long long)max(0, 4 * done + n_reeval + (pending ? -3 : 1) + (handover >= 0 ? (sink.stage & 3) : 0)));
+    } while (0);
+    if (C > 1) {   // publish the chunk: the next task on these members may run on another warp of this CTA
+        __threadfence_block(); __syncwarp();
+        if (lane == 0) chunk_done[mw] = ck + 1;
+    }
+    }
 }
 
 // f_ode!(world) at the current state: test hook + reinit! evaluation

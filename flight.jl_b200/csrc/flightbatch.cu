@@ -59,6 +59,7 @@ struct fb_sim {
     bool air_mode = true;
     bool force_complete = false;
     bool air_wide = false;           // airborne kernel shape: FB_STEP_BLOCK_WIDE threads (one-wave ensembles) or FB_STEP_BLOCK
+    int air_mpc = 0;                 // > step_block_air: time-sliced airborne launches, this many members per CTA (fb_kernels.cuh)
 };
 
 // ------------------------------------------------------------------------------------ kernel dispatch
@@ -73,13 +74,27 @@ template <int VAR, int KIN> struct Ops {
         int grid = (int)((s->E.n + T - 1) / T);
         if (s->air_mode) {
             int Ta = s->step_block_air;
-            int grid_a = (int)((s->E.n + Ta - 1) / Ta);
+            // time-sliced shape (fb_kernels.cuh): mpc members per CTA on Ta threads, in chunks of air_chunk steps — only
+            // when the launch is long enough to be cut up; otherwise (and always for the plain shapes) one thread per member
+            int mpc = s->air_mpc > Ta ? s->air_mpc : Ta, chunk = n > 0 ? n : 1;
+            if (s->air_mpc > Ta && n >= 8) {
+                // cut the launch into C chunks so that the MW * C tasks fill whole rounds of the HW warps; a chunk start
+                // costs one extra right-hand side (no k1 carried over), i.e. a quarter of a step
+                const int MW = s->air_mpc / 32, HW = Ta / 32;
+                double best = 1e300;
+                for (int C = 2; C <= 16 && C * 4 <= n; C++) {
+                    const int ch = (n + C - 1) / C, Cr = (n + ch - 1) / ch;
+                    const double cost = (double)((MW * Cr + HW - 1) / HW) * (ch + 0.25);
+                    if (cost < best) { best = cost; chunk = ch; }
+                }
+            }
+            int grid_a = (int)((s->E.n + mpc - 1) / mpc);
             if (s->air_wide)
                 step_kernel<VAR, KIN, true, FB_STEP_BLOCK_WIDE><<<grid_a, Ta, StepShape<VAR, KIN, true, FB_STEP_BLOCK_WIDE>::SMEM, s->stream>>>(
-                    s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_resume, 0, s->d_ground);
+                    s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_resume, 0, s->d_ground, mpc, chunk);
             else
                 step_kernel<VAR, KIN, true><<<grid_a, Ta, StepShape<VAR, KIN, true>::SMEM, s->stream>>>(
-                    s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_resume, 0, s->d_ground);
+                    s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_resume, 0, s->d_ground, mpc, chunk);
             { CompleteLaunch a{grid, T, s->stream, s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_resume, 1, s->d_ground};
               e = fb_complete_launch(VAR, s->cfg.kinematics, a); if (e != cudaSuccess) return e; }
             *launched = 2;
@@ -332,6 +347,21 @@ int32_t fb_create(const fb_config* cfg, fb_handle* out) {
         // cost model: a launch of the wide (128-register) shape takes ~1.45x as long as one of the 168-register shape
         s->air_wide = (double)waves_w * 1.45 < (double)waves_n;
         s->step_block_air = s->air_wide ? Tw : Tn;
+        // Third option, for ensembles of more than one and at most FB_MW_MAX member-warps per SM: ONE persistent CTA
+        // per SM of the 168-register shape that time-slices its MW member-warps over its 12 warps in chunks of 10 steps:
+        // ceil(MW * C / 12) / C waves (+ ~3 % for the k1 re-evaluated at every chunk start).
+        {
+            const int tmax = FB_DISPATCH(s, step_tmax)(1), hw = tmax / 32;
+            const long long per_sm = (N + sms - 1) / sms;
+            const int mw = (int)((per_sm + 31) / 32), C = 10;
+            const double cost_plain = s->air_wide ? (double)waves_w * 1.45 : (double)waves_n;
+            const double cost_sliced = 1.03 * (double)((mw * C + hw - 1) / hw) / C;
+            const char* env = getenv("FLIGHTBATCH_SLICED");   // diagnostic switch: 0 = never, 1 = whenever possible
+            bool ok = mw > hw && mw <= FB_MW_MAX;
+            bool use = ok && cost_sliced < cost_plain;
+            if (env && ok) use = atoi(env) != 0;
+            if (use) { s->air_wide = false; s->step_block_air = tmax; s->air_mpc = mw * 32; }
+        }
     }
     // FLIGHTBATCH_KERNEL=complete pins the complete kernel (no airborne instantiation, no hand-over): a diagnostic switch used
     // by the tests to check that the two launch paths produce the same trajectories
