@@ -100,7 +100,7 @@ def doublet_events(n, ele0, ail0, ele_f, ail_f):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -108,7 +108,7 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
