@@ -110,7 +110,10 @@ struct RkSink {
         sacc[acol(c) * T] = fma(cb, k, a);
         xs[c] = fma(cx, k, xv);
     }
-    FB_DEV double act(int, int c, const double*, double cmd) const { return fma(pa, sx[c * T] - cmd, cmd); }
+    FB_DEV double act(int, int c, const double*, double cmd) const {   // stage 0 (and 4): the step-start value itself, exactly
+        const double xv = sx[c * T];
+        return (stage & 3) ? fma(pa, xv - cmd, cmd) : xv;
+    }
     FB_DEV void put_act(int, double, double) {}
     template <int NX, class Cmd>
     FB_DEV void combine(double h6, double act_r, const Cmd& cmd) {   // x* = x + dt/6 (k1 + 2 k2 + 2 k3 + k4); xs = x*
