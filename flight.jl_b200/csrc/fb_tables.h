@@ -62,11 +62,14 @@ enum { FB_AX_GE = 0, FB_AX_DF, FB_AX_CD_A, FB_AX_CL_A, FB_AX_N_STD, FB_AX_N_WOT,
 #define FB_GEOID_NLAT 721
 #define FB_GEOID_NLON 1441
 
-// gain schedules (lib/FlightApps/src/c172/c172x/control/data/*.h5): [7 EAS][4 h][P] row-major per schedule, the ten
+// gain schedules (lib/FlightApps/src/c172/c172x/control/data/*.h5): [7 EAS][4 h][P] row-major per schedule (P = gs_P, the record stride), the ten
 // schedules concatenated in GS order right behind the table pack in ONE device buffer, so that the integrator of the
 // fly-by-wire variants stages pack + schedules into shared memory with a single bulk copy.
 enum { GS_TE2TE = 0, GS_TV2TE, GS_VH2TE, GS_AR2AR, GS_PHIBETA2AR, GS_Q2E, GS_C2THETA, GS_V2T, GS_P2PHI, GS_CHI2PHI, GS_COUNT };
-__host__ __device__ constexpr int gs_P(int s) { return s < GS_Q2E ? (s == GS_VH2TE ? 39 : 36) : 4; }   // values per design point
+__host__ __device__ constexpr int gs_NV(int s) { return s < GS_Q2E ? (s == GS_VH2TE ? 39 : 36) : 4; }  // values per design point
+// Record stride in doubles. Odd for the LQR schedules: members of a warp sit in different cells, i.e. read the same value
+// of different records; with a 36-double stride every record starts on one of four shared-memory bank positions.
+__host__ __device__ constexpr int gs_P(int s) { return s < GS_Q2E ? (gs_NV(s) | 1) : 4; }
 __host__ __device__ constexpr int gs_off(int s) { int o = 0; for (int i = 0; i < s; i++) o += 28 * gs_P(i); return o; }
 #define FB_GS_BYTES ((gs_off(GS_COUNT) * 8 + 15) / 16 * 16)
 

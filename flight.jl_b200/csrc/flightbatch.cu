@@ -484,8 +484,8 @@ int32_t fb_load_tables(fb_handle s, const void* blob, size_t nbytes) {
     std::vector<double> gpack(FB_GS_BYTES / 8, 0.0);   // staging must outlive the asynchronous copy
     for (int i = 0; i < GS_COUNT; i++) {
         const BlobSec* sec = find(gnames[i]);
-        if (!sec || sec->dtype != 0 || sec->nbytes != (uint64_t)28 * gs_P(i) * 8) return fail(FB_ERR_ARG, std::string("fb_load_tables: bad or missing section ") + gnames[i]);
-        memcpy(gpack.data() + gs_off(i), b + sec->off, sec->nbytes);
+        if (!sec || sec->dtype != 0 || sec->nbytes != (uint64_t)28 * gs_NV(i) * 8) return fail(FB_ERR_ARG, std::string("fb_load_tables: bad or missing section ") + gnames[i]);
+        for (int pt = 0; pt < 28; pt++) memcpy(gpack.data() + gs_off(i) + pt * gs_P(i), b + sec->off + (size_t)pt * gs_NV(i) * 8, (size_t)gs_NV(i) * 8);
     }
     CK(cudaMemcpyAsync((char*)s->d_pack + FB_TB_BYTES, gpack.data(), FB_GS_BYTES, cudaMemcpyHostToDevice, s->stream));
     CK(cudaStreamSynchronize(s->stream));
