@@ -227,8 +227,8 @@ FB_DEV double geoid_height(const float* __restrict__ g, double lat, double lon) 
     return lerp(lerp(f00, f10, u), lerp(f01, f11, u), w);
 }
 FB_DEV double geoid_at_n(const float* __restrict__ g, d3 n) {
-    double lat = atan2(n.z, fb_sqrt(fma(n.x, n.x, n.y * n.y)));
-    double lon = atan2(n.y, n.x);
+    double lat = fb_atan2(n.z, fb_sqrt(fb_max(fma(n.x, n.x, n.y * n.y), 1e-280)));
+    double lon = fb_atan2(n.y, n.x);
     return geoid_height(g, lat, lon);
 }
 
@@ -332,11 +332,25 @@ FB_DEV double get_mu(double mu_s, double mu_d, double v) {  // landinggear.jl:17
     return k * mu_d + (1.0 - k) * mu_s;
 }
 
+// sin and cos of a small angle (|x| <= pi/6: truncation below 5e-20 and 2e-18), no argument reduction, no slow path
+FB_DEV void sincos_small(double x, double& s, double& c) {
+    const double x2 = x * x;
+    double ps = fma(x2, -1.0 / 1307674368000.0, 1.0 / 6227020800.0);
+    ps = fma(ps, x2, -1.0 / 39916800.0); ps = fma(ps, x2, 1.0 / 362880.0); ps = fma(ps, x2, -1.0 / 5040.0);
+    ps = fma(ps, x2, 1.0 / 120.0); ps = fma(ps, x2, -1.0 / 6.0);
+    s = fma(ps * x2, x, x);
+    double pc = fma(x2, -1.0 / 87178291200.0, 1.0 / 479001600.0);
+    pc = fma(pc, x2, -1.0 / 3628800.0); pc = fma(pc, x2, 1.0 / 40320.0); pc = fma(pc, x2, -1.0 / 720.0);
+    pc = fma(pc, x2, 1.0 / 24.0); pc = fma(pc, x2, -0.5);
+    c = fma(pc, x2, 1.0);
+}
+
 // kinematic data shared by the subsystems of one RHS evaluation
 struct Kin { q4 q_nb, q_eb; d3 n_e, r_eb_e, w_wb_b, w_eb_b, v_eb_b, v_eb_n; double h_e, h_o, lat, lon; };
 
-// one landing-gear unit (strut + contact). Adds its wrench to (F, tau) in body axes. Off the airborne fast path,
-// so it keeps IEEE divisions: wheel speeds and damper rates pass through zero here. Inlined ONCE, inside the
+// one landing-gear unit (strut + contact). Adds its wrench to (F, tau) in body axes. Fast reciprocals / square roots
+// where the operand is bounded away from zero (direction cosines of a strut that has not crashed, friction
+// coefficients); IEEE operations where a wheel speed can pass through zero (castoring nose wheel). Inlined ONCE, inside the
 // non-unrolled loop over the three legs of the RHS: an out-of-line copy would receive the kinematic data through
 // local memory (~25 L2 round trips per leg), three inlined copies would triple the code the I-cache has to hold.
 FB_DEV void ldg_unit(const Kin& k, const float* __restrict__ geoid, double elev, int surface,
@@ -366,16 +380,16 @@ FB_DEV void ldg_unit(const Kin& k, const float* __restrict__ geoid, double elev,
         q4 q_en = qmul(k.q_eb, qconj(k.q_nb));          // product first, then rotate: keeps the reference's norm defect
         d3 ut_e = qrot(q_en, e3);                       // terrain normal (NED down) in ECEF: q_en(0,0,1)
         double ut_ks = dot(ut_e, ks_e);
-        double l = dot(ut_e, r_st_e) / ut_ks;
-        double alpha_ts = acos(fmax(fmin(ut_ks, 1.0), -1.0));
-        bool crash_angle = alpha_ts * (180.0 / FB_PI) > 60.0;
+        double l = dot(ut_e, r_st_e) * fb_rcp(ut_ks);
+        // acos(ut_ks) in degrees > 60 (landinggear.jl:331-339) is ut_ks <= 1/2: acos(0.5) rounds to 60.00000000000001
+        bool crash_angle = ut_ks <= 0.5;
         if (crash_angle) out.crash |= (1 << (2 * leg));
-        double xi = fmin(0.0, l);
+        double xi = fb_min(0.0, l);
         r_bc_b = mk3(r_bs_b.x, r_bs_b.y, r_bs_b.z + xi);
         d3 v_b = k.v_eb_b + cross(k.w_eb_b, r_bc_b);
         double cs = 1.0, sn = 0.0;  // wheel heading in strut axes
         if (has_steering) {
-            if (steering_engaged) sincos(steer_input * (FB_PI / 6), &sn, &cs);
+            if (steering_engaged) sincos_small(steer_input * (FB_PI / 6), sn, cs);   // |angle| <= pi/6: the input is Ranged(-1, 1)
             else { double r = sqrt(fma(v_b.x, v_b.x, v_b.y * v_b.y)); if (r > 0.0) { cs = v_b.x / r; sn = v_b.y / r; } }
         }
         // q_nw = q_nb o Rz(psi_sw) applied to e1 (landinggear.jl:291-296); Rz(psi) built from (cos, sin) by half angles
@@ -388,7 +402,7 @@ FB_DEV void ldg_unit(const Kin& k, const float* __restrict__ geoid, double elev,
         q_bc = qmul(qconj(k.q_nb), q_nc);
         d3 v_c_body = qrot_inv(q_bc, v_b);
         d3 ks_c = qrot_inv(q_bc, e3);
-        double xi_dot = -v_c_body.z / ks_c.z;
+        double xi_dot = -v_c_body.z * fb_rcp(ks_c.z);
         if (-xi_dot > 10.0 && !crash_angle) out.crash |= (2 << (2 * leg));
         double k_d = (xi_dot > 0.0) ? k_d_ext : k_d_cmp;
         F_dmp = -(k_s * xi + k_d * xi_dot);
@@ -402,21 +416,21 @@ FB_DEV void ldg_unit(const Kin& k, const float* __restrict__ geoid, double elev,
     double o0 = pi_lane(-vx, x0, 5.0, 400.0, 0.2, -1.0, 1.0, xd0);
     double o1 = pi_lane(-vy, x1, 5.0, 400.0, 0.2, -1.0, 1.0, xd1);
     if (wow) {
-        double norm_v = sqrt(fma(vx, vx, vy * vy));
+        double norm_v = fb_sqrt(fb_max(fma(vx, vx, vy * vy), 1e-280));   // 1e-140 for a wheel at rest: same mu, same psi_cv branch
         double mu_roll = get_mu(0.03, 0.02, norm_v);
         double mu_skid = (surface == 0) ? get_mu(0.75, 0.25, norm_v) : ((surface == 1) ? get_mu(0.25, 0.15, norm_v) : get_mu(0.075, 0.025, norm_v));
         double mu_x = fma(mu_skid - mu_roll, brake, mu_roll);
-        double psi_cv = (norm_v < 1e-3) ? (FB_PI / 2) : atan2(vy, vx);
+        double psi_cv = (norm_v < 1e-3) ? (FB_PI / 2) : fb_atan2(vy, vx);
         const double psi_skid = 10 * FB_PI / 180.0;
         double psi_abs = fabs(psi_cv);
         double mu_y;
-        if (psi_abs < psi_skid) mu_y = mu_skid * psi_abs / psi_skid;
-        else if (psi_abs > FB_PI - psi_skid) mu_y = mu_skid * (1.0 - (psi_skid + psi_abs - FB_PI) / psi_skid);
+        if (psi_abs < psi_skid) mu_y = mu_skid * psi_abs * (1.0 / psi_skid);
+        else if (psi_abs > FB_PI - psi_skid) mu_y = mu_skid * (1.0 - (psi_skid + psi_abs - FB_PI) * (1.0 / psi_skid));
         else mu_y = mu_skid;
-        double sc = fmin(1.0, mu_skid / sqrt(fma(mu_x, mu_x, mu_y * mu_y)));
+        double sc = fb_min(1.0, mu_skid * fb_rsqrt(fma(mu_x, mu_x, mu_y * mu_y)));   // mu_x >= mu_roll > 0
         d3 f_c = mk3(o0 * mu_x * sc, o1 * mu_y * sc, -1.0);
         d3 f_s = qrot(q_bc, f_c);
-        double Nf = fmax(0.0, -F_dmp / f_s.z);
+        double Nf = fb_max(0.0, -F_dmp * fb_rcp(f_s.z));
         d3 F_b = Nf * f_s;
         F = F + F_b;
         tau = tau + cross(r_bc_b, F_b);
