@@ -67,9 +67,9 @@ enum { FB_AX_GE = 0, FB_AX_DF, FB_AX_CD_A, FB_AX_CL_A, FB_AX_N_STD, FB_AX_N_WOT,
 // fly-by-wire variants stages pack + schedules into shared memory with a single bulk copy.
 enum { GS_TE2TE = 0, GS_TV2TE, GS_VH2TE, GS_AR2AR, GS_PHIBETA2AR, GS_Q2E, GS_C2THETA, GS_V2T, GS_P2PHI, GS_CHI2PHI, GS_COUNT };
 __host__ __device__ constexpr int gs_NV(int s) { return s < GS_Q2E ? (s == GS_VH2TE ? 39 : 36) : 4; }  // values per design point
-// Record stride in doubles. Odd for the LQR schedules: members of a warp sit in different cells, i.e. read the same value
-// of different records; with a 36-double stride every record starts on one of four shared-memory bank positions.
-__host__ __device__ constexpr int gs_P(int s) { return s < GS_Q2E ? (gs_NV(s) | 1) : 4; }
+// Record stride in doubles, odd: members of a warp sit in different cells, i.e. read the same value
+// of different records; with a 36-double (or 4-double) stride every record starts on one of four shared-memory bank positions.
+__host__ __device__ constexpr int gs_P(int s) { return gs_NV(s) | 1; }
 __host__ __device__ constexpr int gs_off(int s) { int o = 0; for (int i = 0; i < s; i++) o += 28 * gs_P(i); return o; }
 #define FB_GS_BYTES ((gs_off(GS_COUNT) * 8 + 15) / 16 * 16)
 
