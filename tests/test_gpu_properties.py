@@ -29,8 +29,8 @@ def _run(fb, n, i0, seconds, mixed=False):
 
 
 def test_sharding_and_launch_shape_do_not_change_trajectories(fb):
-    """65,536 members in one handle (one wave of the 448-thread airborne shape) against the same members in two handles of
-    32,768 (384-thread shape): the per-member result must not depend on the ensemble it is computed in. Different template
+    """65,536 members in one handle (time-sliced airborne launches: 14 member-warps per SM on 12 warps) against the same
+    members in two handles of 32,768 (plain 384-thread shape): the per-member result must not depend on the ensemble it is computed in. Different template
     instantiations may round differently (FMA contraction), so the bound is the parity tolerance, not bit equality."""
     n = 65536
     a = _run(fb, n, 0, 10.0)
