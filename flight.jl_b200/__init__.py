@@ -69,7 +69,7 @@ class fb_config(C.Structure):
     _fields_ = [("variant", C.c_int32), ("kinematics", C.c_int32), ("n_members", C.c_int64), ("member_offset", C.c_int64),
                 ("dt", C.c_double), ("Dt", C.c_double), ("t_start", C.c_double), ("t_end", C.c_double),
                 ("device", C.c_int32), ("log_every", C.c_int32), ("log_n_fields", C.c_int32), ("log_fields", C.c_int32 * 32),
-                ("steps_per_launch", C.c_int32)]
+                ("steps_per_launch", C.c_int32), ("log_flags", C.c_int32)]
 
 
 _DP = C.POINTER(C.c_double)
@@ -94,7 +94,9 @@ class fb_moments(C.Structure):
 EXPORTS = ["fb_api_version", "fb_last_error", "fb_create", "fb_load_tables", "fb_destroy", "fb_sync", "fb_init_trim", "fb_init",
            "fb_init_state", "fb_set_input", "fb_get_input", "fb_schedule_inputs", "fb_step", "fb_run", "fb_time", "fb_nx",
            "fb_get_state", "fb_get_state_async", "fb_wait_state", "fb_get_discrete", "fb_get_output", "fb_status", "fb_log_info", "fb_log_times", "fb_log_fetch",
-           "fb_stats", "fb_rhs", "fb_fstep", "fb_fperiodic", "fb_counters", "fb_linearize", "fb_linearize_dims", "fb_device_state", "fb_stream", "fb_measure_fp64_peak",
+           "fb_stats", "fb_log_stats_begin", "fb_log_stats_end", "fb_log_stats", "fb_comm_unique_id", "fb_comm_init", "fb_log_stats_allreduce", "fb_comm_time",
+           "fb_group_create", "fb_group_destroy", "fb_group_size", "fb_group_shard", "fb_group_load_tables", "fb_group_init_trim", "fb_group_set_input",
+           "fb_group_step", "fb_group_run", "fb_group_sync", "fb_group_get_state", "fb_group_status", "fb_group_log_stats", "fb_rhs", "fb_fstep", "fb_fperiodic", "fb_counters", "fb_linearize", "fb_linearize_dims", "fb_device_state", "fb_stream", "fb_measure_fp64_peak",
            "fb_lss_create", "fb_lss_destroy", "fb_lss_set_model", "fb_lss_from_linearize", "fb_lss_set_state", "fb_lss_get_state",
            "fb_lss_set_input", "fb_lss_get_input", "fb_lss_get_output", "fb_lss_step", "fb_lss_sync", "fb_lss_stream"]
 
@@ -133,6 +135,16 @@ def load_library():
         "fb_lss_set_state": (i32, [vp, _DP]), "fb_lss_get_state": (i32, [vp, _DP]), "fb_lss_set_input": (i32, [vp, _DP]),
         "fb_lss_get_input": (i32, [vp, _DP]), "fb_lss_get_output": (i32, [vp, _DP]), "fb_lss_step": (i32, [vp, dbl]),
         "fb_lss_sync": (i32, [vp]), "fb_lss_stream": (i32, [vp, C.POINTER(vp)]),
+        "fb_log_stats_begin": (i32, [vp, i64, i64]), "fb_log_stats_end": (i32, [vp, i32, C.POINTER(fb_moments)]),
+        "fb_log_stats": (i32, [vp, i32, i64, i64, C.POINTER(fb_moments)]),
+        "fb_comm_unique_id": (i32, [C.c_char_p]), "fb_comm_init": (i32, [vp, i32, i32, C.c_char_p]),
+        "fb_log_stats_allreduce": (i32, [vp]), "fb_comm_time": (i32, [vp, _DP, C.POINTER(i64)]),
+        "fb_group_create": (i32, [C.POINTER(fb_config), C.POINTER(i32), i32, C.POINTER(vp)]), "fb_group_destroy": (i32, [vp]),
+        "fb_group_size": (i32, [vp, C.POINTER(i32)]), "fb_group_shard": (i32, [vp, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]),
+        "fb_group_load_tables": (i32, [vp, C.c_char_p, C.c_size_t]), "fb_group_init_trim": (i32, [vp, C.POINTER(fb_trim_params_soa), _DP, _DP]),
+        "fb_group_set_input": (i32, [vp, i32, _DP, i64]), "fb_group_step": (i32, [vp, dbl]), "fb_group_run": (i32, [vp]), "fb_group_sync": (i32, [vp]),
+        "fb_group_get_state": (i32, [vp, _DP]), "fb_group_status": (i32, [vp, C.POINTER(i32)]),
+        "fb_group_log_stats": (i32, [vp, i32, i64, i64, C.POINTER(fb_moments)]),
     }
     for name in EXPORTS:
         f = getattr(lib, name)   # AttributeError if the library does not export a declared symbol
@@ -293,6 +305,37 @@ class C172:
     Init = Init
 
 
+def _make_config(world, n, dt, Dt, t_start, t_end, saveat, log_fields, device, member_offset, steps_per_launch, log_members, log_moments):
+    world = world if world is not None else SimpleWorld()
+    ac = world.aircraft
+    cfg = fb_config()
+    cfg.variant = ac.variant
+    cfg.kinematics = ac.kinematics.kin
+    cfg.n_members = int(n)
+    cfg.member_offset = int(member_offset)
+    cfg.dt = float(dt)
+    cfg.Dt = float(dt if Dt is None else Dt)
+    cfg.t_start = float(t_start)
+    cfg.t_end = float(t_end)
+    cfg.device = int(device)
+    fields = [OUTPUT_NAMES[f] if isinstance(f, str) else int(f) for f in log_fields]
+    cfg.log_every = 0 if (saveat is None or not fields) else max(1, int(round(saveat / dt)))
+    cfg.log_n_fields = len(fields)
+    for i, f in enumerate(fields):
+        cfg.log_fields[i] = f
+    cfg.steps_per_launch = int(steps_per_launch)
+    cfg.log_flags = (DEFS["FB_LOG_MEMBERS"] if log_members else 0) | (DEFS["FB_LOG_MOMENTS"] if log_moments else 0)
+    return cfg, fields
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it, the host distributes it, every rank passes it to comm_init)."""
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    _ck(lib.fb_comm_unique_id(buf), lib)
+    return buf.raw
+
+
 class _InputProxy:
     """sim.u.<field>: read returns an [N] array, assignment broadcasts a scalar or uploads an [N] array.
     Mirrors direct mutation of nested inputs in the reference (README.md:166)."""
@@ -330,36 +373,26 @@ class BatchSimulation:
     """N independent `Simulation(world; dt, Δt, t_start, t_end, saveat)` stepped in lock-step on one B200."""
 
     def __init__(self, world=None, n=1, dt=0.02, Dt=None, t_start=0.0, t_end=10000.0, saveat=None, log_fields=(),
-                 device=0, member_offset=0, steps_per_launch=0, tables_path=None):
+                 device=0, member_offset=0, steps_per_launch=0, tables_path=None, log_members=True, log_moments=True, _adopt=None):
+        """saveat / log_fields: the outputs saved every `saveat` seconds (TimeSeries(sim)); log_members=False keeps only the
+        ensemble moments of each sample (log_stats), log_moments=False only the per-member samples."""
         self._h = None
         self._lib = load_library()
-        world = world if world is not None else SimpleWorld()
-        ac = world.aircraft
-        cfg = fb_config()
-        cfg.variant = ac.variant
-        cfg.kinematics = ac.kinematics.kin
-        cfg.n_members = int(n)
-        cfg.member_offset = int(member_offset)
-        cfg.dt = float(dt)
-        cfg.Dt = float(dt if Dt is None else Dt)
-        cfg.t_start = float(t_start)
-        cfg.t_end = float(t_end)
-        cfg.device = int(device)
-        fields = [OUTPUT_NAMES[f] if isinstance(f, str) else int(f) for f in log_fields]
-        cfg.log_every = 0 if (saveat is None or not fields) else max(1, int(round(saveat / dt)))
-        cfg.log_n_fields = len(fields)
-        for i, f in enumerate(fields):
-            cfg.log_fields[i] = f
-        cfg.steps_per_launch = int(steps_per_launch)
+        cfg, fields = _make_config(world, n, dt, Dt, t_start, t_end, saveat, log_fields, device, member_offset, steps_per_launch,
+                                   log_members, log_moments)
         self.cfg = cfg
         self.n = int(n)
         self.dt = float(dt)
         self.log_fields = fields
-        h = C.c_void_p()
-        _ck(self._lib.fb_create(C.byref(cfg), C.byref(h)), self._lib)
-        self._h = h
-        blob = open(tables_path or TABLES_PATH, "rb").read()
-        _ck(self._lib.fb_load_tables(self._h, blob, len(blob)), self._lib)
+        self._owned = _adopt is None
+        if _adopt is None:
+            h = C.c_void_p()
+            _ck(self._lib.fb_create(C.byref(cfg), C.byref(h)), self._lib)
+            self._h = h
+            blob = open(tables_path or TABLES_PATH, "rb").read()
+            _ck(self._lib.fb_load_tables(self._h, blob, len(blob)), self._lib)
+        else:
+            self._h = _adopt      # a shard of a BatchGroup: the group owns the handle
         nx = C.c_int32()
         _ck(self._lib.fb_nx(self._h, C.byref(nx)), self._lib)
         self.nx = nx.value
@@ -368,7 +401,8 @@ class BatchSimulation:
 
     def close(self):
         if self._h is not None:
-            self._lib.fb_destroy(self._h)
+            if self._owned:
+                self._lib.fb_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -550,6 +584,49 @@ class BatchSimulation:
         _ck(self._lib.fb_stats(self._h, field, C.byref(m)), self._lib)
         return dict(count=m.count, sum=m.sum, sum_sq=m.sum_sq, min=m.min, max=m.max)
 
+    def log_stats_begin(self, first=0, count=None):
+        """Start the asynchronous fetch of the ensemble moments of log samples [first, first + count)."""
+        ns, nf = C.c_int64(), C.c_int32()
+        _ck(self._lib.fb_log_info(self._h, C.byref(ns), C.byref(nf)), self._lib)
+        count = ns.value - first if count is None else count
+        _ck(self._lib.fb_log_stats_begin(self._h, int(first), int(count)), self._lib)
+        self._stats_range = (int(first), int(count))
+
+    def log_stats_end(self):
+        """Wait for log_stats_begin: {field name: {count, sum, sum_sq, min, max, mean, std: arrays over the samples}}."""
+        first, count = self._stats_range
+        names = {v: k for k, v in OUTPUT_NAMES.items()}
+        out = {}
+        for f in self.log_fields:
+            m = (fb_moments * count)()
+            _ck(self._lib.fb_log_stats_end(self._h, int(f), m), self._lib)
+            d = dict(count=np.array([r.count for r in m], dtype=np.int64), sum=np.array([r.sum for r in m]), sum_sq=np.array([r.sum_sq for r in m]),
+                     min=np.array([r.min for r in m]), max=np.array([r.max for r in m]))
+            with np.errstate(invalid="ignore", divide="ignore"):
+                d["mean"] = d["sum"] / d["count"]
+                d["std"] = np.sqrt(np.maximum(d["sum_sq"] / d["count"] - d["mean"] ** 2, 0.0))
+            out[names[f]] = d
+        return out
+
+    def log_stats(self, first=0, count=None):
+        """Ensemble moments of the logged fields at log samples [first, first + count), accumulated inside the integrator as
+        each sample was taken (after log_stats_allreduce: over every shard of the ensemble)."""
+        self.log_stats_begin(first, count)
+        return self.log_stats_end()
+
+    def comm_init(self, n_ranks, rank, unique_id):
+        """Join the NCCL communicator of the ensemble-moment all-reduce (unique_id: the 128 bytes of comm_unique_id() of rank 0)."""
+        _ck(self._lib.fb_comm_init(self._h, int(n_ranks), int(rank), bytes(unique_id)), self._lib)
+
+    def log_stats_allreduce(self):
+        """All-reduce (NCCL, side stream, asynchronous) the moments of the log samples completed since the previous call."""
+        _ck(self._lib.fb_log_stats_allreduce(self._h), self._lib)
+
+    def comm_time_ms(self):
+        ms, n = C.c_double(), C.c_int64()
+        _ck(self._lib.fb_comm_time(self._h, C.byref(ms), C.byref(n)), self._lib)
+        return ms.value
+
     def linearize(self):
         """linearize(aircraft, trim) for every member (NED kinematics, trimmed state): dict of A [N, nx, nx], B [N, nx, nu],
         C [N, ny, nx], D [N, ny, nu] (row = output, column = perturbed variable) and x0, u0, y0, xdot0 [N, n]."""
@@ -588,6 +665,104 @@ class BatchSimulation:
         pitch = C.c_int64()
         _ck(self._lib.fb_device_state(self._h, C.byref(p), C.byref(pitch)), self._lib)
         return p.value, pitch.value
+
+
+class BatchGroup:
+    """One process driving several GPUs: the ensemble sharded in contiguous blocks over `devices`, host arrays global.
+    `shards[k]` is a BatchSimulation view of shard k (members offsets[k] .. offsets[k + 1]) for everything else."""
+
+    def __init__(self, world=None, n=1, devices=(0,), dt=0.02, Dt=None, t_start=0.0, t_end=10000.0, saveat=None, log_fields=(),
+                 steps_per_launch=0, tables_path=None, log_members=True, log_moments=True):
+        self._g = None
+        self._lib = load_library()
+        cfg, fields = _make_config(world, n, dt, Dt, t_start, t_end, saveat, log_fields, 0, 0, steps_per_launch, log_members, log_moments)
+        devs = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        g = C.c_void_p()
+        _ck(self._lib.fb_group_create(C.byref(cfg), devs, len(devices), C.byref(g)), self._lib)
+        self._g = g
+        blob = open(tables_path or TABLES_PATH, "rb").read()
+        _ck(self._lib.fb_group_load_tables(self._g, blob, len(blob)), self._lib)
+        self.n, self.dt, self.log_fields = int(n), float(dt), fields
+        self.shards, self.offsets = [], [0]
+        for k in range(len(devices)):
+            h, off, cnt = C.c_void_p(), C.c_int64(), C.c_int64()
+            _ck(self._lib.fb_group_shard(self._g, k, C.byref(h), C.byref(off), C.byref(cnt)), self._lib)
+            self.shards.append(BatchSimulation(world, n=cnt.value, dt=dt, Dt=Dt, t_start=t_start, t_end=t_end, saveat=saveat, log_fields=log_fields,
+                                               device=devices[k], member_offset=off.value, steps_per_launch=steps_per_launch,
+                                               log_members=log_members, log_moments=log_moments, _adopt=h))
+            self.offsets.append(off.value + cnt.value)
+        self.nx = self.shards[0].nx
+
+    def close(self):
+        if self._g is not None:
+            for s in self.shards:
+                s._h = None
+            self._lib.fb_group_destroy(self._g)
+            self._g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def init(self, init=None, **kw):
+        if init is None:
+            init = TrimParameters(**kw)
+        if not isinstance(init, TrimParameters):
+            raise TypeError("BatchGroup.init takes C172.TrimParameters (use shards[k].init for C172.Init)")
+        keep, p, v = [], fb_trim_params_soa(), init.values
+
+        def col(a):
+            a = np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), (self.n,)))
+            keep.append(a)
+            return _dp(a)
+        for k in ("lat", "lon", "h_e", "psi_nb", "EAS", "gamma_wb_n", "psi_wb_dot", "theta_wb_dot", "beta_a", "fuel_load", "mixture", "flaps"):
+            if k in v:
+                setattr(p, k, col(v[k]))
+        for j, k in enumerate(("m_pilot", "m_copilot", "m_lpass", "m_rpass", "m_baggage")):
+            if k in v:
+                p.payload[j] = col(v[k])
+        ts, cost = np.zeros((7, self.n)), np.zeros(self.n)
+        _ck(self._lib.fb_group_init_trim(self._g, C.byref(p), _dp(ts), _dp(cost)), self._lib)
+        return self.status() != DEFS["FB_ST_TRIM_FAILED"], ts, cost
+
+    def set_input(self, field, value):
+        field = INPUT_NAMES[field] if isinstance(field, str) else int(field)
+        a = np.asarray(value, dtype=np.float64)
+        if a.ndim == 0:
+            _ck(self._lib.fb_group_set_input(self._g, field, _dp(np.array([float(a)])), 0), self._lib)
+        else:
+            a = np.ascontiguousarray(a)
+            assert a.shape == (self.n,)
+            _ck(self._lib.fb_group_set_input(self._g, field, _dp(a), 1), self._lib)
+
+    def step(self, t_advance=None):
+        _ck(self._lib.fb_group_step(self._g, float(self.dt if t_advance is None else t_advance)), self._lib)
+
+    def run(self):
+        _ck(self._lib.fb_group_run(self._g), self._lib)
+
+    def sync(self):
+        _ck(self._lib.fb_group_sync(self._g), self._lib)
+
+    @property
+    def x(self):
+        out = np.empty((self.nx, self.n))
+        _ck(self._lib.fb_group_get_state(self._g, _dp(out)), self._lib)
+        return out
+
+    def status(self):
+        out = np.zeros(self.n, dtype=np.int32)
+        _ck(self._lib.fb_group_status(self._g, out.ctypes.data_as(C.POINTER(C.c_int32))), self._lib)
+        return out
+
+    def log_stats(self, field, first=0, count=1):
+        """Moments of one logged field over the WHOLE ensemble (in-library NCCL all-reduce over the shards) at samples [first, first + count)."""
+        field = OUTPUT_NAMES[field] if isinstance(field, str) else int(field)
+        m = (fb_moments * count)()
+        _ck(self._lib.fb_group_log_stats(self._g, field, int(first), int(count), m), self._lib)
+        return [dict(count=r.count, sum=r.sum, sum_sq=r.sum_sq, min=r.min, max=r.max) for r in m]
 
 
 # The reference's dotted path under the root `y` (what `TimeSeries(sim)` drills into, sim.jl:666-676) of every fb_output

@@ -120,7 +120,7 @@ struct GainCell {
 // the dominant stall of the fly-by-wire kernels); otherwise they are read from the device buffer.
 template <bool SH>
 struct GainT {
-    const double* p; unsigned a; double u, w;   // low corner's record: generic pointer, or shared-window address when SH
+    const double* p; unsigned a; double w00, w01, w10, w11;   // low corner's record (generic pointer, or shared-window address when SH), corner weights
     int P;
     FB_DEV double ld(int idx) const {
         if (SH) { double v; asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a + 8u * (unsigned)idx)); return v; }
@@ -128,7 +128,9 @@ struct GainT {
     }
     FB_DEV double operator()(int k) const {
         double f00 = ld(k), f01 = ld(P + k), f10 = ld(4 * P + k), f11 = ld(5 * P + k);
-        return (1.0 - u) * ((1.0 - w) * f00 + w * f01) + u * ((1.0 - w) * f10 + w * f11);
+// Four corner weights (formed once per schedule, gain()) instead of the nested form (1-u)((1-w) f00 + w f01) + u (...):
+        // one multiplication + three FMAs per value, same value to rounding
+        return fma(w11, f11, fma(w10, f10, fma(w01, f01, w00 * f00)));
     }
     template <int N>
     FB_DEV void batch(int k0, double* out) const {
@@ -140,7 +142,8 @@ template <bool SH>
 struct GainTables {       // the ten schedules, [7 EAS][4 h][P] each, concatenated (fb_tables.h)
     const double* base; unsigned sbase;
     FB_DEV GainT<SH> gain(int s, const GainCell& c) const {
-        GainT<SH> g; g.P = gs_P(s); g.u = c.u; g.w = c.w;
+        GainT<SH> g; g.P = gs_P(s);
+        { const double um = 1.0 - c.u, wm = 1.0 - c.w; g.w00 = um * wm; g.w01 = um * c.w; g.w10 = c.u * wm; g.w11 = c.u * c.w; }
         g.p = base + gs_off(s) + c.o * gs_P(s);
         g.a = sbase + 8u * (unsigned)(gs_off(s) + c.o * gs_P(s));
         return g;
@@ -158,7 +161,7 @@ struct PidGains {      // (k_p, k_i, k_d, tau_f) of a scheduled PID
 // PID f_periodic! (control.jl:431-471), β_p = β_d = 1; gains g = (k_p, k_i, k_d, τ_f)
 FB_DEV double pid_update(PidS& s, double k_p, double k_i, double k_d, double tau_f, double lo, double hi,
                          double input, int sat_ext, double Dt) {
-    double alpha = 1.0 / (tau_f + Dt);
+    double alpha = fb_rcp(tau_f + Dt);
     bool halted = (isign(input * (double)s.sat) > 0) || (isign(input * (double)sat_ext) > 0);
     double x_i = s.xi + Dt * k_i * input * (halted ? 0.0 : 1.0);
     double x_d = alpha * tau_f * s.xd + Dt * alpha * k_d * input;
@@ -224,7 +227,7 @@ FB_DEV void lqr_reset(LqrS& s, const G& g, double lo0, double lo1, double Dt) {
 // f_periodic!(ControlLawsLon) — c172x_ctl.jl:286-446
 template <class U, class GT>
 FB_CTL_FN void lon_periodic(CtlState& cs, const YFull& v, int wow, const U& u,
-                                          const GT& T, double Dt, int mode_req) {
+                                          const GT& T, double Dt, int mode_req, const GainCell& c) {
     const double EAS = v.EAS, h_e = v.h_e, q = v.w_wb_b.y, r = v.w_wb_b.z, theta = v.theta, phi = v.phi;
     const double clm = -v.v_eb_n.z;
     const double h_ref = u(FB_U_LON_H_REF), EAS_ref = u(FB_U_LON_EAS_REF);
@@ -250,7 +253,6 @@ FB_CTL_FN void lon_periodic(CtlState& cs, const YFull& v, int wow, const U& u,
     const bool q2e_en = te2te_en && mode != LON_SAS;
     const bool t2q_en = mode == LON_THR_THETA || mode == LON_EAS_THETA || mode == LON_EAS_CLM;
     const bool v2t_en = mode >= LON_EAS_Q && mode <= LON_EAS_CLM;
-    GainCell c; c.locate(EAS, h_e);
     const double xred[8] = {v.w_eb_b.y, theta, EAS, v.alpha, v.alpha_filt, v.eng_n, v.act_pos[0], v.act_pos[2]};   // XLonRed :132-147
     if (te2te_en) {
         const int sat_thr = cs.te2te.sat[0], sat_ele = cs.te2te.sat[1];
@@ -270,7 +272,11 @@ FB_CTL_FN void lon_periodic(CtlState& cs, const YFull& v, int wow, const U& u,
                 }
                 double theta_dot_ref = 1.0 * (theta_ref - theta);
                 double phi_bnd = clampd(phi, -FB_PI / 3, FB_PI / 3);
-                q_ref = 1.0 / cos(phi_bnd) * theta_dot_ref + r * tan(phi_bnd);
+                // 1 / cos(phi) * theta_dot_ref + r * tan(phi) (c172x_ctl.jl:375-377): sin and cos of |phi| <= pi/3 by the
+                // double-angle identities from the small-angle series at phi / 2
+                double sh, ch; sincos_small(0.5 * phi_bnd, sh, ch);
+                const double sp = 2.0 * sh * ch, cp = fma(-2.0 * sh, sh, 1.0), icp = fb_rcp(cp);
+                q_ref = fma(icp, theta_dot_ref, r * (sp * icp));
             }
             double io = int_update(cs.q2e_int, q_ref - q, sat_ele, Dt);
             elevator_ref = pid_update(cs.q2e_pid, g.k_p, g.k_i, g.k_d, g.tau_f, -INFINITY, INFINITY, io, sat_ele, Dt);
@@ -300,8 +306,8 @@ FB_DEV double wrap_to_pi(double x) { return x + 2.0 * FB_PI * floor((FB_PI - x) 
 // f_periodic!(ControlLawsLat) — c172x_ctl.jl:880-983
 template <class U, class GT>
 FB_CTL_FN void lat_periodic(CtlState& cs, const YFull& v, int wow, const U& u,
-                                          const GT& T, double Dt, int mode_req) {
-    const double EAS = v.EAS, h_e = v.h_e, p = v.w_wb_b.x;
+                                          const GT& T, double Dt, int mode_req, const GainCell& c) {
+    const double EAS = v.EAS, p = v.w_wb_b.x;
     const int mode_prev = cs.lat_mode;
     const int mode = wow ? LAT_DIRECT : mode_req;
     double aileron_ref = clampd(u(FB_U_LAT_AILERON_AXIS) + u(FB_U_LAT_AILERON_OFFSET), -1.0, 1.0);
@@ -309,7 +315,6 @@ FB_CTL_FN void lat_periodic(CtlState& cs, const YFull& v, int wow, const U& u,
     double aileron_cmd = aileron_ref, rudder_cmd = rudder_ref;
     double phi_ref = u(FB_U_LAT_PHI_REF);
     const double xlat[8] = {v.w_eb_b.x, v.w_eb_b.z, v.phi, EAS, v.beta, v.beta_filt, v.act_pos[1], v.act_pos[3]};   // XLatRed :767-779
-    GainCell c; c.locate(EAS, h_e);
     if (mode == LAT_SAS) {
         const auto g = T.gain(GS_AR2AR, c);
         lqr_update<8>(cs.ar2ar, g, xlat, v.act_cmd[1], v.act_cmd[3], aileron_ref, rudder_ref, -1.0, -1.0, Dt, aileron_cmd, rudder_cmd);   // Zar :806-810
@@ -378,10 +383,12 @@ FB_GDC_FN void gdc_periodic(const CtlState& cs, double lat, double lon, double h
 }
 
 static __device__ __noinline__ void lon_periodic_ool(CtlState& cs, const YFull& v, int wow, const MemberIn& u, const FbDeviceTables& T, double Dt, int mode_req) {
-    lon_periodic(cs, v, wow, u, gains_global(T), Dt, mode_req);
+    GainCell c; c.locate(v.EAS, v.h_e);
+    lon_periodic(cs, v, wow, u, gains_global(T), Dt, mode_req, c);
 }
 static __device__ __noinline__ void lat_periodic_ool(CtlState& cs, const YFull& v, int wow, const MemberIn& u, const FbDeviceTables& T, double Dt, int mode_req) {
-    lat_periodic(cs, v, wow, u, gains_global(T), Dt, mode_req);
+    GainCell c; c.locate(v.EAS, v.h_e);
+    lat_periodic(cs, v, wow, u, gains_global(T), Dt, mode_req, c);
 }
 
 // The control- and guidance-law inputs of one member (fb_input 40..49, 60..68, 70) read in ONE batch of independent
@@ -390,12 +397,14 @@ static __device__ __noinline__ void lat_periodic_ool(CtlState& cs, const YFull& 
 struct CtlIn {
     MemberIn g;
     double lon[10], lat[9], gdc_mode;
-    FB_DEV void load() {
+    FB_DEV void load() {   // rows 40..49, 60..68, 70 of the member's input column: one pointer walked by the pitch
+        const double* p = g.u + (long long)FB_U_LON_MODE_REQ * g.pitch;
 #pragma unroll
-        for (int k = 0; k < 10; k++) lon[k] = g.raw(FB_U_LON_MODE_REQ + k);
+        for (int k = 0; k < 10; k++) { lon[k] = *p; p += g.pitch; }
+        p += 10 * g.pitch;
 #pragma unroll
-        for (int k = 0; k < 9; k++) lat[k] = g.raw(FB_U_LAT_MODE_REQ + k);
-        gdc_mode = g.raw(FB_U_GDC_MODE_REQ);
+        for (int k = 0; k < 9; k++) { lat[k] = *p; p += g.pitch; }
+        gdc_mode = p[g.pitch];
     }
     FB_DEV double operator()(int f) const {
         if (f >= FB_U_LON_MODE_REQ && f < FB_U_LON_MODE_REQ + 10) return lon[f - FB_U_LON_MODE_REQ];
@@ -416,10 +425,11 @@ template <class U>
 FB_DEV bool avionics_assign(const CtlState& cs, U& u) {
     bool ch = false;
     double v;
-    v = clampd(cs.thr_cmd, 0.0, 1.0);  if (u(FB_U_ACT_THROTTLE) != v) { u.set(FB_U_ACT_THROTTLE, v); ch = true; }
-    v = clampd(cs.ail_cmd, -1.0, 1.0); if (u(FB_U_ACT_AILERON) != v) { u.set(FB_U_ACT_AILERON, v); ch = true; }
-    v = clampd(cs.ele_cmd, -1.0, 1.0); if (u(FB_U_ACT_ELEVATOR) != v) { u.set(FB_U_ACT_ELEVATOR, v); ch = true; }
-    v = clampd(cs.rud_cmd, -1.0, 1.0); if (u(FB_U_ACT_RUDDER) != v) { u.set(FB_U_ACT_RUDDER, v); ch = true; }
+    // (the four commands are stored already saturated: lon_periodic / lat_periodic clamp them, f_init! starts them at 0)
+    v = cs.thr_cmd; if (u(FB_U_ACT_THROTTLE) != v) { u.set(FB_U_ACT_THROTTLE, v); ch = true; }
+    v = cs.ail_cmd; if (u(FB_U_ACT_AILERON) != v) { u.set(FB_U_ACT_AILERON, v); ch = true; }
+    v = cs.ele_cmd; if (u(FB_U_ACT_ELEVATOR) != v) { u.set(FB_U_ACT_ELEVATOR, v); ch = true; }
+    v = cs.rud_cmd; if (u(FB_U_ACT_RUDDER) != v) { u.set(FB_U_ACT_RUDDER, v); ch = true; }
     return ch;
 }
 
@@ -430,8 +440,9 @@ FB_DEV bool avionics_periodic(const YFull& yf, const RhsOut& y, CtlIn& u, UA& ua
                               CtlState& cs, const GT& T, double Dt) {
     if (VAR < FB_C172X1) return false;
     gdc_periodic(cs, yf.lat, yf.lon, yf.h_e, y.wow, u);
-    lon_periodic(cs, yf, y.wow, u, T, Dt, (int)u(FB_U_LON_MODE_REQ));
-    lat_periodic(cs, yf, y.wow, u, T, Dt, (int)u(FB_U_LAT_MODE_REQ));
+    GainCell c; c.locate(yf.EAS, yf.h_e);   // both laws schedule on the same (EAS, h_e) (c172x_ctl.jl:296, :889)
+    lon_periodic(cs, yf, y.wow, u, T, Dt, (int)u(FB_U_LON_MODE_REQ), c);
+    lat_periodic(cs, yf, y.wow, u, T, Dt, (int)u(FB_U_LAT_MODE_REQ), c);
     return avionics_assign(cs, ua);
 }
 

@@ -19,6 +19,9 @@
 #ifndef FB_STEP_BLOCK_WIDE
 #define FB_STEP_BLOCK_WIDE 448  // second airborne shape
 #endif
+#ifndef FB_STEP_BLOCK_CTL
+#define FB_STEP_BLOCK_CTL 256   // variants with control laws (C172X1/X2): 8 warps at 255 registers
+#endif
 
 struct EnsembleDev {
     double* x;            // [NX][pitch]
@@ -41,8 +44,57 @@ struct EnsembleDev {
     int log_n_fields;
     int log_every;
     long long log_capacity;
+    // ensemble moments of the logged fields, one record per (sample, field), accumulated as the samples are taken:
+    // count [cap * nf], {sum, sum of squares} [cap * nf][2], min [cap * nf], max [cap * nf] (separate arrays: each is one
+    // typed NCCL all-reduce over a contiguous range of samples). Null = moments not kept.
+    unsigned long long* mom_cnt;
+    double* mom_sum;
+    double* mom_min;
+    double* mom_max;
     FbDeviceTables tables;
 };
+
+// ---- ensemble moments ---------------------------------------------------------------------------------------------
+// min / max of doubles by compare-and-swap; the first read may be stale, which is harmless for a monotone update
+FB_DEV void atomic_min_f64(double* p, double v) {
+    unsigned long long* a = reinterpret_cast<unsigned long long*>(p);
+    unsigned long long old = *a, assumed;
+    do { assumed = old; if (__longlong_as_double((long long)assumed) <= v) break; old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v)); } while (assumed != old);
+}
+FB_DEV void atomic_max_f64(double* p, double v) {
+    unsigned long long* a = reinterpret_cast<unsigned long long*>(p);
+    unsigned long long old = *a, assumed;
+    do { assumed = old; if (__longlong_as_double((long long)assumed) >= v) break; old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v)); } while (assumed != old);
+}
+// One value per calling thread folded into moment record `rec`: the threads of the warp that arrive here together
+// (members of a warp can run one stage out of phase, so the group is whatever is converged) reduce by shuffles and the
+// group's first lane issues one set of atomics.
+FB_DEV void moments_add(const EnsembleDev& E, long long rec, double v) {
+    // Threads that sit at this instruction together need not be in the same iteration of the caller's loop over the logged
+    // fields (the lane that issued the previous record's atomics rejoins the others by program counter, one iteration
+    // behind): the group is the set of converged threads that hold the SAME record.
+    const unsigned m = __match_any_sync(__activemask(), (unsigned long long)rec);
+    const int lane = threadIdx.x & 31;
+    double s = v, s2 = v * v, mn = v, mx = v;
+    if (m == 0xffffffffu) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ts = __shfl_xor_sync(m, s, o), ts2 = __shfl_xor_sync(m, s2, o), tmn = __shfl_xor_sync(m, mn, o), tmx = __shfl_xor_sync(m, mx, o);
+            s += ts; s2 += ts2; mn = (tmn < mn) ? tmn : mn; mx = (tmx > mx) ? tmx : mx;
+        }
+    } else {   // a partial group: every member of it gathers the values of the lanes present, in lane order
+        s = 0.0; s2 = 0.0;
+        for (unsigned rest = m; rest; rest &= rest - 1) {
+            const double t = __shfl_sync(m, v, __ffs(rest) - 1);
+            s += t; s2 += t * t; mn = (t < mn) ? t : mn; mx = (t > mx) ? t : mx;
+        }
+    }
+    if (lane == __ffs(m) - 1) {
+        atomicAdd(E.mom_cnt + rec, (unsigned long long)__popc(m));
+        atomicAdd(E.mom_sum + 2 * rec, s); atomicAdd(E.mom_sum + 2 * rec + 1, s2);
+        atomic_min_f64(E.mom_min + rec, mn); atomic_max_f64(E.mom_max + rec, mx);
+    }
+}
 
 // Stage the lookup-table pack into shared memory with one bulk asynchronous copy (TMA unit,
 // cp.async.bulk + mbarrier complete_tx); every thread of the CTA then waits on the barrier phase.
@@ -157,14 +209,23 @@ struct StepShape {
     static constexpr int BUDGET = 232448 - TBL - 1024;                                         // 227 KB per CTA
     static constexpr int NCOL = 2 * NX - Lay<VAR, KIN, AIR>::NACT;                              // state columns + accumulator columns (none for actuators)
     static constexpr int FIT = (int)(BUDGET / (sizeof(double) * NCOL)) / 32 * 32;
-    static constexpr int T = FIT < CAP ? FIT : CAP;
-    static constexpr int SPARE = (int)(BUDGET / (sizeof(double) * T)) - NCOL;                  // columns left for the input cache
+    // The variants with control laws run 8 warps per CTA at up to 255 registers per thread instead of 12 at 168 (the
+    // register file is split over four sub-partitions: 2 warps each get 255 registers, 3 get 168): their right-hand side
+    // plus the control laws spill ~130 doubles per step at 168 registers, every spill an L2 round trip beside 229 KB of
+    // shared memory, and the 8-warp shape leaves room for the whole input cache and the output tap in shared memory
+    // (measured on cfg 3: 1.11e9 -> 1.17e9 aircraft-steps/s before anything else changed; C172S loses 11 % at 256).
+    static constexpr int VCAP = (VAR >= FB_C172X1 && CAP > FB_STEP_BLOCK_CTL) ? FB_STEP_BLOCK_CTL : CAP;
+    static constexpr int T = FIT < VCAP ? FIT : VCAP;
+    static constexpr int SPARE = (int)(BUDGET / (sizeof(double) * T)) - NCOL;                  // columns left for the input cache and the tap
 #ifndef FB_NSLOT_MAX
 #define FB_NSLOT_MAX 16
 #endif
     static constexpr int NSLOT_MAX = (VAR == FB_C172S) ? FB_NSLOT_MAX : FB_NSLOT_MAX + 3;   // C172X also caches the wind
-    static constexpr int NSLOT = SPARE < NSLOT_MAX ? SPARE : NSLOT_MAX;
-    static constexpr size_t SMEM = TBL + sizeof(double) * (NCOL + NSLOT) * T;
+    // output tap of the f(x*) evaluation (control-law feedback): in shared-memory columns when they fit beside at least
+    // 10 input slots, otherwise in the member's column of E.ctl
+    static constexpr int NTAP = (VAR >= FB_C172X1 && SPARE >= TAP_COUNT + 10) ? TAP_COUNT : 0;
+    static constexpr int NSLOT = (SPARE - NTAP) < NSLOT_MAX ? (SPARE - NTAP) : NSLOT_MAX;
+    static constexpr size_t SMEM = TBL + sizeof(double) * (NCOL + NSLOT + NTAP) * T;
 };
 #define FB_RESUME_PENDING (1 << 30)
 #define FB_MW_MAX 32            // member-warps a CTA can time-slice over its hardware warps (step_kernel)
@@ -224,6 +285,8 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
     double* sx = smem + TBL / 8 + threadIdx.x;
     double* sacc = sx + NX * T;
     CachedIn<VAR, T, StepShape<VAR, KIN, AIR, CAP>::NSLOT> u; u.g = ug; u.sc = sx + StepShape<VAR, KIN, AIR, CAP>::NCOL * T;
+    constexpr int NTAP = StepShape<VAR, KIN, AIR, CAP>::NTAP;
+    double* const stap = u.sc + StepShape<VAR, KIN, AIR, CAP>::NSLOT * T;   // this thread's tap columns (NTAP of them)
     double xs[NX];
 #pragma unroll
     for (int c = 0; c < NX; c++) { double v = E.x[(long long)L::row(c) * E.pitch + i]; xs[c] = v; sx[c * T] = v; }
@@ -251,6 +314,8 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
 
     int done = 0, n_reeval = 0;
     int gnd_seen = 0, handover = -1;
+    int ctl_in = periodic_every - (int)(step0 % periodic_every);                               // steps to the next control update
+    int log_in = (E.log_every > 0 && E.log_n_fields > 0) ? E.log_every - (int)(step0 % E.log_every) : 0;   // ... log sample (0: no log)
     const double h2 = 0.5 * dt, h6 = dt * (1.0 / 6.0);
     RkSink<T, L::ACT, L::NACT> sink; sink.xs = xs; sink.sx = sx; sink.sacc = sacc;
     // stage factors and step factor of the closed-form actuator propagation (RkSink)
@@ -267,8 +332,9 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
         sink.pa = (st == 1) ? ap1 : ((st == 2) ? ap2 : ((st == 3) ? ap3 : 1.0));
         RhsOut y;
         if (VAR >= FB_C172X1) {
-            ColumnTap tap; tap.p = E.ctl + (long long)FB_CTL_TAP_ROW * E.pitch + i; tap.pitch = E.pitch; tap.on = (st == 4);
-            rhs<VAR, KIN, false, AIR>(xs, sink, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr, tap);
+            if (NTAP) { SmemTap<T> tap; tap.p = stap; tap.on = (st == 4); rhs<VAR, KIN, false, AIR>(xs, sink, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr, tap); }
+            else { ColumnTap tap; tap.p = E.ctl + (long long)FB_CTL_TAP_ROW * E.pitch + i; tap.pitch = E.pitch; tap.on = (st == 4);
+                   rhs<VAR, KIN, false, AIR>(xs, sink, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr, tap); }
         } else rhs<VAR, KIN, false, AIR>(xs, sink, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr);
         if (!AIR) gnd_seen |= y.gnd;
         if (y.err) {
@@ -284,28 +350,31 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
         // (It also produced the tentative k1 / first stage state of the next step.)
         done++;
         const long long step_idx = step0 + done;
-        const bool ctl_due = (VAR >= FB_C172X1) && (step_idx % periodic_every) == 0;
-        const bool log_due = E.log_every > 0 && E.log_n_fields > 0 && (step_idx % E.log_every) == 0 &&
-                             (step_idx / E.log_every) < E.log_capacity;
+        // countdowns instead of 64-bit remainders: steps left to the next control update / log sample
+        bool ctl_due = false, log_due = false;
+        if (VAR >= FB_C172X1) { if (--ctl_in == 0) { ctl_due = true; ctl_in = periodic_every; } }
+        if (log_in > 0 && --log_in == 0) { log_in = E.log_every; log_due = (step_idx / E.log_every) < E.log_capacity; }
         YFull yf;
         const int stall_y = stall, eng_y = eng;
         if (ctl_due && !log_due) {
-            // control-law inputs from the tapped intermediates of the f(x*) evaluation just made and from x* itself
-            const double* tp = E.ctl + (long long)FB_CTL_TAP_ROW * E.pitch + i;
-            auto tapv = [&](int k) { return tp[(long long)k * E.pitch]; };
+            // Control-law inputs from the tapped intermediates of the f(x*) evaluation just made and from x* itself. The
+            // angles come from the fast primitives of the right-hand side (a few ulp from the library functions; the
+            // control laws are continuous in them, and the parity tests hold the commands to 1e-9).
+            auto tapv = [&](int k) { return NTAP ? stap[k * T_] : E.ctl[(long long)(FB_CTL_TAP_ROW + k) * E.pitch + i]; };
             q4 q = mkq(tapv(TAP_Q_NB), tapv(TAP_Q_NB + 1), tapv(TAP_Q_NB + 2), tapv(TAP_Q_NB + 3));
             if (KIN == FB_NED) { yf.theta = sink.sx[(L::KINX + 1) * T_]; yf.phi = sink.sx[(L::KINX + 2) * T_]; }
-            else {   // REuler(q_nb), attitude.jl:382-390
-                yf.theta = asin(clampd(2.0 * (q.w * q.y - q.x * q.z), -1.0, 1.0));
-                yf.phi = atan2(2.0 * (q.w * q.x + q.y * q.z), 1.0 - 2.0 * (q.x * q.x + q.y * q.y));
+            else {   // REuler(q_nb), attitude.jl:382-390: asin(s) = atan2(s, sqrt((1 - s)(1 + s)))
+                const double st_ = clampd(2.0 * (q.w * q.y - q.x * q.z), -1.0, 1.0);
+                yf.theta = fb_atan2(st_, fb_sqrt(fb_max((1.0 - st_) * (1.0 + st_), 1e-280)));
+                yf.phi = fb_atan2(2.0 * (q.w * q.x + q.y * q.z), 1.0 - 2.0 * (q.x * q.x + q.y * q.y));
             }
             yf.v_eb_n = mk3(tapv(TAP_V_EB_N), tapv(TAP_V_EB_N + 1), tapv(TAP_V_EB_N + 2));
             yf.w_wb_b = mk3(tapv(TAP_W_WB_B), tapv(TAP_W_WB_B + 1), tapv(TAP_W_WB_B + 2));
             yf.w_eb_b = mk3(sink.sx[L::DYN * T_], sink.sx[(L::DYN + 1) * T_], sink.sx[(L::DYN + 2) * T_]);
-            yf.v_gnd = sqrt(dot(yf.v_eb_n, yf.v_eb_n));
+            yf.v_gnd = fb_sqrt(fb_max(dot(yf.v_eb_n, yf.v_eb_n), 1e-280));
             const bool valid = (KIN == FB_NED) || (yf.v_gnd > 0.1);   // kinematics.jl:212-213 vs :393-394
-            yf.chi_gnd = valid ? atan2(yf.v_eb_n.y, yf.v_eb_n.x) : 0.0;
-            yf.EAS = tapv(TAP_TAS) * sqrt(tapv(TAP_RHO) / isa::rho_std);
+            yf.chi_gnd = valid ? fb_atan2(yf.v_eb_n.y, yf.v_eb_n.x) : 0.0;
+            yf.EAS = tapv(TAP_TAS) * fb_sqrt(tapv(TAP_RHO) * (1.0 / isa::rho_std));
             yf.alpha = tapv(TAP_ALPHA); yf.beta = tapv(TAP_BETA);
             yf.lat = tapv(TAP_LAT); yf.lon = tapv(TAP_LON);
             yf.alpha_filt = sink.sx[L::AERO * T_]; yf.beta_filt = sink.sx[(L::AERO + 1) * T_];
@@ -345,8 +414,11 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
         if (changed) u.refresh();
         if (log_due) {
             const long long smp = step_idx / E.log_every;
-            for (int f = 0; f < E.log_n_fields; f++)
-                E.log[(smp * E.log_n_fields + f) * E.pitch + i] = pick_output(yf, stall_y, eng_y, cs, E.log_fields[f]);
+            for (int f = 0; f < E.log_n_fields; f++) {
+                const double v = pick_output(yf, stall_y, eng_y, cs, E.log_fields[f]);
+                if (E.log) E.log[(smp * E.log_n_fields + f) * E.pitch + i] = v;
+                if (E.mom_cnt) moments_add(E, smp * E.log_n_fields + f, v);
+            }
         }
         if (done == n_steps) break;
         if (changed) {            // re-evaluate k1 from the post-callback x / s / u

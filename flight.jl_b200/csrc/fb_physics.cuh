@@ -174,6 +174,13 @@ struct NoTap { FB_DEV void operator()(int, double) const {} };
 struct ColumnTap {        // column of a [TAP_COUNT][pitch] array, written only while `on`
     double* p; long long pitch; bool on;
     FB_DEV void operator()(int k, double v) const { if (on) p[(long long)k * pitch] = v; }
+    FB_DEV double get(int k) const { return p[(long long)k * pitch]; }
+};
+template <int T>
+struct SmemTap {          // the same in shared-memory columns of the owning thread (compile-time stride)
+    double* p; bool on;
+    FB_DEV void operator()(int k, double v) const { if (on) p[k * T] = v; }
+    FB_DEV double get(int k) const { return p[k * T]; }
 };
 
 // derivative sink that simply stores into a local array (test hook, trim, output pass)

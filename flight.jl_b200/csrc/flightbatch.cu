@@ -9,6 +9,8 @@
 #include <vector>
 #include <algorithm>
 #include <numeric>
+#include <dlfcn.h>
+#include <nccl.h>
 #include "fb_init.cuh"
 #include "fb_lss.cuh"
 #include "fb_complete.h"
@@ -26,6 +28,7 @@ struct fb_sim {
     int var_t = 0;   // template variant actually instantiated (X2 shares X1's kernels)
     int nx = 0;
     long long pitch = 0;
+    long long host_pitch = 0;        // row pitch (elements) of the caller's [C][N] host arrays; 0 = n_members (an fb_group passes global arrays)
     EnsembleDev E{};
     cudaStream_t stream = nullptr;
     double* d_snap = nullptr;                          // device snapshot of x for fb_get_state_async
@@ -43,7 +46,6 @@ struct fb_sim {
     long long* d_ev_cursor = nullptr;
     int* d_log_fields = nullptr;
     double* d_scratch = nullptr;      // [max(nx, 8)][pitch]
-    double* d_stats = nullptr;        // 5 doubles
     unsigned long long* d_rhs_count = nullptr;
     long long launches = 0;
     int periodic_every = 1;
@@ -60,6 +62,24 @@ struct fb_sim {
     bool force_complete = false;
     bool air_wide = false;           // airborne kernel shape: FB_STEP_BLOCK_WIDE threads (one-wave ensembles) or FB_STEP_BLOCK
     int air_mpc = 0;                 // > step_block_air: time-sliced airborne launches, this many members per CTA (fb_kernels.cuh)
+    // ensemble moments of the log samples (EnsembleDev::mom_*): one device allocation, a pinned staging copy for the
+    // asynchronous fetch, and the side stream + communicator of the all-reduce over the shards
+    void* d_mom = nullptr;
+    long long mom_records = 0;                         // [log_capacity][log_n_fields] + 1 scratch record (fb_stats)
+    unsigned long long* m_cnt = nullptr; double* m_sum = nullptr; double* m_min = nullptr; double* m_max = nullptr;
+    char* h_mom = nullptr; size_t h_mom_bytes = 0;
+    long long mom_first = 0, mom_count = 0;            // sample range of the fetch in flight
+    bool mom_pending = false;
+    cudaEvent_t mom_ready = nullptr, mom_done = nullptr;
+    ncclComm_t comm = nullptr;
+    bool comm_owned = false;                           // false: the communicator belongs to an fb_group
+    int comm_ranks = 1;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t comm_in = nullptr, comm_out = nullptr; // launch stream -> side stream, side stream -> readers
+    bool comm_busy = false;
+    long long reduced_upto = 0;                        // log samples [0, reduced_upto) have been all-reduced
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> comm_timers;
+    double comm_ms = 0.0; long long comm_calls = 0;
 };
 
 // ------------------------------------------------------------------------------------ kernel dispatch
@@ -183,38 +203,47 @@ template <int VAR, int KIN> struct Ops {
     ((s)->var_t == FB_C172S ? FB_KIN_DISPATCH(s, FB_C172S, CALL) : ((s)->var_t == FB_C172X0 ? FB_KIN_DISPATCH(s, FB_C172X0, CALL) : FB_KIN_DISPATCH(s, FB_C172X1, CALL)))
 #endif
 
+static size_t hp(const fb_sim* s) { return sizeof(double) * (size_t)(s->host_pitch > 0 ? s->host_pitch : s->E.n); }
 static int layout_nx(int variant, int kin) {
     int nact = (variant == FB_C172S) ? 0 : 7;
     int nkin = (kin == FB_WA) ? 9 : (kin == FB_ECEF ? 8 : 6);
     return 12 + nact + nkin + 6;
 }
 
-// ------------------------------------------------------------------------------------ statistics kernel
-__global__ void stats_kernel(const double* v, const int* status, long long n, double* out /*count,sum,sumsq,min,max*/) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    double c = 0.0, s = 0.0, s2 = 0.0, mn = INFINITY, mx = -INFINITY;
-    if (i < n && (status[i] == FB_ST_RUNNING || status[i] == FB_ST_DONE)) { double x = v[i]; c = 1.0; s = x; s2 = x * x; mn = x; mx = x; }
-    for (int o = 16; o > 0; o >>= 1) {   // warp-level shuffle reduction
-        c += __shfl_down_sync(0xffffffffu, c, o); s += __shfl_down_sync(0xffffffffu, s, o); s2 += __shfl_down_sync(0xffffffffu, s2, o);
-        mn = fmin(mn, __shfl_down_sync(0xffffffffu, mn, o)); mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
-    }
-    if ((threadIdx.x & 31) == 0 && c > 0.0) {
-        atomicAdd(out, c); atomicAdd(out + 1, s); atomicAdd(out + 2, s2);
-        unsigned long long* pmn = (unsigned long long*)(out + 3); unsigned long long* pmx = (unsigned long long*)(out + 4);
-        unsigned long long old = *pmn, assumed;
-        do { assumed = old; if (__longlong_as_double(assumed) <= mn) break; old = atomicCAS(pmn, assumed, (unsigned long long)__double_as_longlong(mn)); } while (assumed != old);
-        old = *pmx;
-        do { assumed = old; if (__longlong_as_double(assumed) >= mx) break; old = atomicCAS(pmx, assumed, (unsigned long long)__double_as_longlong(mx)); } while (assumed != old);
-    }
+// ------------------------------------------------------------------------------------ statistics kernels
+// Moments of one row of values over the members with status RUNNING or DONE, folded into moment record `rec`: the same
+// warp-shuffle reduction + one set of atomics per warp the integrator's log tap uses (moments_add, fb_kernels.cuh).
+__global__ void moments_kernel(EnsembleDev E, const double* v, long long rec) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < E.n && (E.status[i] == FB_ST_RUNNING || E.status[i] == FB_ST_DONE)) moments_add(E, rec, v[i]);
+}
+__global__ void moments_reset_kernel(EnsembleDev E, long long first, long long count) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const long long r = first + k;
+    E.mom_cnt[r] = 0ull; E.mom_sum[2 * r] = 0.0; E.mom_sum[2 * r + 1] = 0.0; E.mom_min[r] = INFINITY; E.mom_max[r] = -INFINITY;
 }
 // row[i] = Ranged-saturated staged value (types.jl:15-20), the device half of fb_set_input
 __global__ void saturate_row_kernel(double* row, const double* staged, long long n, int field) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) row[i] = saturate_input(field, staged[i]);
 }
+__host__ __device__ inline double default_input(int f) {
+    switch (f) {
+        case FB_U_MIXTURE: return 0.5; case FB_U_MIXTURE_AUTO: return 1.0; case FB_U_STEERING_ENGAGED: return 1.0;
+        case FB_U_M_PILOT: case FB_U_M_COPILOT: return 75.0; case FB_U_M_BAGGAGE: return 50.0;
+        case FB_U_T_SL: return 288.15; case FB_U_P_SL: return 101325.0;
+        case FB_U_LON_EAS_REF: return 50.0;
+        case FB_U_GDC_LAT2: return 1e-3;   // Segment() default target, c172x_gdc.jl:90
+        default: return 0.0;
+    }
+}
+__global__ void fill_defaults_kernel(double* u, long long pitch) {   // every input row = the constructed model's default
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < pitch * FB_U__COUNT) u[k] = default_input((int)(k / pitch));
+}
 __global__ void fill_kernel(double* p, long long n, double v) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
 
 // FP64 FMA-pipe peak probe: 8 independent dependent-FMA chains per thread, all SMs, no memory traffic
@@ -246,31 +275,67 @@ static bool parse_blob(const uint8_t* b, size_t n, std::vector<BlobSec>& out) {
     return true;
 }
 
-static double default_input(int f) {
-    switch (f) {
-        case FB_U_MIXTURE: return 0.5; case FB_U_MIXTURE_AUTO: return 1.0; case FB_U_STEERING_ENGAGED: return 1.0;
-        case FB_U_M_PILOT: case FB_U_M_COPILOT: return 75.0; case FB_U_M_BAGGAGE: return 50.0;
-        case FB_U_T_SL: return 288.15; case FB_U_P_SL: return 101325.0;
-        case FB_U_LON_EAS_REF: return 50.0;
-        case FB_U_GDC_LAT2: return 1e-3;   // Segment() default target, c172x_gdc.jl:90
-        default: return 0.0;
+// ------------------------------------------------------------------------------------ NCCL, loaded at run time
+// The library has no link-time dependency on NCCL: a single-GPU host never needs it, and a process that already holds an
+// NCCL (torch's, CUDA.jl's) must get that one, which dlopen by soname does.
+struct NcclApi {
+    void* dl = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi* nccl_api() {
+    static NcclApi api; static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char* names[] = {getenv("FLIGHTBATCH_NCCL"), "libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) { if (nm && (api.dl = dlopen(nm, RTLD_NOW | RTLD_GLOBAL))) break; }
+        if (api.dl) {
+            auto sym = [&](const char* n) { return dlsym(api.dl, n); };
+            api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId"); api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+            api.CommInitAll = (decltype(api.CommInitAll))sym("ncclCommInitAll"); api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+            api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce"); api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+            api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd"); api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+            if (!api.GetUniqueId || !api.CommInitRank || !api.CommInitAll || !api.CommDestroy || !api.AllReduce || !api.GroupStart || !api.GroupEnd || !api.GetErrorString) api.dl = nullptr;
+        }
     }
+    return api.dl ? &api : nullptr;
 }
+#define NK(call)                                                                                   \
+    do {                                                                                           \
+        ncclResult_t r_ = (call);                                                                  \
+        if (r_ != ncclSuccess) return fail(FB_ERR_CUDA, std::string(#call) + ": " + nccl_api()->GetErrorString(r_)); \
+    } while (0)
 
 extern "C" {
 
 int32_t fb_api_version(void) { return FB_API_VERSION; }
 const char* fb_last_error(void) { return g_err.c_str(); }
 
+static int32_t create_body(fb_sim* s);
 int32_t fb_create(const fb_config* cfg, fb_handle* out) {
     if (!cfg || !out) return fail(FB_ERR_ARG, "fb_create: null argument");
+    *out = nullptr;
     if (cfg->variant < FB_C172S || cfg->variant > FB_C172X2) return fail(FB_ERR_ARG, "fb_create: unknown variant");
     if (cfg->kinematics != FB_WA && cfg->kinematics != FB_NED && cfg->kinematics != FB_ECEF) return fail(FB_ERR_ARG, "fb_create: kinematics must be FB_WA, FB_ECEF or FB_NED");
     if (cfg->n_members <= 0) return fail(FB_ERR_ARG, "fb_create: n_members must be positive");
+    if (cfg->member_offset < 0) return fail(FB_ERR_ARG, "fb_create: member_offset must not be negative");
     if (!(cfg->dt > 0.0)) return fail(FB_ERR_ARG, "fb_create: dt must be positive");
     double Dt = cfg->Dt > 0.0 ? cfg->Dt : cfg->dt;
     long long pe = llround(Dt / cfg->dt);
     if (pe < 1 || fabs(pe * cfg->dt - Dt) > 1e-9 * Dt) return fail(FB_ERR_ARG, "fb_create: Dt must be a positive integer multiple of dt");
+    if (cfg->log_every > 0 && cfg->log_n_fields > 0) {
+        if (cfg->log_n_fields > 32) return fail(FB_ERR_ARG, "fb_create: at most 32 log fields");
+        for (int f = 0; f < cfg->log_n_fields; f++)
+            if (cfg->log_fields[f] < 0 || cfg->log_fields[f] >= FB_Y__COUNT) return fail(FB_ERR_ARG, "fb_create: unknown output field in log_fields");
+        if (cfg->t_end < cfg->t_start) return fail(FB_ERR_ARG, "fb_create: t_end < t_start");
+        if (cfg->log_flags & ~(FB_LOG_MEMBERS | FB_LOG_MOMENTS)) return fail(FB_ERR_ARG, "fb_create: unknown bit in log_flags");
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) return fail(FB_ERR_CUDA, "fb_create: no CUDA device available (this engine has no CPU path)");
@@ -279,6 +344,14 @@ int32_t fb_create(const fb_config* cfg, fb_handle* out) {
     fb_sim* s = new fb_sim();
     s->cfg = *cfg; s->cfg.Dt = Dt;
     s->periodic_every = (int)pe;
+    int32_t rc = create_body(s);
+    if (rc != FB_OK) { std::string msg = g_err; fb_destroy(s); g_err = msg; return rc; }   // nothing half-built survives a failure
+    *out = s;
+    return FB_OK;
+}
+
+static int32_t create_body(fb_sim* s) {
+    const fb_config* cfg = &s->cfg;
     s->var_t = cfg->variant >= FB_C172X1 ? FB_C172X1 : cfg->variant;
     s->nx = layout_nx(cfg->variant, cfg->kinematics);
     long long N = cfg->n_members;
@@ -286,7 +359,12 @@ int32_t fb_create(const fb_config* cfg, fb_handle* out) {
     if (s->cfg.steps_per_launch <= 0) s->cfg.steps_per_launch = 250;
     CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&s->snap_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&s->copy_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s->snap_ready, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s->snap_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s->mom_ready, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s->mom_done, cudaEventDisableTiming));
     for (int f = 0; f < FB_U__COUNT; f++) CK(cudaEventCreateWithFlags(&s->stage_consumed[f], cudaEventDisableTiming));
     EnsembleDev& E = s->E;
     E.pitch = s->pitch; E.n = N;
@@ -297,7 +375,6 @@ int32_t fb_create(const fb_config* cfg, fb_handle* out) {
     CK(cudaMalloc(&E.ctl, sizeof(double) * FB_CTL_STATE_COUNT * s->pitch));
     CK(cudaMalloc(&s->d_ev_cursor, sizeof(long long) * s->pitch));
     CK(cudaMalloc(&s->d_scratch, sizeof(double) * std::max(s->nx, 8) * s->pitch));
-    CK(cudaMalloc(&s->d_stats, sizeof(double) * 8));
     CK(cudaMalloc(&s->d_rhs_count, sizeof(unsigned long long)));
     CK(cudaMemsetAsync(s->d_rhs_count, 0, sizeof(unsigned long long), s->stream));
     CK(cudaMemsetAsync(E.x, 0, sizeof(double) * s->nx * s->pitch, s->stream));
@@ -306,26 +383,34 @@ int32_t fb_create(const fb_config* cfg, fb_handle* out) {
     CK(cudaMemsetAsync(E.stall, 0, s->pitch, s->stream)); CK(cudaMemsetAsync(E.eng, 0, s->pitch, s->stream));
     CK(cudaMemsetAsync(E.status, 0, sizeof(int) * s->pitch, s->stream));
     CK(cudaMemsetAsync(s->d_ev_cursor, 0, sizeof(long long) * s->pitch, s->stream));
-    for (int f = 0; f < FB_U__COUNT; f++) {
-        int grid = (int)((s->pitch + 255) / 256);
-        fill_kernel<<<grid, 256, 0, s->stream>>>(E.u + (long long)f * s->pitch, s->pitch, default_input(f));
-    }
+    // one launch fills every input row with its default (the rows are contiguous)
+    fill_defaults_kernel<<<(int)((s->pitch * FB_U__COUNT + 255) / 256), 256, 0, s->stream>>>(E.u, s->pitch);
+    CK(cudaGetLastError());
     E.ev_cursor = s->d_ev_cursor;
-    // decimated log
+    // decimated log: every member's samples (FB_LOG_MEMBERS) and / or the ensemble moments of each sample (FB_LOG_MOMENTS)
     E.log_every = cfg->log_every > 0 ? cfg->log_every : 0;
     E.log_n_fields = 0; E.log_capacity = 0;
+    const int flags = cfg->log_flags ? cfg->log_flags : (FB_LOG_MEMBERS | FB_LOG_MOMENTS);
     if (E.log_every > 0 && cfg->log_n_fields > 0) {
-        if (cfg->log_n_fields > 32) return fail(FB_ERR_ARG, "fb_create: at most 32 log fields");
         long long total = llround((cfg->t_end - cfg->t_start) / cfg->dt);
-        if (total < 0) return fail(FB_ERR_ARG, "fb_create: t_end < t_start");
         E.log_n_fields = cfg->log_n_fields;
         E.log_capacity = total / E.log_every + 1;
-        double bytes = (double)E.log_capacity * E.log_n_fields * s->pitch * 8.0;
-        if (bytes > 64e9) return fail(FB_ERR_ALLOC, "fb_create: log would exceed 64 GB; raise log_every or log fewer fields");
-        CK(cudaMalloc(&E.log, (size_t)bytes));
+        if (flags & FB_LOG_MEMBERS) {
+            double bytes = (double)E.log_capacity * E.log_n_fields * s->pitch * 8.0;
+            if (bytes > 64e9) return fail(FB_ERR_ALLOC, "fb_create: log would exceed 64 GB; raise log_every, log fewer fields or keep the moments only (FB_LOG_MOMENTS)");
+            if (cudaMalloc(&E.log, (size_t)bytes) != cudaSuccess) { (void)cudaGetLastError(); return fail(FB_ERR_ALLOC, "fb_create: out of device memory for the log"); }
+        }
         CK(cudaMalloc(&s->d_log_fields, sizeof(int) * 32));
-        CK(cudaMemcpyAsync(s->d_log_fields, cfg->log_fields, sizeof(int) * cfg->log_n_fields, cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync(s->d_log_fields, s->cfg.log_fields, sizeof(int) * cfg->log_n_fields, cudaMemcpyHostToDevice, s->stream));
         E.log_fields = s->d_log_fields;
+    }
+    {   // moment records: [capacity][fields] for the log samples (when kept) + one scratch record for fb_stats
+        s->mom_records = ((flags & FB_LOG_MOMENTS) ? E.log_capacity * E.log_n_fields : 0) + 1;
+        const long long R = s->mom_records;
+        CK(cudaMalloc(&s->d_mom, (size_t)R * 40));
+        s->m_cnt = (unsigned long long*)s->d_mom; s->m_sum = (double*)((char*)s->d_mom + R * 8);
+        s->m_min = (double*)((char*)s->d_mom + R * 24); s->m_max = (double*)((char*)s->d_mom + R * 32);
+        if (R > 1) { E.mom_cnt = s->m_cnt; E.mom_sum = s->m_sum; E.mom_min = s->m_min; E.mom_max = s->m_max; }
     }
     // Integrator launch shape: one CTA per SM holding the table pack plus two NX x T column blocks in shared
     // memory. T is the largest multiple of 32 that fits 227 KB and the register budget, then shrunk while the
@@ -348,7 +433,7 @@ int32_t fb_create(const fb_config* cfg, fb_handle* out) {
         s->air_wide = (double)waves_w * 1.45 < (double)waves_n;
         s->step_block_air = s->air_wide ? Tw : Tn;
         // Third option, for ensembles of more than one and at most FB_MW_MAX member-warps per SM: ONE persistent CTA
-        // per SM of the 168-register shape that time-slices its MW member-warps over its 12 warps in chunks of 10 steps:
+        // per SM of the 168-register shape that time-slices its MW member-warps over its 12 warps in chunks of steps:
         // ceil(MW * C / 12) / C waves (+ ~3 % for the k1 re-evaluated at every chunk start).
         {
             const int tmax = FB_DISPATCH(s, step_tmax)(1), hw = tmax / 32;
@@ -374,14 +459,13 @@ int32_t fb_create(const fb_config* cfg, fb_handle* out) {
     CK(cudaEventCreateWithFlags(&s->ground_ev, cudaEventDisableTiming));
     CK(FB_DISPATCH(s, prepare)(s));
     CK(cudaStreamSynchronize(s->stream));
-    *out = s;
     return FB_OK;
 }
 
 int32_t fb_destroy(fb_handle s) {
     if (!s) return FB_OK;
     cudaSetDevice(s->cfg.device);
-    cudaStreamSynchronize(s->stream);
+    if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
     if (s->snap_stream) { cudaStreamSynchronize(s->snap_stream); cudaStreamDestroy(s->snap_stream); }
     cudaFree(s->d_snap); if (s->snap_ready) cudaEventDestroy(s->snap_ready); if (s->snap_done) cudaEventDestroy(s->snap_done);
@@ -389,12 +473,20 @@ int32_t fb_destroy(fb_handle s) {
     cudaFree(E.x); cudaFree(E.u); cudaFree(E.stall); cudaFree(E.eng); cudaFree(E.status); cudaFree(E.ctl); cudaFree(E.log);
     cudaFree(s->d_pack); cudaFree(s->d_geoid);
     cudaFree(s->d_ev_off); cudaFree(s->d_ev_step); cudaFree(s->d_ev_field); cudaFree(s->d_ev_value); cudaFree(s->d_ev_cursor);
-    cudaFree(s->d_log_fields); cudaFree(s->d_scratch); cudaFree(s->d_stats); cudaFree(s->d_rhs_count);
+    cudaFree(s->d_log_fields); cudaFree(s->d_scratch); cudaFree(s->d_rhs_count);
     cudaFree(s->d_resume); cudaFree(s->d_ground); if (s->h_ground) cudaFreeHost(s->h_ground); if (s->ground_ev) cudaEventDestroy(s->ground_ev);
+    if (s->comm_stream) cudaStreamSynchronize(s->comm_stream);
+    if (s->comm && s->comm_owned && nccl_api()) nccl_api()->CommDestroy(s->comm);
+    for (auto& t : s->comm_timers) { cudaEventDestroy(t.first); cudaEventDestroy(t.second); }
+    if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
+    if (s->comm_in) cudaEventDestroy(s->comm_in); if (s->comm_out) cudaEventDestroy(s->comm_out);
+    cudaFree(s->d_mom); if (s->h_mom) cudaFreeHost(s->h_mom);
+    if (s->mom_ready) cudaEventDestroy(s->mom_ready); if (s->mom_done) cudaEventDestroy(s->mom_done);
     for (int f = 0; f < FB_U__COUNT; f++) { cudaFree(s->d_stage[f]); if (s->stage_consumed[f]) cudaEventDestroy(s->stage_consumed[f]); }
     if (s->copy_done) cudaEventDestroy(s->copy_done);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
-    cudaStreamDestroy(s->stream);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    (void)cudaGetLastError();
     delete s;
     return FB_OK;
 }
@@ -404,6 +496,7 @@ int32_t fb_sync(fb_handle s) {
     if (!s) return fail(FB_ERR_ARG, "null handle");
     CK(cudaSetDevice(s->cfg.device));
     CK(cudaStreamSynchronize(s->stream));
+    if (s->comm_stream) CK(cudaStreamSynchronize(s->comm_stream));
     return fb_wait_state(s);
 }
 
@@ -510,13 +603,34 @@ struct Uploader {
     ~Uploader() { cudaStreamSynchronize(s->stream); for (double* d : bufs) cudaFree(d); }
 };
 
+static EnsembleDev mom_view(const fb_sim* s) {
+    EnsembleDev E = s->E;
+    E.mom_cnt = s->m_cnt; E.mom_sum = s->m_sum; E.mom_min = s->m_min; E.mom_max = s->m_max;
+    return E;
+}
 static int32_t after_init(fb_sim* s, bool init_avionics) {
     s->n_steps = 0; s->initialised = true;
     if (init_avionics && s->var_t >= FB_C172X1) CK(FB_DISPATCH(s, avionics_init)(s));   // f_init!(avionics, vehicle)
     CK(cudaMemsetAsync(s->d_ev_cursor, 0, sizeof(long long) * s->pitch, s->stream));
+    // A member that stops stepping (crash, altitude bounds, failed trim) writes no further samples: every sample starts
+    // out as NaN, so that what a frozen member never wrote reads as missing rather than as stale memory; the moments
+    // count the members that did write.
+    if (s->E.log) {
+        const long long total = s->E.log_capacity * s->E.log_n_fields * s->pitch;
+        fill_kernel<<<(int)std::min<long long>((total + 255) / 256, 1 << 20), 256, 0, s->stream>>>(s->E.log, total, nan(""));
+        CK(cudaGetLastError());
+    }
+    moments_reset_kernel<<<(int)((s->mom_records + 255) / 256), 256, 0, s->stream>>>(mom_view(s), 0, s->mom_records);
+    CK(cudaGetLastError());
+    s->reduced_upto = 0;
     // log sample 0 = y left by f_init! (sim.jl:405-408)
     for (int f = 0; f < s->E.log_n_fields; f++) {
-        CK(FB_DISPATCH(s, output)(s, s->cfg.log_fields[f], s->E.log + (long long)f * s->pitch));
+        double* row = s->E.log ? s->E.log + (long long)f * s->pitch : s->d_scratch;
+        CK(FB_DISPATCH(s, output)(s, s->cfg.log_fields[f], row));
+        if (s->E.mom_cnt) {
+            moments_kernel<<<(int)((s->E.n + 255) / 256), 256, 0, s->stream>>>(s->E, row, f);
+            CK(cudaGetLastError());
+        }
     }
     return FB_OK;
 }
@@ -539,7 +653,7 @@ int32_t fb_init_trim(fb_handle s, const fb_trim_params_soa* p, double* trim_stat
         CK(cudaMalloc(&d_ts, sizeof(double) * 7 * s->pitch));
         CK(cudaMalloc(&d_cost, sizeof(double) * s->pitch));
         CK(FB_DISPATCH(s, trim)(s, P, d_ts, d_cost));
-        if (trim_state_out) CK(cudaMemcpy2DAsync(trim_state_out, sizeof(double) * s->E.n, d_ts, sizeof(double) * s->pitch, sizeof(double) * s->E.n, 7, cudaMemcpyDeviceToHost, s->stream));
+        if (trim_state_out) CK(cudaMemcpy2DAsync(trim_state_out, hp(s), d_ts, sizeof(double) * s->pitch, sizeof(double) * s->E.n, 7, cudaMemcpyDeviceToHost, s->stream));
         if (cost_out) CK(cudaMemcpyAsync(cost_out, d_cost, sizeof(double) * s->E.n, cudaMemcpyDeviceToHost, s->stream));
         CK(cudaStreamSynchronize(s->stream));
     }
@@ -704,7 +818,7 @@ int32_t fb_nx(fb_handle s, int32_t* nx) { if (!s || !nx) return fail(FB_ERR_ARG,
 int32_t fb_get_state(fb_handle s, double* x) {
     if (!s || !x) return fail(FB_ERR_ARG, "fb_get_state: null argument");
     CK(cudaSetDevice(s->cfg.device));
-    CK(cudaMemcpy2DAsync(x, sizeof(double) * s->E.n, s->E.x, sizeof(double) * s->pitch, sizeof(double) * s->E.n, s->nx, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpy2DAsync(x, hp(s), s->E.x, sizeof(double) * s->pitch, sizeof(double) * s->E.n, s->nx, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     return FB_OK;
 }
@@ -776,9 +890,9 @@ int32_t fb_log_info(fb_handle s, int64_t* n_samples, int32_t* n_fields) {
 }
 
 int32_t fb_log_times(fb_handle s, double* t) {
+    if (!s || !t) return fail(FB_ERR_ARG, "fb_log_times: null argument");
     int64_t ns; int32_t nf;
     fb_log_info(s, &ns, &nf);
-    if (!t) return fail(FB_ERR_ARG, "null argument");
     for (int64_t k = 0; k < ns; k++) t[k] = s->cfg.t_start + (double)(k * s->E.log_every) * s->cfg.dt;
     return FB_OK;
 }
@@ -790,6 +904,7 @@ int32_t fb_log_fetch(fb_handle s, int32_t field, double* out) {
     int fi = -1;
     for (int f = 0; f < nf; f++) if (s->cfg.log_fields[f] == field) fi = f;
     if (fi < 0) return fail(FB_ERR_ARG, "fb_log_fetch: field is not logged");
+    if (!s->E.log) return fail(FB_ERR_STATE, "fb_log_fetch: the per-member samples are not kept (log_flags = FB_LOG_MOMENTS); use fb_log_stats");
     CK(cudaSetDevice(s->cfg.device));
     // sample k of field fi lives at log[(k * nf + fi) * pitch]
     CK(cudaMemcpy2DAsync(out, sizeof(double) * s->E.n, s->E.log + (long long)fi * s->pitch, sizeof(double) * s->pitch * nf,
@@ -798,21 +913,175 @@ int32_t fb_log_fetch(fb_handle s, int32_t field, double* out) {
     return FB_OK;
 }
 
+static void moments_from_raw(const char* raw, long long R, long long r, fb_moments* out) {
+    unsigned long long c; double sm[2], mn, mx;
+    memcpy(&c, raw + r * 8, 8); memcpy(sm, raw + R * 8 + r * 16, 16); memcpy(&mn, raw + R * 24 + r * 8, 8); memcpy(&mx, raw + R * 32 + r * 8, 8);
+    out->count = (int64_t)c; out->sum = sm[0]; out->sum_sq = sm[1]; out->min = mn; out->max = mx;
+}
+
 int32_t fb_stats(fb_handle s, int32_t field, fb_moments* out) {
     if (!s || !out) return fail(FB_ERR_ARG, "fb_stats: null argument");
     if (field < 0 || field >= FB_Y__COUNT) return fail(FB_ERR_ARG, "fb_stats: unknown field");
     if (!s->initialised) return fail(FB_ERR_STATE, "fb_stats: not initialised");
     CK(cudaSetDevice(s->cfg.device));
+    const long long R = s->mom_records, rec = R - 1;   // the scratch record
     CK(FB_DISPATCH(s, output)(s, field, s->d_scratch));
-    double init[5] = {0.0, 0.0, 0.0, INFINITY, -INFINITY};
-    CK(cudaMemcpyAsync(s->d_stats, init, sizeof(init), cudaMemcpyHostToDevice, s->stream));
-    int grid = (int)((s->E.n + 255) / 256);
-    stats_kernel<<<grid, 256, 0, s->stream>>>(s->d_scratch, s->E.status, s->E.n, s->d_stats);
+    moments_reset_kernel<<<1, 32, 0, s->stream>>>(mom_view(s), rec, 1);
+    moments_kernel<<<(int)((s->E.n + 255) / 256), 256, 0, s->stream>>>(mom_view(s), s->d_scratch, rec);
     CK(cudaGetLastError());
-    double r[5];
-    CK(cudaMemcpyAsync(r, s->d_stats, sizeof(r), cudaMemcpyDeviceToHost, s->stream));
+    char raw[40];   // one record gathered from the four arrays
+    CK(cudaMemcpyAsync(raw, s->m_cnt + rec, 8, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(raw + 8, s->m_sum + 2 * rec, 16, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(raw + 24, s->m_min + rec, 8, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(raw + 32, s->m_max + rec, 8, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
-    out->count = (int64_t)r[0]; out->sum = r[1]; out->sum_sq = r[2]; out->min = r[3]; out->max = r[4];
+    moments_from_raw(raw, 1, 0, out);
+    return FB_OK;
+}
+
+int32_t fb_log_stats_begin(fb_handle s, int64_t first, int64_t count) {
+    if (!s) return fail(FB_ERR_ARG, "null handle");
+    if (!s->E.mom_cnt) return fail(FB_ERR_STATE, "fb_log_stats: no moments are kept (no log configured, or log_flags without FB_LOG_MOMENTS)");
+    int64_t ns; int32_t nf;
+    fb_log_info(s, &ns, &nf);
+    if (first < 0 || count <= 0 || first + count > ns) return fail(FB_ERR_ARG, "fb_log_stats: sample range outside the samples taken so far");
+    CK(cudaSetDevice(s->cfg.device));
+    if (s->mom_pending) { CK(cudaEventSynchronize(s->mom_done)); s->mom_pending = false; }
+    const size_t need = (size_t)count * nf * 40;
+    if (need > s->h_mom_bytes) {
+        if (s->h_mom) cudaFreeHost(s->h_mom);
+        s->h_mom = nullptr; s->h_mom_bytes = 0;
+        CK(cudaMallocHost(&s->h_mom, need));
+        s->h_mom_bytes = need;
+    }
+    // behind everything submitted so far on the launch stream and behind a pending all-reduce
+    CK(cudaEventRecord(s->mom_ready, s->stream));
+    CK(cudaStreamWaitEvent(s->snap_stream, s->mom_ready, 0));
+    if (s->comm_busy) CK(cudaStreamWaitEvent(s->snap_stream, s->comm_out, 0));
+    const long long r0 = first * nf, n = count * nf;
+    CK(cudaMemcpyAsync(s->h_mom, s->m_cnt + r0, n * 8, cudaMemcpyDeviceToHost, s->snap_stream));
+    CK(cudaMemcpyAsync(s->h_mom + n * 8, s->m_sum + 2 * r0, n * 16, cudaMemcpyDeviceToHost, s->snap_stream));
+    CK(cudaMemcpyAsync(s->h_mom + n * 24, s->m_min + r0, n * 8, cudaMemcpyDeviceToHost, s->snap_stream));
+    CK(cudaMemcpyAsync(s->h_mom + n * 32, s->m_max + r0, n * 8, cudaMemcpyDeviceToHost, s->snap_stream));
+    CK(cudaEventRecord(s->mom_done, s->snap_stream));
+    s->mom_pending = true; s->mom_first = first; s->mom_count = count;
+    return FB_OK;
+}
+
+int32_t fb_log_stats_end(fb_handle s, int32_t field, fb_moments* out) {
+    if (!s || !out) return fail(FB_ERR_ARG, "fb_log_stats_end: null argument");
+    if (s->mom_count <= 0) return fail(FB_ERR_STATE, "fb_log_stats_end: no fb_log_stats_begin before");
+    int fi = -1;
+    for (int f = 0; f < s->E.log_n_fields; f++) if (s->cfg.log_fields[f] == field) fi = f;
+    if (fi < 0) return fail(FB_ERR_ARG, "fb_log_stats: field is not logged");
+    CK(cudaSetDevice(s->cfg.device));
+    if (s->mom_pending) { CK(cudaEventSynchronize(s->mom_done)); s->mom_pending = false; }
+    const long long nf = s->E.log_n_fields, n = s->mom_count * nf;
+    for (long long k = 0; k < s->mom_count; k++) moments_from_raw(s->h_mom, n, k * nf + fi, out + k);
+    return FB_OK;
+}
+
+int32_t fb_log_stats(fb_handle s, int32_t field, int64_t first, int64_t count, fb_moments* out) {
+    if (!out) return fail(FB_ERR_ARG, "fb_log_stats: null argument");
+    int32_t rc = fb_log_stats_begin(s, first, count);
+    return rc != FB_OK ? rc : fb_log_stats_end(s, field, out);
+}
+
+// ------------------------------------------------------------------------------------------------ sharded ensembles
+int32_t fb_comm_unique_id(void* id128) {
+    if (!id128) return fail(FB_ERR_ARG, "fb_comm_unique_id: null argument");
+    NcclApi* N = nccl_api();
+    if (!N) return fail(FB_ERR_STATE, "fb_comm_unique_id: NCCL (libnccl.so.2) could not be loaded");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NK(N->GetUniqueId(&id));
+    memcpy(id128, &id, 128);
+    return FB_OK;
+}
+
+static int32_t comm_prepare(fb_sim* s) {   // side stream + events of the all-reduce
+    if (!s->comm_stream) {
+        CK(cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&s->comm_in, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s->comm_out, cudaEventDisableTiming));
+    }
+    return FB_OK;
+}
+
+int32_t fb_comm_init(fb_handle s, int32_t n_ranks, int32_t rank, const void* id128) {
+    if (!s || !id128) return fail(FB_ERR_ARG, "fb_comm_init: null argument");
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(FB_ERR_ARG, "fb_comm_init: bad rank / n_ranks");
+    if (s->comm) return fail(FB_ERR_STATE, "fb_comm_init: the handle already has a communicator");
+    NcclApi* N = nccl_api();
+    if (!N) return fail(FB_ERR_STATE, "fb_comm_init: NCCL (libnccl.so.2) could not be loaded");
+    CK(cudaSetDevice(s->cfg.device));
+    ncclUniqueId id; memcpy(&id, id128, 128);
+    NK(N->CommInitRank(&s->comm, n_ranks, id, rank));
+    s->comm_owned = true; s->comm_ranks = n_ranks;
+    return comm_prepare(s);
+}
+
+// enqueue the all-reduce of the log samples [reduced_upto, upto) on the side stream (inside an NCCL group when the caller
+// drives several communicators from one thread)
+static int32_t stats_allreduce_enqueue(fb_sim* s, long long upto) {
+    NcclApi* N = nccl_api();
+    const long long nf = s->E.log_n_fields, r0 = s->reduced_upto * nf, n = (upto - s->reduced_upto) * nf;
+    NK(N->AllReduce(s->m_cnt + r0, s->m_cnt + r0, (size_t)n, ncclUint64, ncclSum, s->comm, s->comm_stream));
+    NK(N->AllReduce(s->m_sum + 2 * r0, s->m_sum + 2 * r0, (size_t)(2 * n), ncclFloat64, ncclSum, s->comm, s->comm_stream));
+    NK(N->AllReduce(s->m_min + r0, s->m_min + r0, (size_t)n, ncclFloat64, ncclMin, s->comm, s->comm_stream));
+    NK(N->AllReduce(s->m_max + r0, s->m_max + r0, (size_t)n, ncclFloat64, ncclMax, s->comm, s->comm_stream));
+    return FB_OK;
+}
+static int32_t stats_allreduce_pre(fb_sim* s, long long* upto) {
+    if (!s->comm) return fail(FB_ERR_STATE, "fb_log_stats_allreduce: no communicator (fb_comm_init / fb_group_create)");
+    if (!s->E.mom_cnt) return fail(FB_ERR_STATE, "fb_log_stats_allreduce: no moments are kept");
+    int64_t ns; int32_t nf;
+    fb_log_info(s, &ns, &nf);
+    *upto = ns;
+    if (ns <= s->reduced_upto) return FB_OK;
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaEventRecord(s->comm_in, s->stream));                 // the samples are final once the launches so far have run
+    CK(cudaStreamWaitEvent(s->comm_stream, s->comm_in, 0));
+    if (s->mom_pending) CK(cudaStreamWaitEvent(s->comm_stream, s->mom_done, 0));   // a fetch in flight reads the same arrays
+    cudaEvent_t t0, t1;
+    CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
+    s->comm_timers.push_back({t0, t1});
+    CK(cudaEventRecord(t0, s->comm_stream));
+    return FB_OK;
+}
+static int32_t stats_allreduce_post(fb_sim* s, long long upto) {
+    if (upto <= s->reduced_upto) return FB_OK;
+    CK(cudaSetDevice(s->cfg.device));
+    CK(cudaEventRecord(s->comm_timers.back().second, s->comm_stream));
+    CK(cudaEventRecord(s->comm_out, s->comm_stream));
+    s->comm_busy = true; s->reduced_upto = upto; s->comm_calls++;
+    return FB_OK;
+}
+
+int32_t fb_log_stats_allreduce(fb_handle s) {
+    if (!s) return fail(FB_ERR_ARG, "null handle");
+    long long upto = 0;
+    int32_t rc = stats_allreduce_pre(s, &upto);
+    if (rc != FB_OK || upto <= s->reduced_upto) return rc;
+    NcclApi* N = nccl_api();
+    NK(N->GroupStart());
+    rc = stats_allreduce_enqueue(s, upto);
+    NK(N->GroupEnd());
+    return rc != FB_OK ? rc : stats_allreduce_post(s, upto);
+}
+
+int32_t fb_comm_time(fb_handle s, double* ms_total, int64_t* n_calls) {
+    if (!s) return fail(FB_ERR_ARG, "null handle");
+    CK(cudaSetDevice(s->cfg.device));
+    if (s->comm_stream) CK(cudaStreamSynchronize(s->comm_stream));
+    for (auto& t : s->comm_timers) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, t.first, t.second) == cudaSuccess) s->comm_ms += ms; else (void)cudaGetLastError();
+        cudaEventDestroy(t.first); cudaEventDestroy(t.second);
+    }
+    s->comm_timers.clear();
+    if (ms_total) *ms_total = s->comm_ms;
+    if (n_calls) *n_calls = s->comm_calls;
     return FB_OK;
 }
 
@@ -1081,6 +1350,146 @@ int32_t fb_stream(fb_handle s, void** stream) {
     if (!s || !stream) return fail(FB_ERR_ARG, "null argument");
     *stream = (void*)s->stream;
     return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ one process, several GPUs
+struct fb_group {
+    std::vector<fb_sim*> sims;
+    std::vector<long long> off;      // off[k] .. off[k + 1]: global members of shard k
+    long long n = 0;
+};
+#define GK(call) do { int32_t rc_ = (call); if (rc_ != FB_OK) return rc_; } while (0)
+
+int32_t fb_group_destroy(fb_group_handle g) {
+    if (!g) return FB_OK;
+    for (fb_sim* s : g->sims) fb_destroy(s);
+    delete g;
+    return FB_OK;
+}
+
+int32_t fb_group_create(const fb_config* cfg, const int32_t* devices, int32_t n_dev, fb_group_handle* out) {
+    if (!cfg || !devices || !out) return fail(FB_ERR_ARG, "fb_group_create: null argument");
+    *out = nullptr;
+    if (n_dev < 1 || cfg->n_members < n_dev) return fail(FB_ERR_ARG, "fb_group_create: need at least one device and one member per device");
+    for (int a = 0; a < n_dev; a++) for (int b = 0; b < a; b++) if (devices[a] == devices[b]) return fail(FB_ERR_ARG, "fb_group_create: a device is listed twice");
+    NcclApi* N = n_dev > 1 ? nccl_api() : nullptr;
+    if (n_dev > 1 && !N) return fail(FB_ERR_STATE, "fb_group_create: NCCL (libnccl.so.2) could not be loaded");
+    fb_group* g = new fb_group();
+    g->n = cfg->n_members;
+    g->off.resize(n_dev + 1);
+    for (int k = 0; k <= n_dev; k++) g->off[k] = (k == n_dev) ? g->n : (g->n * k + n_dev - 1) / n_dev;   // contiguous blocks
+    for (int k = 0; k < n_dev; k++) {
+        fb_config c = *cfg;
+        c.device = devices[k]; c.member_offset = g->off[k]; c.n_members = g->off[k + 1] - g->off[k];
+        fb_sim* s = nullptr;
+        int32_t rc = fb_create(&c, &s);
+        if (rc != FB_OK) { std::string msg = g_err; fb_group_destroy(g); g_err = msg; return rc; }
+        g->sims.push_back(s);
+    }
+    if (n_dev > 1) {
+        std::vector<ncclComm_t> comms(n_dev);
+        std::vector<int> devs(devices, devices + n_dev);
+        ncclResult_t r = N->CommInitAll(comms.data(), n_dev, devs.data());
+        if (r != ncclSuccess) { fb_group_destroy(g); return fail(FB_ERR_CUDA, std::string("ncclCommInitAll: ") + N->GetErrorString(r)); }
+        for (int k = 0; k < n_dev; k++) {
+            g->sims[k]->comm = comms[k]; g->sims[k]->comm_owned = true; g->sims[k]->comm_ranks = n_dev;
+            cudaSetDevice(devices[k]);
+            int32_t rc = comm_prepare(g->sims[k]);
+            if (rc != FB_OK) { std::string msg = g_err; fb_group_destroy(g); g_err = msg; return rc; }
+        }
+    }
+    *out = g;
+    return FB_OK;
+}
+
+int32_t fb_group_size(fb_group_handle g, int32_t* n_dev) {
+    if (!g || !n_dev) return fail(FB_ERR_ARG, "fb_group_size: null argument");
+    *n_dev = (int32_t)g->sims.size();
+    return FB_OK;
+}
+int32_t fb_group_shard(fb_group_handle g, int32_t k, fb_handle* h, int64_t* offset, int64_t* count) {
+    if (!g) return fail(FB_ERR_ARG, "null group");
+    if (k < 0 || k >= (int)g->sims.size()) return fail(FB_ERR_ARG, "fb_group_shard: no such shard");
+    if (h) *h = g->sims[k];
+    if (offset) *offset = g->off[k];
+    if (count) *count = g->off[k + 1] - g->off[k];
+    return FB_OK;
+}
+int32_t fb_group_load_tables(fb_group_handle g, const void* blob, size_t nbytes) {
+    if (!g) return fail(FB_ERR_ARG, "null group");
+    for (fb_sim* s : g->sims) GK(fb_load_tables(s, blob, nbytes));
+    return FB_OK;
+}
+int32_t fb_group_init_trim(fb_group_handle g, const fb_trim_params_soa* p, double* trim_state_out, double* cost_out) {
+    if (!g) return fail(FB_ERR_ARG, "null group");
+    fb_trim_params_soa z; memset(&z, 0, sizeof(z));
+    if (!p) p = &z;
+    for (size_t k = 0; k < g->sims.size(); k++) {
+        const long long o = g->off[k];
+        auto sh = [&](const double* a) { return a ? a + o : nullptr; };   // every field is its own [N] array: a shard is a pointer offset
+        fb_trim_params_soa q;
+        q.lat = sh(p->lat); q.lon = sh(p->lon); q.h_e = sh(p->h_e); q.psi_nb = sh(p->psi_nb); q.EAS = sh(p->EAS); q.gamma_wb_n = sh(p->gamma_wb_n);
+        q.psi_wb_dot = sh(p->psi_wb_dot); q.theta_wb_dot = sh(p->theta_wb_dot); q.beta_a = sh(p->beta_a); q.fuel_load = sh(p->fuel_load);
+        q.mixture = sh(p->mixture); q.flaps = sh(p->flaps);
+        for (int j = 0; j < 5; j++) q.payload[j] = sh(p->payload[j]);
+        fb_sim* s = g->sims[k];
+        s->host_pitch = g->n;
+        int32_t rc = fb_init_trim(s, &q, trim_state_out ? trim_state_out + o : nullptr, cost_out ? cost_out + o : nullptr);
+        s->host_pitch = 0;
+        GK(rc);
+    }
+    return FB_OK;
+}
+int32_t fb_group_set_input(fb_group_handle g, int32_t field, const double* values, int64_t stride) {
+    if (!g || !values) return fail(FB_ERR_ARG, "fb_group_set_input: null argument");
+    for (size_t k = 0; k < g->sims.size(); k++) GK(fb_set_input(g->sims[k], field, values + (stride ? g->off[k] : 0), stride));
+    return FB_OK;
+}
+int32_t fb_group_step(fb_group_handle g, double t_advance) {   // launches are asynchronous: the shards advance concurrently
+    if (!g) return fail(FB_ERR_ARG, "null group");
+    for (fb_sim* s : g->sims) GK(fb_step(s, t_advance));
+    return FB_OK;
+}
+int32_t fb_group_run(fb_group_handle g) {
+    if (!g) return fail(FB_ERR_ARG, "null group");
+    for (fb_sim* s : g->sims) GK(fb_run(s));
+    return FB_OK;
+}
+int32_t fb_group_sync(fb_group_handle g) {
+    if (!g) return fail(FB_ERR_ARG, "null group");
+    for (fb_sim* s : g->sims) GK(fb_sync(s));
+    return FB_OK;
+}
+int32_t fb_group_get_state(fb_group_handle g, double* x) {
+    if (!g || !x) return fail(FB_ERR_ARG, "fb_group_get_state: null argument");
+    for (size_t k = 0; k < g->sims.size(); k++) {
+        fb_sim* s = g->sims[k];
+        s->host_pitch = g->n;
+        int32_t rc = fb_get_state(s, x + g->off[k]);
+        s->host_pitch = 0;
+        GK(rc);
+    }
+    return FB_OK;
+}
+int32_t fb_group_status(fb_group_handle g, int32_t* status) {
+    if (!g || !status) return fail(FB_ERR_ARG, "fb_group_status: null argument");
+    for (size_t k = 0; k < g->sims.size(); k++) GK(fb_status(g->sims[k], status + g->off[k]));
+    return FB_OK;
+}
+int32_t fb_group_log_stats(fb_group_handle g, int32_t field, int64_t first, int64_t count, fb_moments* out) {
+    if (!g || !out) return fail(FB_ERR_ARG, "fb_group_log_stats: null argument");
+    if (g->sims.size() > 1) {
+        NcclApi* N = nccl_api();
+        std::vector<long long> upto(g->sims.size(), 0);
+        for (size_t k = 0; k < g->sims.size(); k++) GK(stats_allreduce_pre(g->sims[k], &upto[k]));
+        if (upto[0] > g->sims[0]->reduced_upto) {
+            NK(N->GroupStart());   // one thread drives every communicator of the clique
+            for (size_t k = 0; k < g->sims.size(); k++) { int32_t rc = stats_allreduce_enqueue(g->sims[k], upto[k]); if (rc != FB_OK) { N->GroupEnd(); return rc; } }
+            NK(N->GroupEnd());
+            for (size_t k = 0; k < g->sims.size(); k++) GK(stats_allreduce_post(g->sims[k], upto[k]));
+        }
+    }
+    return fb_log_stats(g->sims[0], field, first, count, out);
 }
 
 }  // extern "C"

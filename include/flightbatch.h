@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FB_API_VERSION 3
+#define FB_API_VERSION 4
 
 /* error codes */
 #define FB_OK 0
@@ -136,7 +136,12 @@ typedef struct fb_config {
     int32_t log_n_fields;   /* number of entries of log_fields                      */
     int32_t log_fields[32]; /* fb_output ids to log                                 */
     int32_t steps_per_launch; /* K: RK4 steps fused per kernel launch (0 = default) */
+    int32_t log_flags;      /* FB_LOG_* bits; 0 = FB_LOG_MEMBERS | FB_LOG_MOMENTS                       */
 } fb_config;
+/* what a log sample keeps: every member's value (TimeSeries(sim), sim.jl:644-704) and / or the ensemble moments of the
+ * logged fields, reduced inside the integrator as the sample is taken (no reference counterpart: one Simulation = one aircraft) */
+#define FB_LOG_MEMBERS 1
+#define FB_LOG_MOMENTS 2
 
 /* C172.TrimParameters — lib/FlightApps/src/c172/c172.jl:806-818, struct-of-arrays; NULL = default */
 typedef struct fb_trim_params_soa {
@@ -227,7 +232,51 @@ int32_t fb_status(fb_handle h, int32_t* status);
 int32_t fb_log_info(fb_handle h, int64_t* n_samples, int32_t* n_fields);
 int32_t fb_log_times(fb_handle h, double* t);                        /* [n_samples] */
 int32_t fb_log_fetch(fb_handle h, int32_t field, double* out);       /* [n_samples][N] */
+/* moments of output `field` over the members with status RUNNING or DONE, at the current state (one output pass + one
+ * warp-shuffle reduction kernel; blocking) */
 int32_t fb_stats(fb_handle h, int32_t field, fb_moments* out);
+/* Moments of a LOGGED field at log samples [first, first + count), accumulated by the integrator itself when each sample
+ * was taken (warp reduction + one atomic set per warp; members frozen before the sample are not counted). After
+ * fb_log_stats_allreduce they are the moments of the whole sharded ensemble. fb_log_stats_begin enqueues the device-to-
+ * host copy on the read-back stream behind the work submitted so far and returns at once; fb_log_stats_end waits for it
+ * and writes out[count] for one field; fb_log_stats = begin + end. */
+int32_t fb_log_stats_begin(fb_handle h, int64_t first, int64_t count);
+int32_t fb_log_stats_end(fb_handle h, int32_t field, fb_moments* out);
+int32_t fb_log_stats(fb_handle h, int32_t field, int64_t first, int64_t count, fb_moments* out);
+
+/* ---- sharded ensembles --------------------------------------------------------------------------
+ * The path shards by member with no data-path collective; the one exchange is the all-reduce of the
+ * ensemble moments, which the library owns (NCCL, loaded at run time; a side stream, never the launch stream).
+ * One process per GPU: rank 0 calls fb_comm_unique_id, the host distributes the 128 bytes by any means (MPI, torch,
+ * a file), every rank calls fb_comm_init on its handle. fb_log_stats_allreduce then combines, in place on the device,
+ * the moments of every log sample completed since the previous call (SUM of count / sum / sum of squares, MIN, MAX)
+ * over all ranks; it is asynchronous, and every rank must call it at the same simulation time. */
+int32_t fb_comm_unique_id(void* id128);
+int32_t fb_comm_init(fb_handle h, int32_t n_ranks, int32_t rank, const void* id128);
+int32_t fb_log_stats_allreduce(fb_handle h);
+/* device time spent in the all-reduces so far (CUDA events on the side stream; waits for them) and their number */
+int32_t fb_comm_time(fb_handle h, double* ms_total, int64_t* n_calls);
+
+/* One process driving several GPUs: Simulation(...) over `n_members` members sharded in contiguous blocks over the
+ * devices devices[0..n_dev) (cfg->device and cfg->member_offset are ignored), with an in-library NCCL communicator for
+ * the moments. Host arrays passed to the fb_group_* calls are GLOBAL ([C][n_members]); the group scatters / gathers
+ * the shards. fb_group_shard returns the handle of shard k for everything else (per-shard fb_* calls take shard-local
+ * arrays of `count` members starting at global member `offset`). */
+typedef struct fb_group* fb_group_handle;
+int32_t fb_group_create(const fb_config* cfg, const int32_t* devices, int32_t n_dev, fb_group_handle* out);
+int32_t fb_group_destroy(fb_group_handle g);
+int32_t fb_group_size(fb_group_handle g, int32_t* n_dev);
+int32_t fb_group_shard(fb_group_handle g, int32_t k, fb_handle* h, int64_t* offset, int64_t* count);
+int32_t fb_group_load_tables(fb_group_handle g, const void* blob, size_t nbytes);
+int32_t fb_group_init_trim(fb_group_handle g, const fb_trim_params_soa* p, double* trim_state_out, double* cost_out);
+int32_t fb_group_set_input(fb_group_handle g, int32_t field, const double* values, int64_t stride);
+int32_t fb_group_step(fb_group_handle g, double t_advance);   /* every shard advances concurrently */
+int32_t fb_group_run(fb_group_handle g);
+int32_t fb_group_sync(fb_group_handle g);
+int32_t fb_group_get_state(fb_group_handle g, double* x);      /* [nx][n_members] */
+int32_t fb_group_status(fb_group_handle g, int32_t* status);   /* [n_members] */
+/* all-reduce of the samples completed so far + fetch of samples [first, first + count) of one logged field */
+int32_t fb_group_log_stats(fb_group_handle g, int32_t field, int64_t first, int64_t count, fb_moments* out);
 
 /* ---- linearisation -------------------------------------------------------------------------
  * linearize(aircraft, trim_params) : lib/FlightPhysics/src/aircraftbase.jl:292-341 -> linearization.jl:55-111, for every

@@ -16,6 +16,29 @@ def build():
     subprocess.check_call(["make", "-s", "-C", _HERE])
 
 
+FAST_FLAGS = "-O3 -march=native"
+
+
+def _fast_name():
+    """liborc_fast_<hash of this host's CPU flags>.so: the -march=native timing build is only valid where it was built."""
+    import hashlib
+    flags = ""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                flags = line
+                break
+    except OSError:
+        pass
+    return "liborc_fast_%s.so" % hashlib.sha1(flags.encode()).hexdigest()[:10]
+
+
+def build_fast():
+    name = _fast_name()
+    subprocess.check_call(["make", "-s", "-C", _HERE, name])
+    return name
+
+
 def _load(name):
     path = os.path.join(_HERE, name)
     if not os.path.exists(path):
@@ -81,8 +104,8 @@ def _load(name):
 _libs = {}
 
 
-def lib(counting=False):
-    key = "liborc_count.so" if counting else "liborc.so"
+def lib(counting=False, fast=False):
+    key = build_fast() if fast else ("liborc_count.so" if counting else "liborc.so")
     if key not in _libs:
         _libs[key] = _load(key)
     return _libs[key]
@@ -106,8 +129,8 @@ INIT_KEYS = list(INIT_DEFAULT.keys())
 
 
 class World:
-    def __init__(self, counting=False):
-        self.lib = lib(counting)
+    def __init__(self, counting=False, fast=False):
+        self.lib = lib(counting, fast)
         self.h = self.lib.orc_world_create()
         assert self.h
 
@@ -125,17 +148,19 @@ class World:
 _world = {}
 
 
-def world(counting=False):
-    if counting not in _world:
-        _world[counting] = World(counting)
-    return _world[counting]
+def world(counting=False, fast=False):
+    key = (counting, fast)
+    if key not in _world:
+        _world[key] = World(counting, fast)
+    return _world[key]
 
 
 class Sim:
     """One reference `Simulation(SimpleWorld(Cessna172...); dt, Δt)` on the CPU oracle."""
 
-    def __init__(self, variant=0, kin=0, dt=0.02, Dt=None, counting=False):
-        self.w = world(counting)
+    def __init__(self, variant=0, kin=0, dt=0.02, Dt=None, counting=False, fast=False):
+        """fast=True: the -O3 -march=native timing build (bench.py's CPU arm); the checker is the default build."""
+        self.w = world(counting, fast)
         self.lib = self.w.lib
         self.h = self.lib.orc_sim_create(self.w.h, variant, kin, dt, dt if Dt is None else Dt)
         self.nx = self.lib.orc_sim_nx(self.h)

@@ -74,20 +74,31 @@ def build_cfg4(fb, orc, n, idx, dt=0.01):
     return simA, oracles, idx
 
 
+SPREAD_FACTOR = 5.0     # GPU-vs-oracle error allowed as a multiple of the oracle-vs-oracle rounding spread measured in the same test
+
+
 def test_cfg4_takeoff_and_landing_ensemble(fb, orc):
     """Discrete results (status, weight-on-wheels per strut, engine state, stall) are bit-exact at every sampled instant
-    over 25 s. Continuous states agree to the conditioning of the reference's own contact formulation, not to 1e-9: the
-    strut compression is a difference of 6.4e6 m ECEF vectors (landinggear.jl:262-270; ~1e-9 m noise -> 1e-7..1e-6 relative
-    on gear forces), and a member *at rest* on its gear sits on the reference's friction-direction switch at a wheel speed
-    of 1e-3 m/s (landinggear.jl:436-452), which amplifies that noise to ~1e-4 m/s. Hence: median member error < 1e-6,
-    every member < 5e-3 (absolute, SI units, floor 1) on the physical states; the friction-regulator integrators of a resting
-    member (bounded, |x| <= 1, no physical meaning at zero speed) are only held to the median bound."""
+    over 25 s. Continuous states cannot agree to 1e-9 on this path for ANY two implementations that round differently: the
+    reference computes the strut compression from a difference of 6.4e6 m ECEF vectors (landinggear.jl:262-270) and a member
+    at rest sits on the friction-direction switch at 1e-3 m/s (landinggear.jl:436-452). The bound is therefore MEASURED, not
+    picked: the same members are run on two builds of the oracle that differ only in rounding (FMA contraction on / off;
+    tests/ground_util.py), and at every instant the GPU-vs-oracle error (median over members of the all-state error, maximum
+    over members of the physical-state error) must stay within SPREAD_FACTOR times the largest oracle-vs-oracle spread seen
+    up to that instant. While every strut is still unloaded (first instant) the airborne bound 1e-9 applies."""
+    import ground_util as gu
     n = 64
     idx = list(range(0, n, 2))
     sim, oracles, idx = build_cfg4(fb, orc, n, idx)
+    # the oracle-vs-oracle spread from the very same initial states, inputs and schedules
+    x0 = np.array([o.x for o in oracles]).T
+    disc = np.array([o.discrete for o in oracles])
+    inputs = {f: sim.get_input(f)[idx] for f in gu.INPUT_FIELDS}
+    events = [gu.cfg4_events(fb.U, i, n // 2, inputs["elevator"][k]) for k, i in enumerate(idx)]
+    spread = gu.oracle_spread(orc, fb.U, fb.INPUT_NAMES, x0, disc[:, 0], disc[:, 1], inputs, events)
     seen_wow, seen_eng = set(), set(int(v) for v in sim.discrete()[1])
-    worst_med, worst_max = 0.0, 0.0
-    for chunk in [1, 49, 50, 100, 100] + [200] * 11:
+    worst_med, worst_max, run_med, run_max, worst_ratio = 0.0, 0.0, 0.0, 0.0, 0.0
+    for chunk, sp in zip(gu.CHUNKS, spread):
         sim.step(chunk * 0.01)
         for o in oracles:
             o.step(chunk)
@@ -103,16 +114,20 @@ def test_cfg4_takeoff_and_landing_ensemble(fb, orc):
             assert np.array_equal(wg, wo), (k, np.nonzero(wg != wo))
             seen_wow |= set(int(v) for v in wg)
         seen_eng |= set(int(v) for v in eng_g)
-        e_all = np.abs(xg - xo) / np.maximum(np.abs(xo), 1.0)
-        err = e_all.max(axis=0)                                   # every state, per member
-        phys = np.delete(e_all, np.arange(2, 8), axis=0).max(axis=0)   # without the six friction-regulator integrators
-        worst_med = max(worst_med, float(np.median(err))); worst_max = max(worst_max, float(phys.max()))
-        assert np.median(err) < 1e-6 and phys.max() < 5e-3, (float(np.median(err)), float(phys.max()), int(phys.argmax()))
+        err, phys = gu.member_errors(xg, xo)
+        run_med = max(run_med, float(np.median(sp["fma"][0])), float(np.median(sp["ulp"][0])))
+        run_max = max(run_max, float(sp["fma"][1].max()), float(sp["ulp"][1].max()))
+        med, mx = float(np.median(err)), float(phys.max())
+        worst_med = max(worst_med, med); worst_max = max(worst_max, mx)
+        worst_ratio = max(worst_ratio, med / max(run_med, 1e-9), mx / max(run_max, 1e-9))
+        assert med <= max(SPREAD_FACTOR * run_med, 1e-9), (med, run_med)
+        assert mx <= max(SPREAD_FACTOR * run_max, 1e-9), (mx, run_max, int(phys.argmax()))
     assert seen_wow == {0, 1} and seen_eng == {0, 1, 2}      # contact made and lost, engine off -> starting -> running
     # the takeoff half flew away, the approach half is rolling or stopped on the runway
     wow_any = np.maximum.reduce([sim.get_output(k) for k in ("wow_left", "wow_right", "wow_nose")])
     assert wow_any[: n // 2].mean() < 0.5 and wow_any[n // 2:].mean() > 0.9
-    print("cfg4 median / max member error", worst_med, worst_max)
+    print(f"cfg4 GPU-vs-oracle median / max member error {worst_med:.3e} / {worst_max:.3e}; oracle-vs-oracle spread {run_med:.3e} / {run_max:.3e}; "
+          f"worst ratio {worst_ratio:.2f} (allowed {SPREAD_FACTOR})")
     sim.close()
 
 
