@@ -300,8 +300,17 @@ def julia_reference(args, wl_name):
     if not julia or not os.path.isdir(proj) or not os.path.exists(script):
         return None
     threads = os.cpu_count() or 1
+    # the members the GPU arm integrates (same counter-based draws), as a text table the script reads
+    n_s = 64 * threads
+    p = cfg3_member_params(0, n_s) if wl_name == "cfg3" else member_params(0, n_s)
+    members = os.path.join(ROOT, "baseline", f"_members_{wl_name}.txt")
+    keys = list(p.keys())
+    with open(members, "w") as f:
+        f.write(" ".join(keys) + "\n")
+        for i in range(n_s):
+            f.write(" ".join(repr(float(p[k][i])) for k in keys) + "\n")
     try:
-        out = subprocess.run([julia, f"--project={proj}", f"--threads={threads}", script, wl_name, str(args.steps), str(args.warmup)],
+        out = subprocess.run([julia, f"--project={proj}", f"--threads={threads}", script, wl_name, members, str(args.steps), str(args.warmup)],
                              capture_output=True, text=True, timeout=1500)
         for line in reversed(out.stdout.splitlines()):
             if line.startswith("{"):
@@ -393,10 +402,14 @@ def main():
     ap.add_argument("--no-aux", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--save-peak", default="", help="write the FP64 probe result and its clock record to this JSON file")
+    ap.add_argument("--rk-per-step", type=int, default=0, help="diagnostic: RK4 steps fused per bench step / launch (default 100 = 1 s)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.rk_per_step > 0:
+        global RK_PER_STEP
+        RK_PER_STEP = args.rk_per_step
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

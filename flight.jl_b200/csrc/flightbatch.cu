@@ -269,7 +269,7 @@ static bool parse_blob(const uint8_t* b, size_t n, std::vector<BlobSec>& out) {
         BlobSec s; char nm[25]; memcpy(nm, r, 24); nm[24] = 0; s.name = nm;
         memcpy(&s.dtype, r + 24, 4); memcpy(&s.ndim, r + 28, 4); memcpy(s.dims, r + 32, 16);
         memcpy(&s.off, r + 48, 8); memcpy(&s.nbytes, r + 56, 8);
-        if (s.off + s.nbytes > n) return false;
+        if (s.off > n || s.nbytes > n - s.off) return false;   // (written so that a huge offset cannot wrap the sum)
         out.push_back(s);
     }
     return true;

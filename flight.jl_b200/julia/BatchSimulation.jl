@@ -1,6 +1,8 @@
 # BatchSimulation.jl — Julia host side of the B200 batched C172 engine (thin `ccall` layer over
 # include/flightbatch.h). SOURCE ONLY in this repository: Julia is not installed in the build image, so this file has
-# not been executed here; the same C ABI is exercised by the Python mirror (flight.jl_b200/__init__.py) in tests/.
+# not been executed here; the same C ABI is exercised by the Python mirror (flight.jl_b200/__init__.py) and by the C
+# driver tests/abi_driver.c, and tests/test_abi_and_host.py checks THIS file against the header mechanically: the layout
+# of every struct below (field by field against offsetof in C) and the arity of every `ccall` against its prototype.
 #
 # It mirrors the user surface of Flight.jl for N members stepped in lock-step:
 #   Simulation(world; dt, Δt, t_start, t_end, saveat)  lib/FlightCore/src/sim.jl:183-196  -> BatchSimulation(world, N; ...)
@@ -12,7 +14,7 @@
 module BatchSimulations
 
 export BatchSimulation, state_async!, wait_state, FlightBatchError, init!, step!, run!, setinput!, getinput, getoutput, schedule_inputs!, set_segment!, BatchTimeSeries, BatchLinearizedSS, getstate, getinputs, getoutputs, setinputs!, setstate!,
-       status, stats, linearize, TimeSeriesColumn
+       status, stats, linearize, TimeSeriesColumn, log_stats, comm_unique_id, comm_init!, log_stats_allreduce!
 
 const libflightbatch = get(ENV, "FLIGHTBATCH_LIB", joinpath(@__DIR__, "..", "libflightbatch.so"))
 const tables_path = get(ENV, "FLIGHTBATCH_TABLES", joinpath(@__DIR__, "..", "data", "c172_tables.bin"))
@@ -29,7 +31,7 @@ check(rc::Int32) = rc == 0 ? nothing : throw(FlightBatchError(rc, last_error()))
 # enums of include/flightbatch.h (kept in the same order; FB_API_VERSION is checked at load)
 @enum Variant::Int32 C172S = 0 C172X0 = 1 C172X1 = 2 C172X2 = 3
 @enum KinematicsKind::Int32 WA = 0 ECEF = 1 NED = 2
-const FB_API_VERSION = 3
+const FB_API_VERSION = 4
 
 # struct fb_config (must match the C layout field by field)
 struct FbConfig
@@ -46,6 +48,7 @@ struct FbConfig
     log_n_fields::Int32
     log_fields::NTuple{32,Int32}
     steps_per_launch::Int32
+    log_flags::Int32          # FB_LOG_MEMBERS (1) | FB_LOG_MOMENTS (2); 0 = both
 end
 
 mutable struct BatchSimulation
@@ -53,22 +56,23 @@ mutable struct BatchSimulation
     n::Int
     nx::Int
     dt::Float64
+    device::Int32
     log_fields::Vector{Int32}
     function BatchSimulation(variant::Variant, kin::KinematicsKind, n::Integer;
                              dt = 0.02, Δt = dt, t_start = 0.0, t_end = 10000.0, saveat = nothing,
-                             log_fields = Int32[], device = 0, member_offset = 0, steps_per_launch = 0)
+                             log_fields = Int32[], device = 0, member_offset = 0, steps_per_launch = 0, log_flags = 0)
         @assert ccall((:fb_api_version, libflightbatch), Int32, ()) == FB_API_VERSION
         lf = ntuple(i -> i <= length(log_fields) ? Int32(log_fields[i]) : Int32(0), 32)
         log_every = (saveat === nothing || isempty(log_fields)) ? 0 : max(1, round(Int, saveat / dt))
         cfg = Ref(FbConfig(Int32(variant), Int32(kin), n, member_offset, dt, Δt, t_start, t_end, device, log_every,
-                           length(log_fields), lf, steps_per_launch))
+                           length(log_fields), lf, steps_per_launch, log_flags))
         h = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:fb_create, libflightbatch), Int32, (Ref{FbConfig}, Ref{Ptr{Cvoid}}), cfg, h))
         blob = read(tables_path)
         GC.@preserve blob check(ccall((:fb_load_tables, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Csize_t), h[], blob, length(blob)))
         nx = Ref{Int32}(0)
         check(ccall((:fb_nx, libflightbatch), Int32, (Ptr{Cvoid}, Ref{Int32}), h[], nx))
-        sim = new(h[], n, nx[], dt, collect(Int32, log_fields))
+        sim = new(h[], n, nx[], dt, Int32(device), collect(Int32, log_fields))
         finalizer(s -> (s.handle != C_NULL && ccall((:fb_destroy, libflightbatch), Int32, (Ptr{Cvoid},), s.handle); s.handle = C_NULL), sim)
     end
 end
@@ -84,8 +88,9 @@ column(sim::BatchSimulation, v::AbstractVector) = (length(v) == sim.n || throw(A
     init!(sim; EAS = ..., h_e = ..., flaps = ..., ...)   # init!(sim, C172.TrimParameters(...)) for every member
 
 Each keyword is a scalar (broadcast) or a length-N vector. Returns `(success::BitVector, trim_state::Matrix (N×7), cost)`.
-Members whose trim does not reach the reference's stop value (cost ≤ 1e-16, c172.jl:927) get status 6, like the
-reference's `success = false` + warning (c172.jl:934-940).
+Members whose trim does not reach the reference's stop value (cost ≤ 1e-16, c172.jl:927) get status 6 and are frozen. This is
+a deliberate deviation: the reference only warns, assigns the best trim state found and keeps simulating (c172.jl:934-940);
+here a member that failed to trim is excluded from stepping and from every ensemble moment, and reported through `success`.
 """
 function init!(sim::BatchSimulation; kw...)
     cols = Dict{Symbol,Vector{Float64}}(k => column(sim, v) for (k, v) in kw)
@@ -190,6 +195,27 @@ function stats(sim::BatchSimulation, field::Integer)
     check(ccall((:fb_stats, libflightbatch), Int32, (Ptr{Cvoid}, Int32, Ref{Moments}), sim.handle, field, m)); m[]
 end
 
+"""
+    log_stats(sim, field, first, count) -> Vector{Moments}
+
+Ensemble moments of a logged `fb_output` field at log samples `first .. first + count - 1` (0-based), accumulated inside
+the integrator as each sample was taken; after `log_stats_allreduce!` they cover every shard of the ensemble.
+"""
+function log_stats(sim::BatchSimulation, field::Integer, first::Integer, count::Integer)
+    m = Vector{Moments}(undef, count)
+    check(ccall((:fb_log_stats, libflightbatch), Int32, (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Moments}), sim.handle, field, first, count, m)); m
+end
+
+"128-byte NCCL unique id: rank 0 creates it, the host distributes it (MPI.bcast, a file, ...), every rank calls `comm_init!`"
+function comm_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    check(ccall((:fb_comm_unique_id, libflightbatch), Int32, (Ptr{UInt8},), id)); id
+end
+comm_init!(sim::BatchSimulation, n_ranks::Integer, rank::Integer, id::Vector{UInt8}) =
+    check(ccall((:fb_comm_init, libflightbatch), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}), sim.handle, n_ranks, rank, id))
+"all-reduce (NCCL inside the library, side stream, asynchronous) of the moments of the log samples completed since the last call"
+log_stats_allreduce!(sim::BatchSimulation) = check(ccall((:fb_log_stats_allreduce, libflightbatch), Int32, (Ptr{Cvoid},), sim.handle))
+
 "TimeSeries(sim) column: `(t, values)` with `values` of size N × n_samples for one logged `fb_output` field"
 function TimeSeriesColumn(sim::BatchSimulation, field::Integer)
     ns = Ref{Int64}(0); nf = Ref{Int32}(0)
@@ -251,7 +277,7 @@ Base.propertynames(ts::BatchTimeSeries) = begin
 end
 
 """
-    linearize(sim)  ->  (A, B, C, D, x0, u0, y0)  # linearize(aircraft, trim_params), aircraftbase.jl:292-341
+    linearize(sim)  ->  (A, B, C, D, x0, u0, y0, ẋ0)  # linearize(aircraft, trim_params), aircraftbase.jl:292-341
 
 Forward-difference Jacobians of every member about its current (trimmed) state; arrays are `N × rows × cols`
 (member fastest, exactly the layout `fb_linearize` writes). Needs NED kinematics, like the reference's
@@ -264,9 +290,11 @@ function linearize(sim::BatchSimulation)
     A = Array{Float64}(undef, sim.n, nxs, nxs); B = Array{Float64}(undef, sim.n, nxs, nus)
     C = Array{Float64}(undef, sim.n, nys, nxs); D = Array{Float64}(undef, sim.n, nys, nus)
     x0 = Matrix{Float64}(undef, sim.n, nxs); u0 = Matrix{Float64}(undef, sim.n, nus); y0 = Matrix{Float64}(undef, sim.n, nys)
-    check(ccall((:fb_linearize, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-                sim.handle, A, B, C, D, x0, u0, y0))
-    (A, B, C, D, x0, u0, y0)
+    xdot0 = Matrix{Float64}(undef, sim.n, nxs)
+    check(ccall((:fb_linearize, libflightbatch), Int32,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                sim.handle, A, B, C, D, x0, u0, y0, xdot0))
+    (A, B, C, D, x0, u0, y0, xdot0)
 end
 
 # ---- LinearizedSS ensembles (linearization.jl:24-111,157-192; README example 3 per member) ----------------------
@@ -286,13 +314,19 @@ function BatchLinearizedSS(sim::BatchSimulation)
     finalizer(l -> ccall((:fb_lss_destroy, libflightbatch), Int32, (Ptr{Cvoid},), l.handle), lss)
 end
 step!(lss::BatchLinearizedSS, Δt::Real = lss.dt) = check(ccall((:fb_lss_step, libflightbatch), Int32, (Ptr{Cvoid}, Float64), lss.handle, Δt))
-function _lss_get(lss::BatchLinearizedSS, f::Symbol, rows::Integer)
-    out = Matrix{Float64}(undef, lss.n, rows)      # N × rows: the C layout [rows][N]
-    check(ccall((f, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{Float64}), lss.handle, out)); out
+# N × rows matrices: the C layout [rows][N]. (`ccall` needs a literal function name, hence one method per entry point.)
+function getstate(lss::BatchLinearizedSS)
+    out = Matrix{Float64}(undef, lss.n, lss.nx)
+    check(ccall((:fb_lss_get_state, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{Float64}), lss.handle, out)); out
 end
-getstate(lss::BatchLinearizedSS) = _lss_get(lss, :fb_lss_get_state, lss.nx)
-getinputs(lss::BatchLinearizedSS) = _lss_get(lss, :fb_lss_get_input, lss.nu)
-getoutputs(lss::BatchLinearizedSS) = _lss_get(lss, :fb_lss_get_output, lss.ny)
+function getinputs(lss::BatchLinearizedSS)
+    out = Matrix{Float64}(undef, lss.n, lss.nu)
+    check(ccall((:fb_lss_get_input, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{Float64}), lss.handle, out)); out
+end
+function getoutputs(lss::BatchLinearizedSS)
+    out = Matrix{Float64}(undef, lss.n, lss.ny)
+    check(ccall((:fb_lss_get_output, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{Float64}), lss.handle, out)); out
+end
 setinputs!(lss::BatchLinearizedSS, u::Matrix{Float64}) = check(ccall((:fb_lss_set_input, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{Float64}), lss.handle, u))
 setstate!(lss::BatchLinearizedSS, x::Matrix{Float64}) = check(ccall((:fb_lss_set_state, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{Float64}), lss.handle, x))
 

@@ -127,7 +127,7 @@ typedef struct fb_config {
     int32_t variant;        /* FB_C172*                                             */
     int32_t kinematics;     /* FB_WA / FB_ECEF / FB_NED                             */
     int64_t n_members;      /* members held by THIS handle (one handle per GPU)     */
-    int64_t member_offset;  /* global index of member 0 (sharding; used by RNG-free bookkeeping only) */
+    int64_t member_offset;  /* global index of this handle's member 0 in a sharded ensemble (>= 0; set by fb_group_create, informational elsewhere) */
     double dt;              /* RK4 step (reference default 0.02)                    */
     double Dt;              /* periodic (avionics) interval; must be k*dt, k>=1     */
     double t_start, t_end;
@@ -191,7 +191,12 @@ int32_t fb_sync(fb_handle h);
 
 /* ---- initialisation -------------------------------------------------------------------- */
 /* init!(sim, C172.TrimParameters(...)) : sim.jl:390-414 -> c172.jl:883-942. trim_state_out [7][N] and
- * cost_out [N] may be NULL. Members whose trim does not reach cost <= 1e-16 get FB_ST_TRIM_FAILED. */
+ * cost_out [N] may be NULL. Members whose trim does not reach cost <= 1e-16 get FB_ST_TRIM_FAILED and are frozen:
+ * a deliberate deviation from the reference, which only warns, assigns the best trim state it found and keeps
+ * simulating (c172.jl:934-940). In an ensemble a member that never reached its trim point is excluded from stepping and
+ * from every moment instead of flying an untrimmed transient; the caller sees it in fb_status. The solver also differs
+ * (damped Newton to 1e-26 here, NLopt BOBYQA stopping at 1e-16 there): trim states agree with the reference's stored
+ * trims to ~1e-7 (tests/golden/trim_points.json), which is the optimiser's own stopping distance. */
 int32_t fb_init_trim(fb_handle h, const fb_trim_params_soa* p, double* trim_state_out, double* cost_out);
 /* init!(sim, C172.Init(kin, sys)) : aircraftbase.jl:76-86 */
 int32_t fb_init(fb_handle h, const fb_init_soa* ic);

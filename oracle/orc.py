@@ -70,6 +70,7 @@ def _load(name):
         "orc_sim_clear_events": (None, [vp]),
         "orc_sim_rhs": (i32, [vp]),
         "orc_sim_step": (i32, [vp, i64]),
+        "orc_sim_step_noisy": (i32, [vp, i64, C.c_ulonglong]),
         "orc_sim_steps_taken": (i64, [vp]),
         "orc_sim_fstep": (i32, [vp]), "orc_sim_fperiodic": (i32, [vp]),
         "orc_sim_linearize_dims": (None, [vp, C.POINTER(i32)]),
@@ -234,6 +235,10 @@ class Sim:
 
     def step(self, n=1):
         return self.lib.orc_sim_step(self.h, int(n))
+
+    def step_noisy(self, n, seed):
+        """n steps with a one-ulp random nudge of every state component after each (rounding-sensitivity probe)."""
+        return self.lib.orc_sim_step_noisy(self.h, int(n), int(seed))
 
     def f_step(self):
         return self.lib.orc_sim_fstep(self.h)

@@ -264,6 +264,23 @@ int orc_sim_step(void* s, long long n) {
     for (long long i = 0; i < n; i++) S->step();
     return S->m.status;
 }
+// Rounding-sensitivity probe (tests/ground_util.py): n steps with every state component moved by one ulp in a random
+// direction after each step — the per-step difference any other correct implementation of the same algorithm may show.
+int orc_sim_step_noisy(void* s, long long n, unsigned long long seed) {
+    Sim* S = (Sim*)s;
+    unsigned long long z = seed * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+    for (long long k = 0; k < n; k++) {
+        S->step();
+        if (S->m.status != ST_RUNNING) break;
+        for (int i = 0; i < S->m.L.nx; i++) {
+            z += 0x9E3779B97F4A7C15ull;
+            unsigned long long r = z; r = (r ^ (r >> 30)) * 0xBF58476D1CE4E5B9ull; r = (r ^ (r >> 27)) * 0x94D049BB133111EBull; r ^= r >> 31;
+            const double v = val(S->m.x[i]);
+            if (v != 0.0) S->m.x[i] = std::nextafter(v, (r & 1) ? INFINITY : -INFINITY);
+        }
+    }
+    return S->m.status;
+}
 // Modeling-protocol pieces in isolation (parity hooks): f_ode! at the current state for y, then f_step!(world) /
 // f_periodic!(avionics) + assign!, exactly the callback bodies of Sim::step()
 int orc_sim_fstep(void* s) {

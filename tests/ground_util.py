@@ -6,8 +6,11 @@ The reference computes a strut's compression from the difference of two ECEF pos
 millimetre-to-centimetre compression, and a member at rest sits on the friction-direction switch at 1e-3 m/s
 (landinggear.jl:436-452). Two builds of the SAME restatement that differ only in rounding therefore drift apart on the
 gear-driven states by far more than 1e-9. `oracle_spread` measures that: the checker build (-O2 -ffp-contract=off)
-against (a) the same sources compiled with FMA contraction (-O3 -march=native) and (b) the checker started from a state
-perturbed by one ulp. The GPU-vs-oracle bound of tests/test_gpu_ground.py is this measured spread times a stated factor."""
+against (a) the same sources compiled with FMA contraction (-O3 -march=native), (b) the checker started from a state
+perturbed by one ulp, and (c) the checker with every state component nudged by one ulp in a random direction after every
+step, which is the step-to-step difference any other correct implementation (such as a GPU kernel with its own operation
+order, fused multiply-adds and reciprocal sequences) shows against it. The GPU-vs-oracle bound of tests/test_gpu_ground.py is
+this measured spread times a stated factor."""
 import numpy as np
 
 SEED = 20261018
@@ -76,7 +79,8 @@ def member_errors(xa, xb):
 
 def oracle_spread(orc, U, IN, x0, stall, eng, inputs, events, chunks=CHUNKS, dt=0.01):
     """Rounding spread of the reference formulation over the given members (columns of x0): checker build vs the FMA-contracted
-    build, and checker vs checker started one ulp away (h_e and the first attitude-quaternion component nudged by one ulp).
+    build, checker vs checker started one ulp away (h_e and the first attitude-quaternion component nudged by one ulp), and
+    checker vs checker with one-ulp noise on every state component after every step.
     Returns per comparison instant the per-member (all-state, physical-state) errors of both experiments, and the statuses / WoW
     histories needed to tell which members the perturbation pushed across a discrete event."""
     n = x0.shape[1]
@@ -87,14 +91,17 @@ def oracle_spread(orc, U, IN, x0, stall, eng, inputs, events, chunks=CHUNKS, dt=
     x1[kin0 + 8] = np.nextafter(x1[kin0 + 8], np.inf)
     x1[kin0] = np.nextafter(x1[kin0], np.inf)
     ulp = [clone(orc, U, IN, {f: v[i] for f, v in inputs.items()}, events[i], x1[:, i], stall[i], eng[i], dt) for i in range(n)]
+    noisy = [clone(orc, U, IN, {f: v[i] for f, v in inputs.items()}, events[i], x0[:, i], stall[i], eng[i], dt) for i in range(n)]
     out = []
-    for c in chunks:
+    for k, c in enumerate(chunks):
         for group in (base, fma, ulp):
             for o in group:
                 o.step(c)
+        for i, o in enumerate(noisy):
+            o.step_noisy(c, 1000003 * k + i)
         xb = np.array([o.x for o in base]).T
         rec = {}
-        for name, group in (("fma", fma), ("ulp", ulp)):
+        for name, group in (("fma", fma), ("ulp", ulp), ("noisy", noisy)):
             xg = np.array([o.x for o in group]).T
             rec[name] = member_errors(xg, xb)
             rec[name + "_same_discrete"] = np.array([(a.status == b.status) and (a.discrete == b.discrete) for a, b in zip(group, base)])

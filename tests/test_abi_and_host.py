@@ -147,3 +147,120 @@ def test_two_rank_gloo_statistics_allreduce():
         g = res[r]
         assert g["count"] == ref["count"] and g["min"] == ref["min"] and g["max"] == ref["max"]
         assert abs(g["sum"] - ref["sum"]) < 1e-9 * abs(ref["sum"]) and abs(g["mean"] - full[keep].mean()) < 1e-12 * 50
+
+
+# ------------------------------------------------------------------------------------------------ the boundary from outside Python
+def build_abi_driver():
+    """tests/abi_driver.c compiled with gcc against include/flightbatch.h and linked to libflightbatch.so (prototypes checked by
+    the compiler, -Werror)."""
+    import subprocess
+    import tempfile
+    libdir = os.path.join(ROOT, "flight.jl_b200")
+    exe = os.path.join(tempfile.gettempdir(), "fb_abi_driver_%d" % os.getpid())
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-O1", "-I", os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "abi_driver.c"), "-L", libdir, "-lflightbatch", "-lm", f"-Wl,-rpath,{libdir}"])
+    return exe
+
+
+JL_TYPES = {"Int32": (4, 4), "Int64": (8, 8), "Float64": (8, 8), "UInt8": (1, 1), "NTuple{32,Int32}": (128, 4)}
+
+
+def _julia_struct_layout(name):
+    """Field offsets of an isbits `struct` of BatchSimulation.jl under Julia's C-compatible layout rules (natural alignment)."""
+    txt = open(os.path.join(ROOT, "flight.jl_b200", "julia", "BatchSimulation.jl")).read()
+    body = re.search(r"^struct %s\n(.*?)^end" % name, txt, re.S | re.M).group(1)
+    off, out, amax = 0, {}, 1
+    for line in body.splitlines():
+        line = line.split("#")[0].strip()
+        if not line:
+            continue
+        field, typ = [t.strip() for t in line.split("::")]
+        size, align = JL_TYPES[typ]
+        off = (off + align - 1) // align * align
+        out[field] = off
+        off += size
+        amax = max(amax, align)
+    out["size"] = (off + amax - 1) // amax * amax
+    return out
+
+
+def test_struct_layouts_agree_between_c_ctypes_and_julia(fb):
+    import json
+    import subprocess
+    c = json.loads(subprocess.check_output([build_abi_driver(), "layout"]))
+    assert c["api_version"] == fb.DEFS["FB_API_VERSION"] and c["FB_U__COUNT"] == fb.U["FB_U__COUNT"] and c["FB_Y__COUNT"] == fb.Y["FB_Y__COUNT"]
+    # ctypes mirror (what every Python test goes through)
+    for sname, cls in (("fb_config", fb.fb_config), ("fb_moments", fb.fb_moments), ("fb_trim_params_soa", fb.fb_trim_params_soa), ("fb_init_soa", fb.fb_init_soa)):
+        assert C.sizeof(cls) == c[sname]["size"], sname
+        for f, o in c[sname].items():
+            if f != "size":
+                assert getattr(cls, f).offset == o, (sname, f)
+    # Julia mirror (never executed in this image: checked mechanically instead)
+    jl = _julia_struct_layout("FbConfig")
+    assert jl == {k: v for k, v in c["fb_config"].items()}, (jl, c["fb_config"])
+    assert _julia_struct_layout("Moments") == c["fb_moments"]
+    txt = open(os.path.join(ROOT, "flight.jl_b200", "julia", "BatchSimulation.jl")).read()
+    assert int(re.search(r"const FB_API_VERSION = (\d+)", txt).group(1)) == c["api_version"]
+    assert len(re.search(r"const TRIM_FIELDS = \((.*?)\)", txt, re.S).group(1).split(",")) * 8 == c["fb_trim_params_soa"]["size"]
+
+
+def test_every_entry_point_rejects_null_handles_from_c():
+    import subprocess
+    r = subprocess.run([build_abi_driver(), "null"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+def _split_top(s):
+    """Split at commas that are not nested in (), {} or []."""
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "({[":
+            depth += 1
+        elif ch in ")}]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur); cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur)
+    return [t.strip() for t in out if t.strip()]
+
+
+def test_julia_ccalls_match_the_header_prototypes():
+    """Every `ccall((:fb_x, libflightbatch), ret, (argtypes...), args...)` of BatchSimulation.jl: the function exists in the header,
+    the number of argument types equals the prototype's parameter count and the number of values passed, and the return type is
+    the prototype's. (Round 1 shipped an 8-argument call of the 9-parameter fb_linearize.)"""
+    hdr = open(os.path.join(ROOT, "include", "flightbatch.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = {}
+    for ret, name, args in re.findall(r"^(int32_t|const char\*)\s+(fb_[a-z0-9_]+)\s*\((.*?)\);", hdr, re.S | re.M):
+        a = [t for t in _split_top(" ".join(args.split())) if t != "void"]
+        protos[name] = (ret, len(a))
+    txt = open(os.path.join(ROOT, "flight.jl_b200", "julia", "BatchSimulation.jl")).read()
+    calls = 0
+    for m in re.finditer(r"ccall\(\((:?\w+), libflightbatch\)", txt):
+        assert m.group(1).startswith(":"), f"ccall needs a literal function name, got `{m.group(1)}`"
+        name = m.group(1)[1:]
+        # the whole argument list of this ccall( ... ) by bracket matching
+        i = m.start() + len("ccall(")
+        depth, j = 1, i
+        while depth:
+            depth += {"(": 1, ")": -1}.get(txt[j], 0)
+            j += 1
+        parts = _split_top(txt[i:j - 1])
+        ret, argtypes, values = parts[1], parts[2], parts[3:]
+        assert name in protos, f"{name} is not declared in flightbatch.h"
+        ntypes = len(_split_top(argtypes[1:-1]))
+        assert ntypes == protos[name][1], f"{name}: {ntypes} argument types, the prototype has {protos[name][1]}"
+        assert len(values) == ntypes, f"{name}: {len(values)} values for {ntypes} argument types"
+        assert (ret == "Cstring") == (protos[name][0] == "const char*") and (ret == "Int32") == (protos[name][0] == "int32_t"), (name, ret)
+        calls += 1
+    assert calls >= 40
+    # fields the binding reads must exist on the struct it reads them from
+    sim_fields = set(re.findall(r"^\s+(\w+)::", re.search(r"mutable struct BatchSimulation\n(.*?)function BatchSimulation", txt, re.S).group(1), re.M))
+    code = "\n".join(line.split("#")[0] for line in txt.splitlines())      # comments and docstring references do not count
+    code = re.sub(r'"""(.*?)"""', "", code, flags=re.S)
+    code = re.sub(r'^"[^"\n]*"$', "", code, flags=re.M)                     # one-line docstrings
+    for f in set(re.findall(r"\bsim\.(\w+)", code)):
+        assert f in sim_fields | {"t", "x"}, f"BatchSimulation has no field {f}"

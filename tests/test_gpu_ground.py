@@ -82,8 +82,8 @@ def test_cfg4_takeoff_and_landing_ensemble(fb, orc):
     over 25 s. Continuous states cannot agree to 1e-9 on this path for ANY two implementations that round differently: the
     reference computes the strut compression from a difference of 6.4e6 m ECEF vectors (landinggear.jl:262-270) and a member
     at rest sits on the friction-direction switch at 1e-3 m/s (landinggear.jl:436-452). The bound is therefore MEASURED, not
-    picked: the same members are run on two builds of the oracle that differ only in rounding (FMA contraction on / off;
-    tests/ground_util.py), and at every instant the GPU-vs-oracle error (median over members of the all-state error, maximum
+    picked: the same members are run on the oracle under three rounding perturbations (FMA contraction on / off, a one-ulp
+    change of the start, one-ulp noise after every step; tests/ground_util.py), and at every instant the GPU-vs-oracle error (median over members of the all-state error, maximum
     over members of the physical-state error) must stay within SPREAD_FACTOR times the largest oracle-vs-oracle spread seen
     up to that instant. While every strut is still unloaded (first instant) the airborne bound 1e-9 applies."""
     import ground_util as gu
@@ -115,8 +115,8 @@ def test_cfg4_takeoff_and_landing_ensemble(fb, orc):
             seen_wow |= set(int(v) for v in wg)
         seen_eng |= set(int(v) for v in eng_g)
         err, phys = gu.member_errors(xg, xo)
-        run_med = max(run_med, float(np.median(sp["fma"][0])), float(np.median(sp["ulp"][0])))
-        run_max = max(run_max, float(sp["fma"][1].max()), float(sp["ulp"][1].max()))
+        run_med = max(run_med, *(float(np.median(sp[e][0])) for e in ("fma", "ulp", "noisy")))
+        run_max = max(run_max, *(float(sp[e][1].max()) for e in ("fma", "ulp", "noisy")))
         med, mx = float(np.median(err)), float(phys.max())
         worst_med = max(worst_med, med); worst_max = max(worst_max, mx)
         worst_ratio = max(worst_ratio, med / max(run_med, 1e-9), mx / max(run_max, 1e-9))

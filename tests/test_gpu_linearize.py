@@ -51,3 +51,39 @@ def test_linearize_needs_ned(fb):
     with pytest.raises(fb.FlightBatchError, match="NED"):
         sim.linearize()
     sim.close()
+
+
+def test_cfg5_lattice_of_1296_points(fb, orc):
+    """BASELINE.json configs[4] at 1,296 lattice points (the tools/bench_configs.py cfg5 lattice, 6 values per axis): every 9th
+    point against the oracle — trim state and operating point <= 1e-9, Jacobians to forward-difference noise, infeasible
+    lattice corners flagged identically."""
+    m = 6
+    EAS, h, fl, mass = np.meshgrid(np.linspace(25, 55, m), np.linspace(50, 3050, m), np.linspace(0, 1, m), np.linspace(0, 100, m), indexing="ij")
+    EAS, h, fl, mass = (a.ravel() for a in (EAS, h, fl, mass))
+    fl = np.where(EAS > 42, 0.0, fl)
+    n = EAS.size
+    assert n == 1296
+    sim = fb.BatchSimulation(fb.SimpleWorld(fb.Cessna172Sv0(fb.NED())), n=n, dt=0.01, t_end=1.0)
+    ok, ts, cost = sim.init(fb.C172.TrimParameters(EAS=EAS, h_e=h, flaps=fl, m_pilot=mass, m_copilot=mass))
+    g = sim.linearize()
+    worst_ts, worst_j, n_fail = 0.0, 0.0, 0
+    for i in range(0, n, 9):
+        o = orc.Sim(variant=0, kin=2, dt=0.01)
+        ok_o, ts_o, _ = o.init_trim(EAS=EAS[i], h_e=h[i], flaps=fl[i], m_pilot=mass[i], m_copilot=mass[i])
+        assert ok_o == bool(ok[i]), (i, EAS[i], h[i], fl[i])
+        if not ok_o:
+            n_fail += 1
+            continue
+        e = np.abs(ts[:, i] - ts_o) / np.maximum(np.abs(ts_o), 1e-2)
+        worst_ts = max(worst_ts, float(e.max()))
+        assert e.max() < 1e-9, (i, e)
+        r = o.linearize()
+        for k in ("x0", "u0", "y0"):
+            assert np.all(np.abs(g[k][i] - r[k]) <= 1e-9 * np.maximum(np.abs(r[k]), 1e-2)), (k, i)
+        for k in ("A", "B", "C", "D"):
+            err = np.abs(g[k][i] - r[k]) / np.maximum(np.abs(r[k]).max(axis=1, keepdims=True), 1.0)
+            worst_j = max(worst_j, float(err.max()))
+            assert err.max() < 2e-5, (k, i, float(err.max()))
+    print(f"cfg5 lattice: {n} points, {n_fail} of the sampled {len(range(0, n, 9))} infeasible (slow, low, flapless corners); worst trim-state error {worst_ts:.2e}, "
+          f"worst row-scaled Jacobian error {worst_j:.2e}")
+    sim.close()

@@ -145,4 +145,4 @@ def test_time_sliced_launch_is_bit_identical_to_plain_launch(fb, model):
     assert np.array_equal(a["disc"][0], b["disc"][0]) and np.array_equal(a["disc"][1], b["disc"][1])
     assert np.array_equal(a["x"], b["x"])
     for la, lb in zip(a["log"], b["log"]):
-        assert np.array_equal(la, lb)
+        assert np.array_equal(la, lb, equal_nan=True)     # a frozen member leaves NaN in both

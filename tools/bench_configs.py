@@ -109,23 +109,59 @@ def cfg4(fb, n, seconds):
 
 
 def cfg5(fb, n, seconds):
+    """BASELINE.json configs[4]: n lattice points sharded over the ranks (torchrun: one rank per GPU, no exchange); per rank a
+    batched trim solve + forward-difference linearize() per point. Two legs: Jacobians left on the device as a LinearizedSS
+    ensemble (fb_lss_from_linearize: what a downstream batched analysis consumes) and Jacobians gathered to the host."""
     import torch
+    from flightbatch.dist import shard_range
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     # regular lattice EAS x h x flaps x payload, NED kinematics (linearize's layout)
     m = int(round(n ** 0.25)) + 1
     EAS, h, fl, mass = np.meshgrid(np.linspace(25, 55, m), np.linspace(50, 3050, m), np.linspace(0, 1, m), np.linspace(0, 100, m), indexing="ij")
     EAS, h, fl, mass = (a.ravel()[:n] for a in (EAS, h, fl, mass))
     fl = np.where(EAS > 42, 0.0, fl)
-    sim = fb.BatchSimulation(fb.SimpleWorld(fb.Cessna172Sv0(fb.NED())), n=n, dt=DT, t_end=10.0)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    ok, _, _ = sim.init(fb.C172.TrimParameters(EAS=EAS, h_e=h, flaps=fl, m_pilot=mass, m_copilot=mass))
-    sim.sync(); t1 = time.perf_counter()
-    lin = sim.linearize()
-    sim.sync(); t2 = time.perf_counter()
-    sim.close()
-    return {"config": "cfg5: envelope sweep, Cessna172Sv0/NED, trim + forward-difference A,B,C,D per point (host wall clock incl. D2H of the Jacobians)",
-            "points": n, "trim_ok": int(ok.sum()), "trim_s": t1 - t0, "linearize_s": t2 - t1, "points_per_s": n / (t2 - t0),
-            "A_shape": list(np.shape(lin["A"]))}
+    lo, hi = shard_range(n, rank, world)
+    sl = slice(lo, hi)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def leg(gather):
+        sim = fb.BatchSimulation(fb.SimpleWorld(fb.Cessna172Sv0(fb.NED())), n=hi - lo, dt=DT, t_end=10.0, device=local, member_offset=lo)
+        barrier()
+        t0 = time.perf_counter()
+        ok, _, _ = sim.init(fb.C172.TrimParameters(EAS=EAS[sl], h_e=h[sl], flaps=fl[sl], m_pilot=mass[sl], m_copilot=mass[sl]))
+        sim.sync(); t1 = time.perf_counter()
+        if gather:
+            out = sim.linearize(); shape = list(np.shape(out["A"]))
+        else:
+            out = fb.LinearizedSS(sim); out.sync(); shape = [hi - lo, out.nx, out.nx]
+        sim.sync(); barrier(); t2 = time.perf_counter()
+        tt = torch.tensor([t1 - t0, t2 - t1, t2 - t0], dtype=torch.float64, device="cuda")
+        okc = torch.tensor([float(ok.sum())], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX); dist.all_reduce(okc, op=dist.ReduceOp.SUM)
+        if not gather:
+            out.close()
+        sim.close()
+        return [float(v) for v in tt.tolist()], int(okc.item()), shape
+    leg(False)                                   # warm-up (context, module load)
+    td, okd, shape = leg(False)
+    tg, okg, _ = leg(True)
+    res = {"config": "cfg5: envelope sweep, Cessna172Sv0/NED, batched trim + forward-difference A,B,C,D per lattice point, points sharded over the GPUs (no exchange)",
+           "points": n, "n_gpus": world, "points_per_gpu": hi - lo, "trim_ok": okd,
+           "device_resident": {"trim_s": td[0], "linearize_s": td[1], "points_per_s": n / td[2], "what": "Jacobians stay on the device as a LinearizedSS ensemble (fb_lss_from_linearize)"},
+           "gathered": {"trim_s": tg[0], "linearize_s": tg[1], "points_per_s": n / tg[2], "what": "A, B, C, D, x0, u0, y0 copied to pageable host arrays (fb_linearize)", "d2h_bytes_per_gpu": int((hi - lo) * 8 * (16 * 16 + 16 * 4 + 33 * 16 + 33 * 4 + 16 + 4 + 33 + 16))},
+           "A_shape_per_gpu": shape, "timing": "host wall clock, barrier + synchronize on both sides, max over ranks"}
+    if world > 1:
+        dist.destroy_process_group()
+    return res if rank == 0 else None
 
 
 def lss(fb, n, seconds):
@@ -164,7 +200,8 @@ def main():
     import flightbatch as fb
     n = args.members or {"cfg3": 1 << 20, "cfg4": 1 << 18, "cfg5": 100000, "lss": 65536}[args.which]
     out = {"cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "lss": lss}[args.which](fb, n, args.seconds)
-    print(json.dumps(out))
+    if out is not None:
+        print(json.dumps(out))
 
 
 if __name__ == "__main__":
