@@ -244,7 +244,9 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
     constexpr int TBL = StepShape<VAR, KIN, AIR, CAP>::TBL;
     __shared__ int chunk_done_s[FB_MW_MAX];
     if (threadIdx.x < FB_MW_MAX) chunk_done_s[threadIdx.x] = 0;
-    stage_tables(smem_tb, E.tables.pack, TBL);
+    __shared__ unsigned long long rhs_cta;
+    if (threadIdx.x == 0) rhs_cta = 0ull;
+    stage_tables(smem_tb, E.tables.pack, TBL);   // (contains the __syncthreads that orders the two initialisations above)
     GainsShared gains; gains.base = nullptr; gains.sbase = (unsigned)__cvta_generic_to_shared(smem) + FB_TB_BYTES;
     // Work distribution: the CTA owns `mpc` consecutive members = MW member-warps, and the launch is cut into C chunks
     // of `chunk` steps. Task j = (member-warp j % MW, chunk j / MW); hardware warp w runs tasks w, w + HW, ... Each task
@@ -258,6 +260,10 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
     const int MW = (int)((min((long long)mpc, E.n - cta_base) + 31) / 32);
     const int C = (n_steps_launch + chunk - 1) / chunk;
     volatile int* chunk_done = chunk_done_s;
+    // right-hand-side evaluations of this thread's tasks; folded into one shared-memory counter and ONE global atomic per CTA
+    // at the end (a global atomic per thread and task put 2.6e5 same-address atomics behind every time-sliced cfg-3 launch of a
+    // 131,072-member shard: ~0.3 ms of an 11.5 ms launch)
+    unsigned rhs_mine = 0;
     for (int task = threadIdx.x >> 5; task < MW * C; task += HW) {
     const int mw = task % MW, ck = task / MW;
     if (C > 1) {
@@ -448,12 +454,17 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
     if (AIR) { resume[i] = handover; if (handover >= 0) atomicAdd(ground_count, 1u); }
     else if (!resume_mode && gnd_seen) atomicAdd(ground_count, 1u);
     // RHS evaluations of this launch: k1 of the first step, then k2..k4 and f(x*) per step, plus re-evaluations
-    if (rhs_count) atomicAdd(rhs_count, (unsigned long long)max(0, 4 * done + n_reeval + (pending ? -3 : 1) + (handover >= 0 ? (sink.stage & 3) : 0)));
+    rhs_mine += max(0, 4 * done + n_reeval + (pending ? -3 : 1) + (handover >= 0 ? (sink.stage & 3) : 0));
     } while (0);
     if (C > 1) {   // publish the chunk: the next task on these members may run on another warp of this CTA
         __threadfence_block(); __syncwarp();
         if (lane == 0) chunk_done[mw] = ck + 1;
     }
+    }
+    if (rhs_count) {   // every thread of the CTA arrives here (tasks are left by `break`, never by `return`)
+        if (rhs_mine) atomicAdd(&rhs_cta, (unsigned long long)rhs_mine);
+        __syncthreads();
+        if (threadIdx.x == 0 && rhs_cta) atomicAdd(rhs_count, rhs_cta);
     }
 }
 
