@@ -155,7 +155,7 @@ FB_DEV void trim_assign(double* x, const MemberIn& u, int& stall, int& eng, cons
     // AtmosphericData(atmosphere, Ob): Ob has an ellipsoidal altitude -> orthometric through the geoid
     double h_o = p.h_e - geoid_height(geoid, p.lat, p.lon);
     double T, pr, lnp;
-    isa_data(h_o, u(FB_U_T_SL), u(FB_U_P_SL), u(FB_UX_TRF), T, pr, lnp, err);
+    isa_data(h_o, u(FB_U_T_SL), [&]() { return u(FB_U_P_SL); }, u(FB_UX_TRC), T, pr, lnp, err);
     double rho = pr / (isa::R * T);
     double TAS = p.EAS * sqrt(isa::rho_std / rho);
     double sa, ca, sb, cb;

@@ -5,6 +5,7 @@
 // (component-major, member fastest) and is touched once per launch of K fused steps.
 #pragma once
 #include <climits>
+#include <type_traits>
 #include "fb_physics.cuh"
 #include "fb_avionics.cuh"
 
@@ -217,15 +218,23 @@ struct StepShape {
     static constexpr int VCAP = (VAR >= FB_C172X1 && CAP > FB_STEP_BLOCK_CTL) ? FB_STEP_BLOCK_CTL : CAP;
     static constexpr int T = FIT < VCAP ? FIT : VCAP;
     static constexpr int SPARE = (int)(BUDGET / (sizeof(double) * T)) - NCOL;                  // columns left for the input cache and the tap
-#ifndef FB_NSLOT_MAX
-#define FB_NSLOT_MAX 16
+    // Spare columns, in this order: the anchor of the slowly varying transcendentals (SmemAnchor: five columns, taken when
+    // at least FB_ANC_MIN_SLOTS input slots remain beside it), the input cache, and what is left holds the leading entries
+    // of the output tap of the f(x*) evaluation (control-law feedback); the rest of the tap goes to the member's column of
+    // E.ctl (written and read back once per step, against inputs that every evaluation reads).
+#ifndef FB_ANCHORS
+#define FB_ANCHORS 1
 #endif
-    static constexpr int NSLOT_MAX = (VAR == FB_C172S) ? FB_NSLOT_MAX : FB_NSLOT_MAX + 3;   // C172X also caches the wind
-    // output tap of the f(x*) evaluation (control-law feedback): in shared-memory columns when they fit beside at least
-    // 10 input slots, otherwise in the member's column of E.ctl
-    static constexpr int NTAP = (VAR >= FB_C172X1 && SPARE >= TAP_COUNT + 10) ? TAP_COUNT : 0;
-    static constexpr int NSLOT = (SPARE - NTAP) < NSLOT_MAX ? (SPARE - NTAP) : NSLOT_MAX;
-    static constexpr size_t SMEM = TBL + sizeof(double) * (NCOL + NSLOT + NTAP) * T;
+#ifndef FB_ANC_MIN_SLOTS
+#define FB_ANC_MIN_SLOTS 9
+#endif
+    static constexpr int NANC = (FB_ANCHORS && KIN != FB_NED && SPARE >= ANC_COUNT + FB_ANC_MIN_SLOTS) ? ANC_COUNT : 0;
+    // input slots wanted: 9 common + 6 payload moments + wind 3 + sea-level pressure; the complete layout adds the brakes
+    static constexpr int NSLOT_MAX = AIR ? 19 : 21;
+    static constexpr int NSLOT = (SPARE - NANC) < NSLOT_MAX ? (SPARE - NANC) : NSLOT_MAX;
+    static constexpr int TAP_WANT = (VAR >= FB_C172X1) ? (NANC ? TAP_LAT : TAP_COUNT) : 0;     // latitude / longitude are the anchor's
+    static constexpr int NTAP = (SPARE - NANC - NSLOT) < TAP_WANT ? (SPARE - NANC - NSLOT) : TAP_WANT;
+    static constexpr size_t SMEM = TBL + sizeof(double) * (NCOL + NSLOT + NTAP + NANC) * T;
 };
 #define FB_RESUME_PENDING (1 << 30)
 #define FB_MW_MAX 32            // member-warps a CTA can time-slice over its hardware warps (step_kernel)
@@ -291,8 +300,10 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
     double* sx = smem + TBL / 8 + threadIdx.x;
     double* sacc = sx + NX * T;
     CachedIn<VAR, T, StepShape<VAR, KIN, AIR, CAP>::NSLOT> u; u.g = ug; u.sc = sx + StepShape<VAR, KIN, AIR, CAP>::NCOL * T;
-    constexpr int NTAP = StepShape<VAR, KIN, AIR, CAP>::NTAP;
+    constexpr int NTAP = StepShape<VAR, KIN, AIR, CAP>::NTAP, NANC = StepShape<VAR, KIN, AIR, CAP>::NANC;
     double* const stap = u.sc + StepShape<VAR, KIN, AIR, CAP>::NSLOT * T;   // this thread's tap columns (NTAP of them)
+    double* const sanc = stap + NTAP * T;                                   // ... and its anchor columns (NANC of them)
+    double* const gtap = E.ctl ? E.ctl + (long long)FB_CTL_TAP_ROW * E.pitch + i : nullptr;
     double xs[NX];
 #pragma unroll
     for (int c = 0; c < NX; c++) { double v = E.x[(long long)L::row(c) * E.pitch + i]; xs[c] = v; sx[c * T] = v; }
@@ -337,11 +348,13 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
         sink.cx = (st == 2) ? dt : h2;
         sink.pa = (st == 1) ? ap1 : ((st == 2) ? ap2 : ((st == 3) ? ap3 : 1.0));
         RhsOut y;
+        typedef typename std::conditional<(NANC > 0), SmemAnchor<T, KIN, L::KINX>, NoAnchor>::type Anc;
+        Anc anc;
+        if constexpr (NANC > 0) { anc.p = sanc; anc.sx = sx; anc.ex = (st & 3) == 0; }
         if (VAR >= FB_C172X1) {
-            if (NTAP) { SmemTap<T> tap; tap.p = stap; tap.on = (st == 4); rhs<VAR, KIN, false, AIR>(xs, sink, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr, tap); }
-            else { ColumnTap tap; tap.p = E.ctl + (long long)FB_CTL_TAP_ROW * E.pitch + i; tap.pitch = E.pitch; tap.on = (st == 4);
-                   rhs<VAR, KIN, false, AIR>(xs, sink, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr, tap); }
-        } else rhs<VAR, KIN, false, AIR>(xs, sink, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr);
+            SplitTap<T, NTAP, (NANC > 0)> tap; tap.ps = stap; tap.pg = gtap; tap.pitch = E.pitch; tap.on = (st == 4);
+            rhs<VAR, KIN, false, AIR>(xs, sink, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr, tap, anc);
+        } else rhs<VAR, KIN, false, AIR>(xs, sink, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr, NoTap(), anc);
         if (!AIR) gnd_seen |= y.gnd;
         if (y.err) {
             if (AIR && y.err == FB_NEED_COMPLETE) {
@@ -366,7 +379,7 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
             // Control-law inputs from the tapped intermediates of the f(x*) evaluation just made and from x* itself. The
             // angles come from the fast primitives of the right-hand side (a few ulp from the library functions; the
             // control laws are continuous in them, and the parity tests hold the commands to 1e-9).
-            auto tapv = [&](int k) { return NTAP ? stap[k * T_] : E.ctl[(long long)(FB_CTL_TAP_ROW + k) * E.pitch + i]; };
+            auto tapv = [&](int k) { return k < NTAP ? stap[k * T_] : ((NANC && k >= TAP_LAT) ? sanc[(k - TAP_LAT + ANC_LAT) * T_] : gtap[(long long)k * E.pitch]); };
             q4 q = mkq(tapv(TAP_Q_NB), tapv(TAP_Q_NB + 1), tapv(TAP_Q_NB + 2), tapv(TAP_Q_NB + 3));
             if (KIN == FB_NED) { yf.theta = sink.sx[(L::KINX + 1) * T_]; yf.phi = sink.sx[(L::KINX + 2) * T_]; }
             else {   // REuler(q_nb), attitude.jl:382-390: asin(s) = atan2(s, sqrt((1 - s)(1 + s)))

@@ -98,7 +98,23 @@ static __device__ __noinline__ double pow_slow(double a, double b) { return pow(
 enum { FB_UX_AE = 100,   // -clamp(elevator_offset + elevator)   C172S MechanicalActuation, c172s.jl:92-120
        FB_UX_AA,         //  clamp(aileron_offset + aileron)
        FB_UX_RU,         //  clamp(rudder_offset + rudder)
-       FB_UX_TRF };      //  (p_sl / p_std)^(-beta R / g): sea-level factor of T_ISA(p)/T_std (piston.jl:38), 1 for the standard day
+       FB_UX_TRF,        //  (p_sl / p_std)^(-beta R / g): sea-level factor of T_ISA(p)/T_std (piston.jl:38), 1 for the standard day
+       FB_UX_TRC,        //  FB_UX_TRF / T_sl: T_ISA(p)/T_std = T * FB_UX_TRC in the troposphere
+       FB_UX_PL0,        //  payload moments (c172.jl:542-554: five point masses, all at z = 0.899): sum m
+       FB_UX_PL1, FB_UX_PL2, FB_UX_PL3, FB_UX_PL4, FB_UX_PL5 };   // sum m x, sum m y, sum m x^2, sum m y^2, sum m x y
+// The five payload stations share one height and two lateral offsets, so their contribution to the mass properties is
+// six moments of the masses; the right-hand side adds them to the airframe's and the fuel's (affine in the masses).
+FB_DEV void payload_moments(double m_pilot, double m_copilot, double m_lpass, double m_rpass, double m_baggage, double* S) {
+    constexpr double xf = 0.183, xr = -0.681, xb = -1.316, y = 0.356;
+    const double front = m_pilot + m_copilot, rear = m_lpass + m_rpass;
+    const double dfront = m_copilot - m_pilot, drear = m_rpass - m_lpass;     // right minus left
+    S[0] = front + rear + m_baggage;
+    S[1] = fma(xf, front, fma(xr, rear, xb * m_baggage));
+    S[2] = y * (dfront + drear);
+    S[3] = fma(xf * xf, front, fma(xr * xr, rear, (xb * xb) * m_baggage));
+    S[4] = (y * y) * (front + rear);
+    S[5] = fma(xf * y, dfront, (xr * y) * drear);
+}
 struct MemberIn {       // per-member input view: field f of this member is u[f * pitch]
     double* u;          // plain (coherent) loads: the owning thread also writes inputs (events, control laws)
     long long pitch;
@@ -107,8 +123,16 @@ struct MemberIn {       // per-member input view: field f of this member is u[f 
         if (f == FB_UX_AE) return -clampd(raw(FB_U_ELEVATOR_OFFSET) + raw(FB_U_ELEVATOR), -1.0, 1.0);
         if (f == FB_UX_AA) return clampd(raw(FB_U_AILERON_OFFSET) + raw(FB_U_AILERON), -1.0, 1.0);
         if (f == FB_UX_RU) return clampd(raw(FB_U_RUDDER_OFFSET) + raw(FB_U_RUDDER), -1.0, 1.0);
-        if (f == FB_UX_TRF) { double p_sl = raw(FB_U_P_SL); return (p_sl == 101325.0) ? 1.0 : pow_slow(p_sl * (1.0 / 101325.0), 6.5e-3 * 287.05287 / 9.80665); }
+        if (f == FB_UX_TRF || f == FB_UX_TRC) {
+            double p_sl = raw(FB_U_P_SL);
+            double trf = (p_sl == 101325.0) ? 1.0 : pow_slow(p_sl * (1.0 / 101325.0), 6.5e-3 * 287.05287 / 9.80665);
+            return (f == FB_UX_TRF) ? trf : trf * fb_rcp(raw(FB_U_T_SL));
+        }
+        if (f >= FB_UX_PL0 && f <= FB_UX_PL5) { double S[6]; payload(S); return S[f - FB_UX_PL0]; }
         return raw(f);
+    }
+    FB_DEV void payload(double* S) const {
+        payload_moments(raw(FB_U_M_PILOT), raw(FB_U_M_COPILOT), raw(FB_U_M_LPASS), raw(FB_U_M_RPASS), raw(FB_U_M_BAGGAGE), S);
     }
     FB_DEV void set(int f, double v) const { u[(long long)f * pitch] = v; }
 };
@@ -121,25 +145,36 @@ struct CachedIn {
     MemberIn g;
     double* sc;         // shared: column 0 of this thread's slots
     int flags;          // bit 0 mixture_auto, 1 eng_start, 2 eng_stop, 3 any wind component non-zero
+    // Slot priority. First what every evaluation reads whatever the model (sea-level temperature and the T_ISA factor,
+    // terrain elevation, the surface / throttle / mixture commands), then the six payload moments (all or none: with
+    // fewer than 15 slots they are formed from the five masses on every evaluation), the wind, the sea-level pressure
+    // (read once per step where the ISA anchor is in use) and the brake commands (ground contact only).
     __host__ __device__ static constexpr int field_of(int s) {
-        if (VAR == FB_C172S) {
-            switch (s) {
-                case 0: return FB_U_T_SL; case 1: return FB_U_P_SL; case 2: return FB_U_TRN_ELEVATION; case 3: return FB_UX_AE;
-                case 4: return FB_UX_AA; case 5: return FB_UX_RU; case 6: return FB_U_FLAPS; case 7: return FB_U_THROTTLE;
-                case 8: return FB_U_MIXTURE; case 9: return FB_UX_TRF; case 10: return FB_U_M_PILOT; case 11: return FB_U_M_COPILOT;
-                case 12: return FB_U_M_LPASS; case 13: return FB_U_M_RPASS; case 14: return FB_U_M_BAGGAGE; default: return -1;
-            }
-        } else {
-            switch (s) {
-                case 0: return FB_U_T_SL; case 1: return FB_U_P_SL; case 2: return FB_U_TRN_ELEVATION; case 3: return FB_U_ACT_THROTTLE;
-                case 4: return FB_U_ACT_AILERON; case 5: return FB_U_ACT_ELEVATOR; case 6: return FB_U_ACT_RUDDER; case 7: return FB_U_ACT_FLAPS;
-                case 8: return FB_U_MIXTURE; case 9: return FB_UX_TRF; case 10: return FB_U_M_PILOT; case 11: return FB_U_M_COPILOT;
-                case 12: return FB_U_M_LPASS; case 13: return FB_U_M_RPASS; case 14: return FB_U_M_BAGGAGE; case 15: return FB_U_WIND_N;
-                case 16: return FB_U_WIND_E; case 17: return FB_U_WIND_D; case 18: return FB_U_ACT_BRAKE_LEFT;
-                default: return -1;
+        if (s < 0) return -1;
+        if (s < 9) {
+            if (VAR == FB_C172S) {
+                switch (s) {
+                    case 0: return FB_U_T_SL; case 1: return FB_UX_TRC; case 2: return FB_U_TRN_ELEVATION; case 3: return FB_UX_AE;
+                    case 4: return FB_UX_AA; case 5: return FB_UX_RU; case 6: return FB_U_FLAPS; case 7: return FB_U_THROTTLE;
+                    default: return FB_U_MIXTURE;
+                }
+            } else {
+                switch (s) {
+                    case 0: return FB_U_T_SL; case 1: return FB_UX_TRC; case 2: return FB_U_TRN_ELEVATION; case 3: return FB_U_ACT_THROTTLE;
+                    case 4: return FB_U_ACT_AILERON; case 5: return FB_U_ACT_ELEVATOR; case 6: return FB_U_ACT_RUDDER; case 7: return FB_U_ACT_FLAPS;
+                    default: return FB_U_MIXTURE;
+                }
             }
         }
+        int r = s - 9;
+        if (NSLOT >= 15) { if (r < 6) return FB_UX_PL0 + r; r -= 6; }
+        switch (r) {
+            case 0: return FB_U_WIND_N; case 1: return FB_U_WIND_E; case 2: return FB_U_WIND_D; case 3: return FB_U_P_SL;
+            case 4: return VAR == FB_C172S ? FB_U_BRAKE_LEFT : FB_U_ACT_BRAKE_LEFT; case 5: return VAR == FB_C172S ? FB_U_BRAKE_RIGHT : FB_U_ACT_BRAKE_RIGHT;
+            default: return -1;
+        }
     }
+    static constexpr int NFIELDS = 9 + 6 + 6;     // upper bound of useful slots
     __host__ __device__ static constexpr int slot(int f) {
         for (int s = 0; s < NSLOT; s++) if (field_of(s) == f) return s;
         return -1;
@@ -153,14 +188,26 @@ struct CachedIn {
         if (f >= FB_U_WIND_N && f <= FB_U_WIND_D) return (flags & 8) ? g(f) : 0.0;
         return g(f);
     }
+    FB_DEV void payload(double* S) const {
+        if (slot(FB_UX_PL5) >= 0) {
+#pragma unroll
+            for (int j = 0; j < 6; j++) S[j] = sc[slot(FB_UX_PL0 + j) * T];
+        } else g.payload(S);
+    }
     FB_DEV void set(int f, double v) {       // one plain field (not a flag, not a derived slot): ensemble + cached copy
         g.set(f, v);
         const int s = slot(f);
         if (s >= 0) sc[s * T] = v;
     }
     FB_DEV void refresh() {
+        double S[6];
+        if (slot(FB_UX_PL5) >= 0) g.payload(S);
 #pragma unroll
-        for (int s = 0; s < NSLOT; s++) if (field_of(s) >= 0) sc[s * T] = g(field_of(s));
+        for (int s = 0; s < NSLOT; s++) {
+            const int f = field_of(s);
+            if (f >= FB_UX_PL0 && f <= FB_UX_PL5) sc[s * T] = S[f - FB_UX_PL0];
+            else if (f >= 0) sc[s * T] = g(f);
+        }
         flags = (g(FB_U_MIXTURE_AUTO) != 0.0 ? 1 : 0) | (g(FB_U_ENG_START) != 0.0 ? 2 : 0) | (g(FB_U_ENG_STOP) != 0.0 ? 4 : 0) |
                 ((g(FB_U_WIND_N) != 0.0 || g(FB_U_WIND_E) != 0.0 || g(FB_U_WIND_D) != 0.0) ? 8 : 0);
     }
@@ -169,18 +216,56 @@ struct CachedIn {
 // Output tap of the lean RHS: the handful of intermediate values the control and guidance laws feed back (attitude
 // quaternion, NED velocity, wander-frame body rates, TAS, density, alpha, beta, latitude, longitude). The integrator stores them when the evaluation is the
 // one at x* (whose outputs the reference's f_periodic! sees), which saves a second, output-producing evaluation.
-enum { TAP_Q_NB = 0, TAP_V_EB_N = 4, TAP_W_WB_B = 7, TAP_TAS = 10, TAP_RHO = 11, TAP_ALPHA = 12, TAP_BETA = 13, TAP_LAT = 14, TAP_LON = 15, TAP_COUNT = 16 };
+// In priority order for the shared-memory part (the first NS entries sit in spare columns of the owning thread, the rest in
+// the member's column of E.ctl): what the scheduled gains and every law read first.
+enum { TAP_TAS = 0, TAP_RHO = 1, TAP_ALPHA = 2, TAP_BETA = 3, TAP_W_WB_B = 4, TAP_V_EB_N = 7, TAP_Q_NB = 10, TAP_LAT = 14, TAP_LON = 15, TAP_COUNT = 16 };
 struct NoTap { FB_DEV void operator()(int, double) const {} };
-struct ColumnTap {        // column of a [TAP_COUNT][pitch] array, written only while `on`
-    double* p; long long pitch; bool on;
-    FB_DEV void operator()(int k, double v) const { if (on) p[(long long)k * pitch] = v; }
-    FB_DEV double get(int k) const { return p[(long long)k * pitch]; }
+// Tap split between shared-memory columns (entries < NS, compile-time stride T) and the member's column of a
+// [TAP_COUNT][pitch] array; written only while `on`. With ANC the latitude / longitude entries are the anchor's (below).
+template <int T, int NS, bool ANC>
+struct SplitTap {
+    double* ps; double* pg; long long pitch; bool on;
+    FB_DEV void operator()(int k, double v) const {
+        if (ANC && k >= TAP_LAT) return;
+        if (on) { if (k < NS) ps[k * T] = v; else pg[(long long)k * pitch] = v; }
+    }
 };
-template <int T>
-struct SmemTap {          // the same in shared-memory columns of the owning thread (compile-time stride)
-    double* p; bool on;
-    FB_DEV void operator()(int k, double v) const { if (on) p[k * T] = v; }
+
+// Anchor of the slowly varying transcendentals. Within one Runge-Kutta step the position moves by |v| dt (metres), so
+// the geodetic latitude / longitude and the ISA pressure at the stage states differ from their values at the step-start
+// state by ~1e-7 relative. The evaluation at the step-start state (k1, or f(x*) doubling as the next k1) computes them
+// exactly (two atan2, exp o log) and leaves an anchor in five shared-memory columns of the owning thread; the other three
+// evaluations of the step update from it:
+//   lat = lat0 + asin(sin lat cos lat0 - cos lat sin lat0),  lon likewise from the horizontal components of n_e, with
+//   asin(s) = s + s^3/6 (|s| < 1e-4 enforced: the next term is 3 s^5 / 40 < 1e-21);
+//   p = p0 (T / T0)^k = p0 (1 + e)^k, e = T / T0 - 1, as the binomial series to e^4 (|e| < 2e-4 enforced: the e^5 term is
+//   < 6e-19);
+// outside those bounds (never at dt = 0.01) the evaluation falls back to the exact formulas. The anchor state itself is
+// not stored: it is the step-start column of the integrator (n0 is rebuilt from it), which no stage writes.
+enum { ANC_LAT = 0, ANC_LON, ANC_ICLAT, ANC_P, ANC_IT, ANC_COUNT };
+struct NoAnchor {
+    static constexpr bool ON = false;
+    FB_DEV bool exact() const { return true; }
+    FB_DEV double get(int) const { return 0.0; }
+    FB_DEV void set(int, double) const {}
+    FB_DEV d3 n0() const { return mk3(0.0, 0.0, 0.0); }
+};
+template <int T, int KIN, int KINX>
+struct SmemAnchor {
+    static constexpr bool ON = true;
+    double* p;              // this thread's anchor columns
+    const double* sx;       // this thread's step-start state column
+    bool ex;                // this evaluation is at the step-start state
+    FB_DEV bool exact() const { return ex; }
     FB_DEV double get(int k) const { return p[k * T]; }
+    FB_DEV void set(int k, double v) const { p[k * T] = v; }
+    FB_DEV d3 n0() const {  // n_e of the step-start state
+        if (KIN == FB_WA) {
+            const double w = sx[(KINX + 4) * T], x = sx[(KINX + 5) * T], y = sx[(KINX + 6) * T], z = sx[(KINX + 7) * T];
+            return mk3(-(2.0 * x * z + 2.0 * w * y), -(2.0 * y * z - 2.0 * w * x), -(1.0 - 2.0 * (x * x + y * y)));
+        }
+        return mk3(sx[(KINX + 4) * T], sx[(KINX + 5) * T], sx[(KINX + 6) * T]);
+    }
 };
 
 // derivative sink that simply stores into a local array (test hook, trim, output pass)
@@ -304,22 +389,31 @@ static __device__ __noinline__ void isa_upper(double hg, double T_sl, double p_s
 // ISA temperature / pressure at orthometric altitude h_o, plus tr = (p/p_std)^(-beta R/g) for the engine
 // trf = (p_sl / p_std)^kT (input-derived, see FB_UX_TRF). TROPO_ONLY (the airborne integrator layout): above 11 km the
 // member is handed to the complete kernel instead of carrying the upper-layer code.
-template <bool TROPO_ONLY = false>
-FB_DEV void isa_data(double h_o, double T_sl, double p_sl, double trf, double& T, double& p, double& tr, int& err) {
+template <bool TROPO_ONLY = false, class Anc = NoAnchor, class PSL>
+FB_DEV void isa_data(double h_o, double T_sl, const PSL& p_sl_of, double trc, double& T, double& p, double& tr, int& err, const Anc& anc = Anc()) {
     constexpr double beta = -6.5e-3;
     constexpr double k = -isa::g_std / (beta * isa::R);     // 5.2558...
-    constexpr double kT = -beta * isa::R / isa::g_std;      // 1 / k
     if (h_o < -1000.0) err = FB_ST_BOUNDS;
     double hg = h_o * wgs::a * fb_rcp(wgs::a + h_o);
     if (TROPO_ONLY || hg < 11000.0) {
         T = fma(beta, hg, T_sl);
-        double ratio = T * fb_rcp(T_sl);
-        p = p_sl * exp(k * log(ratio));
-        tr = ratio * trf;                                   // (p/p_std)^kT = (p_sl/p_std)^kT * ratio, since k * kT == 1
+        tr = T * trc;                                       // (p/p_std)^kT = (p_sl/p_std)^kT * T / T_sl, since k * kT == 1
+        bool ex = !Anc::ON || anc.exact();
+        double e = 0.0;
+        if (Anc::ON && !ex) { e = fma(T, anc.get(ANC_IT), -1.0); ex = !(fabs(e) < 2e-4); }
+        if (ex) {
+            double ratio = T * fb_rcp(T_sl);
+            p = p_sl_of() * exp(k * log(ratio));
+            if (Anc::ON) { anc.set(ANC_P, p); anc.set(ANC_IT, fb_rcp(T)); }
+        } else {   // p0 (1 + e)^k
+            constexpr double c2 = k * (k - 1) / 2, c3 = c2 * (k - 2) / 3, c4 = c3 * (k - 3) / 4;
+            p = anc.get(ANC_P) * fma(e, fma(e, fma(e, fma(e, c4, c3), c2), k), 1.0);
+        }
         if (TROPO_ONLY && !(hg < 11000.0)) err = FB_NEED_COMPLETE;
     } else {   // rare: copies keep the callee's by-reference outputs from pinning the caller's values in local memory
+        constexpr double kT = -beta * isa::R / isa::g_std;      // 1 / k
         double T2, p2; int e2 = 0;
-        isa_upper(hg, T_sl, p_sl, T2, p2, e2);
+        isa_upper(hg, T_sl, p_sl_of(), T2, p2, e2);
         T = T2; p = p2; if (e2) err = e2;
         tr = pow_slow(p2 * (1.0 / isa::p_std), kT);
     }
@@ -352,8 +446,13 @@ FB_DEV void sincos_small(double x, double& s, double& c) {
     c = fma(pc, x2, 1.0);
 }
 
+#ifndef FB_COM_EXACT
+#define FB_COM_EXACT 0     // 1: geodetic coordinates of the CoM by a second ECEF -> geodetic conversion, as the reference does (diagnostic)
+#endif
 // kinematic data shared by the subsystems of one RHS evaluation
-struct Kin { q4 q_nb, q_eb; d3 n_e, r_eb_e, w_wb_b, w_eb_b, v_eb_b, v_eb_n; double h_e, h_o, lat, lon; };
+struct Kin { q4 q_nb, q_eb; d3 n_e, r_eb_e, w_wb_b, w_eb_b, v_eb_b, v_eb_n; double h_e, h_o, lat, lon;
+             double iMh, iNh, clat;      // 1 / (M + h), 1 / (N + h), cos(lat) = |(n_x, n_y)|
+             double s_eb, s_ew; };       // norm defects |q_eb|^2 - 1 and |q_ew|^2 - 1 (0 where the quaternion is built from angles)
 
 // one landing-gear unit (strut + contact). Adds its wrench to (F, tau) in body axes. Fast reciprocals / square roots
 // where the operand is bounded away from zero (direction cosines of a strut that has not crashed, friction
@@ -472,9 +571,34 @@ FB_DEV double interp_2x9_line(const double* y, double n0, double n1, double x0, 
 
 // ------------------------------------------------------------------------------------------- the RHS
 // x: state (read-only; every component is read before its derivative is put into the sink).
-template <int VAR, int KIN, bool WY, bool AIR = false, class Sink, class U, class Tap = NoTap>
+// Geodetic latitude / longitude and cos(lat) of the n-vector k.n_e (geodesy.jl:103-106), exactly at the step-start state
+// and by the anchor's increment at the other stage states (see SmemAnchor).
+template <class Anc>
+FB_DEV void latlon(Kin& k, const Anc& anc) {
+    const double p2 = fb_max(fma(k.n_e.x, k.n_e.x, k.n_e.y * k.n_e.y), 1e-280);
+    const double ip = fb_rsqrt(p2);
+    { const double c = p2 * ip; k.clat = fma(fma(-c, c, p2), 0.5 * ip, c); }   // sqrt(p2) to the last bit: one ulp of the latitude is 7e-10 m, which the
+                                                                               // guidance laws differentiate (test_gpu_guidance.py)
+    bool ex = !Anc::ON || anc.exact();
+    if (Anc::ON && !ex) {
+        const d3 n0 = anc.n0();
+        const double ip0 = anc.get(ANC_ICLAT);
+        const double clat0 = fma(n0.x, n0.x, n0.y * n0.y) * ip0;
+        const double s = fma(k.n_e.z, clat0, -(k.clat * n0.z));                        // sin(lat - lat0)
+        const double t = fma(k.n_e.y, n0.x, -(k.n_e.x * n0.y)) * (ip * ip0);           // sin(lon - lon0)
+        k.lat = anc.get(ANC_LAT) + fma(s * s * (1.0 / 6.0), s, s);
+        k.lon = anc.get(ANC_LON) + fma(t * t * (1.0 / 6.0), t, t);
+        ex = !(fabs(s) < 1e-4 && fabs(t) < 1e-4 && p2 > 1e-6);
+    }
+    if (ex) {
+        k.lat = fb_atan2(k.n_e.z, k.clat);
+        k.lon = fb_atan2(k.n_e.y, k.n_e.x);
+        if (Anc::ON && anc.exact()) { anc.set(ANC_LAT, k.lat); anc.set(ANC_LON, k.lon); anc.set(ANC_ICLAT, ip); }
+    }
+}
+template <int VAR, int KIN, bool WY, bool AIR = false, class Sink, class U, class Tap = NoTap, class Anc = NoAnchor>
 FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& u,
-                const double* __restrict__ tb, const float* __restrict__ geoid, RhsOut& out, YFull* yf, const Tap tap = Tap()) {
+                const double* __restrict__ tb, const float* __restrict__ geoid, RhsOut& out, YFull* yf, const Tap tap = Tap(), const Anc anc = Anc()) {
     typedef Lay<VAR, KIN, AIR> L;
     out.wow = 0; out.crash = 0; out.err = 0; out.gnd = 0;
     Kin k;
@@ -485,6 +609,8 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
         q4 q_wb = mkq(x[L::KINX], x[L::KINX + 1], x[L::KINX + 2], x[L::KINX + 3]);
         q4 q_ew = mkq(x[L::KINX + 4], x[L::KINX + 5], x[L::KINX + 6], x[L::KINX + 7]);
         k.h_e = x[L::KINX + 8];
+        k.s_ew = fma(q_ew.w, q_ew.w, fma(q_ew.x, q_ew.x, fma(q_ew.y, q_ew.y, q_ew.z * q_ew.z))) - 1.0;
+        k.s_eb = fma(q_wb.w, q_wb.w, fma(q_wb.x, q_wb.x, fma(q_wb.y, q_wb.y, q_wb.z * q_wb.z))) - 1.0 + k.s_ew;
         double dq12 = 2.0 * q_ew.w * q_ew.x, dq13 = 2.0 * q_ew.w * q_ew.y;
         double dq24 = 2.0 * q_ew.x * q_ew.z, dq34 = 2.0 * q_ew.y * q_ew.z;
         // psi_nw = atan2(-(dq34+dq12), dq24-dq13); q_nw = Rz(psi_nw), built from (cos, sin) by half-angle identities
@@ -497,13 +623,13 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
         k.q_nb = qmul(q_nw, q_wb);
         k.q_eb = qmul(q_ew, q_wb);
         k.n_e = mk3(-(dq24 + dq13), -(dq34 - dq12), -(1.0 - 2.0 * (q_ew.x * q_ew.x + q_ew.y * q_ew.y)));
-        k.lat = fb_atan2(k.n_e.z, fb_sqrt(fma(k.n_e.x, k.n_e.x, k.n_e.y * k.n_e.y)));
-        k.lon = fb_atan2(k.n_e.y, k.n_e.x);
+        latlon(k, anc);
         k.v_eb_n = qrot(k.q_nb, k.v_eb_b);
         double M, N;
         radii(k.n_e.z, M, N);
         k.r_eb_e = mk3((N + k.h_e) * k.n_e.x, (N + k.h_e) * k.n_e.y, fma(N, 1 - wgs::e2, k.h_e) * k.n_e.z);
-        double wn_x = k.v_eb_n.y * fb_rcp(N + k.h_e), wn_y = -k.v_eb_n.x * fb_rcp(M + k.h_e);
+        k.iNh = fb_rcp(N + k.h_e); k.iMh = fb_rcp(M + k.h_e);
+        double wn_x = k.v_eb_n.y * k.iNh, wn_y = -k.v_eb_n.x * k.iMh;
         d3 w_ew_w = mk3(fma(c, wn_x, s * wn_y), fma(-s, wn_x, c * wn_y), 0.0);  // q_nw'(w_ew_n)
         d3 w_ew_b = qrot_inv(q_wb, w_ew_w);
         k.w_wb_b = k.w_eb_b - w_ew_b;
@@ -515,6 +641,8 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
         k.q_eb = mkq(x[L::KINX], x[L::KINX + 1], x[L::KINX + 2], x[L::KINX + 3]);
         k.n_e = mk3(x[L::KINX + 4], x[L::KINX + 5], x[L::KINX + 6]);
         k.h_e = x[L::KINX + 7];
+        k.s_ew = 0.0;
+        k.s_eb = fma(k.q_eb.w, k.q_eb.w, fma(k.q_eb.x, k.q_eb.x, fma(k.q_eb.y, k.q_eb.y, k.q_eb.z * k.q_eb.z))) - 1.0;
         // q_en = ltf(n_e) = Rz(lon) o Ry(-(lat + pi/2)) with (lat, lon) = LatLon(n_e): built from direction cosines by
         // half-angle identities. cos/sin of -(lat + pi/2) are (-sin lat, -cos lat).
         double p2 = fma(k.n_e.x, k.n_e.x, k.n_e.y * k.n_e.y);
@@ -527,13 +655,13 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
         half_angle_cs(-k.n_e.z * inn, -p * inn, cha, sha);
         q4 q_en = qmul(mkq(chl, 0.0, 0.0, shl), mkq(cha, 0.0, sha, 0.0));
         k.q_nb = qmul(qconj(q_en), k.q_eb);
-        k.lat = fb_atan2(k.n_e.z, p);
-        k.lon = fb_atan2(k.n_e.y, k.n_e.x);
+        latlon(k, anc);
         k.v_eb_n = qrot(k.q_nb, k.v_eb_b);
         double M, N;
         radii(k.n_e.z, M, N);
         k.r_eb_e = mk3((N + k.h_e) * k.n_e.x, (N + k.h_e) * k.n_e.y, fma(N, 1 - wgs::e2, k.h_e) * k.n_e.z);
-        double wx = k.v_eb_n.y * fb_rcp(N + k.h_e), wy = -k.v_eb_n.x * fb_rcp(M + k.h_e);
+        k.iNh = fb_rcp(N + k.h_e); k.iMh = fb_rcp(M + k.h_e);
+        double wx = k.v_eb_n.y * k.iNh, wy = -k.v_eb_n.x * k.iMh;
         k.w_wb_b = k.w_eb_b - qrot_inv(k.q_nb, mk3(wx, wy, 0.0));
         q4 d1 = qdt(k.q_eb, k.w_eb_b);
         d3 nd = qrot(q_en, mk3(-wy, wx, 0.0));                 // w_ew_n x (0, 0, -1)
@@ -543,6 +671,7 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
     } else if (KIN == FB_NED) {
         double psi = x[L::KINX], th = x[L::KINX + 1], phi = x[L::KINX + 2];
         k.lat = x[L::KINX + 3]; k.lon = x[L::KINX + 4]; k.h_e = x[L::KINX + 5];
+        k.s_ew = 0.0; k.s_eb = 0.0;
         if (fabs(k.lat) > 0.5 * FB_PI || fabs(k.lon) > FB_PI) out.err = FB_ST_BOUNDS;
         double sps, cps, sth, cth, sph, cph;
         sincos(0.5 * psi, &sps, &cps); sincos(0.5 * th, &sth, &cth); sincos(0.5 * phi, &sph, &cph);
@@ -560,7 +689,8 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
         radii(k.n_e.z, M, N);
         k.r_eb_e = mk3((N + k.h_e) * k.n_e.x, (N + k.h_e) * k.n_e.y, fma(N, 1 - wgs::e2, k.h_e) * k.n_e.z);
         double iN = fb_rcp(N + k.h_e);
-        double wx = k.v_eb_n.y * iN, wy = -k.v_eb_n.x * fb_rcp(M + k.h_e);
+        k.iNh = iN; k.iMh = fb_rcp(M + k.h_e); k.clat = cla;
+        double wx = k.v_eb_n.y * iN, wy = -k.v_eb_n.x * k.iMh;
         double icla = fb_rcp(cla);
         d3 w_en_n = mk3(wx, wy, -k.v_eb_n.y * (sla * icla) * iN);
         d3 w_nb_b = k.w_eb_b - qrot_inv(k.q_nb, w_en_n);
@@ -599,7 +729,7 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
 
     // ------------------------------------------------------------------ atmosphere + air data
     Air air;
-    isa_data<AIR>(k.h_o, u(FB_U_T_SL), u(FB_U_P_SL), u(FB_UX_TRF), air.T, air.p, air.tr, out.err);
+    isa_data<AIR>(k.h_o, u(FB_U_T_SL), [&]() { return u(FB_U_P_SL); }, u(FB_UX_TRC), air.T, air.p, air.tr, out.err, anc);
     {
         air.iRT = fb_rcp(isa::R * air.T);
         air.rho = air.p * air.iRT;
@@ -915,24 +1045,18 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
 
     // ------------------------------------------------------------------ mass properties (affine in the masses)
     // airframe at Ob: m 767, J_G diag(820,1164,1702), r (0.056,0,0.582): J_O = J_G + m (|r|^2 I - r r^T)
+    // fuel: two tanks of m_fuel / 2 at (0.325, -+2.845, 0); payload: six moments of the five station masses (payload_moments)
     double m, mrx, mry, mrz, Jxx, Jyy, Jzz, Jxy, Jxz, Jyz;
     {
-        constexpr double ma = 767.0, ax = 0.056, az = 0.582;
-        m = ma; mrx = ma * ax; mry = 0.0; mrz = ma * az;
-        Jxx = 820.0 + ma * (az * az); Jyy = 1164.0 + ma * (ax * ax + az * az); Jzz = 1702.0 + ma * (ax * ax);
-        Jxy = 0.0; Jxz = -ma * ax * az; Jyz = 0.0;
-        auto add_pt = [&](double mp, double rx, double ry, double rz) {
-            m += mp; mrx = fma(mp, rx, mrx); mry = fma(mp, ry, mry); mrz = fma(mp, rz, mrz);
-            Jxx = fma(mp, ry * ry + rz * rz, Jxx); Jyy = fma(mp, rx * rx + rz * rz, Jyy); Jzz = fma(mp, rx * rx + ry * ry, Jzz);
-            Jxy = fma(mp, -rx * ry, Jxy); Jxz = fma(mp, -rx * rz, Jxz); Jyz = fma(mp, -ry * rz, Jyz);
-        };
-        add_pt(0.5 * m_fuel, 0.325, -2.845, 0.0);
-        add_pt(0.5 * m_fuel, 0.325, 2.845, 0.0);
-        add_pt(u(FB_U_M_PILOT), 0.183, -0.356, 0.899);
-        add_pt(u(FB_U_M_COPILOT), 0.183, 0.356, 0.899);
-        add_pt(u(FB_U_M_LPASS), -0.681, -0.356, 0.899);
-        add_pt(u(FB_U_M_RPASS), -0.681, 0.356, 0.899);
-        add_pt(u(FB_U_M_BAGGAGE), -1.316, 0.0, 0.899);
+        constexpr double ma = 767.0, ax = 0.056, az = 0.582, fx = 0.325, fy = 2.845, pz = 0.899;
+        double S[6];
+        u.payload(S);
+        m = (ma + m_fuel) + S[0];
+        mrx = fma(fx, m_fuel, ma * ax) + S[1]; mry = S[2]; mrz = fma(pz, S[0], ma * az);
+        Jxx = fma(fy * fy, m_fuel, 820.0 + ma * (az * az)) + fma(pz * pz, S[0], S[4]);
+        Jyy = fma(fx * fx, m_fuel, 1164.0 + ma * (ax * ax + az * az)) + fma(pz * pz, S[0], S[3]);
+        Jzz = fma(fx * fx + fy * fy, m_fuel, 1702.0 + ma * (ax * ax)) + (S[3] + S[4]);
+        Jxy = -S[5]; Jxz = fma(-pz, S[1], -ma * ax * az); Jyz = -pz * S[2];
     }
     // ------------------------------------------------------------------ rigid-body dynamics (dynamics.jl:443-499)
     {
@@ -944,6 +1068,7 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
         d3 w = k.w_eb_b;
         d3 tau_c = tau - cross(rc, F);
         d3 v_c = k.v_eb_b + cross(w, rc);
+#if FB_COM_EXACT
         d3 w_ie_b = qrot_inv(k.q_eb, mk3(0.0, 0.0, wgs::w_ie));
         d3 w_ic = w_ie_b + w;
         d3 r_ec_e = k.r_eb_e + qrot(k.q_eb, rc);
@@ -962,6 +1087,36 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
             double s1 = fma(k.q_eb.w, k.q_eb.w, fma(k.q_eb.x, k.q_eb.x, fma(k.q_eb.y, k.q_eb.y, k.q_eb.z * k.q_eb.z))) - 1.0;
             g_c = mk3(fma(s1, u_dn.x, g_c.x), fma(s1, u_dn.y, g_c.y), fma(s1, u_dn.z - g, g_c.z));
         }
+#else
+        // Geodetic coordinates of the CoM without a second ECEF -> geodetic conversion. The reference converts
+        // r_ec_e = r_eb_e + R_eb rc back with Fukushima's method (dynamics.jl:481-487, geodesy.jl:367-412) to get the
+        // ellipsoid normal n_c and the altitude h_c at Oc for gravity(Oc) and ltf(Oc). Oc is |rc| < 1.5 m from Ob, so
+        // with (dN, dE, dD) = R_nb rc the normal tilts by thN = dN / (M + h) towards north and thE = dE / (N + h)
+        // towards east, sin(lat_c) = sin(lat) + thN cos(lat), and h_c = h_e - dD + (thN dN + thE dE) / 2 (the
+        // ellipsoid falling away under the tangent plane); what is dropped is of second order in |rc| / R,
+        // < 1e-13 relative on the direction and 1e-14 m on the altitude. Gravity at Oc in the local-level axes of Ob
+        // is then g (-thN, -thE, 1), and q_nb takes it to body axes; the Earth rate comes the same way from its
+        // local-level components w_ie (cos lat, 0, -sin lat).
+        // Norm defect (the state quaternions are only renormalised when | |q| - 1 | > 1e-8, kinematics.jl:114-118, and a
+        // steady turn holds |q_wb|^2 - 1 at a few 1e-10, so it is part of the reference's arithmetic — dropping it moves a
+        // 600 s cfg-3 trajectory by 2e-9): the reference rotates a vector v given in the axes it starts from by a
+        // quaternion q with the formula v + 2 q_im x (q_re v + q_im x v) = R v + (|q|^2 - 1)(R v - v). It does so with
+        // q_eb' on the Earth rate (0, 0, w_ie) and with q_eb' o ltf(Oc) on (0, 0, g); here both are rotated by q_nb' from
+        // their local-level components t, which carries (|q_nb|^2 - 1)(R t - t) instead. To first order in the defects
+        // the difference is (|q_eb|^2 - 1)(t - v) on the Earth rate (t and v are far apart) and (|q_ew|^2 - 1)(R v - v) on
+        // gravity (t = v to 2e-7); both are restored below.
+        const d3 t_ie = mk3(wgs::w_ie * k.clat, 0.0, -wgs::w_ie * k.n_e.z);
+        d3 w_ie_b = qrot_inv(k.q_nb, t_ie);
+        w_ie_b = mk3(fma(k.s_eb, t_ie.x, w_ie_b.x), w_ie_b.y, fma(k.s_eb, t_ie.z - wgs::w_ie, w_ie_b.z));
+        d3 w_ic = w_ie_b + w;
+        d3 d_n = qrot(k.q_nb, rc);
+        const double thN = d_n.x * k.iMh, thE = d_n.y * k.iNh;
+        const double h_c = k.h_e - d_n.z + 0.5 * fma(thN, d_n.x, thE * d_n.y);
+        if (h_c < -1000.0) out.err = FB_ST_BOUNDS;
+        const double g = gravity(fma(thN, k.clat, k.n_e.z), h_c);
+        d3 g_c = qrot_inv(k.q_nb, mk3(-g * thN, -g * thE, g));
+        if (KIN == FB_WA) g_c = mk3(fma(k.s_ew, g_c.x, g_c.x), fma(k.s_ew, g_c.y, g_c.y), fma(k.s_ew, g_c.z - g, g_c.z));
+#endif
         auto Jmul = [&](d3 v) { return mk3(a11 * v.x + a12 * v.y + a13 * v.z, a12 * v.x + a22 * v.y + a23 * v.z, a13 * v.x + a23 * v.y + a33 * v.z); };
         d3 hc = Jmul(w_ic);
         hc.x += h_rot_x;

@@ -1,0 +1,8 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+O=gpurun_out; mkdir -p $O
+python -m pytest tests -m gpu -q -s 2>&1 | grep -E "AssertionError|passed|failed|FAILED|worst|Error" | cut -c1-300 | tail -30
+B="python bench.py --no-cpu-baseline --no-aux --no-e2e --warmup 3"
+for m in 131072 1048576; do
+$B --steps 6 --members $m 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$m', 'steps/s %.4g'%d['value'], 'ms %.3f'%d['ms_per_step'], 'frac %.3f'%d['roofline']['frac'])"
+done
