@@ -241,7 +241,8 @@ struct StepShape {
 template <int VAR, int KIN, bool AIR, int CAP = FB_STEP_BLOCK>
 __global__ void __launch_bounds__((StepShape<VAR, KIN, AIR, CAP>::T), 1)
 step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt, int periodic_every, double Dt,
-            unsigned long long* rhs_count, int* resume, int resume_mode, unsigned* ground_count, int mpc, int chunk) {
+            unsigned long long* rhs_count, int* resume, int resume_mode, unsigned* ground_count, int mpc, int chunk,
+            unsigned* queue = nullptr, int* done_g = nullptr) {
     typedef Lay<VAR, KIN, AIR> L;
     typedef Lay<VAR, KIN, false> LF;
     constexpr int NX = L::NX;
@@ -257,27 +258,41 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
     if (threadIdx.x == 0) rhs_cta = 0ull;
     stage_tables(smem_tb, E.tables.pack, TBL);   // (contains the __syncthreads that orders the two initialisations above)
     GainsShared gains; gains.base = nullptr; gains.sbase = (unsigned)__cvta_generic_to_shared(smem) + FB_TB_BYTES;
-    // Work distribution: the CTA owns `mpc` consecutive members = MW member-warps, and the launch is cut into C chunks
-    // of `chunk` steps. Task j = (member-warp j % MW, chunk j / MW); hardware warp w runs tasks w, w + HW, ... Each task
-    // is the whole body below on its members (state from HBM, `chunk` steps, state back to HBM). With mpc = blockDim
-    // and chunk = n_steps this is the plain one-thread-per-member launch. With MW > HW it time-slices the member-warps
-    // over the 12 warps the register file holds, so an ensemble of e.g. 443 members per SM takes 14/12 of a wave
-    // instead of two waves (or a 14-warp shape at 128 registers). A task's predecessor (same members, previous chunk)
-    // sits MW tasks earlier in the sequence, i.e. always in an earlier round of some warp: the wait below cannot deadlock.
+    // Work distribution. A task = (member-warp, chunk of `chunk` steps): the whole per-member body below — state from HBM, the
+    // chunk's steps, state back to HBM. Tasks are numbered chunk-major (all member-warps of chunk 0, then chunk 1, ...), and a
+    // task may only start when the same member-warp's previous chunk has been published.
+    //  * queue == nullptr (static): the CTA owns `mpc` consecutive members = MW member-warps; hardware warp w runs tasks w,
+    //    w + HW, ...; the predecessor of a task always sits in an earlier round of the same CTA, so the wait on the
+    //    shared-memory counter cannot deadlock. With mpc = block size and one chunk this is the plain one-thread-per-member launch.
+    //  * queue != nullptr (dynamic, the airborne launches): ONE persistent CTA per SM, and every hardware warp of the GPU
+    //    draws its next task from a global counter, so that neither a slow warp nor a slow SM holds the launch up (a
+    //    131,072-member shard is 3.46 tasks per hardware warp: statically distributed, 6.5 % of the launch was SMs waiting for
+    //    the slowest one). A predecessor has a smaller number than its successor, so it has been drawn by a resident warp
+    //    before the successor can wait for it: no deadlock. State handed from one SM to another goes through L2: the writer
+    //    fences before it publishes `done_g[mw]`, and this translation unit is compiled with -dlcm=cg (every global load is
+    //    an L2 load), so a stale line in the other SM's L1 can never be read.
     const int lane = threadIdx.x & 31, HW = blockDim.x >> 5;
-    const long long cta_base = (long long)blockIdx.x * mpc;
-    const int MW = (int)((min((long long)mpc, E.n - cta_base) + 31) / 32);
+    const bool dyn = queue != nullptr;
+    const long long cta_base = dyn ? 0ll : (long long)blockIdx.x * mpc;
+    const int MW = (int)((min(dyn ? E.n : (long long)mpc, E.n - cta_base) + 31) / 32);
     const int C = (n_steps_launch + chunk - 1) / chunk;
-    volatile int* chunk_done = chunk_done_s;
+    volatile int* chunk_done = dyn ? done_g : chunk_done_s;
     // right-hand-side evaluations of this thread's tasks; folded into one shared-memory counter and ONE global atomic per CTA
     // at the end (a global atomic per thread and task put 2.6e5 same-address atomics behind every time-sliced cfg-3 launch of a
     // 131,072-member shard: ~0.3 ms of an 11.5 ms launch)
     unsigned rhs_mine = 0;
-    for (int task = threadIdx.x >> 5; task < MW * C; task += HW) {
+    for (int task = threadIdx.x >> 5;; task += HW) {
+    if (dyn) {
+        int t = 0;
+        if (lane == 0) t = (int)atomicAdd(queue, 1u);
+        task = __shfl_sync(0xffffffffu, t, 0);
+    }
+    if (task >= MW * C) break;
     const int mw = task % MW, ck = task / MW;
     if (C > 1) {
-        while (chunk_done[mw] < ck) __nanosleep(64);
-        __threadfence_block(); __syncwarp();
+        while (chunk_done[mw] < ck) __nanosleep(dyn ? 200 : 64);
+        if (dyn) __threadfence(); else __threadfence_block();
+        __syncwarp();
     }
     do {   // one task; `break` leaves it
     long long step0 = step0_launch + (long long)ck * chunk;
@@ -469,8 +484,9 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
     // RHS evaluations of this launch: k1 of the first step, then k2..k4 and f(x*) per step, plus re-evaluations
     rhs_mine += max(0, 4 * done + n_reeval + (pending ? -3 : 1) + (handover >= 0 ? (sink.stage & 3) : 0));
     } while (0);
-    if (C > 1) {   // publish the chunk: the next task on these members may run on another warp of this CTA
-        __threadfence_block(); __syncwarp();
+    if (C > 1) {   // publish the chunk: the next task on these members may run on another warp (of this CTA, or of any SM)
+        if (dyn) __threadfence(); else __threadfence_block();
+        __syncwarp();
         if (lane == 0) chunk_done[mw] = ck + 1;
     }
     }

@@ -62,6 +62,9 @@ struct fb_sim {
     bool force_complete = false;
     bool air_wide = false;           // airborne kernel shape: FB_STEP_BLOCK_WIDE threads (one-wave ensembles) or FB_STEP_BLOCK
     int air_mpc = 0;                 // > step_block_air: time-sliced airborne launches, this many members per CTA (fb_kernels.cuh)
+    bool air_dyn = false;            // airborne launches draw (member-warp, chunk) tasks from a global queue: one persistent CTA per SM
+    int air_grid = 0;                // ... this many CTAs
+    unsigned* d_queue = nullptr;     // [0]: next task, [1 .. 1 + member-warps): chunks published per member-warp
     // ensemble moments of the log samples (EnsembleDev::mom_*): one device allocation, a pinned staging copy for the
     // asynchronous fetch, and the side stream + communicator of the all-reduce over the shards
     void* d_mom = nullptr;
@@ -109,7 +112,24 @@ template <int VAR, int KIN> struct Ops {
                 }
             }
             int grid_a = (int)((s->E.n + mpc - 1) / mpc);
-            if (s->air_wide)
+            if (s->air_dyn) {
+                // dynamic distribution: cut the launch into C chunks so that the MWT * C tasks keep all HWT hardware warps
+                // of the GPU busy to the end (cost in step units: rounds x (chunk + the k1 a chunk start re-evaluates +
+                // the state round trip of a task))
+                const long long MWT = (s->E.n + 31) / 32, HWT = (long long)s->air_grid * (Ta / 32);
+                double best = 1e300;
+                chunk = n > 0 ? n : 1;
+                for (int C = 1; C <= 16 && (C == 1 || C * 4 <= n); C++) {
+                    const int ch = (n + C - 1) / C, Cr = (n + ch - 1) / ch;
+                    const double cost = (double)((MWT * Cr + HWT - 1) / HWT) * (ch + (Cr > 1 ? 0.25 : 0.0) + 0.3);
+                    if (cost < best) { best = cost; chunk = ch; }
+                }
+                e = cudaMemsetAsync(s->d_queue, 0, sizeof(unsigned) * (size_t)(1 + MWT), s->stream);
+                if (e != cudaSuccess) return e;
+                step_kernel<VAR, KIN, true><<<s->air_grid, Ta, StepShape<VAR, KIN, true>::SMEM, s->stream>>>(
+                    s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_resume, 0, s->d_ground, Ta, chunk,
+                    s->d_queue, reinterpret_cast<int*>(s->d_queue + 1));
+            } else if (s->air_wide)
                 step_kernel<VAR, KIN, true, FB_STEP_BLOCK_WIDE><<<grid_a, Ta, StepShape<VAR, KIN, true, FB_STEP_BLOCK_WIDE>::SMEM, s->stream>>>(
                     s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_resume, 0, s->d_ground, mpc, chunk);
             else
@@ -448,6 +468,25 @@ static int32_t create_body(fb_sim* s) {
             if (use) { s->air_wide = false; s->step_block_air = tmax; s->air_mpc = mw * 32; }
         }
     }
+    {   // Fourth option: one persistent CTA per SM of the full-register shape, (member-warp, chunk) tasks drawn from a global
+        // queue (fb_kernels.cuh). Measured on one B200 (same box, interleaved): fly-by-wire kernels (8 warps per SM) +3.3 % on a
+        // 131,072-member shard (3.5 tasks per hardware warp), -0.7 % at 2^20 members (27.7 CTA waves balance themselves);
+        // C172S (12 warps per SM, whose static time-slicing is already an exact number of rounds) -1 %. Hence: the variants
+        // with control laws, below eight CTA waves. FLIGHTBATCH_DYNAMIC=1/0 forces it on/off, FLIGHTBATCH_SLICED=0/1 selects
+        // the static shapes above (diagnostic switches).
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, cfg->device));
+        const int tmax = FB_DISPATCH(s, step_tmax)(1), hw = tmax / 32;
+        const long long mwt = (N + 31) / 32;
+        bool use = cfg->variant >= FB_C172X1 && mwt < 8ll * prop.multiProcessorCount * hw;
+        if (const char* dynv = getenv("FLIGHTBATCH_DYNAMIC")) use = atoi(dynv) != 0;
+        if (getenv("FLIGHTBATCH_SLICED")) use = false;
+        if (use) {
+            s->air_dyn = true; s->air_wide = false; s->air_mpc = 0; s->step_block_air = tmax;
+            s->air_grid = (int)std::min<long long>(prop.multiProcessorCount, (mwt + hw - 1) / hw);
+            CK(cudaMalloc(&s->d_queue, sizeof(unsigned) * (size_t)(1 + mwt)));
+        }
+    }
     // FLIGHTBATCH_KERNEL=complete pins the complete kernel (no airborne instantiation, no hand-over): a diagnostic switch used
     // by the tests to check that the two launch paths produce the same trajectories
     if (const char* k = getenv("FLIGHTBATCH_KERNEL")) s->force_complete = (strcmp(k, "complete") == 0);
@@ -474,7 +513,7 @@ int32_t fb_destroy(fb_handle s) {
     cudaFree(s->d_pack); cudaFree(s->d_geoid);
     cudaFree(s->d_ev_off); cudaFree(s->d_ev_step); cudaFree(s->d_ev_field); cudaFree(s->d_ev_value); cudaFree(s->d_ev_cursor);
     cudaFree(s->d_log_fields); cudaFree(s->d_scratch); cudaFree(s->d_rhs_count);
-    cudaFree(s->d_resume); cudaFree(s->d_ground); if (s->h_ground) cudaFreeHost(s->h_ground); if (s->ground_ev) cudaEventDestroy(s->ground_ev);
+    cudaFree(s->d_resume); cudaFree(s->d_ground); cudaFree(s->d_queue); if (s->h_ground) cudaFreeHost(s->h_ground); if (s->ground_ev) cudaEventDestroy(s->ground_ev);
     if (s->comm_stream) cudaStreamSynchronize(s->comm_stream);
     if (s->comm && s->comm_owned && nccl_api()) nccl_api()->CommDestroy(s->comm);
     for (auto& t : s->comm_timers) { cudaEventDestroy(t.first); cudaEventDestroy(t.second); }

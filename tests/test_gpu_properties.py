@@ -146,3 +146,60 @@ def test_time_sliced_launch_is_bit_identical_to_plain_launch(fb, model):
     assert np.array_equal(a["x"], b["x"])
     for la, lb in zip(a["log"], b["log"]):
         assert np.array_equal(la, lb, equal_nan=True)     # a frozen member leaves NaN in both
+
+
+@pytest.mark.parametrize("model", ["Cessna172Sv0", "Cessna172Xv2"])
+def test_dynamic_task_queue_is_bit_identical_to_plain_launch(fb, model):
+    """The airborne launches that draw (member-warp, chunk) tasks from a global queue (one persistent CTA per SM, a member's
+    state handed from SM to SM through L2 between chunks: FLIGHTBATCH_DYNAMIC=1) against the plain one-thread-per-member
+    launches: a ragged 60,001-member ensemble, scheduled inputs inside chunks, autopilot every step, a decimated log, some members
+    flown into the terrain gate so that the hand-over to the complete kernel happens in the middle of a chunk. Bit for bit."""
+    import bench
+    n = 60001
+    p = bench.member_params(0, n)
+
+    def run(dyn):
+        os.environ["FLIGHTBATCH_DYNAMIC"] = "1" if dyn else "0"
+        if not dyn:
+            os.environ["FLIGHTBATCH_SLICED"] = "0"
+        try:
+            ac = getattr(fb, model)(fb.WA())
+            sim = fb.BatchSimulation(fb.SimpleWorld(ac), n=n, dt=0.01, Dt=0.01, t_end=4.0, steps_per_launch=100, saveat=0.07,
+                                     log_fields=("theta", "eas"))
+        finally:
+            del os.environ["FLIGHTBATCH_DYNAMIC"]
+            os.environ.pop("FLIGHTBATCH_SLICED", None)
+        rng = np.random.default_rng(5)
+        if model == "Cessna172Xv2":
+            sim.set_input("wind_n", rng.uniform(-10, 10, n))
+        # every 97th member starts 4.5..6.5 m above its terrain and descends: it crosses the 4 m gate inside a chunk
+        low = np.arange(0, n, 97)
+        elev = np.zeros(n); elev[low] = p["h_e"][low] - bench.geoid_height(p["lat"][low], p["lon"][low]) - rng.uniform(4.5, 6.5, low.size)
+        sim.set_input("trn_elevation", elev)
+        sim.init(fb.C172.TrimParameters(**p))
+        idx = np.arange(n)
+        if model == "Cessna172Xv2":
+            sim.set_input("lon_mode_req", 7.0); sim.set_input("lat_mode_req", 3.0)
+            clm = np.linspace(0.5, 3.0, n); clm[low] = -3.0
+            sim.set_input("lon_clm_ref", clm); sim.set_input("lat_phi_ref", np.linspace(-0.5, 0.5, n))
+            sim.schedule_inputs(idx, np.full(n, 123), np.full(n, fb.U["FB_U_LAT_PHI_REF"]), np.linspace(0.5, -0.5, n))
+        else:
+            ele = sim.get_input("elevator")
+            d = np.full(n, 0.05); d[low] = -0.08
+            sim.schedule_inputs(np.concatenate([idx, idx]), np.concatenate([np.full(n, 57), np.full(n, 130)]),
+                                np.full(2 * n, fb.U["FB_U_ELEVATOR"]), np.concatenate([ele + d, ele - 0.05]))
+        sim.step(3.0)
+        sim.step(0.01); sim.step(0.07)
+        ts = fb.TimeSeries(sim)
+        out = dict(x=sim.x, status=sim.status(), disc=sim.discrete(), counters=sim.counters(), log=[ts.theta.copy(), ts.eas.copy()],
+                   low_h=sim.get_output("h_o")[low] - elev[low])
+        sim.close()
+        return out
+    a, b = run(True), run(False)
+    assert a["counters"]["rhs_evals"] > b["counters"]["rhs_evals"]     # the queue really cut the launches into chunks
+    assert (b["low_h"] < 4.0).sum() > 50                               # members did go through the hand-over
+    assert np.array_equal(a["status"], b["status"])
+    assert np.array_equal(a["disc"][0], b["disc"][0]) and np.array_equal(a["disc"][1], b["disc"][1])
+    assert np.array_equal(a["x"], b["x"])
+    for la, lb in zip(a["log"], b["log"]):
+        assert np.array_equal(la, lb, equal_nan=True)

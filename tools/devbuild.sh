@@ -7,7 +7,8 @@ ONLY=-DFB_ONLY_S_WA
 for a in "$@"; do [ "$a" = "-DFB_ONLY_X1_WA" ] && ONLY=; done
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC $ONLY -Xptxas -v"
 for tu in flightbatch flightbatch_complete; do
-  nvcc $FLAGS "$@" -c -o build/dev_$name/$tu.o flight.jl_b200/csrc/$tu.cu > build/dev_$name/$tu.log 2>&1 &
+  EXTRA=; [ $tu = flightbatch ] && EXTRA="-Xptxas -dlcm=cg"
+  nvcc $FLAGS $EXTRA "$@" -c -o build/dev_$name/$tu.o flight.jl_b200/csrc/$tu.cu > build/dev_$name/$tu.log 2>&1 &
 done
 wait
 grep -h -A1 "Function properties for _Z11step_kernel" build/dev_$name/*.log | grep -v "^--" | sed 's/ptxas info    : Function properties for //'
