@@ -11,7 +11,9 @@
 // ~9 instructions per call on sm_100a, and this path is NaN-free by construction.
 __host__ __device__ inline double fb_max(double a, double b) { return (a < b) ? b : a; }
 __host__ __device__ inline double fb_min(double a, double b) { return (a > b) ? b : a; }
-__host__ __device__ inline double clampd(double x, double lo, double hi) { x = (x < lo) ? lo : x; return (x > hi) ? hi : x; }
+// Both compares read the ORIGINAL x, so they issue back to back instead of the second waiting for the first select (lo <= hi:
+// at most one of them holds); same result as max(lo, min(x, hi)) for every non-NaN x.
+__host__ __device__ inline double clampd(double x, double lo, double hi) { const bool below = x < lo, above = x > hi; const double r = below ? lo : x; return above ? hi : r; }
 
 struct d3 { double x, y, z; };
 struct q4 { double w, x, y, z; };

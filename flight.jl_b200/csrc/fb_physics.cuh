@@ -446,6 +446,9 @@ FB_DEV void sincos_small(double x, double& s, double& c) {
     c = fma(pc, x2, 1.0);
 }
 
+#ifndef FB_LDG_EXACT
+#define FB_LDG_EXACT 1     // 1: strut attachment geodesy by ECEF -> geodetic conversions and ECEF vector differences, as the reference does; 0: to first order in |r_bs| / R (see ldg_unit)
+#endif
 #ifndef FB_COM_EXACT
 #define FB_COM_EXACT 0     // 1: geodetic coordinates of the CoM by a second ECEF -> geodetic conversion, as the reference does (diagnostic)
 #endif
@@ -465,13 +468,36 @@ FB_DEV void ldg_unit(const Kin& k, const float* __restrict__ geoid, double elev,
                                       double x0, double x1, double& xd0, double& xd1, d3& F, d3& tau, int leg, RhsOut& out,
                                       double* xi_out, double* fdmp_out) {
     const d3 e3 = mk3(0.0, 0.0, 1.0);
+#if FB_LDG_EXACT
     d3 ks_e = qrot(k.q_eb, e3);
     d3 r_bs_e = qrot(k.q_eb, r_bs_b);
     d3 r_es_e = k.r_eb_e + r_bs_e;
     d3 n_t; double he_w;
     geo_from_cartesian(r_es_e, n_t, he_w);
     if (he_w < -1000.0) out.err = FB_ST_BOUNDS;
-    double he_t = elev + geoid_at_n(geoid, n_t);
+    // Geoid undulation under the strut: the reference takes LatLon(n_t) (two atan2) for the table lookup; here latitude and
+    // longitude of Os come from those of Ob to first order in |r_bs| / R, (dN, dE) = horizontal part of R_nb r_bs — the
+    // second-order remainder (1e-14 rad) moves the bilinear undulation by < 1e-11 m, two orders below the rounding of he_w.
+    // (he_w and the compression below keep the reference's own formulation: see FB_LDG_EXACT.)
+    double he_t;
+    {
+        const d3 d_s = qrot(k.q_nb, r_bs_b);
+        he_t = elev + geoid_height(geoid, fma(d_s.x, k.iMh, k.lat), fma(d_s.y * k.iNh, fb_rcp(fb_max(k.clat, 1e-9)), k.lon));
+    }
+#else
+    // Geodetic coordinates of the strut attachment Os to first order in |r_bs| / R (as for the CoM in the dynamics
+    // block): with (dN, dE, dD) = R_nb r_bs, lat_s = lat + dN / (M + h), lon_s = lon + dE / ((N + h) cos lat),
+    // h_s = h_e - dD + (curvature term). The reference converts r_es_e = r_eb_e + R_eb r_bs with Fukushima's method
+    // (landinggear.jl:245) and later differences two 6.4e6 m ECEF vectors for the compression (:262-270: r_et_e - r_es_e,
+    // which is exactly -dh n_t, projected on the terrain normal: l = dh / (u_t . k_s) up to cos(1e-7) - 1); the algebraic
+    // form carries less rounding noise than the reference's own (one ulp of 6.4e6 m is 9.3e-10 m), i.e. it differs from
+    // it by the reference's rounding spread, which is what tests/test_gpu_ground.py bounds.
+    const d3 d_s = qrot(k.q_nb, r_bs_b);
+    const double thN = d_s.x * k.iMh, thE = d_s.y * k.iNh;
+    const double he_w = k.h_e - d_s.z + 0.5 * fma(thN, d_s.x, thE * d_s.y);
+    if (he_w < -1000.0) out.err = FB_ST_BOUNDS;
+    double he_t = elev + geoid_height(geoid, k.lat + thN, fma(thE, fb_rcp(fb_max(k.clat, 1e-9)), k.lon));
+#endif
     if (he_t < -1000.0 || elev < -1000.0) out.err = FB_ST_BOUNDS;
     double dh = he_w - he_t;
     bool wow = dh <= 0.0;
@@ -481,12 +507,17 @@ FB_DEV void ldg_unit(const Kin& k, const float* __restrict__ geoid, double elev,
     d3 r_bc_b = r_bs_b;
     if (wow) {
         out.wow |= (1 << leg);
+#if FB_LDG_EXACT
         d3 r_et_e = cartesian_from_geo(n_t, he_t);
         d3 r_st_e = r_et_e - r_es_e;
         q4 q_en = qmul(k.q_eb, qconj(k.q_nb));          // product first, then rotate: keeps the reference's norm defect
         d3 ut_e = qrot(q_en, e3);                       // terrain normal (NED down) in ECEF: q_en(0,0,1)
         double ut_ks = dot(ut_e, ks_e);
         double l = dot(ut_e, r_st_e) * fb_rcp(ut_ks);
+#else
+        const double ut_ks = qrot(k.q_nb, e3).z;        // terrain normal (NED down at Ob) . strut axis
+        const double l = dh * fb_rcp(ut_ks);
+#endif
         // acos(ut_ks) in degrees > 60 (landinggear.jl:331-339) is ut_ks <= 1/2: acos(0.5) rounds to 60.00000000000001
         bool crash_angle = ut_ks <= 0.5;
         if (crash_angle) out.crash |= (1 << (2 * leg));

@@ -105,8 +105,15 @@ def _load(name):
 _libs = {}
 
 
+def build_fma():
+    subprocess.check_call(["make", "-s", "-C", _HERE, "liborc_fma.so"])
+    return "liborc_fma.so"
+
+
 def lib(counting=False, fast=False):
-    key = build_fast() if fast else ("liborc_count.so" if counting else "liborc.so")
+    # fast: False = the checker, True = the -march=native timing build of THIS host, "fma" = the portable FMA-contracted build
+    # (same code on every host: the rounding-spread tests must not depend on which CPU the GPU box has)
+    key = build_fma() if fast == "fma" else (build_fast() if fast else ("liborc_count.so" if counting else "liborc.so"))
     if key not in _libs:
         _libs[key] = _load(key)
     return _libs[key]
@@ -160,7 +167,8 @@ class Sim:
     """One reference `Simulation(SimpleWorld(Cessna172...); dt, Δt)` on the CPU oracle."""
 
     def __init__(self, variant=0, kin=0, dt=0.02, Dt=None, counting=False, fast=False):
-        """fast=True: the -O3 -march=native timing build (bench.py's CPU arm); the checker is the default build."""
+        """fast=True: the -O3 -march=native timing build (bench.py's CPU arm); fast="fma": the portable FMA-contracted build
+        (rounding-spread tests); the checker is the default build."""
         self.w = world(counting, fast)
         self.lib = self.w.lib
         self.h = self.lib.orc_sim_create(self.w.h, variant, kin, dt, dt if Dt is None else Dt)

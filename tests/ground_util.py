@@ -6,7 +6,7 @@ The reference computes a strut's compression from the difference of two ECEF pos
 millimetre-to-centimetre compression, and a member at rest sits on the friction-direction switch at 1e-3 m/s
 (landinggear.jl:436-452). Two builds of the SAME restatement that differ only in rounding therefore drift apart on the
 gear-driven states by far more than 1e-9. `oracle_spread` measures that: the checker build (-O2 -ffp-contract=off)
-against (a) the same sources compiled with FMA contraction (-O3 -march=native), (b) the checker started from a state
+against (a) the same sources compiled with FMA contraction (-O2 -ffp-contract=fast -mfma: a portable build, the same on every host), (b) the checker started from a state
 perturbed by one ulp, and (c) the checker with every state component nudged by one ulp in a random direction after every
 step, which is the step-to-step difference any other correct implementation (such as a GPU kernel with its own operation
 order, fused multiply-adds and reciprocal sequences) shows against it. The GPU-vs-oracle bound of tests/test_gpu_ground.py is
@@ -85,7 +85,7 @@ def oracle_spread(orc, U, IN, x0, stall, eng, inputs, events, chunks=CHUNKS, dt=
     histories needed to tell which members the perturbation pushed across a discrete event."""
     n = x0.shape[1]
     base = [clone(orc, U, IN, {f: v[i] for f, v in inputs.items()}, events[i], x0[:, i], stall[i], eng[i], dt) for i in range(n)]
-    fma = [clone(orc, U, IN, {f: v[i] for f, v in inputs.items()}, events[i], x0[:, i], stall[i], eng[i], dt, fast=True) for i in range(n)]
+    fma = [clone(orc, U, IN, {f: v[i] for f, v in inputs.items()}, events[i], x0[:, i], stall[i], eng[i], dt, fast="fma") for i in range(n)]
     x1 = x0.copy()
     kin0 = 12                                              # C172S/WA layout: kinematics block starts at row 12, h_e is its 9th entry
     x1[kin0 + 8] = np.nextafter(x1[kin0 + 8], np.inf)

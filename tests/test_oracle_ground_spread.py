@@ -2,7 +2,7 @@
 
 North star: states agree to <= 1e-9 relative. On the landing-gear path that cannot hold between ANY two implementations
 whose rounding differs: this test runs the cfg-4 takeoff / landing members (BASELINE.json configs[3] at test size) on two
-builds of the same restatement — the checker (-O2 -ffp-contract=off) and the timing build (-O3 -march=native, FMA contraction
+builds of the same restatement — the checker (-O2 -ffp-contract=off) and a second build of the same sources (-O2 -ffp-contract=fast -mfma, FMA contraction
 allowed) — and on the checker started one ulp away, and records how far they drift apart. tests/test_gpu_ground.py bounds the
 GPU-vs-oracle error by this spread (x5), measured there on the members it compares. Reference: landinggear.jl:262-275 (strut
 compression from the difference of two 6.4e6 m ECEF vectors), :436-452 (friction direction switch at 1e-3 m/s)."""

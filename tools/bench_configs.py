@@ -66,6 +66,11 @@ def cfg3(fb, n, seconds):
 
 
 def cfg4(fb, n, seconds):
+    # load both integrator kernels before the clock starts (CUDA loads a kernel's image at its first launch): a throw-away
+    # 64-member ensemble dropped on the gear, so that the timed run itself can start at t = 0 of the takeoff / landing sequence
+    w = fb.BatchSimulation(fb.SimpleWorld(fb.Cessna172Sv0(fb.WA())), n=64, dt=DT, t_end=10.0)
+    w.init(fb.C172.Init(h_e=2.0 + float(bench.geoid_height(0.0, 0.0))))
+    w.step(0.05); w.sync(); w.close()
     rng = np.random.default_rng(SEED + 40)
     half = n // 2
     lat = np.deg2rad(rng.uniform(-60, 60, n)); lon = rng.uniform(-np.pi, np.pi, n)
