@@ -46,6 +46,7 @@ UNIT = "aircraft-steps/s"
 # tests/test_oracle_golden.py::test_algorithmic_flop_count_of_record:
 A_STEP_FLOP = 15695.0        # airborne C172S/WA: 4 RHS x 3835 + RK combine + f_step!
 A_STEP_FLOP_CFG3 = 17390.0   # airborne C172X/WA with the control laws every step
+A_STEP_FLOP_GROUND = 22989.0  # C172S/WA standing on all three wheels, engine running (cfg 4): 4 RHS x 5657 + RK combine + f_step!
 STATS_FIELDS = ("h_e", "eas", "theta", "phi")
 
 

@@ -256,6 +256,14 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
     if (threadIdx.x < FB_MW_MAX) chunk_done_s[threadIdx.x] = 0;
     __shared__ unsigned long long rhs_cta;
     if (threadIdx.x == 0) rhs_cta = 0ull;
+    // Member index of lane 0 of each hardware warp's current task. Everything indexed by the member inside the step loop (the
+    // member's input column, its tap column, the log) re-derives its address from this word where it is used: those 64-bit
+    // pointers are touched once per step, and carried across the right-hand side they were spilled and re-read from local
+    // memory — an L2 round trip each beside 229 KB of shared memory — on every evaluation (16 % of all long-scoreboard stalls;
+    // cfg 3 +3.3 %). (Moving the loop's own counters to shared-memory words the same way was measured too: 3 % slower — the
+    // columns they take are worth more as tap entries, and ptxas spills more around the volatile accesses.)
+    __shared__ long long task_i0_s[32];
+    volatile long long* const task_i0 = task_i0_s + (threadIdx.x >> 5);
     stage_tables(smem_tb, E.tables.pack, TBL);   // (contains the __syncthreads that orders the two initialisations above)
     GainsShared gains; gains.base = nullptr; gains.sbase = (unsigned)__cvta_generic_to_shared(smem) + FB_TB_BYTES;
     // Work distribution. A task = (member-warp, chunk of `chunk` steps): the whole per-member body below — state from HBM, the
@@ -297,6 +305,9 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
     do {   // one task; `break` leaves it
     long long step0 = step0_launch + (long long)ck * chunk;
     int n_steps = min(chunk, n_steps_launch - ck * chunk);
+    __syncwarp();
+    if (lane == 0) *task_i0 = cta_base + (long long)mw * 32;
+    __syncwarp();
     const long long i = cta_base + (long long)mw * 32 + lane;
     if (i >= E.n) break;
     int status = E.status[i];
@@ -318,7 +329,7 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
     constexpr int NTAP = StepShape<VAR, KIN, AIR, CAP>::NTAP, NANC = StepShape<VAR, KIN, AIR, CAP>::NANC;
     double* const stap = u.sc + StepShape<VAR, KIN, AIR, CAP>::NSLOT * T;   // this thread's tap columns (NTAP of them)
     double* const sanc = stap + NTAP * T;                                   // ... and its anchor columns (NANC of them)
-    double* const gtap = E.ctl ? E.ctl + (long long)FB_CTL_TAP_ROW * E.pitch + i : nullptr;
+    double* const gtap0 = E.ctl ? E.ctl + (long long)FB_CTL_TAP_ROW * E.pitch : nullptr;   // tap rows of member 0
     double xs[NX];
 #pragma unroll
     for (int c = 0; c < NX; c++) { double v = E.x[(long long)L::row(c) * E.pitch + i]; xs[c] = v; sx[c * T] = v; }
@@ -367,7 +378,7 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
         Anc anc;
         if constexpr (NANC > 0) { anc.p = sanc; anc.sx = sx; anc.ex = (st & 3) == 0; }
         if (VAR >= FB_C172X1) {
-            SplitTap<T, NTAP, (NANC > 0)> tap; tap.ps = stap; tap.pg = gtap; tap.pitch = E.pitch; tap.on = (st == 4);
+            SplitTap<T, NTAP, (NANC > 0)> tap; tap.ps = stap; tap.gbase = gtap0; tap.i0 = task_i0; tap.lane = lane; tap.pitch = E.pitch; tap.on = (st == 4);
             rhs<VAR, KIN, false, AIR>(xs, sink, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr, tap, anc);
         } else rhs<VAR, KIN, false, AIR>(xs, sink, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr, NoTap(), anc);
         if (!AIR) gnd_seen |= y.gnd;
@@ -384,6 +395,9 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
         // (It also produced the tentative k1 / first stage state of the next step.)
         done++;
         const long long step_idx = step0 + done;
+        const long long im = *task_i0 + lane;          // this member (see task_i0_s)
+        ug.u = E.u + im; u.g = ug;
+        const double* const gtap = gtap0 + im;
         // countdowns instead of 64-bit remainders: steps left to the next control update / log sample
         bool ctl_due = false, log_due = false;
         if (VAR >= FB_C172X1) { if (--ctl_in == 0) { ctl_due = true; ctl_in = periodic_every; } }
@@ -450,7 +464,7 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
             const long long smp = step_idx / E.log_every;
             for (int f = 0; f < E.log_n_fields; f++) {
                 const double v = pick_output(yf, stall_y, eng_y, cs, E.log_fields[f]);
-                if (E.log) E.log[(smp * E.log_n_fields + f) * E.pitch + i] = v;
+                if (E.log) E.log[(smp * E.log_n_fields + f) * E.pitch + im] = v;
                 if (E.mom_cnt) moments_add(E, smp * E.log_n_fields + f, v);
             }
         }
@@ -474,13 +488,16 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
         }
         sink.stage = 1;
     }
+    {
+    const long long ie = *task_i0 + lane;              // (== i; re-derived so that i does not live across the step loop)
 #pragma unroll
-    for (int c = 0; c < NX; c++) E.x[(long long)L::row(c) * E.pitch + i] = sink.sx[c * T];
-    E.stall[i] = (unsigned char)stall; E.eng[i] = (unsigned char)eng; E.status[i] = status;
-    if (E.ev_off) E.ev_cursor[i] = ev_cur - E.ev_off[i];
-    if (VAR >= FB_C172X1) cs.store(E.ctl + i, E.pitch);
-    if (AIR) { resume[i] = handover; if (handover >= 0) atomicAdd(ground_count, 1u); }
+    for (int c = 0; c < NX; c++) E.x[(long long)L::row(c) * E.pitch + ie] = sink.sx[c * T];
+    E.stall[ie] = (unsigned char)stall; E.eng[ie] = (unsigned char)eng; E.status[ie] = status;
+    if (E.ev_off) E.ev_cursor[ie] = ev_cur - E.ev_off[ie];
+    if (VAR >= FB_C172X1) cs.store(E.ctl + ie, E.pitch);
+    if (AIR) { resume[ie] = handover; if (handover >= 0) atomicAdd(ground_count, 1u); }
     else if (!resume_mode && gnd_seen) atomicAdd(ground_count, 1u);
+    }
     // RHS evaluations of this launch: k1 of the first step, then k2..k4 and f(x*) per step, plus re-evaluations
     rhs_mine += max(0, 4 * done + n_reeval + (pending ? -3 : 1) + (handover >= 0 ? (sink.stage & 3) : 0));
     } while (0);

@@ -224,10 +224,14 @@ struct NoTap { FB_DEV void operator()(int, double) const {} };
 // [TAP_COUNT][pitch] array; written only while `on`. With ANC the latitude / longitude entries are the anchor's (below).
 template <int T, int NS, bool ANC>
 struct SplitTap {
-    double* ps; double* pg; long long pitch; bool on;
+    double* ps;                      // shared: this thread's tap columns
+    double* gbase;                   // row 0 of the [TAP_COUNT][pitch] array (member 0)
+    const volatile long long* i0;    // shared: member index of lane 0 of this warp's task; the address of the member's column is
+    int lane;                        //   formed where a value is stored (a 64-bit pointer kept across the right-hand side would be spilled)
+    long long pitch; bool on;
     FB_DEV void operator()(int k, double v) const {
         if (ANC && k >= TAP_LAT) return;
-        if (on) { if (k < NS) ps[k * T] = v; else pg[(long long)k * pitch] = v; }
+        if (on) { if (k < NS) ps[k * T] = v; else gbase[(long long)k * pitch + *i0 + lane] = v; }
     }
 };
 

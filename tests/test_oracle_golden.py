@@ -188,3 +188,18 @@ def test_algorithmic_flop_count_of_record(orc):
     orc.ops_reset(lc); s.step(100); t = orc.ops_get(lc)["total"] / 100
     a_step = 4 * r + (t - 5 * r)     # 4 RHS + RK combine + f_step! (the 5th reference evaluation is redundant, App. B)
     assert abs(a_step - bench.A_STEP_FLOP) <= 0.01 * bench.A_STEP_FLOP, (r, t, a_step)
+
+
+def test_algorithmic_flop_count_on_the_ground(orc):
+    """The same count for a member standing on all three wheels with the engine running (cfg 4's roofline numerator)."""
+    import bench
+    import flightbatch as fb
+    lc = orc.lib(counting=True)
+    s = orc.Sim(0, 0, 0.01, counting=True)
+    s.init(h_e=1.9 + float(bench.geoid_height(0.0, 0.0)), engine_state=2.0, n_eng=0.3, throttle=0.2)
+    s.step(300)
+    assert [s.y(fb.OUTPUT_NAMES[k]) for k in ("wow_left", "wow_right", "wow_nose")] == [1.0, 1.0, 1.0]
+    orc.ops_reset(lc); s.rhs(); r = orc.ops_get(lc)["total"]
+    orc.ops_reset(lc); s.step(100); t = orc.ops_get(lc)["total"] / 100
+    a_step = 4 * r + (t - 5 * r)
+    assert abs(a_step - bench.A_STEP_FLOP_GROUND) <= 0.01 * bench.A_STEP_FLOP_GROUND, (r, t, a_step)

@@ -109,6 +109,13 @@ def cfg4(fb, n, seconds):
            "members": n, "rk4_steps": steps, "ms": ms, "aircraft_steps_per_s": float((st == 0).sum()) * steps / (ms * 1e-3), "status_hist": np.bincount(st, minlength=7).tolist(),
            "on_ground_at_end": float(wow.mean()), "rhs_per_member_step": (c1["rhs_evals"] - c0["rhs_evals"]) / max(1, n * steps),
            "kernel_launches": c1["kernel_launches"] - c0["kernel_launches"]}
+    # roofline of the ground path: unit-FLOP of a step on all three wheels with the engine running (op-counting oracle,
+    # tests/test_oracle_golden.py) against the FP64 FMA probe of this device
+    peak = fb.measure_fp64_peak() if hasattr(fb, "measure_fp64_peak") else None
+    if peak:
+        ach = out["aircraft_steps_per_s"] * bench.A_STEP_FLOP_GROUND * 1e-12
+        out["roofline"] = {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                           "note": "22,989 unit-FLOP per on-ground aircraft-step x aircraft-steps/s; peak = FP64 FMA probe of this run"}
     sim.close()
     return out
 
