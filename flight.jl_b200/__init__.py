@@ -69,7 +69,9 @@ class fb_config(C.Structure):
     _fields_ = [("variant", C.c_int32), ("kinematics", C.c_int32), ("n_members", C.c_int64), ("member_offset", C.c_int64),
                 ("dt", C.c_double), ("Dt", C.c_double), ("t_start", C.c_double), ("t_end", C.c_double),
                 ("device", C.c_int32), ("log_every", C.c_int32), ("log_n_fields", C.c_int32), ("log_fields", C.c_int32 * 32),
-                ("steps_per_launch", C.c_int32), ("log_flags", C.c_int32)]
+                ("steps_per_launch", C.c_int32), ("log_flags", C.c_int32),
+                ("prop_pitch_n", C.c_int32), ("reserved0", C.c_int32), ("prop_pitch_lo", C.c_double), ("prop_pitch_hi", C.c_double),
+                ("act2_omega_n", C.c_double), ("act2_zeta", C.c_double)]
 
 
 _DP = C.POINTER(C.c_double)
@@ -196,6 +198,39 @@ class Cessna172Xv1(_Aircraft):
 
 class Cessna172Xv2(_Aircraft):
     variant = DEFS["FB_C172X2"]
+
+
+class FixedPitch:
+    """Propellers.FixedPitch — lib/FlightPhysics/src/propellers.jl:337-339 (what every C172 of the reference flies)"""
+    n = 0
+    lower = upper = 0.0
+
+
+class VariablePitch:
+    """Propellers.VariablePitch(lower, upper; length = 11) — propellers.jl:341-349: the blade-pitch offset follows the
+    propeller input `prop_pitch` in [0, 1] linearly over [lower, upper] (rad)"""
+
+    def __init__(self, lower, upper, length=11):
+        self.lower, self.upper, self.n = float(lower), float(upper), int(length)
+
+
+class Actuator2:
+    """C172X.Actuator2(; ω_n = 5 * 2π, ζ = 0.6) — lib/FlightApps/src/c172/c172x/c172x.jl:68-106"""
+
+    def __init__(self, omega_n=5 * 2 * np.pi, zeta=0.6):
+        self.omega_n, self.zeta = float(omega_n), float(zeta)
+
+
+class Cessna172Xv0A2(_Aircraft):
+    """Cessna172Xv0 assembled from the non-default components the reference's Model tree admits: a
+    FlyByWireActuation of seven Actuator2 units (x.act = (v, p) per unit: nx grows by 7) and a FixedPitch or VariablePitch
+    propeller. NoAvionics."""
+    variant = DEFS["FB_C172XA2"]
+
+    def __init__(self, kinematics=None, propeller=None, actuator=None):
+        super().__init__(kinematics)
+        self.propeller = propeller if propeller is not None else FixedPitch()
+        self.actuator = actuator if actuator is not None else Actuator2()
 
 
 class SimpleWorld:
@@ -325,6 +360,10 @@ def _make_config(world, n, dt, Dt, t_start, t_end, saveat, log_fields, device, m
         cfg.log_fields[i] = f
     cfg.steps_per_launch = int(steps_per_launch)
     cfg.log_flags = (DEFS["FB_LOG_MEMBERS"] if log_members else 0) | (DEFS["FB_LOG_MOMENTS"] if log_moments else 0)
+    if isinstance(ac, Cessna172Xv0A2):
+        cfg.prop_pitch_n = ac.propeller.n
+        cfg.prop_pitch_lo, cfg.prop_pitch_hi = ac.propeller.lower, ac.propeller.upper
+        cfg.act2_omega_n, cfg.act2_zeta = ac.actuator.omega_n, ac.actuator.zeta
     return cfg, fields
 
 

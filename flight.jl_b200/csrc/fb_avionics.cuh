@@ -92,6 +92,7 @@ FB_DEV double pick_output(const YFull& y, int stall, int eng, const CtlState& cs
         case FB_Y_ENG_OMEGA: return y.eng_omega; case FB_Y_ENG_STATE: return (double)eng; case FB_Y_ENG_MAP: return y.eng_MAP;
         case FB_Y_ENG_P_SHAFT: return y.eng_P_shaft; case FB_Y_ENG_TAU_SHAFT: return y.eng_tau_shaft; case FB_Y_ENG_MDOT: return y.eng_mdot;
         case FB_Y_FUEL_M_TOTAL: return y.fuel_m_total; case FB_Y_PROP_THRUST: return y.prop_thrust; case FB_Y_PROP_J: return y.prop_J;
+        case FB_Y_PROP_DBETA: return y.prop_dbeta;
         case FB_Y_MASS: return y.mass; case FB_Y_F_X: return y.f_c_c.x; case FB_Y_F_Y: return y.f_c_c.y; case FB_Y_F_Z: return y.f_c_c.z;
         case FB_Y_LON_MODE: return (double)cs.lon_mode; case FB_Y_LAT_MODE: return (double)cs.lat_mode;
         case FB_Y_THROTTLE_CMD: return cs.thr_cmd; case FB_Y_ELEVATOR_CMD: return cs.ele_cmd;

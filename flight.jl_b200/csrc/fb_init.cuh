@@ -97,7 +97,8 @@ FB_DEV void sys_init(double* x, const MemberIn& u, int& stall, int& eng, const S
         for (int j = 0; j < 7; j++) {
             double v = clampd(c[j], (j == 0 || j >= 4) ? 0.0 : -1.0, 1.0);
             u.set(FB_U_ACT_THROTTLE + j, v);
-            x[L::ACT + j] = v;
+            if (VAR == FB_C172XA2) { x[L::ACT + 2 * j] = 0.0; x[L::ACT + 2 * j + 1] = v; }   // act.x.<unit>.p = value; an Actuator2's v keeps its zero
+            else x[L::ACT + j] = v;
         }
     }
     eng = s.engine_state; stall = s.stall;

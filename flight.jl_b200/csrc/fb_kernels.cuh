@@ -124,6 +124,7 @@ __host__ __device__ inline double saturate_input(int f, double v) {   // Ranged{
     if (f <= FB_U_RUDDER_OFFSET) return clampd(v, -1.0, 1.0);
     if (f <= FB_U_MIXTURE) return clampd(v, 0.0, 1.0);
     if (f >= FB_U_M_PILOT && f <= FB_U_M_BAGGAGE) return clampd(v, 0.0, 100.0);
+    if (f == FB_U_PROP_PITCH) return clampd(v, 0.0, 1.0);   // Ranged(0, 0, 1), propellers.jl:385
     if (f == FB_U_T_SL) return clampd(v, isa::T_std - 50.0, isa::T_std + 50.0);
     if (f == FB_U_P_SL) return clampd(v, isa::p_std - 10000.0, isa::p_std + 10000.0);
     if (f >= FB_U_ACT_THROTTLE && f <= FB_U_ACT_BRAKE_RIGHT) {
@@ -206,16 +207,16 @@ template <int VAR, int KIN, bool AIR, int CAP = FB_STEP_BLOCK>
 struct StepShape {
     static constexpr int NX = Lay<VAR, KIN, AIR>::NX;
     // shared-memory tables: the lookup pack, plus the gain schedules for the variants that run control laws
-    static constexpr int TBL = FB_TB_BYTES + (VAR >= FB_C172X1 ? FB_GS_BYTES : 0);
+    static constexpr int TBL = FB_TB_BYTES + (VAR == FB_C172X1 ? FB_GS_BYTES : 0);
     static constexpr int BUDGET = 232448 - TBL - 1024;                                         // 227 KB per CTA
-    static constexpr int NCOL = 2 * NX - Lay<VAR, KIN, AIR>::NACT;                              // state columns + accumulator columns (none for actuators)
+    static constexpr int NCOL = 2 * NX - Lay<VAR, KIN, AIR>::NACT_CF;                             // state columns + accumulator columns (none for actuators)
     static constexpr int FIT = (int)(BUDGET / (sizeof(double) * NCOL)) / 32 * 32;
     // The variants with control laws run 8 warps per CTA at up to 255 registers per thread instead of 12 at 168 (the
     // register file is split over four sub-partitions: 2 warps each get 255 registers, 3 get 168): their right-hand side
     // plus the control laws spill ~130 doubles per step at 168 registers, every spill an L2 round trip beside 229 KB of
     // shared memory, and the 8-warp shape leaves room for the whole input cache and the output tap in shared memory
     // (measured on cfg 3: 1.11e9 -> 1.17e9 aircraft-steps/s before anything else changed; C172S loses 11 % at 256).
-    static constexpr int VCAP = (VAR >= FB_C172X1 && CAP > FB_STEP_BLOCK_CTL) ? FB_STEP_BLOCK_CTL : CAP;
+    static constexpr int VCAP = (VAR == FB_C172X1 && CAP > FB_STEP_BLOCK_CTL) ? FB_STEP_BLOCK_CTL : CAP;
     static constexpr int T = FIT < VCAP ? FIT : VCAP;
     static constexpr int SPARE = (int)(BUDGET / (sizeof(double) * T)) - NCOL;                  // columns left for the input cache and the tap
     // Spare columns, in this order: the anchor of the slowly varying transcendentals (SmemAnchor: five columns, taken when
@@ -232,7 +233,7 @@ struct StepShape {
     // input slots wanted: 9 common + 6 payload moments + wind 3 + sea-level pressure; the complete layout adds the brakes
     static constexpr int NSLOT_MAX = AIR ? 19 : 21;
     static constexpr int NSLOT = (SPARE - NANC) < NSLOT_MAX ? (SPARE - NANC) : NSLOT_MAX;
-    static constexpr int TAP_WANT = (VAR >= FB_C172X1) ? (NANC ? TAP_LAT : TAP_COUNT) : 0;     // latitude / longitude are the anchor's
+    static constexpr int TAP_WANT = (VAR == FB_C172X1) ? (NANC ? TAP_LAT : TAP_COUNT) : 0;     // latitude / longitude are the anchor's
     static constexpr int NTAP = (SPARE - NANC - NSLOT) < TAP_WANT ? (SPARE - NANC - NSLOT) : TAP_WANT;
     static constexpr size_t SMEM = TBL + sizeof(double) * (NCOL + NSLOT + NTAP + NANC) * T;
 };
@@ -343,7 +344,7 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
     long long ev_cur = E.ev_off ? E.ev_off[i] + E.ev_cursor[i] : 0;
     const long long ev_end = E.ev_off ? E.ev_off[i + 1] : 0;
     CtlState cs;
-    if (VAR >= FB_C172X1) cs.load(E.ctl + i, E.pitch);
+    if (VAR == FB_C172X1) cs.load(E.ctl + i, E.pitch);
     // inputs scheduled at or before the current step index are in force from the start of this launch
     while (ev_cur < ev_end && E.ev_step[ev_cur] <= step0) {
         int f = E.ev_field[ev_cur];
@@ -352,7 +353,7 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
     }
     // launch-relative step count at which the next scheduled input fires (checked once per step with one compare)
     int next_ev = (ev_cur < ev_end) ? (int)min(E.ev_step[ev_cur] - step0, (long long)INT_MAX) : INT_MAX;
-    if (VAR >= FB_C172X1) avionics_assign(cs, ug);   // assign!(vehicle, avionics) precedes every f_ode! (aircraftbase.jl:221-230)
+    if (VAR == FB_C172X1) avionics_assign(cs, ug);   // assign!(vehicle, avionics) precedes every f_ode! (aircraftbase.jl:221-230)
     u.refresh();
 
     int done = 0, n_reeval = 0;
@@ -360,7 +361,7 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
     int ctl_in = periodic_every - (int)(step0 % periodic_every);                               // steps to the next control update
     int log_in = (E.log_every > 0 && E.log_n_fields > 0) ? E.log_every - (int)(step0 % E.log_every) : 0;   // ... log sample (0: no log)
     const double h2 = 0.5 * dt, h6 = dt * (1.0 / 6.0);
-    RkSink<T, L::ACT, L::NACT> sink; sink.xs = xs; sink.sx = sx; sink.sacc = sacc;
+    RkSink<T, L::ACT, L::NACT_CF> sink; sink.xs = xs; sink.sx = sx; sink.sacc = sacc;
     // stage factors and step factor of the closed-form actuator propagation (RkSink)
     const double az = dt * (1.0 / 0.05);
     const double ap1 = 1.0 - 0.5 * az, ap2 = 1.0 - 0.5 * az * ap1, ap3 = 1.0 - az * ap2;
@@ -377,7 +378,7 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
         typedef typename std::conditional<(NANC > 0), SmemAnchor<T, KIN, L::KINX>, NoAnchor>::type Anc;
         Anc anc;
         if constexpr (NANC > 0) { anc.p = sanc; anc.sx = sx; anc.ex = (st & 3) == 0; }
-        if (VAR >= FB_C172X1) {
+        if (VAR == FB_C172X1) {
             SplitTap<T, NTAP, (NANC > 0)> tap; tap.ps = stap; tap.gbase = gtap0; tap.i0 = task_i0; tap.lane = lane; tap.pitch = E.pitch; tap.on = (st == 4);
             rhs<VAR, KIN, false, AIR>(xs, sink, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr, tap, anc);
         } else rhs<VAR, KIN, false, AIR>(xs, sink, stall, eng, u, smem_tb, E.tables.geoid, y, nullptr, NoTap(), anc);
@@ -400,7 +401,7 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
         const double* const gtap = gtap0 + im;
         // countdowns instead of 64-bit remainders: steps left to the next control update / log sample
         bool ctl_due = false, log_due = false;
-        if (VAR >= FB_C172X1) { if (--ctl_in == 0) { ctl_due = true; ctl_in = periodic_every; } }
+        if (VAR == FB_C172X1) { if (--ctl_in == 0) { ctl_due = true; ctl_in = periodic_every; } }
         if (log_in > 0 && --log_in == 0) { log_in = E.log_every; log_due = (step_idx / E.log_every) < E.log_capacity; }
         YFull yf;
         const int stall_y = stall, eng_y = eng;
@@ -429,7 +430,7 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
             yf.eng_n = sink.sx[L::ENG * T_] * (1.0 / (2700 * FB_PI / 30));
             yf.h_e = sink.sx[(L::KINX + (KIN == FB_WA ? 8 : (KIN == FB_ECEF ? 7 : 5))) * T_];
 #pragma unroll
-            for (int a = 0; a < L::NACT; a++) {
+            for (int a = 0; a < L::NACT_CF; a++) {
                 yf.act_pos[a] = clampd(sink.sx[(L::ACT + a) * T_], (a == 0 || a >= 4) ? 0.0 : -1.0, 1.0);
                 yf.act_cmd[a] = ug(FB_U_ACT_THROTTLE + a);
             }
@@ -457,8 +458,8 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
             }
             next_ev = (ev_cur < ev_end) ? (int)min(E.ev_step[ev_cur] - step0, (long long)INT_MAX) : INT_MAX;
             changed = true;
-            if (VAR >= FB_C172X1) avionics_assign(cs, ug);   // an event cannot override a command the control laws own
-        } else if (VAR >= FB_C172X1 && changed) avionics_assign(cs, ug);
+            if (VAR == FB_C172X1) avionics_assign(cs, ug);   // an event cannot override a command the control laws own
+        } else if (VAR == FB_C172X1 && changed) avionics_assign(cs, ug);
         if (changed) u.refresh();
         if (log_due) {
             const long long smp = step_idx / E.log_every;
@@ -481,10 +482,10 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
         // Variants with control laws: the first stage state of the next step is rebuilt from the two shared-memory columns
         // (this evaluation ran as stage 0: acc = k1, xs = x + dt/2 k1) rather than carried in registers across the
         // callbacks above. (Without control laws carrying it is cheaper: measured on cfg 4.)
-        if (VAR >= FB_C172X1) {
+        if (VAR == FB_C172X1) {
 #pragma unroll
             for (int c = 0; c < NX; c++)
-                if (c < L::ACT || c >= L::ACT + L::NACT) xs[c] = fma(h2, sink.sacc[sink.acol(c) * T], sink.sx[c * T]);
+                if (c < L::ACT || c >= L::ACT + L::NACT_CF) xs[c] = fma(h2, sink.sacc[sink.acol(c) * T], sink.sx[c * T]);
         }
         sink.stage = 1;
     }
@@ -494,7 +495,7 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
     for (int c = 0; c < NX; c++) E.x[(long long)L::row(c) * E.pitch + ie] = sink.sx[c * T];
     E.stall[ie] = (unsigned char)stall; E.eng[ie] = (unsigned char)eng; E.status[ie] = status;
     if (E.ev_off) E.ev_cursor[ie] = ev_cur - E.ev_off[ie];
-    if (VAR >= FB_C172X1) cs.store(E.ctl + ie, E.pitch);
+    if (VAR == FB_C172X1) cs.store(E.ctl + ie, E.pitch);
     if (AIR) { resume[ie] = handover; if (handover >= 0) atomicAdd(ground_count, 1u); }
     else if (!resume_mode && gnd_seen) atomicAdd(ground_count, 1u);
     }
@@ -528,7 +529,7 @@ rhs_kernel(EnsembleDev E, double* xdot, double* alpha_out, int* wow_out, int* er
     double x[NX], k[NX];
 #pragma unroll
     for (int c = 0; c < NX; c++) x[c] = E.x[(long long)c * E.pitch + i];
-    if (VAR >= FB_C172X1) { CtlState cs; cs.load(E.ctl + i, E.pitch); avionics_assign(cs, u); }
+    if (VAR == FB_C172X1) { CtlState cs; cs.load(E.ctl + i, E.pitch); avionics_assign(cs, u); }
     RhsOut y;
     ArraySink sink; sink.xd = k;
     rhs<VAR, KIN, false>(x, sink, E.stall[i], E.eng[i], u, smem_tb, E.tables.geoid, y, nullptr);
@@ -555,7 +556,7 @@ output_kernel(EnsembleDev E, int field, double* out) {
 #pragma unroll
     for (int c = 0; c < NX; c++) x[c] = E.x[(long long)c * E.pitch + i];
     CtlState cs;
-    if (VAR >= FB_C172X1) { cs.load(E.ctl + i, E.pitch); avionics_assign(cs, u); }
+    if (VAR == FB_C172X1) { cs.load(E.ctl + i, E.pitch); avionics_assign(cs, u); }
     YFull yf; RhsOut y; double k[NX];
     ArraySink sink; sink.xd = k;
     rhs<VAR, KIN, true>(x, sink, E.stall[i], E.eng[i], u, smem_tb, E.tables.geoid, y, &yf);
@@ -579,7 +580,7 @@ fstep_kernel(EnsembleDev E, int* changed_out) {
     double x[NX], k[NX];
 #pragma unroll
     for (int c = 0; c < NX; c++) x[c] = E.x[(long long)c * E.pitch + i];
-    if (VAR >= FB_C172X1) { CtlState cs; cs.load(E.ctl + i, E.pitch); avionics_assign(cs, u); }
+    if (VAR == FB_C172X1) { CtlState cs; cs.load(E.ctl + i, E.pitch); avionics_assign(cs, u); }
     int stall = E.stall[i], eng = E.eng[i];
     RhsOut y;
     ArraySink sink; sink.xd = k;

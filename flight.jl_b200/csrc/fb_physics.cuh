@@ -44,7 +44,10 @@ template <int VAR, int KIN, bool AIR = false>
 struct Lay {
     static constexpr int NLDG = AIR ? 0 : 6;
     static constexpr int AERO = 0, LDG = 2, FUEL = 2 + NLDG, ENG = FUEL + 1, ACT = ENG + 3;
-    static constexpr int NACT = (VAR == FB_C172S) ? 0 : 7;
+    // actuator states: none (C172S), one per first-order unit (C172X), (v, p) per second-order unit (FB_C172XA2, c172x.jl:84)
+    static constexpr int NACT = (VAR == FB_C172S) ? 0 : (VAR == FB_C172XA2 ? 14 : 7);
+    // ... of which the integrator propagates in closed form (first-order lags only: no stage register, no accumulator column)
+    static constexpr int NACT_CF = (VAR == FB_C172X0 || VAR == FB_C172X1) ? 7 : 0;
     static constexpr int KINX = ACT + NACT;
     __host__ __device__ static constexpr int row(int c) { return (AIR && c >= 2) ? c + 6 : c; }
     static constexpr int NKIN = (KIN == FB_WA) ? 9 : (KIN == FB_ECEF ? 8 : 6);
@@ -91,6 +94,7 @@ struct YFull {
     double eng_omega, eng_n, eng_MAP, eng_P_shaft, eng_tau_shaft, eng_mdot, fuel_m_total, prop_thrust, prop_J, mass;
     d3 f_c_c;
     double act_pos[7], act_cmd[7];
+    double prop_dbeta;
 };
 
 static __device__ __noinline__ double pow_slow(double a, double b) { return pow(a, b); }
@@ -795,6 +799,21 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
         a_a = u(FB_UX_AA);
         a_f = u(FB_U_FLAPS); br_l = u(FB_U_BRAKE_LEFT); br_r = u(FB_U_BRAKE_RIGHT);
         throttle = u(FB_U_THROTTLE);
+    } else if (VAR == FB_C172XA2) {   // seven Actuator2 units, c172x.jl:91-106: x = (v, p), v' = w_n^2 (cmd - p) - 2 zeta w_n v, p' = v
+        const FbTablesTail* const tl = tables_tail(geoid);
+        const double wn2 = tl->act2_wn2, zw2 = tl->act2_2zw;
+        double pos[7];
+#pragma unroll
+        for (int i = 0; i < 7; i++) {
+            const double lo = (i == 0 || i >= 4) ? 0.0 : -1.0;
+            const double cmd = u(FB_U_ACT_THROTTLE + i);   // stored saturated (Ranged)
+            const double xv = x[L::ACT + 2 * i], xp = x[L::ACT + 2 * i + 1];
+            pos[i] = clampd(xp, lo, 1.0);
+            sink.put(L::ACT + 2 * i, fma(wn2, cmd - xp, -(zw2 * xv)));
+            sink.put(L::ACT + 2 * i + 1, xv);
+            if (WY) { yf->act_pos[i] = pos[i]; yf->act_cmd[i] = cmd; }
+        }
+        throttle = pos[0]; a_a = pos[1]; a_e = -pos[2]; a_r = -pos[3]; steer = pos[3]; a_f = pos[4]; br_l = pos[5]; br_r = pos[6];
     } else {
         double pos[7];
 #pragma unroll
@@ -964,6 +983,27 @@ FB_DEV void rhs(const double* x, Sink& sink, int stall, int eng_state, const U& 
         double cf[4];
 #pragma unroll
         for (int c = 0; c < 4; c++) cf[c] = lerp(lerp(p00[c], p00[4 + c], wm), lerp(p10[c], p10[4 + c], wm), wj);
+        if (VAR == FB_C172XA2) {   // Propeller{<:VariablePitch}: third table axis, the blade-pitch offset (propellers.jl:395-398, 253-273)
+            const FbTablesTail* const tl = tables_tail(geoid);
+            const double* const t3 = tl->prop3;
+            if (WY) yf->prop_dbeta = 0.0;
+            if (t3) {   // (uniform over the ensemble)
+                const int nb = tl->prop3_n;
+                const double db = fma(tl->prop3_hi - tl->prop3_lo, clampd(u(FB_U_PROP_PITCH), 0.0, 1.0), tl->prop3_lo);   // linear_scaling(u, range), types.jl:70-73
+                const double tb3 = clampd((db - tl->prop3_lo) * tl->prop3_is, 0.0, (double)(nb - 1));
+                const int ib = min((int)tb3, nb - 2);
+                const double wb = tb3 - (double)ib;
+                const double* q00 = t3 + (((long long)ij * 21 + im) * nb + ib) * 4;   // [iJ][iMt][iB][4]
+                const double* q10 = q00 + 21 * nb * 4;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const double f00 = lerp(q00[c], q00[4 + c], wb), f01 = lerp(q00[nb * 4 + c], q00[nb * 4 + 4 + c], wb);
+                    const double f10 = lerp(q10[c], q10[4 + c], wb), f11 = lerp(q10[nb * 4 + c], q10[nb * 4 + 4 + c], wb);
+                    cf[c] = lerp(lerp(f00, f01, wm), lerp(f10, f11, wm), wj);
+                }
+                if (WY) yf->prop_dbeta = db;
+            }
+        } else if (WY) yf->prop_dbeta = 0.0;
         double al_p, be_p;
         {
             double vxz2 = fma(v.x, v.x, v.z * v.z);

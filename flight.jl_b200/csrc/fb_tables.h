@@ -73,8 +73,24 @@ __host__ __device__ constexpr int gs_P(int s) { return gs_NV(s) | 1; }
 __host__ __device__ constexpr int gs_off(int s) { int o = 0; for (int i = 0; i < s; i++) o += 28 * gs_P(i); return o; }
 #define FB_GS_BYTES ((gs_off(GS_COUNT) * 8 + 15) / 16 * 16)
 
+// Tail of the geoid buffer: what only the non-default components (FB_C172XA2) read. It sits behind the geoid table so that
+// the right-hand side finds it from the pointer it already has (no extra parameter at any call site of the tuned kernels).
+struct FbTablesTail {
+    const double* prop3;      // [21 J][21 Mt][prop3_n][4] coefficients of the VariablePitch propeller (null: FixedPitch)
+    double prop3_lo, prop3_hi, prop3_is;   // blade-pitch offset range (rad) and 1 / knot spacing
+    int prop3_n, pad;
+    double act2_wn2, act2_2zw;            // Actuator2: w_n^2 and 2 zeta w_n (c172x.jl:100)
+};
+#define FB_GEOID_TAIL_OFF (((size_t)FB_GEOID_NLAT * FB_GEOID_NLON * 4 + 15) / 16 * 16)     // bytes
+#define FB_GEOID_BYTES (FB_GEOID_TAIL_OFF + sizeof(FbTablesTail))
+#ifdef __CUDACC__
+__device__ __forceinline__ const FbTablesTail* tables_tail(const float* geoid) {
+    return reinterpret_cast<const FbTablesTail*>(reinterpret_cast<const char*>(geoid) + FB_GEOID_TAIL_OFF);
+}
+#endif
+
 struct FbDeviceTables {
     const double* pack;   // TB_COUNT doubles, 16-byte aligned (global source of the shared pack), followed by
     const double* gains;  // the gain schedules (= pack + FB_TB_BYTES / 8)
-    const float* geoid;   // [1441 lon][721 lat]
+    const float* geoid;   // [1441 lon][721 lat], followed by an FbTablesTail at byte FB_GEOID_TAIL_OFF
 };

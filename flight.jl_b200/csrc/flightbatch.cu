@@ -11,9 +11,8 @@
 #include <numeric>
 #include <dlfcn.h>
 #include <nccl.h>
-#include "fb_init.cuh"
+#include "fb_host.cuh"
 #include "fb_lss.cuh"
-#include "fb_complete.h"
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -23,195 +22,6 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
         if (e_ != cudaSuccess) return fail(FB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
-struct fb_sim {
-    fb_config cfg;
-    int var_t = 0;   // template variant actually instantiated (X2 shares X1's kernels)
-    int nx = 0;
-    long long pitch = 0;
-    long long host_pitch = 0;        // row pitch (elements) of the caller's [C][N] host arrays; 0 = n_members (an fb_group passes global arrays)
-    EnsembleDev E{};
-    cudaStream_t stream = nullptr;
-    double* d_snap = nullptr;                          // device snapshot of x for fb_get_state_async
-    cudaEvent_t snap_ready = nullptr, snap_done = nullptr;
-    cudaStream_t snap_stream = nullptr;                // its own stream: the input copy stream must not queue behind a read-back
-    bool snap_pending = false;
-    cudaStream_t copy_stream = nullptr;                // host-to-device staging of per-member inputs (fb_set_input)
-    double* d_stage[FB_U__COUNT] = {};                 // lazily allocated staging rows
-    cudaEvent_t stage_consumed[FB_U__COUNT] = {};
-    cudaEvent_t copy_done = nullptr;
-    double* d_pack = nullptr; float* d_geoid = nullptr;
-    bool tables_loaded = false, initialised = false;
-    long long n_steps = 0;
-    long long* d_ev_off = nullptr; long long* d_ev_step = nullptr; int* d_ev_field = nullptr; double* d_ev_value = nullptr;
-    long long* d_ev_cursor = nullptr;
-    int* d_log_fields = nullptr;
-    double* d_scratch = nullptr;      // [max(nx, 8)][pitch]
-    unsigned long long* d_rhs_count = nullptr;
-    long long launches = 0;
-    int periodic_every = 1;
-    int step_block = 128;            // threads per CTA of the complete integrator kernel (one CTA per SM)
-    int step_block_air = 128;        // ... of the AIR (clear-of-terrain) instantiation
-    // hand-over between the two instantiations (fb_kernels.cuh): per-member resume record, device counter of members that
-    // were (AIR launch) or would have been (complete launch) handed over, and its pinned host copy read one launch late
-    int* d_resume = nullptr;
-    unsigned* d_ground = nullptr;
-    unsigned* h_ground = nullptr;
-    cudaEvent_t ground_ev = nullptr;
-    bool ground_ev_pending = false;
-    bool air_mode = true;
-    bool force_complete = false;
-    bool air_wide = false;           // airborne kernel shape: FB_STEP_BLOCK_WIDE threads (one-wave ensembles) or FB_STEP_BLOCK
-    int air_mpc = 0;                 // > step_block_air: time-sliced airborne launches, this many members per CTA (fb_kernels.cuh)
-    bool air_dyn = false;            // airborne launches draw (member-warp, chunk) tasks from a global queue: one persistent CTA per SM
-    int air_grid = 0;                // ... this many CTAs
-    unsigned* d_queue = nullptr;     // [0]: next task, [1 .. 1 + member-warps): chunks published per member-warp
-    // ensemble moments of the log samples (EnsembleDev::mom_*): one device allocation, a pinned staging copy for the
-    // asynchronous fetch, and the side stream + communicator of the all-reduce over the shards
-    void* d_mom = nullptr;
-    long long mom_records = 0;                         // [log_capacity][log_n_fields] + 1 scratch record (fb_stats)
-    unsigned long long* m_cnt = nullptr; double* m_sum = nullptr; double* m_min = nullptr; double* m_max = nullptr;
-    char* h_mom = nullptr; size_t h_mom_bytes = 0;
-    long long mom_first = 0, mom_count = 0;            // sample range of the fetch in flight
-    bool mom_pending = false;
-    cudaEvent_t mom_ready = nullptr, mom_done = nullptr;
-    ncclComm_t comm = nullptr;
-    bool comm_owned = false;                           // false: the communicator belongs to an fb_group
-    int comm_ranks = 1;
-    cudaStream_t comm_stream = nullptr;
-    cudaEvent_t comm_in = nullptr, comm_out = nullptr; // launch stream -> side stream, side stream -> readers
-    bool comm_busy = false;
-    long long reduced_upto = 0;                        // log samples [0, reduced_upto) have been all-reduced
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> comm_timers;
-    double comm_ms = 0.0; long long comm_calls = 0;
-};
-
-// ------------------------------------------------------------------------------------ kernel dispatch
-template <int VAR, int KIN> struct Ops {
-    // One advance of n steps: the AIR instantiation for everybody followed by the complete kernel for the members it
-    // handed over (it returns at once when there are none), or — while a large share of the ensemble is near the
-    // terrain — the complete kernel alone. Returns the number of kernels launched through *launched.
-    static cudaError_t step(fb_sim* s, long long step0, int n, int* launched) {
-        cudaError_t e = cudaMemsetAsync(s->d_ground, 0, sizeof(unsigned), s->stream);
-        if (e != cudaSuccess) return e;
-        int T = s->step_block;
-        int grid = (int)((s->E.n + T - 1) / T);
-        if (s->air_mode) {
-            int Ta = s->step_block_air;
-            // time-sliced shape (fb_kernels.cuh): mpc members per CTA on Ta threads, in chunks of air_chunk steps — only
-            // when the launch is long enough to be cut up; otherwise (and always for the plain shapes) one thread per member
-            int mpc = s->air_mpc > Ta ? s->air_mpc : Ta, chunk = n > 0 ? n : 1;
-            if (s->air_mpc > Ta && n >= 8) {
-                // cut the launch into C chunks so that the MW * C tasks fill whole rounds of the HW warps; a chunk start
-                // costs one extra right-hand side (no k1 carried over), i.e. a quarter of a step
-                const int MW = s->air_mpc / 32, HW = Ta / 32;
-                double best = 1e300;
-                for (int C = 2; C <= 16 && C * 4 <= n; C++) {
-                    const int ch = (n + C - 1) / C, Cr = (n + ch - 1) / ch;
-                    const double cost = (double)((MW * Cr + HW - 1) / HW) * (ch + 0.25);
-                    if (cost < best) { best = cost; chunk = ch; }
-                }
-            }
-            int grid_a = (int)((s->E.n + mpc - 1) / mpc);
-            if (s->air_dyn) {
-                // dynamic distribution: cut the launch into C chunks so that the MWT * C tasks keep all HWT hardware warps
-                // of the GPU busy to the end (cost in step units: rounds x (chunk + the k1 a chunk start re-evaluates +
-                // the state round trip of a task))
-                const long long MWT = (s->E.n + 31) / 32, HWT = (long long)s->air_grid * (Ta / 32);
-                double best = 1e300;
-                chunk = n > 0 ? n : 1;
-                for (int C = 1; C <= 16 && (C == 1 || C * 4 <= n); C++) {
-                    const int ch = (n + C - 1) / C, Cr = (n + ch - 1) / ch;
-                    const double cost = (double)((MWT * Cr + HWT - 1) / HWT) * (ch + (Cr > 1 ? 0.25 : 0.0) + 0.3);
-                    if (cost < best) { best = cost; chunk = ch; }
-                }
-                e = cudaMemsetAsync(s->d_queue, 0, sizeof(unsigned) * (size_t)(1 + MWT), s->stream);
-                if (e != cudaSuccess) return e;
-                step_kernel<VAR, KIN, true><<<s->air_grid, Ta, StepShape<VAR, KIN, true>::SMEM, s->stream>>>(
-                    s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_resume, 0, s->d_ground, Ta, chunk,
-                    s->d_queue, reinterpret_cast<int*>(s->d_queue + 1));
-            } else if (s->air_wide)
-                step_kernel<VAR, KIN, true, FB_STEP_BLOCK_WIDE><<<grid_a, Ta, StepShape<VAR, KIN, true, FB_STEP_BLOCK_WIDE>::SMEM, s->stream>>>(
-                    s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_resume, 0, s->d_ground, mpc, chunk);
-            else
-                step_kernel<VAR, KIN, true><<<grid_a, Ta, StepShape<VAR, KIN, true>::SMEM, s->stream>>>(
-                    s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_resume, 0, s->d_ground, mpc, chunk);
-            { CompleteLaunch a{grid, T, s->stream, s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_resume, 1, s->d_ground};
-              e = fb_complete_launch(VAR, s->cfg.kinematics, a); if (e != cudaSuccess) return e; }
-            *launched = 2;
-        } else {
-            CompleteLaunch a{grid, T, s->stream, s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, nullptr, 0, s->d_ground};
-            e = fb_complete_launch(VAR, s->cfg.kinematics, a); if (e != cudaSuccess) return e;
-            *launched = 1;
-        }
-        return cudaGetLastError();
-    }
-    // shape 0: complete kernel, 1: airborne, 2: airborne wide
-    static int step_tmax(int shape) {
-        return shape == 0 ? fb_complete_tmax(VAR, KIN) : (shape == 1 ? StepShape<VAR, KIN, true>::T : StepShape<VAR, KIN, true, FB_STEP_BLOCK_WIDE>::T);
-    }
-    static cudaError_t prepare(fb_sim* s) {
-        cudaError_t e = fb_complete_prepare(VAR, KIN);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(step_kernel<VAR, KIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StepShape<VAR, KIN, true>::SMEM);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(step_kernel<VAR, KIN, true, FB_STEP_BLOCK_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)StepShape<VAR, KIN, true, FB_STEP_BLOCK_WIDE>::SMEM);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(rhs_kernel<VAR, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(output_kernel<VAR, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(avionics_init_kernel<VAR, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(fstep_kernel<VAR, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(fperiodic_kernel<VAR, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(linearize_kernel<VAR, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES);
-        if (e != cudaSuccess) return e;
-        return cudaFuncSetAttribute(trim_kernel<VAR, KIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TB_BYTES);
-    }
-    static cudaError_t rhs(fb_sim* s, double* xdot) {
-        int grid = (int)((s->E.n + FB_BLOCK - 1) / FB_BLOCK);
-        rhs_kernel<VAR, KIN><<<grid, FB_BLOCK, FB_TB_BYTES, s->stream>>>(s->E, xdot, nullptr, nullptr, nullptr);
-        return cudaGetLastError();
-    }
-    static cudaError_t output(fb_sim* s, int field, double* out) {
-        int grid = (int)((s->E.n + FB_BLOCK - 1) / FB_BLOCK);
-        output_kernel<VAR, KIN><<<grid, FB_BLOCK, FB_TB_BYTES, s->stream>>>(s->E, field, out);
-        return cudaGetLastError();
-    }
-    static cudaError_t fstep(fb_sim* s, int* changed) {
-        int grid = (int)((s->E.n + FB_BLOCK - 1) / FB_BLOCK);
-        fstep_kernel<VAR, KIN><<<grid, FB_BLOCK, FB_TB_BYTES, s->stream>>>(s->E, changed);
-        return cudaGetLastError();
-    }
-    static cudaError_t fperiodic(fb_sim* s) {
-        int grid = (int)((s->E.n + FB_BLOCK - 1) / FB_BLOCK);
-        fperiodic_kernel<VAR, KIN><<<grid, FB_BLOCK, FB_TB_BYTES, s->stream>>>(s->E, s->cfg.Dt);
-        return cudaGetLastError();
-    }
-    static cudaError_t init(fb_sim* s, const InitSoA& I) {
-        int grid = (int)((s->E.n + FB_BLOCK - 1) / FB_BLOCK);
-        init_kernel<VAR, KIN><<<grid, FB_BLOCK, 0, s->stream>>>(s->E, I);
-        return cudaGetLastError();
-    }
-    static cudaError_t linearize(fb_sim* s, double* A, double* B, double* C, double* D, double* x0, double* u0, double* y0, double* xd0) {
-        int grid = (int)((s->E.n + FB_BLOCK - 1) / FB_BLOCK);
-        linearize_kernel<VAR, KIN><<<grid, FB_BLOCK, FB_TB_BYTES, s->stream>>>(s->E, A, B, C, D, x0, u0, y0, xd0);
-        return cudaGetLastError();
-    }
-    static cudaError_t avionics_init(fb_sim* s) {
-        int grid = (int)((s->E.n + FB_BLOCK - 1) / FB_BLOCK);
-        avionics_init_kernel<VAR, KIN><<<grid, FB_BLOCK, FB_TB_BYTES, s->stream>>>(s->E, s->cfg.Dt);
-        return cudaGetLastError();
-    }
-    static cudaError_t trim(fb_sim* s, const TrimSoA& P, double* ts, double* cost) {
-        int grid = (int)((s->E.n + FB_BLOCK - 1) / FB_BLOCK);
-        trim_kernel<VAR, KIN><<<grid, FB_BLOCK, FB_TB_BYTES, s->stream>>>(s->E, P, ts, cost);
-        return cudaGetLastError();
-    }
-};
 #if defined(FB_ONLY_S_WA)   // development builds: one instantiation only (fast compile)
 #define FB_DISPATCH(s, CALL) (Ops<FB_C172S, FB_WA>::CALL)
 #elif defined(FB_ONLY_X1_WA)
@@ -220,12 +30,13 @@ template <int VAR, int KIN> struct Ops {
 #define FB_KIN_DISPATCH(s, V, CALL) \
     ((s)->cfg.kinematics == FB_WA ? Ops<V, FB_WA>::CALL : ((s)->cfg.kinematics == FB_NED ? Ops<V, FB_NED>::CALL : Ops<V, FB_ECEF>::CALL))
 #define FB_DISPATCH(s, CALL) \
-    ((s)->var_t == FB_C172S ? FB_KIN_DISPATCH(s, FB_C172S, CALL) : ((s)->var_t == FB_C172X0 ? FB_KIN_DISPATCH(s, FB_C172X0, CALL) : FB_KIN_DISPATCH(s, FB_C172X1, CALL)))
+    ((s)->var_t == FB_C172S ? FB_KIN_DISPATCH(s, FB_C172S, CALL) : ((s)->var_t == FB_C172X0 ? FB_KIN_DISPATCH(s, FB_C172X0, CALL) : \
+     ((s)->var_t == FB_C172XA2 ? fb_ext_ops((s)->cfg.kinematics)->CALL : FB_KIN_DISPATCH(s, FB_C172X1, CALL))))
 #endif
 
 static size_t hp(const fb_sim* s) { return sizeof(double) * (size_t)(s->host_pitch > 0 ? s->host_pitch : s->E.n); }
 static int layout_nx(int variant, int kin) {
-    int nact = (variant == FB_C172S) ? 0 : 7;
+    int nact = (variant == FB_C172S) ? 0 : (variant == FB_C172XA2 ? 14 : 7);
     int nkin = (kin == FB_WA) ? 9 : (kin == FB_ECEF ? 8 : 6);
     return 12 + nact + nkin + 6;
 }
@@ -341,7 +152,12 @@ static int32_t create_body(fb_sim* s);
 int32_t fb_create(const fb_config* cfg, fb_handle* out) {
     if (!cfg || !out) return fail(FB_ERR_ARG, "fb_create: null argument");
     *out = nullptr;
-    if (cfg->variant < FB_C172S || cfg->variant > FB_C172X2) return fail(FB_ERR_ARG, "fb_create: unknown variant");
+    if (cfg->variant < FB_C172S || cfg->variant > FB_C172XA2) return fail(FB_ERR_ARG, "fb_create: unknown variant");
+    if (cfg->variant == FB_C172XA2) {
+        if (cfg->prop_pitch_n > 64 || cfg->prop_pitch_n < 0) return fail(FB_ERR_ARG, "fb_create: prop_pitch_n out of range");
+        if (cfg->prop_pitch_n > 1 && !(cfg->prop_pitch_hi > cfg->prop_pitch_lo)) return fail(FB_ERR_ARG, "fb_create: VariablePitch needs prop_pitch_hi > prop_pitch_lo");
+        if (cfg->act2_omega_n < 0.0 || cfg->act2_zeta < 0.0) return fail(FB_ERR_ARG, "fb_create: negative Actuator2 parameter");
+    }
     if (cfg->kinematics != FB_WA && cfg->kinematics != FB_NED && cfg->kinematics != FB_ECEF) return fail(FB_ERR_ARG, "fb_create: kinematics must be FB_WA, FB_ECEF or FB_NED");
     if (cfg->n_members <= 0) return fail(FB_ERR_ARG, "fb_create: n_members must be positive");
     if (cfg->member_offset < 0) return fail(FB_ERR_ARG, "fb_create: member_offset must not be negative");
@@ -372,7 +188,7 @@ int32_t fb_create(const fb_config* cfg, fb_handle* out) {
 
 static int32_t create_body(fb_sim* s) {
     const fb_config* cfg = &s->cfg;
-    s->var_t = cfg->variant >= FB_C172X1 ? FB_C172X1 : cfg->variant;
+    s->var_t = (cfg->variant == FB_C172X1 || cfg->variant == FB_C172X2) ? FB_C172X1 : cfg->variant;
     s->nx = layout_nx(cfg->variant, cfg->kinematics);
     long long N = cfg->n_members;
     s->pitch = (N + 31) / 32 * 32;
@@ -478,7 +294,7 @@ static int32_t create_body(fb_sim* s) {
         CK(cudaGetDeviceProperties(&prop, cfg->device));
         const int tmax = FB_DISPATCH(s, step_tmax)(1), hw = tmax / 32;
         const long long mwt = (N + 31) / 32;
-        bool use = cfg->variant >= FB_C172X1 && mwt < 8ll * prop.multiProcessorCount * hw;
+        bool use = s->var_t == FB_C172X1 && mwt < 8ll * prop.multiProcessorCount * hw;
         if (const char* dynv = getenv("FLIGHTBATCH_DYNAMIC")) use = atoi(dynv) != 0;
         if (getenv("FLIGHTBATCH_SLICED")) use = false;
         if (use) {
@@ -490,6 +306,7 @@ static int32_t create_body(fb_sim* s) {
     // FLIGHTBATCH_KERNEL=complete pins the complete kernel (no airborne instantiation, no hand-over): a diagnostic switch used
     // by the tests to check that the two launch paths produce the same trajectories
     if (const char* k = getenv("FLIGHTBATCH_KERNEL")) s->force_complete = (strcmp(k, "complete") == 0);
+    if (cfg->variant == FB_C172XA2) s->force_complete = true;   // the non-default components exist in the complete kernel only
     if (s->force_complete) s->air_mode = false;
     CK(cudaMalloc(&s->d_resume, sizeof(int) * s->pitch));
     CK(cudaMalloc(&s->d_ground, sizeof(unsigned)));
@@ -510,7 +327,7 @@ int32_t fb_destroy(fb_handle s) {
     cudaFree(s->d_snap); if (s->snap_ready) cudaEventDestroy(s->snap_ready); if (s->snap_done) cudaEventDestroy(s->snap_done);
     EnsembleDev& E = s->E;
     cudaFree(E.x); cudaFree(E.u); cudaFree(E.stall); cudaFree(E.eng); cudaFree(E.status); cudaFree(E.ctl); cudaFree(E.log);
-    cudaFree(s->d_pack); cudaFree(s->d_geoid);
+    cudaFree(s->d_pack); cudaFree(s->d_geoid); cudaFree(s->d_prop3);
     cudaFree(s->d_ev_off); cudaFree(s->d_ev_step); cudaFree(s->d_ev_field); cudaFree(s->d_ev_value); cudaFree(s->d_ev_cursor);
     cudaFree(s->d_log_fields); cudaFree(s->d_scratch); cudaFree(s->d_rhs_count);
     cudaFree(s->d_resume); cudaFree(s->d_ground); cudaFree(s->d_queue); if (s->h_ground) cudaFreeHost(s->h_ground); if (s->ground_ev) cudaEventDestroy(s->ground_ev);
@@ -608,9 +425,35 @@ int32_t fb_load_tables(fb_handle s, const void* blob, size_t nbytes) {
     const BlobSec* g = find("geoid");
     if (!g || g->dtype != 1 || g->nbytes != (uint64_t)FB_GEOID_NLAT * FB_GEOID_NLON * 4) return fail(FB_ERR_ARG, "fb_load_tables: bad or missing geoid section");
     if (!s->d_pack) CK(cudaMalloc(&s->d_pack, FB_TB_BYTES + FB_GS_BYTES));
-    if (!s->d_geoid) CK(cudaMalloc(&s->d_geoid, g->nbytes));
+    if (!s->d_geoid) CK(cudaMalloc(&s->d_geoid, FB_GEOID_BYTES));
     CK(cudaMemcpyAsync(s->d_pack, pack.data(), FB_TB_BYTES, cudaMemcpyHostToDevice, s->stream));
     CK(cudaMemcpyAsync(s->d_geoid, b + g->off, g->nbytes, cudaMemcpyHostToDevice, s->stream));
+    // tail of the geoid buffer: parameters and tables of the non-default components (FB_C172XA2; zero otherwise)
+    FbTablesTail tail; memset(&tail, 0, sizeof(tail));
+    std::vector<double> p3;   // staging must outlive the asynchronous copy
+    if (s->cfg.variant == FB_C172XA2) {
+        const double wn = s->cfg.act2_omega_n > 0.0 ? s->cfg.act2_omega_n : 5.0 * 2.0 * FB_PI, zt = s->cfg.act2_zeta > 0.0 ? s->cfg.act2_zeta : 0.6;   // c172x.jl:71
+        tail.act2_wn2 = wn * wn; tail.act2_2zw = 2.0 * zt * wn;
+        if (s->cfg.prop_pitch_n > 1) {
+            // Lookup of Propeller(VariablePitch(lo, hi; length = n)): "prop.tables3" [21][21][n][6] with its range in "prop.pitch3",
+            // written by tools/build_tables.py for exactly this VariablePitch (the reference builds the Lookup when the
+            // Propeller is constructed, propellers.jl:356-359)
+            const BlobSec* t3 = find("prop.tables3"); const BlobSec* r3 = find("prop.pitch3");
+            const int nb = s->cfg.prop_pitch_n;
+            if (!t3 || !r3 || t3->dtype != 0 || r3->nbytes != 16 || t3->nbytes != 441ull * nb * 6 * 8)
+                return fail(FB_ERR_ARG, "fb_load_tables: the table blob holds no prop.tables3 / prop.pitch3 section for this prop_pitch_n");
+            double rng[2]; memcpy(rng, b + r3->off, 16);
+            if (rng[0] != s->cfg.prop_pitch_lo || rng[1] != s->cfg.prop_pitch_hi)
+                return fail(FB_ERR_ARG, "fb_load_tables: prop.pitch3 of the table blob differs from (prop_pitch_lo, prop_pitch_hi); rebuild the blob for this VariablePitch");
+            const double* src = reinterpret_cast<const double*>(b + t3->off);
+            p3.resize(441ull * nb * 4);
+            for (size_t o = 0; o < 441ull * nb; o++) for (int c = 0; c < 4; c++) p3[o * 4 + c] = src[o * 6 + c];   // C_Fx, C_Mx, C_Fz_a, C_Mz_a (C_P, eta_p are not on the path)
+            if (!s->d_prop3) CK(cudaMalloc(&s->d_prop3, p3.size() * 8));
+            CK(cudaMemcpyAsync(s->d_prop3, p3.data(), p3.size() * 8, cudaMemcpyHostToDevice, s->stream));
+            tail.prop3 = s->d_prop3; tail.prop3_lo = rng[0]; tail.prop3_hi = rng[1]; tail.prop3_n = nb; tail.prop3_is = (nb - 1) / (rng[1] - rng[0]);
+        }
+    }
+    CK(cudaMemcpyAsync((char*)s->d_geoid + FB_GEOID_TAIL_OFF, &tail, sizeof(tail), cudaMemcpyHostToDevice, s->stream));
     static const char* gnames[GS_COUNT] = {"gain.te2te", "gain.tv2te", "gain.vh2te", "gain.ar2ar", "gain.phibeta2ar",
                                            "gain.q2e", "gain.c2theta", "gain.v2t", "gain.p2phi", "gain.chi2phi"};
     std::vector<double> gpack(FB_GS_BYTES / 8, 0.0);   // staging must outlive the asynchronous copy
@@ -649,7 +492,7 @@ static EnsembleDev mom_view(const fb_sim* s) {
 }
 static int32_t after_init(fb_sim* s, bool init_avionics) {
     s->n_steps = 0; s->initialised = true;
-    if (init_avionics && s->var_t >= FB_C172X1) CK(FB_DISPATCH(s, avionics_init)(s));   // f_init!(avionics, vehicle)
+    if (init_avionics && s->var_t == FB_C172X1) CK(FB_DISPATCH(s, avionics_init)(s));   // f_init!(avionics, vehicle)
     CK(cudaMemsetAsync(s->d_ev_cursor, 0, sizeof(long long) * s->pitch, s->stream));
     // A member that stops stepping (crash, altitude bounds, failed trim) writes no further samples: every sample starts
     // out as NaN, so that what a frozen member never wrote reads as missing rather than as stale memory; the moments
@@ -1175,6 +1018,7 @@ int32_t fb_counters(fb_handle s, int64_t* kernel_launches, int64_t* rhs_evals) {
 
 int32_t fb_linearize_dims(fb_handle s, int32_t* dims) {
     if (!s || !dims) return fail(FB_ERR_ARG, "fb_linearize_dims: null argument");
+    if (s->cfg.variant == FB_C172XA2) return fail(FB_ERR_ARG, "fb_linearize: not offered for FB_C172XA2 (the reference's XStateSpace knows first-order actuators only, c172x.jl:332-498)");
     dims[0] = s->cfg.variant == FB_C172S ? 16 : 20; dims[1] = 4; dims[2] = s->cfg.variant == FB_C172S ? 33 : 38;
     return FB_OK;
 }
@@ -1184,7 +1028,7 @@ int32_t fb_linearize(fb_handle s, double* A, double* B, double* C, double* D, do
     if (!s->initialised) return fail(FB_ERR_STATE, "fb_linearize: not initialised (trim first)");
     if (s->cfg.kinematics != FB_NED) return fail(FB_ERR_ARG, "fb_linearize: needs NED kinematics (the reference defines XStateSpace for Vehicle{NED} only)");
     CK(cudaSetDevice(s->cfg.device));
-    int32_t d[3]; fb_linearize_dims(s, d);
+    int32_t d[3]; if (int32_t rc = fb_linearize_dims(s, d)) return rc;
     const long long nxs = d[0], nus = d[1], nys = d[2], P = s->pitch, N = s->E.n;
     const long long counts[8] = {nxs * nxs, nxs * nus, nys * nxs, nys * nus, nxs, nus, nys, nxs};
     double* host[8] = {A, B, C, D, x0, u0, y0, xdot0};
@@ -1274,7 +1118,7 @@ int32_t fb_lss_from_linearize(fb_lss_handle l, fb_handle s) {
     if (!l || !s) return fail(FB_ERR_ARG, "fb_lss_from_linearize: null argument");
     if (!s->initialised) return fail(FB_ERR_STATE, "fb_lss_from_linearize: the simulation is not initialised (trim first)");
     if (s->cfg.kinematics != FB_NED) return fail(FB_ERR_ARG, "fb_lss_from_linearize: needs NED kinematics");
-    int32_t d[3]; fb_linearize_dims(s, d);
+    int32_t d[3]; if (int32_t rc = fb_linearize_dims(s, d)) return rc;
     if (d[0] != l->nx || d[1] != l->nu || d[2] != l->ny || s->E.n != l->n || s->cfg.device != l->device)
         return fail(FB_ERR_ARG, "fb_lss_from_linearize: sizes / device of the two handles differ");
     CK(cudaSetDevice(l->device));

@@ -29,9 +29,9 @@ last_error() = unsafe_string(ccall((:fb_last_error, libflightbatch), Cstring, ()
 check(rc::Int32) = rc == 0 ? nothing : throw(FlightBatchError(rc, last_error()))
 
 # enums of include/flightbatch.h (kept in the same order; FB_API_VERSION is checked at load)
-@enum Variant::Int32 C172S = 0 C172X0 = 1 C172X1 = 2 C172X2 = 3
+@enum Variant::Int32 C172S = 0 C172X0 = 1 C172X1 = 2 C172X2 = 3 C172XA2 = 4   # C172XA2: Cessna172Xv0 with Actuator2 actuation and an optional VariablePitch propeller
 @enum KinematicsKind::Int32 WA = 0 ECEF = 1 NED = 2
-const FB_API_VERSION = 4
+const FB_API_VERSION = 5
 
 # struct fb_config (must match the C layout field by field)
 struct FbConfig
@@ -49,6 +49,12 @@ struct FbConfig
     log_fields::NTuple{32,Int32}
     steps_per_launch::Int32
     log_flags::Int32          # FB_LOG_MEMBERS (1) | FB_LOG_MOMENTS (2); 0 = both
+    prop_pitch_n::Int32       # C172XA2 only: > 1 = Propeller(VariablePitch(lo, hi; length = n)), 0 / 1 = FixedPitch
+    reserved0::Int32
+    prop_pitch_lo::Float64
+    prop_pitch_hi::Float64
+    act2_omega_n::Float64     # C172XA2 only: Actuator2 parameters (0 = the reference defaults 5 * 2π, 0.6)
+    act2_zeta::Float64
 end
 
 mutable struct BatchSimulation
@@ -60,12 +66,15 @@ mutable struct BatchSimulation
     log_fields::Vector{Int32}
     function BatchSimulation(variant::Variant, kin::KinematicsKind, n::Integer;
                              dt = 0.02, Δt = dt, t_start = 0.0, t_end = 10000.0, saveat = nothing,
-                             log_fields = Int32[], device = 0, member_offset = 0, steps_per_launch = 0, log_flags = 0)
+                             log_fields = Int32[], device = 0, member_offset = 0, steps_per_launch = 0, log_flags = 0,
+                             prop_pitch = nothing, act2 = (0.0, 0.0))   # prop_pitch = (lower, upper, length) for a VariablePitch propeller
         @assert ccall((:fb_api_version, libflightbatch), Int32, ()) == FB_API_VERSION
         lf = ntuple(i -> i <= length(log_fields) ? Int32(log_fields[i]) : Int32(0), 32)
         log_every = (saveat === nothing || isempty(log_fields)) ? 0 : max(1, round(Int, saveat / dt))
         cfg = Ref(FbConfig(Int32(variant), Int32(kin), n, member_offset, dt, Δt, t_start, t_end, device, log_every,
-                           length(log_fields), lf, steps_per_launch, log_flags))
+                           length(log_fields), lf, steps_per_launch, log_flags,
+                           prop_pitch === nothing ? 0 : prop_pitch[3], 0, prop_pitch === nothing ? 0.0 : prop_pitch[1],
+                           prop_pitch === nothing ? 0.0 : prop_pitch[2], act2[1], act2[2]))
         h = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:fb_create, libflightbatch), Int32, (Ref{FbConfig}, Ref{Ptr{Cvoid}}), cfg, h))
         blob = read(tables_path)

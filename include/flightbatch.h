@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FB_API_VERSION 4
+#define FB_API_VERSION 5
 
 /* error codes */
 #define FB_OK 0
@@ -39,6 +39,11 @@ extern "C" {
 #define FB_C172X0 1  /* Cessna172Xv0: fly-by-wire actuators, NoAvionics         */
 #define FB_C172X1 2  /* Cessna172Xv1: + C172XControl.ControlLaws                */
 #define FB_C172X2 3  /* Cessna172Xv2: + C172XGuidance.GuidanceLaws (direct and segment modes) */
+/* Cessna172Xv0 assembled from the non-default components the Model tree admits: a fly-by-wire
+ * actuation of seven Actuator2 units (second-order lag, X = (v, p) per unit, c172x.jl:68-106: nx grows by 7) and,
+ * when fb_config.prop_pitch_n > 1, a Propeller(VariablePitch(prop_pitch_lo, prop_pitch_hi; length = prop_pitch_n))
+ * (propellers.jl:341-400) driven by the input FB_U_PROP_PITCH. NoAvionics; fb_linearize is not offered for it. */
+#define FB_C172XA2 4
 /* kinematic mechanisation: lib/FlightPhysics/src/kinematics.jl:150,250,329 */
 #define FB_WA 0
 #define FB_ECEF 1
@@ -77,6 +82,8 @@ enum fb_input {
     /* C172X FlyByWireActuation commands, c172x.jl:112-120 (written by the control laws for X1/X2) */
     FB_U_ACT_THROTTLE = 27, FB_U_ACT_AILERON, FB_U_ACT_ELEVATOR, FB_U_ACT_RUDDER, FB_U_ACT_FLAPS,
     FB_U_ACT_BRAKE_LEFT, FB_U_ACT_BRAKE_RIGHT,
+    /* Propeller{<:VariablePitch}.u: Ranged(0, 0, 1) blade-pitch command, propellers.jl:385,395-398 (FB_C172XA2 only) */
+    FB_U_PROP_PITCH = 34,
     /* C172XControl.ControlLawsLon.u, c172x_ctl.jl:226-237 */
     FB_U_LON_MODE_REQ = 40, FB_U_LON_THROTTLE_AXIS, FB_U_LON_THROTTLE_OFFSET, FB_U_LON_ELEVATOR_AXIS, FB_U_LON_ELEVATOR_OFFSET,
     FB_U_LON_Q_REF, FB_U_LON_THETA_REF, FB_U_LON_EAS_REF, FB_U_LON_CLM_REF, FB_U_LON_H_REF,
@@ -117,6 +124,7 @@ enum fb_output {
      * update (c172x_gdc.jl:101-111,215-223,285-289) */
     FB_Y_GDC_MODE, FB_Y_GDC_HOR, FB_Y_GDC_VRT, FB_Y_GDC_DCHI, FB_Y_GDC_CHI_REF, FB_Y_GDC_H_REF,
     FB_Y_GDC_CHI_12, FB_Y_GDC_GAMMA_12, FB_Y_GDC_S_12, FB_Y_GDC_S_1B, FB_Y_GDC_E_SB, FB_Y_GDC_V_SB,
+    FB_Y_PROP_DBETA,                               /* systems.pwp.propeller.Δβ (propellers.jl:372; 0 for FixedPitch) */
     FB_Y__COUNT
 };
 
@@ -137,6 +145,12 @@ typedef struct fb_config {
     int32_t log_fields[32]; /* fb_output ids to log                                 */
     int32_t steps_per_launch; /* K: RK4 steps fused per kernel launch (0 = default) */
     int32_t log_flags;      /* FB_LOG_* bits; 0 = FB_LOG_MEMBERS | FB_LOG_MOMENTS                       */
+    /* FB_C172XA2 only (ignored otherwise; all zero = the reference's defaults) */
+    int32_t prop_pitch_n;   /* > 1: VariablePitch with this many blade-pitch knots (reference default 11, propellers.jl:351); 0 / 1: FixedPitch */
+    int32_t reserved0;
+    double prop_pitch_lo, prop_pitch_hi; /* rad: VariablePitch(lower, upper); must match the "prop.tables3" section of the table blob */
+    double act2_omega_n;    /* Actuator2 natural frequency, rad/s (0 = 5 * 2 pi, c172x.jl:71) */
+    double act2_zeta;       /* Actuator2 damping ratio (0 = 0.6)                              */
 } fb_config;
 /* what a log sample keeps: every member's value (TimeSeries(sim), sim.jl:644-704) and / or the ensemble moments of the
  * logged fields, reduced inside the integrator as the sample is taken (no reference counterpart: one Simulation = one aircraft) */

@@ -52,6 +52,8 @@ def _load(name):
         "orc_world_prop_table": (None, [vp, dp]),
         "orc_world_engine_tables": (None, [vp, dp, dp, dp]),
         "orc_sim_create": (vp, [vp, i32, i32, dbl, dbl]),
+        "orc_sim_set_components": (None, [vp, dbl, dbl, i32, dbl, dbl]),
+        "orc_sim_prop3": (i32, [vp, dp]),
         "orc_sim_destroy": (None, [vp]),
         "orc_sim_nx": (i32, [vp]),
         "orc_sim_status": (i32, [vp]),
@@ -166,14 +168,29 @@ def world(counting=False, fast=False):
 class Sim:
     """One reference `Simulation(SimpleWorld(Cessna172...); dt, Δt)` on the CPU oracle."""
 
-    def __init__(self, variant=0, kin=0, dt=0.02, Dt=None, counting=False, fast=False):
+    def __init__(self, variant=0, kin=0, dt=0.02, Dt=None, counting=False, fast=False, prop_pitch=None, act2=None):
         """fast=True: the -O3 -march=native timing build (bench.py's CPU arm); fast="fma": the portable FMA-contracted build
-        (rounding-spread tests); the checker is the default build."""
+        (rounding-spread tests); the checker is the default build. variant 4 (Actuator2 actuation): prop_pitch = (lo, hi[, n])
+        makes the propeller a Propeller(VariablePitch(lo, hi; length = n)), act2 = (omega_n, zeta) overrides the actuator
+        defaults."""
         self.w = world(counting, fast)
         self.lib = self.w.lib
         self.h = self.lib.orc_sim_create(self.w.h, variant, kin, dt, dt if Dt is None else Dt)
         self.nx = self.lib.orc_sim_nx(self.h)
         self.dt = dt
+        if prop_pitch is not None or act2 is not None:
+            lo, hi, n = (tuple(prop_pitch) + (11,))[:3] if prop_pitch is not None else (0.0, 0.0, 0)
+            wn, zt = act2 if act2 is not None else (0.0, 0.0)
+            self.lib.orc_sim_set_components(self.h, float(wn), float(zt), int(n), float(lo), float(hi))
+
+    def prop3(self):
+        """[21][21][n][6] coefficient table of the variable-pitch propeller (None for FixedPitch)"""
+        n = self.lib.orc_sim_prop3(self.h, None)
+        if n <= 0:
+            return None
+        out = np.zeros((21, 21, n, 6))
+        self.lib.orc_sim_prop3(self.h, _dp(out))
+        return out
 
     def __del__(self):
         try:

@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE ONLY (see orc_real.hpp). extern "C" surface used by tests/, smoke() and
 // bench.py's cpu_baseline / --impl reference legs through ctypes.
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -50,6 +51,7 @@ bool set_input_field(Member& m, int f, double v) {
         case FB_U_WIND_D: u.wind_n.z = v; break;
         case FB_U_TRN_ELEVATION: u.trn_elev = v; break;
         case FB_U_TRN_SURFACE: u.surface = (int)v; break;
+        case FB_U_PROP_PITCH: u.prop_pitch = clampd(v, 0, 1); break;
         default:
             if (f >= FB_U_ACT_THROTTLE && f <= FB_U_ACT_BRAKE_RIGHT) { int i = f - FB_U_ACT_THROTTLE; u.act_cmd[i] = clampd(v, ACT_LO[i], ACT_HI[i]); break; }
             return false;
@@ -71,6 +73,7 @@ double get_input_field(const Member& m, int f) {
         case FB_U_T_SL: return val(u.T_sl); case FB_U_P_SL: return val(u.p_sl);
         case FB_U_WIND_N: return val(u.wind_n.x); case FB_U_WIND_E: return val(u.wind_n.y); case FB_U_WIND_D: return val(u.wind_n.z);
         case FB_U_TRN_ELEVATION: return val(u.trn_elev); case FB_U_TRN_SURFACE: return u.surface;
+        case FB_U_PROP_PITCH: return val(u.prop_pitch);
         default:
             if (f >= FB_U_ACT_THROTTLE && f <= FB_U_ACT_BRAKE_RIGHT) return val(u.act_cmd[f - FB_U_ACT_THROTTLE]);
     }
@@ -95,6 +98,7 @@ static double get_output_field(const Sim& s, int f) {
         case FB_Y_ENG_P_SHAFT: return val(y.eng.P_shaft); case FB_Y_ENG_TAU_SHAFT: return val(y.eng.tau_shaft); case FB_Y_ENG_MDOT: return val(y.eng.mdot);
         case FB_Y_FUEL_M_TOTAL: return val(y.fuel.m_total);
         case FB_Y_PROP_THRUST: return val(y.prop.wr_p.F.x); case FB_Y_PROP_J: return val(y.prop.J);
+        case FB_Y_PROP_DBETA: return val(y.prop.dbeta);
         case FB_Y_MASS: return val(y.dyn.mp_b.m);
         case FB_Y_F_X: return val(y.dyn.f_c_c.x); case FB_Y_F_Y: return val(y.dyn.f_c_c.y); case FB_Y_F_Z: return val(y.dyn.f_c_c.z);
         default: return s.av.output(s.m, f);
@@ -170,7 +174,34 @@ void* orc_sim_create(void* w, int variant, int kin, double dt, double Dt) {
     if (s->periodic_every < 1) s->periodic_every = 1;
     return s;
 }
-void orc_sim_destroy(void* s) { delete (Sim*)s; }
+void orc_sim_destroy(void* s) { Sim* S = (Sim*)s; delete S->W_own; delete S; }
+// Non-default components of the variant VAR_C172XA2: the Sim gets its own copy of the World with the Actuator2 parameters and,
+// for n_pitch > 1, the Lookup of Propeller(VariablePitch(lo, hi; length = n_pitch)) (built once per (lo, hi, n) and cached).
+void orc_sim_set_components(void* s, double act2_wn, double act2_zeta, int n_pitch, double pitch_lo, double pitch_hi) {
+    Sim* S = (Sim*)s;
+    if (!S->W_own) { S->W_own = new World(*S->W); S->W = S->W_own; }
+    if (act2_wn > 0) S->W_own->act2_wn = act2_wn;
+    if (act2_zeta > 0) S->W_own->act2_zeta = act2_zeta;
+    if (n_pitch > 1) {
+        static std::mutex mu; static std::vector<PropTables3*> cache; static std::vector<int> cache_n;
+        std::lock_guard<std::mutex> g(mu);
+        const PropTables3* hit = nullptr;
+        for (size_t i = 0; i < cache.size(); i++) if (cache[i]->lo == pitch_lo && cache[i]->hi == pitch_hi && cache_n[i] == n_pitch) hit = cache[i];
+        if (!hit) { cache.push_back(new PropTables3(pitch_lo, pitch_hi, n_pitch)); cache_n.push_back(n_pitch); hit = cache.back(); }
+        S->W_own->prop3 = hit;
+    } else S->W_own->prop3 = nullptr;
+}
+// prop3 table of a Sim as [21][21][n][6] (C_Fx, C_Mx, C_Fz_a, C_Mz_a, C_P, eta_p): golden check of the blob section
+int orc_sim_prop3(void* s, double* out) {
+    const PropTables3* P = ((Sim*)s)->W->prop3;
+    if (!P) return 0;
+    const int n = P->C_Fx.a2.n();
+    if (out) {
+        const Interp3* all[6] = {&P->C_Fx, &P->C_Mx, &P->C_Fz_a, &P->C_Mz_a, &P->C_P, &P->eta_p};
+        for (size_t o = 0; o < (size_t)21 * 21 * n; o++) for (int c = 0; c < 6; c++) out[o * 6 + c] = all[c]->y[o];
+    }
+    return n;
+}
 int orc_sim_nx(void* s) { return ((Sim*)s)->m.L.nx; }
 int orc_sim_status(void* s) { return ((Sim*)s)->m.status; }
 void orc_sim_want_y_extra(void* s, int on) { ((Sim*)s)->m.want_y_extra = on != 0; }

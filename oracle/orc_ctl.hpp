@@ -182,7 +182,7 @@ struct Avionics {
              GeoLLH p1{{0.0, 0.0}, 0.0}, p2{{1e-3, 0.0}, 0.0}; } ugdc;
     struct { int mode = 0; SegmentData data; real dchi = 0.0, chi_ref = 0.0, h_ref = 0.0; bool hor = false, vrt = false; } ygdc;
 
-    bool active() const { return variant >= VAR_C172X1; }
+    bool active() const { return variant == VAR_C172X1 || variant == VAR_C172X2; }
 
     // assign!(vehicle, avionics): c172x_ctl.jl:449-458, 986-995 — commands are Ranged on assignment
     void assign(Member& m) {

@@ -83,3 +83,26 @@ struct Interp2 {
         return v;
     }
 };
+
+// three scaled-linear axes with Flat extrapolation: the propeller Lookup of a VariablePitch propeller
+// (propellers.jl:253-273: extrapolate(scale(interpolate(coef, (BSpline(Linear()) x3)), J, Mt, dbeta), Flat()))
+struct Interp3 {
+    Axis a0, a1, a2;
+    std::vector<double> y;  // y[(i0 * n1 + i1) * n2 + i2]
+    double at(int i, int j, int k) const { return y[((size_t)i * a1.n() + j) * a2.n() + k]; }
+    real operator()(real x0, real x1, real x2) const {
+        real xs0 = rclamp(x0, a0.knots.front(), a0.knots.back());
+        real xs1 = rclamp(x1, a1.knots.front(), a1.knots.back());
+        real xs2 = rclamp(x2, a2.knots.front(), a2.knots.back());
+        int i, j, k; real u, w, t;
+        a0.locate(xs0, i, u);
+        a1.locate(xs1, j, w);
+        a2.locate(xs2, k, t);
+        auto face = [&](int ii) {
+            real f0 = (1.0 - t) * at(ii, j, k) + t * at(ii, j, k + 1);
+            real f1 = (1.0 - t) * at(ii, j + 1, k) + t * at(ii, j + 1, k + 1);
+            return (1.0 - w) * f0 + w * f1;
+        };
+        return (1.0 - u) * face(i) + u * face(i + 1);
+    }
+};

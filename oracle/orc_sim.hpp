@@ -76,7 +76,12 @@ inline void sys_init(Member& m, const World& W, const SysInit& si) {
         u.brake_left = clampR(si.brake_left, 0, 1); u.brake_right = clampR(si.brake_right, 0, 1);
     } else {
         real c[7] = {si.throttle, si.aileron, si.elevator, si.rudder, si.flaps, si.brake_left, si.brake_right};
-        for (int i = 0; i < 7; i++) { u.act_cmd[i] = clampR(c[i], ACT_LO[i], ACT_HI[i]); m.x[L.act + i] = u.act_cmd[i]; }
+        // act.<unit>.u[] = value; act.x.<unit>.p = value (c172x.jl:258-274); an Actuator2's velocity state keeps its zero
+        const bool a2 = (L.variant == VAR_C172XA2);
+        for (int i = 0; i < 7; i++) {
+            u.act_cmd[i] = clampR(c[i], ACT_LO[i], ACT_HI[i]);
+            if (a2) { m.x[L.act + 2 * i] = 0.0; m.x[L.act + 2 * i + 1] = u.act_cmd[i]; } else m.x[L.act + i] = u.act_cmd[i];
+        }
     }
     m.s.eng_state = si.engine_state;
     m.x[L.eng] = si.n_eng * W.w_rated; m.x[L.eng + 1] = 0.0; m.x[L.eng + 2] = 0.0;
@@ -216,6 +221,7 @@ double get_input_field(const Member& m, int field);
 
 struct Sim {
     const World* W;
+    World* W_own = nullptr;    // a private copy when the member's components differ from the shared World's (orc_sim_set_components)
     Member m;
     Avionics av;
     double dt = 0.02, Dt = 0.02, t_start = 0.0;

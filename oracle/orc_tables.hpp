@@ -246,3 +246,22 @@ struct PropTables {  // 21x21 over J in [0,1.5], Mt in [0,1.5]; scaled, Flat (pr
         }
     }
 };
+
+// Lookup of a Propeller(VariablePitch(lo, hi; length = n)) (propellers.jl:235-251, 341-356): the same blade-element
+// coefficients over a third, blade-pitch-offset axis. Built on demand (the C172 itself flies a FixedPitch propeller).
+struct PropTables3 {
+    Interp3 C_Fx, C_Mx, C_Fz_a, C_Mz_a, C_P, eta_p;
+    double lo, hi;
+    PropTables3(double lo_, double hi_, int nb = 11, int n_blades = 2) : lo(lo_), hi(hi_) {
+        const int n = 21;
+        Axis aj = Axis::range(0, 1.5, n, FLAT, FLAT), am = Axis::range(0, 1.5, n, FLAT, FLAT), ab = Axis::range(lo, hi, nb, FLAT, FLAT);
+        Interp3* all[6] = {&C_Fx, &C_Mx, &C_Fz_a, &C_Mz_a, &C_P, &eta_p};
+        for (auto* t : all) { t->a0 = aj; t->a1 = am; t->a2 = ab; t->y.resize((size_t)n * n * nb); }
+        prop::BladeP bl;
+        for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) for (int k = 0; k < nb; k++) {
+            prop::Coefs c = prop::coefficients(n_blades, bl, aj.knots[i], am.knots[j], ab.knots[k]);
+            const size_t o = ((size_t)i * n + j) * nb + k;
+            C_Fx.y[o] = c.C_Fx; C_Mx.y[o] = c.C_Mx; C_Fz_a.y[o] = c.C_Fz_a; C_Mz_a.y[o] = c.C_Mz_a; C_P.y[o] = c.C_P; eta_p.y[o] = c.eta_p;
+        }
+    }
+};

@@ -11,7 +11,11 @@
 #include "orc_tables.hpp"
 
 enum KinType { KIN_WA = 0, KIN_ECEF = 1, KIN_NED = 2 };
-enum Variant { VAR_C172S = 0, VAR_C172X0 = 1, VAR_C172X1 = 2, VAR_C172X2 = 3 };
+enum Variant { VAR_C172S = 0, VAR_C172X0 = 1, VAR_C172X1 = 2, VAR_C172X2 = 3,
+               // Cessna172Xv0 assembled from the non-default components the Model tree admits: a
+               // FlyByWireActuation of seven Actuator2 units (c172x.jl:68-106) and, optionally, a VariablePitch propeller
+               // (propellers.jl:341-400)
+               VAR_C172XA2 = 4 };
 enum EngState { ENG_OFF = 0, ENG_STARTING = 1, ENG_RUNNING = 2 };
 enum Surface { SURF_DRY = 0, SURF_WET = 1, SURF_ICY = 2 };
 
@@ -61,10 +65,10 @@ struct PIY { real out[2]; real out_free[2]; int sat_out[2]; bool halted[2]; };
 struct StrutY { real dh = 0.0; bool wow = false; real xi = 0.0, xi_dot = 0.0, F_dmp = 0.0, psi_sw = 0.0, alpha_ts = 0.0; Frame t_sc, t_bc; real v_xy[2] = {0.0, 0.0}; int surface = SURF_DRY; };
 struct ContactY { real mu_roll = 0.0, mu_skid = 0.0, kappa_br = 0.0, psi_cv = 0.0; real mu_max[2] = {0.0, 0.0}, mu_eff[2] = {0.0, 0.0}; V3 f_c, F_c; Wrench wr_b; PIY frc; };
 struct AeroY { real e, a, r, f, de, da, dr, df, alpha, beta, alpha_filt, beta_filt, alpha_filt_dot, beta_filt_dot; bool stall; real C_D, C_Y, C_L, C_l, C_m, C_n; Wrench wr_b; };
-struct PropY { V3 v_wOp_p; real omega, J, Mt; Wrench wr_p, wr_b; V3 hr_p, hr_b; real P, eta_p; };
+struct PropY { V3 v_wOp_p; real omega, J, Mt, dbeta = 0.0; Wrench wr_p, wr_b; V3 hr_p, hr_b; real P, eta_p; };
 struct EngY { bool start, stop; int state; real throttle, MAP, mixture, mixture_pos, f, mdot, omega, n, tau_shaft, P_shaft, SFC; PIY idle, frc; };
 struct FuelY { real x_avail, m_total, m_avail; };
-struct ActY { real cmd[7], pos[7]; int sat[7]; };  // throttle, aileron, elevator, rudder, flaps, brake_left, brake_right
+struct ActY { real cmd[7], pos[7], vel[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0}; int sat[7]; };  // throttle, aileron, elevator, rudder, flaps, brake_left, brake_right
 struct DynY { Wrench wr_c, wr_b; MassProps mp_c, mp_b; V3 ho_b, wd_ec_c, vd_ec_c, a_ec_c, a_ic_c, g_c_c, gam_c_c, f_c_c, wd_eb_b, vd_eb_b, al_ib_b, a_eb_b, a_ib_b; };
 struct VehicleY { KinData kin; AirData air; AeroY aero; StrutY strut[3]; ContactY contact[3]; PropY prop; EngY eng; FuelY fuel; ActY act; DynY dyn; };
 
@@ -73,14 +77,14 @@ struct Layout {
     int variant, kin;
     int aero = 0, ldg = 2, fuel = 8, eng = 9, act = 12, kinx, dyn, nx, nkin;
     Layout(int v = VAR_C172S, int k = KIN_WA) : variant(v), kin(k) {
-        int nact = (v == VAR_C172S) ? 0 : 7;
+        int nact = (v == VAR_C172S) ? 0 : (v == VAR_C172XA2 ? 14 : 7);   // Actuator2: X = (v, p) per unit (c172x.jl:84)
         kinx = 12 + nact;
         nkin = (k == KIN_WA) ? 9 : (k == KIN_ECEF ? 8 : 6);
         dyn = kinx + nkin;
         nx = dyn + 6;
     }
 };
-static const int ORC_NX_MAX = 34;
+static const int ORC_NX_MAX = 41;
 
 struct Inputs {
     // C172S MechanicalActuation.u (c172s.jl:62-72); every assignment saturates (types.jl:15-20)
@@ -97,6 +101,8 @@ struct Inputs {
     real trn_elev = 0.0; int surface = SURF_DRY;
     // C172X fly-by-wire actuator commands (c172x.jl:33); index order as ActY
     real act_cmd[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    // Propeller{<:VariablePitch}.u: Ranged(0, 0, 1) (propellers.jl:385)
+    real prop_pitch = 0.0;
 };
 struct Discrete { bool stall = false; int eng_state = ENG_OFF; };
 
@@ -108,6 +114,9 @@ struct World {
     AeroTables aero;
     EngineTables eng;
     PropTables prop;
+    const PropTables3* prop3 = nullptr;   // set: the propeller is Propeller(VariablePitch(prop3->lo, prop3->hi)) instead of FixedPitch
+    // Actuator2 parameters (c172x.jl:71: defaults 5 Hz natural frequency, damping ratio 0.6)
+    double act2_wn = 5 * 2 * ORC_PI, act2_zeta = 0.6;
     // engine parameters (c172s.jl:16-27)
     double P_rated = 735.49875 * 200, w_rated = 2700 * ORC_PI / 30, w_stall = 300 * ORC_PI / 30, w_max = 3100 * ORC_PI / 30,
            w_idle = 600 * ORC_PI / 30, tau_start = 40, J_eng = 0.05;
@@ -412,7 +421,17 @@ struct Member {
         real J = 2 * ORC_PI * v_J / (w_J * d);
         real Mt = rabs(w) * (d / 2) / air.a;
         const PropTables& PT = W.prop;
-        real C_Fx = PT.C_Fx(J, Mt), C_Mx = PT.C_Mx(J, Mt), C_Fz_a = PT.C_Fz_a(J, Mt), C_Mz_a = PT.C_Mz_a(J, Mt), C_P = PT.C_P(J, Mt), eta_p = PT.eta_p(J, Mt);
+        real C_Fx, C_Mx, C_Fz_a, C_Mz_a, C_P, eta_p;
+        if (W.prop3) {   // get_dbeta(::Model{<:Propeller{<:VariablePitch}}) = linear_scaling(u[], range) (propellers.jl:395-398, types.jl:70-73)
+            const PropTables3& P3 = *W.prop3;
+            real dbeta = P3.lo + (P3.hi - P3.lo) / (1.0 - 0.0) * (rclamp(u.prop_pitch, 0.0, 1.0) - 0.0);
+            C_Fx = P3.C_Fx(J, Mt, dbeta); C_Mx = P3.C_Mx(J, Mt, dbeta); C_Fz_a = P3.C_Fz_a(J, Mt, dbeta);
+            C_Mz_a = P3.C_Mz_a(J, Mt, dbeta); C_P = P3.C_P(J, Mt, dbeta); eta_p = P3.eta_p(J, Mt, dbeta);
+            p.dbeta = dbeta;
+        } else {
+            C_Fx = PT.C_Fx(J, Mt); C_Mx = PT.C_Mx(J, Mt); C_Fz_a = PT.C_Fz_a(J, Mt); C_Mz_a = PT.C_Mz_a(J, Mt); C_P = PT.C_P(J, Mt); eta_p = PT.eta_p(J, Mt);
+            p.dbeta = 0.0;
+        }
         real al_p, be_p;
         airflow_angles(v_wOp_p, al_p, be_p);
         V3 C_F(C_Fx, C_Fz_a * be_p, C_Fz_a * al_p);
@@ -551,6 +570,21 @@ struct Member {
             a_r = -rclamp(u.rudder_offset + u.rudder, -1.0, 1.0);
             a_f = u.flaps;
             throttle = u.throttle;
+        } else if (L.variant == VAR_C172XA2) {  // Actuator2, c172x.jl:91-106: second-order lag, clamped position, x = (v, p)
+            ActY& a = y.act;
+            const double wn = W.act2_wn, zt = W.act2_zeta;
+            for (int i = 0; i < 7; i++) {
+                real cmd = rclamp(u.act_cmd[i], ACT_LO[i], ACT_HI[i]);
+                real xv = x[L.act + 2 * i], xp = x[L.act + 2 * i + 1];
+                a.cmd[i] = cmd;
+                a.pos[i] = rclamp(xp, ACT_LO[i], ACT_HI[i]);
+                a.vel[i] = xv;
+                a.sat[i] = (cmd == ACT_HI[i]) - (cmd == ACT_LO[i]);
+                xdot[L.act + 2 * i] = (wn * wn) * (cmd - xp) - 2 * zt * wn * xv;
+                xdot[L.act + 2 * i + 1] = xv;
+            }
+            a_e = -a.pos[2]; a_a = a.pos[1]; a_r = -a.pos[3]; a_f = a.pos[4];
+            throttle = a.pos[0]; steer = a.pos[3]; br_l = a.pos[5]; br_r = a.pos[6];
         } else {  // c172x.jl:39-52, 127-143
             ActY& a = y.act;
             for (int i = 0; i < 7; i++) {

@@ -16,7 +16,7 @@
 _Static_assert(sizeof(fb_moments) == 40, "fb_moments: int64 + 4 doubles");
 _Static_assert(offsetof(fb_config, n_members) == 8 && offsetof(fb_config, dt) == 24, "fb_config head");
 _Static_assert(offsetof(fb_config, log_fields) == 68 && offsetof(fb_config, steps_per_launch) == 196, "fb_config log block");
-_Static_assert(offsetof(fb_config, log_flags) == 200 && sizeof(fb_config) == 208, "fb_config tail");
+_Static_assert(offsetof(fb_config, log_flags) == 200 && offsetof(fb_config, prop_pitch_n) == 204 && offsetof(fb_config, prop_pitch_lo) == 216 && sizeof(fb_config) == 248, "fb_config tail");
 _Static_assert(sizeof(fb_trim_params_soa) == 17 * sizeof(void*), "fb_trim_params_soa: 12 columns + payload[5]");
 _Static_assert(sizeof(fb_init_soa) == 32 * sizeof(void*), "fb_init_soa: 32 columns");
 
@@ -25,11 +25,13 @@ static int failures = 0;
 
 static int layout(void) {
     printf("{\"fb_config\": {\"size\": %zu, \"variant\": %zu, \"kinematics\": %zu, \"n_members\": %zu, \"member_offset\": %zu, \"dt\": %zu, \"Dt\": %zu, "
-           "\"t_start\": %zu, \"t_end\": %zu, \"device\": %zu, \"log_every\": %zu, \"log_n_fields\": %zu, \"log_fields\": %zu, \"steps_per_launch\": %zu, \"log_flags\": %zu}, ",
+           "\"t_start\": %zu, \"t_end\": %zu, \"device\": %zu, \"log_every\": %zu, \"log_n_fields\": %zu, \"log_fields\": %zu, \"steps_per_launch\": %zu, \"log_flags\": %zu, "
+           "\"prop_pitch_n\": %zu, \"reserved0\": %zu, \"prop_pitch_lo\": %zu, \"prop_pitch_hi\": %zu, \"act2_omega_n\": %zu, \"act2_zeta\": %zu}, ",
            sizeof(fb_config), offsetof(fb_config, variant), offsetof(fb_config, kinematics), offsetof(fb_config, n_members), offsetof(fb_config, member_offset),
            offsetof(fb_config, dt), offsetof(fb_config, Dt), offsetof(fb_config, t_start), offsetof(fb_config, t_end), offsetof(fb_config, device),
            offsetof(fb_config, log_every), offsetof(fb_config, log_n_fields), offsetof(fb_config, log_fields), offsetof(fb_config, steps_per_launch),
-           offsetof(fb_config, log_flags));
+           offsetof(fb_config, log_flags), offsetof(fb_config, prop_pitch_n), offsetof(fb_config, reserved0), offsetof(fb_config, prop_pitch_lo),
+           offsetof(fb_config, prop_pitch_hi), offsetof(fb_config, act2_omega_n), offsetof(fb_config, act2_zeta));
     printf("\"fb_moments\": {\"size\": %zu, \"count\": %zu, \"sum\": %zu, \"sum_sq\": %zu, \"min\": %zu, \"max\": %zu}, ",
            sizeof(fb_moments), offsetof(fb_moments, count), offsetof(fb_moments, sum), offsetof(fb_moments, sum_sq), offsetof(fb_moments, min), offsetof(fb_moments, max));
     printf("\"fb_trim_params_soa\": {\"size\": %zu, \"lat\": %zu, \"flaps\": %zu, \"payload\": %zu}, ",

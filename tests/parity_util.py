@@ -5,7 +5,7 @@ import numpy as np
 # (angular rates, lateral velocity, friction-regulator states) from turning rounding noise into an
 # "infinite" relative error; floors are small against each block's natural magnitude.
 def state_floors(nx, variant, kin):
-    nact = 0 if variant == 0 else 7
+    nact = 0 if variant == 0 else (14 if variant == 4 else 7)   # variant 4: Actuator2 units, (v, p) per unit
     f = np.empty(nx)
     f[0:2] = 1e-2          # alpha_filt, beta_filt [rad]
     f[2:8] = 1e-2          # contact friction regulators [-]
@@ -14,6 +14,8 @@ def state_floors(nx, variant, kin):
     f[10:12] = 1e-2        # idle / friction compensators
     k0 = 12 + nact
     f[12:k0] = 1e-2        # actuator positions
+    if variant == 4:
+        f[12:k0:2] = 1.0   # actuator velocities [1/s]: a 0.1 command step peaks near 2
     nkin = {0: 9, 1: 8, 2: 6}[kin]
     if kin == 0:
         f[k0:k0 + 8] = 1e-2   # unit quaternions

@@ -222,6 +222,19 @@ def prop_tables(n=21):
     return {"prop.tables": out}
 
 
+def prop_tables3(lo=-0.1, hi=0.2, nb=11, n=21):
+    """Lookup of Propeller(VariablePitch(lo, hi; length = nb)) (propellers.jl:235-251, 341-356): the same blade-element
+    coefficients over a third axis, the blade-pitch offset. Default range: the reference's own VariablePitch test case
+    (lib/FlightPhysics/test/test_propellers.jl:152). Layout [iJ][iMt][ib][6]; only FB_C172XA2 reads it."""
+    Jr = np.linspace(0, 1.5, n); Mr = np.linspace(0, 1.5, n); Br = np.linspace(lo, hi, nb)
+    out = np.zeros((n, n, nb, 6))
+    for i, J in enumerate(Jr):
+        for j, Mt in enumerate(Mr):
+            for k, db in enumerate(Br):
+                out[i, j, k, :] = prop_coefficients(J, Mt, dbeta=db)
+    return {"prop.tables3": out, "prop.pitch3": np.array([lo, hi], dtype=np.float64)}
+
+
 # ----------------------------------------------------------------------------- geoid + gains
 def geoid_table():
     path = os.path.join(REF, "lib/FlightPhysics/src/data/ww15mgh_le.bin")
@@ -297,6 +310,7 @@ def main():
     tables.update(aero_tables())
     tables.update(engine_tables())
     tables.update(prop_tables())
+    tables.update(prop_tables3())
     tables.update(gain_tables())
     tables.update(geoid_table())
     write_blob(tables, OUT)
