@@ -21,7 +21,7 @@
 #define FB_STEP_BLOCK_WIDE 448  // second airborne shape
 #endif
 #ifndef FB_STEP_BLOCK_CTL
-#define FB_STEP_BLOCK_CTL 256   // variants with control laws (C172X1/X2): 8 warps at 255 registers
+#define FB_STEP_BLOCK_CTL 256   // variants with control laws (C172X1/X2) and every complete kernel: 8 warps at 255 registers
 #endif
 
 struct EnsembleDev {
@@ -216,7 +216,11 @@ struct StepShape {
     // plus the control laws spill ~130 doubles per step at 168 registers, every spill an L2 round trip beside 229 KB of
     // shared memory, and the 8-warp shape leaves room for the whole input cache and the output tap in shared memory
     // (measured on cfg 3: 1.11e9 -> 1.17e9 aircraft-steps/s before anything else changed; C172S loses 11 % at 256).
-    static constexpr int VCAP = (VAR == FB_C172X1 && CAP > FB_STEP_BLOCK_CTL) ? FB_STEP_BLOCK_CTL : CAP;
+    // The complete (ground-capable) kernels of every variant take the same shape: at 168 registers the C172S one spilled 880
+    // bytes per thread (172 at 255) and twelve warps at twelve different program counters overran the instruction cache
+    // (cfg 4, 2^18 members on the ground: 5.78e8 -> 6.41e8 aircraft-steps/s; drawing the member-warps from a global queue on
+    // top of either shape was measured too and changes nothing: the 4.6 waves are not what costs).
+    static constexpr int VCAP = ((VAR == FB_C172X1 || !AIR) && CAP > FB_STEP_BLOCK_CTL) ? FB_STEP_BLOCK_CTL : CAP;
     static constexpr int T = FIT < VCAP ? FIT : VCAP;
     static constexpr int SPARE = (int)(BUDGET / (sizeof(double) * T)) - NCOL;                  // columns left for the input cache and the tap
     // Spare columns, in this order: the anchor of the slowly varying transcendentals (SmemAnchor: five columns, taken when

@@ -424,6 +424,9 @@ FB_DEV void isa_data(double h_o, double T_sl, const PSL& p_sl_of, double trc, do
         isa_upper(hg, T_sl, p_sl_of(), T2, p2, e2);
         T = T2; p = p2; if (e2) err = e2;
         tr = pow_slow(p2 * (1.0 / isa::p_std), kT);
+        // the anchor holds a tropospheric state: an evaluation above the tropopause invalidates it, so that the next evaluation
+        // below 11 km (a later stage of the same step, or a descent) takes the exact branch and anchors afresh
+        if (Anc::ON) anc.set(ANC_IT, 0.0);
     }
 }
 

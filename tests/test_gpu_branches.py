@@ -27,19 +27,23 @@ def _check(fb, sim, oracles, variant, kin, tol=1e-9):
     return worst
 
 
-def test_tropopause_crossing_and_upper_isa_layers(fb, orc):
+@pytest.mark.parametrize("variant", [0, 2])
+def test_tropopause_crossing_and_upper_isa_layers(fb, orc, variant):
     """Members launched at 9-13 km (and two at 20 km) climbing or descending through 11 km / 20 km: the airborne kernel
     carries the troposphere only and hands a member to the complete kernel above it; T, p, the engine's density ratio and
-    every state must follow the oracle through the layer change."""
+    every state must follow the oracle through the layer change. (The complete kernel anchors its ISA pressure on the
+    step-start state, a tropospheric formula: a step that straddles 11 km must not reuse an anchor across the layer change —
+    this test caught exactly that when the complete C172S kernel got the anchored shape.) Cessna172Sv0 and Cessna172Xv1."""
     h = np.array([9000.0, 10900.0, 10960.0, 10995.0, 11005.0, 11050.0, 11200.0, 12000.0, 13000.0, 19990.0, 20030.0])
     vD = np.array([-15.0, -60.0, -40.0, -20.0, 15.0, 20.0, 25.0, 5.0, -5.0, -30.0, 20.0])
     n = h.size
     kw = dict(h_e=h, vN=np.full(n, 60.0), vD=vD, n_eng=np.full(n, 0.85), engine_state=np.full(n, 2.0), throttle=np.full(n, 1.0), mixture=0.5)
-    sim = fb.BatchSimulation(fb.SimpleWorld(fb.Cessna172Sv0(fb.WA())), n=n, dt=0.01, t_end=100.0, steps_per_launch=40)
+    ac = {0: fb.Cessna172Sv0, 2: fb.Cessna172Xv1}[variant]
+    sim = fb.BatchSimulation(fb.SimpleWorld(ac(fb.WA())), n=n, dt=0.01, Dt=0.01, t_end=100.0, steps_per_launch=40)
     sim.init(fb.C172.Init(**kw))
     oracles = []
     for i in range(n):
-        o = orc.Sim(variant=0, kin=0, dt=0.01)
+        o = orc.Sim(variant=variant, kin=0, dt=0.01, Dt=0.01)
         o.init(**{k: float(np.broadcast_to(v, (n,))[i]) for k, v in kw.items()})
         oracles.append(o)
     crossed = np.zeros(n, dtype=bool)
@@ -48,7 +52,7 @@ def test_tropopause_crossing_and_upper_isa_layers(fb, orc):
         sim.step(2.0)
         for o in oracles:
             o.step(200)
-        worst = _check(fb, sim, oracles, 0, 0)
+        worst = _check(fb, sim, oracles, variant, 0)
         h1 = sim.get_output("h_o")
         for lvl in (11000.0, 20000.0):
             crossed |= (np.minimum(h0, h1) < lvl) & (np.maximum(h0, h1) > lvl)
