@@ -218,8 +218,10 @@ struct StepShape {
     // (measured on cfg 3: 1.11e9 -> 1.17e9 aircraft-steps/s before anything else changed; C172S loses 11 % at 256).
     // The complete (ground-capable) kernels of every variant take the same shape: at 168 registers the C172S one spilled 880
     // bytes per thread (172 at 255) and twelve warps at twelve different program counters overran the instruction cache
-    // (cfg 4, 2^18 members on the ground: 5.78e8 -> 6.41e8 aircraft-steps/s; drawing the member-warps from a global queue on
-    // top of either shape was measured too and changes nothing: the 4.6 waves are not what costs).
+    // (cfg 4, 2^18 members on the ground: 5.78e8 -> 6.41e8 aircraft-steps/s). Drawing the member-warps of the hand-over pass
+    // from a global queue (persistent CTAs, as the airborne fly-by-wire launches do) was measured on top and is 5 % SLOWER
+    // here (6.07e8): warps that pick up work one by one drift apart in program counter, and this kernel lives on the
+    // instruction-cache lines its warps share (`no_instruction` is its second-largest stall).
     static constexpr int VCAP = ((VAR == FB_C172X1 || !AIR) && CAP > FB_STEP_BLOCK_CTL) ? FB_STEP_BLOCK_CTL : CAP;
     static constexpr int T = FIT < VCAP ? FIT : VCAP;
     static constexpr int SPARE = (int)(BUDGET / (sizeof(double) * T)) - NCOL;                  // columns left for the input cache and the tap
