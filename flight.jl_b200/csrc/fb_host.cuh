@@ -33,6 +33,7 @@ struct fb_sim {
     long long* d_ev_cursor = nullptr;
     int* d_log_fields = nullptr;
     double* d_scratch = nullptr;      // [max(nx, 8)][pitch]
+    double* d_upload = nullptr;       // [Uploader::ROWS][pitch]: staging rows of the initialisation calls
     unsigned long long* d_rhs_count = nullptr;
     long long launches = 0;
     int periodic_every = 1;

@@ -327,7 +327,7 @@ int32_t fb_destroy(fb_handle s) {
     cudaFree(s->d_snap); if (s->snap_ready) cudaEventDestroy(s->snap_ready); if (s->snap_done) cudaEventDestroy(s->snap_done);
     EnsembleDev& E = s->E;
     cudaFree(E.x); cudaFree(E.u); cudaFree(E.stall); cudaFree(E.eng); cudaFree(E.status); cudaFree(E.ctl); cudaFree(E.log);
-    cudaFree(s->d_pack); cudaFree(s->d_geoid); cudaFree(s->d_prop3);
+    cudaFree(s->d_pack); cudaFree(s->d_geoid); cudaFree(s->d_prop3); cudaFree(s->d_upload);
     cudaFree(s->d_ev_off); cudaFree(s->d_ev_step); cudaFree(s->d_ev_field); cudaFree(s->d_ev_value); cudaFree(s->d_ev_cursor);
     cudaFree(s->d_log_fields); cudaFree(s->d_scratch); cudaFree(s->d_rhs_count);
     cudaFree(s->d_resume); cudaFree(s->d_ground); cudaFree(s->d_queue); if (s->h_ground) cudaFreeHost(s->h_ground); if (s->ground_ev) cudaEventDestroy(s->ground_ev);
@@ -470,19 +470,27 @@ int32_t fb_load_tables(fb_handle s, const void* blob, size_t nbytes) {
 }
 
 // upload an optional host column [N] into a device row of the scratch arena; returns device pointer or nullptr
+// (rows of ONE arena per handle, allocated at the first initialisation and kept: an allocation per column was up to 19
+// cudaMalloc / cudaFree pairs, each a device-wide synchronisation, per init call)
 struct Uploader {
-    fb_sim* s; std::vector<double*> bufs; cudaError_t err = cudaSuccess;
+    fb_sim* s; int used = 0; cudaError_t err = cudaSuccess;
+    static constexpr int ROWS = 40;      // fb_init_soa has 32 columns; fb_trim_params_soa 17 + 7 trim-state rows + the cost
+    explicit Uploader(fb_sim* s_) : s(s_) {
+        if (!s->d_upload) { err = cudaMalloc(&s->d_upload, sizeof(double) * ROWS * s->pitch); if (err != cudaSuccess) s->d_upload = nullptr; }
+    }
+    double* row(int n_rows = 1) {        // n_rows consecutive rows of the arena (device memory only)
+        if (!s->d_upload || used + n_rows > ROWS) { if (err == cudaSuccess) err = cudaErrorMemoryAllocation; return nullptr; }
+        double* d = s->d_upload + (long long)used * s->pitch; used += n_rows; return d;
+    }
     const double* up(const double* h) {
         if (!h) return nullptr;
-        double* d = nullptr;
-        cudaError_t e = cudaMalloc(&d, sizeof(double) * s->pitch);
-        if (e != cudaSuccess) { err = e; return nullptr; }
-        bufs.push_back(d);
-        e = cudaMemcpyAsync(d, h, sizeof(double) * s->E.n, cudaMemcpyHostToDevice, s->stream);
+        double* d = row();
+        if (!d) return nullptr;
+        cudaError_t e = cudaMemcpyAsync(d, h, sizeof(double) * s->E.n, cudaMemcpyHostToDevice, s->stream);
         if (e != cudaSuccess) err = e;
         return d;
     }
-    ~Uploader() { cudaStreamSynchronize(s->stream); for (double* d : bufs) cudaFree(d); }
+    ~Uploader() { cudaStreamSynchronize(s->stream); }   // the caller's arrays and the arena are free again on return
 };
 
 static EnsembleDev mom_view(const fb_sim* s) {
@@ -531,15 +539,13 @@ int32_t fb_init_trim(fb_handle s, const fb_trim_params_soa* p, double* trim_stat
         P.gamma_wb_n = U.up(p->gamma_wb_n); P.psi_wb_dot = U.up(p->psi_wb_dot); P.theta_wb_dot = U.up(p->theta_wb_dot);
         P.beta_a = U.up(p->beta_a); P.fuel_load = U.up(p->fuel_load); P.mixture = U.up(p->mixture); P.flaps = U.up(p->flaps);
         for (int j = 0; j < 5; j++) P.payload[j] = U.up(p->payload[j]);
+        d_ts = U.row(7); d_cost = U.row();
         if (U.err != cudaSuccess) return fail(FB_ERR_CUDA, cudaGetErrorString(U.err));
-        CK(cudaMalloc(&d_ts, sizeof(double) * 7 * s->pitch));
-        CK(cudaMalloc(&d_cost, sizeof(double) * s->pitch));
         CK(FB_DISPATCH(s, trim)(s, P, d_ts, d_cost));
         if (trim_state_out) CK(cudaMemcpy2DAsync(trim_state_out, hp(s), d_ts, sizeof(double) * s->pitch, sizeof(double) * s->E.n, 7, cudaMemcpyDeviceToHost, s->stream));
         if (cost_out) CK(cudaMemcpyAsync(cost_out, d_cost, sizeof(double) * s->E.n, cudaMemcpyDeviceToHost, s->stream));
         CK(cudaStreamSynchronize(s->stream));
     }
-    cudaFree(d_ts); cudaFree(d_cost);
     return after_init(s, true);
 }
 
