@@ -139,10 +139,13 @@ def cfg5(fb, n, seconds):
     lo, hi = shard_range(n, rank, world)
     sl = slice(lo, hi)
 
-    def barrier():
+    tok = torch.zeros(1, device="cuda")
+
+    def barrier():   # an NCCL all-reduce of one element: dist.barrier() itself costs ~20 ms per call here, ten times the linearize leg
         torch.cuda.synchronize()
         if world > 1:
-            dist.barrier()
+            dist.all_reduce(tok)
+            torch.cuda.synchronize()
 
     def leg(gather):
         sim = fb.BatchSimulation(fb.SimpleWorld(fb.Cessna172Sv0(fb.NED())), n=hi - lo, dt=DT, t_end=10.0, device=local, member_offset=lo)
