@@ -221,7 +221,9 @@ struct StepShape {
     // (cfg 4, 2^18 members on the ground: 5.78e8 -> 6.41e8 aircraft-steps/s). Drawing the member-warps of the hand-over pass
     // from a global queue (persistent CTAs, as the airborne fly-by-wire launches do) was measured on top and is 5 % SLOWER
     // here (6.07e8): warps that pick up work one by one drift apart in program counter, and this kernel lives on the
-    // instruction-cache lines its warps share (`no_instruction` is its second-largest stall).
+    // instruction-cache lines its warps share (`no_instruction` is its second-largest stall). For the same reason two 4-warp
+    // CTAs per SM (a table pack each fits; it would hide the 6 % the early warps of a CTA spend at its closing barrier) are 6 %
+    // slower as well (6.03e8): the two CTAs run out of phase.
     static constexpr int VCAP = ((VAR == FB_C172X1 || !AIR) && CAP > FB_STEP_BLOCK_CTL) ? FB_STEP_BLOCK_CTL : CAP;
     static constexpr int T = FIT < VCAP ? FIT : VCAP;
     static constexpr int SPARE = (int)(BUDGET / (sizeof(double) * T)) - NCOL;                  // columns left for the input cache and the tap
