@@ -231,3 +231,60 @@ def test_fstep_and_fperiodic_hooks_match_oracle(fb, orc):
             a, b = cmds[k][i], o.get_input(fb.INPUT_NAMES[k])
             assert abs(a - b) <= 1e-9 * max(abs(b), 1e-2), (k, i, a, b)
     sim.close()
+
+
+def test_cfg1_single_member_elevator_step(fb, orc):
+    """BASELINE.json configs[0], the reference's own CPU-runnable case (README example 3, `README.md:142-204`): ONE
+    Cessna172Sv0 on NED kinematics, `C172.TrimParameters()` defaults, 1 s at trim, then `act.u.elevator += 0.1`, to t = 10 s at
+    dt = 0.01 — an ensemble of one member (one thread of one warp), every logged sample of theta against the oracle, and the
+    picture-level pins of the README plot (theta_trim ~ 0.0236 rad; pitch-up to ~0.2 rad within the 10 s)."""
+    dt = 0.01
+    sim = fb.BatchSimulation(fb.SimpleWorld(fb.Cessna172Sv0(fb.NED())), n=1, dt=dt, t_end=10.0, saveat=0.1, log_fields=("theta", "h_e", "eas"))
+    ok, ts, cost = sim.init(fb.C172.TrimParameters())
+    assert ok.all() and cost[0] <= 1e-16
+    o = orc.Sim(variant=0, kin=2, dt=dt)
+    ok_o, ts_o, _ = o.init_trim()
+    assert ok_o and np.allclose(np.asarray(ts).reshape(7, -1)[:, 0], ts_o, rtol=0, atol=1e-11)
+    theta0 = float(sim.get_output("theta")[0])
+    assert abs(theta0 - 0.0236) < 5e-4
+    sim.step(1.0); o.step(100)
+    assert np.max(np.abs(sim.x[:, 0] - o.x) / np.maximum(np.abs(o.x), 1e-2)) < 1e-10      # still at trim
+    e = fb.U["FB_U_ELEVATOR"]
+    sim.set_input("elevator", sim.get_input("elevator") + 0.1)
+    o.set_input(e, o.get_input(e) + 0.1)
+    th_o = []
+    for k in range(90):
+        o.step(10); th_o.append(o.y(fb.Y["FB_Y_THETA"]))
+    sim.run()
+    assert sim.n_steps == 1000 and sim.status()[0] == fb.FB_ST_DONE          # run!(sim) ran to t_end (sim.jl:611)
+    fl = state_floors(sim.nx, 0, 2)
+    err = scaled_err(sim.x[:, 0], o.x, fl)
+    assert err.max() < 1e-9, (int(err.argmax()), float(err.max()))
+    th = fb.TimeSeries(sim).theta[:, 0]
+    assert th.shape == (101,)
+    assert np.max(np.abs(th[11:] - np.array(th_o))) < 1e-10          # samples at t = 1.1 .. 10.0
+    assert abs(th[:11] - theta0).max() < 1e-5 and th.max() > 0.18     # flat for the first second (fuel burn moves the trim by 1e-6), then the pitch-up of the README plot
+    print(f"cfg1: worst scaled state error after 10 s {err.max():.3e}, theta peak {th.max():.4f} rad")
+    sim.close()
+
+
+def test_empty_and_tiny_ensembles(fb):
+    """Edge sizes: an ensemble of zero members is refused at construction (FB_ERR_ARG), ensembles of 1, 31, 33 members (one
+    partial warp, one full + one partial) step and keep every member (ragged N: the padded lanes of the last warp stay out)."""
+    with pytest.raises(fb.FlightBatchError, match="n_members"):
+        fb.BatchSimulation(fb.SimpleWorld(fb.Cessna172Sv0(fb.WA())), n=0, dt=0.01, t_end=1.0)
+    ref = None
+    for n in (1, 31, 33):
+        sim = fb.BatchSimulation(fb.SimpleWorld(fb.Cessna172Sv0(fb.WA())), n=n, dt=0.01, t_end=1.0)
+        ok, _, _ = sim.init(fb.C172.TrimParameters(EAS=np.full(n, 47.0), h_e=np.full(n, 1200.0)))
+        assert ok.all()
+        sim.set_input("elevator", sim.get_input("elevator") + 0.05)
+        sim.step(0.5)
+        x = sim.x
+        assert x.shape == (sim.nx, n) and (sim.status() == 0).all() and np.isfinite(x).all()
+        if ref is None:
+            ref = x[:, 0].copy()
+        assert (x == ref[:, None]).all()          # identical members, identical trajectories whatever the ensemble size
+        m = sim.stats("theta")
+        assert m["count"] == n
+        sim.close()
