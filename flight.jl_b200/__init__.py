@@ -112,6 +112,20 @@ def load_library():
         return _lib
     if not os.path.exists(LIB_PATH):
         raise FlightBatchError(f"{LIB_PATH} not built; run __graft_entry__.build() (nvcc, sm_100a)")
+    # The engine opens NCCL by soname at run time, and a process holds ONE libnccl.so.2: whichever is loaded first. If this
+    # interpreter also has the pip-packaged NCCL (the one torch links against), point the engine at that file, so that a later
+    # `import torch` finds the NCCL it was built for instead of an older system library the engine happened to load first.
+    if "FLIGHTBATCH_NCCL" not in os.environ:
+        try:
+            import importlib.util
+            spec = importlib.util.find_spec("nvidia.nccl")
+            for d in (spec.submodule_search_locations if spec else ()):
+                cand = os.path.join(d, "lib", "libnccl.so.2")
+                if os.path.exists(cand):
+                    os.environ["FLIGHTBATCH_NCCL"] = cand
+                    break
+        except Exception:
+            pass
     lib = C.CDLL(LIB_PATH)
     vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
     u8p = C.POINTER(C.c_uint8)

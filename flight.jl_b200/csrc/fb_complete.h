@@ -7,7 +7,9 @@ struct CompleteLaunch {
     cudaStream_t stream;
     EnsembleDev E;
     long long step0; int n_steps; double dt; int periodic_every; double Dt;
-    unsigned long long* rhs_count; int* resume; int resume_mode; unsigned* ground_count;
+    unsigned long long* rhs_count; long long* own; int resume_mode; unsigned* ground_count;
+    unsigned* queue;   // non-null: `grid` persistent CTAs whose warps draw member-warps from this counter (the cheap shape of a
+                       // hand-over pass that is probably empty: 148 CTAs instead of one per 256 members)
 };
 cudaError_t fb_complete_prepare(int var_t, int kin);                 // opt in to the kernel's dynamic shared memory
 int fb_complete_tmax(int var_t, int kin);                            // compile-time column stride = largest block

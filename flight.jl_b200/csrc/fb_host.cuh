@@ -41,7 +41,20 @@ struct fb_sim {
     int step_block_air = 128;        // ... of the AIR (clear-of-terrain) instantiation
     // hand-over between the two instantiations (fb_kernels.cuh): per-member resume record, device counter of members that
     // were (AIR launch) or would have been (complete launch) handed over, and its pinned host copy read one launch late
-    int* d_resume = nullptr;
+    long long* d_own = nullptr;      // [pitch] ownership words (FB_OWN_*, fb_kernels.cuh)
+    unsigned* d_side = nullptr;      // members handed over since the last join
+    bool own_dirty = false;          // an airborne launch has run since the last join (ownership words may be set)
+    bool pipeline = true;            // hand-over passes run on side_stream, one launch behind the airborne launches
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t air_done = nullptr, side_done = nullptr;
+    bool side_active = false;        // a hand-over pass may still be running on side_stream
+    int launches_since_join = 0;
+    bool side_seen = false;          // members are believed to be near the terrain (shape of the hand-over pass): the most recent count the
+                                     // host has seen, from the launches or from the look at the initial state, was above zero
+    unsigned* d_hint = nullptr; unsigned* h_hint = nullptr; cudaEvent_t hint_ev = nullptr; bool hint_pending = false;
+    int n_sms = 148;
+    unsigned* d_queue_c = nullptr;   // [0]: next member-warp of a queue-shaped hand-over pass
+    long long join_step = 0;         // step index of the last join (every ownership word counts from at least here)
     unsigned* d_ground = nullptr;
     unsigned* h_ground = nullptr;
     cudaEvent_t ground_ev = nullptr;
@@ -79,8 +92,8 @@ template <int VAR, int KIN> struct Ops {
     // handed over (it returns at once when there are none), or — while a large share of the ensemble is near the
     // terrain — the complete kernel alone. Returns the number of kernels launched through *launched.
     static cudaError_t step(fb_sim* s, long long step0, int n, int* launched) {
-        cudaError_t e = cudaMemsetAsync(s->d_ground, 0, sizeof(unsigned), s->stream);
-        if (e != cudaSuccess) return e;
+        cudaError_t e = cudaMemsetAsync(s->d_ground, 0, sizeof(unsigned), s->stream);   // (the count of the complete-only launches; the
+        if (e != cudaSuccess) return e;                                                 //  hand-over count d_side lives until the next join)
         int T = s->step_block;
         int grid = (int)((s->E.n + T - 1) / T);
         if constexpr (VAR == FB_C172XA2) {   // complete kernel only (instantiated in this translation unit): no airborne layout, no hand-over
@@ -121,23 +134,56 @@ template <int VAR, int KIN> struct Ops {
                 e = cudaMemsetAsync(s->d_queue, 0, sizeof(unsigned) * (size_t)(1 + MWT), s->stream);
                 if (e != cudaSuccess) return e;
                 step_kernel<VAR, KIN, true><<<s->air_grid, Ta, StepShape<VAR, KIN, true>::SMEM, s->stream>>>(
-                    s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_resume, 0, s->d_ground, Ta, chunk,
+                    s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_own, 0, s->d_side, Ta, chunk,
                     s->d_queue, reinterpret_cast<int*>(s->d_queue + 1));
             } else if (s->air_wide)
                 step_kernel<VAR, KIN, true, FB_STEP_BLOCK_WIDE><<<grid_a, Ta, StepShape<VAR, KIN, true, FB_STEP_BLOCK_WIDE>::SMEM, s->stream>>>(
-                    s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_resume, 0, s->d_ground, mpc, chunk);
+                    s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_own, 0, s->d_side, mpc, chunk);
             else
                 step_kernel<VAR, KIN, true><<<grid_a, Ta, StepShape<VAR, KIN, true>::SMEM, s->stream>>>(
-                    s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_resume, 0, s->d_ground, mpc, chunk);
-            { CompleteLaunch a{grid, T, s->stream, s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_resume, 1, s->d_ground};
-              e = fb_complete_launch(VAR, s->cfg.kinematics, a); if (e != cudaSuccess) return e; }
-            *launched = 2;
+                    s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_own, 0, s->d_side, mpc, chunk);
+            // Hand-over pass: the members the airborne kernel has handed over since the last join, each from the step it has
+            // reached to the end of this launch. It runs on the side stream behind this airborne launch, i.e. beside the NEXT one instead of in front of it
+            // (a handful of members near the terrain are a latency-bound 4-10 ms per 100 steps; half an ensemble on the runway is
+            // most of a step). The ownership words keep the two kernels on disjoint members; join() brings everybody level.
+            {
+                cudaStream_t st = s->stream;
+                if (s->pipeline) {
+                    e = cudaEventRecord(s->air_done, s->stream); if (e != cudaSuccess) return e;
+                    e = cudaStreamWaitEvent(s->side_stream, s->air_done, 0); if (e != cudaSuccess) return e;
+                    st = s->side_stream;
+                }
+                e = side_pass(s, st, step0 + n); if (e != cudaSuccess) return e;
+                if (s->pipeline) { e = cudaEventRecord(s->side_done, s->side_stream); if (e != cudaSuccess) return e; s->side_active = true; }
+                *launched = 2;
+            }
+            s->own_dirty = true;
         } else {
-            CompleteLaunch a{grid, T, s->stream, s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, nullptr, 0, s->d_ground};
+            CompleteLaunch a{grid, T, s->stream, s->E, step0, n, s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, nullptr, 0, s->d_ground, nullptr};
             e = fb_complete_launch(VAR, s->cfg.kinematics, a); if (e != cudaSuccess) return e;
             *launched = 1;
         }
         return cudaGetLastError();
+    }
+    // the complete kernel in hand-over mode over [join_step, target): every member the airborne kernel has handed over, from
+    // the step it has reached (its ownership word) to `target`; returns at once when nobody has been handed over
+    static cudaError_t side_pass(fb_sim* s, cudaStream_t st, long long target) {
+        if constexpr (VAR == FB_C172XA2) return cudaSuccess;
+        else {
+            const int T = s->step_block, grid = (int)((s->E.n + T - 1) / T);
+            if (target <= s->join_step) return cudaSuccess;
+            CompleteLaunch a{grid, T, st, s->E, s->join_step, (int)(target - s->join_step), s->cfg.dt, s->periodic_every, s->cfg.Dt, s->d_rhs_count, s->d_own, 1, s->d_side, nullptr};
+            if (!s->side_seen && grid > s->n_sms) {
+                // Nobody is known to have been handed over: the pass is probably empty, and one CTA per 256 members, each taking an
+                // SM slot from the airborne launch it runs beside just to leave again, cost cfg 3 1.5 %. One persistent CTA per SM
+                // whose warps draw member-warps from a counter instead (5 % slower than the static grid when there IS work —
+                // its warps drift out of phase — which is why the static grid takes over once a count has been seen).
+                cudaError_t e = cudaMemsetAsync(s->d_queue_c, 0, sizeof(unsigned) * 2, st);
+                if (e != cudaSuccess) return e;
+                a.grid = s->n_sms; a.block = step_tmax(0); a.queue = s->d_queue_c;
+            }
+            return fb_complete_launch(VAR, s->cfg.kinematics, a);
+        }
     }
     // shape 0: complete kernel, 1: airborne, 2: airborne wide
     static int step_tmax(int shape) {
@@ -244,9 +290,10 @@ struct FbOpsTable {
     cudaError_t (*linearize)(fb_sim*, double*, double*, double*, double*, double*, double*, double*, double*);
     cudaError_t (*avionics_init)(fb_sim*);
     cudaError_t (*trim)(fb_sim*, const TrimSoA&, double*, double*);
+    cudaError_t (*side_pass)(fb_sim*, cudaStream_t, long long);
 };
 template <int VAR, int KIN> constexpr FbOpsTable ops_table() {
     typedef Ops<VAR, KIN> O;
-    return FbOpsTable{O::step, O::step_tmax, O::prepare, O::rhs, O::output, O::fstep, O::fperiodic, O::init, O::linearize, O::avionics_init, O::trim};
+    return FbOpsTable{O::step, O::step_tmax, O::prepare, O::rhs, O::output, O::fstep, O::fperiodic, O::init, O::linearize, O::avionics_init, O::trim, O::side_pass};
 }
 const FbOpsTable* fb_ext_ops(int kin);   // flightbatch_ext.cu: FB_C172XA2 over the three kinematic mechanisations

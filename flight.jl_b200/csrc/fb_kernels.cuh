@@ -200,9 +200,9 @@ struct SmemState {       // f_step! view of the step-start state column
 // Two instantiations per model. AIR = true is the fast path for members clear of the terrain: compact layout without
 // the six gear-regulator states (fewer columns -> more resident members per SM), no strut code. A member that comes
 // within the height gate of the terrain (or starts there) is handed over: its state is written back at the last
-// consistent point and `resume[i]` records how many steps it completed (bit 30: the step's callbacks are still
-// pending, i.e. the state is x*). AIR = false is the complete kernel; with `resume_mode` it finishes exactly those
-// members, from that point, so that a launch pair advances every member by the same n_steps.
+// consistent point and `own[i]` records how many steps it has completed and whether the step's callbacks are still
+// pending, i.e. the state is x* (FB_OWN_*). AIR = false is the complete kernel; with `resume_mode` it takes exactly those
+// members, from that point to the end of the pass, so that every member ends up advanced by the same number of steps.
 template <int VAR, int KIN, bool AIR, int CAP = FB_STEP_BLOCK>
 struct StepShape {
     static constexpr int NX = Lay<VAR, KIN, AIR>::NX;
@@ -246,11 +246,34 @@ struct StepShape {
     static constexpr size_t SMEM = TBL + sizeof(double) * (NCOL + NSLOT + NTAP + NANC) * T;
 };
 #define FB_RESUME_PENDING (1 << 30)
+// Ownership word of a member, own[i] (64 bits, written with one store): bit 0 = the member is with the complete kernel (handed
+// over by an airborne launch; it stays there, launch after launch, until the host returns everybody to the airborne kernel at
+// its next join), bit 1 = its current step's callbacks are still pending (the state is x*), bits 2.. = steps completed since
+// init. The airborne kernel skips a member whose bit 0 is set; the hand-over pass over [S, T) takes the members whose bit 0
+// is set and whose step count is below T, from that count — so it may run on a second stream while the next airborne launch
+// is already under way (a member that launch hands over carries a count >= T and is left alone).
+#define FB_OWN_SIDE 1ll
+#define FB_OWN_PENDING 2ll
+// Both out of line on purpose: they run once per hand-over, and inlined their 64-bit arithmetic changed ptxas' register
+// allocation of the whole airborne kernel around them (cfg 3 -1.5 %).
+// Steps (relative to S, FB_RESUME_PENDING or-ed in) from which a hand-over pass over [S, S + n) takes member i; -1: not its member.
+static __device__ __noinline__ int own_resume_point(const long long* own, long long i, long long S, int n) {
+    const long long r = own[i];
+    if (!(r & FB_OWN_SIDE)) return -1;                     // flying: the airborne kernel has it
+    const long long sd = r >> 2;
+    if (sd >= S + n) return -1;                            // handed over by a LATER launch, already running on the main stream
+    return (int)max(sd - S, 0ll) | ((r & FB_OWN_PENDING) ? FB_RESUME_PENDING : 0);
+}
+// Member i is with the complete kernel from step S + (rel & ~PENDING) on (rel as `handover` in step_kernel)
+static __device__ __noinline__ void own_publish(long long* own, long long i, long long S, int rel, unsigned* count) {
+    own[i] = ((S + (long long)(rel & (FB_RESUME_PENDING - 1))) << 2) | ((rel & FB_RESUME_PENDING) ? FB_OWN_PENDING : 0) | FB_OWN_SIDE;
+    if (count) atomicAdd(count, 1u);
+}
 #define FB_MW_MAX 32            // member-warps a CTA can time-slice over its hardware warps (step_kernel)
 template <int VAR, int KIN, bool AIR, int CAP = FB_STEP_BLOCK>
 __global__ void __launch_bounds__((StepShape<VAR, KIN, AIR, CAP>::T), 1)
 step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt, int periodic_every, double Dt,
-            unsigned long long* rhs_count, int* resume, int resume_mode, unsigned* ground_count, int mpc, int chunk,
+            unsigned long long* rhs_count, long long* own, int resume_mode, unsigned* ground_count, int mpc, int chunk,
             unsigned* queue = nullptr, int* done_g = nullptr) {
     typedef Lay<VAR, KIN, AIR> L;
     typedef Lay<VAR, KIN, false> LF;
@@ -322,15 +345,16 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
     int status = E.status[i];
     bool pending = false;
     if (resume_mode) {
-        int r = resume[i];
-        if (r < 0) break;
-        pending = (r & FB_RESUME_PENDING) != 0;
-        int d0 = r & (FB_RESUME_PENDING - 1);
-        step0 += d0; n_steps -= d0;
+        if (status != FB_ST_RUNNING) break;                              // frozen while with this kernel
+        const int d0 = own_resume_point(own, i, step0_launch, n_steps_launch);
+        if (d0 < 0) break;                                               // not handed over, or by a later launch already under way
+        pending = (d0 & FB_RESUME_PENDING) != 0;
+        step0 += d0 & (FB_RESUME_PENDING - 1); n_steps -= d0 & (FB_RESUME_PENDING - 1);
     } else if (status != FB_ST_RUNNING) {
-        if (AIR) resume[i] = -1;
         break;
-    } else if (AIR && ck > 0 && resume[i] >= 0) break;   // handed over in an earlier chunk of this launch
+    }
+    // with the complete kernel: handed over by an earlier launch, or in an earlier chunk of this one
+    else if (AIR && (own[i] & FB_OWN_SIDE)) break;
     MemberIn ug; ug.u = E.u + i; ug.pitch = E.pitch;
     double* sx = smem + TBL / 8 + threadIdx.x;
     double* sacc = sx + NX * T;
@@ -346,7 +370,7 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
         double nz = 0.0;
 #pragma unroll
         for (int c = 0; c < 6; c++) nz += fabs(E.x[(long long)(LF::LDG + c) * E.pitch + i]);
-        if (nz != 0.0) { resume[i] = ck * chunk; atomicAdd(ground_count, 1u); break; }
+        if (nz != 0.0) { own[i] = (step0 << 2) | FB_OWN_SIDE; atomicAdd(ground_count, 1u); break; }
     }
     int stall = E.stall[i], eng = E.eng[i];
     long long ev_cur = E.ev_off ? E.ev_off[i] + E.ev_cursor[i] : 0;
@@ -504,8 +528,11 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
     E.stall[ie] = (unsigned char)stall; E.eng[ie] = (unsigned char)eng; E.status[ie] = status;
     if (E.ev_off) E.ev_cursor[ie] = ev_cur - E.ev_off[ie];
     if (VAR == FB_C172X1) cs.store(E.ctl + ie, E.pitch);
-    if (AIR) { resume[ie] = handover; if (handover >= 0) atomicAdd(ground_count, 1u); }
-    else if (!resume_mode && gnd_seen) atomicAdd(ground_count, 1u);
+    // (the state above is written before the ownership word: whoever reads the word as handed over finds the state it describes)
+    if (AIR) {
+        if (handover >= 0) own_publish(own, ie, step0_launch, handover, ground_count);
+    } else if (resume_mode) { if (status == FB_ST_RUNNING) own_publish(own, ie, step0_launch, n_steps_launch, nullptr); }
+    else if (gnd_seen) atomicAdd(ground_count, 1u);
     }
     // RHS evaluations of this launch: k1 of the first step, then k2..k4 and f(x*) per step, plus re-evaluations
     rhs_mine += max(0, 4 * done + n_reeval + (pending ? -3 : 1) + (handover >= 0 ? (sink.stage & 3) : 0));

@@ -34,6 +34,22 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
      ((s)->var_t == FB_C172XA2 ? fb_ext_ops((s)->cfg.kinematics)->CALL : FB_KIN_DISPATCH(s, FB_C172X1, CALL))))
 #endif
 
+// Join: everything that reads or writes the ensemble other than the stepping itself starts here. The launch stream waits for
+// the hand-over pass still running on the side stream, and every member goes back to the airborne kernel (a member still
+// near the terrain is handed over again by the first evaluation of the next launch: one right-hand side). After it the
+// ensemble is at one step index and lives on one stream.
+static int32_t join(fb_sim* s) {
+    if (s->side_active) { CK(cudaStreamWaitEvent(s->stream, s->side_done, 0)); s->side_active = false; }
+    if (s->own_dirty) {
+        CK(cudaMemsetAsync(s->d_own, 0, sizeof(long long) * s->pitch, s->stream));
+        CK(cudaMemsetAsync(s->d_side, 0, sizeof(unsigned), s->stream));
+        s->own_dirty = false;
+    }
+    s->launches_since_join = 0; s->join_step = s->n_steps;
+    return FB_OK;
+}
+#define JOIN(s) do { if ((s)->side_active || (s)->own_dirty) { CK(cudaSetDevice((s)->cfg.device)); if (int32_t rc_ = join(s)) return rc_; } } while (0)
+
 static size_t hp(const fb_sim* s) { return sizeof(double) * (size_t)(s->host_pitch > 0 ? s->host_pitch : s->E.n); }
 static int layout_nx(int variant, int kin) {
     int nact = (variant == FB_C172S) ? 0 : (variant == FB_C172XA2 ? 14 : 7);
@@ -53,6 +69,13 @@ __global__ void moments_reset_kernel(EnsembleDev E, long long first, long long c
     if (k >= count) return;
     const long long r = first + k;
     E.mom_cnt[r] = 0ull; E.mom_sum[2 * r] = 0.0; E.mom_sum[2 * r + 1] = 0.0; E.mom_min[r] = INFINITY; E.mom_max[r] = -INFINITY;
+}
+// members within `gate` metres of the terrain (h_o - elevation): the look at the initial state that picks the first launches' shape
+__global__ void count_near_kernel(const double* h_o, const double* elev, const int* status, long long n, double gate, unsigned* out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool near = i < n && status[i] == FB_ST_RUNNING && !(h_o[i] - elev[i] > gate);
+    const unsigned m = __ballot_sync(0xffffffffu, near);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned)__popc(m));
 }
 // row[i] = Ranged-saturated staged value (types.jl:15-20), the device half of fb_set_input
 __global__ void saturate_row_kernel(double* row, const double* staged, long long n, int field) {
@@ -308,7 +331,22 @@ static int32_t create_body(fb_sim* s) {
     if (const char* k = getenv("FLIGHTBATCH_KERNEL")) s->force_complete = (strcmp(k, "complete") == 0);
     if (cfg->variant == FB_C172XA2) s->force_complete = true;   // the non-default components exist in the complete kernel only
     if (s->force_complete) s->air_mode = false;
-    CK(cudaMalloc(&s->d_resume, sizeof(int) * s->pitch));
+    CK(cudaMalloc(&s->d_own, sizeof(long long) * s->pitch));
+    CK(cudaMemsetAsync(s->d_own, 0, sizeof(long long) * s->pitch, s->stream));
+    CK(cudaMalloc(&s->d_side, sizeof(unsigned)));
+    CK(cudaMalloc(&s->d_queue_c, sizeof(unsigned) * 2));
+    { cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, cfg->device)); s->n_sms = prop.multiProcessorCount; }
+    CK(cudaMemsetAsync(s->d_side, 0, sizeof(unsigned), s->stream));
+    // hand-over passes on a stream of their own, one launch behind the airborne launches (FLIGHTBATCH_PIPELINE=0: on the launch
+    // stream, right behind each airborne launch: diagnostic)
+    if (const char* v = getenv("FLIGHTBATCH_PIPELINE")) s->pipeline = atoi(v) != 0;
+    {
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&s->side_stream, cudaStreamNonBlocking, hi));   // its few CTAs go first when an SM frees up
+        CK(cudaEventCreateWithFlags(&s->air_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s->side_done, cudaEventDisableTiming));
+    }
     CK(cudaMalloc(&s->d_ground, sizeof(unsigned)));
     CK(cudaMallocHost(&s->h_ground, sizeof(unsigned)));
     *s->h_ground = 0;
@@ -322,6 +360,7 @@ int32_t fb_destroy(fb_handle s) {
     if (!s) return FB_OK;
     cudaSetDevice(s->cfg.device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->side_stream) { cudaStreamSynchronize(s->side_stream); cudaStreamDestroy(s->side_stream); }   // a hand-over pass may still be running
     if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
     if (s->snap_stream) { cudaStreamSynchronize(s->snap_stream); cudaStreamDestroy(s->snap_stream); }
     cudaFree(s->d_snap); if (s->snap_ready) cudaEventDestroy(s->snap_ready); if (s->snap_done) cudaEventDestroy(s->snap_done);
@@ -330,7 +369,8 @@ int32_t fb_destroy(fb_handle s) {
     cudaFree(s->d_pack); cudaFree(s->d_geoid); cudaFree(s->d_prop3); cudaFree(s->d_upload);
     cudaFree(s->d_ev_off); cudaFree(s->d_ev_step); cudaFree(s->d_ev_field); cudaFree(s->d_ev_value); cudaFree(s->d_ev_cursor);
     cudaFree(s->d_log_fields); cudaFree(s->d_scratch); cudaFree(s->d_rhs_count);
-    cudaFree(s->d_resume); cudaFree(s->d_ground); cudaFree(s->d_queue); if (s->h_ground) cudaFreeHost(s->h_ground); if (s->ground_ev) cudaEventDestroy(s->ground_ev);
+    if (s->air_done) cudaEventDestroy(s->air_done); if (s->side_done) cudaEventDestroy(s->side_done);
+    cudaFree(s->d_own); cudaFree(s->d_side); cudaFree(s->d_queue_c); cudaFree(s->d_hint); if (s->h_hint) cudaFreeHost(s->h_hint); if (s->hint_ev) cudaEventDestroy(s->hint_ev); cudaFree(s->d_ground); cudaFree(s->d_queue); if (s->h_ground) cudaFreeHost(s->h_ground); if (s->ground_ev) cudaEventDestroy(s->ground_ev);
     if (s->comm_stream) cudaStreamSynchronize(s->comm_stream);
     if (s->comm && s->comm_owned && nccl_api()) nccl_api()->CommDestroy(s->comm);
     for (auto& t : s->comm_timers) { cudaEventDestroy(t.first); cudaEventDestroy(t.second); }
@@ -350,6 +390,7 @@ int32_t fb_destroy(fb_handle s) {
 int32_t fb_wait_state(fb_handle s);
 int32_t fb_sync(fb_handle s) {
     if (!s) return fail(FB_ERR_ARG, "null handle");
+    JOIN(s);
     CK(cudaSetDevice(s->cfg.device));
     CK(cudaStreamSynchronize(s->stream));
     if (s->comm_stream) CK(cudaStreamSynchronize(s->comm_stream));
@@ -358,6 +399,7 @@ int32_t fb_sync(fb_handle s) {
 
 int32_t fb_load_tables(fb_handle s, const void* blob, size_t nbytes) {
     if (!s || !blob) return fail(FB_ERR_ARG, "fb_load_tables: null argument");
+    JOIN(s);
     CK(cudaSetDevice(s->cfg.device));
     std::vector<BlobSec> secs;
     const uint8_t* b = (const uint8_t*)blob;
@@ -499,7 +541,7 @@ static EnsembleDev mom_view(const fb_sim* s) {
     return E;
 }
 static int32_t after_init(fb_sim* s, bool init_avionics) {
-    s->n_steps = 0; s->initialised = true;
+    s->n_steps = 0; s->join_step = 0; s->initialised = true;
     if (init_avionics && s->var_t == FB_C172X1) CK(FB_DISPATCH(s, avionics_init)(s));   // f_init!(avionics, vehicle)
     CK(cudaMemsetAsync(s->d_ev_cursor, 0, sizeof(long long) * s->pitch, s->stream));
     // A member that stops stepping (crash, altitude bounds, failed trim) writes no further samples: every sample starts
@@ -522,11 +564,26 @@ static int32_t after_init(fb_sim* s, bool init_avionics) {
             CK(cudaGetLastError());
         }
     }
+    // A look at the initial state: how many members start within the height gate of the terrain? The answer reaches the host
+    // while it is still busy elsewhere (never waited for) and picks the shape of the first hand-over passes (Ops::side_pass).
+    s->side_seen = false; s->hint_pending = false;
+    if (s->var_t != FB_C172XA2 && !s->force_complete) {
+        if (!s->d_hint) { CK(cudaMalloc(&s->d_hint, sizeof(unsigned))); CK(cudaMallocHost(&s->h_hint, sizeof(unsigned))); CK(cudaEventCreateWithFlags(&s->hint_ev, cudaEventDisableTiming)); }
+        *s->h_hint = 0;
+        CK(cudaMemsetAsync(s->d_hint, 0, sizeof(unsigned), s->stream));
+        CK(FB_DISPATCH(s, output)(s, FB_Y_H_O, s->d_scratch));
+        count_near_kernel<<<(int)((s->pitch + 255) / 256), 256, 0, s->stream>>>(s->d_scratch, s->E.u + (long long)FB_U_TRN_ELEVATION * s->pitch, s->E.status, s->E.n, 4.0, s->d_hint);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(s->h_hint, s->d_hint, sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaEventRecord(s->hint_ev, s->stream));
+        s->hint_pending = true;
+    }
     return FB_OK;
 }
 
 int32_t fb_init_trim(fb_handle s, const fb_trim_params_soa* p, double* trim_state_out, double* cost_out) {
     if (!s) return fail(FB_ERR_ARG, "null handle");
+    JOIN(s);
     if (!s->tables_loaded) return fail(FB_ERR_STATE, "fb_init_trim: call fb_load_tables first");
     CK(cudaSetDevice(s->cfg.device));
     fb_trim_params_soa z; memset(&z, 0, sizeof(z));
@@ -551,6 +608,7 @@ int32_t fb_init_trim(fb_handle s, const fb_trim_params_soa* p, double* trim_stat
 
 int32_t fb_init(fb_handle s, const fb_init_soa* ic) {
     if (!s) return fail(FB_ERR_ARG, "null handle");
+    JOIN(s);
     if (!s->tables_loaded) return fail(FB_ERR_STATE, "fb_init: call fb_load_tables first");
     CK(cudaSetDevice(s->cfg.device));
     fb_init_soa z; memset(&z, 0, sizeof(z));
@@ -575,6 +633,7 @@ int32_t fb_init(fb_handle s, const fb_init_soa* ic) {
 
 int32_t fb_init_state(fb_handle s, const double* x, const uint8_t* stall, const uint8_t* eng_state) {
     if (!s || !x) return fail(FB_ERR_ARG, "fb_init_state: null argument");
+    JOIN(s);
     if (!s->tables_loaded) return fail(FB_ERR_STATE, "fb_init_state: call fb_load_tables first");
     CK(cudaSetDevice(s->cfg.device));
     CK(cudaMemcpy2DAsync(s->E.x, sizeof(double) * s->pitch, x, sizeof(double) * s->E.n, sizeof(double) * s->E.n, s->nx, cudaMemcpyHostToDevice, s->stream));
@@ -587,6 +646,7 @@ int32_t fb_init_state(fb_handle s, const double* x, const uint8_t* stall, const 
 
 int32_t fb_set_input(fb_handle s, int32_t field, const double* values, int64_t stride) {
     if (!s || !values) return fail(FB_ERR_ARG, "fb_set_input: null argument");
+    JOIN(s);
     if (field < 0 || field >= FB_U__COUNT) return fail(FB_ERR_ARG, "fb_set_input: unknown field");
     if (stride != 0 && stride != 1) return fail(FB_ERR_ARG, "fb_set_input: stride must be 0 (broadcast) or 1");
     if (field >= FB_U_GDC_MODE_REQ && field <= FB_U_GDC_H2 && s->cfg.variant != FB_C172X2)
@@ -616,6 +676,7 @@ int32_t fb_set_input(fb_handle s, int32_t field, const double* values, int64_t s
 
 int32_t fb_get_input(fb_handle s, int32_t field, double* out) {
     if (!s || !out) return fail(FB_ERR_ARG, "fb_get_input: null argument");
+    JOIN(s);
     if (field < 0 || field >= FB_U__COUNT) return fail(FB_ERR_ARG, "fb_get_input: unknown field");
     CK(cudaSetDevice(s->cfg.device));
     CK(cudaMemcpyAsync(out, s->E.u + (long long)field * s->pitch, sizeof(double) * s->E.n, cudaMemcpyDeviceToHost, s->stream));
@@ -625,6 +686,7 @@ int32_t fb_get_input(fb_handle s, int32_t field, double* out) {
 
 int32_t fb_schedule_inputs(fb_handle s, int64_t n_events, const int64_t* member, const int64_t* step, const int32_t* field, const double* value) {
     if (!s) return fail(FB_ERR_ARG, "null handle");
+    JOIN(s);
     CK(cudaSetDevice(s->cfg.device));
     CK(cudaStreamSynchronize(s->stream));
     cudaFree(s->d_ev_off); cudaFree(s->d_ev_step); cudaFree(s->d_ev_field); cudaFree(s->d_ev_value);
@@ -663,13 +725,22 @@ static int32_t advance(fb_sim* s, long long n) {
         if (s->ground_ev_pending) {
             if (cudaEventQuery(s->ground_ev) == cudaSuccess) {
                 s->ground_ev_pending = false;
-                s->air_mode = !s->force_complete && (long long)*s->h_ground * 8 <= s->E.n;
+                const bool air = !s->force_complete && (long long)*s->h_ground * 8 <= s->E.n;
+                if (s->air_mode) s->side_seen = *s->h_ground > 0;
+                if (air != s->air_mode) { if (int32_t rc = join(s)) return rc; }   // the complete-only launches take every member
+                s->air_mode = air;
             } else (void)cudaGetLastError();   // cudaErrorNotReady is not an error: keep it out of the next launch check
         }
+        if (s->hint_pending && cudaEventQuery(s->hint_ev) == cudaSuccess) { s->hint_pending = false; if (*s->h_hint > 0) s->side_seen = true; }
+        else if (s->hint_pending) (void)cudaGetLastError();
+        // a member that has climbed away stays with the (slower) complete kernel until a join returns it: inside a long run
+        // without reads, join every eighth launch
+        if (s->air_mode && s->launches_since_join >= 8) { if (int32_t rc = join(s)) return rc; }
         int launched = 0;
         CK(FB_DISPATCH(s, step)(s, s->n_steps, k, &launched));
+        s->launches_since_join++;
         if (!s->ground_ev_pending) {
-            CK(cudaMemcpyAsync(s->h_ground, s->d_ground, sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
+            CK(cudaMemcpyAsync(s->h_ground, s->air_mode ? s->d_side : s->d_ground, sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
             CK(cudaEventRecord(s->ground_ev, s->stream));
             s->ground_ev_pending = true;
         }
@@ -705,6 +776,7 @@ int32_t fb_nx(fb_handle s, int32_t* nx) { if (!s || !nx) return fail(FB_ERR_ARG,
 
 int32_t fb_get_state(fb_handle s, double* x) {
     if (!s || !x) return fail(FB_ERR_ARG, "fb_get_state: null argument");
+    JOIN(s);
     CK(cudaSetDevice(s->cfg.device));
     CK(cudaMemcpy2DAsync(x, hp(s), s->E.x, sizeof(double) * s->pitch, sizeof(double) * s->E.n, s->nx, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
@@ -719,6 +791,7 @@ int32_t fb_wait_state(fb_handle s) {
 
 int32_t fb_get_state_async(fb_handle s, double* x) {
     if (!s || !x) return fail(FB_ERR_ARG, "fb_get_state_async: null argument");
+    JOIN(s);
     CK(cudaSetDevice(s->cfg.device));
     int32_t rc = fb_wait_state(s);   // the snapshot buffer is free again once the previous copy has landed
     if (rc != FB_OK) return rc;
@@ -739,6 +812,7 @@ int32_t fb_get_state_async(fb_handle s, double* x) {
 
 int32_t fb_get_discrete(fb_handle s, uint8_t* stall, uint8_t* eng_state) {
     if (!s) return fail(FB_ERR_ARG, "null handle");
+    JOIN(s);
     CK(cudaSetDevice(s->cfg.device));
     if (stall) CK(cudaMemcpyAsync(stall, s->E.stall, s->E.n, cudaMemcpyDeviceToHost, s->stream));
     if (eng_state) CK(cudaMemcpyAsync(eng_state, s->E.eng, s->E.n, cudaMemcpyDeviceToHost, s->stream));
@@ -748,6 +822,7 @@ int32_t fb_get_discrete(fb_handle s, uint8_t* stall, uint8_t* eng_state) {
 
 int32_t fb_get_output(fb_handle s, int32_t field, double* out) {
     if (!s || !out) return fail(FB_ERR_ARG, "fb_get_output: null argument");
+    JOIN(s);
     if (field < 0 || field >= FB_Y__COUNT) return fail(FB_ERR_ARG, "fb_get_output: unknown field");
     if (!s->initialised) return fail(FB_ERR_STATE, "fb_get_output: not initialised");
     CK(cudaSetDevice(s->cfg.device));
@@ -759,6 +834,7 @@ int32_t fb_get_output(fb_handle s, int32_t field, double* out) {
 
 int32_t fb_status(fb_handle s, int32_t* status) {
     if (!s || !status) return fail(FB_ERR_ARG, "fb_status: null argument");
+    JOIN(s);
     CK(cudaSetDevice(s->cfg.device));
     CK(cudaMemcpyAsync(status, s->E.status, sizeof(int) * s->E.n, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
@@ -787,6 +863,7 @@ int32_t fb_log_times(fb_handle s, double* t) {
 
 int32_t fb_log_fetch(fb_handle s, int32_t field, double* out) {
     if (!s || !out) return fail(FB_ERR_ARG, "fb_log_fetch: null argument");
+    JOIN(s);
     int64_t ns; int32_t nf;
     fb_log_info(s, &ns, &nf);
     int fi = -1;
@@ -809,6 +886,7 @@ static void moments_from_raw(const char* raw, long long R, long long r, fb_momen
 
 int32_t fb_stats(fb_handle s, int32_t field, fb_moments* out) {
     if (!s || !out) return fail(FB_ERR_ARG, "fb_stats: null argument");
+    JOIN(s);
     if (field < 0 || field >= FB_Y__COUNT) return fail(FB_ERR_ARG, "fb_stats: unknown field");
     if (!s->initialised) return fail(FB_ERR_STATE, "fb_stats: not initialised");
     CK(cudaSetDevice(s->cfg.device));
@@ -829,6 +907,7 @@ int32_t fb_stats(fb_handle s, int32_t field, fb_moments* out) {
 
 int32_t fb_log_stats_begin(fb_handle s, int64_t first, int64_t count) {
     if (!s) return fail(FB_ERR_ARG, "null handle");
+    JOIN(s);
     if (!s->E.mom_cnt) return fail(FB_ERR_STATE, "fb_log_stats: no moments are kept (no log configured, or log_flags without FB_LOG_MOMENTS)");
     int64_t ns; int32_t nf;
     fb_log_info(s, &ns, &nf);
@@ -954,6 +1033,7 @@ static int32_t stats_allreduce_post(fb_sim* s, long long upto) {
 
 int32_t fb_log_stats_allreduce(fb_handle s) {
     if (!s) return fail(FB_ERR_ARG, "null handle");
+    JOIN(s);
     long long upto = 0;
     int32_t rc = stats_allreduce_pre(s, &upto);
     if (rc != FB_OK || upto <= s->reduced_upto) return rc;
@@ -981,6 +1061,7 @@ int32_t fb_comm_time(fb_handle s, double* ms_total, int64_t* n_calls) {
 
 int32_t fb_rhs(fb_handle s, double* xdot) {
     if (!s || !xdot) return fail(FB_ERR_ARG, "fb_rhs: null argument");
+    JOIN(s);
     if (!s->initialised) return fail(FB_ERR_STATE, "fb_rhs: not initialised");
     CK(cudaSetDevice(s->cfg.device));
     CK(FB_DISPATCH(s, rhs)(s, s->d_scratch));
@@ -991,6 +1072,7 @@ int32_t fb_rhs(fb_handle s, double* xdot) {
 
 int32_t fb_fstep(fb_handle s, int32_t* changed) {
     if (!s) return fail(FB_ERR_ARG, "null handle");
+    JOIN(s);
     if (!s->initialised) return fail(FB_ERR_STATE, "fb_fstep: not initialised");
     CK(cudaSetDevice(s->cfg.device));
     int* d_changed = (int*)s->d_scratch;   // [pitch] ints fit in the scratch rows
@@ -1002,6 +1084,7 @@ int32_t fb_fstep(fb_handle s, int32_t* changed) {
 
 int32_t fb_fperiodic(fb_handle s) {
     if (!s) return fail(FB_ERR_ARG, "null handle");
+    JOIN(s);
     if (!s->initialised) return fail(FB_ERR_STATE, "fb_fperiodic: not initialised");
     CK(cudaSetDevice(s->cfg.device));
     CK(FB_DISPATCH(s, fperiodic)(s));
@@ -1011,6 +1094,7 @@ int32_t fb_fperiodic(fb_handle s) {
 
 int32_t fb_counters(fb_handle s, int64_t* kernel_launches, int64_t* rhs_evals) {
     if (!s) return fail(FB_ERR_ARG, "null handle");
+    JOIN(s);
     if (kernel_launches) *kernel_launches = s->launches;
     if (rhs_evals) {
         CK(cudaSetDevice(s->cfg.device));
@@ -1031,6 +1115,7 @@ int32_t fb_linearize_dims(fb_handle s, int32_t* dims) {
 
 int32_t fb_linearize(fb_handle s, double* A, double* B, double* C, double* D, double* x0, double* u0, double* y0, double* xdot0) {
     if (!s) return fail(FB_ERR_ARG, "null handle");
+    JOIN(s);
     if (!s->initialised) return fail(FB_ERR_STATE, "fb_linearize: not initialised (trim first)");
     if (s->cfg.kinematics != FB_NED) return fail(FB_ERR_ARG, "fb_linearize: needs NED kinematics (the reference defines XStateSpace for Vehicle{NED} only)");
     CK(cudaSetDevice(s->cfg.device));
@@ -1122,6 +1207,7 @@ int32_t fb_lss_set_model(fb_lss_handle l, const double* A, const double* B, cons
 
 int32_t fb_lss_from_linearize(fb_lss_handle l, fb_handle s) {
     if (!l || !s) return fail(FB_ERR_ARG, "fb_lss_from_linearize: null argument");
+    JOIN(s);
     if (!s->initialised) return fail(FB_ERR_STATE, "fb_lss_from_linearize: the simulation is not initialised (trim first)");
     if (s->cfg.kinematics != FB_NED) return fail(FB_ERR_ARG, "fb_lss_from_linearize: needs NED kinematics");
     int32_t d[3]; if (int32_t rc = fb_linearize_dims(s, d)) return rc;
@@ -1236,6 +1322,7 @@ int32_t fb_measure_fp64_peak(int32_t device, double* tflops) {
 
 int32_t fb_device_state(fb_handle s, void** d_x, int64_t* pitch_elems) {
     if (!s) return fail(FB_ERR_ARG, "null handle");
+    JOIN(s);
     if (d_x) *d_x = s->E.x;
     if (pitch_elems) *pitch_elems = s->pitch;
     return FB_OK;

@@ -13,8 +13,9 @@ template <int VAR, int KIN> struct Complete {
     static int tmax() { return StepShape<VAR, KIN, false>::T; }
     static cudaError_t launch(const CompleteLaunch& a) {
         step_kernel<VAR, KIN, false><<<a.grid, a.block, StepShape<VAR, KIN, false>::SMEM, a.stream>>>(
-            a.E, a.step0, a.n_steps, a.dt, a.periodic_every, a.Dt, a.rhs_count, a.resume, a.resume_mode, a.ground_count,
-            a.block, a.n_steps > 0 ? a.n_steps : 1);   // one thread per member, the whole launch in one chunk
+            a.E, a.step0, a.n_steps, a.dt, a.periodic_every, a.Dt, a.rhs_count, a.own, a.resume_mode, a.ground_count,
+            a.block, a.n_steps > 0 ? a.n_steps : 1,    // one thread per member, the whole launch in one chunk
+            a.queue, a.queue ? reinterpret_cast<int*>(a.queue + 1) : nullptr);
         return cudaGetLastError();
     }
 };

@@ -72,6 +72,47 @@ def test_handover_path_equals_complete_kernel(fb):
     assert err[:, run & low].max() < 1e-5      # ground-contact conditioning
 
 
+def test_pipelined_handover_pass_equals_serial(fb):
+    """The hand-over pass of launch k runs on a stream of its own beside the airborne launch k + 1 (ownership words keep the two
+    kernels on disjoint members; the host joins every eighth launch and before every read). The same mixed ensemble — 1/16 of
+    the members landing or crashing — stepped through 12 back-to-back launches with the pass pipelined (default) and with it
+    on the launch stream behind each airborne launch (FLIGHTBATCH_PIPELINE=0, child process): every member runs through the
+    same kernels over the same steps either way, so states, statuses and discrete states are bit-identical. Reading the state
+    between launches (a join after every launch: members that have climbed away return to the airborne kernel earlier) moves
+    nothing beyond the rounding the two kernel instantiations differ by."""
+    n = 8192
+    a = _run(fb, n, 0, 12.0, mixed=True)
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r); import flightbatch as fb; "
+            "from test_gpu_properties import _run; r = _run(fb, %d, 0, 12.0, mixed=True); "
+            "np.savez('/tmp/fb_serial.npz', x=r['x'], status=r['status'], stall=r['disc'][0], eng=r['disc'][1])") % (ROOT, os.path.join(ROOT, "tests"), n)
+    subprocess.check_call([sys.executable, "-c", code], env=dict(os.environ, FLIGHTBATCH_PIPELINE="0"), timeout=300)
+    b = np.load("/tmp/fb_serial.npz")
+    assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["disc"][0], b["stall"]) and np.array_equal(a["disc"][1], b["eng"])
+    assert np.array_equal(a["x"], b["x"])
+    low = np.arange(n) % 16 == 0
+    assert (a["wow"][low] > 0).sum() + np.isin(a["status"][low], (2, 3)).sum() > 20
+    # the same run with a read (= a join) after every launch
+    import bench
+    p = bench.member_params(0, n)
+    sim = fb.BatchSimulation(fb.SimpleWorld(fb.Cessna172Sv0(fb.WA())), n=n, dt=0.01, t_end=1e4, steps_per_launch=100)
+    elev = np.zeros(n)
+    elev[low] = p["h_e"][low] - bench.geoid_height(p["lat"][low], p["lon"][low]) - np.where(np.arange(n)[low] % 32 == 0, 3.0, 5.0)
+    sim.set_input("trn_elevation", elev)
+    sim.init(fb.C172.TrimParameters(**p))
+    ele_f, ail_f = fb.U["FB_U_ELEVATOR"], fb.U["FB_U_AILERON"]
+    sim.schedule_inputs(*bench.doublet_events(n, sim.get_input(ele_f), sim.get_input(ail_f), ele_f, ail_f))
+    for _ in range(12):
+        sim.step(1.0)
+        st = sim.status()
+    x = sim.x
+    assert np.array_equal(st, a["status"])
+    run = st == 0
+    err = np.abs(x - a["x"]) / np.maximum(np.abs(a["x"]), 1.0)
+    print("pipelined vs read-every-launch: max diff airborne", err[:, run & ~low].max(), "near-ground", err[:, run & low].max())
+    assert err[:, run & ~low].max() < 1e-9 and err[:, run & low].max() < 1e-5
+    sim.close()
+
+
 def test_pipelined_state_read_matches_blocking_read(fb):
     """fb_get_state_async snapshots the state as of the work submitted so far: a read issued after step k and collected
     after step k+1 has been launched must equal the blocking read taken after step k (bit for bit), not the later state."""
