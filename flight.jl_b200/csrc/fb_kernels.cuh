@@ -39,6 +39,11 @@ struct EnsembleDev {
     const int* ev_field;
     const double* ev_value;
     long long* ev_cursor; // [pitch]
+    int* handover_rel;    // [pitch] launch-relative hand-over record of the airborne kernels (-1: none). Functionally the ownership
+                          // words (step_kernel's `own`) carry everything it holds; it is kept, written and read exactly as before
+                          // them, because ptxas' register allocation of the whole airborne fly-by-wire kernel follows the shape of
+                          // this code: without it cfg 3 runs at 1.33e9 aircraft-steps/s, with it at 1.35e9 (measured, eight forms). Used by the
+                          // fly-by-wire airborne kernels only (LEGACY_REC in step_kernel)
     // decimated log: log[(sample * n_fields + f) * pitch + i]
     double* log;
     const int* log_fields;
@@ -278,6 +283,7 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
     typedef Lay<VAR, KIN, AIR> L;
     typedef Lay<VAR, KIN, false> LF;
     constexpr int NX = L::NX;
+    constexpr bool LEGACY_REC = AIR && VAR == FB_C172X1;   // see EnsembleDev::handover_rel (the C172S kernels are faster without it: cfg 2 2.03e9 against 1.91e9)
     extern __shared__ __align__(16) double smem[];
     double* smem_tb = smem;
     constexpr int T = StepShape<VAR, KIN, AIR, CAP>::T;
@@ -351,10 +357,10 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
         pending = (d0 & FB_RESUME_PENDING) != 0;
         step0 += d0 & (FB_RESUME_PENDING - 1); n_steps -= d0 & (FB_RESUME_PENDING - 1);
     } else if (status != FB_ST_RUNNING) {
+        if (LEGACY_REC) E.handover_rel[i] = -1;
         break;
-    }
-    // with the complete kernel: handed over by an earlier launch, or in an earlier chunk of this one
-    else if (AIR && (own[i] & FB_OWN_SIDE)) break;
+    } else if (LEGACY_REC && ck > 0 && E.handover_rel[i] >= 0) break;   // handed over in an earlier chunk of this launch
+    else if (AIR && (own[i] & FB_OWN_SIDE)) break;               // with the complete kernel since an earlier launch
     MemberIn ug; ug.u = E.u + i; ug.pitch = E.pitch;
     double* sx = smem + TBL / 8 + threadIdx.x;
     double* sacc = sx + NX * T;
@@ -530,6 +536,7 @@ step_kernel(EnsembleDev E, long long step0_launch, int n_steps_launch, double dt
     if (VAR == FB_C172X1) cs.store(E.ctl + ie, E.pitch);
     // (the state above is written before the ownership word: whoever reads the word as handed over finds the state it describes)
     if (AIR) {
+        if (LEGACY_REC) E.handover_rel[ie] = handover;
         if (handover >= 0) own_publish(own, ie, step0_launch, handover, ground_count);
     } else if (resume_mode) { if (status == FB_ST_RUNNING) own_publish(own, ie, step0_launch, n_steps_launch, nullptr); }
     else if (gnd_seen) atomicAdd(ground_count, 1u);

@@ -331,6 +331,7 @@ static int32_t create_body(fb_sim* s) {
     if (const char* k = getenv("FLIGHTBATCH_KERNEL")) s->force_complete = (strcmp(k, "complete") == 0);
     if (cfg->variant == FB_C172XA2) s->force_complete = true;   // the non-default components exist in the complete kernel only
     if (s->force_complete) s->air_mode = false;
+    CK(cudaMalloc(&s->E.handover_rel, sizeof(int) * s->pitch));
     CK(cudaMalloc(&s->d_own, sizeof(long long) * s->pitch));
     CK(cudaMemsetAsync(s->d_own, 0, sizeof(long long) * s->pitch, s->stream));
     CK(cudaMalloc(&s->d_side, sizeof(unsigned)));
@@ -370,7 +371,7 @@ int32_t fb_destroy(fb_handle s) {
     cudaFree(s->d_ev_off); cudaFree(s->d_ev_step); cudaFree(s->d_ev_field); cudaFree(s->d_ev_value); cudaFree(s->d_ev_cursor);
     cudaFree(s->d_log_fields); cudaFree(s->d_scratch); cudaFree(s->d_rhs_count);
     if (s->air_done) cudaEventDestroy(s->air_done); if (s->side_done) cudaEventDestroy(s->side_done);
-    cudaFree(s->d_own); cudaFree(s->d_side); cudaFree(s->d_queue_c); cudaFree(s->d_hint); if (s->h_hint) cudaFreeHost(s->h_hint); if (s->hint_ev) cudaEventDestroy(s->hint_ev); cudaFree(s->d_ground); cudaFree(s->d_queue); if (s->h_ground) cudaFreeHost(s->h_ground); if (s->ground_ev) cudaEventDestroy(s->ground_ev);
+    cudaFree(E.handover_rel); cudaFree(s->d_own); cudaFree(s->d_side); cudaFree(s->d_queue_c); cudaFree(s->d_hint); if (s->h_hint) cudaFreeHost(s->h_hint); if (s->hint_ev) cudaEventDestroy(s->hint_ev); cudaFree(s->d_ground); cudaFree(s->d_queue); if (s->h_ground) cudaFreeHost(s->h_ground); if (s->ground_ev) cudaEventDestroy(s->ground_ev);
     if (s->comm_stream) cudaStreamSynchronize(s->comm_stream);
     if (s->comm && s->comm_owned && nccl_api()) nccl_api()->CommDestroy(s->comm);
     for (auto& t : s->comm_timers) { cudaEventDestroy(t.first); cudaEventDestroy(t.second); }
