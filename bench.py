@@ -574,7 +574,7 @@ def main():
                        "l2": "flushed between timed steps (256 MiB write outside the event pair); the kernel is FP64-issue bound, not memory bound",
                        "timing": "CUDA events on the library's launch stream, sum over steps, max over ranks", "wall_s": wall_s,
                        "ms_per_step_min_max": [min(ms), max(ms)],
-                       "launches_per_step": "2: airborne-layout kernel + hand-over pass of the complete kernel (returns at once when no member is near the terrain)"},
+                       "launches_per_step": "2: airborne-layout kernel + the hand-over pass of the complete kernel, pipelined on the library's side stream (148 CTAs that return at once while no member is near the terrain)"},
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": int(launches),
