@@ -1016,6 +1016,7 @@ static int32_t stats_allreduce_pre(fb_sim* s, long long* upto) {
     CK(cudaSetDevice(s->cfg.device));
     CK(cudaEventRecord(s->comm_in, s->stream));                 // the samples are final once the launches so far have run
     CK(cudaStreamWaitEvent(s->comm_stream, s->comm_in, 0));
+    if (s->side_active) CK(cudaStreamWaitEvent(s->comm_stream, s->side_done, 0));   // ... and the hand-over passes so far (no join: stepping goes on)
     if (s->mom_pending) CK(cudaStreamWaitEvent(s->comm_stream, s->mom_done, 0));   // a fetch in flight reads the same arrays
     cudaEvent_t t0, t1;
     CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
@@ -1034,7 +1035,6 @@ static int32_t stats_allreduce_post(fb_sim* s, long long upto) {
 
 int32_t fb_log_stats_allreduce(fb_handle s) {
     if (!s) return fail(FB_ERR_ARG, "null handle");
-    JOIN(s);
     long long upto = 0;
     int32_t rc = stats_allreduce_pre(s, &upto);
     if (rc != FB_OK || upto <= s->reduced_upto) return rc;
