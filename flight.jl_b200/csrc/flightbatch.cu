@@ -732,8 +732,14 @@ static int32_t advance(fb_sim* s, long long n) {
                 s->air_mode = air;
             } else (void)cudaGetLastError();   // cudaErrorNotReady is not an error: keep it out of the next launch check
         }
-        if (s->hint_pending && cudaEventQuery(s->hint_ev) == cudaSuccess) { s->hint_pending = false; if (*s->h_hint > 0) s->side_seen = true; }
-        else if (s->hint_pending) (void)cudaGetLastError();
+        if (s->hint_pending && cudaEventQuery(s->hint_ev) == cudaSuccess) {
+            // the look at the initial state has arrived: it stands in for the first hand-over counts (same 1/8 rule: an ensemble
+            // that starts on the runway goes to the complete kernel alone from its first launch — cfg 4: 7.5e8 against 7.1e8)
+            s->hint_pending = false;
+            if (*s->h_hint > 0) s->side_seen = true;
+            const bool air = !s->force_complete && (long long)*s->h_hint * 8 <= s->E.n;
+            if (air != s->air_mode && !s->ground_ev_pending) { if (int32_t rc = join(s)) return rc; s->air_mode = air; }
+        } else if (s->hint_pending) (void)cudaGetLastError();
         // a member that has climbed away stays with the (slower) complete kernel until a join returns it: inside a long run
         // without reads, join every eighth launch
         if (s->air_mode && s->launches_since_join >= 8) { if (int32_t rc = join(s)) return rc; }
