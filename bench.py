@@ -564,7 +564,12 @@ def main():
                 prof = json.load(open(ppath))
             except Exception:
                 prof = {}
-        state_bytes = (2 * nx_state * 8 + 40 * 8) * n   # state in + out, inputs read: per launch of 100 steps
+        # Algorithmic HBM bytes per member and launch of 100 fused steps: state in + out; the input rows the variant reads (27 for
+        # C172S; + 7 actuator commands, 19 control-law and 9 guidance inputs for the fly-by-wire variants) and, there, the 7
+        # commands written back and the 48 rows of controller memory in + out; ~40 B of discrete state, status, event cursor and
+        # ownership word. (The measured DRAM traffic of the cfg-3 launch is 1.5x this: the 14 tap rows and partially used sectors.)
+        ctl_variant = wl.name == "cfg3"
+        state_bytes = (2 * nx_state * 8 + (62 if ctl_variant else 27) * 8 + (7 * 8 + 2 * 48 * 8 if ctl_variant else 0) + 40) * n
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": 1e3 * dev_s / K, "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None,
