@@ -264,3 +264,30 @@ def test_julia_ccalls_match_the_header_prototypes():
     code = re.sub(r'^"[^"\n]*"$', "", code, flags=re.M)                     # one-line docstrings
     for f in set(re.findall(r"\bsim\.(\w+)", code)):
         assert f in sim_fields | {"t", "x"}, f"BatchSimulation has no field {f}"
+
+
+def test_julia_enums_follow_the_header(fb):
+    """The Julia mirror's `Variant` / `KinematicsKind` enums and the input / output ids it names must be the header's values
+    (the mirror is never executed in this image)."""
+    txt = open(os.path.join(ROOT, "flight.jl_b200", "julia", "BatchSimulation.jl")).read()
+    var = dict(re.findall(r"(C172\w+) = (\d+)", re.search(r"@enum Variant::Int32 ([^\n#]*)", txt).group(1)))
+    assert {k: int(v) for k, v in var.items()} == {"C172S": fb.DEFS["FB_C172S"], "C172X0": fb.DEFS["FB_C172X0"], "C172X1": fb.DEFS["FB_C172X1"],
+                                                   "C172X2": fb.DEFS["FB_C172X2"], "C172XA2": fb.DEFS["FB_C172XA2"]}
+    kin = dict(re.findall(r"(\w+) = (\d+)", re.search(r"@enum KinematicsKind::Int32 ([^\n#]*)", txt).group(1)))
+    assert {k: int(v) for k, v in kin.items()} == {"WA": fb.DEFS["FB_WA"], "ECEF": fb.DEFS["FB_ECEF"], "NED": fb.DEFS["FB_NED"]}
+    for name, val in re.findall(r"const (FB_[UY]_\w+) = Int32\((\d+)\)", txt):
+        table = fb.U if name.startswith("FB_U_") else fb.Y
+        assert table[name] == int(val), name
+
+
+def test_table_blob_holds_the_variable_pitch_sections():
+    """The FB_C172XA2 variant's VariablePitch Lookup travels in the same blob (prop.tables3 [21][21][n][6] + prop.pitch3)."""
+    import struct
+    b = open(os.path.join(ROOT, "flight.jl_b200", "data", "c172_tables.bin"), "rb").read()
+    n = struct.unpack_from("<I", b, 8)[0]
+    secs = {}
+    for i in range(n):
+        nm, dt, nd, d0, d1, d2, d3, off, nb = struct.unpack_from("<24sII4IQQ", b, 16 + 64 * i)
+        secs[nm.rstrip(b"\0").decode()] = ([d0, d1, d2, d3][:nd], nb)
+    assert secs["prop.tables3"][0][:2] == [21, 21] and secs["prop.tables3"][0][3] == 6
+    assert secs["prop.tables3"][1] == 21 * 21 * secs["prop.tables3"][0][2] * 6 * 8 and secs["prop.pitch3"][1] == 16

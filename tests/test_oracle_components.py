@@ -146,3 +146,26 @@ def test_blob_holds_the_variable_pitch_table_of_the_reference_test_case(orc):
     assert np.allclose(t, s.prop3(), rtol=1e-9, atol=1e-12)
     # monotone in pitch where the blade is not stalled: static thrust coefficient grows with delta_beta (test_propellers.jl:165)
     assert (np.diff(t[10, 5, :, 0]) > 0).all()
+
+
+def test_actuator2_variant_on_every_kinematic_mechanisation(orc, fb):
+    """The component variant over WA / ECEF / NED (kinematics.jl:150,250,329): same trim, and after 5 s with an elevator command
+    step through the second-order unit the three descriptions agree on attitude, altitude and airspeed like the reference's
+    own kinematics test demands of them (test_kinematics.jl:75-93), with identical actuator states."""
+    sims = []
+    for kin in (0, 1, 2):
+        s = orc.Sim(variant=VAR_A2, kin=kin, dt=0.01, prop_pitch=(-0.1, 0.2))
+        s.set_input(fb.U["FB_U_PROP_PITCH"], 0.2)
+        ok, ts, cost = s.init_trim(EAS=42.0, h_e=900.0, psi_nb=0.7, lat=0.6, lon=-0.4)
+        assert ok and cost < 1e-16
+        s.set_input(fb.U["FB_U_ACT_ELEVATOR"], s.get_input(fb.U["FB_U_ACT_ELEVATOR"]) + 0.08)
+        s.step(500)
+        sims.append((s, ts))
+    assert s.nx == 38 and sims[0][0].nx == 41 and sims[1][0].nx == 40
+    ref, ts0 = sims[0]
+    for s, ts in sims[1:]:
+        assert np.allclose(ts, ts0, rtol=0, atol=1e-9)
+        assert np.allclose(s.x[12:26], ref.x[12:26], rtol=0, atol=1e-12)                    # the units see nothing but their commands
+        for f, tol in (("FB_Y_THETA", 1e-7), ("FB_Y_PHI", 1e-7), ("FB_Y_H_E", 1e-4), ("FB_Y_EAS", 1e-6), ("FB_Y_PROP_DBETA", 0.0)):
+            assert abs(s.y(fb.Y[f]) - ref.y(fb.Y[f])) <= tol, (f, s.y(fb.Y[f]), ref.y(fb.Y[f]))
+    assert abs(ref.y(fb.Y["FB_Y_PROP_DBETA"]) - (-0.1 + 0.3 * 0.2)) < 1e-15
