@@ -14,7 +14,8 @@
 module BatchSimulations
 
 export BatchSimulation, state_async!, wait_state, FlightBatchError, init!, step!, run!, setinput!, getinput, getoutput, schedule_inputs!, set_segment!, BatchTimeSeries, BatchLinearizedSS, getstate, getinputs, getoutputs, setinputs!, setstate!,
-       status, stats, linearize, TimeSeriesColumn, log_stats, comm_unique_id, comm_init!, log_stats_allreduce!
+       status, stats, linearize, TimeSeriesColumn, log_stats, comm_unique_id, comm_init!, log_stats_allreduce!,
+       BatchGroup, shard, sync, group_size
 
 const libflightbatch = get(ENV, "FLIGHTBATCH_LIB", joinpath(@__DIR__, "..", "libflightbatch.so"))
 const tables_path = get(ENV, "FLIGHTBATCH_TABLES", joinpath(@__DIR__, "..", "data", "c172_tables.bin"))
@@ -338,5 +339,79 @@ function getoutputs(lss::BatchLinearizedSS)
 end
 setinputs!(lss::BatchLinearizedSS, u::Matrix{Float64}) = check(ccall((:fb_lss_set_input, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{Float64}), lss.handle, u))
 setstate!(lss::BatchLinearizedSS, x::Matrix{Float64}) = check(ccall((:fb_lss_set_state, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{Float64}), lss.handle, x))
+
+################################################################################
+# BatchGroup: ONE Julia process driving several GPUs (fb_group_*, include/flightbatch.h). The ensemble is sharded in contiguous
+# blocks over `devices`; host arrays are GLOBAL (N_total × columns), the library scatters / gathers the shards, steps them
+# concurrently and all-reduces the ensemble moments over its own NCCL communicator: no MPI, no Distributed.jl needed.
+
+mutable struct BatchGroup
+    handle::Ptr{Cvoid}
+    n::Int
+    nx::Int
+    dt::Float64
+    n_dev::Int
+    function BatchGroup(variant::Variant, kin::KinematicsKind, n::Integer, devices::AbstractVector{<:Integer};
+                        dt = 0.02, Δt = dt, t_start = 0.0, t_end = 10000.0, saveat = nothing, log_fields = Int32[],
+                        steps_per_launch = 0, log_flags = 0, prop_pitch = nothing, act2 = (0.0, 0.0))
+        lf = ntuple(i -> i <= length(log_fields) ? Int32(log_fields[i]) : Int32(0), 32)
+        log_every = (saveat === nothing || isempty(log_fields)) ? 0 : max(1, round(Int, saveat / dt))
+        cfg = Ref(FbConfig(Int32(variant), Int32(kin), n, 0, dt, Δt, t_start, t_end, 0, log_every,
+                           length(log_fields), lf, steps_per_launch, log_flags,
+                           prop_pitch === nothing ? 0 : prop_pitch[3], 0, prop_pitch === nothing ? 0.0 : prop_pitch[1],
+                           prop_pitch === nothing ? 0.0 : prop_pitch[2], act2[1], act2[2]))
+        dev = Vector{Int32}(devices)
+        g = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:fb_group_create, libflightbatch), Int32, (Ref{FbConfig}, Ptr{Int32}, Int32, Ref{Ptr{Cvoid}}), cfg, dev, length(dev), g))
+        blob = read(tables_path)
+        GC.@preserve blob check(ccall((:fb_group_load_tables, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Csize_t), g[], blob, length(blob)))
+        h = Ref{Ptr{Cvoid}}(C_NULL); off = Ref{Int64}(0); cnt = Ref{Int64}(0); nx = Ref{Int32}(0)
+        check(ccall((:fb_group_shard, libflightbatch), Int32, (Ptr{Cvoid}, Int32, Ref{Ptr{Cvoid}}, Ref{Int64}, Ref{Int64}), g[], 0, h, off, cnt))
+        check(ccall((:fb_nx, libflightbatch), Int32, (Ptr{Cvoid}, Ref{Int32}), h[], nx))
+        grp = new(g[], n, nx[], dt, length(dev))
+        finalizer(x -> (x.handle != C_NULL && ccall((:fb_group_destroy, libflightbatch), Int32, (Ptr{Cvoid},), x.handle); x.handle = C_NULL), grp)
+    end
+end
+
+"(handle, offset, count) of shard `k` (0-based): everything the per-shard `fb_*` entry points offer, on shard-local arrays"
+function shard(grp::BatchGroup, k::Integer)
+    h = Ref{Ptr{Cvoid}}(C_NULL); off = Ref{Int64}(0); cnt = Ref{Int64}(0)
+    check(ccall((:fb_group_shard, libflightbatch), Int32, (Ptr{Cvoid}, Int32, Ref{Ptr{Cvoid}}, Ref{Int64}, Ref{Int64}), grp.handle, k, h, off, cnt))
+    (h[], Int(off[]), Int(cnt[]))
+end
+
+"init!(grp; EAS = ..., h_e = ...): `init!(sim, C172.TrimParameters(...))` for every member of the sharded ensemble (global columns)"
+function init!(grp::BatchGroup; kw...)
+    cols = Dict(k => (v isa Real ? fill(Float64(v), grp.n) : Vector{Float64}(v)) for (k, v) in kw)
+    ptrs = [haskey(cols, f) ? pointer(cols[f]) : Ptr{Float64}(C_NULL) for f in TRIM_FIELDS]
+    ts = Matrix{Float64}(undef, grp.n, 7); cost = Vector{Float64}(undef, grp.n)
+    GC.@preserve cols ptrs check(ccall((:fb_group_init_trim, libflightbatch), Int32,
+        (Ptr{Cvoid}, Ptr{Ptr{Float64}}, Ptr{Float64}, Ptr{Float64}), grp.handle, ptrs, ts, cost))
+    (status(grp) .!= 6, ts, cost)
+end
+step!(grp::BatchGroup, Δt::Real = grp.dt) = check(ccall((:fb_group_step, libflightbatch), Int32, (Ptr{Cvoid}, Float64), grp.handle, Δt))
+run!(grp::BatchGroup) = check(ccall((:fb_group_run, libflightbatch), Int32, (Ptr{Cvoid},), grp.handle))
+sync(grp::BatchGroup) = check(ccall((:fb_group_sync, libflightbatch), Int32, (Ptr{Cvoid},), grp.handle))
+function setinput!(grp::BatchGroup, field::Integer, v)
+    col = v isa Real ? [Float64(v)] : Vector{Float64}(v)
+    check(ccall((:fb_group_set_input, libflightbatch), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64), grp.handle, field, col, v isa Real ? 0 : 1))
+end
+function getstate(grp::BatchGroup)
+    x = Matrix{Float64}(undef, grp.n, grp.nx)
+    check(ccall((:fb_group_get_state, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{Float64}), grp.handle, x)); x
+end
+function status(grp::BatchGroup)
+    st = Vector{Int32}(undef, grp.n)
+    check(ccall((:fb_group_status, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{Int32}), grp.handle, st)); st
+end
+"ensemble moments (all shards, all-reduced over NCCL inside the library) of a logged field at samples `first .. first + count - 1`"
+function log_stats(grp::BatchGroup, field::Integer, first::Integer, count::Integer)
+    m = Vector{Moments}(undef, count)
+    check(ccall((:fb_group_log_stats, libflightbatch), Int32, (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Moments}), grp.handle, field, first, count, m)); m
+end
+function group_size(grp::BatchGroup)
+    n = Ref{Int32}(0)
+    check(ccall((:fb_group_size, libflightbatch), Int32, (Ptr{Cvoid}, Ref{Int32}), grp.handle, n)); Int(n[])
+end
 
 end # module
