@@ -15,7 +15,7 @@ module BatchSimulations
 
 export BatchSimulation, state_async!, wait_state, FlightBatchError, init!, step!, run!, setinput!, getinput, getoutput, schedule_inputs!, set_segment!, BatchTimeSeries, BatchLinearizedSS, getstate, getinputs, getoutputs, setinputs!, setstate!,
        status, stats, linearize, TimeSeriesColumn, log_stats, comm_unique_id, comm_init!, log_stats_allreduce!,
-       BatchGroup, shard, sync, group_size
+       BatchGroup, shard, group_size
 
 const libflightbatch = get(ENV, "FLIGHTBATCH_LIB", joinpath(@__DIR__, "..", "libflightbatch.so"))
 const tables_path = get(ENV, "FLIGHTBATCH_TABLES", joinpath(@__DIR__, "..", "data", "c172_tables.bin"))
@@ -391,7 +391,7 @@ function init!(grp::BatchGroup; kw...)
 end
 step!(grp::BatchGroup, Δt::Real = grp.dt) = check(ccall((:fb_group_step, libflightbatch), Int32, (Ptr{Cvoid}, Float64), grp.handle, Δt))
 run!(grp::BatchGroup) = check(ccall((:fb_group_run, libflightbatch), Int32, (Ptr{Cvoid},), grp.handle))
-sync(grp::BatchGroup) = check(ccall((:fb_group_sync, libflightbatch), Int32, (Ptr{Cvoid},), grp.handle))
+Base.wait(grp::BatchGroup) = check(ccall((:fb_group_sync, libflightbatch), Int32, (Ptr{Cvoid},), grp.handle))   # as for BatchSimulation
 function setinput!(grp::BatchGroup, field::Integer, v)
     col = v isa Real ? [Float64(v)] : Vector{Float64}(v)
     check(ccall((:fb_group_set_input, libflightbatch), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64), grp.handle, field, col, v isa Real ? 0 : 1))
