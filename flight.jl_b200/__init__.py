@@ -95,7 +95,7 @@ class fb_moments(C.Structure):
 
 EXPORTS = ["fb_api_version", "fb_last_error", "fb_create", "fb_load_tables", "fb_destroy", "fb_sync", "fb_init_trim", "fb_init",
            "fb_init_state", "fb_set_input", "fb_get_input", "fb_schedule_inputs", "fb_step", "fb_run", "fb_time", "fb_nx",
-           "fb_get_state", "fb_get_state_async", "fb_wait_state", "fb_get_discrete", "fb_get_output", "fb_status", "fb_log_info", "fb_log_times", "fb_log_fetch",
+           "fb_get_state", "fb_get_state_async", "fb_wait_state", "fb_get_discrete", "fb_get_output", "fb_status", "fb_release_trim_failed", "fb_log_info", "fb_log_times", "fb_log_fetch",
            "fb_stats", "fb_log_stats_begin", "fb_log_stats_end", "fb_log_stats", "fb_comm_unique_id", "fb_comm_init", "fb_log_stats_allreduce", "fb_comm_time",
            "fb_group_create", "fb_group_destroy", "fb_group_size", "fb_group_shard", "fb_group_load_tables", "fb_group_init_trim", "fb_group_set_input",
            "fb_group_step", "fb_group_run", "fb_group_sync", "fb_group_get_state", "fb_group_status", "fb_group_log_stats", "fb_rhs", "fb_fstep", "fb_fperiodic", "fb_counters", "fb_linearize", "fb_linearize_dims", "fb_device_state", "fb_stream", "fb_measure_fp64_peak",
@@ -140,6 +140,7 @@ def load_library():
         "fb_step": (i32, [vp, dbl]), "fb_run": (i32, [vp]), "fb_time": (i32, [vp, _DP, C.POINTER(i64)]),
         "fb_nx": (i32, [vp, C.POINTER(i32)]), "fb_get_state": (i32, [vp, _DP]), "fb_get_state_async": (i32, [vp, _DP]), "fb_wait_state": (i32, [vp]), "fb_get_discrete": (i32, [vp, u8p, u8p]),
         "fb_get_output": (i32, [vp, i32, _DP]), "fb_status": (i32, [vp, C.POINTER(i32)]),
+        "fb_release_trim_failed": (i32, [vp, C.POINTER(i64)]),
         "fb_log_info": (i32, [vp, C.POINTER(i64), C.POINTER(i32)]), "fb_log_times": (i32, [vp, _DP]),
         "fb_log_fetch": (i32, [vp, i32, _DP]), "fb_stats": (i32, [vp, i32, C.POINTER(fb_moments)]),
         "fb_rhs": (i32, [vp, _DP]), "fb_fstep": (i32, [vp, C.POINTER(i32)]), "fb_fperiodic": (i32, [vp]), "fb_counters": (i32, [vp, C.POINTER(i64), C.POINTER(i64)]),
@@ -624,6 +625,13 @@ class BatchSimulation:
         out = np.zeros(self.n, dtype=np.int32)
         _ck(self._lib.fb_status(self._h, out.ctypes.data_as(C.POINTER(C.c_int32))), self._lib)
         return out
+
+    def release_trim_failed(self):
+        """The reference's handling of a failed trim (c172.jl:934-940): warn, keep the best trim state found, go on simulating.
+        Members frozen with FB_ST_TRIM_FAILED become RUNNING again; returns how many."""
+        n = C.c_int64(0)
+        _ck(self._lib.fb_release_trim_failed(self._h, C.byref(n)), self._lib)
+        return int(n.value)
 
     def get_output(self, field):
         field = OUTPUT_NAMES[field] if isinstance(field, str) else int(field)

@@ -607,6 +607,26 @@ int32_t fb_init_trim(fb_handle s, const fb_trim_params_soa* p, double* trim_stat
     return after_init(s, true);
 }
 
+__global__ void release_trim_failed_kernel(int* status, long long n, unsigned* count) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && status[i] == FB_ST_TRIM_FAILED) { status[i] = FB_ST_RUNNING; atomicAdd(count, 1u); }
+}
+int32_t fb_release_trim_failed(fb_handle s, int64_t* n_released) {
+    if (!s) return fail(FB_ERR_ARG, "null handle");
+    JOIN(s);
+    if (!s->initialised) return fail(FB_ERR_STATE, "fb_release_trim_failed: not initialised");
+    CK(cudaSetDevice(s->cfg.device));
+    unsigned* d_n = reinterpret_cast<unsigned*>(s->d_scratch);
+    CK(cudaMemsetAsync(d_n, 0, sizeof(unsigned), s->stream));
+    release_trim_failed_kernel<<<(int)((s->E.n + 255) / 256), 256, 0, s->stream>>>(s->E.status, s->E.n, d_n);
+    CK(cudaGetLastError());
+    unsigned h_n = 0;
+    CK(cudaMemcpyAsync(&h_n, d_n, sizeof(unsigned), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    if (n_released) *n_released = (int64_t)h_n;
+    return FB_OK;
+}
+
 int32_t fb_init(fb_handle s, const fb_init_soa* ic) {
     if (!s) return fail(FB_ERR_ARG, "null handle");
     JOIN(s);

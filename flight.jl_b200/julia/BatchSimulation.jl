@@ -15,7 +15,7 @@ module BatchSimulations
 
 export BatchSimulation, state_async!, wait_state, FlightBatchError, init!, step!, run!, setinput!, getinput, getoutput, schedule_inputs!, set_segment!, BatchTimeSeries, BatchLinearizedSS, getstate, getinputs, getoutputs, setinputs!, setstate!,
        status, stats, linearize, TimeSeriesColumn, log_stats, comm_unique_id, comm_init!, log_stats_allreduce!,
-       BatchGroup, shard, group_size
+       BatchGroup, shard, group_size, release_trim_failed!
 
 const libflightbatch = get(ENV, "FLIGHTBATCH_LIB", joinpath(@__DIR__, "..", "libflightbatch.so"))
 const tables_path = get(ENV, "FLIGHTBATCH_TABLES", joinpath(@__DIR__, "..", "data", "c172_tables.bin"))
@@ -188,6 +188,11 @@ function schedule_inputs!(sim::BatchSimulation, member::Vector{Int64}, step::Vec
                 sim.handle, n, member, step, field, value))
 end
 
+"release_trim_failed!(sim): the reference's own handling of a failed trim (warn, keep the best state found, go on, c172.jl:934-940); returns the number of members released"
+function release_trim_failed!(sim::BatchSimulation)
+    n = Ref{Int64}(0)
+    check(ccall((:fb_release_trim_failed, libflightbatch), Int32, (Ptr{Cvoid}, Ref{Int64}), sim.handle, n)); Int(n[])
+end
 function status(sim::BatchSimulation)
     st = Vector{Int32}(undef, sim.n)
     check(ccall((:fb_status, libflightbatch), Int32, (Ptr{Cvoid}, Ptr{Int32}), sim.handle, st)); st

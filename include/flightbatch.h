@@ -212,6 +212,9 @@ int32_t fb_sync(fb_handle h);
  * (damped Newton to 1e-26 here, NLopt BOBYQA stopping at 1e-16 there): trim states agree with the reference's stored
  * trims to ~1e-7 (tests/golden/trim_points.json), which is the optimiser's own stopping distance. */
 int32_t fb_init_trim(fb_handle h, const fb_trim_params_soa* p, double* trim_state_out, double* cost_out);
+/* The reference's own handling of a failed trim (c172.jl:934-940: warn, keep the best trim state found, go on simulating):
+ * every member with FB_ST_TRIM_FAILED goes back to FB_ST_RUNNING from the state the solver left it in. n_released may be NULL. */
+int32_t fb_release_trim_failed(fb_handle h, int64_t* n_released);
 /* init!(sim, C172.Init(kin, sys)) : aircraftbase.jl:76-86 */
 int32_t fb_init(fb_handle h, const fb_init_soa* ic);
 /* raw state injection (mdl.x, aero.s.stall, engine.s[]) followed by the reinit! RHS evaluation */

@@ -72,6 +72,7 @@ static int null_calls(void) {
     EXPECT(fb_get_discrete(NULL, u8, u8) == FB_ERR_ARG, "fb_get_discrete");
     EXPECT(fb_get_output(NULL, 0, buf) == FB_ERR_ARG, "fb_get_output");
     EXPECT(fb_status(NULL, &i32) == FB_ERR_ARG, "fb_status");
+    EXPECT(fb_release_trim_failed(NULL, NULL) == FB_ERR_ARG, "fb_release_trim_failed");
     EXPECT(fb_log_info(NULL, &i64, &i32) == FB_ERR_ARG, "fb_log_info");
     EXPECT(fb_log_times(NULL, buf) == FB_ERR_ARG, "fb_log_times");
     EXPECT(fb_log_fetch(NULL, 0, buf) == FB_ERR_ARG, "fb_log_fetch");

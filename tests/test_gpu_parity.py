@@ -139,6 +139,14 @@ def test_infeasible_trim_is_flagged_like_the_oracle(fb, orc):
         assert bool(ok[i]) == ok_o
         assert (st[i] == fb.FB_ST_TRIM_FAILED) == (not ok_o)
     assert not ok.all() and ok.any()
+    # the reference itself only warns and goes on from the best trim state found (c172.jl:934-940): release_trim_failed gives that
+    x0 = sim.x.copy()
+    sim.step(0.2)
+    assert np.array_equal(sim.x[:, ~ok], x0[:, ~ok])                      # frozen until released
+    assert sim.release_trim_failed() == int((~ok).sum()) and (sim.status() == 0).all()
+    sim.step(0.2)
+    x1 = sim.x
+    assert (np.abs(x1[:, ~ok] - x0[:, ~ok]).max(axis=0) > 0).all() and np.isfinite(x1).all()
     sim.close()
 
 
