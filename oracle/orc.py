@@ -90,6 +90,7 @@ def _load(name):
         "orc_gain_lookup": (i32, [i32, dbl, dbl, dp]),
         "orc_geo_roundtrip": (None, [dbl, dbl, dbl, dp]),
         "orc_lss_step": (None, [i32, i32, dp, dp, dp, dp, dp, dp, dp, dbl, i64]),
+        "orc_lss_rhs": (None, [i32, i32, i32, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp]),
         "orc_segment_end": (None, [dbl, dbl, dbl, dbl, dbl, dbl, dp]),
         "orc_segment_data": (None, [dp, dp, dp, dp]),
         "orc_segment_valid": (i32, [dp, dp]),
@@ -331,6 +332,15 @@ def gain_lookup(which, EAS, h):
     out = np.zeros(64)
     n = lib().orc_gain_lookup(int(which), float(EAS), float(h), _dp(out))
     return out[:n]
+
+
+def lss_rhs(A, B, Cm, D, xdot0, x0, u0, y0, x, u):
+    """LinearizedSS f_ode! (linearization.jl:164-190): returns (xdot, y)"""
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    A, B, Cm, D, xdot0, x0, u0, y0, x, u = map(f, (A, B, Cm, D, xdot0, x0, u0, y0, x, u))
+    xd, y = np.zeros(A.shape[0]), np.zeros(Cm.shape[0])
+    lib().orc_lss_rhs(A.shape[0], B.shape[1], Cm.shape[0], _dp(A), _dp(B), _dp(Cm), _dp(D), _dp(xdot0), _dp(x0), _dp(u0), _dp(y0), _dp(x), _dp(u), _dp(xd), _dp(y))
+    return xd, y
 
 
 def lss_step(A, B, x0, u0, xdot0, x, u, dt, n_steps):

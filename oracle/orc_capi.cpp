@@ -520,6 +520,22 @@ void orc_lss_step(int nx, int nu, const double* A, const double* B, const double
     }
 }
 
+// LinearizedSS f_ode! alone (linearization.jl:164-190), in the reference's order: dx = x - x0, du = u - u0; xdot = xdot0, += A dx,
+// += B du; y = y0, += C dx, += D du. Row-major matrices. (Known answers: test_linearization.jl:27-45.)
+void orc_lss_rhs(int nx, int nu, int ny, const double* A, const double* B, const double* C, const double* D, const double* xd0,
+                 const double* x0, const double* u0, const double* y0, const double* x, const double* u, double* xdot, double* y) {
+    std::vector<double> dx(nx), du(nu);
+    for (int i = 0; i < nx; i++) dx[i] = x[i] - x0[i];
+    for (int i = 0; i < nu; i++) du[i] = u[i] - u0[i];
+    auto mul_add = [](int n, int m, const double* M, const double* v, double* out) {
+        for (int i = 0; i < n; i++) { double a = 0.0; for (int j = 0; j < m; j++) a += M[i * m + j] * v[j]; out[i] += a; }
+    };
+    for (int i = 0; i < nx; i++) xdot[i] = xd0[i];
+    mul_add(nx, nx, A, dx.data(), xdot); mul_add(nx, nu, B, du.data(), xdot);
+    for (int i = 0; i < ny; i++) y[i] = y0[i];
+    mul_add(ny, nx, C, dx.data(), y); mul_add(ny, nu, D, du.data(), y);
+}
+
 void orc_ops_reset() {
 #if ORC_COUNT
     g_ops = OpCounts();

@@ -72,3 +72,24 @@ def test_linear_model_reproduces_a_small_elevator_step(orc, fb):
     theta_lin, theta_nl = np.array(theta_lin), np.array(theta_nl)
     assert np.abs(theta_nl).max() > 5e-3                                       # the step does something
     assert np.abs(theta_lin - theta_nl).max() < 0.05 * np.abs(theta_nl).max()   # and the linear model follows it
+
+
+def test_linearized_ss_known_answers_of_the_reference(orc):
+    """lib/FlightPhysics/test/test_linearization.jl:14-45 transcribed: a LinearizedSS built from x0 = (1, 0.5, 0.3, 5), u0 = (0.1,
+    0.2), y0 = (0.3, 0.8, 2, 3, -9.8) with xdot0 = x0, A = x0 x0', B = x0 u0', C = y0 x0', D = y0 u0', evaluated at x = 2 x0,
+    u = 3 u0, must give xdot = xdot0 + A (x - x0) + B (u - u0) and y = y0 + C (x - x0) + D (u - u0) — the reference asserts
+    `all(.==)`, i.e. its non-allocating update order reproduces the one-line formula exactly."""
+    x0 = np.array([1.0, 0.5, 0.3, 5.0]); u0 = np.array([0.1, 0.2]); y0 = np.array([0.3, 0.8, 2.0, 3.0, -9.8])
+    A, B, C, D = np.outer(x0, x0), np.outer(x0, u0), np.outer(y0, x0), np.outer(y0, u0)
+    x, u = 2 * x0, 3 * u0
+    xd, y = orc.lss_rhs(A, B, C, D, x0.copy(), x0, u0, y0, x, u)
+    # Julia's `xdot0 + A * (x - x0) + B * (u - u0)` is left-associative: (xdot0 + A dx) + B du
+    assert np.array_equal(xd, (x0 + A @ (x - x0)) + B @ (u - u0))
+    assert np.array_equal(y, (y0 + C @ (x - x0)) + D @ (u - u0))
+    # at the linearisation point the model returns xdot0 and y0 themselves
+    xd, y = orc.lss_rhs(A, B, C, D, x0.copy(), x0, u0, y0, x0, u0)
+    assert np.array_equal(xd, x0) and np.array_equal(y, y0)
+    # and the RK4 stepping of the same model (orc.lss_step) is consistent with it: one small step ~ x + dt f(x)
+    x1 = orc.lss_step(A, B, x0, u0, x0.copy(), x, u, 1e-6, 1)
+    f0, _ = orc.lss_rhs(A, B, C, D, x0.copy(), x0, u0, y0, x, u)
+    assert np.allclose((x1 - x) / 1e-6, f0, rtol=1e-4)
