@@ -90,6 +90,7 @@ def _load(name):
         "orc_gain_lookup": (i32, [i32, dbl, dbl, dp]),
         "orc_geo_roundtrip": (None, [dbl, dbl, dbl, dp]),
         "orc_lss_step": (None, [i32, i32, dp, dp, dp, dp, dp, dp, dp, dbl, i64]),
+        "orc_attitude_test": (None, [dp]),
         "orc_lss_rhs": (None, [i32, i32, i32, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp]),
         "orc_segment_end": (None, [dbl, dbl, dbl, dbl, dbl, dbl, dp]),
         "orc_segment_data": (None, [dp, dp, dp, dp]),
@@ -332,6 +333,13 @@ def gain_lookup(which, EAS, h):
     out = np.zeros(64)
     n = lib().orc_gain_lookup(int(which), float(EAS), float(h), _dp(out))
     return out[:n]
+
+
+def attitude_test():
+    """Residuals / values of the rotation-algebra known answers of test_attitude.jl (layout: orc_capi.cpp:orc_attitude_test)"""
+    out = np.zeros(36)
+    lib().orc_attitude_test(_dp(out))
+    return out
 
 
 def lss_rhs(A, B, Cm, D, xdot0, x0, u0, y0, x, u):

@@ -520,6 +520,54 @@ void orc_lss_step(int nx, int nu, const double* A, const double* B, const double
     }
 }
 
+// Rotation algebra known answers (lib/FlightPhysics/test/test_attitude.jl:29-82 RQuat, :182-240 REuler), evaluated with the
+// primitives every right-hand side uses (orc_math.hpp = attitude.jl:98-103,118,304-308,382-395; quaternions.jl:109-115).
+// out[0..2]   q_ab * (q_bc * x_c) - (q_ab o q_bc) * x_c          (:66)
+// out[3..5]   x_c - q_bc' * (q_bc * x_c)                          (:67)
+// out[6..9]   dt(q_ab, w) - 0.5 q_ab (x) (0, w)                   (:76)
+// out[10..12] w - omega(q_ab, qdot)                               (:78)
+// out[13..15] dt(REuler(phi = pi/2), (0,1,0))                     (:203, = (1,0,0))
+// out[16..18] dt(REuler(phi = pi), (0,1,0))                       (:204, = (0,-1,0))
+// out[19..21] dt(REuler(theta = pi/3, phi = pi/4), (1,0,0))       (:208, = (0,0,1))
+// out[22..24] dt(REuler(psi = pi/3, theta = pi/4), (-1,2,1)) - dt(REuler(psi = pi/6, theta = pi/4), (-1,2,1))   (:209, = 0)
+// out[25..27] w - omega(r_ab, dt(r_ab, w)), r_ab = REuler(-1.234, sqrt 2, sqrt 3), w = (2,-3.2,4)               (:213-215)
+// out[28]     worst |REuler - REuler(RQuat(REuler))| over the 10 x 10 x 10 angle lattice of :225-233 (gimbal lock avoided by 1e-3)
+// out[29..32] RQuat(REuler()) - (1,0,0,0)                          (:221)
+// out[33..35] r_ab * (r_bc * x_c) - (r_ab o r_bc) * x_c, r_bc = REuler(1.34, -sqrt 2, sqrt 2), x_c = (-1,2,3)    (:199)
+void orc_attitude_test(double* out) {
+    auto put3 = [&](int o, V3 v) { out[o] = val(v.x); out[o + 1] = val(v.y); out[o + 2] = val(v.z); };
+    Q4 q_ab = qnormalize(Q4(0.8, 0.1, 0.1, 0.3)), q_bc = qnormalize(Q4(0.2, -0.5, 0.6, 0.1));   // RQuat(v) normalises (attitude.jl:69-71)
+    V3 x_c(1.0, 2.0, 3.0);
+    put3(0, qrot(q_ab, qrot(q_bc, x_c)) - qrot(qmul(q_ab, q_bc), x_c));
+    put3(3, x_c - qrot(qconj(q_bc), qrot(q_bc, x_c)));
+    V3 w(10.0, -4.0, 2.0);
+    Q4 qd = qdt(q_ab, w);
+    Q4 h = qmul(q_ab, Q4(0.0, w.x, w.y, w.z));
+    out[6] = val(qd.w - 0.5 * h.w); out[7] = val(qd.x - 0.5 * h.x); out[8] = val(qd.y - 0.5 * h.y); out[9] = val(qd.z - 0.5 * h.z);
+    Q4 wq = qmul(qconj(q_ab), qd);                                            // omega = 2 Im(q' (x) qdot), attitude.jl:120-122
+    put3(10, w - V3(2.0 * wq.x, 2.0 * wq.y, 2.0 * wq.z));
+    put3(13, euler_dt(Euler(0.0, 0.0, ORC_PI / 2), V3(0.0, 1.0, 0.0)));
+    put3(16, euler_dt(Euler(0.0, 0.0, ORC_PI), V3(0.0, 1.0, 0.0)));
+    put3(19, euler_dt(Euler(0.0, ORC_PI / 3, ORC_PI / 4), V3(1.0, 0.0, 0.0)));
+    put3(22, euler_dt(Euler(ORC_PI / 3, ORC_PI / 4, 0.0), V3(-1.0, 2.0, 1.0)) - euler_dt(Euler(ORC_PI / 6, ORC_PI / 4, 0.0), V3(-1.0, 2.0, 1.0)));
+    Euler r_ab(-1.234, std::sqrt(2.0), std::sqrt(3.0)), r_bc(1.34, -std::sqrt(2.0), std::sqrt(2.0));
+    V3 w2(2.0, -3.2, 4.0);
+    put3(25, w2 - omega_from_euler_dt(r_ab, euler_dt(r_ab, w2)));
+    double worst = 0.0;
+    for (int i = 0; i < 10; i++) for (int j = 0; j < 10; j++) for (int k = 0; k < 10; k++) {
+        const double psi = -ORC_PI + 2 * ORC_PI * i / 9.0, th = -(ORC_PI / 2 - 0.001) + 2 * (ORC_PI / 2 - 0.001) * j / 9.0, phi = -ORC_PI + 2 * ORC_PI * k / 9.0;
+        Euler e = euler_from_q(q_from_euler(Euler(psi, th, phi)));
+        auto dang = [](double a, double b) { double d = std::fabs(a - b); return std::fmin(d, std::fabs(d - 2 * ORC_PI)); };   // psi, phi = +-pi are one rotation (:194-195)
+        worst = std::fmax(worst, std::fmax(dang(val(e.psi), psi), std::fmax(std::fabs(val(e.theta) - th), dang(val(e.phi), phi))));
+    }
+    out[28] = worst;
+    Q4 q0 = q_from_euler(Euler());
+    out[29] = val(q0.w) - 1.0; out[30] = val(q0.x); out[31] = val(q0.y); out[32] = val(q0.z);
+    V3 xc2(-1.0, 2.0, 3.0);
+    Q4 qa = q_from_euler(r_ab), qb = q_from_euler(r_bc);
+    put3(33, qrot(qa, qrot(qb, xc2)) - qrot(qmul(qa, qb), xc2));
+}
+
 // LinearizedSS f_ode! alone (linearization.jl:164-190), in the reference's order: dx = x - x0, du = u - u0; xdot = xdot0, += A dx,
 // += B du; y = y0, += C dx, += D du. Row-major matrices. (Known answers: test_linearization.jl:27-45.)
 void orc_lss_rhs(int nx, int nu, int ny, const double* A, const double* B, const double* C, const double* D, const double* xd0,

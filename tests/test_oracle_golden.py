@@ -203,3 +203,22 @@ def test_algorithmic_flop_count_on_the_ground(orc):
     orc.ops_reset(lc); s.step(100); t = orc.ops_get(lc)["total"] / 100
     a_step = 4 * r + (t - 5 * r)
     assert abs(a_step - bench.A_STEP_FLOP_GROUND) <= 0.01 * bench.A_STEP_FLOP_GROUND, (r, t, a_step)
+
+
+# ---- rotation algebra: lib/FlightPhysics/test/test_attitude.jl:29-82 (RQuat), :182-240 (REuler) ------------------------------
+def test_rotation_algebra_known_answers(orc):
+    """Composition, inversion, quaternion and Euler-angle kinematics with the primitives every right-hand side uses, on the
+    reference's own test values: transformation by a composed rotation = successive transformations (:66, :199), inverse (:67),
+    q' = 1/2 q (x) (0, w) and its inverse (:76-78), Euler rates at the reference's six sample attitudes (:203-209), the
+    Euler -> omega round trip (:213-215), Euler -> quaternion -> Euler over the 1,000-point angle lattice (:225-233)."""
+    o = orc.attitude_test()
+    assert np.abs(o[0:3]).max() < 1e-14 and np.abs(o[3:6]).max() < 1e-14 and np.abs(o[33:36]).max() < 1e-14
+    assert np.abs(o[6:10]).max() == 0.0                       # the reference asserts equality here (:76)
+    assert np.abs(o[10:13]).max() < 1e-13
+    assert np.allclose(o[13:16], [1.0, 0.0, 0.0], rtol=0, atol=1e-10)          # dt(REuler(phi = pi/2), (0, 1, 0)) = (1, 0, 0)
+    assert np.allclose(o[16:19], [0.0, -1.0, 0.0], rtol=0, atol=1e-10)         # dt(REuler(phi = pi), (0, 1, 0)) = (0, -1, 0)
+    assert np.allclose(o[19:22], [0.0, 0.0, 1.0], rtol=0, atol=1e-10)          # dt(REuler(theta = pi/3, phi = pi/4), (1, 0, 0)) = (0, 0, 1)
+    assert np.abs(o[22:25]).max() < 1e-14                                      # Euler rates do not depend on the heading
+    assert np.abs(o[25:28]).max() < 1e-13
+    assert o[28] < 1e-9                                                         # the reference's isapprox on the lattice
+    assert np.abs(o[29:33]).max() == 0.0                                        # RQuat(REuler()) = (1, 0, 0, 0)
