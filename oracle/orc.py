@@ -91,6 +91,8 @@ def _load(name):
         "orc_geo_roundtrip": (None, [dbl, dbl, dbl, dp]),
         "orc_lss_step": (None, [i32, i32, dp, dp, dp, dp, dp, dp, dp, dbl, i64]),
         "orc_attitude_test": (None, [dp]),
+        "orc_pid_run": (None, [dp, dp, dbl, i32, dbl, i64, dp]),
+        "orc_integ_run": (None, [dbl, dbl, dp, dbl, i32, dbl, i64, dp]),
         "orc_lss_rhs": (None, [i32, i32, i32, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp]),
         "orc_segment_end": (None, [dbl, dbl, dbl, dbl, dbl, dbl, dp]),
         "orc_segment_data": (None, [dp, dp, dp, dp]),
@@ -333,6 +335,40 @@ def gain_lookup(which, EAS, h):
     out = np.zeros(64)
     n = lib().orc_gain_lookup(int(which), float(EAS), float(h), _dp(out))
     return out[:n]
+
+
+class DiscretePID:
+    """PIDDiscrete (control.jl:370-471) in isolation: parameters as attributes, `run(input, sat_ext, Dt, n)` = n periodic updates,
+    returns PIDDiscreteY as a dict."""
+
+    def __init__(self, k_p=1.0, k_i=0.0, k_d=0.0, tau_f=0.01, lo=-np.inf, hi=np.inf):
+        self.k_p, self.k_i, self.k_d, self.tau_f, self.lo, self.hi = k_p, k_i, k_d, tau_f, lo, hi
+        self.st = np.zeros(3)
+
+    def init(self):
+        self.st[:] = 0.0
+
+    def run(self, input, sat_ext, Dt, n):
+        par = np.array([self.k_p, self.k_i, self.k_d, self.tau_f, self.lo, self.hi], dtype=np.float64)
+        out = np.zeros(8)
+        lib().orc_pid_run(_dp(par), _dp(self.st), float(input), int(sat_ext), float(Dt), int(n), _dp(out))
+        return dict(y_p=out[0], y_i=out[1], y_d=out[2], out_free=out[3], output=out[4], sat_out=int(out[5]), int_halted=bool(out[6]), u_i=out[7])
+
+
+class DiscreteIntegrator:
+    """IntegratorDiscrete (control.jl:123-185) in isolation."""
+
+    def __init__(self, lo=-np.inf, hi=np.inf):
+        self.lo, self.hi = lo, hi
+        self.st = np.zeros(2)
+
+    def init(self):
+        self.st[:] = 0.0
+
+    def run(self, input, sat_ext, Dt, n):
+        out = np.zeros(4)
+        lib().orc_integ_run(float(self.lo), float(self.hi), _dp(self.st), float(input), int(sat_ext), float(Dt), int(n), _dp(out))
+        return dict(x1=out[0], output=out[1], sat_out=int(out[2]), halted=bool(out[3]), x0=self.st[0])
 
 
 def attitude_test():

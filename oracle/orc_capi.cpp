@@ -520,6 +520,25 @@ void orc_lss_step(int nx, int nu, const double* A, const double* B, const double
     }
 }
 
+// Discrete compensators in isolation (control.jl:123-185 Integrator, :370-471 PID), for the known answers of the reference's
+// test_control.jl:88-146, 254-372: n periodic updates with the given input / external saturation.
+// par = {k_p, k_i, k_d, tau_f, lo, hi}; st (in/out) = {x_i0, x_d0, sat_out_0}; out = {y_p, y_i, y_d, out_free, output, sat_out, int_halted, u_i}
+void orc_pid_run(const double* par, double* st, double input, int sat_ext, double Dt, long long n, double* out) {
+    PIDc c; c.k_p = par[0]; c.k_i = par[1]; c.k_d = par[2]; c.tau_f = par[3]; c.lo = par[4]; c.hi = par[5];
+    c.x_i0 = st[0]; c.x_d0 = st[1]; c.sat_out_0 = (int)st[2]; c.input = input; c.sat_ext = sat_ext;
+    for (long long k = 0; k < n; k++) c.periodic(Dt);
+    st[0] = val(c.x_i0); st[1] = val(c.x_d0); st[2] = c.sat_out_0;
+    out[0] = val(c.y_p); out[1] = val(c.y_i); out[2] = val(c.y_d); out[3] = val(c.out_free); out[4] = val(c.output); out[5] = c.sat_out;
+    out[6] = c.int_halted; out[7] = val(c.u_i_y);
+}
+// lo, hi; st (in/out) = {x0, sat_out_0}; out = {x1, output, sat_out, halted}
+void orc_integ_run(double lo, double hi, double* st, double input, int sat_ext, double Dt, long long n, double* out) {
+    Integ c; c.lo = lo; c.hi = hi; c.x0 = st[0]; c.sat_out_0 = (int)st[1]; c.input = input; c.sat_ext = sat_ext;
+    for (long long k = 0; k < n; k++) c.periodic(Dt);
+    st[0] = val(c.x0); st[1] = c.sat_out_0;
+    out[0] = val(c.x1_y); out[1] = val(c.output); out[2] = c.sat_out_y; out[3] = c.halted_y;
+}
+
 // Rotation algebra known answers (lib/FlightPhysics/test/test_attitude.jl:29-82 RQuat, :182-240 REuler), evaluated with the
 // primitives every right-hand side uses (orc_math.hpp = attitude.jl:98-103,118,304-308,382-395; quaternions.jl:109-115).
 // out[0..2]   q_ab * (q_bc * x_c) - (q_ab o q_bc) * x_c          (:66)

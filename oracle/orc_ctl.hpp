@@ -43,6 +43,7 @@ struct PIDc {   // control.jl:370-471
     real input = 0.0; int sat_ext = 0;
     real x_i0 = 0.0, x_d0 = 0.0; int sat_out_0 = 0;
     real output = 0.0; int sat_out = 0;
+    real y_p = 0.0, y_i = 0.0, y_d = 0.0, out_free = 0.0, u_i_y = 0.0; bool int_halted = false;   // the rest of PIDDiscreteY (control.jl:392-407)
     void assign(const real* g) { k_p = g[0]; k_i = g[1]; k_d = g[2]; tau_f = g[3]; }
     void periodic(double Dt) {
         real alpha = 1.0 / (tau_f + Dt);
@@ -50,8 +51,9 @@ struct PIDc {   // control.jl:370-471
         bool halted = (isign(u_i * (double)sat_out_0) > 0) || (isign(u_i * (double)sat_ext) > 0);
         real x_i = x_i0 + Dt * k_i * u_i * (halted ? 0.0 : 1.0);
         real x_d = alpha * tau_f * x_d0 + Dt * alpha * k_d * u_d;
-        real y_p = k_p * u_p, y_i = x_i, y_d = alpha * (-x_d0 + k_d * u_d);
-        real out_free = y_p + y_i + y_d;
+        y_p = k_p * u_p; y_i = x_i; y_d = alpha * (-x_d0 + k_d * u_d);
+        out_free = y_p + y_i + y_d;
+        u_i_y = u_i; int_halted = halted;
         sat_out = (out_free >= hi) - (out_free <= lo);
         output = rclamp(out_free, lo, hi);
         x_i0 = x_i; x_d0 = x_d; sat_out_0 = sat_out;
@@ -64,11 +66,13 @@ struct Integ {   // control.jl:123-185
     real input = 0.0; int sat_ext = 0;
     real x0 = 0.0; int sat_out_0 = 0;
     real output = 0.0;
+    real x1_y = 0.0; int sat_out_y = 0; bool halted_y = false;   // the rest of IntegratorDiscreteY (control.jl:140-147)
     void periodic(double Dt) {
         bool halted = (isign(input * (double)sat_out_0) > 0) || (isign(input * (double)sat_ext) > 0);
         real x1 = x0 + Dt * input * (halted ? 0.0 : 1.0);
         output = rclamp(x1, lo, hi);
         int sat_out = (x1 >= hi) - (x1 <= lo);
+        x1_y = x1; sat_out_y = sat_out; halted_y = halted;
         x0 = x1; sat_out_0 = sat_out;
     }
     void init(double Dt, real x_init = 0.0) { input = 0.0; sat_ext = 0; x0 = x_init; sat_out_0 = 0; periodic(Dt); }

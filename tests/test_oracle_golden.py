@@ -222,3 +222,64 @@ def test_rotation_algebra_known_answers(orc):
     assert np.abs(o[25:28]).max() < 1e-13
     assert o[28] < 1e-9                                                         # the reference's isapprox on the lattice
     assert np.abs(o[29:33]).max() == 0.0                                        # RQuat(REuler()) = (1, 0, 0, 0)
+
+
+# ---- discrete compensators: lib/FlightPhysics/test/test_control.jl:88-146 (Integrator), :254-372 (PID) ------------------------
+def test_discrete_integrator_reference_sequence(orc):
+    """test_control.jl:88-146 transcribed: bounds (-1, 2), Dt = 0.01; 2 s of input -1 saturate low and halt; input +1 releases,
+    2 s later saturates high and halts; reversing releases; an external saturation of the input's sign halts, of the other
+    sign does not; f_init! zeroes the state."""
+    m = orc.DiscreteIntegrator(lo=-1.0, hi=2.0)
+    y = m.run(-1.0, 0, 0.01, 200)
+    assert y["x0"] <= -1 and abs(y["output"] + 1.0) < 1e-12 and y["sat_out"] == -1 and y["halted"]
+    y = m.run(1.0, 0, 0.01, 200)
+    assert y["sat_out"] == 0 and not y["halted"]
+    y = m.run(1.0, 0, 0.01, 200)
+    assert y["sat_out"] == 1 and y["halted"]
+    y = m.run(-1.0, 0, 0.01, 100)
+    assert y["sat_out"] == 0 and not y["halted"]
+    y = m.run(-1.0, +1, 0.01, 100)        # sat_ext = -sign(input)
+    assert not y["halted"]
+    y = m.run(-1.0, -1, 0.01, 100)        # sat_ext = sign(input)
+    assert y["halted"]
+    m.init()
+    y = m.run(0.0, 0, 0.01, 1)
+    assert y["x1"] == 0 and y["output"] == 0 and y["sat_out"] == 0 and not y["halted"]
+
+
+def test_discrete_pid_reference_sequence(orc):
+    """test_control.jl:254-372 transcribed: k_p = k_i = 1, k_d = 0.1, Dt = 0.01, unit input for 1 s -> y_p = 1, y_i ~ 1, output ~ 2;
+    with bounds (-1, 1) it saturates and the integrator halts; reversing saturates low; a small input releases; external
+    saturation halts only with the integrator input's sign; as a filtered derivative (k_d = 1, tau_f = 0.2) the output
+    decays to zero within 5 s; and the discretisation follows the continuous PID k_p + k_i / s + k_d s / (tau_f s + 1),
+    whose unit-step response k_p + k_i t + (k_d / tau_f) exp(-t / tau_f) the reference simulates as a LinearizedSS, to 1e-3
+    at t = 2 with Dt = 1e-4."""
+    m = orc.DiscretePID(k_p=1.0, k_i=1.0, k_d=0.1)
+    y = m.run(1.0, 0, 0.01, 100)
+    assert y["y_p"] == 1.0 and abs(y["y_i"] - 1.0) < 1e-9 and abs(y["out_free"] - 2.0) < 1e-6 and abs(y["output"] - 2.0) < 1e-6
+    assert y["sat_out"] == 0 and not y["int_halted"]
+    m.lo, m.hi = -1.0, 1.0
+    y = m.run(1.0, 0, 0.01, 100)
+    assert y["out_free"] > 2.0 and abs(y["output"] - 1.0) < 1e-12 and y["sat_out"] == 1 and y["int_halted"]
+    y = m.run(-1.0, 0, 0.01, 200)
+    assert y["sat_out"] == -1 and y["int_halted"]
+    y = m.run(0.1, 0, 0.01, 100)
+    assert y["sat_out"] == 0 and not y["int_halted"]
+    y = m.run(0.1, -int(np.sign(y["u_i"])), 0.01, 1)
+    assert not y["int_halted"]
+    y = m.run(0.1, int(np.sign(y["u_i"])), 0.01, 1)
+    assert y["int_halted"]
+    m.init()
+    y = m.run(0.0, 0, 0.01, 1)
+    assert y["y_i"] == 0 and y["y_d"] == 0 and y["y_p"] == 0 and not y["int_halted"]
+    # filtered derivative
+    d = orc.DiscretePID(k_p=0.0, k_i=0.0, k_d=1.0, tau_f=0.2)
+    y = d.run(1.0, 0, 0.01, 1)
+    assert y["y_d"] > 0.0
+    y = d.run(1.0, 0, 0.01, 500)
+    assert abs(y["y_d"]) < 1e-6
+    # numerical correctness of the discretisation against the continuous transfer function
+    k_p, k_i, k_d, tau_f = 1.0, 1.0, 0.2, 0.1
+    c = orc.DiscretePID(k_p=k_p, k_i=k_i, k_d=k_d, tau_f=tau_f)
+    y = c.run(1.0, 0, 1e-4, 20000)
+    assert abs(y["output"] - (k_p + k_i * 2.0 + k_d / tau_f * np.exp(-2.0 / tau_f))) < 1e-3
