@@ -91,6 +91,7 @@ def _load(name):
         "orc_geo_roundtrip": (None, [dbl, dbl, dbl, dp]),
         "orc_lss_step": (None, [i32, i32, dp, dp, dp, dp, dp, dp, dp, dbl, i64]),
         "orc_attitude_test": (None, [dp]),
+        "orc_pi_run": (None, [dp, dp, dbl, i32, dbl, i64, dp]),
         "orc_pid_run": (None, [dp, dp, dbl, i32, dbl, i64, dp]),
         "orc_integ_run": (None, [dbl, dbl, dp, dbl, i32, dbl, i64, dp]),
         "orc_lss_rhs": (None, [i32, i32, i32, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp]),
@@ -335,6 +336,13 @@ def gain_lookup(which, EAS, h):
     out = np.zeros(64)
     n = lib().orc_gain_lookup(int(which), float(EAS), float(h), _dp(out))
     return out[:n]
+
+
+def pi_run(k_p, k_i, k_l, lo, hi, x, input, sat_ext, dt, n):
+    """One lane of PIContinuous (control.jl:52-81) under RK4: returns (x_new, PIContinuousY of the lane as a dict)"""
+    par = np.array([k_p, k_i, k_l, lo, hi], dtype=np.float64); xs = np.array([x], dtype=np.float64); out = np.zeros(6)
+    lib().orc_pi_run(_dp(par), _dp(xs), float(input), int(sat_ext), float(dt), int(n), _dp(out))
+    return float(xs[0]), dict(output=out[0], out_free=out[1], sat_out=int(out[2]), int_halted=bool(out[3]), y_i=out[4], u_i=out[5])
 
 
 class DiscretePID:

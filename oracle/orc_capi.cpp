@@ -539,6 +539,21 @@ void orc_integ_run(double lo, double hi, double* st, double input, int sat_ext, 
     out[0] = val(c.x1_y); out[1] = val(c.output); out[2] = c.sat_out_y; out[3] = c.halted_y;
 }
 
+// One lane of the continuous PI compensator with anti-windup (control.jl:52-81: the landing gear's friction regulators, the
+// engine's idle and friction compensators) under the fixed-step RK4, for the reference's test_control.jl:36-84.
+// par = {k_p, k_i, k_l, lo, hi}; x (in/out) = the integrator state; out = {output, out_free, sat_out, int_halted, y_i, u_i}
+void orc_pi_run(const double* par, double* x, double input, int sat_ext, double dt, long long n, double* out) {
+    real xi = *x, xd, o, of; int so; bool h;
+    auto f = [&](real xv) { pi_lane(input, sat_ext, xv, par[0], par[1], par[2], par[3], par[4], xd, o, of, so, h); return xd; };
+    for (long long k = 0; k < n; k++) {
+        real k1 = f(xi), k2 = f(xi + (dt / 2) * k1), k3 = f(xi + (dt / 2) * k2), k4 = f(xi + dt * k3);
+        xi = xi + (dt / 6) * (2.0 * (k2 + k3) + (k1 + k4));
+    }
+    f(xi);   // y of the f_ode! at the final state
+    *x = val(xi);
+    out[0] = val(o); out[1] = val(of); out[2] = so; out[3] = h; out[4] = val(xi); out[5] = input;
+}
+
 // Rotation algebra known answers (lib/FlightPhysics/test/test_attitude.jl:29-82 RQuat, :182-240 REuler), evaluated with the
 // primitives every right-hand side uses (orc_math.hpp = attitude.jl:98-103,118,304-308,382-395; quaternions.jl:109-115).
 // out[0..2]   q_ab * (q_bc * x_c) - (q_ab o q_bc) * x_c          (:66)

@@ -283,3 +283,19 @@ def test_discrete_pid_reference_sequence(orc):
     c = orc.DiscretePID(k_p=k_p, k_i=k_i, k_d=k_d, tau_f=tau_f)
     y = c.run(1.0, 0, 1e-4, 20000)
     assert abs(y["output"] - (k_p + k_i * 2.0 + k_d / tau_f * np.exp(-2.0 / tau_f))) < 1e-3
+
+
+# ---- continuous PI with anti-windup: lib/FlightPhysics/test/test_control.jl:36-84 --------------------------------------------------
+def test_continuous_pi_reference_sequence(orc):
+    """test_control.jl:36-84 transcribed for the two lanes of PIContinuous{2} (k_p = k_i = 1, default dt = 0.02): lane 1 bounded to
+    (-1, 1) saturates at once and its integrator halts (|y_i| < 0.1, output -1); lane 2 unbounded integrates to y_i = -2,
+    output = -3 after 2 s; an external saturation halts lane 2 only when it has the sign of the integrator's input."""
+    inf = float("inf")
+    x1, y1 = orc.pi_run(1.0, 1.0, 0.0, -1.0, 1.0, 0.0, -1.0, 0, 0.02, 100)
+    assert y1["sat_out"] == -1 and y1["int_halted"] and abs(y1["y_i"]) < 0.1 and abs(y1["output"] + 1.0) < 1e-12
+    x2, y2 = orc.pi_run(1.0, 1.0, 0.0, -inf, inf, 0.0, -1.0, 0, 0.02, 100)
+    assert y2["sat_out"] == 0 and not y2["int_halted"] and abs(y2["y_i"] + 2.0) < 1e-2 and abs(y2["output"] + 3.0) < 1e-2
+    x2, y2 = orc.pi_run(1.0, 1.0, 0.0, -inf, inf, x2, -1.0, -int(np.sign(y2["u_i"])), 0.02, 50)
+    assert not y2["int_halted"]
+    x2b, y2 = orc.pi_run(1.0, 1.0, 0.0, -inf, inf, x2, -1.0, int(np.sign(y2["u_i"])), 0.02, 50)
+    assert y2["int_halted"] and x2b == x2 and x2 != 0
