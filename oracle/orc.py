@@ -91,6 +91,7 @@ def _load(name):
         "orc_geo_roundtrip": (None, [dbl, dbl, dbl, dp]),
         "orc_lss_step": (None, [i32, i32, dp, dp, dp, dp, dp, dp, dp, dbl, i64]),
         "orc_attitude_test": (None, [dp]),
+        "orc_geodesy_test": (None, [dp]),
         "orc_pi_run": (None, [dp, dp, dbl, i32, dbl, i64, dp]),
         "orc_pid_run": (None, [dp, dp, dbl, i32, dbl, i64, dp]),
         "orc_integ_run": (None, [dbl, dbl, dp, dbl, i32, dbl, i64, dp]),
@@ -336,6 +337,13 @@ def gain_lookup(which, EAS, h):
     out = np.zeros(64)
     n = lib().orc_gain_lookup(int(which), float(EAS), float(h), _dp(out))
     return out[:n]
+
+
+def geodesy_test():
+    """Known answers of test_geodesy.jl (layout: orc_capi.cpp:orc_geodesy_test)"""
+    out = np.zeros(8)
+    lib().orc_geodesy_test(_dp(out))
+    return out
 
 
 def pi_run(k_p, k_i, k_l, lo, hi, x, input, sat_ext, dt, n):

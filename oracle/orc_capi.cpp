@@ -554,6 +554,42 @@ void orc_pi_run(const double* par, double* x, double input, int sat_ext, double 
     out[0] = val(o); out[1] = val(of); out[2] = so; out[3] = h; out[4] = val(xi); out[5] = input;
 }
 
+// Wander-azimuth geodesy known answers (lib/FlightPhysics/test/test_geodesy.jl:20-62 NVector, :64-94 LatLon, :96-112 Altitude),
+// with the functions the WA / ECEF kinematics and the terrain lookup use (orc_geo_atm.hpp):
+// out[0]     get_psi_nw(ltf(n_e))                                   (:45, = 0),  n_e = normalize(1, 2, 3)
+// out[1]     get_psi_nw(ltf(n_e) o Rz(pi/3)) - pi/3                 (:50)
+// out[2..4]  NVector(ltf(n_e) o Rz(pi/3)) - n_e                     (:55)
+// out[5]     worst |LatLon - LatLon(NVector(ltf(NVector(LatLon)) o Rz(psi_nw)))| over the 10 x 10 x 10 lattice of :84-92
+//            (longitude compared modulo 2 pi; at the poles every longitude is the same point)
+// out[6]     Orthometric(Ellipsoidal(h_orth, loc), loc) - h_orth, h_orth = 1500, loc = NVector(3, 1, -5)   (:108, == 0)
+// out[7]     norm(n_e) - 1                                           (:26)
+void orc_geodesy_test(double* out) {
+    V3 n_e = normalize(V3(1.0, 2.0, 3.0));
+    Q4 r_en = ltf(n_e, 0.0);
+    out[0] = val(get_psi_nw(r_en));
+    Q4 r_ew = qmul(r_en, Rz(ORC_PI / 3));
+    out[1] = val(get_psi_nw(r_ew)) - ORC_PI / 3;
+    V3 d = n_from_q(r_ew) - n_e;
+    out[2] = val(d.x); out[3] = val(d.y); out[4] = val(d.z);
+    double worst = 0.0;
+    for (int i = 0; i < 10; i++) for (int j = 0; j < 10; j++) for (int k = 0; k < 10; k++) {
+        LatLon ll; ll.lat = -ORC_PI / 2 + ORC_PI * i / 9.0; ll.lon = -ORC_PI + 2 * ORC_PI * j / 9.0;
+        const double psi = -ORC_PI + 2 * ORC_PI * k / 9.0;
+        LatLon t = latlon_from_n(n_from_q(qmul(ltf(n_from_latlon(ll), 0.0), Rz(psi))));
+        double dlat = std::fabs(val(t.lat) - val(ll.lat));
+        double dlon = std::fabs(val(t.lon) - val(ll.lon)); dlon = std::fmin(dlon, std::fabs(dlon - 2 * ORC_PI));
+        if (i == 0 || i == 9) dlon = 0.0;
+        worst = std::fmax(worst, std::fmax(dlat, dlon));
+    }
+    out[5] = worst;
+    V3 loc = normalize(V3(3.0, 1.0, -5.0));
+    Geoid g; g.data = g_geoid_data.data();
+    real h_orth = 1500.0;
+    real h_ell = h_orth + g.height(loc);          // Altitude{Ellipsoidal}(h_orth, loc), geodesy.jl:238-240
+    out[6] = val((h_ell - g.height(loc)) - h_orth);
+    out[7] = val(norm(n_e)) - 1.0;
+}
+
 // Rotation algebra known answers (lib/FlightPhysics/test/test_attitude.jl:29-82 RQuat, :182-240 REuler), evaluated with the
 // primitives every right-hand side uses (orc_math.hpp = attitude.jl:98-103,118,304-308,382-395; quaternions.jl:109-115).
 // out[0..2]   q_ab * (q_bc * x_c) - (q_ab o q_bc) * x_c          (:66)

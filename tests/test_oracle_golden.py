@@ -299,3 +299,15 @@ def test_continuous_pi_reference_sequence(orc):
     assert not y2["int_halted"]
     x2b, y2 = orc.pi_run(1.0, 1.0, 0.0, -inf, inf, x2, -1.0, int(np.sign(y2["u_i"])), 0.02, 50)
     assert y2["int_halted"] and x2b == x2 and x2 != 0
+
+
+# ---- wander-azimuth geodesy: lib/FlightPhysics/test/test_geodesy.jl:20-112 ---------------------------------------------------------
+def test_wander_azimuth_geodesy_known_answers(orc):
+    """The local-tangent-frame rotation of an n-vector has zero wander angle (:45); composing it with Rz(psi_nw) gives back psi_nw
+    (:50) and the same n-vector (:55); LatLon -> NVector -> ltf -> o Rz(psi) -> NVector -> LatLon is the identity over the
+    reference's 1,000-point torture lattice including the poles and the date line (:84-92); orthometric -> ellipsoidal ->
+    orthometric altitude is exact (:108)."""
+    o = orc.geodesy_test()
+    assert abs(o[0]) < 1e-15 and abs(o[1]) < 1e-15 and np.abs(o[2:5]).max() < 1e-15
+    assert o[5] < 1e-9
+    assert o[6] == 0.0 and abs(o[7]) < 1e-15
