@@ -91,6 +91,7 @@ def _load(name):
         "orc_geo_roundtrip": (None, [dbl, dbl, dbl, dp]),
         "orc_lss_step": (None, [i32, i32, dp, dp, dp, dp, dp, dp, dp, dbl, i64]),
         "orc_attitude_test": (None, [dp]),
+        "orc_theta_constraint_test": (dbl, []),
         "orc_geodesy_test": (None, [dp]),
         "orc_pi_run": (None, [dp, dp, dbl, i32, dbl, i64, dp]),
         "orc_pid_run": (None, [dp, dp, dbl, i32, dbl, i64, dp]),
@@ -337,6 +338,11 @@ def gain_lookup(which, EAS, h):
     out = np.zeros(64)
     n = lib().orc_gain_lookup(int(which), float(EAS), float(h), _dp(out))
     return out[:n]
+
+
+def theta_constraint_test():
+    """test_aircraft_base.jl:16-40: flight-path angle recovered from the theta the trim constraint returns, minus the one asked for"""
+    return float(lib().orc_theta_constraint_test())
 
 
 def geodesy_test():

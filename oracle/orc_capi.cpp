@@ -590,6 +590,16 @@ void orc_geodesy_test(double* out) {
     out[7] = val(norm(n_e)) - 1.0;
 }
 
+// theta constraint of the trim (aircraftbase.jl:110-118) on the reference's test values (test_aircraft_base.jl:16-40): alpha_a 0.15,
+// beta_a -0.11, TAS 100, gamma_wb_n -0.07, psi_nb 0.3, phi_nb 0.7 -> theta_nb; returns inclination(REuler(psi, theta, phi)(v_wb_b)) - gamma
+double orc_theta_constraint_test() {
+    const double al = 0.15, be = -0.11, TAS = 100.0, gam = -0.07, psi = 0.3, phi = 0.7;
+    V3 v_wb_b = TAS * V3(std::cos(al) * std::cos(be), std::sin(be), std::sin(al) * std::cos(be));    // get_velocity_vector, atmosphere.jl:323-326
+    real th = theta_constraint(v_wb_b, gam, phi);
+    V3 v_wb_n = qrot(q_from_euler(Euler(psi, th, phi)), v_wb_b);
+    return val(inclination(v_wb_n)) - gam;
+}
+
 // Rotation algebra known answers (lib/FlightPhysics/test/test_attitude.jl:29-82 RQuat, :182-240 REuler), evaluated with the
 // primitives every right-hand side uses (orc_math.hpp = attitude.jl:98-103,118,304-308,382-395; quaternions.jl:109-115).
 // out[0..2]   q_ab * (q_bc * x_c) - (q_ab o q_bc) * x_c          (:66)

@@ -311,3 +311,24 @@ def test_wander_azimuth_geodesy_known_answers(orc):
     assert abs(o[0]) < 1e-15 and abs(o[1]) < 1e-15 and np.abs(o[2:5]).max() < 1e-15
     assert o[5] < 1e-9
     assert o[6] == 0.0 and abs(o[7]) < 1e-15
+
+
+# ---- trim constraint and model-level tests: test_aircraft_base.jl:16-40, test_c172s.jl:20-68, test_c172x.jl:18-67 -------------------
+def test_theta_constraint_recovers_the_flight_path_angle(orc):
+    """test_aircraft_base.jl:16-40: theta_nb from theta_constraint(v_wb_b, gamma_wb_n, phi_nb) must give back gamma_wb_n when the
+    aerodynamic velocity is rotated to NED by REuler(psi_nb, theta_nb, phi_nb) (the reference's isapprox)."""
+    assert abs(orc.theta_constraint_test()) < 1e-12
+
+
+def test_default_trim_succeeds_and_ground_init_loads_the_struts(orc, fb):
+    """test_c172s.jl / test_c172x.jl: `f_init!(vehicle, C172.TrimParameters())` reports success for the mechanical and the
+    fly-by-wire vehicle (:36-38 / :33-34), and `KinInit(h = elevation + 1.8) |> C172.Init` puts the aircraft on its wheels
+    (`ldg.left.strut.wow == true`, :58-68 / :57-67: the reference uses this state for full landing-gear code coverage)."""
+    import bench
+    for variant in (0, 1):
+        s = orc.Sim(variant=variant, kin=0, dt=0.01)
+        ok, ts, cost = s.init_trim()
+        assert ok and cost <= 1e-16
+        g = orc.Sim(variant=variant, kin=0, dt=0.01)
+        g.init(h_e=float(bench.geoid_height(0.0, 0.0)) + 1.8)          # HorizontalTerrain: elevation 0 (orthometric) at NVector()
+        assert g.y(fb.Y["FB_Y_WOW_LEFT"]) == 1.0 and g.y(fb.Y["FB_Y_WOW_RIGHT"]) == 1.0 and g.status == 0
