@@ -91,6 +91,7 @@ def _load(name):
         "orc_geo_roundtrip": (None, [dbl, dbl, dbl, dp]),
         "orc_lss_step": (None, [i32, i32, dp, dp, dp, dp, dp, dp, dp, dbl, i64]),
         "orc_attitude_test": (None, [dp]),
+        "orc_quat_test": (None, [dp]),
         "orc_theta_constraint_test": (dbl, []),
         "orc_geodesy_test": (None, [dp]),
         "orc_pi_run": (None, [dp, dp, dbl, i32, dbl, i64, dp]),
@@ -338,6 +339,13 @@ def gain_lookup(which, EAS, h):
     out = np.zeros(64)
     n = lib().orc_gain_lookup(int(which), float(EAS), float(h), _dp(out))
     return out[:n]
+
+
+def quat_test():
+    """Hamilton-product identities of test_quaternions.jl (layout: orc_capi.cpp:orc_quat_test)"""
+    out = np.zeros(7)
+    lib().orc_quat_test(_dp(out))
+    return out
 
 
 def theta_constraint_test():

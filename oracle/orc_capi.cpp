@@ -600,6 +600,24 @@ double orc_theta_constraint_test() {
     return val(inclination(v_wb_n)) - gam;
 }
 
+// Hamilton-product identities of lib/FlightPhysics/test/test_quaternions.jl:60-105 with the oracle's product (quaternions.jl:109-115):
+// out[0] |(q1 q2) q3 - q1 (q2 q3)| (:94), out[1] |(q1 + q2) q3 - (q1 q3 + q2 q3)| (:95), out[2] |q1 inv(q1) - 1| (:96),
+// out[3] |q1 1 - q1| (:93), out[4] |norm(normalize(q1)) - 1| (:39), out[5] |conj(q1).imag + q1.imag| (:79), out[6] |q1 \ q2 - q2 / q1| (:99, must NOT vanish)
+void orc_quat_test(double* out) {
+    Q4 q1(1.0, 2.0, 3.0, 4.0), q2(-0.5, 0.7, 2.0, -1.5), q3(0.3, -4.0, 1.0, 2.5);
+    auto add = [](Q4 a, Q4 b) { return Q4(a.w + b.w, a.x + b.x, a.y + b.y, a.z + b.z); };
+    auto sub = [](Q4 a, Q4 b) { return Q4(a.w - b.w, a.x - b.x, a.y - b.y, a.z - b.z); };
+    auto inv = [](Q4 a) { real n2 = a.w * a.w + a.x * a.x + a.y * a.y + a.z * a.z; Q4 c = qconj(a); return Q4(c.w / n2, c.x / n2, c.y / n2, c.z / n2); };
+    out[0] = val(qnorm(sub(qmul(qmul(q1, q2), q3), qmul(q1, qmul(q2, q3)))));
+    out[1] = val(qnorm(sub(qmul(add(q1, q2), q3), add(qmul(q1, q3), qmul(q2, q3)))));
+    out[2] = val(qnorm(sub(qmul(q1, inv(q1)), Q4(1.0, 0.0, 0.0, 0.0))));
+    out[3] = val(qnorm(sub(qmul(q1, Q4(1.0, 0.0, 0.0, 0.0)), q1)));
+    out[4] = std::fabs(val(qnorm(qnormalize(q1))) - 1.0);
+    Q4 c = qconj(q1);
+    out[5] = std::fabs(val(c.x + q1.x)) + std::fabs(val(c.y + q1.y)) + std::fabs(val(c.z + q1.z)) + std::fabs(val(c.w - q1.w));
+    out[6] = val(qnorm(sub(qmul(inv(q1), q2), qmul(q2, inv(q1)))));
+}
+
 // Rotation algebra known answers (lib/FlightPhysics/test/test_attitude.jl:29-82 RQuat, :182-240 REuler), evaluated with the
 // primitives every right-hand side uses (orc_math.hpp = attitude.jl:98-103,118,304-308,382-395; quaternions.jl:109-115).
 // out[0..2]   q_ab * (q_bc * x_c) - (q_ab o q_bc) * x_c          (:66)

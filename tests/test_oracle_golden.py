@@ -332,3 +332,12 @@ def test_default_trim_succeeds_and_ground_init_loads_the_struts(orc, fb):
         g = orc.Sim(variant=variant, kin=0, dt=0.01)
         g.init(h_e=float(bench.geoid_height(0.0, 0.0)) + 1.8)          # HorizontalTerrain: elevation 0 (orthometric) at NVector()
         assert g.y(fb.Y["FB_Y_WOW_LEFT"]) == 1.0 and g.y(fb.Y["FB_Y_WOW_RIGHT"]) == 1.0 and g.status == 0
+
+
+# ---- quaternion algebra: lib/FlightPhysics/test/test_quaternions.jl:60-105 -----------------------------------------------------------
+def test_hamilton_product_identities(orc):
+    """Associativity (:94), distributivity (:95), inverse (:96), identity (:93), normalisation (:39), conjugation (:79), and the
+    non-commutativity the reference insists on (`q1 \\ q2 != q2 / q1`, :99)."""
+    o = orc.quat_test()
+    assert o[0] < 1e-12 and o[1] < 1e-12 and o[2] < 1e-15 and o[3] == 0.0 and o[4] < 1e-15 and o[5] == 0.0
+    assert o[6] > 0.1
