@@ -231,7 +231,10 @@ int32_t fb_schedule_inputs(fb_handle h, int64_t n_events, const int64_t* member,
                            const int32_t* field, const double* value);
 
 /* ---- stepping ---------------------------------------------------------------------------- */
-/* step!(sim, Δt, true) : sim.jl:386 — advance every running member by round(t_advance/dt) steps */
+/* step!(sim, Δt, true) : sim.jl:386 — advance every running member by round(t_advance/dt) steps. Asynchronous. Members near
+ * the terrain may be advanced by a pass that runs on a second, internal stream beside the next launch; every
+ * entry point other than fb_step / fb_run / fb_time / fb_nx first joins the two streams, so no caller ever sees an ensemble
+ * at two step indices. */
 int32_t fb_step(fb_handle h, double t_advance);
 /* run!(sim) headless : sim.jl:611-638 — step until t_end */
 int32_t fb_run(fb_handle h);
@@ -347,7 +350,9 @@ int32_t fb_counters(fb_handle h, int64_t* kernel_launches, int64_t* rhs_evals_pe
 int32_t fb_measure_fp64_peak(int32_t device, double* tflops);
 /* device pointers for zero-copy interop with torch / CUDA.jl (valid until fb_destroy) */
 int32_t fb_device_state(fb_handle h, void** d_x, int64_t* pitch_elems);
-/* launch stream handle (cudaStream_t) so that callers can time with events on the right stream */
+/* launch stream handle (cudaStream_t) so that callers can time with events on the right stream. To CONSUME the state on
+ * this stream after stepping (CUDA.jl / torch interop), call fb_device_state again first: it is the join that orders the
+ * internal hand-over stream in front of whatever the caller enqueues next. */
 int32_t fb_stream(fb_handle h, void** stream);
 
 #ifdef __cplusplus
