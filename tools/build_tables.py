@@ -306,15 +306,22 @@ def write_blob(tables, path):
 
 
 def main():
+    import argparse
+    ap = argparse.ArgumentParser(description="write flight.jl_b200/data/c172_tables.bin")
+    ap.add_argument("--pitch", nargs=3, metavar=("LOWER", "UPPER", "LENGTH"), default=("-0.1", "0.2", "11"),
+                    help="blade-pitch offset range of the VariablePitch propeller whose Lookup goes into prop.tables3 (rad, rad, knots); "
+                         "default: the reference's test case VariablePitch(-0.1, 0.2), length 11. fb_config.prop_pitch_* must match it.")
+    ap.add_argument("--out", default=OUT)
+    args = ap.parse_args()
     tables = {}
     tables.update(aero_tables())
     tables.update(engine_tables())
     tables.update(prop_tables())
-    tables.update(prop_tables3())
+    tables.update(prop_tables3(float(args.pitch[0]), float(args.pitch[1]), int(args.pitch[2])))
     tables.update(gain_tables())
     tables.update(geoid_table())
-    write_blob(tables, OUT)
-    print("wrote", OUT, os.path.getsize(OUT), "bytes;", len(tables), "sections")
+    write_blob(tables, args.out)
+    print("wrote", args.out, os.path.getsize(args.out), "bytes;", len(tables), "sections")
 
 
 if __name__ == "__main__":
